@@ -1,0 +1,170 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see c2o_ingest.hpp header).
+// Flat C API over the CPU restatement so tests/ and bench.py's cpu_baseline leg can drive it through ctypes.
+#include <chrono>
+
+#include "c2o_query.hpp"
+
+using namespace c2o;
+typedef std::shared_ptr<Scan> ScanPtr;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static void fill_head(const Scan &s, c2g_scan_head *h) {
+  std::memset(h, 0, sizeof(*h));
+  h->int_id = s.int_id;
+  int off = 0;
+  for (int l = 0; l < C2G_NLEV; ++l) {
+    h->n_views[l] = (int) s.cont_views[l].size();
+    h->view_off[l] = off;
+    off += h->n_views[l];
+    h->layer_cell_cnt[l] = s.layer_cell_cnt[l];
+    for (int q = 0; q < s.cfg.piv_firsts && q < C2G_MAX_PIV; ++q) {
+      for (int d = 0; d < C2G_KEY_DIM; ++d) h->keys[l][q][d] = s.layer_keys[l][q][d];
+      h->bcis[l][q] = s.layer_key_bcis[l][q];
+    }
+  }
+  if (off > C2G_VIEW_CAP) h->status |= 1;
+  h->n_occupied = (int) s.bev_pixfs.size();
+  GMMScanData g = buildGMMScan(s);
+  for (int li = 0; li < 4; ++li) h->n_ell[li] = (int) g.ell[li].size();
+  h->gmm_auto_corr = g.auto_corr;
+}
+
+extern "C" {
+
+void *c2o_scan_create(const c2g_cm_config *cfg, int int_id) { return new ScanPtr(std::make_shared<Scan>(*cfg, int_id)); }
+void c2o_scan_free(void *h) { delete (ScanPtr *) h; }
+void c2o_scan_make_bev(void *h, const float *pts, int n) { (*(ScanPtr *) h)->makeBEV(pts, n); }
+void c2o_scan_make_contours(void *h) { (*(ScanPtr *) h)->makeContoursRecurs(); }
+void c2o_scan_ingest(void *h, const float *pts, int n) {
+  (*(ScanPtr *) h)->makeBEV(pts, n);
+  (*(ScanPtr *) h)->makeContoursRecurs();
+}
+// dense images: bev (init -1000), row_f / col_f (-1 where no pillar)
+void c2o_scan_get_bev(void *h, float *bev, float *row_f, float *col_f) {
+  const Scan &s = **(ScanPtr *) h;
+  const size_t n = (size_t) s.cfg.n_row * s.cfg.n_col;
+  for (size_t i = 0; i < n; ++i) {
+    bev[i] = s.bev[i];
+    row_f[i] = -1.0f;
+    col_f[i] = -1.0f;
+  }
+  for (auto &p : s.bev_pixfs) {
+    row_f[p.first] = p.second.row_f;
+    col_f[p.first] = p.second.col_f;
+  }
+}
+int c2o_scan_n_views(void *h, int level) { return (int) (*(ScanPtr *) h)->cont_views[level].size(); }
+void c2o_scan_get_views(void *h, int level, int presort, c2g_view *out) {
+  const Scan &s = **(ScanPtr *) h;
+  const auto &v = presort ? s.presort_views[level] : s.cont_views[level];
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+}
+void c2o_scan_get_head(void *h, c2g_scan_head *out) { fill_head(**(ScanPtr *) h, out); }
+
+// ---- stand-alone helpers exposed for unit tests -----------------------------------------------------------------
+void c2o_eig2f(float a, float b, float c, float *evals, float *evecs) { selfAdjointEigen2f(a, b, c, evals, evecs); }
+// CCL on an arbitrary mask (h x w uint8) -> labels int32 + stats (n+1) x 5 (left, top, width, height, area); returns n
+int c2o_ccl8(const uint8_t *mask, int h, int w, int32_t *labels, int32_t *stats, int stats_cap) {
+  std::vector<int> lab;
+  std::vector<CCStat> st = connectedComponents8(mask, h, w, lab);
+  for (size_t i = 0; i < lab.size(); ++i) labels[i] = lab[i];
+  for (size_t i = 0; i < st.size() && (int) i < stats_cap; ++i) {
+    stats[i * 5 + 0] = st[i].left;
+    stats[i * 5 + 1] = st[i].top;
+    stats[i * 5 + 2] = st[i].width;
+    stats[i * 5 + 3] = st[i].height;
+    stats[i * 5 + 4] = st[i].area;
+  }
+  return (int) st.size() - 1;
+}
+float c2o_gauss_pdf_f(float x, float mean, float sd) { return gaussPDF<float>(x, mean, sd); }
+double c2o_exp(double x) { return std::exp(x); }
+float c2o_atan2f(float y, float x) { return std::atan2(y, x); }
+float c2o_acosf(float x) { return std::acos(x); }
+
+// ---- database ----------------------------------------------------------------------------------------------------
+void *c2o_db_create(const c2g_db_config *cfg) { return new ContourDB(*cfg); }
+void c2o_db_free(void *db) { delete (ContourDB *) db; }
+void c2o_db_add_scan(void *db, void *scan, double ts) { ((ContourDB *) db)->addScan(*(ScanPtr *) scan, ts); }
+void c2o_db_push_and_balance(void *db, int seed, double ts) { ((ContourDB *) db)->pushAndBalance(seed, ts); }
+int c2o_db_n_scans(void *db) { return (int) ((ContourDB *) db)->all_bevs_.size(); }
+
+// layer state for mirroring / parity: bucket_ranges[7], tree_sizes[6], buffer_sizes[6]
+void c2o_db_layer_state(void *db, int ll, float *bucket_ranges, int32_t *tree_sizes, int32_t *buffer_sizes) {
+  const LayerDB &l = ((ContourDB *) db)->layer_db_[ll];
+  for (int i = 0; i <= C2G_NUM_BUCKETS; ++i) bucket_ranges[i] = l.bucket_ranges_[i];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
+    tree_sizes[i] = (int) l.buckets_[i].data_tree.size();
+    buffer_sizes[i] = (int) l.buckets_[i].buffer.size();
+  }
+}
+// keys + (gidx, level, seq) of one bucket's tree, in tree order
+void c2o_db_bucket_tree(void *db, int ll, int bucket, float *keys, int32_t *gidx, int32_t *seq) {
+  const TreeBucket &b = ((ContourDB *) db)->layer_db_[ll].buckets_[bucket];
+  for (size_t i = 0; i < b.data_tree.size(); ++i) {
+    for (int d = 0; d < C2G_KEY_DIM; ++d) keys[i * C2G_KEY_DIM + d] = b.data_tree[i][d];
+    gidx[i] = (int32_t) b.gkidx_tree[i].gidx;
+    seq[i] = b.gkidx_tree[i].seq;
+  }
+}
+
+// query one scan; optionally returns the full hint trace (hints in reference order + cascade result per hint)
+int c2o_db_query(void *db, void *scan, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub, c2g_query_result *out,
+                 c2g_hint *hints, c2g_pair_score *scores, int cap) {
+  std::vector<HintTrace> trace;
+  ((ContourDB *) db)->queryRangedKNN(*(ScanPtr *) scan, *lb, *ub, *out, &trace);
+  int n = (int) trace.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (hints) hints[i] = trace[i].hint;
+    if (scores) scores[i] = trace[i].score;
+  }
+  return n;
+}
+
+// raw kNN of one key against one layer (for kNN parity tests): returns count
+int c2o_db_layer_knn(void *db, int ll, const float *key, int k, float max_dist_sq, int32_t *gidx, int32_t *seq, float *dist) {
+  Key q;
+  for (int d = 0; d < C2G_KEY_DIM; ++d) q[d] = key[d];
+  std::vector<std::pair<IndexOfKey, float>> res;
+  ((ContourDB *) db)->layer_db_[ll].layerKNNSearch(q, k, max_dist_sq, res);
+  for (size_t i = 0; i < res.size(); ++i) {
+    gidx[i] = (int32_t) res[i].first.gidx;
+    seq[i] = res[i].first.seq;
+    dist[i] = res[i].second;
+  }
+  return (int) res.size();
+}
+
+// ---- CPU baseline driver: for each of B scans {ingest; query; (optional) addScan + pushAndBalance}, single thread.
+// pts: concatenated scans, offsets[b]..offsets[b+1] in points. t_stage[5]: make bev / KNN search / Constell / L2 opt /
+// Update database (seconds, accumulated) — the reference's SequentialTimeProfiler stage names.
+void c2o_run_loop(void *db_, const c2g_cm_config *cfg, const float *pts, const int64_t *offsets, int B, int first_id,
+                  const double *ts, int do_query, int do_add, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+                  c2g_query_result *results, double *t_stage) {
+  ContourDB *db = (ContourDB *) db_;
+  for (int b = 0; b < B; ++b) {
+    double t0 = now_s();
+    ScanPtr s = std::make_shared<Scan>(*cfg, first_id + b);
+    s->makeBEV(pts + 4 * offsets[b], (int) (offsets[b + 1] - offsets[b]));
+    s->makeContoursRecurs();
+    std::vector<float>().swap(s->bev);  // clearImage() (test/batch_bin_test.cpp:169)
+    t_stage[0] += now_s() - t0;
+    if (do_query) {
+      c2g_query_result r;
+      db->queryRangedKNN(s, *lb, *ub, r, nullptr, &t_stage[1], &t_stage[2], &t_stage[3]);
+      if (results) results[b] = r;
+    }
+    if (do_add) {
+      double t1 = now_s();
+      db->addScan(s, ts[b]);
+      db->pushAndBalance(first_id + b, ts[b]);
+      t_stage[4] += now_s() - t1;
+    }
+  }
+}
+
+int c2o_sizeof_scan_head() { return (int) sizeof(c2g_scan_head); }
+int c2o_sizeof_query_result() { return (int) sizeof(c2g_query_result); }
+
+}  // extern "C"
