@@ -1,0 +1,263 @@
+// c2g_api.cu — context + the extern "C" entry points declared in include/c2g.h.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/c2g.h"
+#include "c2g_common.cuh"
+#include "c2g_ctx.cuh"
+#include "stdsort.cuh"
+
+// launchers implemented in the kernel translation units
+int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P,
+                           c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream);
+int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
+                        const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
+                        cudaStream_t stream);
+int c2g_query_alloc(c2g_ctx *ctx);
+void c2g_query_free(c2g_ctx *ctx);
+
+namespace {
+
+int make_params(const c2g_cm_config &cfg, C2gIngestParams &P) {
+  if (cfg.n_levels != C2G_NLEV) return C2G_ERR_ARG;
+  if (cfg.n_row <= 0 || cfg.n_col <= 0 || cfg.n_row * cfg.n_col > C2G_MAX_CELLS) return C2G_ERR_ARG;
+  if (cfg.n_row % 2 || cfg.n_col % 2) return C2G_ERR_ARG;  // CHECK in contour_mng.h:479-480
+  if (cfg.n_row > 255 || cfg.n_col > 255) return C2G_ERR_ARG;
+  if (cfg.piv_firsts < 0 || cfg.piv_firsts > C2G_MAX_PIV) return C2G_ERR_ARG;
+  if (cfg.dist_firsts < 0 || cfg.dist_firsts > C2G_MAX_DIST_FIRSTS) return C2G_ERR_ARG;
+  if (!(cfg.roi_radius > 0.0f) || cfg.roi_radius > 10.0f) return C2G_ERR_ARG;  // key window list capacity
+  P.cfg = cfg;
+  // ContourManager ctor (contour_mng.h:483-486) + hashPointToImage's padding (contour_mng.h:450), all in float
+  const float x_min = -(float) (cfg.n_row / 2) * cfg.reso_row, x_max = -x_min;
+  const float y_min = -(float) (cfg.n_col / 2) * cfg.reso_col, y_max = -y_min;
+  const float padding = 1e-2f;
+  P.x_min_pad = x_min + padding;
+  P.x_max_pad = x_max - padding;
+  P.y_min_pad = y_min + padding;
+  P.y_max_pad = y_max - padding;
+  P.half_row = cfg.n_row / 2;
+  P.half_col = cfg.n_col / 2;
+  P.half_row_f = (float) P.half_row;
+  P.half_col_f = (float) P.half_col;
+  P.n_cells = cfg.n_row * cfg.n_col;
+  return 0;
+}
+
+int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, const float **pts_dev) {
+  if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
+  const long long total = offsets_host[B] - offsets_host[0];
+  if (total < 0) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_offsets, offsets_host, sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (pts_on_device) {
+    if (((uintptr_t) pts) & 15) return C2G_ERR_ARG;
+    *pts_dev = pts;
+  } else {
+    if (offsets_host[B] > ctx->max_points) return C2G_ERR_CAPACITY;
+    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage, pts, sizeof(float) * 4 * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
+    *pts_dev = ctx->d_pts_stage;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int c2g_abi_version(void) { return 1; }
+
+int c2g_sizeof(int which) {
+  switch (which) {
+    case 0: return (int) sizeof(c2g_scan_head);
+    case 1: return (int) sizeof(c2g_view);
+    case 2: return (int) sizeof(c2g_bci);
+    case 3: return (int) sizeof(c2g_hint);
+    case 4: return (int) sizeof(c2g_pair_score);
+    case 5: return (int) sizeof(c2g_query_result);
+    case 6: return (int) sizeof(c2g_cm_config);
+    case 7: return (int) sizeof(c2g_db_config);
+    default: return -1;
+  }
+}
+
+int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int device, int scan_capacity, int max_batch,
+               long long max_points, c2g_ctx **out) {
+  if (!cm_cfg || !db_cfg || !out || scan_capacity <= 0 || max_batch <= 0 || max_points <= 0) return C2G_ERR_ARG;
+  if (db_cfg->n_q_levels <= 0 || db_cfg->n_q_levels > C2G_NUM_Q_LEVELS_MAX || db_cfg->nnk <= 0 || db_cfg->nnk > 64) return C2G_ERR_ARG;
+  for (int i = 0; i < db_cfg->n_q_levels; ++i)
+    if (db_cfg->q_levels[i] < 1 || db_cfg->q_levels[i] > 4) return C2G_ERR_ARG;  // pair bitmap covers levels 1..4
+  c2g_ctx *ctx = new (std::nothrow) c2g_ctx();
+  if (!ctx) return C2G_ERR_ARG;
+  memset(ctx, 0, sizeof(*ctx));
+  int rc = make_params(*cm_cfg, ctx->P);
+  if (rc) {
+    delete ctx;
+    return rc;
+  }
+  ctx->db = *db_cfg;
+  ctx->device = device;
+  ctx->scan_cap = scan_capacity;
+  ctx->max_batch = max_batch;
+  ctx->max_points = max_points;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return -(int) e;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return -(int) e;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  const size_t ncell = ctx->P.n_cells;
+#define ALLOC(ptr, bytes)                                        \
+  do {                                                           \
+    e = cudaMalloc((void **) &(ptr), (bytes));                   \
+    if (e != cudaSuccess) {                                      \
+      c2g_destroy(ctx);                                          \
+      return -(int) e;                                           \
+    }                                                            \
+  } while (0)
+  e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return -(int) e;
+  }
+  ctx->stream = ctx->own_stream;
+  ALLOC(ctx->d_pts_stage, sizeof(float) * 4 * (size_t) max_points);
+  ALLOC(ctx->d_offsets, sizeof(long long) * (max_batch + 1));
+  ALLOC(ctx->d_int_ids, sizeof(int) * max_batch);
+  ALLOC(ctx->d_tiles, sizeof(c2g_cellkey) * ncell * max_batch);
+  ALLOC(ctx->d_bev_h, sizeof(float) * ncell * max_batch);
+  ALLOC(ctx->d_bev_rf, sizeof(float) * ncell * max_batch);
+  ALLOC(ctx->d_bev_cf, sizeof(float) * ncell * max_batch);
+  ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) ctx->num_sms);
+  ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
+  ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
+#undef ALLOC
+  rc = c2g_query_alloc(ctx);
+  if (rc) {
+    c2g_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int c2g_destroy(c2g_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  c2g_query_free(ctx);
+  cudaFree(ctx->d_pts_stage);
+  cudaFree(ctx->d_offsets);
+  cudaFree(ctx->d_int_ids);
+  cudaFree(ctx->d_tiles);
+  cudaFree(ctx->d_bev_h);
+  cudaFree(ctx->d_bev_rf);
+  cudaFree(ctx->d_bev_cf);
+  cudaFree(ctx->d_presort);
+  cudaFree(ctx->d_heads);
+  cudaFree(ctx->d_views);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return 0;
+}
+
+int c2g_set_stream(c2g_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return C2G_ERR_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+  return 0;
+}
+
+int c2g_sync(c2g_ctx *ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device) {
+  const float *pts_dev = nullptr;
+  int rc = stage_inputs(ctx, pts, offsets_host, B, pts_on_device, &pts_dev);
+  if (rc) return rc;
+  rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, ctx->d_tiles, ctx->num_sms, ctx->stream);
+  if (rc) return rc;
+  ctx->launches += 1;
+  ctx->last_B = B;
+  ctx->last_pts = pts_dev;
+  return 0;
+}
+
+int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
+               const int *int_ids_host) {
+  if (!ctx || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+  int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
+  if (rc) return rc;
+  const int *ids_dev = nullptr;
+  if (int_ids_host) {
+    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids, int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
+    ids_dev = ctx->d_int_ids;
+  }
+  rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->num_sms, ctx->stream);
+  if (rc) return rc;
+  ctx->launches += 1;
+  return 0;
+}
+
+int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host) {
+  if (!ctx || !out_host || first_slot < 0 || n < 0 || first_slot + n > ctx->scan_cap) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_heads + first_slot, sizeof(c2g_scan_head) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host) {
+  if (!ctx || !out_host || slot < 0 || slot >= ctx->scan_cap) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_views + (size_t) slot * C2G_VIEW_CAP, sizeof(c2g_view) * C2G_VIEW_CAP, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f) {
+  if (!ctx || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
+  const size_t n = ctx->P.n_cells, off = n * batch_index;
+  if (bev) C2G_CUDA_TRY(cudaMemcpyAsync(bev, ctx->d_bev_h + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (row_f) C2G_CUDA_TRY(cudaMemcpyAsync(row_f, ctx->d_bev_rf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (col_f) C2G_CUDA_TRY(cudaMemcpyAsync(col_f, ctx->d_bev_cf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host) {
+  if (!ctx || !out_host || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
+  const size_t n = ctx->P.n_cells;
+  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_tiles + n * batch_index, sizeof(c2g_cellkey) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n) {
+  if (!ctx || n < 0 || src_first < 0 || dst_first < 0 || src_first + n > ctx->scan_cap || dst_first + n > ctx->scan_cap) return C2G_ERR_ARG;
+  if (n == 0 || src_first == dst_first) return 0;
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_heads + dst_first, ctx->d_heads + src_first, sizeof(c2g_scan_head) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_views + (size_t) dst_first * C2G_VIEW_CAP, ctx->d_views + (size_t) src_first * C2G_VIEW_CAP,
+                               sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+long long c2g_launch_count(c2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int c2g_selftest_stdsort(unsigned int *words, int n, int desc) {
+  if (!words || n < 0) return C2G_ERR_ARG;
+  if (desc)
+    c2g_sort::std_sort(words, (long) n, [](unsigned a, unsigned b) { return (a >> 16) > (b >> 16); });
+  else
+    c2g_sort::std_sort(words, (long) n, [](unsigned a, unsigned b) { return (a >> 16) < (b >> 16); });
+  return 0;
+}
+
+}  // extern "C"

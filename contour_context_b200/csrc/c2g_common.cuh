@@ -1,0 +1,58 @@
+// c2g_common.cuh — shared device/host definitions of the B200-native cont2contops hot path.
+// Compiled with -fmad=false: the reference is built without FMA contraction (CMakeLists.txt:4,10-11), so every float /
+// double multiply-add here must round twice exactly like the x86-64 SSE2 code of the reference.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/c2g_types.h"
+
+#define C2G_CUDA_TRY(expr)                       \
+  do {                                           \
+    cudaError_t e__ = (expr);                    \
+    if (e__ != cudaSuccess) return -(int) e__;   \
+  } while (0)
+
+// Scalar parameters every ingest kernel needs, precomputed on the host in float exactly like the ContourManager
+// constructor does (include/cont2/contour_mng.h:478-498).
+struct C2gIngestParams {
+  c2g_cm_config cfg;
+  float x_min_pad, x_max_pad, y_min_pad, y_max_pad;  // x_min_ + 0.01f etc. (contour_mng.h:450-452)
+  float half_row_f, half_col_f;                      // float(n_row / 2), float(n_col / 2)
+  int half_row, half_col;
+  int n_cells;
+};
+
+// Monotone map float -> uint32 (total order of finite floats and infinities; NaNs never reach it).
+__host__ __device__ __forceinline__ uint32_t c2g_orderable(float h) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(h);
+#else
+  union {
+    float f;
+    uint32_t u;
+  } cv;
+  cv.f = h;
+  uint32_t u = cv.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float c2g_from_orderable(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union {
+    float f;
+    uint32_t u;
+  } cv;
+  cv.u = u;
+  return cv.f;
+#endif
+}
+
+// BEV cell record produced by the scatter kernel: (orderable(height) << 32) | (0xFFFFFFFF - point_index); 0 = empty.
+// A max over these keys implements "highest point wins, the earliest point in file order wins ties"
+// (strict `<` in include/cont2/contour_mng.h:517).
+typedef unsigned long long c2g_cellkey;

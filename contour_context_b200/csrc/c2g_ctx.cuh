@@ -1,0 +1,39 @@
+// c2g_ctx.cuh — the context object behind the opaque c2g_ctx handle of include/c2g.h.
+#pragma once
+#include "c2g_common.cuh"
+
+struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
+  float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans
+  int *gidx;             // IndexOfKey::gidx
+  signed char *seq;      // IndexOfKey::seq
+  unsigned char *bucket; // which TreeBucket the key lives in
+  int n, cap;
+  float ranges[C2G_NUM_BUCKETS + 1];
+};
+
+struct c2g_ctx {
+  int device, num_sms;
+  C2gIngestParams P;
+  c2g_db_config db;
+  int scan_cap, max_batch;
+  long long max_points;
+  cudaStream_t own_stream, stream;
+  // ingest buffers
+  float *d_pts_stage;
+  long long *d_offsets;
+  int *d_int_ids;
+  c2g_cellkey *d_tiles;
+  float *d_bev_h, *d_bev_rf, *d_bev_cf;
+  c2g_view *d_presort;
+  c2g_scan_head *d_heads;
+  c2g_view *d_views;
+  const float *last_pts;
+  int last_B;
+  long long launches;
+  // query buffers
+  C2gLayerTable layers[C2G_NUM_Q_LEVELS_MAX];
+  c2g_hint *d_hints;
+  c2g_pair_score *d_scores;
+  c2g_query_result *d_results;
+  long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
+};

@@ -1,0 +1,757 @@
+// contours.cu — K2: BEV tile -> multi-level contours -> ContourView statistics -> per-level order -> retrieval keys ->
+// BCIs -> per-scan GMM terms.  One persistent CTA per SM, one scan per CTA iteration, everything between the BEV tile and
+// the finished descriptor stays in shared memory / L2.
+//
+// Reference functions restated here (paths relative to the reference repo):
+//   ContourManager::makeContourRecursiveHelper   src/cont2/contour_mng.cpp:274-353
+//   RunningStatRecorder::runningStatsF           include/cont2/contour.h:74-84
+//   ContourView::calcStatVals (+ salience tests) include/cont2/contour.h:142-265
+//   ContourManager::makeContoursRecurs           include/cont2/contour_mng.h:588-608 (sort), :693-830 (keys), :848-888 (BCI)
+//   GMMPair ctor (scan-only part)                include/cont2/correlation.h:49-82,102-119
+//
+// How the recursion becomes data-parallel: a level-(L+1) component is a connected component of {bev > lv[L+1]} and is
+// contained in exactly one level-L component, so a GLOBAL 8-connected labelling per level finds the same pixel sets as
+// the reference's recursive ROI-by-ROI labelling.  What the recursion adds is ORDER: cont_views_[L] is filled in DFS
+// order, children of one parent in OpenCV label order, which is the block-raster order of each component's first 2x2
+// block with blocks aligned to the parent's bounding-box origin (SURVEY.md §7 hard part 2).  Hence
+//   order(level L) = sort by (rank of parent in level L-1, min over pixels of ((r-y0)>>1, (c-x0)>>1)).
+// Per-pixel label words pack (rank of the enclosing level-(L-1) component) << 16 | union-find parent pixel, so one native
+// 32-bit shared atomicMin implements the union (all words of one tree share the upper half).
+//
+// Bit-exactness rules: float/double sums that feed views and keys are accumulated in the reference's raster order by a
+// single logical accumulator (warp-redundant), never by tree reductions; compiled with -fmad=false.
+#include <math_constants.h>
+
+#include "c2g_common.cuh"
+#include "stdsort.cuh"
+
+namespace {
+
+constexpr int K2_THREADS = 1024;
+constexpr int K2_WARPS = K2_THREADS / 32;
+constexpr int NC = 2048;        // components (any size) per level
+constexpr int NVL = 1024;       // significant components (area >= min_cont_cell_cnt) per level
+constexpr int KEY_LIST_CAP = 400;  // cells of one key window that can lie inside the 9.99-cell radius
+constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
+constexpr int N_DIVS = 35;
+
+struct TopView {  // what keys / BCI / GMM need from a sorted view
+  float mean0, mean1, eig0, eig1;
+  int cnt;
+};
+
+struct Smem {
+  uint32_t L[C2G_MAX_CELLS];      // label words; reused as scratch after the level loop
+  uint8_t msk[C2G_MAX_CELLS + 28];  // bit e: bev > lv_grads[e]
+  int c_area[NC], c_minr[NC], c_minc[NC], c_maxr[NC], c_maxc[NC], c_key[NC], c_poi[NC];
+  uint16_t c_rank[NC], c_pcid[NC];
+  uint16_t sig_slot[NVL], order[NVL];
+  uint32_t sig_key[NVL];
+  uint8_t px0[NVL], py0[NVL];          // bbox origin of the previous level's components, by rank
+  uint32_t sortbuf[C2G_VIEW_CAP];      // (cell_cnt << 16 | presort index), all levels back to back
+  int n_views[C2G_NLEV], view_off[C2G_NLEV], layer_cnt[C2G_NLEV];
+  TopView top[C2G_NLEV][C2G_MAX_DIST_FIRSTS];
+  float divs[N_ANCH][N_DIVS];
+  int cnt_point[N_ANCH];
+  int ncomp, nsig, status, n_occ;
+  double red[K2_WARPS];
+};
+
+__device__ __forceinline__ uint32_t uf_find(volatile uint32_t *L, uint32_t c) {
+  uint32_t p = L[c] & 0xFFFFu;
+  while (p != c) {
+    c = p;
+    p = L[c] & 0xFFFFu;
+  }
+  return c;
+}
+__device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b) {
+  while (true) {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) {
+      uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    const uint32_t hi = ((volatile uint32_t *) L)[a] & 0xFFFF0000u;
+    const uint32_t old = atomicMin(&L[a], hi | b);
+    if ((old & 0xFFFFu) == a) return;
+    a = old & 0xFFFFu;
+  }
+}
+__device__ __forceinline__ int slot_of(const uint32_t *L, int c) {
+  uint32_t low = L[c] & 0xFFFFu;
+  if (!(low & 0x8000u)) low = L[low] & 0xFFFFu;
+  return (int) (low & 0x7FFFu);
+}
+
+// ---- Eigen::SelfAdjointEigenSolver<Matrix2f> (Eigen 3.3.7 iterative path), device restatement ----------------------
+__device__ __forceinline__ void givens(float p, float q, float &c, float &s) {
+  if (q == 0.0f) {
+    c = p < 0.0f ? -1.0f : 1.0f;
+    s = 0.0f;
+  } else if (p == 0.0f) {
+    c = 0.0f;
+    s = q < 0.0f ? 1.0f : -1.0f;
+  } else if (fabsf(p) > fabsf(q)) {
+    const float t = q / p;
+    float u = sqrtf(1.0f + t * t);
+    if (p < 0.0f) u = -u;
+    c = 1.0f / u;
+    s = -t * c;
+  } else {
+    const float t = p / q;
+    float u = sqrtf(1.0f + t * t);
+    if (q < 0.0f) u = -u;
+    s = -1.0f / u;
+    c = -t * s;
+  }
+}
+__device__ void eig_sym2(float a, float b, float c, float ev[2], float vec[4]) {
+  float scale = fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c));
+  if (scale == 0.0f) scale = 1.0f;
+  float d0 = a / scale, d1 = c / scale, e = b / scale;
+  d1 = d1 + (-1.0f) * (d1 * 0.0f + d1 * 0.0f);  // degenerate Householder rank update of the 2x2 tridiagonalisation
+  float q00 = 1.0f, q10 = 0.0f, q01 = 0.0f, q11 = 1.0f;
+  bool converged = true;
+  for (int iter = 0;; ) {
+    if (fabsf(e) <= (fabsf(d0) + fabsf(d1)) * (2.0f * 1.1920928955078125e-07f) || fabsf(e) <= 1.17549435082228750797e-38f) e = 0.0f;
+    if (e == 0.0f) break;
+    if (++iter > 60) {
+      converged = false;
+      break;
+    }
+    const float td = (d0 - d1) * 0.5f;
+    float mu = d1;
+    if (td == 0.0f) {
+      mu -= fabsf(e);
+    } else {
+      const float e2 = e * e;
+      const float at = fabsf(td), ae = fabsf(e);
+      float hp, hq;
+      if (at > ae) {
+        hp = at;
+        hq = ae / hp;
+      } else {
+        hp = ae;
+        hq = at / hp;
+      }
+      const float h = (hp == 0.0f) ? 0.0f : hp * sqrtf(1.0f + hq * hq);
+      if (e2 == 0.0f)
+        mu -= (e / (td + (td > 0.0f ? 1.0f : -1.0f))) * (e / h);
+      else
+        mu -= e2 / (td + (td > 0.0f ? h : -h));
+    }
+    float gc, gs;
+    givens(d0 - mu, e, gc, gs);
+    const float sdk = gs * d0 + gc * e;
+    const float dkp1 = gs * e + gc * d1;
+    const float nd0 = gc * (gc * d0 - gs * e) - gs * (gc * e - gs * d1);
+    d1 = gs * sdk + gc * dkp1;
+    e = gc * sdk - gs * dkp1;
+    d0 = nd0;
+    const float x0 = q00, y0 = q01, x1 = q10, y1 = q11;
+    q00 = gc * x0 + (-gs) * y0;
+    q01 = gs * x0 + gc * y0;
+    q10 = gc * x1 + (-gs) * y1;
+    q11 = gs * x1 + gc * y1;
+  }
+  if (converged && d1 < d0) {
+    float t = d0;
+    d0 = d1;
+    d1 = t;
+    t = q00;
+    q00 = q01;
+    q01 = t;
+    t = q10;
+    q10 = q11;
+    q11 = t;
+  }
+  ev[0] = d0 * scale;
+  ev[1] = d1 * scale;
+  vec[0] = q00;
+  vec[1] = q10;
+  vec[2] = q01;
+  vec[3] = q11;
+}
+
+struct Moments {
+  int cnt;
+  double s0, s1, t00, t01, t11, q0, q1;
+  float vol3;
+};
+
+__device__ void calc_stat_vals(const Moments &m, const c2g_cm_config &cfg, int level, int poi_r, int poi_c, c2g_view &v) {
+  v.level = (int16_t) level;
+  v.poi_r = (int16_t) poi_r;
+  v.poi_c = (int16_t) poi_c;
+  v.cell_cnt = (int16_t) m.cnt;
+  const float cntf = (float) m.cnt;
+  v.pos_mean[0] = (float) m.s0 / cntf;
+  v.pos_mean[1] = (float) m.s1 / cntf;
+  v.vol3_mean = m.vol3 / cntf;
+  v.com[0] = (float) m.q0 / m.vol3;
+  v.com[1] = (float) m.q1 / m.vol3;
+  v.eccen = 0.0f;
+  for (int i = 0; i < 6; ++i) v.pad_[i] = 0;
+  if (m.cnt < cfg.min_cell_cov) {
+    const float s2 = 1.0f * cfg.point_sigma * cfg.point_sigma, z2 = 0.0f * cfg.point_sigma * cfg.point_sigma;
+    v.pos_cov[0] = s2;
+    v.pos_cov[1] = z2;
+    v.pos_cov[2] = z2;
+    v.pos_cov[3] = s2;
+    v.eig_vals[0] = v.eig_vals[1] = cfg.point_sigma;
+    v.eig_vecs[0] = 1.0f;
+    v.eig_vecs[1] = 0.0f;
+    v.eig_vecs[2] = 0.0f;
+    v.eig_vecs[3] = 1.0f;
+    v.ecc_feat = 0;
+    v.com_feat = 0;
+  } else {
+    const float cm1 = (float) (m.cnt - 1);
+    const float m0 = v.pos_mean[0], m1 = v.pos_mean[1];
+    const float c00 = ((float) m.t00 - (m0 * m0) * cntf) / cm1;
+    const float c01 = ((float) m.t01 - (m0 * m1) * cntf) / cm1;
+    const float c11 = ((float) m.t11 - (m1 * m1) * cntf) / cm1;
+    v.pos_cov[0] = c00;
+    v.pos_cov[1] = c01;
+    v.pos_cov[2] = c01;
+    v.pos_cov[3] = c11;
+    float ev[2], vec[4];
+    eig_sym2(c00, c01, c11, ev, vec);
+    if (ev[0] < cfg.point_sigma) ev[0] = cfg.point_sigma;
+    if (ev[1] < cfg.point_sigma) ev[1] = cfg.point_sigma;
+    v.eig_vals[0] = ev[0];
+    v.eig_vals[1] = ev[1];
+    for (int i = 0; i < 4; ++i) v.eig_vecs[i] = vec[i];
+    v.eccen = sqrtf(ev[1] * ev[1] - ev[0] * ev[0]) / ev[1];
+    const bool dp = fabsf((ev[0] - ev[1]) / fmaxf(ev[0], ev[1])) > 0.2f;
+    v.ecc_feat = (m.cnt > 5 && dp && ev[1] > 2.5f) ? 1 : 0;
+    const float dx = v.com[0] - m0, dy = v.com[1] - m1;
+    v.com_feat = (sqrtf(dx * dx + dy * dy) > cfg.com_bias_thres) ? 1 : 0;
+  }
+}
+
+// V * diag(lambda) * V^T in float (ContourView::getManualCov, include/cont2/contour.h:376-378), column-major out
+__device__ __forceinline__ void manual_cov(const float ev[2], const float vec[4], float out[4]) {
+  const float vd00 = vec[0] * ev[0], vd10 = vec[1] * ev[0], vd01 = vec[2] * ev[1], vd11 = vec[3] * ev[1];
+  out[0] = vd00 * vec[0] + vd01 * vec[2];
+  out[1] = vd10 * vec[0] + vd11 * vec[2];
+  out[2] = vd00 * vec[1] + vd01 * vec[3];
+  out[3] = vd10 * vec[1] + vd11 * vec[3];
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
+contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
+               int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
+               float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
+               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncell = P.n_cells, ncol = P.cfg.n_col, nrow = P.cfg.n_row;
+  const c2g_cm_config &cfg = P.cfg;
+  c2g_view *const presort = presort_scratch + (size_t) blockIdx.x * C2G_VIEW_CAP;
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const size_t cbase = (size_t) b * ncell;
+    const float *hg = bev_h + cbase, *rfg = bev_rf + cbase, *cfp = bev_cf + cbase;
+    c2g_scan_head *head = heads + (first_slot + b);
+    c2g_view *vout = views + (size_t) (first_slot + b) * C2G_VIEW_CAP;
+
+    // ---------------- phase A: decode the tile, gather the winner's continuous coordinates -------------------------
+    if (tid == 0) {
+      S.status = 0;
+      S.n_occ = 0;
+    }
+    __syncthreads();
+    {
+      const float4 *p = pts + offsets[b];
+      int occ = 0;
+      for (int c = tid; c < ncell; c += K2_THREADS) {
+        const c2g_cellkey k = tiles[cbase + c];
+        float h = -1000.0f, rf = -1.0f, cf = -1.0f;
+        uint8_t m = 0;
+        if (k != 0ull) {
+          h = c2g_from_orderable((uint32_t) (k >> 32));
+          const uint32_t idx = 0xFFFFFFFFu - (uint32_t) k;
+          const float2 xy = *reinterpret_cast<const float2 *>(p + idx);
+          // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
+          rf = (xy.x / cfg.reso_row + P.half_row_f) - 0.5f;
+          cf = (xy.y / cfg.reso_col + P.half_col_f) - 0.5f;
+#pragma unroll
+          for (int e = 0; e < C2G_NLEV; ++e) m |= (h > cfg.lv_grads[e]) ? (1u << e) : 0u;
+          occ++;
+        }
+        bev_h[cbase + c] = h;
+        bev_rf[cbase + c] = rf;
+        bev_cf[cbase + c] = cf;
+        S.msk[c] = m;
+        S.L[c] = 0u;
+      }
+      if (occ) atomicAdd(&S.n_occ, occ);
+    }
+    __syncthreads();
+
+    // ---------------- phase B: levels ------------------------------------------------------------------------------
+    int total_views = 0;
+    for (int lev = 0; lev < C2G_NLEV; ++lev) {
+      const uint8_t bit = (uint8_t) (1u << lev);
+      if (tid == 0) {
+        S.ncomp = 0;
+        S.nsig = 0;
+      }
+      // B1 init label words (keep the upper half = rank of the enclosing component of the previous level)
+      for (int c = tid; c < ncell; c += K2_THREADS)
+        if (S.msk[c] & bit) S.L[c] = (S.L[c] & 0xFFFF0000u) | (uint32_t) c;
+      __syncthreads();
+      // B2 unions with the 4 already-visited neighbours of the 8-neighbourhood
+      for (int c = tid; c < ncell; c += K2_THREADS) {
+        if (!(S.msk[c] & bit)) continue;
+        const int r = c / ncol, cc = c - r * ncol;
+        if (cc > 0 && (S.msk[c - 1] & bit)) uf_union(S.L, c, c - 1);
+        if (r > 0) {
+          const int up = c - ncol;
+          if (S.msk[up] & bit) uf_union(S.L, c, up);
+          if (cc > 0 && (S.msk[up - 1] & bit)) uf_union(S.L, c, up - 1);
+          if (cc + 1 < ncol && (S.msk[up + 1] & bit)) uf_union(S.L, c, up + 1);
+        }
+      }
+      __syncthreads();
+      // B3 flatten
+      for (int c = tid; c < ncell; c += K2_THREADS)
+        if (S.msk[c] & bit) {
+          const uint32_t root = uf_find(S.L, c);
+          S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
+        }
+      __syncthreads();
+      // B4 roots -> table slots
+      for (int c = tid; c < ncell; c += K2_THREADS)
+        if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) {
+          int slot = atomicAdd(&S.ncomp, 1);
+          if (slot < NC) {
+            S.c_area[slot] = 0;
+            S.c_minr[slot] = 1 << 20;
+            S.c_minc[slot] = 1 << 20;
+            S.c_maxr[slot] = -1;
+            S.c_maxc[slot] = -1;
+            S.c_key[slot] = 1 << 30;
+            S.c_poi[slot] = -1;
+            S.c_pcid[slot] = (uint16_t) (S.L[c] >> 16);
+            S.c_rank[slot] = 0xFFFFu;
+          } else {
+            slot = 0x7FFF;
+            atomicOr(&S.status, 2);
+          }
+          S.L[c] = (S.L[c] & 0xFFFF0000u) | 0x8000u | (uint32_t) slot;
+        }
+      __syncthreads();
+      // B5 per-component area / bbox / first-block key / last pixel, aggregated over horizontal runs per thread chunk
+      {
+        const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
+        const int c0 = tid * chunk, c1 = min(ncell, c0 + chunk);
+        int cur = -1, run_r = 0, run_c0 = 0, run_c1 = 0;
+        for (int c = c0; c <= c1; ++c) {
+          int slot = -1, r = 0, cc = 0;
+          if (c < c1 && (S.msk[c] & bit)) {
+            slot = slot_of(S.L, c);
+            if (slot == 0x7FFF) slot = -1;
+            r = c / ncol;
+            cc = c - r * ncol;
+          }
+          if (slot != cur || (slot >= 0 && r != run_r)) {
+            if (cur >= 0) {
+              atomicAdd(&S.c_area[cur], run_c1 - run_c0 + 1);
+              atomicMin(&S.c_minr[cur], run_r);
+              atomicMax(&S.c_maxr[cur], run_r);
+              atomicMin(&S.c_minc[cur], run_c0);
+              atomicMax(&S.c_maxc[cur], run_c1);
+              const int pc = S.c_pcid[cur];
+              const int x0 = lev ? (int) S.px0[pc & (NVL - 1)] : 0, y0 = lev ? (int) S.py0[pc & (NVL - 1)] : 0;
+              atomicMin(&S.c_key[cur], ((run_r - y0) >> 1) * 128 + ((run_c0 - x0) >> 1));
+              atomicMax(&S.c_poi[cur], run_r * ncol + run_c1);
+            }
+            cur = slot;
+            run_r = r;
+            run_c0 = cc;
+          }
+          run_c1 = cc;
+        }
+      }
+      __syncthreads();
+      // B6 significant components -> DFS order rank
+      const int ncomp = min(S.ncomp, NC);
+      for (int s = tid; s < ncomp; s += K2_THREADS)
+        if (S.c_area[s] >= cfg.min_cont_cell_cnt) {
+          const int i = atomicAdd(&S.nsig, 1);
+          if (i < NVL) {
+            S.sig_slot[i] = (uint16_t) s;
+            S.sig_key[i] = ((uint32_t) S.c_pcid[s] << 16) | (uint32_t) S.c_key[s];
+          } else
+            atomicOr(&S.status, 2);
+        }
+      __syncthreads();
+      int nsig = min(S.nsig, NVL);
+      if (total_views + nsig > C2G_VIEW_CAP) {
+        nsig = C2G_VIEW_CAP - total_views;
+        if (tid == 0) atomicOr(&S.status, 1);
+      }
+      for (int i = tid; i < min(S.nsig, NVL); i += K2_THREADS) {
+        const uint32_t ki = S.sig_key[i];
+        int rank = 0;
+        for (int j = 0; j < min(S.nsig, NVL); ++j) rank += (S.sig_key[j] < ki) ? 1 : 0;
+        if (rank < nsig) {
+          S.order[rank] = S.sig_slot[i];
+          S.c_rank[S.sig_slot[i]] = (uint16_t) rank;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        S.n_views[lev] = nsig;
+        S.view_off[lev] = total_views;
+      }
+      // B7 moments in bbox-raster order + calcStatVals: one warp per component, all lanes carry the same accumulators
+      for (int rk = warp; rk < nsig; rk += K2_WARPS) {
+        const int s = S.order[rk];
+        const int r0 = S.c_minr[s], c0 = S.c_minc[s], w = S.c_maxc[s] - c0 + 1, hgt = S.c_maxr[s] - r0 + 1;
+        const int total = w * hgt;
+        Moments m;
+        m.cnt = 0;
+        m.s0 = m.s1 = m.t00 = m.t01 = m.t11 = m.q0 = m.q1 = 0.0;
+        m.vol3 = 0.0f;
+        for (int base = 0; base < total; base += 32) {
+          const int i = base + lane;
+          bool member = false;
+          float h = 0.f, rf = 0.f, cf = 0.f;
+          if (i < total) {
+            const int rr = r0 + i / w, cc = c0 + i % w;
+            const int c = rr * ncol + cc;
+            if ((S.msk[c] & bit) && slot_of(S.L, c) == s) {
+              member = true;
+              h = hg[c];
+              rf = rfg[c];
+              cf = cfp[c];
+            }
+          }
+          unsigned bal = __ballot_sync(0xFFFFFFFFu, member);
+          while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const float hh = __shfl_sync(0xFFFFFFFFu, h, src);
+            const double v0 = (double) __shfl_sync(0xFFFFFFFFu, rf, src);
+            const double v1 = (double) __shfl_sync(0xFFFFFFFFu, cf, src);
+            m.cnt += 1;
+            m.s0 += v0;
+            m.s1 += v1;
+            m.t00 += v0 * v0;
+            m.t01 += v0 * v1;
+            m.t11 += v1 * v1;
+            m.vol3 += hh;
+            m.q0 += (double) hh * v0;
+            m.q1 += (double) hh * v1;
+          }
+        }
+        if (lane == 0) {
+          c2g_view v;
+          const int poi = S.c_poi[s];
+          calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, v);
+          presort[total_views + rk] = v;
+          S.sortbuf[total_views + rk] = ((uint32_t) m.cnt << 16) | (uint32_t) rk;
+        }
+      }
+      // B8 hand the ranks down: upper half of every foreground word = rank of its component (0xFFFF if insignificant)
+      for (int i = tid; i < nsig; i += K2_THREADS) {
+        const int s = S.order[i];
+        S.px0[i] = (uint8_t) S.c_minc[s];
+        S.py0[i] = (uint8_t) S.c_minr[s];
+      }
+      for (int c = tid; c < ncell; c += K2_THREADS)
+        if (S.msk[c] & bit) {
+          const int s = slot_of(S.L, c);
+          const uint32_t rk = (s == 0x7FFF) ? 0xFFFFu : (uint32_t) S.c_rank[s];
+          // written after the slot lookups of this thread's own cell only; other threads may still read the ROOT word's
+          // low half, which is preserved below
+          S.L[c] = (rk << 16) | (S.L[c] & 0xFFFFu);
+        }
+      total_views += nsig;
+      __syncthreads();
+    }
+
+    // ---------------- phase C: per-level std::sort replay (cell_cnt descending), sorted views to the arena ----------
+    if (tid < C2G_NLEV) {
+      uint32_t *first = S.sortbuf + S.view_off[tid];
+      c2g_sort::std_sort(first, (long) S.n_views[tid], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
+      int sum = 0;
+      for (int i = 0; i < S.n_views[tid]; ++i) sum += (int) (first[i] >> 16);
+      S.layer_cnt[tid] = sum;
+    }
+    __syncthreads();
+    {
+      // copy 80-byte records as 20 x 4-byte words: sorted position j of level l <- presort index (sortbuf & 0xFFFF)
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(presort);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(vout);
+      constexpr int WPV = sizeof(c2g_view) / 4;
+      for (int lev = 0; lev < C2G_NLEV; ++lev) {
+        const int off = S.view_off[lev], n = S.n_views[lev];
+        for (int i = tid; i < n * WPV; i += K2_THREADS) {
+          const int j = i / WPV, wd = i - j * WPV;
+          const int from = off + (int) (S.sortbuf[off + j] & 0xFFFFu);
+          dst[(size_t) (off + j) * WPV + wd] = src[(size_t) from * WPV + wd];
+        }
+      }
+      for (int i = tid; i < C2G_NLEV * C2G_MAX_DIST_FIRSTS; i += K2_THREADS) {
+        const int lev = i / C2G_MAX_DIST_FIRSTS, j = i % C2G_MAX_DIST_FIRSTS;
+        TopView t;
+        t.cnt = 0;
+        t.mean0 = t.mean1 = t.eig0 = t.eig1 = 0.f;
+        if (j < S.n_views[lev]) {
+          const c2g_view &v = presort[S.view_off[lev] + (S.sortbuf[S.view_off[lev] + j] & 0xFFFFu)];
+          t.cnt = v.cell_cnt;
+          t.mean0 = v.pos_mean[0];
+          t.mean1 = v.pos_mean[1];
+          t.eig0 = v.eig_vals[0];
+          t.eig1 = v.eig_vals[1];
+        }
+        S.top[lev][j] = t;
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase D: retrieval keys (contour_mng.h:693-830) ------------------------------------------------
+    // D1: per anchor, ordered list of the window cells that contribute: (dist, higher_cnt). One warp per anchor.
+    float *klist_dist = reinterpret_cast<float *>(S.L);                               // [N_ANCH][KEY_LIST_CAP]
+    uint8_t *klist_hc = reinterpret_cast<uint8_t *>(klist_dist + N_ANCH * KEY_LIST_CAP);  // [N_ANCH][KEY_LIST_CAP]
+    static_assert(N_ANCH * KEY_LIST_CAP * 5 <= sizeof(uint32_t) * C2G_MAX_CELLS, "key lists must fit in the label array");
+    const int piv = cfg.piv_firsts;
+    const int roi_pad = (int) ceilf(cfg.roi_radius + 1.0f);
+    for (int a = warp; a < N_ANCH; a += K2_WARPS) {
+      const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
+      int cnt = 0;
+      const bool valid = seq < piv && seq < S.n_views[ll] && S.top[ll][seq].cnt >= cfg.min_cont_key_cnt;
+      if (valid) {
+        const float cx = S.top[ll][seq].mean0, cy = S.top[ll][seq].mean1;
+        const int r_cen = (int) cx, c_cen = (int) cy;
+        const int r_min = max(0, r_cen - roi_pad), r_max = min(nrow - 1, r_cen + roi_pad);
+        const int c_min = max(0, c_cen - roi_pad), c_max = min(ncol - 1, c_cen + roi_pad);
+        const int w = c_max - c_min + 1, total = w * (r_max - r_min + 1);
+        const double rad = (double) cfg.roi_radius - 1e-2;
+        for (int base = 0; base < total; base += 32) {
+          const int i = base + lane;
+          bool pass = false;
+          float dist = 0.f;
+          uint8_t hc = 0;
+          if (i < total) {
+            const int c = (r_min + i / w) * ncol + (c_min + i % w);
+            const uint8_t m = S.msk[c];
+            if (m & 2u) {  // bev > lv_grads[1]  (cells with bev == lv_grads[1] pass the first test but fail this one)
+              const float dx = rfg[c] - cx, dy = cfp[c] - cy;
+              dist = sqrtf(dx * dx + dy * dy);
+              if ((double) dist < rad) {
+                pass = true;
+                hc = (uint8_t) __popc((unsigned) (m & 0x3Eu));
+              }
+            }
+          }
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+          if (pass) {
+            const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+            if (pos < KEY_LIST_CAP) {
+              klist_dist[a * KEY_LIST_CAP + pos] = dist;
+              klist_hc[a * KEY_LIST_CAP + pos] = hc;
+            }
+          }
+          cnt += __popc(bal);
+        }
+        if (cnt > KEY_LIST_CAP && lane == 0) atomicOr(&S.status, 4);
+      }
+      if (lane == 0) S.cnt_point[a] = valid ? cnt : -1;
+    }
+    __syncthreads();
+    // D2: one thread per (anchor, division): sequential float accumulation in raster order
+    {
+      const float div_len = cfg.roi_radius / (float) ((C2G_KEY_DIM - 3) * 5);
+      const double inv_norm_den = sqrt(2 * 3.14159265358979323846 * 1.0f * 1.0f);
+      for (int w = tid; w < N_ANCH * N_DIVS; w += K2_THREADS) {
+        const int a = w / N_DIVS, d = w - a * N_DIVS;
+        const int n = min(S.cnt_point[a], KEY_LIST_CAP);
+        float acc = 0.0f;
+        if (n > 0) {
+          const float x = (float) ((double) ((float) d * div_len) + 0.5 * (double) div_len);
+          const float *dl = klist_dist + a * KEY_LIST_CAP;
+          const uint8_t *hl = klist_hc + a * KEY_LIST_CAP;
+          for (int k = 0; k < n; ++k) {
+            const float t = (x - dl[k]) / 1.0f;
+            const double q = (-0.5 * (double) t) * (double) t;
+            const float g = (float) (exp(q) / inv_norm_den);
+            acc += (float) hl[k] * g;
+          }
+        }
+        S.divs[a][d] = acc;
+      }
+    }
+    __syncthreads();
+    for (int w = tid; w < N_ANCH * C2G_KEY_DIM; w += K2_THREADS) {
+      const int a = w / C2G_KEY_DIM, kd = w - a * C2G_KEY_DIM;
+      const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
+      float val = 0.0f;
+      if (S.cnt_point[a] >= 0) {
+        const TopView &t = S.top[ll][seq];
+        if (kd == 0)
+          val = sqrtf(t.eig1 * (float) t.cnt);
+        else if (kd == 1)
+          val = sqrtf(t.eig0 * (float) t.cnt);
+        else if (kd == 2) {
+          int accum = 0;
+          for (int s2 = 0; s2 <= seq; ++s2) accum += S.top[ll][s2].cnt;
+          val = (float) sqrt((double) accum);
+        } else {
+          const int bn = kd - 3;
+          float ring = 0.0f;
+          for (int d = 0; d < 5; ++d) ring += S.divs[a][bn * 5 + d];
+          const float bin_len = cfg.roi_radius / (float) (C2G_KEY_DIM - 3);
+          ring = (float) ((double) ring * ((double) bin_len / sqrt((double) S.cnt_point[a])));
+          val = ring;
+        }
+      }
+      head->keys[ll][seq][kd] = val;
+    }
+
+    // ---------------- phase E: BCIs (contour_mng.h:848-883), one thread per anchor ---------------------------------
+    if (tid < N_ANCH) {
+      const int a = tid, ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
+      if (seq < piv) {
+        c2g_bci &bci = head->bcis[ll][seq];
+        uint64_t bins[4] = {0, 0, 0, 0};
+        c2g_relpt nei[C2G_MAX_NEI];
+        uint32_t ord[C2G_MAX_NEI];
+        int n = 0;
+        if (S.cnt_point[a] >= 0) {
+          const TopView &an = S.top[ll][seq];
+          for (int bl = 0; bl < C2G_NUM_BIN_LAYERS; ++bl) {
+            const int layer = bl + 1;
+            const int lim = min(cfg.dist_firsts, S.n_views[layer]);
+            for (int j = 0; j < lim; ++j) {
+              if (ll == layer && j == seq) continue;
+              const float vx = S.top[layer][j].mean0 - an.mean0, vy = S.top[layer][j].mean1 - an.mean1;
+              const float dist = sqrtf(vx * vx + vy * vy);
+              if ((double) dist > (C2G_BITS_PER_LAYER - 1) * 1.01 + 5.43 - 1e-3 || (double) dist <= 5.43) continue;
+              const float orie = atan2f(vy, vx);
+              const int idx = (int) (fmin(floor(((double) dist - 5.43) / 1.01), C2G_BITS_PER_LAYER - 1.0) + (double) (bl * C2G_BITS_PER_LAYER));
+              bins[idx >> 6] |= 1ull << (idx & 63);
+              nei[n].level = (int8_t) layer;
+              nei[n].seq = (int8_t) j;
+              nei[n].bit_pos = (int16_t) idx;
+              nei[n].r = dist;
+              nei[n].theta = orie;
+              ord[n] = ((uint32_t) idx << 16) | (uint32_t) n;
+              ++n;
+            }
+          }
+        }
+        c2g_sort::std_sort(ord, (long) n, [](uint32_t x, uint32_t y) { return (x >> 16) < (y >> 16); });
+        for (int i = 0; i < 4; ++i) bci.dist_bin[i] = bins[i];
+        int nseg = 0;
+        for (int i = 0; i < C2G_MAX_NEI; ++i) {
+          c2g_relpt rp;
+          rp.level = 0;
+          rp.seq = 0;
+          rp.bit_pos = 0;
+          rp.r = 0.f;
+          rp.theta = 0.f;
+          if (i < n) rp = nei[ord[i] & 0xFFFFu];
+          bci.nei[i] = rp;
+        }
+        uint16_t segv[C2G_MAX_NEI + 2];
+        if (n > 0) {
+          segv[nseg++] = 0;
+          for (int p1 = 0; p1 < n; ++p1)
+            if ((ord[segv[nseg - 1]] >> 16) != (ord[p1] >> 16)) segv[nseg++] = (uint16_t) p1;
+          segv[nseg++] = (uint16_t) n;
+        }
+        for (int i = 0; i < C2G_MAX_NEI + 2; ++i) bci.seg[i] = i < nseg ? segv[i] : (uint16_t) 0;
+        bci.n_nei = (int16_t) n;
+        bci.n_seg = (int16_t) nseg;
+        bci.piv_seq = (int8_t) seq;
+        bci.level = (int8_t) ll;
+        for (int i = 0; i < 6; ++i) bci.pad_[i] = 0;
+      }
+    }
+
+    // ---------------- phase F: scan-only GMM terms (correlation.h:49-82,102-119) -----------------------------------
+    __shared__ int n_ell_s[C2G_NUM_BIN_LAYERS];
+    if (tid < C2G_NUM_BIN_LAYERS) {
+      const int lev = tid + 1;
+      const int full = S.layer_cnt[lev];
+      int run = 0, k = 0;
+      const uint32_t *sb = S.sortbuf + S.view_off[lev];
+      for (; k < S.n_views[lev]; ++k) {
+        if ((double) run * 1.0 / (double) full >= 0.95) break;
+        run += (int) (sb[k] >> 16);
+      }
+      n_ell_s[tid] = k;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
+      const int n = n_ell_s[li];
+      const c2g_view *lv = vout + S.view_off[li + 1];
+      for (int w = tid; w < n * n; w += K2_THREADS) {
+        const int i = w / n, j = w - i * n;
+        const c2g_view &A = lv[i], &Bv = lv[j];
+        float ca[4], cb[4];
+        manual_cov(A.eig_vals, A.eig_vecs, ca);
+        manual_cov(Bv.eig_vals, Bv.eig_vecs, cb);
+        const double c00 = 2.0 * ((double) ca[0] + (double) cb[0]), c10 = 2.0 * ((double) ca[1] + (double) cb[1]);
+        const double c01 = 2.0 * ((double) ca[2] + (double) cb[2]), c11 = 2.0 * ((double) ca[3] + (double) cb[3]);
+        const double mx = (double) A.pos_mean[0] - (double) Bv.pos_mean[0], my = (double) A.pos_mean[1] - (double) Bv.pos_mean[1];
+        const double det = c00 * c11 - c01 * c10;
+        const double invdet = 1.0 / det;
+        const double qf = mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my);
+        acc += (double) A.cell_cnt * (double) Bv.cell_cnt / sqrt(det) * exp(-0.5 * qf);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) S.red[warp] = acc;
+    __syncthreads();
+    // ---------------- phase G: head ------------------------------------------------------------------------------------
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int i = 0; i < K2_WARPS; ++i) tot += S.red[i];
+      head->int_id = int_ids ? int_ids[b] : (first_slot + b);
+      head->status = S.status;
+      for (int l = 0; l < C2G_NLEV; ++l) {
+        head->n_views[l] = S.n_views[l];
+        head->view_off[l] = S.view_off[l];
+        head->layer_cell_cnt[l] = S.layer_cnt[l];
+      }
+      for (int l = 0; l < C2G_NUM_BIN_LAYERS; ++l) head->n_ell[l] = n_ell_s[l];
+      head->n_occupied = S.n_occ;
+      head->pad_ = 0;
+      head->gmm_auto_corr = tot;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
+
+int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
+                        const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
+    attr_set = true;
+  }
+  const int grid = B < num_sms ? B : num_sms;
+  if (grid <= 0) return 0;
+  contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views);
+  C2G_CUDA_TRY(cudaGetLastError());
+  return 0;
+}

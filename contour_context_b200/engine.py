@@ -1,0 +1,131 @@
+"""Thin Python mirror of the C-ABI context (include/c2g.h).  torch is plumbing only: device buffers, streams, NCCL.
+
+`Engine` owns one c2g context on one GPU.  Names follow the reference: a *scan* is one ContourManager
+(include/cont2/contour_mng.h:414), a *slot* is where its finished descriptor lives in HBM, gidx == slot for DB scans.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from . import ctypes_defs as D
+
+
+class Engine:
+    def __init__(self, cm_cfg: D.CmConfig = None, db_cfg: D.DbConfig = None, device: int = 0, scan_capacity: int = 1024,
+                 max_batch: int = 256, max_points: int = 256 * 131072):
+        self.cm_cfg = cm_cfg or D.kitti_cm_config()
+        self.db_cfg = db_cfg or D.kitti_db_config()
+        self.device = device
+        self.scan_capacity = scan_capacity
+        self.max_batch = max_batch
+        self.n_cells = self.cm_cfg.n_row * self.cm_cfg.n_col
+        h = C.c_void_p()
+        capi.check(capi.lib().c2g_create(C.byref(self.cm_cfg), C.byref(self.db_cfg), device, scan_capacity, max_batch,
+                                         max_points, C.byref(h)), "c2g_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().c2g_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- streams ---------------------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr: int):
+        capi.check(capi.lib().c2g_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "c2g_set_stream")
+
+    def sync(self):
+        capi.check(capi.lib().c2g_sync(self.h), "c2g_sync")
+
+    # ---- ingest (ContourManager::makeBEV + makeContoursRecurs) --------------------------------------------------------
+    def ingest(self, pts, offsets, first_slot: int = 0, int_ids=None, on_device: bool = None):
+        """pts: float32 [sum_n, 4] numpy array / torch tensor (host or cuda); offsets: int64 [B+1] in points."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        B = len(offsets) - 1
+        if on_device is None:
+            on_device = bool(getattr(pts, "is_cuda", False))
+        ids = None if int_ids is None else np.ascontiguousarray(int_ids, np.int32)
+        capi.check(capi.lib().c2g_ingest(self.h, capi.ptr(pts), capi.ptr(offsets), B, int(on_device), first_slot,
+                                         capi.ptr(ids)), "c2g_ingest")
+        return B
+
+    def ingest_bev_only(self, pts, offsets, on_device: bool = None):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        if on_device is None:
+            on_device = bool(getattr(pts, "is_cuda", False))
+        capi.check(capi.lib().c2g_ingest_bev_only(self.h, capi.ptr(pts), capi.ptr(offsets), len(offsets) - 1,
+                                                  int(on_device)), "c2g_ingest_bev_only")
+
+    def heads(self, first_slot: int, n: int) -> np.ndarray:
+        out = np.zeros(n, D.SCAN_HEAD_DTYPE)
+        capi.check(capi.lib().c2g_get_heads(self.h, first_slot, n, capi.ptr(out)), "c2g_get_heads")
+        return out
+
+    def views(self, slot: int, head=None):
+        """Per-level sorted ContourView lists of one scan: list of NLEV structured arrays."""
+        raw = np.zeros(D.VIEW_CAP, D.VIEW_DTYPE)
+        capi.check(capi.lib().c2g_get_views(self.h, slot, capi.ptr(raw)), "c2g_get_views")
+        if head is None:
+            head = self.heads(slot, 1)[0]
+        return [raw[head["view_off"][l]: head["view_off"][l] + head["n_views"][l]].copy() for l in range(D.NLEV)]
+
+    def bev(self, batch_index: int):
+        b, r, c = (np.empty(self.n_cells, np.float32) for _ in range(3))
+        capi.check(capi.lib().c2g_get_bev(self.h, batch_index, capi.ptr(b), capi.ptr(r), capi.ptr(c)), "c2g_get_bev")
+        return b, r, c
+
+    def tiles(self, batch_index: int):
+        t = np.empty(self.n_cells, np.uint64)
+        capi.check(capi.lib().c2g_get_tiles(self.h, batch_index, capi.ptr(t)), "c2g_get_tiles")
+        return t
+
+    def copy_slots(self, src_first: int, dst_first: int, n: int):
+        capi.check(capi.lib().c2g_copy_slots(self.h, src_first, dst_first, n), "c2g_copy_slots")
+
+    # ---- database mirror + query -----------------------------------------------------------------------------------------
+    def db_set_layer(self, ll: int, keys: np.ndarray, gidx: np.ndarray, seq: np.ndarray, bucket: np.ndarray,
+                     bucket_ranges: np.ndarray):
+        keys = np.ascontiguousarray(keys, np.float32).reshape(-1, D.KEY_DIM)
+        gidx = np.ascontiguousarray(gidx, np.int32)
+        seq = np.ascontiguousarray(seq, np.int8)
+        bucket = np.ascontiguousarray(bucket, np.uint8)
+        rng = np.ascontiguousarray(bucket_ranges, np.float32)
+        assert rng.shape == (D.NUM_BUCKETS + 1,)
+        capi.check(capi.lib().c2g_db_set_layer(self.h, ll, keys.shape[0], capi.ptr(keys), capi.ptr(gidx), capi.ptr(seq),
+                                               capi.ptr(bucket), capi.ptr(rng)), "c2g_db_set_layer")
+
+    def hint_slots(self, B: int) -> int:
+        return B * self.db_cfg.n_q_levels * D.MAX_PIV * self.db_cfg.nnk
+
+    def query(self, first_slot: int, B: int, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble, want_trace: bool = False):
+        res = np.zeros(B, D.QUERY_RESULT_DTYPE)
+        hints = scores = None
+        if want_trace:
+            hints = np.zeros(self.hint_slots(B), D.HINT_DTYPE)
+            scores = np.zeros(self.hint_slots(B), D.PAIR_SCORE_DTYPE)
+        capi.check(capi.lib().c2g_query(self.h, first_slot, B, C.byref(lb), C.byref(ub), capi.ptr(res), capi.ptr(hints),
+                                        capi.ptr(scores)), "c2g_query")
+        return (res, hints, scores) if want_trace else res
+
+    def query_async(self, first_slot: int, B: int, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble):
+        capi.check(capi.lib().c2g_query_async(self.h, first_slot, B, C.byref(lb), C.byref(ub)), "c2g_query_async")
+
+    def query_buffers(self):
+        r, h, s, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_longlong()
+        capi.check(capi.lib().c2g_query_buffers(self.h, C.byref(r), C.byref(h), C.byref(s), C.byref(n)), "c2g_query_buffers")
+        return r.value, h.value, s.value, n.value
+
+    def finish_from_scores(self, first_slot: int, B: int, lb: D.ScoreEnsemble, hints_dev: int, scores_dev: int):
+        res = np.zeros(B, D.QUERY_RESULT_DTYPE)
+        capi.check(capi.lib().c2g_finish_from_scores(self.h, first_slot, B, C.byref(lb), C.c_void_p(hints_dev),
+                                                     C.c_void_p(scores_dev), capi.ptr(res)), "c2g_finish_from_scores")
+        return res
+
+    def launch_count(self) -> int:
+        return int(capi.lib().c2g_launch_count(self.h))

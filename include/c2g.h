@@ -1,0 +1,105 @@
+/*
+ * c2g.h — the C-ABI of the B200-native cont2contops hot path (libc2g.so).
+ *
+ * The reference has no FFI/plugin interface: its "plugin API" is the C++ class surface ContourManager / ContourDB that
+ * test/batch_bin_test.cpp drives.  This header is the thin boundary a maintainer binds to keep that
+ * surface and move the work to the GPU: plain pointers, sizes and POD structs (include/c2g_types.h), no torch / STL
+ * types, `int` return codes (0 = ok, < 0 = -cudaError_t, <= -1000 = argument error), never throws.
+ * The host-side C++ facade in contour_context_b200/host/ (same class and method names as the reference) and the
+ * Python mirror in contour_context_b200/ are both written against exactly these entry points.
+ *
+ * Each entry point cites the reference interface it replaces (file:line relative to the reference repo).
+ * One context per (process, device); calls are stream-ordered on the context's stream; not thread-safe.
+ */
+#ifndef C2G_H
+#define C2G_H
+
+#include "c2g_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct c2g_ctx c2g_ctx;
+
+#define C2G_ERR_ARG (-1000)
+#define C2G_ERR_CAPACITY (-1001)
+#define C2G_ERR_STATE (-1002)
+
+/* Library / ABI version and struct sizes (lets a binding verify it was generated against the same header). */
+int c2g_abi_version(void);
+int c2g_sizeof(int which); /* 0 scan_head, 1 view, 2 bci, 3 hint, 4 pair_score, 5 query_result, 6 cm_config, 7 db_config */
+
+/* Replaces: ContourManager::ContourManager(cfg, int_id) storage (include/cont2/contour_mng.h:478-498) and
+ * ContourDB::ContourDB(cfg) (include/cont2/contour_db.h:680-684).
+ * `scan_capacity` = number of scan slots (DB scans + in-flight query scans) resident in HBM,
+ * `max_batch` = largest number of scans one c2g_ingest / c2g_query call may carry,
+ * `max_points` = largest total number of points of one batch (staging buffer for host inputs). */
+int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int device, int scan_capacity, int max_batch,
+               long long max_points, c2g_ctx **out);
+int c2g_destroy(c2g_ctx *ctx);
+
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*) for all subsequent work; NULL = context's own. */
+int c2g_set_stream(c2g_ctx *ctx, void *cuda_stream);
+int c2g_sync(c2g_ctx *ctx);
+
+/* Replaces, for a batch of B scans: readKITTIPointCloudBin's output buffer (include/tools/pointcloud_util.h:12-50,
+ * N x 4 float32 per scan) -> ContourManager::makeBEV (include/cont2/contour_mng.h:505-556) ->
+ * ContourManager::makeContoursRecurs (:588-960).  Scan b's points are pts[4*offsets[b] .. 4*offsets[b+1]).
+ * `pts_on_device` != 0: pts is a device pointer (16-byte aligned); otherwise a host pointer that is copied through the
+ * context's staging buffer inside the call (pinned host memory makes that copy asynchronous).
+ * The descriptors land in scan slots first_slot .. first_slot + B - 1; int_ids (host, may be NULL) are the
+ * ContourManager int ids (evaluator.h:290). Asynchronous on the context stream. */
+int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
+               const int *int_ids_host);
+
+/* Individual stages of c2g_ingest for profiling and parity tests (same arguments; `first_slot` as above). */
+int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device);
+
+/* Read back (synchronises the stream): ContourManager getters (include/cont2/contour_mng.h:1052-1106). */
+int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host);
+int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host /* C2G_VIEW_CAP records */);
+/* Dense BEV of scan `batch_index` of the LAST ingest batch: ContourManager::getBevImage (:573-586) plus the
+ * continuous pillar coordinates bev_pixfs_ (:435); empty cells are -1000 / -1 / -1. Each array holds n_row*n_col. */
+int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f);
+/* Raw 64-bit BEV cell keys of the last batch (debug / K1 parity). */
+int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host);
+
+/* Copy finished descriptors between slots (ContourDB::addScan keeps the shared_ptr, include/cont2/contour_db.h:823). */
+int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n);
+
+/* Mirror of the host-maintained LayerDB state (include/cont2/contour_db.h:159-217, src/cont2/contour_db.cpp:63-317):
+ * for q-level index `ll`, the keys currently INSIDE the KD-trees (not the time-delay buffers), the bucket each one
+ * lives in, where it came from (IndexOfKey gidx/seq) and the 7 bucket boundaries. keys: n x 10 floats, row-major. */
+int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const int *gidx_host, const signed char *seq_host,
+                     const unsigned char *bucket_host, const float *bucket_ranges_host);
+
+/* Replaces ContourDB::queryRangedKNN (include/cont2/contour_db.h:698-811) for B query scans sitting in slots
+ * first_slot.. : ranged kNN over the mirrored key tables (LayerDB::layerKNNSearch, contour_db.cpp:319-379) ->
+ * CandidateManager::checkCandWithHint for every hint (contour_db.h:374-488) -> tidyUpCandidates (:494-596) ->
+ * fineOptimize's selection without the Ceres step (:604-648). gidx of a DB scan == its slot.
+ * results_host: B records. hints_host / scores_host (optional, may be NULL): B * n_q_levels * piv * nnk records in
+ * reference order (layer, query seq, ascending distance), empty slots have cand_gidx = -1. Synchronises the stream. */
+int c2g_query(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+              c2g_query_result *results_host, c2g_hint *hints_host, c2g_pair_score *scores_host);
+/* Same, asynchronous, results stay on the device (for multi-GPU gathers and timing); pointers are device pointers
+ * owned by the context, valid until the next query call. */
+int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub);
+int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void **scores_dev, long long *n_hint_slots);
+/* Finish a query from pair-score records produced elsewhere (multi-GPU: after the all-gather of score records):
+ * replay CandidatePoseData::addProposal / tidyUpCandidates for B queries from device arrays laid out like
+ * c2g_query_buffers'. */
+int c2g_finish_from_scores(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const void *hints_dev,
+                           const void *scores_dev, c2g_query_result *results_host);
+
+/* Counters: kernels launched by this context since creation (bench.py's gpu_launches). */
+long long c2g_launch_count(c2g_ctx *ctx);
+
+/* Host-side replay of libstdc++ std::sort used by the kernels (tests only): sorts `n` packed (key << 16 | index)
+ * words with comparator key-descending (desc != 0) or key-ascending. */
+int c2g_selftest_stdsort(unsigned int *words, int n, int desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2G_H */

@@ -168,3 +168,24 @@ int c2o_sizeof_scan_head() { return (int) sizeof(c2g_scan_head); }
 int c2o_sizeof_query_result() { return (int) sizeof(c2g_query_result); }
 
 }  // extern "C"
+
+// real libstdc++ std::sort on packed (key << 16 | index) words — the reference behaviour tests compare the device-side
+// replay (contour_context_b200/csrc/stdsort.cuh) against.
+extern "C" void c2o_std_sort_words(uint32_t *words, int n, int desc) {
+  if (desc)
+    std::sort(words, words + n, [](uint32_t a, uint32_t b) { return (a >> 16) > (b >> 16); });
+  else
+    std::sort(words, words + n, [](uint32_t a, uint32_t b) { return (a >> 16) < (b >> 16); });
+}
+
+// test hook: put n keys straight into bucket 0's tree of q-level ll (gidx = index, seq = 0)
+extern "C" void c2o_test_fill_layer(void *db, int ll, const float *keys, int n) {
+  TreeBucket &b = ((ContourDB *) db)->layer_db_[ll].buckets_[0];
+  for (int i = 0; i < n; ++i) {
+    Key k;
+    for (int d = 0; d < C2G_KEY_DIM; ++d) k[d] = keys[i * C2G_KEY_DIM + d];
+    b.data_tree.push_back(k);
+    b.gkidx_tree.push_back(IndexOfKey{(size_t) i, 0, 0});
+  }
+  b.rebuildTree();
+}

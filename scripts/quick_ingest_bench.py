@@ -1,0 +1,41 @@
+"""Developer timing of the ingest kernels on device-resident input (CUDA events on the context stream)."""
+import sys, os, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from contour_context_b200 import synth
+from contour_context_b200.engine import Engine
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+N = 120000
+eng = Engine(scan_capacity=B + 8, max_batch=B, max_points=1024)
+chunks = []
+for i0 in range(0, B, 74):
+    n = min(74, B - i0)
+    seeds, visits = synth.db_layout(n, 4, first_scene=i0 // 4)
+    chunks.append(synth.make_scans(seeds, visits, N, device="cuda", noise_seed=i0))
+pts = torch.cat(chunks).reshape(-1, 4).contiguous()
+offsets = np.arange(B + 1, dtype=np.int64) * N
+st = torch.cuda.Stream()
+eng.set_stream(st.cuda_stream)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+def timeit(fn, reps=5):
+    ts = []
+    for _ in range(reps):
+        with torch.cuda.stream(st):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            fn()
+            e1.record(st)
+        st.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), float(np.median(ts))
+for _ in range(3):
+    eng.ingest(pts, offsets, 0); eng.sync()
+k1 = timeit(lambda: eng.ingest_bev_only(pts, offsets))
+full = timeit(lambda: eng.ingest(pts, offsets, 0))
+bytes_ = B * N * 16
+print(f"B={B} K1 bev_scatter: min {k1[0]:.3f} ms median {k1[1]:.3f} ms -> {bytes_/k1[0]/1e6:.1f} GB/s, {B/k1[0]*1e3:.0f} scans/s")
+print(f"B={B} K1+K2 ingest : min {full[0]:.3f} ms median {full[1]:.3f} ms -> {bytes_/full[0]/1e6:.1f} GB/s, {B/full[0]*1e3:.0f} scans/s; K2 alone ~{full[0]-k1[0]:.3f} ms")
+h = eng.heads(0, B)
+print("status", np.unique(h["status"]), "views/level mean", h["n_views"].mean(0))

@@ -1,0 +1,120 @@
+"""GPU parity of the ingest path (BEV -> contours -> views -> keys -> BCI) against the CPU oracle, through the C-ABI.
+
+Bar (BASELINE.json north_star): bit-exact BEV cells, contour order, ContourView fields; retrieval keys bit-exact up to the
+documented libm caveat (device exp vs glibc exp differ by <= 1 ulp in double, which can flip the float rounding of one
+gaussPDF term with probability ~1e-8 per call; mismatches are COUNTED and bounded, never ignored)."""
+import numpy as np
+import pytest
+
+from contour_context_b200 import ctypes_defs as D
+from helpers import make_batch, ulp_diff, view_fields_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(built_lib):
+    from contour_context_b200.engine import Engine
+
+    e = Engine(scan_capacity=64, max_batch=16, max_points=16 * 131072)
+    yield e
+    e.close()
+
+
+def _oracle_scans(oracle, cfg, pts, offsets):
+    out = []
+    for b in range(len(offsets) - 1):
+        out.append(oracle.Scan(cfg, b).ingest(pts[offsets[b]:offsets[b + 1]]))
+    return out
+
+
+@pytest.mark.parametrize("n_pts", [120000, 30001])
+def test_bev_bit_exact(engine, oracle, n_pts):
+    pts, offsets = make_batch([3, 3, 4, 5], [0, 1, 0, 2], n_pts)
+    engine.ingest(pts, offsets, first_slot=0)
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        ob, orf, ocf = s.bev()
+        gb, grf, gcf = engine.bev(b)
+        assert gb.tobytes() == ob.tobytes(), f"scan {b}: bev heights differ"
+        assert grf.tobytes() == orf.tobytes() and gcf.tobytes() == ocf.tobytes(), f"scan {b}: pillar coords differ"
+
+
+def test_views_keys_bci(engine, oracle):
+    seeds, visits = [10, 10, 11, 12, 13, 13], [0, 1, 0, 0, 2, 3]
+    pts, offsets = make_batch(seeds, visits, 120000)
+    engine.ingest(pts, offsets, first_slot=8, int_ids=np.arange(100, 106))
+    heads = engine.heads(8, len(seeds))
+    key_ulp_bad = 0
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        oh = s.head()
+        gh = heads[b]
+        assert gh["status"] == 0
+        assert gh["int_id"] == 100 + b
+        assert np.array_equal(gh["n_views"], oh["n_views"]), (b, gh["n_views"], oh["n_views"])
+        assert np.array_equal(gh["layer_cell_cnt"], oh["layer_cell_cnt"])
+        assert gh["n_occupied"] == oh["n_occupied"]
+        assert np.array_equal(gh["n_ell"], oh["n_ell"])
+        gviews = engine.views(8 + b, gh)
+        for lev in range(D.NLEV):
+            ov = s.views(lev)
+            bad = view_fields_equal(gviews[lev], ov)
+            assert not bad, f"scan {b} level {lev}: view fields differ: {bad}"
+        # keys: bit-exact except for counted <= 2-ulp libm effects
+        gk, ok = gh["keys"], oh["keys"]
+        nan_g, nan_o = np.isnan(gk), np.isnan(ok)
+        assert np.array_equal(nan_g, nan_o)
+        d = ulp_diff(np.where(nan_g, 0, gk), np.where(nan_o, 0, ok))
+        assert d.max() <= 2, f"scan {b}: key differs by {d.max()} ulp"
+        key_ulp_bad += int((d > 0).sum())
+        # BCI: bitsets, neighbour identity and order, segments exact; r exact; theta within 1 ulp (atan2f libm caveat)
+        gb_, ob_ = gh["bcis"], oh["bcis"]
+        assert gb_["dist_bin"].tobytes() == ob_["dist_bin"].tobytes()
+        for f in ("n_nei", "n_seg", "piv_seq", "level", "seg"):
+            assert np.array_equal(gb_[f], ob_[f]), f
+        for f in ("level", "seq", "bit_pos"):
+            assert np.array_equal(gb_["nei"][f], ob_["nei"][f]), f
+        assert gb_["nei"]["r"].tobytes() == ob_["nei"]["r"].tobytes()
+        assert ulp_diff(gb_["nei"]["theta"], ob_["nei"]["theta"]).max() <= 1
+        assert abs(gh["gmm_auto_corr"] - oh["gmm_auto_corr"]) <= 1e-9 * abs(oh["gmm_auto_corr"])
+    # at most a handful of 1-ulp key entries over 6 scans x 360 key entries
+    assert key_ulp_bad <= 4, f"{key_ulp_bad} key entries differ from the oracle"
+
+
+def test_ragged_and_degenerate_inputs(engine, oracle):
+    """Ragged batch: different point counts per scan, an (almost) empty scan, points outside the BEV, NaNs, ties."""
+    rng = np.random.default_rng(7)
+    base, _ = make_batch([20], [0], 50000)
+    scans = [base[:50000], base[:1000], base[:17].copy(), base[:5000].copy(), base[:8000].copy()]
+    scans[2][:, :2] = 500.0                      # everything outside the square -> empty BEV
+    scans[3][::7, 0] = np.nan                    # NaN x dropped
+    scans[3][::11, 2] = np.nan                   # NaN z never stored
+    scans[4][:, 2] = np.round(scans[4][:, 2])    # many exact height ties -> first point in file order wins
+    pts = np.ascontiguousarray(np.concatenate(scans))
+    offsets = np.cumsum([0] + [len(s) for s in scans]).astype(np.int64)
+    engine.ingest(pts, offsets, first_slot=0)
+    heads = engine.heads(0, len(scans))
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        ob, orf, ocf = s.bev()
+        gb, grf, gcf = engine.bev(b)
+        assert gb.tobytes() == ob.tobytes() and grf.tobytes() == orf.tobytes() and gcf.tobytes() == ocf.tobytes(), b
+        oh = s.head()
+        assert np.array_equal(heads[b]["n_views"], oh["n_views"])
+        gviews = engine.views(b, heads[b])
+        for lev in range(D.NLEV):
+            assert not view_fields_equal(gviews[lev], s.views(lev)), (b, lev)
+        gk, ok = heads[b]["keys"], oh["keys"]
+        assert np.array_equal(np.isnan(gk), np.isnan(ok))
+        assert ulp_diff(np.nan_to_num(gk), np.nan_to_num(ok)).max() <= 2
+
+
+def test_device_resident_input_matches_host_input(engine):
+    import torch
+
+    pts, offsets = make_batch([30, 31], [0, 1], 60000)
+    engine.ingest(pts, offsets, first_slot=0)
+    h_host = engine.heads(0, 2).copy()
+    t = torch.from_numpy(pts).cuda()
+    engine.ingest(t, offsets, first_slot=2)
+    h_dev = engine.heads(2, 2)
+    for f in ("n_views", "layer_cell_cnt", "keys", "n_ell"):
+        assert h_host[f].tobytes() == h_dev[f].tobytes(), f
