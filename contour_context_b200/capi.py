@@ -48,6 +48,20 @@ def lib():
         L.c2g_query_async.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble)]
         L.c2g_query_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
         L.c2g_finish_from_scores.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), vp, vp, vp]
+        L.c2g_db_add_scans.argtypes = [vp, ip, ip, vp]
+        L.c2g_db_push_and_balance.argtypes = [vp, ip, C.c_double]
+        L.c2g_db_size.argtypes = [vp]
+        L.c2g_db_sync.argtypes = [vp]
+        L.c2g_db_layer_state.argtypes = [vp, ip, vp, vp, vp]
+        L.c2g_db_bucket_tree.argtypes = [vp, ip, ip, vp, vp, vp]
+        L.c2g_hostdb_create.restype = vp
+        L.c2g_hostdb_create.argtypes = [ip, C.c_double, C.c_double]
+        L.c2g_hostdb_free.argtypes = [vp]
+        L.c2g_hostdb_push_key.argtypes = [vp, ip, vp, C.c_double, ip, ip]
+        L.c2g_hostdb_balance.argtypes = [vp, ip, C.c_double]
+        L.c2g_hostdb_state.argtypes = [vp, ip, vp, vp, vp]
+        L.c2g_hostdb_tree.argtypes = [vp, ip, ip, vp, vp, vp]
+        L.c2g_debug_clocks.argtypes = [vp, vp]
         L.c2g_launch_count.restype = ll
         L.c2g_launch_count.argtypes = [vp]
         L.c2g_selftest_stdsort.argtypes = [vp, ip, ip]

@@ -1,11 +1,14 @@
 // c2g_api.cu — context + the extern "C" entry points declared in include/c2g.h.
 #include <cstdio>
 #include <cstring>
+#include <cstddef>
 #include <new>
+#include <vector>
 
 #include "../../include/c2g.h"
 #include "c2g_common.cuh"
 #include "c2g_ctx.cuh"
+#include "layer_db_host.h"
 #include "stdsort.cuh"
 
 // launchers implemented in the kernel translation units
@@ -14,7 +17,7 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
-                        cudaStream_t stream);
+                        cudaStream_t stream, long long *dbg);
 int c2g_query_alloc(c2g_ctx *ctx);
 void c2g_query_free(c2g_ctx *ctx);
 
@@ -137,12 +140,20 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) ctx->num_sms);
   ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
+  ALLOC(ctx->d_dbg, sizeof(long long) * 64);
 #undef ALLOC
   rc = c2g_query_alloc(ctx);
   if (rc) {
     c2g_destroy(ctx);
     return rc;
   }
+  ctx->hostdb = new (std::nothrow) C2gHostDB();
+  if (!ctx->hostdb) {
+    c2g_destroy(ctx);
+    return C2G_ERR_CAPACITY;
+  }
+  c2g_hostdb_init(*ctx->hostdb, db_cfg->n_q_levels, db_cfg->max_elapse, db_cfg->min_elapse);
+  ctx->db_dirty = 0;
   *out = ctx;
   return 0;
 }
@@ -152,6 +163,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   c2g_query_free(ctx);
+  delete ctx->hostdb;
   cudaFree(ctx->d_pts_stage);
   cudaFree(ctx->d_offsets);
   cudaFree(ctx->d_int_ids);
@@ -162,6 +174,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_presort);
   cudaFree(ctx->d_heads);
   cudaFree(ctx->d_views);
+  cudaFree(ctx->d_dbg);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
@@ -202,7 +215,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
     ids_dev = ctx->d_int_ids;
   }
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->num_sms, ctx->stream);
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -249,7 +262,134 @@ int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n) {
   return 0;
 }
 
+int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host) {
+  if (!ctx || !ts_host || n <= 0 || first_slot < 0 || first_slot + n > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gHostDB &db = *ctx->hostdb;
+  if (first_slot != db.n_scans) return C2G_ERR_STATE;  // gidx == all_bevs_.size() at the time of addScan
+  std::vector<float> keys((size_t) n * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM);
+  const size_t kbytes = sizeof(float) * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
+  C2G_CUDA_TRY(cudaMemcpy2DAsync(keys.data(), kbytes, (const char *) (ctx->d_heads + first_slot) + offsetof(c2g_scan_head, keys),
+                                 sizeof(c2g_scan_head), kbytes, (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    const float *sk = keys.data() + (size_t) i * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
+    for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+      const int lev = ctx->db.q_levels[ll];
+      for (int seq = 0; seq < ctx->P.cfg.piv_firsts; ++seq)
+        c2g_hostdb_push(db, ll, sk + ((size_t) lev * C2G_MAX_PIV + seq) * C2G_KEY_DIM, ts_host[i], first_slot + i, seq);
+    }
+    db.n_scans++;
+  }
+  ctx->db_dirty = 1;
+  return 0;
+}
+
+int c2g_db_push_and_balance(c2g_ctx *ctx, int seed, double ts) {
+  if (!ctx) return C2G_ERR_ARG;
+  c2g_hostdb_push_and_balance(*ctx->hostdb, seed, ts);
+  ctx->db_dirty = 1;
+  return 0;
+}
+
+int c2g_db_size(c2g_ctx *ctx) { return ctx ? ctx->hostdb->n_scans : C2G_ERR_ARG; }
+
+int c2g_db_sync(c2g_ctx *ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!ctx->db_dirty) return 0;
+  std::vector<float> keys;
+  std::vector<int> gidx;
+  std::vector<signed char> seq;
+  std::vector<unsigned char> bucket;
+  for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+    const C2gLayerHost &L = ctx->hostdb->layers[ll];
+    keys.clear();
+    gidx.clear();
+    seq.clear();
+    bucket.clear();
+    for (int b = 0; b < C2G_NUM_BUCKETS; ++b)
+      for (const C2gKeyRec &r : L.buckets[b].tree) {
+        keys.insert(keys.end(), r.k, r.k + C2G_KEY_DIM);
+        gidx.push_back(r.gidx);
+        seq.push_back((signed char) r.seq);
+        bucket.push_back((unsigned char) b);
+      }
+    int rc = c2g_db_set_layer(ctx, ll, (int) gidx.size(), keys.data(), gidx.data(), seq.data(), bucket.data(), L.ranges);
+    if (rc) return rc;
+  }
+  ctx->db_dirty = 0;
+  return 0;
+}
+
+int c2g_db_layer_state(c2g_ctx *ctx, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes) {
+  if (!ctx || ll < 0 || ll >= ctx->db.n_q_levels) return C2G_ERR_ARG;
+  const C2gLayerHost &L = ctx->hostdb->layers[ll];
+  for (int i = 0; i <= C2G_NUM_BUCKETS; ++i) bucket_ranges[i] = L.ranges[i];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
+    tree_sizes[i] = (int) L.buckets[i].tree.size();
+    buffer_sizes[i] = (int) L.buckets[i].buffer.size();
+  }
+  return 0;
+}
+
+int c2g_db_bucket_tree(c2g_ctx *ctx, int ll, int bucket, float *keys, int *gidx, int *seq) {
+  if (!ctx || ll < 0 || ll >= ctx->db.n_q_levels || bucket < 0 || bucket >= C2G_NUM_BUCKETS) return C2G_ERR_ARG;
+  const std::vector<C2gKeyRec> &t = ctx->hostdb->layers[ll].buckets[bucket].tree;
+  for (size_t i = 0; i < t.size(); ++i) {
+    for (int d = 0; d < C2G_KEY_DIM; ++d) keys[i * C2G_KEY_DIM + d] = t[i].k[d];
+    gidx[i] = t[i].gidx;
+    seq[i] = t[i].seq;
+  }
+  return 0;
+}
+
+/* stand-alone host LayerDB handles (no CUDA context needed): CPU tests of the rebalancing logic */
+void *c2g_hostdb_create(int n_layers, double max_elapse, double min_elapse) {
+  if (n_layers <= 0 || n_layers > C2G_NUM_Q_LEVELS_MAX) return nullptr;
+  C2gHostDB *db = new (std::nothrow) C2gHostDB();
+  if (db) c2g_hostdb_init(*db, n_layers, max_elapse, min_elapse);
+  return db;
+}
+void c2g_hostdb_free(void *h) { delete (C2gHostDB *) h; }
+int c2g_hostdb_push_key(void *h, int ll, const float *key, double ts, int gidx, int seq) {
+  if (!h || !key) return C2G_ERR_ARG;
+  c2g_hostdb_push(*(C2gHostDB *) h, ll, key, ts, gidx, seq);
+  return 0;
+}
+int c2g_hostdb_balance(void *h, int seed, double ts) {
+  if (!h) return C2G_ERR_ARG;
+  c2g_hostdb_push_and_balance(*(C2gHostDB *) h, seed, ts);
+  return 0;
+}
+int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes) {
+  if (!h) return C2G_ERR_ARG;
+  const C2gLayerHost &L = ((C2gHostDB *) h)->layers[ll];
+  for (int i = 0; i <= C2G_NUM_BUCKETS; ++i) bucket_ranges[i] = L.ranges[i];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
+    tree_sizes[i] = (int) L.buckets[i].tree.size();
+    buffer_sizes[i] = (int) L.buckets[i].buffer.size();
+  }
+  return 0;
+}
+int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq) {
+  if (!h) return C2G_ERR_ARG;
+  const std::vector<C2gKeyRec> &t = ((C2gHostDB *) h)->layers[ll].buckets[bucket].tree;
+  for (size_t i = 0; i < t.size(); ++i) {
+    for (int d = 0; d < C2G_KEY_DIM; ++d) keys[i * C2G_KEY_DIM + d] = t[i].k[d];
+    gidx[i] = t[i].gidx;
+    seq[i] = t[i].seq;
+  }
+  return 0;
+}
+
 long long c2g_launch_count(c2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+/* developer aid: per-phase clock64() stamps of CTA 0's first scan in the last contour kernel (64 values) */
+int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host) {
+  if (!ctx || !out_host) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 
 int c2g_selftest_stdsort(unsigned int *words, int n, int desc) {
   if (!words || n < 0) return C2G_ERR_ARG;

@@ -3,13 +3,15 @@
 #include "c2g_common.cuh"
 
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
-  float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans
+  float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans, bucket-major, tree order inside a bucket
   int *gidx;             // IndexOfKey::gidx
   signed char *seq;      // IndexOfKey::seq
-  unsigned char *bucket; // which TreeBucket the key lives in
   int n, cap;
+  int bucket_off[C2G_NUM_BUCKETS + 1];
   float ranges[C2G_NUM_BUCKETS + 1];
 };
+
+struct C2gHostDB;  // host-side LayerDB state (layer_db_host.h)
 
 struct c2g_ctx {
   int device, num_sms;
@@ -27,6 +29,7 @@ struct c2g_ctx {
   c2g_view *d_presort;
   c2g_scan_head *d_heads;
   c2g_view *d_views;
+  long long *d_dbg;
   const float *last_pts;
   int last_B;
   long long launches;
@@ -36,4 +39,6 @@ struct c2g_ctx {
   c2g_pair_score *d_scores;
   c2g_query_result *d_results;
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
+  C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
+  int db_dirty;            // device mirror older than the host state
 };

@@ -34,6 +34,7 @@ constexpr int NVL = 1024;       // significant components (area >= min_cont_cell
 constexpr int KEY_LIST_CAP = 400;  // cells of one key window that can lie inside the 9.99-cell radius
 constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
 constexpr int N_DIVS = 35;
+constexpr int WL_CAP = 256;
 
 struct TopView {  // what keys / BCI / GMM need from a sorted view
   float mean0, mean1, eig0, eig1;
@@ -55,13 +56,18 @@ struct Smem {
   int cnt_point[N_ANCH];
   int ncomp, nsig, status, n_occ;
   double red[K2_WARPS];
+  uint16_t wlist[K2_WARPS][WL_CAP];  // per-warp list of member cells of the component being walked
 };
 
 __device__ __forceinline__ uint32_t uf_find(volatile uint32_t *L, uint32_t c) {
-  uint32_t p = L[c] & 0xFFFFu;
+  uint32_t w = L[c];
+  uint32_t p = w & 0xFFFFu;
   while (p != c) {
+    const uint32_t gp = L[p] & 0xFFFFu;
+    if (gp != p) L[c] = (w & 0xFFFF0000u) | gp;  // path halving: any ancestor is a valid parent (links only go down)
     c = p;
-    p = L[c] & 0xFFFFu;
+    w = L[c];
+    p = w & 0xFFFFu;
   }
   return c;
 }
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
                int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
-               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views) {
+               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,6 +267,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     c2g_scan_head *head = heads + (first_slot + b);
     c2g_view *vout = views + (size_t) (first_slot + b) * C2G_VIEW_CAP;
 
+#define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0 && b == 0) dbg[i] = clock64(); } while (0)
+    C2G_DBG(0);
     // ---------------- phase A: decode the tile, gather the winner's continuous coordinates -------------------------
     if (tid == 0) {
       S.status = 0;
@@ -270,31 +278,47 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     {
       const float4 *p = pts + offsets[b];
       int occ = 0;
-      for (int c = tid; c < ncell; c += K2_THREADS) {
-        const c2g_cellkey k = tiles[cbase + c];
-        float h = -1000.0f, rf = -1.0f, cf = -1.0f;
-        uint8_t m = 0;
-        if (k != 0ull) {
-          h = c2g_from_orderable((uint32_t) (k >> 32));
-          const uint32_t idx = 0xFFFFFFFFu - (uint32_t) k;
-          const float2 xy = *reinterpret_cast<const float2 *>(p + idx);
-          // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
-          rf = (xy.x / cfg.reso_row + P.half_row_f) - 0.5f;
-          cf = (xy.y / cfg.reso_col + P.half_col_f) - 0.5f;
+      constexpr int PA = 6;  // cells per thread per batch: all tile loads, then all gathers, then the stores
+      for (int c0 = tid; c0 < ncell; c0 += K2_THREADS * PA) {
+        c2g_cellkey k[PA];
+        float2 xy[PA];
 #pragma unroll
-          for (int e = 0; e < C2G_NLEV; ++e) m |= (h > cfg.lv_grads[e]) ? (1u << e) : 0u;
-          occ++;
+        for (int u = 0; u < PA; ++u) {
+          const int c = c0 + u * K2_THREADS;
+          k[u] = c < ncell ? tiles[cbase + c] : 0ull;
         }
-        bev_h[cbase + c] = h;
-        bev_rf[cbase + c] = rf;
-        bev_cf[cbase + c] = cf;
-        S.msk[c] = m;
-        S.L[c] = 0u;
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+          xy[u] = make_float2(0.f, 0.f);
+          if (k[u] != 0ull) xy[u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+          const int c = c0 + u * K2_THREADS;
+          if (c >= ncell) continue;
+          float h = -1000.0f, rf = -1.0f, cf = -1.0f;
+          uint8_t m = 0;
+          if (k[u] != 0ull) {
+            h = c2g_from_orderable((uint32_t) (k[u] >> 32));
+            // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
+            rf = (xy[u].x / cfg.reso_row + P.half_row_f) - 0.5f;
+            cf = (xy[u].y / cfg.reso_col + P.half_col_f) - 0.5f;
+#pragma unroll
+            for (int e = 0; e < C2G_NLEV; ++e) m |= (h > cfg.lv_grads[e]) ? (1u << e) : 0u;
+            occ++;
+          }
+          bev_h[cbase + c] = h;
+          bev_rf[cbase + c] = rf;
+          bev_cf[cbase + c] = cf;
+          S.msk[c] = m;
+          S.L[c] = 0u;
+        }
       }
       if (occ) atomicAdd(&S.n_occ, occ);
     }
     __syncthreads();
 
+    C2G_DBG(1);
     // ---------------- phase B: levels ------------------------------------------------------------------------------
     int total_views = 0;
     for (int lev = 0; lev < C2G_NLEV; ++lev) {
@@ -303,30 +327,54 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.ncomp = 0;
         S.nsig = 0;
       }
-      // B1 init label words (keep the upper half = rank of the enclosing component of the previous level)
-      for (int c = tid; c < ncell; c += K2_THREADS)
-        if (S.msk[c] & bit) S.L[c] = (S.L[c] & 0xFFFF0000u) | (uint32_t) c;
-      __syncthreads();
-      // B2 unions with the 4 already-visited neighbours of the 8-neighbourhood
-      for (int c = tid; c < ncell; c += K2_THREADS) {
-        if (!(S.msk[c] & bit)) continue;
-        const int r = c / ncol, cc = c - r * ncol;
-        if (cc > 0 && (S.msk[c - 1] & bit)) uf_union(S.L, c, c - 1);
-        if (r > 0) {
-          const int up = c - ncol;
-          if (S.msk[up] & bit) uf_union(S.L, c, up);
-          if (cc > 0 && (S.msk[up - 1] & bit)) uf_union(S.L, c, up - 1);
-          if (cc + 1 < ncol && (S.msk[up + 1] & bit)) uf_union(S.L, c, up + 1);
+      // B1 init label words (keep the upper half = rank of the enclosing component of the previous level). Every thread
+      // owns a contiguous chunk of cells; a horizontal run inside the chunk is linked straight to its first cell.
+      const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
+      const int cb0 = tid * chunk, cb1 = min(ncell, cb0 + chunk);
+      {
+        int runstart = -1;
+        for (int c = cb0; c < cb1; ++c) {
+          if (S.msk[c] & bit) {
+            if (runstart < 0 || (c % ncol) == 0) runstart = c;
+            S.L[c] = (S.L[c] & 0xFFFF0000u) | (uint32_t) runstart;
+          } else
+            runstart = -1;
         }
       }
       __syncthreads();
+      C2G_DBG(10 + lev * 8 + 0);
+      // B2 unions. W: only where the run was cut by a chunk boundary. Row above: N if set (NW/NE then belong to N's run);
+      // otherwise NW and NE. A cell whose W neighbour is set skips what W already did (its N/NE are this cell's NW/N).
+      for (int c = cb0; c < cb1; ++c) {
+        if (!(S.msk[c] & bit)) continue;
+        const int r = c / ncol, cc = c - r * ncol;
+        const bool w_set = cc > 0 && (S.msk[c - 1] & bit);
+        if (w_set && c == cb0) uf_union(S.L, c, c - 1);
+        if (r > 0) {
+          const int up = c - ncol;
+          const bool n_set = (S.msk[up] & bit) != 0;
+          const bool ne_set = cc + 1 < ncol && (S.msk[up + 1] & bit);
+          if (!w_set) {
+            if (n_set)
+              uf_union(S.L, c, up);
+            else {
+              if (cc > 0 && (S.msk[up - 1] & bit)) uf_union(S.L, c, up - 1);
+              if (ne_set) uf_union(S.L, c, up + 1);
+            }
+          } else if (!n_set && ne_set)
+            uf_union(S.L, c, up + 1);
+        }
+      }
+      __syncthreads();
+      C2G_DBG(10 + lev * 8 + 1);
       // B3 flatten
-      for (int c = tid; c < ncell; c += K2_THREADS)
+      for (int c = cb0; c < cb1; ++c)
         if (S.msk[c] & bit) {
           const uint32_t root = uf_find(S.L, c);
           S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
         }
       __syncthreads();
+      C2G_DBG(10 + lev * 8 + 2);
       // B4 roots -> table slots
       for (int c = tid; c < ncell; c += K2_THREADS)
         if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) {
@@ -348,10 +396,10 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           S.L[c] = (S.L[c] & 0xFFFF0000u) | 0x8000u | (uint32_t) slot;
         }
       __syncthreads();
+      C2G_DBG(10 + lev * 8 + 3);
       // B5 per-component area / bbox / first-block key / last pixel, aggregated over horizontal runs per thread chunk
       {
-        const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
-        const int c0 = tid * chunk, c1 = min(ncell, c0 + chunk);
+        const int c0 = cb0, c1 = cb1;
         int cur = -1, run_r = 0, run_c0 = 0, run_c1 = 0;
         for (int c = c0; c <= c1; ++c) {
           int slot = -1, r = 0, cc = 0;
@@ -381,6 +429,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         }
       }
       __syncthreads();
+      C2G_DBG(10 + lev * 8 + 4);
       // B6 significant components -> DFS order rank
       const int ncomp = min(S.ncomp, NC);
       for (int s = tid; s < ncomp; s += K2_THREADS)
@@ -412,6 +461,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.n_views[lev] = nsig;
         S.view_off[lev] = total_views;
       }
+      C2G_DBG(10 + lev * 8 + 5);
       // B7 moments in bbox-raster order + calcStatVals: one warp per component, all lanes carry the same accumulators
       for (int rk = warp; rk < nsig; rk += K2_WARPS) {
         const int s = S.order[rk];
@@ -421,36 +471,57 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         m.cnt = 0;
         m.s0 = m.s1 = m.t00 = m.t01 = m.t11 = m.q0 = m.q1 = 0.0;
         m.vol3 = 0.0f;
+        uint16_t *wl = S.wlist[warp];
+        int nlist = 0;
         for (int base = 0; base < total; base += 32) {
+          // membership needs shared memory only; member cells are appended in bbox-raster order
           const int i = base + lane;
           bool member = false;
-          float h = 0.f, rf = 0.f, cf = 0.f;
+          int c = 0;
           if (i < total) {
-            const int rr = r0 + i / w, cc = c0 + i % w;
-            const int c = rr * ncol + cc;
-            if ((S.msk[c] & bit) && slot_of(S.L, c) == s) {
-              member = true;
-              h = hg[c];
-              rf = rfg[c];
-              cf = cfp[c];
-            }
+            c = (r0 + i / w) * ncol + (c0 + i % w);
+            member = (S.msk[c] & bit) && slot_of(S.L, c) == s;
           }
-          unsigned bal = __ballot_sync(0xFFFFFFFFu, member);
-          while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float hh = __shfl_sync(0xFFFFFFFFu, h, src);
-            const double v0 = (double) __shfl_sync(0xFFFFFFFFu, rf, src);
-            const double v1 = (double) __shfl_sync(0xFFFFFFFFu, cf, src);
-            m.cnt += 1;
-            m.s0 += v0;
-            m.s1 += v1;
-            m.t00 += v0 * v0;
-            m.t01 += v0 * v1;
-            m.t11 += v1 * v1;
-            m.vol3 += hh;
-            m.q0 += (double) hh * v0;
-            m.q1 += (double) hh * v1;
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, member);
+          if (member) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = (uint16_t) c;
+          nlist += __popc(bal);
+          if (nlist > WL_CAP - 32 || base + 32 >= total) {
+            __syncwarp();
+            // flush: 4 groups of 32 cells in flight from L2, then strictly sequential accumulation in list order
+            for (int g = 0; g < nlist; g += 128) {
+              float hv[4], rv[4], cv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = g + u * 32 + lane;
+                hv[u] = rv[u] = cv[u] = 0.f;
+                if (j < nlist) {
+                  const int cc = wl[j];
+                  hv[u] = hg[cc];
+                  rv[u] = rfg[cc];
+                  cv[u] = cfp[cc];
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int cntu = min(32, nlist - (g + u * 32));
+                for (int src = 0; src < cntu; ++src) {
+                  const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
+                  const double v0 = (double) __shfl_sync(0xFFFFFFFFu, rv[u], src);
+                  const double v1 = (double) __shfl_sync(0xFFFFFFFFu, cv[u], src);
+                  m.cnt += 1;
+                  m.s0 += v0;
+                  m.s1 += v1;
+                  m.t00 += v0 * v0;
+                  m.t01 += v0 * v1;
+                  m.t11 += v1 * v1;
+                  m.vol3 += hh;
+                  m.q0 += (double) hh * v0;
+                  m.q1 += (double) hh * v1;
+                }
+              }
+            }
+            __syncwarp();
+            nlist = 0;
           }
         }
         if (lane == 0) {
@@ -461,6 +532,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           S.sortbuf[total_views + rk] = ((uint32_t) m.cnt << 16) | (uint32_t) rk;
         }
       }
+      C2G_DBG(10 + lev * 8 + 6);
       // B8 hand the ranks down: upper half of every foreground word = rank of its component (0xFFFF if insignificant)
       for (int i = tid; i < nsig; i += K2_THREADS) {
         const int s = S.order[i];
@@ -479,15 +551,17 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       __syncthreads();
     }
 
+    C2G_DBG(2);
     // ---------------- phase C: per-level std::sort replay (cell_cnt descending), sorted views to the arena ----------
-    if (tid < C2G_NLEV) {
-      uint32_t *first = S.sortbuf + S.view_off[tid];
-      c2g_sort::std_sort(first, (long) S.n_views[tid], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
+    if (lane == 0 && warp < C2G_NLEV) {  // one warp per level: the six serial replays run on different schedulers
+      uint32_t *first = S.sortbuf + S.view_off[warp];
+      c2g_sort::std_sort(first, (long) S.n_views[warp], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
       int sum = 0;
-      for (int i = 0; i < S.n_views[tid]; ++i) sum += (int) (first[i] >> 16);
-      S.layer_cnt[tid] = sum;
+      for (int i = 0; i < S.n_views[warp]; ++i) sum += (int) (first[i] >> 16);
+      S.layer_cnt[warp] = sum;
     }
     __syncthreads();
+    C2G_DBG(3);
     {
       // copy 80-byte records as 20 x 4-byte words: sorted position j of level l <- presort index (sortbuf & 0xFFFF)
       const uint32_t *src = reinterpret_cast<const uint32_t *>(presort);
@@ -519,6 +593,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     }
     __syncthreads();
 
+    C2G_DBG(4);
     // ---------------- phase D: retrieval keys (contour_mng.h:693-830) ------------------------------------------------
     // D1: per anchor, ordered list of the window cells that contribute: (dist, higher_cnt). One warp per anchor.
     float *klist_dist = reinterpret_cast<float *>(S.L);                               // [N_ANCH][KEY_LIST_CAP]
@@ -569,6 +644,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       if (lane == 0) S.cnt_point[a] = valid ? cnt : -1;
     }
     __syncthreads();
+    C2G_DBG(5);
     // D2: one thread per (anchor, division): sequential float accumulation in raster order
     {
       const float div_len = cfg.roi_radius / (float) ((C2G_KEY_DIM - 3) * 5);
@@ -618,10 +694,11 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       head->keys[ll][seq][kd] = val;
     }
 
+    C2G_DBG(6);
     // ---------------- phase E: BCIs (contour_mng.h:848-883), one thread per anchor ---------------------------------
-    if (tid < N_ANCH) {
-      const int a = tid, ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
-      if (seq < piv) {
+    for (int a = warp; a < N_ANCH; a += K2_WARPS) {
+      const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
+      if (lane == 0 && seq < piv) {
         c2g_bci &bci = head->bcis[ll][seq];
         uint64_t bins[4] = {0, 0, 0, 0};
         c2g_relpt nei[C2G_MAX_NEI];
@@ -679,6 +756,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
     }
 
+    C2G_DBG(7);
     // ---------------- phase F: scan-only GMM terms (correlation.h:49-82,102-119) -----------------------------------
     __shared__ int n_ell_s[C2G_NUM_BIN_LAYERS];
     if (tid < C2G_NUM_BIN_LAYERS) {
@@ -715,6 +793,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     if (lane == 0) S.red[warp] = acc;
     __syncthreads();
+    C2G_DBG(8);
     // ---------------- phase G: head ------------------------------------------------------------------------------------
     if (tid == 0) {
       double tot = 0.0;
@@ -732,6 +811,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       head->gmm_auto_corr = tot;
     }
     __syncthreads();
+    C2G_DBG(9);
   }
 }
 
@@ -742,7 +822,7 @@ size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, long long *dbg) {
   static bool attr_set = false;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -751,7 +831,7 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views);
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

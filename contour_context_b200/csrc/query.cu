@@ -1,15 +1,912 @@
-// query.cu — kNN over the mirrored key tables, hint scoring cascade, candidate replay, GMM-L2 (placeholder until the
-// kernels land; the entry points report C2G_ERR_STATE).
+// query.cu — the database/query half of the hot path on the device.
+//
+//   knn_kernel     LayerDB::layerKNNSearch + TreeBucket::knnSearch        src/cont2/contour_db.cpp:319-403
+//                  (+ dist_ub of ContourDB::queryRangedKNN, include/cont2/contour_db.h:733-749; nanoflann L2 metric order
+//                  thirdparty/nanoflann.hpp:428-462) as a flat scan over the device mirror of the KD-tree contents.
+//   score_kernel   CandidateManager::checkCandWithHint up to addProposal   include/cont2/contour_db.h:374-437
+//                    ContourView::checkSim                                 include/cont2/contour.h:278-329
+//                    BCI::checkConstellSim                                 include/cont2/contour_mng.h:288-388
+//                    ContourManager::checkConstellCorrespSim               include/cont2/contour_mng.h:1124-1242
+//                    ContourManager::getTFFromConstell                     include/cont2/contour_mng.h:1251-1277
+//   finish_kernel  CandidatePoseData::addProposal replay (:286-338), tidyUpCandidates (:494-596) with the GMM-L2 initial
+//                  correlation (include/cont2/correlation.h:42-202) and fineOptimize's ordering (:604-648, no Ceres step).
+//
+// With DYNAMIC_THRES=0 (CMakeLists.txt:21) every hint check is independent, so hints are scored in parallel (one warp
+// each) and only the small order-dependent proposal merge is replayed sequentially per query scan, in reference order
+// (q-level, query seq, ascending key distance).
 #include "../../include/c2g.h"
 #include "c2g_ctx.cuh"
+#include "stdsort.cuh"
 
-int c2g_query_alloc(c2g_ctx *ctx) { (void) ctx; return 0; }
-void c2g_query_free(c2g_ctx *ctx) { (void) ctx; }
+namespace {
+
+constexpr int QK_WARPS = 8;           // warps per CTA in the kNN kernel
+constexpr int SC_WARPS = 4;           // warps per CTA in the score kernel (7.2 KB of scratch per warp)
+constexpr int MAX_POT_PAIRS = 400;    // 4 layers x 10 x 10 neighbour pairs
+constexpr double C2G_PI = 3.14159265358979323846;
+
+struct LayerDev {
+  const float *keys_t;  // [KEY_DIM][cap]
+  const int *gidx;
+  const signed char *seq;
+  int cap;
+  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1])
+  float ranges[C2G_NUM_BUCKETS + 1];
+};
+struct QueryParams {
+  LayerDev layer[C2G_NUM_Q_LEVELS_MAX];
+  int n_q_levels, q_levels[C2G_NUM_Q_LEVELS_MAX];
+  int nnk, piv;
+  c2g_sim_config sim;
+  c2g_score_ensemble lb;
+  int n_row, n_col;
+};
+
+__device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
+  return views[(size_t) slot * C2G_VIEW_CAP + heads[slot].view_off[level] + seq];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// kNN: one warp per query key. Lanes stride over the keys of the visited buckets; the running top-k is kept sorted
+// across the warp's registers (slot j lives in lane j % 32, register j / 32) and updated by warp-cooperative insertion.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QK_WARPS * 32)
+knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, QueryParams Q, c2g_hint *__restrict__ hints) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = blockIdx.x * QK_WARPS + (threadIdx.x >> 5);
+  const int keys_per_scan = Q.n_q_levels * C2G_MAX_PIV;
+  if (wglobal >= B * keys_per_scan) return;
+  // layer-major ordering of the work so that the warps of one CTA scan the same table
+  const int ll = wglobal / (B * C2G_MAX_PIV);
+  const int rem = wglobal - ll * (B * C2G_MAX_PIV);
+  const int q = rem / C2G_MAX_PIV, seq = rem - q * C2G_MAX_PIV;
+  const int level = Q.q_levels[ll];
+  c2g_hint *out = hints + ((size_t) (q * Q.n_q_levels + ll) * C2G_MAX_PIV + seq) * Q.nnk;
+  const float *qk = heads[first_slot + q].keys[level][seq];
+  float key[C2G_KEY_DIM];
+  float ksum = 0.0f;
+#pragma unroll
+  for (int d = 0; d < C2G_KEY_DIM; ++d) {
+    key[d] = qk[d];
+    ksum += key[d];
+  }
+  float bd[2] = {3.0e38f, 3.0e38f};  // top-k distances (sorted ascending across slots), empty = +big
+  int bi[2] = {-1, -1};
+  int count = 0;
+  const int K = Q.nnk;  // <= 64
+  if (seq < Q.piv && ksum != 0.0f) {  // `q_keys[seq].sum() != 0` (contour_db.h:726); NaN keys search and find nothing
+    // dist_ub (contour_db.h:733-749): bounds stored as float, products with double literals evaluated in double
+    const float b00 = (float) ((double) key[0] * 0.8), b01 = (float) ((double) key[0] / 0.8);
+    const float b10 = (float) ((double) key[1] * 0.8), b11 = (float) ((double) key[1] / 0.8);
+    const float b20 = (float) (((double) key[2] * 0.8) * 0.75), b21 = (float) ((double) key[2] / (0.8 * 0.75));
+    const float dist_ub = fmaxf((key[0] - b00) * (key[0] - b00), (key[0] - b01) * (key[0] - b01)) +
+                          fmaxf((key[1] - b10) * (key[1] - b10), (key[1] - b11) * (key[1] - b11)) +
+                          fmaxf((key[2] - b20) * (key[2] - b20), (key[2] - b21) * (key[2] - b21));
+    const LayerDev &T = Q.layer[ll];
+    int mid = 0;
+    for (int i = 0; i < C2G_NUM_BUCKETS; ++i)
+      if (T.ranges[i] <= key[0] && T.ranges[i + 1] > key[0]) {
+        mid = i;
+        break;
+      }
+    // visited set of layerKNNSearch's else-if chain: {mid, mid-1, .., 0} and {mid+i : i > mid, mid+i < 6}
+    unsigned visit = 0;
+    for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
+      if (i == 0)
+        visit |= 1u << mid;
+      else if (mid - i >= 0)
+        visit |= 1u << (mid - i);
+      else if (mid + i < C2G_NUM_BUCKETS)
+        visit |= 1u << (mid + i);
+    }
+    float thr = dist_ub;  // strict `dist < worst` (nanoflann.hpp:1575); NaN dist_ub admits nothing
+    for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
+      if (!((visit >> bk) & 1u)) continue;
+      const int beg = T.bucket_off[bk], end = T.bucket_off[bk + 1];
+      for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        float dist = 3.0e38f;
+        if (i < end) {
+          float df[C2G_KEY_DIM];
+#pragma unroll
+          for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
+          // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
+          float r = 0.0f;
+          r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
+          r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
+          r += df[8] * df[8];
+          r += df[9] * df[9];
+          dist = r;
+        }
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, i < end && dist < thr);
+        while (cand) {
+          const int src = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
+          const int ni = base + src;
+          if (!(nd < thr)) continue;  // threshold may have tightened since the ballot
+          // position = number of kept entries with distance <= nd (equal distances keep the earlier index first)
+          const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] <= nd);
+          const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] <= nd);
+          const int pos = __popc(le0) + __popc(le1);
+          // shift slots [pos, K-1) up by one: slot j takes slot j-1
+          const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
+          const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
+          const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
+          const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31);
+          const int j0 = lane, j1 = lane + 32;
+          if (j1 > pos) {
+            bd[1] = (lane == 0) ? last0 : up1;
+            bi[1] = (lane == 0) ? lasti0 : ui1;
+          }
+          if (j0 > pos) {
+            bd[0] = up0;
+            bi[0] = ui0;
+          }
+          if (j0 == pos) {
+            bd[0] = nd;
+            bi[0] = ni;
+          }
+          if (j1 == pos) {
+            bd[1] = nd;
+            bi[1] = ni;
+          }
+          if (count < K) ++count;
+          if (count == K) {  // threshold = K-th best
+            const int ks = K - 1;
+            thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
+          }
+        }
+      }
+    }
+    // slots >= K may hold spill-over entries; they are never emitted
+  }
+  const int level8 = level;
+  for (int j = lane; j < Q.nnk; j += 32) {
+    c2g_hint h;
+    h.q_idx = q;
+    h.cand_gidx = -1;
+    h.level = (int8_t) level8;
+    h.cand_seq = 0;
+    h.q_seq = (int8_t) seq;
+    h.q_level_idx = (int8_t) ll;
+    h.dist_sq = 0.0f;
+    const float dj = (j < 32) ? bd[0] : bd[1];
+    const int ij = (j < 32) ? bi[0] : bi[1];
+    // (j & 31) == lane by construction of the loop
+    if (j < count && ij >= 0) {
+      h.cand_gidx = Q.layer[ll].gidx[ij];
+      h.cand_seq = Q.layer[ll].seq[ij];
+      h.dist_sq = dj;
+    }
+    out[j] = h;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Hint scoring
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool diff_perc_f(float a, float b, float perc) { return fabsf((a - b) / fmaxf(a, b)) > perc; }
+__device__ __forceinline__ bool diff_delt_f(float a, float b, float delta) { return fabsf(a - b) > delta; }
+
+__device__ bool check_sim(const c2g_view &s, const c2g_view &t, const c2g_sim_config &th) {
+  const float sc = (float) s.cell_cnt, tc = (float) t.cell_cnt;
+  if (diff_perc_f(sc, tc, th.tp_cell_cnt) && diff_delt_f(sc, tc, th.ta_cell_cnt)) return false;
+  if ((double) fmaxf(s.eig_vals[1], t.eig_vals[1]) > 2.0 && diff_perc_f(sqrtf(s.eig_vals[1]), sqrtf(t.eig_vals[1]), th.tp_eigval)) return false;
+  if ((double) fmaxf(s.eig_vals[0], t.eig_vals[0]) > 2.0 && diff_perc_f(sqrtf(s.eig_vals[0]), sqrtf(t.eig_vals[0]), th.tp_eigval)) return false;
+  if (max((int) s.cell_cnt, (int) t.cell_cnt) > 15 && diff_delt_f(s.vol3_mean, t.vol3_mean, th.ta_h_bar)) return false;
+  const float sx = s.com[0] - s.pos_mean[0], sy = s.com[1] - s.pos_mean[1];
+  const float tx = t.com[0] - t.pos_mean[0], ty = t.com[1] - t.pos_mean[1];
+  const float r1 = sqrtf(sx * sx + sy * sy), r2 = sqrtf(tx * tx + ty * ty);
+  if (diff_delt_f(r1, r2, th.ta_rcom) && diff_perc_f(r1, r2, th.tp_rcom)) return false;
+  return true;
+}
+
+struct PotPair {
+  float orie_diff;
+  int8_t seq_src, seq_tgt, level, pad;
+};
+struct CPairD {
+  int8_t level, seq_src, seq_tgt;
+};
+
+struct ScoreScratch {
+  PotPair pot[MAX_POT_PAIRS];
+  uint32_t ord[MAX_POT_PAIRS];  // sort permutation (indices into pot)
+  CPairD c1[MAX_POT_PAIRS + 1];
+  CPairD c2[MAX_POT_PAIRS + 1];
+};
+
+__device__ __forceinline__ float clamp_ang_f(float ang) {  // clampAng<float>: double arithmetic, stored to float
+  return (float) ((double) ang - floor(((double) ang + C2G_PI) / (2 * C2G_PI)) * 2 * C2G_PI);
+}
+__device__ __forceinline__ void normalized2(float x, float y, float &ox, float &oy) {  // Eigen normalized()
+  const float n2 = x * x + y * y;
+  if (n2 > 0.0f) {
+    const float n = sqrtf(n2);
+    ox = x / n;
+    oy = y / n;
+  } else {
+    ox = x;
+    oy = y;
+  }
+}
+
+// lane 0 of the warp runs the sequential cascade; `sc` is the warp's shared scratch
+__device__ void score_hint(const c2g_scan_head *heads, const c2g_view *views, int q_slot, const c2g_hint &hint, const QueryParams &Q,
+                           ScoreScratch &sc, c2g_pair_score &rec) {
+  const int cand = hint.cand_gidx, level = hint.level, cseq = hint.cand_seq, qseq = hint.q_seq;
+  // (1/4) anchor similarity
+  if (!check_sim(view_at(heads, views, cand, level, cseq), view_at(heads, views, q_slot, level, qseq), Q.sim)) {
+    rec.passed = 0;
+    return;
+  }
+  // (2/4) BCI::checkConstellSim(src = candidate, tgt = query)
+  const c2g_bci &src = heads[cand].bcis[level][cseq];
+  const c2g_bci &tgt = heads[q_slot].bcis[level][qseq];
+  int ov1 = 0, ov2 = 0, ov3 = 0;
+  {
+    unsigned long long s4[4], t4[4];
+    for (int i = 0; i < 4; ++i) {
+      s4[i] = src.dist_bin[i];
+      t4[i] = tgt.dist_bin[i];
+    }
+    for (int i = 0; i < 4; ++i) {
+      const unsigned long long sl = (s4[i] << 1) | (i > 0 ? (s4[i - 1] >> 63) : 0ull);
+      const unsigned long long sr = (s4[i] >> 1) | (i < 3 ? (s4[i + 1] << 63) : 0ull);
+      ov1 += __popcll(s4[i] & t4[i]);
+      ov2 += __popcll(sl & t4[i]);
+      ov3 += __popcll(sr & t4[i]);
+    }
+  }
+  rec.constell[0] = ov1 + ov2 + ov3;
+  rec.constell[1] = max(ov1, max(ov2, ov3));
+  rec.constell[2] = 0;
+  if (!(rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one)) {
+    rec.passed = -1;
+    return;
+  }
+  int npot = 0;
+  {
+    const int n_sseg = src.n_seg, n_tseg = tgt.n_seg;
+    int p11 = 0, p12;
+    for (int p2 = 0; p2 < n_tseg - 1; p2++) {
+      const int tb = tgt.nei[tgt.seg[p2]].bit_pos;
+      while (p11 < n_sseg - 1 && src.nei[src.seg[p11]].bit_pos < tb - 1) p11++;
+      p12 = p11;
+      while (p12 < n_sseg - 1 && src.nei[src.seg[p12]].bit_pos <= tb + 1) p12++;
+      for (int i = tgt.seg[p2]; i < tgt.seg[p2 + 1]; i++)
+        for (int j = src.seg[p11]; j < src.seg[p12]; j++) {
+          if (npot < MAX_POT_PAIRS) {
+            PotPair pp;
+            pp.orie_diff = clamp_ang_f(tgt.nei[i].theta - src.nei[j].theta);
+            pp.seq_src = src.nei[j].seq;
+            pp.seq_tgt = tgt.nei[i].seq;
+            pp.level = src.nei[j].level;
+            pp.pad = 0;
+            sc.pot[npot] = pp;
+            sc.ord[npot] = (uint32_t) npot;
+            ++npot;
+          }
+        }
+    }
+  }
+  // std::sort by orie_diff (contour_mng.h:340-342): sort the index permutation with the same comparator
+  {
+    const PotPair *pot = sc.pot;
+    c2g_sort::std_sort(sc.ord, (long) npot, [pot](uint32_t a, uint32_t b) { return pot[a].orie_diff < pot[b].orie_diff; });
+  }
+  int longest = 1, longest_beg = 0;
+  {
+    const float angular_range = (float) (C2G_PI / 16);
+    int p1 = 0, p2 = 0;
+    const int pot_sz = npot;
+    while (p1 < pot_sz) {
+      const float dd = sc.pot[sc.ord[p2 % pot_sz]].orie_diff - sc.pot[sc.ord[p1]].orie_diff;
+      if ((double) dd + 2 * C2G_PI * (double) (p2 / pot_sz) > (double) angular_range)
+        p1++;
+      else {
+        if (p2 - p1 + 1 > longest) {
+          longest = p2 - p1 + 1;
+          longest_beg = p1;
+        }
+        p2++;
+      }
+    }
+  }
+  rec.constell[2] = longest;
+  if (longest < Q.lb.i_in_ang_rng) {
+    rec.passed = -1;
+    return;
+  }
+  int n1 = 0;
+  for (int i = longest_beg; i < longest + longest_beg; i++) {
+    const PotPair &pp = sc.pot[sc.ord[i % npot]];
+    sc.c1[n1].level = pp.level;
+    sc.c1[n1].seq_src = pp.seq_src;
+    sc.c1[n1].seq_tgt = pp.seq_tgt;
+    ++n1;
+  }
+  sc.c1[n1].level = src.level;
+  sc.c1[n1].seq_src = src.piv_seq;
+  sc.c1[n1].seq_tgt = tgt.piv_seq;
+  ++n1;
+  // (3/4) checkConstellCorrespSim
+  int n2 = 0;
+  for (int i = 0; i < n1; ++i) {
+    const CPairD pr = sc.c1[i];
+    if (check_sim(view_at(heads, views, cand, pr.level, pr.seq_src), view_at(heads, views, q_slot, pr.level, pr.seq_tgt), Q.sim))
+      sc.c2[n2++] = pr;
+  }
+  rec.pairwise[0] = n2;
+  rec.pairwise[1] = 0;
+  if (n2 < Q.lb.i_indiv_sim) {
+    rec.passed = -2;
+    return;
+  }
+  float ssx = 0.f, ssy = 0.f, stx = 0.f, sty = 0.f;
+  for (int i = 1; i < min(n2, 10); i++)
+    for (int j = 0; j < i; j++) {
+      const float *mi = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
+      const float *mj = view_at(heads, views, cand, sc.c2[j].level, sc.c2[j].seq_src).pos_mean;
+      const float cx = mi[0] - mj[0], cy = mi[1] - mj[1];
+      if (sqrtf(cx * cx + cy * cy) > sqrtf(ssx * ssx + ssy * ssy)) {
+        normalized2(cx, cy, ssx, ssy);
+        const float *ti = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
+        const float *tj = view_at(heads, views, q_slot, sc.c2[j].level, sc.c2[j].seq_tgt).pos_mean;
+        normalized2(ti[0] - tj[0], ti[1] - tj[1], stx, sty);
+      }
+    }
+  int num_sim = n2;
+  for (int i = 0; i < num_sim;) {
+    const c2g_view &sc1 = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src);
+    const c2g_view &tc1 = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt);
+    if (sc1.ecc_feat && tc1.ecc_feat) {
+      const float theta_s = acosf(ssx * sc1.eig_vecs[2] + ssy * sc1.eig_vecs[3]);
+      const float theta_t = acosf(stx * tc1.eig_vecs[2] + sty * tc1.eig_vecs[3]);
+      const float pi6 = (float) (C2G_PI / 6);
+      if (diff_delt_f(theta_s, theta_t, pi6) && diff_delt_f((float) (C2G_PI - (double) theta_s), theta_t, pi6)) {
+        const CPairD tmp = sc.c2[i];
+        sc.c2[i] = sc.c2[num_sim - 1];
+        sc.c2[num_sim - 1] = tmp;
+        num_sim--;
+        continue;
+      }
+    }
+    i++;
+  }
+  n2 = num_sim;
+  rec.pairwise[1] = n2;
+  if (n2 < Q.lb.i_orie_sim) {
+    rec.passed = -2;
+    return;
+  }
+  // getTFFromConstell: 2-D Umeyama without scaling, closed form (double)
+  {
+    const double inv_n = 1.0 / (double) n2;
+    double sm0 = 0, sm1 = 0, dm0 = 0, dm1 = 0;
+    for (int i = 0; i < n2; ++i) {
+      const float *ps = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
+      const float *pt = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
+      sm0 += (double) ps[0];
+      sm1 += (double) ps[1];
+      dm0 += (double) pt[0];
+      dm1 += (double) pt[1];
+    }
+    sm0 *= inv_n;
+    sm1 *= inv_n;
+    dm0 *= inv_n;
+    dm1 *= inv_n;
+    double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+    for (int i = 0; i < n2; ++i) {
+      const float *ps = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
+      const float *pt = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
+      const double sx = (double) ps[0] - sm0, sy = (double) ps[1] - sm1;
+      const double dx = (double) pt[0] - dm0, dy = (double) pt[1] - dm1;
+      s00 += dx * sx;
+      s01 += dx * sy;
+      s10 += dy * sx;
+      s11 += dy * sy;
+    }
+    s00 *= inv_n;
+    s01 *= inv_n;
+    s10 *= inv_n;
+    s11 *= inv_n;
+    const double ang0 = atan2(s10 - s01, s00 + s11);
+    const double c0 = cos(ang0), s0 = sin(ang0);
+    const double tx = dm0 - (c0 * sm0 - s0 * sm1);
+    const double ty = dm1 - (s0 * sm0 + c0 * sm1);
+    const double ang = atan2(s0, c0);
+    rec.T[0] = cos(ang);
+    rec.T[1] = sin(ang);
+    rec.T[2] = tx;
+    rec.T[3] = ty;
+  }
+  rec.passed = 1;
+  rec.n_pairs = n2;
+  for (int i = 0; i < n2; ++i) {
+    const int bit = (sc.c2[i].level - 1) * 100 + sc.c2[i].seq_src * 10 + sc.c2[i].seq_tgt;
+    rec.pair_bits[bit >> 6] |= 1ull << (bit & 63);
+  }
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
+score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, long long n_hints,
+             QueryParams Q, const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores) {
+  __shared__ ScoreScratch scratch[SC_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long hid = (long long) blockIdx.x * SC_WARPS + w;
+  if (hid >= n_hints) return;
+  if (lane == 0) {
+    const c2g_hint h = hints[hid];
+    c2g_pair_score rec;
+    rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
+    rec.pairwise[0] = rec.pairwise[1] = 0;
+    rec.passed = 0;
+    rec.n_pairs = 0;
+    rec.pad_ = 0;
+    rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
+    for (int i = 0; i < C2G_PAIR_WORDS; ++i) rec.pair_bits[i] = 0ull;
+    rec.pad2_ = 0ull;
+    if (h.cand_gidx >= 0) score_hint(heads, views, first_slot + h.q_idx, h, Q, scratch[w], rec);
+    scores[hid] = rec;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Proposal replay + tidy-up + GMM-L2 initial correlation, one warp per query scan
+// ------------------------------------------------------------------------------------------------------------------
+struct Prop {
+  double T[4];  // cos, sin, tx, ty
+  uint64_t bits[C2G_PAIR_WORDS];
+  int vote_cnt;
+  float area_perc;
+};
+struct CandState {
+  int gidx, n_prop;
+  float corr_init;
+  int alive;
+  double neg_est_dist;
+  Prop prop[C2G_MAX_PROP];
+};
+struct FinishScratch {
+  CandState cand[C2G_MAX_CAND];
+  int n_cand;
+  uint32_t ord[C2G_MAX_CAND];
+  float corr[C2G_MAX_CAND];
+  uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64];  // hint indices that reached addProposal, in order
+};
+
+__device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
+  // cont_perc_[l][j] = cell_cnt * 1.0f / layer_cell_cnt (contour_mng.h:605-608)
+  return (float) view_at(heads, views, slot, level, seq).cell_cnt * 1.0f / (float) heads[slot].layer_cell_cnt[level];
+}
+
+__device__ __forceinline__ void manual_cov_d(const c2g_view &v, double out[4]) {
+  const float vd00 = v.eig_vecs[0] * v.eig_vals[0], vd10 = v.eig_vecs[1] * v.eig_vals[0];
+  const float vd01 = v.eig_vecs[2] * v.eig_vals[1], vd11 = v.eig_vecs[3] * v.eig_vals[1];
+  out[0] = (double) (vd00 * v.eig_vecs[0] + vd01 * v.eig_vecs[2]);
+  out[1] = (double) (vd10 * v.eig_vecs[0] + vd11 * v.eig_vecs[2]);
+  out[2] = (double) (vd00 * v.eig_vecs[1] + vd01 * v.eig_vecs[3]);
+  out[3] = (double) (vd10 * v.eig_vecs[1] + vd11 * v.eig_vecs[3]);
+}
+
+// GMM-L2 initial correlation (correlation.h:84-96,125-152,196-202); all lanes of the warp cooperate, every lane returns
+// the same value.  src = candidate, tgt = query.
+__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *views, int src_slot, int tgt_slot, const double T[4], int lane) {
+  const double theta = atan2(T[1], T[0]);
+  const double c = cos(theta), s = sin(theta);
+  double cost = 0.0;
+  for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
+    const int lev = li + 1;
+    const int ns = heads[src_slot].n_ell[li], nt = heads[tgt_slot].n_ell[li];
+    const c2g_view *sv = views + (size_t) src_slot * C2G_VIEW_CAP + heads[src_slot].view_off[lev];
+    const c2g_view *tv = views + (size_t) tgt_slot * C2G_VIEW_CAP + heads[tgt_slot].view_off[lev];
+    for (int w = lane; w < ns * nt; w += 32) {
+      const int si = w / nt, ti = w - si * nt;
+      const c2g_view &a = sv[si], &b = tv[ti];
+      const double amx = (double) a.pos_mean[0], amy = (double) a.pos_mean[1];
+      const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
+      const double ddx = qx - (double) b.pos_mean[0], ddy = qy - (double) b.pos_mean[1];
+      const float maj = sqrtf(a.eig_vals[1]) + sqrtf(b.eig_vals[1]);
+      if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) maj)) continue;
+      double ca[4], cb[4];
+      manual_cov_d(a, ca);
+      manual_cov_d(b, cb);
+      const double t00 = c * ca[0] + (-s) * ca[1], t01 = c * ca[2] + (-s) * ca[3];
+      const double t10 = s * ca[0] + c * ca[1], t11 = s * ca[2] + c * ca[3];
+      const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
+      const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
+      const double c00 = 2.0 * (ra00 + cb[0]), c10 = 2.0 * (ra10 + cb[1]), c01 = 2.0 * (ra01 + cb[2]), c11 = 2.0 * (ra11 + cb[3]);
+      const double mx = (c * amx + (-s) * amy) + T[2] - (double) b.pos_mean[0];
+      const double my = (s * amx + c * amy) + T[3] - (double) b.pos_mean[1];
+      const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
+      const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
+      cost += -(double) b.cell_cnt * (double) a.cell_cnt * 1.0 / sqrt(det) * exp(qua);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+  return -cost / sqrt(heads[src_slot].gmm_auto_corr * heads[tgt_slot].gmm_auto_corr);
+}
+
+__device__ void add_proposal(CandState &cs, const double Tp[4], const uint64_t bits[C2G_PAIR_WORDS], int n_pairs) {
+  for (int i = 0; i < cs.n_prop; i++) {
+    Prop &pr = cs.prop[i];
+    // delta_T = T_prop.inverse() * anch.T_delta_
+    const double i00 = Tp[0], i01 = Tp[1], i10 = -Tp[1], i11 = Tp[0];  // R^T
+    const double itx = -(i00 * Tp[2] + i01 * Tp[3]), ity = -(i10 * Tp[2] + i11 * Tp[3]);
+    const double a00 = pr.T[0], a10 = pr.T[1];
+    const double d00 = i00 * a00 + i01 * a10, d10 = i10 * a00 + i11 * a10;
+    const double dtx = (i00 * pr.T[2] + i01 * pr.T[3]) + itx, dty = (i10 * pr.T[2] + i11 * pr.T[3]) + ity;
+    if (sqrt(dtx * dtx + dty * dty) < 2.0 && fabs(atan2(d10, d00)) < 0.3) {
+      for (int k = 0; k < C2G_PAIR_WORDS; ++k) pr.bits[k] |= bits[k];
+      pr.vote_cnt += n_pairs;
+      const int w1 = pr.vote_cnt, w2 = n_pairs;
+      const double tbx = (pr.T[2] * w1 + Tp[2] * w2) / (w1 + w2), tby = (pr.T[3] * w1 + Tp[3] * w2) / (w1 + w2);
+      const double ang1 = atan2(pr.T[1], pr.T[0]), ang2 = atan2(Tp[1], Tp[0]);
+      double diff = ang2 - ang1;
+      if (diff < 0) diff += 2 * C2G_PI;
+      if (diff > C2G_PI) diff -= 2 * C2G_PI;
+      const double ang_bl = diff * w2 / (w1 + w2) + ang1;
+      pr.T[0] = cos(ang_bl);
+      pr.T[1] = sin(ang_bl);
+      pr.T[2] = tbx;
+      pr.T[3] = tby;
+      return;
+    }
+  }
+  if (cs.n_prop > 3) return;
+  Prop &np = cs.prop[cs.n_prop++];
+  for (int k = 0; k < 4; ++k) np.T[k] = Tp[k];
+  for (int k = 0; k < C2G_PAIR_WORDS; ++k) np.bits[k] = bits[k];
+  np.vote_cnt = n_pairs;
+  np.area_perc = 0.0f;
+}
+
+__global__ void __launch_bounds__(128)
+finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int B, QueryParams Q,
+              int max_fine_opt, const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores,
+              c2g_query_result *__restrict__ results) {
+  extern __shared__ __align__(16) unsigned char fsm_raw[];
+  FinishScratch *all = reinterpret_cast<FinishScratch *>(fsm_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + w;
+  if (q >= B) return;
+  FinishScratch &F = all[w];
+  const int q_slot = first_slot + q;
+  const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
+  const c2g_hint *hq = hints + (size_t) q * per_q;
+  const c2g_pair_score *sq = scores + (size_t) q * per_q;
+  int aft1 = 0, aft2 = 0, aft3 = 0, overflow = 0;
+  // all lanes scan the hint records; only the few that reached addProposal are replayed sequentially
+  int n_pass = 0;
+  for (long long base = 0; base < per_q; base += 32) {
+    const long long i = base + lane;
+    int p = 0;
+    if (i < per_q && hq[i].cand_gidx >= 0) p = sq[i].passed;
+    const bool valid = i < per_q && hq[i].cand_gidx >= 0;
+    aft1 += __popc(__ballot_sync(0xFFFFFFFFu, valid && p != 0));
+    aft2 += __popc(__ballot_sync(0xFFFFFFFFu, valid && (p == 1 || p == -2)));
+    const unsigned pm = __ballot_sync(0xFFFFFFFFu, valid && p == 1);
+    if (valid && p == 1) F.passlist[n_pass + __popc(pm & ((1u << lane) - 1u))] = (uint16_t) i;
+    n_pass += __popc(pm);
+  }
+  aft3 = n_pass;
+  __syncwarp();
+  if (lane == 0) {
+    F.n_cand = 0;
+    // replay checkCandWithHint's bookkeeping in reference order: (q-level, query seq, ascending distance)
+    for (int k0 = 0; k0 < n_pass; ++k0) {
+      const int i = F.passlist[k0];
+      const c2g_pair_score &r = sq[i];
+      const int gidx = hq[i].cand_gidx;
+      int ci = -1;
+      for (int k = 0; k < F.n_cand; ++k)
+        if (F.cand[k].gidx == gidx) {
+          ci = k;
+          break;
+        }
+      if (ci < 0) {
+        if (F.n_cand >= C2G_MAX_CAND) {
+          overflow = 1;
+          continue;
+        }
+        ci = F.n_cand++;
+        F.cand[ci].gidx = gidx;
+        F.cand[ci].n_prop = 0;
+        F.cand[ci].corr_init = 0.0f;
+        F.cand[ci].alive = 0;
+        F.cand[ci].neg_est_dist = 0.0;
+      }
+      add_proposal(F.cand[ci], r.T, r.pair_bits, r.n_pairs);
+    }
+  }
+  __syncwarp();
+  const int n_before = F.n_cand;
+  // tidyUpCandidates
+  for (int ci = 0; ci < n_before; ++ci) {
+    CandState &cs = F.cand[ci];
+    int pass = 0;
+    if (lane == 0) {
+      int idx_sel = 0;
+      for (int i = 0; i < cs.n_prop; i++) {
+        float lev_perc[C2G_NLEV] = {0, 0, 0, 0, 0, 0};
+        for (int bit = 0; bit < C2G_PAIR_BITS; ++bit)  // std::map iteration order == ascending (level, seq_src, seq_tgt)
+          if ((cs.prop[i].bits[bit >> 6] >> (bit & 63)) & 1ull) {
+            const int level = bit / 100 + 1, ss = (bit / 10) % 10, st = bit % 10;
+            lev_perc[level] += 0.5f * (cont_perc(heads, views, cs.gidx, level, ss) + cont_perc(heads, views, q_slot, level, st));
+          }
+        const float LW[4] = {0.3f, 0.3f, 0.3f, 0.1f};
+        float perc = 0;
+        for (int j = 0; j < C2G_NUM_BIN_LAYERS; j++) perc += LW[j] * lev_perc[j + 1];
+        cs.prop[i].area_perc = perc;
+        if (cs.prop[i].vote_cnt > cs.prop[idx_sel].vote_cnt) idx_sel = i;
+      }
+      if (idx_sel != 0) {
+        const Prop tmp = cs.prop[0];
+        cs.prop[0] = cs.prop[idx_sel];
+        cs.prop[idx_sel] = tmp;
+      }
+      pass = 1;
+      if (cs.prop[0].area_perc < Q.lb.area_perc) pass = 0;
+      if (pass) {
+        // getEstSensTF: T_so^-1 * T_delta * T_so with T_so = translate(n_row/2 - 0.5, n_col/2 - 0.5)
+        const double ox = Q.n_row / 2 - 0.5, oy = Q.n_col / 2 - 0.5;
+        const double *T = cs.prop[0].T;
+        const double mx = (T[0] * ox + (-T[1]) * oy) + T[2], my = (T[1] * ox + T[0] * oy) + T[3];  // (T_delta * T_so).translation
+        const double ex = (1.0 * mx + 0.0 * my) + (-(1.0 * ox + 0.0 * oy)), ey = (0.0 * mx + 1.0 * my) + (-(0.0 * ox + 1.0 * oy));
+        cs.neg_est_dist = -sqrt(ex * ex + ey * ey);
+        if (cs.neg_est_dist < (double) Q.lb.neg_est_dist) pass = 0;
+      }
+    }
+    pass = __shfl_sync(0xFFFFFFFFu, pass, 0);
+    if (pass) {
+      __syncwarp();
+      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane);
+      if (lane == 0) {
+        cs.corr_init = (float) corr;
+        cs.alive = (cs.corr_init < Q.lb.correlation) ? 0 : 1;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    // swap-compaction of the survivors exactly as contour_db.h:580-592
+    int p1 = 0, p2 = n_before - 1;
+    while (p1 <= p2) {
+      if (!F.cand[p1].alive && F.cand[p2].alive) {
+        const CandState tmp = F.cand[p1];
+        F.cand[p1] = F.cand[p2];
+        F.cand[p2] = tmp;
+        p1++;
+        p2--;
+      } else {
+        if (F.cand[p1].alive) p1++;
+        if (!F.cand[p2].alive) p2--;
+      }
+    }
+    const int n = p2 + 1;
+    // fineOptimize: std::sort on correlation_ (all zero here), "optimise" the first max_fine_opt (identity), sort those
+    for (int i = 0; i < n; ++i) {
+      F.ord[i] = (uint32_t) i;
+      F.corr[i] = 0.0f;
+    }
+    const float *corr = F.corr;
+    c2g_sort::std_sort(F.ord, (long) n, [corr](uint32_t a, uint32_t b) { return corr[a] > corr[b]; });
+    const int pre = min(max_fine_opt, n);
+    for (int i = 0; i < pre; ++i) F.corr[F.ord[i]] = F.cand[F.ord[i]].corr_init;
+    c2g_sort::std_sort(F.ord, (long) pre, [corr](uint32_t a, uint32_t b) { return corr[a] > corr[b]; });
+    c2g_query_result &R = results[q];
+    R.n_cand = n;
+    R.n_pose_before = n_before;
+    R.cand_aft_check[0] = aft1;
+    R.cand_aft_check[1] = aft2;
+    R.cand_aft_check[2] = aft3;
+    R.overflow = overflow;
+    R.best = n > 0 ? 0 : -1;
+    R.pad_ = 0;
+    for (int i = 0; i < C2G_MAX_CAND; ++i) {
+      c2g_cand c;
+      c.cand_gidx = -1;
+      c.vote_cnt = 0;
+      c.area_perc = 0.f;
+      c.corr_init = 0.f;
+      c.neg_est_dist = 0.0;
+      c.T[0] = c.T[1] = c.T[2] = c.T[3] = 0.0;
+      if (i < n) {
+        const CandState &cs = F.cand[F.ord[i]];
+        c.cand_gidx = cs.gidx;
+        c.vote_cnt = cs.prop[0].vote_cnt;
+        c.area_perc = cs.prop[0].area_perc;
+        c.corr_init = cs.corr_init;
+        c.neg_est_dist = cs.neg_est_dist;
+        for (int k = 0; k < 4; ++k) c.T[k] = cs.prop[0].T[k];
+      }
+      R.cand[i] = c;
+    }
+  }
+}
+
+int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &Q) {
+  memset(&Q, 0, sizeof(Q));
+  Q.n_q_levels = ctx->db.n_q_levels;
+  for (int i = 0; i < Q.n_q_levels; ++i) {
+    Q.q_levels[i] = ctx->db.q_levels[i];
+    const C2gLayerTable &t = ctx->layers[i];
+    Q.layer[i].keys_t = t.keys_t;
+    Q.layer[i].gidx = t.gidx;
+    Q.layer[i].seq = t.seq;
+    Q.layer[i].cap = t.cap;
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
+      Q.layer[i].bucket_off[k] = t.bucket_off[k];
+      Q.layer[i].ranges[k] = t.ranges[k];
+    }
+  }
+  Q.nnk = ctx->db.nnk;
+  Q.piv = ctx->P.cfg.piv_firsts;
+  Q.sim = ctx->db.cont_sim;
+  Q.lb = *lb;
+  Q.n_row = ctx->P.cfg.n_row;
+  Q.n_col = ctx->P.cfg.n_col;
+  return 0;
+}
+
+int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores) {
+  static bool attr_set = false;
+  const int warps = 4;
+  const size_t smem = sizeof(FinishScratch) * warps;
+  if (!attr_set) {
+    C2G_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_set = true;
+  }
+  finish_kernel<<<(B + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q,
+                                                                            ctx->db.max_fine_opt, hints, scores, ctx->d_results);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+int c2g_query_alloc(c2g_ctx *ctx) {
+  ctx->n_hint_slots = (long long) ctx->max_batch * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_hints, sizeof(c2g_hint) * (size_t) ctx->n_hint_slots));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_scores, sizeof(c2g_pair_score) * (size_t) ctx->n_hint_slots));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_results, sizeof(c2g_query_result) * (size_t) ctx->max_batch));
+  for (int i = 0; i < ctx->db.n_q_levels; ++i) {
+    C2gLayerTable &t = ctx->layers[i];
+    t.cap = ctx->scan_cap * C2G_MAX_PIV;
+    t.n = 0;
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.keys_t, sizeof(float) * C2G_KEY_DIM * (size_t) t.cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * (size_t) t.cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, (size_t) t.cap));
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
+      t.bucket_off[k] = 0;
+      t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
+    }
+  }
+  return 0;
+}
+
+void c2g_query_free(c2g_ctx *ctx) {
+  cudaFree(ctx->d_hints);
+  cudaFree(ctx->d_scores);
+  cudaFree(ctx->d_results);
+  for (int i = 0; i < C2G_NUM_Q_LEVELS_MAX; ++i) {
+    cudaFree(ctx->layers[i].keys_t);
+    cudaFree(ctx->layers[i].gidx);
+    cudaFree(ctx->layers[i].seq);
+  }
+}
 
 extern "C" {
-int c2g_db_set_layer(c2g_ctx *, int, int, const float *, const int *, const signed char *, const unsigned char *, const float *) { return C2G_ERR_STATE; }
-int c2g_query(c2g_ctx *, int, int, const c2g_score_ensemble *, const c2g_score_ensemble *, c2g_query_result *, c2g_hint *, c2g_pair_score *) { return C2G_ERR_STATE; }
-int c2g_query_async(c2g_ctx *, int, int, const c2g_score_ensemble *, const c2g_score_ensemble *) { return C2G_ERR_STATE; }
-int c2g_query_buffers(c2g_ctx *, void **, void **, void **, long long *) { return C2G_ERR_STATE; }
-int c2g_finish_from_scores(c2g_ctx *, int, int, const c2g_score_ensemble *, const void *, const void *, c2g_query_result *) { return C2G_ERR_STATE; }
+
+int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const int *gidx_host, const signed char *seq_host,
+                     const unsigned char *bucket_host, const float *bucket_ranges_host) {
+  if (!ctx || ll < 0 || ll >= ctx->db.n_q_levels || n < 0 || !bucket_ranges_host) return C2G_ERR_ARG;
+  C2gLayerTable &t = ctx->layers[ll];
+  if (n > t.cap) return C2G_ERR_CAPACITY;
+  if (n > 0 && (!keys_host || !gidx_host || !seq_host || !bucket_host)) return C2G_ERR_ARG;
+  // bucket-major, tree order inside a bucket (stable counting sort on the host), keys transposed for coalesced scans
+  int cnt[C2G_NUM_BUCKETS + 1] = {0};
+  for (int i = 0; i < n; ++i) {
+    if (bucket_host[i] >= C2G_NUM_BUCKETS) return C2G_ERR_ARG;
+    cnt[bucket_host[i] + 1]++;
+  }
+  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) cnt[k + 1] += cnt[k];
+  for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
+    t.bucket_off[k] = cnt[k];
+    t.ranges[k] = bucket_ranges_host[k];
+  }
+  t.n = n;
+  if (n == 0) return 0;
+  float *kt = (float *) malloc(sizeof(float) * C2G_KEY_DIM * (size_t) n);
+  int *gi = (int *) malloc(sizeof(int) * (size_t) n);
+  signed char *sq = (signed char *) malloc((size_t) n);
+  if (!kt || !gi || !sq) {
+    free(kt);
+    free(gi);
+    free(sq);
+    return C2G_ERR_CAPACITY;
+  }
+  int pos[C2G_NUM_BUCKETS];
+  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) pos[k] = cnt[k];
+  for (int i = 0; i < n; ++i) {
+    const int p = pos[bucket_host[i]]++;
+    for (int d = 0; d < C2G_KEY_DIM; ++d) kt[(size_t) d * n + p] = keys_host[(size_t) i * C2G_KEY_DIM + d];
+    gi[p] = gidx_host[i];
+    sq[p] = seq_host[i];
+  }
+  cudaError_t e = cudaSuccess;
+  for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d)
+    e = cudaMemcpyAsync(t.keys_t + (size_t) d * t.cap, kt + (size_t) d * n, sizeof(float) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t.gidx, gi, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t.seq, sq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  free(kt);
+  free(gi);
+  free(sq);
+  return e == cudaSuccess ? 0 : -(int) e;
 }
+
+int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub) {
+  if (!ctx || !lb || !ub || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+  // CHECKs of the CandidateManager constructor (contour_db.h:365-367)
+  if (!(lb->i_ovlp_sum < ub->i_ovlp_sum && lb->i_ovlp_max_one < ub->i_ovlp_max_one && lb->i_in_ang_rng < ub->i_in_ang_rng &&
+        lb->i_indiv_sim < ub->i_indiv_sim && lb->i_orie_sim < ub->i_orie_sim && lb->correlation < ub->correlation &&
+        lb->area_perc < ub->area_perc && lb->neg_est_dist < ub->neg_est_dist))
+    return C2G_ERR_ARG;
+  if (ctx->db_dirty) {
+    int rc = c2g_db_sync(ctx);
+    if (rc) return rc;
+  }
+  QueryParams Q;
+  build_query_params(ctx, lb, Q);
+  const int n_keys = B * Q.n_q_levels * C2G_MAX_PIV;
+  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, first_slot, B, Q, ctx->d_hints);
+  C2G_CUDA_TRY(cudaGetLastError());
+  const long long n_hints = (long long) n_keys * Q.nnk;
+  score_kernel<<<(unsigned) ((n_hints + SC_WARPS - 1) / SC_WARPS), SC_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot,
+                                                                                                    n_hints, Q, ctx->d_hints, ctx->d_scores);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 2;
+  return launch_finish(ctx, first_slot, B, Q, ctx->d_hints, ctx->d_scores);
+}
+
+int c2g_query(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+              c2g_query_result *results_host, c2g_hint *hints_host, c2g_pair_score *scores_host) {
+  if (!results_host) return C2G_ERR_ARG;
+  int rc = c2g_query_async(ctx, first_slot, B, lb, ub);
+  if (rc) return rc;
+  const size_t nh = (size_t) B * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
+  C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hints_host) C2G_CUDA_TRY(cudaMemcpyAsync(hints_host, ctx->d_hints, sizeof(c2g_hint) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scores_host) C2G_CUDA_TRY(cudaMemcpyAsync(scores_host, ctx->d_scores, sizeof(c2g_pair_score) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void **scores_dev, long long *n_hint_slots) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (results_dev) *results_dev = ctx->d_results;
+  if (hints_dev) *hints_dev = ctx->d_hints;
+  if (scores_dev) *scores_dev = ctx->d_scores;
+  if (n_hint_slots) *n_hint_slots = ctx->n_hint_slots;
+  return 0;
+}
+
+int c2g_finish_from_scores(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const void *hints_dev,
+                           const void *scores_dev, c2g_query_result *results_host) {
+  if (!ctx || !lb || !hints_dev || !scores_dev || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
+  QueryParams Q;
+  build_query_params(ctx, lb, Q);
+  int rc = launch_finish(ctx, first_slot, B, Q, (const c2g_hint *) hints_dev, (const c2g_pair_score *) scores_dev);
+  if (rc) return rc;
+  if (results_host) {
+    C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDeviceToHost, ctx->stream));
+    C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -88,6 +88,38 @@ class Engine:
     def copy_slots(self, src_first: int, dst_first: int, n: int):
         capi.check(capi.lib().c2g_copy_slots(self.h, src_first, dst_first, n), "c2g_copy_slots")
 
+    # ---- ContourDB::addScan / pushAndBalance (host-side LayerDB bookkeeping inside the library) ----------------------
+    def db_add_scans(self, first_slot: int, n: int, ts):
+        ts = np.ascontiguousarray(ts, np.float64)
+        assert len(ts) == n
+        capi.check(capi.lib().c2g_db_add_scans(self.h, first_slot, n, capi.ptr(ts)), "c2g_db_add_scans")
+
+    def db_push_and_balance(self, seed: int, ts: float):
+        capi.check(capi.lib().c2g_db_push_and_balance(self.h, seed, float(ts)), "c2g_db_push_and_balance")
+
+    def db_size(self) -> int:
+        return int(capi.lib().c2g_db_size(self.h))
+
+    def db_sync(self):
+        capi.check(capi.lib().c2g_db_sync(self.h), "c2g_db_sync")
+
+    def db_layer_state(self, ll: int):
+        rng = np.zeros(D.NUM_BUCKETS + 1, np.float32)
+        ts = np.zeros(D.NUM_BUCKETS, np.int32)
+        bs = np.zeros(D.NUM_BUCKETS, np.int32)
+        capi.check(capi.lib().c2g_db_layer_state(self.h, ll, capi.ptr(rng), capi.ptr(ts), capi.ptr(bs)), "c2g_db_layer_state")
+        return rng, ts, bs
+
+    def db_bucket_tree(self, ll: int, bucket: int):
+        n = int(self.db_layer_state(ll)[1][bucket])
+        keys = np.zeros((n, D.KEY_DIM), np.float32)
+        gidx = np.zeros(n, np.int32)
+        seq = np.zeros(n, np.int32)
+        if n:
+            capi.check(capi.lib().c2g_db_bucket_tree(self.h, ll, bucket, capi.ptr(keys), capi.ptr(gidx), capi.ptr(seq)),
+                       "c2g_db_bucket_tree")
+        return keys, gidx, seq
+
     # ---- database mirror + query -----------------------------------------------------------------------------------------
     def db_set_layer(self, ll: int, keys: np.ndarray, gidx: np.ndarray, seq: np.ndarray, bucket: np.ndarray,
                      bucket_ranges: np.ndarray):

@@ -68,7 +68,20 @@ int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host);
 /* Copy finished descriptors between slots (ContourDB::addScan keeps the shared_ptr, include/cont2/contour_db.h:823). */
 int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n);
 
-/* Mirror of the host-maintained LayerDB state (include/cont2/contour_db.h:159-217, src/cont2/contour_db.cpp:63-317):
+/* Replaces ContourDB::addScan (include/cont2/contour_db.h:814-824) for the n finished scans in slots first_slot.. (which
+ * must equal the current DB size: gidx == slot == all_bevs_.size()): their non-zero q-level keys enter the time-delay
+ * buffers of the host-side LayerDBs with timestamps ts_host[i]. Synchronises the stream (reads the keys back, 1.4 KB/scan). */
+int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host);
+/* Replaces ContourDB::pushAndBalance (include/cont2/contour_db.h:827-843, LayerDB::rebuild src/cont2/contour_db.cpp:63-317). */
+int c2g_db_push_and_balance(c2g_ctx *ctx, int seed, double ts);
+int c2g_db_size(c2g_ctx *ctx);
+/* Upload the host-side tree contents to the device tables if they changed (c2g_query* call it implicitly). */
+int c2g_db_sync(c2g_ctx *ctx);
+/* Introspection for parity tests: bucket boundaries [7], tree sizes [6], buffer sizes [6]; one bucket's tree in order. */
+int c2g_db_layer_state(c2g_ctx *ctx, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes);
+int c2g_db_bucket_tree(c2g_ctx *ctx, int ll, int bucket, float *keys, int *gidx, int *seq);
+
+/* Low-level mirror call used by c2g_db_sync: device copy of the host-maintained LayerDB state (include/cont2/contour_db.h:159-217, src/cont2/contour_db.cpp:63-317):
  * for q-level index `ll`, the keys currently INSIDE the KD-trees (not the time-delay buffers), the bucket each one
  * lives in, where it came from (IndexOfKey gidx/seq) and the 7 bucket boundaries. keys: n x 10 floats, row-major. */
 int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const int *gidx_host, const signed char *seq_host,
@@ -91,6 +104,18 @@ int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void *
  * c2g_query_buffers'. */
 int c2g_finish_from_scores(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const void *hints_dev,
                            const void *scores_dev, c2g_query_result *results_host);
+
+/* Stand-alone handles on the host-side LayerDB logic (no CUDA context): used by the C++ facade's unit tests and the
+ * CPU parity tests of the bucket rebalancing (src/cont2/contour_db.cpp:63-317). */
+void *c2g_hostdb_create(int n_layers, double max_elapse, double min_elapse);
+void c2g_hostdb_free(void *h);
+int c2g_hostdb_push_key(void *h, int ll, const float *key, double ts, int gidx, int seq);
+int c2g_hostdb_balance(void *h, int seed, double ts);
+int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes);
+int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq);
+
+/* Developer aid: clock64() stamps of the contour kernel's phases (64 values). */
+int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host);
 
 /* Counters: kernels launched by this context since creation (bench.py's gpu_launches). */
 long long c2g_launch_count(c2g_ctx *ctx);

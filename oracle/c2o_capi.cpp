@@ -189,3 +189,11 @@ extern "C" void c2o_test_fill_layer(void *db, int ll, const float *keys, int n) 
   }
   b.rebuildTree();
 }
+
+// test hook: LayerDB::pushBuffer with a raw key (as ContourDB::addScan would do for one key)
+extern "C" void c2o_test_push_key(void *db, int ll, const float *key, double ts, int gidx, int seq) {
+  Key k;
+  for (int d = 0; d < C2G_KEY_DIM; ++d) k[d] = key[d];
+  ContourDB *D = (ContourDB *) db;
+  D->layer_db_[ll].pushBuffer(k, ts, IndexOfKey{(size_t) gidx, D->cfg_.q_levels[ll], seq});
+}

@@ -39,3 +39,15 @@ print(f"B={B} K1 bev_scatter: min {k1[0]:.3f} ms median {k1[1]:.3f} ms -> {bytes
 print(f"B={B} K1+K2 ingest : min {full[0]:.3f} ms median {full[1]:.3f} ms -> {bytes_/full[0]/1e6:.1f} GB/s, {B/full[0]*1e3:.0f} scans/s; K2 alone ~{full[0]-k1[0]:.3f} ms")
 h = eng.heads(0, B)
 print("status", np.unique(h["status"]), "views/level mean", h["n_views"].mean(0))
+import ctypes as C
+from contour_context_b200 import capi
+clk = np.zeros(64, np.int64)
+capi.lib().c2g_debug_clocks.argtypes = [C.c_void_p, C.c_void_p]
+capi.lib().c2g_debug_clocks(eng.h, clk.ctypes.data_as(C.c_void_p))
+names = {0:'start',1:'A done',2:'levels done',3:'sort done',4:'views copied',5:'D1 done',6:'D2+keys done',7:'BCI done',8:'GMM done',9:'end'}
+t0 = clk[0]
+for i in range(10): print(f"  {names[i]:14s} {(clk[i]-t0)/1e3:9.1f} kcyc")
+for lev in range(6):
+    s = clk[10+lev*8: 10+lev*8+7]
+    base = clk[1] if lev == 0 else clk[10+(lev-1)*8+6]
+    print(f"  lev{lev}: init {(s[0]-base)/1e3:.1f} union {(s[1]-s[0])/1e3:.1f} flatten {(s[2]-s[1])/1e3:.1f} roots {(s[3]-s[2])/1e3:.1f} tables {(s[4]-s[3])/1e3:.1f} rank {(s[5]-s[4])/1e3:.1f} walk {(s[6]-s[5])/1e3:.1f} kcyc")

@@ -74,7 +74,7 @@ def test_views_keys_bci(engine, oracle):
         for f in ("level", "seq", "bit_pos"):
             assert np.array_equal(gb_["nei"][f], ob_["nei"][f]), f
         assert gb_["nei"]["r"].tobytes() == ob_["nei"]["r"].tobytes()
-        assert ulp_diff(gb_["nei"]["theta"], ob_["nei"]["theta"]).max() <= 1
+        assert ulp_diff(gb_["nei"]["theta"], ob_["nei"]["theta"]).max() <= 2
         assert abs(gh["gmm_auto_corr"] - oh["gmm_auto_corr"]) <= 1e-9 * abs(oh["gmm_auto_corr"])
     # at most a handful of 1-ulp key entries over 6 scans x 360 key entries
     assert key_ulp_bad <= 4, f"{key_ulp_bad} key entries differ from the oracle"

@@ -1,0 +1,128 @@
+"""GPU parity of the database/query path against the CPU oracle, through the C-ABI:
+growing DB bookkeeping -> ranged kNN hints -> per-hint cascade scores -> candidate poses -> GMM-L2 initial correlation.
+
+Bar: hint identity/order and squared key distances bit-exact; constellation / pairwise integer scores equal; matched-pair
+sets equal; SE(2) proposals, area_perc and correlation within 1e-5 (north_star)."""
+import numpy as np
+import pytest
+
+from contour_context_b200 import ctypes_defs as D
+from contour_context_b200 import synth
+from helpers import make_batch
+
+pytestmark = pytest.mark.gpu
+
+N_PTS = 120000
+N_SCENES = 16
+VISITS_DB = 3
+
+
+@pytest.fixture(scope="module")
+def world(built_lib, oracle):
+    """A 48-scan DB (16 scenes x 3 visits) grown scan by scan on both sides + 16 query scans (4th visit)."""
+    from contour_context_b200.engine import Engine
+
+    n_db = N_SCENES * VISITS_DB
+    eng = Engine(scan_capacity=n_db + 32, max_batch=16, max_points=16 * 131072)
+    cfg, dbc = eng.cm_cfg, eng.db_cfg
+    odb = oracle.DB(dbc)
+    seeds, visits = synth.db_layout(n_db, VISITS_DB, first_scene=100)
+    oscans = []
+    for i0 in range(0, n_db, 16):
+        pts, offsets = make_batch(seeds[i0:i0 + 16], visits[i0:i0 + 16], N_PTS, noise_seed=i0)
+        eng.ingest(pts, offsets, first_slot=i0, int_ids=np.arange(i0, i0 + 16))
+        for j in range(16):
+            i = i0 + j
+            s = oracle.Scan(cfg, i).ingest(pts[offsets[j]:offsets[j + 1]])
+            oscans.append(s)
+            ts = 0.5 * i  # 0.5 s apart so that the 15 s / 25 s gates and several rebalancing rounds are exercised
+            odb.add_scan(s, ts)
+            odb.push_and_balance(i, ts)
+            eng.db_add_scans(i, 1, [ts])
+            eng.db_push_and_balance(i, ts)
+    for k in range(12):  # flush: later timestamps move every buffered key into a tree
+        odb.push_and_balance(k, 1000.0 + k)
+        eng.db_push_and_balance(k, 1000.0 + k)
+    q_seeds = list(range(100, 100 + N_SCENES))
+    qpts, qoff = make_batch(q_seeds, [3] * N_SCENES, N_PTS, noise_seed=999)
+    q_first = n_db
+    eng.ingest(qpts, qoff, first_slot=q_first, int_ids=np.arange(1000, 1000 + N_SCENES))
+    oq = [oracle.Scan(cfg, 1000 + j).ingest(qpts[qoff[j]:qoff[j + 1]]) for j in range(N_SCENES)]
+    yield dict(eng=eng, odb=odb, oq=oq, q_first=q_first)
+    eng.close()
+
+
+def test_db_bookkeeping_matches(world):
+    eng, odb = world["eng"], world["odb"]
+    assert eng.db_size() == odb.n_scans()
+    for ll in range(eng.db_cfg.n_q_levels):
+        o_rng, o_ts, o_bs = odb.layer_state(ll)
+        g_rng, g_ts, g_bs = eng.db_layer_state(ll)
+        assert o_rng.tobytes() == g_rng.tobytes()
+        assert np.array_equal(o_ts, g_ts) and np.array_equal(o_bs, g_bs)
+        assert o_bs.sum() == 0
+        for b in range(D.NUM_BUCKETS):
+            ok, og, osq = odb.bucket_tree(ll, b)
+            gk, gg, gsq = eng.db_bucket_tree(ll, b)
+            assert ok.tobytes() == gk.tobytes() and np.array_equal(og, gg) and np.array_equal(osq, gsq)
+
+
+def test_hints_scores_candidates(world):
+    eng, odb, oq, q_first = world["eng"], world["odb"], world["oq"], world["q_first"]
+    lb, ub = D.kitti_thres()
+    res, hints, scores = eng.query(q_first, N_SCENES, lb, ub, want_trace=True)
+    per_q = eng.hint_slots(1)
+    n_pass_total = n_cand_total = 0
+    for j in range(N_SCENES):
+        ores, ohints, oscores = odb.query(oq[j], lb, ub)
+        gh = hints[j * per_q:(j + 1) * per_q]
+        gs = scores[j * per_q:(j + 1) * per_q]
+        keep = gh["cand_gidx"] >= 0
+        gh, gs = gh[keep], gs[keep]
+        # --- hints: same list in the same order
+        assert len(gh) == len(ohints), (j, len(gh), len(ohints))
+        for f in ("cand_gidx", "level", "cand_seq", "q_seq", "q_level_idx"):
+            assert np.array_equal(gh[f], ohints[f]), (j, f)
+        assert gh["dist_sq"].tobytes() == ohints["dist_sq"].tobytes()
+        # --- per-hint cascade
+        assert np.array_equal(gs["passed"], oscores["passed"]), j
+        assert np.array_equal(gs["constell"], oscores["constell"]), j
+        assert np.array_equal(gs["pairwise"], oscores["pairwise"]), j
+        assert np.array_equal(gs["n_pairs"], oscores["n_pairs"])
+        assert np.array_equal(gs["pair_bits"], oscores["pair_bits"])
+        ok = oscores["passed"] == 1
+        n_pass_total += int(ok.sum())
+        if ok.any():
+            assert np.abs(gs["T"][ok] - oscores["T"][ok]).max() < 1e-9
+        # --- candidate poses
+        g = res[j]
+        assert g["n_pose_before"] == ores["n_pose_before"]
+        assert np.array_equal(g["cand_aft_check"], ores["cand_aft_check"])
+        assert g["n_cand"] == ores["n_cand"], (j, g["n_cand"], ores["n_cand"])
+        assert g["overflow"] == 0 and g["best"] == ores["best"]
+        n = int(g["n_cand"])
+        n_cand_total += n
+        if n:
+            gc, oc = g["cand"][:n], ores["cand"][:n]
+            assert np.array_equal(gc["cand_gidx"], oc["cand_gidx"]), (j, gc["cand_gidx"], oc["cand_gidx"])
+            assert np.array_equal(gc["vote_cnt"], oc["vote_cnt"])
+            assert np.abs(gc["area_perc"] - oc["area_perc"]).max() <= 1e-6
+            assert np.abs(gc["corr_init"] - oc["corr_init"]).max() <= 1e-5
+            assert np.abs(gc["neg_est_dist"] - oc["neg_est_dist"]).max() <= 1e-8
+            assert np.abs(gc["T"] - oc["T"]).max() <= 1e-8
+    # the synthetic revisits must actually exercise the whole cascade
+    assert n_pass_total >= 50, n_pass_total
+    assert n_cand_total >= 8, n_cand_total
+
+
+def test_query_is_deterministic_and_async_path_agrees(world):
+    eng, q_first = world["eng"], world["q_first"]
+    lb, ub = D.kitti_thres()
+    a = eng.query(q_first, N_SCENES, lb, ub)
+    b = eng.query(q_first, N_SCENES, lb, ub)
+    assert a.tobytes() == b.tobytes()
+    # finish_from_scores on the context's own buffers reproduces the same results (the multi-GPU merge path)
+    eng.query_async(q_first, N_SCENES, lb, ub)
+    _, h_dev, s_dev, _ = eng.query_buffers()
+    c = eng.finish_from_scores(q_first, N_SCENES, lb, h_dev, s_dev)
+    assert a.tobytes() == c.tobytes()
