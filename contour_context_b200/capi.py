@@ -47,6 +47,7 @@ def lib():
         L.c2g_query.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp, vp, vp]
         L.c2g_query_async.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble)]
         L.c2g_query_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
+        L.c2g_query_export.argtypes = [vp, ip, vp, vp, vp]
         L.c2g_finish_from_scores.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), vp, vp, vp]
         L.c2g_db_add_scans.argtypes = [vp, ip, ip, vp]
         L.c2g_db_push_and_balance.argtypes = [vp, ip, C.c_double]

@@ -24,6 +24,7 @@
 
 #include "c2g_common.cuh"
 #include "stdsort.cuh"
+#include "c2g_libm.cuh"
 
 namespace {
 
@@ -267,7 +268,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     c2g_scan_head *head = heads + (first_slot + b);
     c2g_view *vout = views + (size_t) (first_slot + b) * C2G_VIEW_CAP;
 
-#define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0 && b == 0) dbg[i] = clock64(); } while (0)
+#define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0) dbg[i] = clock64(); } while (0)
     C2G_DBG(0);
     // ---------------- phase A: decode the tile, gather the winner's continuous coordinates -------------------------
     if (tid == 0) {
@@ -368,33 +369,56 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 1);
       // B3 flatten
-      for (int c = cb0; c < cb1; ++c)
-        if (S.msk[c] & bit) {
-          const uint32_t root = uf_find(S.L, c);
-          S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
+      {
+        // one find per horizontal run of the chunk: the other cells of the run share its root by construction
+        uint32_t root = 0;
+        bool in_run = false;
+        for (int c = cb0; c < cb1; ++c) {
+          if (S.msk[c] & bit) {
+            if (!in_run || (c % ncol) == 0) root = uf_find(S.L, c);
+            in_run = true;
+            S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
+          } else
+            in_run = false;
         }
+      }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 2);
-      // B4 roots -> table slots
-      for (int c = tid; c < ncell; c += K2_THREADS)
-        if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) {
-          int slot = atomicAdd(&S.ncomp, 1);
-          if (slot < NC) {
-            S.c_area[slot] = 0;
-            S.c_minr[slot] = 1 << 20;
-            S.c_minc[slot] = 1 << 20;
-            S.c_maxr[slot] = -1;
-            S.c_maxc[slot] = -1;
-            S.c_key[slot] = 1 << 30;
-            S.c_poi[slot] = -1;
-            S.c_pcid[slot] = (uint16_t) (S.L[c] >> 16);
-            S.c_rank[slot] = 0xFFFFu;
-          } else {
-            slot = 0x7FFF;
-            atomicOr(&S.status, 2);
-          }
-          S.L[c] = (S.L[c] & 0xFFFF0000u) | 0x8000u | (uint32_t) slot;
+      // B4 roots -> table slots (one shared-memory atomic per warp: same-address atomics serialise)
+      {
+        int nroot = 0;
+        for (int c = cb0; c < cb1; ++c)
+          if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) ++nroot;
+        int incl = nroot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
         }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&S.ncomp, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        int slot_next = base + incl - nroot;
+        for (int c = cb0; c < cb1 && nroot > 0; ++c)
+          if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) {
+            int slot = slot_next++;
+            if (slot < NC) {
+              S.c_area[slot] = 0;
+              S.c_minr[slot] = 1 << 20;
+              S.c_minc[slot] = 1 << 20;
+              S.c_maxr[slot] = -1;
+              S.c_maxc[slot] = -1;
+              S.c_key[slot] = 1 << 30;
+              S.c_poi[slot] = -1;
+              S.c_pcid[slot] = (uint16_t) (S.L[c] >> 16);
+              S.c_rank[slot] = 0xFFFFu;
+            } else {
+              slot = 0x7FFF;
+              atomicOr(&S.status, 2);
+            }
+            S.L[c] = (S.L[c] & 0xFFFF0000u) | 0x8000u | (uint32_t) slot;
+          }
+      }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 3);
       // B5 per-component area / bbox / first-block key / last pixel, aggregated over horizontal runs per thread chunk
@@ -467,10 +491,14 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         const int s = S.order[rk];
         const int r0 = S.c_minr[s], c0 = S.c_minc[s], w = S.c_maxc[s] - c0 + 1, hgt = S.c_maxr[s] - r0 + 1;
         const int total = w * hgt;
-        Moments m;
-        m.cnt = 0;
-        m.s0 = m.s1 = m.t00 = m.t01 = m.t11 = m.q0 = m.q1 = 0.0;
-        m.vol3 = 0.0f;
+        // The seven double accumulators of RunningStatRecorder live in lanes 0..6: lane k adds a_k * b_k per member cell
+        // (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1, t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the
+        // FP64 pipe one DMUL + one DADD per warp instead of fifteen. Accumulation order = bbox-raster order.
+        const int selA = (lane == 0 || lane == 2 || lane == 3) ? 0 : (lane == 1 || lane == 4) ? 1 : (lane == 5 || lane == 6) ? 2 : 3;
+        const int selB = (lane == 2 || lane == 5) ? 0 : (lane == 3 || lane == 4 || lane == 6) ? 1 : 3;
+        double acc = 0.0;
+        float vol3 = 0.0f;
+        int cnt = 0;
         uint16_t *wl = S.wlist[warp];
         int nlist = 0;
         for (int base = 0; base < total; base += 32) {
@@ -487,18 +515,21 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           nlist += __popc(bal);
           if (nlist > WL_CAP - 32 || base + 32 >= total) {
             __syncwarp();
-            // flush: 4 groups of 32 cells in flight from L2, then strictly sequential accumulation in list order
+            // flush: 4 groups of 32 cells in flight from L2 (converted to double at the source lane), then strictly
+            // sequential accumulation in list order
             for (int g = 0; g < nlist; g += 128) {
-              float hv[4], rv[4], cv[4];
+              float hv[4];
+              double rv[4], cv[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int j = g + u * 32 + lane;
-                hv[u] = rv[u] = cv[u] = 0.f;
+                hv[u] = 0.f;
+                rv[u] = cv[u] = 0.0;
                 if (j < nlist) {
                   const int cc = wl[j];
                   hv[u] = hg[cc];
-                  rv[u] = rfg[cc];
-                  cv[u] = cfp[cc];
+                  rv[u] = (double) rfg[cc];
+                  cv[u] = (double) cfp[cc];
                 }
               }
 #pragma unroll
@@ -506,24 +537,31 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
                 const int cntu = min(32, nlist - (g + u * 32));
                 for (int src = 0; src < cntu; ++src) {
                   const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
-                  const double v0 = (double) __shfl_sync(0xFFFFFFFFu, rv[u], src);
-                  const double v1 = (double) __shfl_sync(0xFFFFFFFFu, cv[u], src);
-                  m.cnt += 1;
-                  m.s0 += v0;
-                  m.s1 += v1;
-                  m.t00 += v0 * v0;
-                  m.t01 += v0 * v1;
-                  m.t11 += v1 * v1;
-                  m.vol3 += hh;
-                  m.q0 += (double) hh * v0;
-                  m.q1 += (double) hh * v1;
+                  const double v0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
+                  const double v1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
+                  const double hd = (double) hh;
+                  const double a = selA == 0 ? v0 : selA == 1 ? v1 : selA == 2 ? hd : 1.0;
+                  const double bb = selB == 0 ? v0 : selB == 1 ? v1 : 1.0;
+                  acc += a * bb;
+                  vol3 += hh;
                 }
+                cnt += max(cntu, 0);
               }
             }
             __syncwarp();
             nlist = 0;
           }
         }
+        Moments m;
+        m.cnt = cnt;
+        m.vol3 = vol3;
+        m.s0 = __shfl_sync(0xFFFFFFFFu, acc, 0);
+        m.s1 = __shfl_sync(0xFFFFFFFFu, acc, 1);
+        m.t00 = __shfl_sync(0xFFFFFFFFu, acc, 2);
+        m.t01 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        m.t11 = __shfl_sync(0xFFFFFFFFu, acc, 4);
+        m.q0 = __shfl_sync(0xFFFFFFFFu, acc, 5);
+        m.q1 = __shfl_sync(0xFFFFFFFFu, acc, 6);
         if (lane == 0) {
           c2g_view v;
           const int poi = S.c_poi[s];
@@ -660,7 +698,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           for (int k = 0; k < n; ++k) {
             const float t = (x - dl[k]) / 1.0f;
             const double q = (-0.5 * (double) t) * (double) t;
-            const float g = (float) (exp(q) / inv_norm_den);
+            const float g = (float) (c2g_exp(q) / inv_norm_den);
             acc += (float) hl[k] * g;
           }
         }
@@ -695,42 +733,81 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     }
 
     C2G_DBG(6);
-    // ---------------- phase E: BCIs (contour_mng.h:848-883), one thread per anchor ---------------------------------
-    for (int a = warp; a < N_ANCH; a += K2_WARPS) {
-      const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
-      if (lane == 0 && seq < piv) {
+    // ---------------- phase E: BCIs (contour_mng.h:848-883), one warp per anchor ------------------------------------
+    // candidate t = bl * 10 + j (reference loop order) is evaluated by lane t % 32; kept neighbours are compacted in
+    // that order, lane 0 replays std::sort on bit_pos and builds the run boundaries, all lanes write the record.
+    {
+      c2g_relpt *nei_all = reinterpret_cast<c2g_relpt *>(S.L);                                         // [warps][40]
+      uint32_t *ord_all = reinterpret_cast<uint32_t *>(nei_all + K2_WARPS * C2G_MAX_NEI);              // [warps][40]
+      uint16_t *seg_all = reinterpret_cast<uint16_t *>(ord_all + K2_WARPS * C2G_MAX_NEI);              // [warps][42]
+      c2g_relpt *nei = nei_all + warp * C2G_MAX_NEI;
+      uint32_t *ord = ord_all + warp * C2G_MAX_NEI;
+      uint16_t *segv = seg_all + warp * (C2G_MAX_NEI + 2);
+      for (int a = warp; a < N_ANCH; a += K2_WARPS) {
+        const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
+        if (seq >= piv) continue;
         c2g_bci &bci = head->bcis[ll][seq];
-        uint64_t bins[4] = {0, 0, 0, 0};
-        c2g_relpt nei[C2G_MAX_NEI];
-        uint32_t ord[C2G_MAX_NEI];
         int n = 0;
         if (S.cnt_point[a] >= 0) {
-          const TopView &an = S.top[ll][seq];
-          for (int bl = 0; bl < C2G_NUM_BIN_LAYERS; ++bl) {
-            const int layer = bl + 1;
-            const int lim = min(cfg.dist_firsts, S.n_views[layer]);
-            for (int j = 0; j < lim; ++j) {
-              if (ll == layer && j == seq) continue;
-              const float vx = S.top[layer][j].mean0 - an.mean0, vy = S.top[layer][j].mean1 - an.mean1;
-              const float dist = sqrtf(vx * vx + vy * vy);
-              if ((double) dist > (C2G_BITS_PER_LAYER - 1) * 1.01 + 5.43 - 1e-3 || (double) dist <= 5.43) continue;
-              const float orie = atan2f(vy, vx);
-              const int idx = (int) (fmin(floor(((double) dist - 5.43) / 1.01), C2G_BITS_PER_LAYER - 1.0) + (double) (bl * C2G_BITS_PER_LAYER));
-              bins[idx >> 6] |= 1ull << (idx & 63);
-              nei[n].level = (int8_t) layer;
-              nei[n].seq = (int8_t) j;
-              nei[n].bit_pos = (int16_t) idx;
-              nei[n].r = dist;
-              nei[n].theta = orie;
-              ord[n] = ((uint32_t) idx << 16) | (uint32_t) n;
-              ++n;
+          const TopView an = S.top[ll][seq];
+          for (int t0 = 0; t0 < C2G_MAX_NEI; t0 += 32) {
+            const int t = t0 + lane;
+            bool keep = false;
+            c2g_relpt rp;
+            rp.level = 0;
+            rp.seq = 0;
+            rp.bit_pos = 0;
+            rp.r = 0.f;
+            rp.theta = 0.f;
+            if (t < C2G_MAX_NEI) {
+              const int bl = t / C2G_MAX_DIST_FIRSTS, j = t % C2G_MAX_DIST_FIRSTS, layer = bl + 1;
+              if (j < min(cfg.dist_firsts, S.n_views[layer]) && !(ll == layer && j == seq)) {
+                const float vx = S.top[layer][j].mean0 - an.mean0, vy = S.top[layer][j].mean1 - an.mean1;
+                const float dist = sqrtf(vx * vx + vy * vy);
+                if (!((double) dist > (C2G_BITS_PER_LAYER - 1) * 1.01 + 5.43 - 1e-3 || (double) dist <= 5.43)) {
+                  keep = true;
+                  const int idx = (int) (fmin(floor(((double) dist - 5.43) / 1.01), C2G_BITS_PER_LAYER - 1.0) + (double) (bl * C2G_BITS_PER_LAYER));
+                  rp.level = (int8_t) layer;
+                  rp.seq = (int8_t) j;
+                  rp.bit_pos = (int16_t) idx;
+                  rp.r = dist;
+                  rp.theta = c2g_atan2f(vy, vx);
+                }
+              }
             }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) {
+              const int pos = n + __popc(bal & ((1u << lane) - 1u));
+              nei[pos] = rp;
+              ord[pos] = ((uint32_t) (uint16_t) rp.bit_pos << 16) | (uint32_t) pos;
+            }
+            n += __popc(bal);
           }
         }
-        c2g_sort::std_sort(ord, (long) n, [](uint32_t x, uint32_t y) { return (x >> 16) < (y >> 16); });
-        for (int i = 0; i < 4; ++i) bci.dist_bin[i] = bins[i];
+        __syncwarp();
         int nseg = 0;
-        for (int i = 0; i < C2G_MAX_NEI; ++i) {
+        uint64_t bins[4] = {0, 0, 0, 0};
+        if (lane == 0) {
+          c2g_sort::std_sort(ord, (long) n, [](uint32_t x, uint32_t y) { return (x >> 16) < (y >> 16); });
+          if (n > 0) {
+            segv[nseg++] = 0;
+            for (int p1 = 0; p1 < n; ++p1) {
+              const int bp = (int) (ord[p1] >> 16);
+              bins[bp >> 6] |= 1ull << (bp & 63);
+              if ((ord[segv[nseg - 1]] >> 16) != (ord[p1] >> 16)) segv[nseg++] = (uint16_t) p1;
+            }
+            segv[nseg++] = (uint16_t) n;
+          }
+          for (int i = 0; i < 4; ++i) bci.dist_bin[i] = bins[i];
+          bci.n_nei = (int16_t) n;
+          bci.n_seg = (int16_t) nseg;
+          bci.piv_seq = (int8_t) seq;
+          bci.level = (int8_t) ll;
+          for (int i = 0; i < 6; ++i) bci.pad_[i] = 0;
+        }
+        nseg = __shfl_sync(0xFFFFFFFFu, nseg, 0);
+        __syncwarp();
+        for (int i = lane; i < C2G_MAX_NEI; i += 32) {
           c2g_relpt rp;
           rp.level = 0;
           rp.seq = 0;
@@ -740,22 +817,10 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           if (i < n) rp = nei[ord[i] & 0xFFFFu];
           bci.nei[i] = rp;
         }
-        uint16_t segv[C2G_MAX_NEI + 2];
-        if (n > 0) {
-          segv[nseg++] = 0;
-          for (int p1 = 0; p1 < n; ++p1)
-            if ((ord[segv[nseg - 1]] >> 16) != (ord[p1] >> 16)) segv[nseg++] = (uint16_t) p1;
-          segv[nseg++] = (uint16_t) n;
-        }
-        for (int i = 0; i < C2G_MAX_NEI + 2; ++i) bci.seg[i] = i < nseg ? segv[i] : (uint16_t) 0;
-        bci.n_nei = (int16_t) n;
-        bci.n_seg = (int16_t) nseg;
-        bci.piv_seq = (int8_t) seq;
-        bci.level = (int8_t) ll;
-        for (int i = 0; i < 6; ++i) bci.pad_[i] = 0;
+        for (int i = lane; i < C2G_MAX_NEI + 2; i += 32) bci.seg[i] = i < nseg ? segv[i] : (uint16_t) 0;
+        __syncwarp();
       }
     }
-
     C2G_DBG(7);
     // ---------------- phase F: scan-only GMM terms (correlation.h:49-82,102-119) -----------------------------------
     __shared__ int n_ell_s[C2G_NUM_BIN_LAYERS];

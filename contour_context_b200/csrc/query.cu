@@ -17,6 +17,7 @@
 #include "../../include/c2g.h"
 #include "c2g_ctx.cuh"
 #include "stdsort.cuh"
+#include "c2g_libm.cuh"
 
 namespace {
 
@@ -362,8 +363,8 @@ __device__ void score_hint(const c2g_scan_head *heads, const c2g_view *views, in
     const c2g_view &sc1 = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src);
     const c2g_view &tc1 = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt);
     if (sc1.ecc_feat && tc1.ecc_feat) {
-      const float theta_s = acosf(ssx * sc1.eig_vecs[2] + ssy * sc1.eig_vecs[3]);
-      const float theta_t = acosf(stx * tc1.eig_vecs[2] + sty * tc1.eig_vecs[3]);
+      const float theta_s = c2g_acosf(ssx * sc1.eig_vecs[2] + ssy * sc1.eig_vecs[3]);
+      const float theta_t = c2g_acosf(stx * tc1.eig_vecs[2] + sty * tc1.eig_vecs[3]);
       const float pi6 = (float) (C2G_PI / 6);
       if (diff_delt_f(theta_s, theta_t, pi6) && diff_delt_f((float) (C2G_PI - (double) theta_s), theta_t, pi6)) {
         const CPairD tmp = sc.c2[i];
@@ -892,6 +893,16 @@ int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void *
   if (hints_dev) *hints_dev = ctx->d_hints;
   if (scores_dev) *scores_dev = ctx->d_scores;
   if (n_hint_slots) *n_hint_slots = ctx->n_hint_slots;
+  return 0;
+}
+
+int c2g_query_export(c2g_ctx *ctx, int B, void *hints_dst_dev, void *scores_dst_dev, void *results_dst_host) {
+  if (!ctx || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
+  const size_t nh = (size_t) B * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
+  if (hints_dst_dev) C2G_CUDA_TRY(cudaMemcpyAsync(hints_dst_dev, ctx->d_hints, sizeof(c2g_hint) * nh, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (scores_dst_dev) C2G_CUDA_TRY(cudaMemcpyAsync(scores_dst_dev, ctx->d_scores, sizeof(c2g_pair_score) * nh, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (results_dst_host)
+    C2G_CUDA_TRY(cudaMemcpyAsync(results_dst_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 

@@ -153,6 +153,11 @@ class Engine:
         capi.check(capi.lib().c2g_query_buffers(self.h, C.byref(r), C.byref(h), C.byref(s), C.byref(n)), "c2g_query_buffers")
         return r.value, h.value, s.value, n.value
 
+    def query_export(self, B: int, hints_dst=None, scores_dst=None, results_dst_host=None):
+        """Async copies of the last query's buffers: device tensors for hints / scores, a pinned host tensor for results."""
+        capi.check(capi.lib().c2g_query_export(self.h, B, capi.ptr(hints_dst), capi.ptr(scores_dst), capi.ptr(results_dst_host)),
+                   "c2g_query_export")
+
     def finish_from_scores(self, first_slot: int, B: int, lb: D.ScoreEnsemble, hints_dev: int, scores_dev: int):
         res = np.zeros(B, D.QUERY_RESULT_DTYPE)
         capi.check(capi.lib().c2g_finish_from_scores(self.h, first_slot, B, C.byref(lb), C.c_void_p(hints_dev),

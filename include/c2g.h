@@ -99,6 +99,9 @@ int c2g_query(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb,
  * owned by the context, valid until the next query call. */
 int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub);
 int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void **scores_dev, long long *n_hint_slots);
+/* Asynchronous export of the last query's buffers: hint / pair-score records to caller-owned DEVICE buffers (the send
+ * buffers of the multi-GPU all-gather) and/or the per-query results to a (pinned) HOST buffer. NULL skips a part. */
+int c2g_query_export(c2g_ctx *ctx, int B, void *hints_dst_dev, void *scores_dst_dev, void *results_dst_host);
 /* Finish a query from pair-score records produced elsewhere (multi-GPU: after the all-gather of score records):
  * replay CandidatePoseData::addProposal / tidyUpCandidates for B queries from device arrays laid out like
  * c2g_query_buffers'. */

@@ -25,16 +25,32 @@ def build(force: bool = False) -> None:
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    ref_so = os.path.join(_HERE, "_ref", "libref_knn.so")
-    if os.path.exists("/root/reference/thirdparty/nanoflann.hpp") and (force or not os.path.exists(ref_so)):
+    ref_so = os.path.join(_HERE, "_ref", "liboracle_nf.so")
+    ref_stale = force or not os.path.exists(ref_so) or any(os.path.getmtime(s) > os.path.getmtime(ref_so) for s in srcs)
+    if os.path.exists("/root/reference/thirdparty/nanoflann.hpp") and ref_stale:
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def use_nanoflann_build() -> bool:
+    """Switch to oracle/_ref/liboracle_nf.so (the restatement linked against the reference's own nanoflann KD-tree).
+    Must be called before the first lib() call; returns False if that build is not available."""
+    global _LIB_PATH
+    build()
+    p = os.path.join(_HERE, "_ref", "liboracle_nf.so")
+    if _LIB is None and os.path.exists(p):
+        _LIB_PATH = p
+        return True
+    return False
+
+
+_LIB_PATH = None
 
 
 def lib():
     global _LIB
     if _LIB is None:
         build()
-        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        L = C.CDLL(_LIB_PATH or os.path.join(_HERE, "liboracle.so"))
         L.c2o_scan_create.restype = C.c_void_p
         L.c2o_scan_create.argtypes = [C.POINTER(D.CmConfig), C.c_int]
         L.c2o_scan_free.argtypes = [C.c_void_p]
@@ -70,6 +86,9 @@ def lib():
         L.c2o_run_loop.argtypes = [C.c_void_p, C.POINTER(D.CmConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int, C.c_int, C.POINTER(D.ScoreEnsemble),
                                    C.POINTER(D.ScoreEnsemble), C.c_void_p, C.c_void_p]
+        L.c2o_scan_from_descriptor.restype = C.c_void_p
+        L.c2o_scan_from_descriptor.argtypes = [C.POINTER(D.CmConfig), C.c_void_p, C.c_void_p]
+        L.c2o_std_sort_words.argtypes = [C.c_void_p, C.c_int, C.c_int]
         assert L.c2o_sizeof_scan_head() == D.SCAN_HEAD_DTYPE.itemsize
         assert L.c2o_sizeof_query_result() == D.QUERY_RESULT_DTYPE.itemsize
         _LIB = L
@@ -101,9 +120,16 @@ def _ptr(a):
 class Scan:
     """One ContourManager (oracle side)."""
 
-    def __init__(self, cfg: D.CmConfig, int_id: int = 0):
+    def __init__(self, cfg: D.CmConfig, int_id: int = 0, _handle=None):
         self.cfg = cfg
-        self.h = lib().c2o_scan_create(C.byref(cfg), int_id)
+        self.h = _handle if _handle is not None else lib().c2o_scan_create(C.byref(cfg), int_id)
+
+    @classmethod
+    def from_descriptor(cls, cfg: D.CmConfig, head: np.ndarray, views: np.ndarray):
+        """head: one SCAN_HEAD_DTYPE record; views: the scan's VIEW_CAP-record arena (sorted, level by level)."""
+        head = np.ascontiguousarray(head).reshape(1)
+        views = np.ascontiguousarray(views)
+        return cls(cfg, _handle=lib().c2o_scan_from_descriptor(C.byref(cfg), _ptr(head), _ptr(views)))
 
     def __del__(self):
         if getattr(self, "h", None) and _LIB is not None:

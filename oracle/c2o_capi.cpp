@@ -197,3 +197,35 @@ extern "C" void c2o_test_push_key(void *db, int ll, const float *key, double ts,
   ContourDB *D = (ContourDB *) db;
   D->layer_db_[ll].pushBuffer(k, ts, IndexOfKey{(size_t) gidx, D->cfg_.q_levels[ll], seq});
 }
+
+// Build a Scan from a finished descriptor (head + sorted views) instead of from points: lets bench.py hand the CPU
+// baseline the same 5 000-scan database the GPU path built (descriptor parity is what tests/ establish) without spending
+// 40 s of single-thread CPU ingest before every baseline run.  The BEV image is not restored (the reference drops it
+// after ingest too, test/batch_bin_test.cpp:169).
+extern "C" void *c2o_scan_from_descriptor(const c2g_cm_config *cfg, const c2g_scan_head *head, const c2g_view *views) {
+  ScanPtr *h = new ScanPtr(std::make_shared<Scan>(*cfg, head->int_id));
+  Scan &s = **h;
+  std::vector<float>().swap(s.bev);
+  for (int l = 0; l < C2G_NLEV; ++l) {
+    s.cont_views[l].assign(views + head->view_off[l], views + head->view_off[l] + head->n_views[l]);
+    s.layer_cell_cnt[l] = head->layer_cell_cnt[l];
+    s.cont_perc[l].clear();
+    for (auto &v : s.cont_views[l]) s.cont_perc[l].push_back(v.cell_cnt * 1.0f / s.layer_cell_cnt[l]);
+    s.layer_keys[l].clear();
+    s.layer_key_bcis[l].clear();
+    for (int q = 0; q < cfg->piv_firsts; ++q) {
+      std::array<float, C2G_KEY_DIM> k;
+      for (int d = 0; d < C2G_KEY_DIM; ++d) k[d] = head->keys[l][q][d];
+      s.layer_keys[l].push_back(k);
+      s.layer_key_bcis[l].push_back(head->bcis[l][q]);
+    }
+  }
+  return h;
+}
+extern "C" int c2o_uses_nanoflann() {
+#ifdef C2O_USE_NANOFLANN
+  return 1;
+#else
+  return 0;
+#endif
+}

@@ -28,9 +28,35 @@
 
 #include "c2o_ingest.hpp"
 
+#ifdef C2O_USE_NANOFLANN
+// Built only by `make ref` (oracle/_ref/liboracle_nf.so) when the reference tree is present: the reference's own
+// vendored KD-tree (thirdparty/nanoflann.hpp + KDTreeVectorOfVectorsAdaptor.h, included from /root/reference, never
+// copied) replaces the exhaustive scan in TreeBucket::knnSearch, so that the timed CPU baseline searches exactly like the
+// reference does (leaf size 10, metric_L2, MyKNNResSet, SearchParams(10); contour_db.h:32-52,109-117, contour_db.cpp:381-403).
+#include <cstdint>
+#include <nanoflann.hpp>
+#include <KDTreeVectorOfVectorsAdaptor.h>
+#endif
+
 namespace c2o {
 
 using Key = std::array<float, C2G_KEY_DIM>;
+
+#ifdef C2O_USE_NANOFLANN
+typedef std::vector<Key> my_vector_of_vectors_t;
+typedef KDTreeVectorOfVectorsAdaptor<my_vector_of_vectors_t, float> my_kd_tree_t;
+template <typename DD, typename II = size_t, typename CC = size_t>
+class MyKNNResSet : public nanoflann::KNNResultSet<DD, II, CC> {
+ public:
+  explicit MyKNNResSet(CC capacity_) : nanoflann::KNNResultSet<DD, II, CC>(capacity_) {}
+  void init(II *indices_, DD *dists_, DD max_dist_metric) {
+    this->indices = indices_;
+    this->dists = dists_;
+    this->count = 0;
+    if (this->capacity) this->dists[this->capacity - 1] = max_dist_metric;
+  }
+};
+#endif
 
 inline float keySum(const Key &k) {  // ArrayAsKey::sum (contour_mng.h:74-79)
   float ret(0);
@@ -411,6 +437,9 @@ struct TreeBucket {
   std::vector<Key> data_tree;
   bool has_tree = false;      // tree_ptr != nullptr
   size_t indexed_size = 0;    // number of points in the built index
+#ifdef C2O_USE_NANOFLANN
+  std::shared_ptr<my_kd_tree_t> tree_ptr;
+#endif
   std::vector<RetrTriplet> buffer;
   std::vector<IndexOfKey> gkidx_tree;
 
@@ -424,6 +453,15 @@ struct TreeBucket {
   void rebuildTree() {
     has_tree = true;
     indexed_size = data_tree.size();
+#ifdef C2O_USE_NANOFLANN
+    if (data_tree.empty()) {
+      tree_ptr.reset();
+      has_tree = false;
+    } else if (tree_ptr)
+      tree_ptr->index->buildIndex();
+    else
+      tree_ptr = std::make_shared<my_kd_tree_t>(C2G_KEY_DIM, data_tree, 10);
+#endif
   }
   void popBufferMax(double curr_ts) {
     double ts_cutoff = curr_ts - min_elapse;
@@ -446,6 +484,15 @@ struct TreeBucket {
     out_dist_sq.assign(num_res, MAX_DIST_SQ);
     if (!has_tree) return;
     std::vector<size_t> idx(num_res, 0);
+#ifdef C2O_USE_NANOFLANN
+    {
+      MyKNNResSet<float> resultSet(num_res);
+      resultSet.init(&idx[0], &out_dist_sq[0], max_dist_sq);
+      tree_ptr->index->findNeighbors(resultSet, q.data(), nanoflann::SearchParams(10));
+      for (int i = 0; i < num_res; i++) ret_idx.push_back(gkidx_tree[idx[i]]);
+      return;
+    }
+#endif
     size_t count = 0;
     const size_t capacity = (size_t) num_res;
     if (capacity) out_dist_sq[capacity - 1] = max_dist_sq;
@@ -930,11 +977,10 @@ struct ContourDB {
     for (int i = 0; i < cfg_.n_q_levels; ++i) layer_db_.emplace_back(cfg_.max_elapse, cfg_.min_elapse);
   }
 
-  const GMMScanData &gmmOf(const Scan *s) {
-    auto it = gmm_cache_.find(s);
-    if (it == gmm_cache_.end()) it = gmm_cache_.emplace(s, buildGMMScan(*s)).first;
-    return it->second;
-  }
+  // DB scans get their scan-only GMM terms when they are added (read-only afterwards, so concurrent queries are safe);
+  // the query scan's own terms are built once per query.  NOTE: the reference rebuilds both inside every initProblem
+  // (correlation.h:42-122); caching them makes this CPU baseline FASTER than the reference, never slower.
+  const GMMScanData &gmmOfDb(const Scan *s) const { return gmm_cache_.at(s); }
 
   // queryRangedKNN (contour_db.h:698-811)
   void queryRangedKNN(const std::shared_ptr<const Scan> &q_ptr, const c2g_score_ensemble &thres_lb,
@@ -990,7 +1036,15 @@ struct ContourDB {
       }
     }
     double t2 = now();
-    cand_mng.tidyUpCandidates([this](const Scan *s) -> const GMMScanData & { return gmmOf(s); });
+    std::unique_ptr<GMMScanData> q_gmm;
+    const Scan *q_raw = q_ptr.get();
+    cand_mng.tidyUpCandidates([this, &q_gmm, q_raw](const Scan *s) -> const GMMScanData & {
+      if (s == q_raw) {
+        if (!q_gmm) q_gmm.reset(new GMMScanData(buildGMMScan(*s)));
+        return *q_gmm;
+      }
+      return gmmOfDb(s);
+    });
     cand_mng.fineOptimize(cfg_.max_fine_opt);
     if (t_l2) *t_l2 += now() - t2;
     out.n_pose_before = cand_mng.n_pose_before;
@@ -1024,6 +1078,7 @@ struct ContourDB {
         seq++;
       }
     }
+    gmm_cache_.emplace(added.get(), buildGMMScan(*added));
     all_bevs_.emplace_back(added);
   }
 

@@ -14,6 +14,7 @@ for i0 in range(0, B, 74):
     seeds, visits = synth.db_layout(n, 4, first_scene=i0 // 4)
     chunks.append(synth.make_scans(seeds, visits, N, device="cuda", noise_seed=i0))
 pts = torch.cat(chunks).reshape(-1, 4).contiguous()
+torch.cuda.synchronize()
 offsets = np.arange(B + 1, dtype=np.int64) * N
 st = torch.cuda.Stream()
 eng.set_stream(st.cuda_stream)
