@@ -72,6 +72,16 @@ __device__ __forceinline__ uint32_t uf_find(volatile uint32_t *L, uint32_t c) {
   }
   return c;
 }
+// read-only variant for the flatten phase: there every thread stores the final root into its OWN cells, and a path-halving
+// store from another thread could overwrite that root with a stale ancestor
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t *L, uint32_t c) {
+  uint32_t p = L[c] & 0xFFFFu;
+  while (p != c) {
+    c = p;
+    p = L[c] & 0xFFFFu;
+  }
+  return c;
+}
 __device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b) {
   while (true) {
     a = uf_find(L, a);
@@ -375,7 +385,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         bool in_run = false;
         for (int c = cb0; c < cb1; ++c) {
           if (S.msk[c] & bit) {
-            if (!in_run || (c % ncol) == 0) root = uf_find(S.L, c);
+            if (!in_run || (c % ncol) == 0) root = uf_find_ro(S.L, c);
             in_run = true;
             S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
           } else
