@@ -457,6 +457,12 @@ score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict
 // ------------------------------------------------------------------------------------------------------------------
 // Proposal replay + tidy-up + GMM-L2 initial correlation, one warp per query scan
 // ------------------------------------------------------------------------------------------------------------------
+struct EllD {
+  double mx, my, c00, c10, c01, c11;
+  float maj, w;
+};
+constexpr int ELL_CAP = 128;
+
 struct Prop {
   double T[4];  // cos, sin, tx, ty
   uint64_t bits[C2G_PAIR_WORDS];
@@ -476,6 +482,7 @@ struct FinishScratch {
   uint32_t ord[C2G_MAX_CAND];
   float corr[C2G_MAX_CAND];
   uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64];  // hint indices that reached addProposal, in order
+  EllD es[ELL_CAP], et[ELL_CAP];                                // one level's ellipses of candidate / query
 };
 
 __device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
@@ -493,8 +500,29 @@ __device__ __forceinline__ void manual_cov_d(const c2g_view &v, double out[4]) {
 }
 
 // GMM-L2 initial correlation (correlation.h:84-96,125-152,196-202); all lanes of the warp cooperate, every lane returns
-// the same value.  src = candidate, tgt = query.
-__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *views, int src_slot, int tgt_slot, const double T[4], int lane) {
+// the same value.  src = candidate, tgt = query.  The ellipses of one level are staged in shared memory first (mean,
+// dilatable covariance, pre-selection radius, weight), so the O(n_src * n_tgt) pre-selection runs out of shared memory.
+
+__device__ __forceinline__ void stage_ellipses(const c2g_view *v, int n, EllD *dst, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    const c2g_view &a = v[i];
+    double c[4];
+    manual_cov_d(a, c);
+    EllD e;
+    e.mx = (double) a.pos_mean[0];
+    e.my = (double) a.pos_mean[1];
+    e.c00 = c[0];
+    e.c10 = c[1];
+    e.c01 = c[2];
+    e.c11 = c[3];
+    e.maj = sqrtf(a.eig_vals[1]);
+    e.w = (float) a.cell_cnt;
+    dst[i] = e;
+  }
+}
+
+__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *views, int src_slot, int tgt_slot, const double T[4], int lane,
+                                EllD *es, EllD *et) {
   const double theta = atan2(T[1], T[0]);
   const double c = cos(theta), s = sin(theta);
   double cost = 0.0;
@@ -503,28 +531,32 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *view
     const int ns = heads[src_slot].n_ell[li], nt = heads[tgt_slot].n_ell[li];
     const c2g_view *sv = views + (size_t) src_slot * C2G_VIEW_CAP + heads[src_slot].view_off[lev];
     const c2g_view *tv = views + (size_t) tgt_slot * C2G_VIEW_CAP + heads[tgt_slot].view_off[lev];
-    for (int w = lane; w < ns * nt; w += 32) {
-      const int si = w / nt, ti = w - si * nt;
-      const c2g_view &a = sv[si], &b = tv[ti];
-      const double amx = (double) a.pos_mean[0], amy = (double) a.pos_mean[1];
-      const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
-      const double ddx = qx - (double) b.pos_mean[0], ddy = qy - (double) b.pos_mean[1];
-      const float maj = sqrtf(a.eig_vals[1]) + sqrtf(b.eig_vals[1]);
-      if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) maj)) continue;
-      double ca[4], cb[4];
-      manual_cov_d(a, ca);
-      manual_cov_d(b, cb);
-      const double t00 = c * ca[0] + (-s) * ca[1], t01 = c * ca[2] + (-s) * ca[3];
-      const double t10 = s * ca[0] + c * ca[1], t11 = s * ca[2] + c * ca[3];
-      const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
-      const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
-      const double c00 = 2.0 * (ra00 + cb[0]), c10 = 2.0 * (ra10 + cb[1]), c01 = 2.0 * (ra01 + cb[2]), c11 = 2.0 * (ra11 + cb[3]);
-      const double mx = (c * amx + (-s) * amy) + T[2] - (double) b.pos_mean[0];
-      const double my = (s * amx + c * amy) + T[3] - (double) b.pos_mean[1];
-      const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
-      const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
-      cost += -(double) b.cell_cnt * (double) a.cell_cnt * 1.0 / sqrt(det) * exp(qua);
-    }
+    for (int s0 = 0; s0 < ns; s0 += ELL_CAP)
+      for (int t0 = 0; t0 < nt; t0 += ELL_CAP) {
+        const int cs_ = min(ELL_CAP, ns - s0), ct_ = min(ELL_CAP, nt - t0);
+        __syncwarp();
+        stage_ellipses(sv + s0, cs_, es, lane);
+        stage_ellipses(tv + t0, ct_, et, lane);
+        __syncwarp();
+        for (int w = lane; w < cs_ * ct_; w += 32) {
+          const int si = w / ct_, ti = w - si * ct_;
+          const EllD a = es[si];
+          const EllD b = et[ti];
+          const double qx = (T[0] * a.mx + (-T[1]) * a.my) + T[2], qy = (T[1] * a.mx + T[0] * a.my) + T[3];
+          const double ddx = qx - b.mx, ddy = qy - b.my;
+          if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + b.maj))) continue;
+          const double t00 = c * a.c00 + (-s) * a.c10, t01 = c * a.c01 + (-s) * a.c11;
+          const double t10 = s * a.c00 + c * a.c10, t11 = s * a.c01 + c * a.c11;
+          const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
+          const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
+          const double c00 = 2.0 * (ra00 + b.c00), c10 = 2.0 * (ra10 + b.c10), c01 = 2.0 * (ra01 + b.c01), c11 = 2.0 * (ra11 + b.c11);
+          const double mx = (c * a.mx + (-s) * a.my) + T[2] - b.mx;
+          const double my = (s * a.mx + c * a.my) + T[3] - b.my;
+          const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
+          const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
+          cost += -(double) b.w * (double) a.w * 1.0 / sqrt(det) * exp(qua);
+        }
+      }
   }
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
   return -cost / sqrt(heads[src_slot].gmm_auto_corr * heads[tgt_slot].gmm_auto_corr);
@@ -628,21 +660,36 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
   for (int ci = 0; ci < n_before; ++ci) {
     CandState &cs = F.cand[ci];
     int pass = 0;
+    // area_perc of every proposal: lanes evaluate the per-pair percentages of 32 map entries at a time, the float sums
+    // run in std::map order (ascending (level, seq_src, seq_tgt) == ascending bit index) on all lanes redundantly
+    for (int i = 0; i < cs.n_prop; i++) {
+      float lev_perc[C2G_NLEV] = {0, 0, 0, 0, 0, 0};
+      for (int base = 0; base < C2G_PAIR_BITS; base += 32) {
+        const int bit = base + lane;
+        const bool set = bit < C2G_PAIR_BITS && ((cs.prop[i].bits[bit >> 6] >> (bit & 63)) & 1ull);
+        float pv = 0.0f;
+        if (set) {
+          const int level = bit / 100 + 1, ss = (bit / 10) % 10, st = bit % 10;
+          pv = 0.5f * (cont_perc(heads, views, cs.gidx, level, ss) + cont_perc(heads, views, q_slot, level, st));
+        }
+        unsigned m = __ballot_sync(0xFFFFFFFFu, set);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float v = __shfl_sync(0xFFFFFFFFu, pv, src);
+          lev_perc[(base + src) / 100 + 1] += v;
+        }
+      }
+      const float LW[4] = {0.3f, 0.3f, 0.3f, 0.1f};
+      float perc = 0;
+      for (int j = 0; j < C2G_NUM_BIN_LAYERS; j++) perc += LW[j] * lev_perc[j + 1];
+      if (lane == 0) cs.prop[i].area_perc = perc;
+    }
+    __syncwarp();
     if (lane == 0) {
       int idx_sel = 0;
-      for (int i = 0; i < cs.n_prop; i++) {
-        float lev_perc[C2G_NLEV] = {0, 0, 0, 0, 0, 0};
-        for (int bit = 0; bit < C2G_PAIR_BITS; ++bit)  // std::map iteration order == ascending (level, seq_src, seq_tgt)
-          if ((cs.prop[i].bits[bit >> 6] >> (bit & 63)) & 1ull) {
-            const int level = bit / 100 + 1, ss = (bit / 10) % 10, st = bit % 10;
-            lev_perc[level] += 0.5f * (cont_perc(heads, views, cs.gidx, level, ss) + cont_perc(heads, views, q_slot, level, st));
-          }
-        const float LW[4] = {0.3f, 0.3f, 0.3f, 0.1f};
-        float perc = 0;
-        for (int j = 0; j < C2G_NUM_BIN_LAYERS; j++) perc += LW[j] * lev_perc[j + 1];
-        cs.prop[i].area_perc = perc;
+      for (int i = 0; i < cs.n_prop; i++)
         if (cs.prop[i].vote_cnt > cs.prop[idx_sel].vote_cnt) idx_sel = i;
-      }
       if (idx_sel != 0) {
         const Prop tmp = cs.prop[0];
         cs.prop[0] = cs.prop[idx_sel];
@@ -663,7 +710,7 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
     pass = __shfl_sync(0xFFFFFFFFu, pass, 0);
     if (pass) {
       __syncwarp();
-      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane);
+      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane, F.es, F.et);
       if (lane == 0) {
         cs.corr_init = (float) corr;
         cs.alive = (cs.corr_init < Q.lb.correlation) ? 0 : 1;
@@ -754,7 +801,7 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
 
 int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores) {
   static bool attr_set = false;
-  const int warps = 4;
+  const int warps = 2;
   const size_t smem = sizeof(FinishScratch) * warps;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

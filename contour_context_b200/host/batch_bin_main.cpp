@@ -1,0 +1,89 @@
+// batch_bin_main.cpp — ROS-free equivalent of the reference's cont2_batch_bin_test main loop
+// (test/batch_bin_test.cpp:105-247: load scan -> make bev -> query -> add -> balance), driving the facade classes with the
+// same call sequence.  Input: a text file with one "<timestamp> <path/to/scan.bin>" per line (the layout of the
+// reference's ts-lidar_bins-*.txt lists) and, optionally, MulRan/KITTI parameter selection by argv.
+//   usage: cont2_batch_bin <list.txt> [kitti|mulran]
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+#include "cont2/contour_db.h"
+
+SequentialTimeProfiler stp;  // the library's stage timers write here, like the reference executable
+
+static std::vector<float> readKITTIBin(const std::string &path) {  // tools/pointcloud_util.h:12-50 (format: N x 4 f32)
+  std::vector<float> buf;
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) {
+    std::printf("Lidar bin file %s does not exist.\n", path.c_str());
+    std::exit(-1);
+  }
+  buf.resize(1000000);
+  size_t n = std::fread(buf.data(), sizeof(float), buf.size(), f) / 4;
+  std::fclose(f);
+  buf.resize(n * 4);
+  return buf;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::printf("usage: %s <ts-lidar_bins.txt> [kitti|mulran]\n", argv[0]);
+    return 1;
+  }
+  const bool mulran = argc > 2 && std::string(argv[2]) == "mulran";
+  ContourManagerConfig cm_config;  // config/batch_bin_test_config.yaml:28-46
+  cm_config.lv_grads_ = mulran ? std::vector<float>{1.0f, 2.5f, 4.0f, 5.5f, 7.0f, 8.5f} : std::vector<float>{1.5f, 2.f, 2.5f, 3.f, 3.5f, 4.f};
+  ContourDBConfig db_config;       // config/batch_bin_test_config.yaml:6-23
+  db_config.q_levels_ = {1, 2, 3};
+  db_config.cont_sim_cfg_.ta_h_bar = mulran ? 0.75f : 0.3f;
+  CandidateScoreEnsemble thres_lb_, thres_ub_;  // config/batch_bin_test_config.yaml:70-87
+  thres_lb_.sim_constell.i_ovlp_sum = 3, thres_lb_.sim_constell.i_ovlp_max_one = 3, thres_lb_.sim_constell.i_in_ang_rng = 3;
+  thres_lb_.sim_pair.i_indiv_sim = 3, thres_lb_.sim_pair.i_orie_sim = 4;
+  thres_lb_.sim_post.correlation = 0.3f, thres_lb_.sim_post.area_perc = 0.03f, thres_lb_.sim_post.neg_est_dist = -5.01f;
+  thres_ub_.sim_constell.i_ovlp_sum = 6, thres_ub_.sim_constell.i_ovlp_max_one = 6, thres_ub_.sim_constell.i_in_ang_rng = 6;
+  thres_ub_.sim_pair.i_indiv_sim = 6, thres_ub_.sim_pair.i_orie_sim = 6;
+  thres_ub_.sim_post.correlation = 0.75f, thres_ub_.sim_post.area_perc = 0.15f, thres_ub_.sim_post.neg_est_dist = -5.0f;
+
+  ContourDB contour_db(db_config);
+  std::ifstream list(argv[1]);
+  std::string line;
+  int seq = 0, n_pos = 0;
+  while (std::getline(list, line)) {
+    std::istringstream ss(line);
+    double ts;
+    std::string path;
+    if (!(ss >> ts >> path)) continue;
+    stp.lap();
+    stp.start();
+    std::shared_ptr<ContourManager> ptr_cm_tgt(new ContourManager(cm_config, seq));
+    std::vector<float> bin = readKITTIBin(path);
+    ptr_cm_tgt->makeBEVFromBin(bin.data(), bin.size() / 4, "assigned_id_" + std::to_string(seq));
+    ptr_cm_tgt->makeContoursRecurs();
+    stp.record("make bev");
+    ptr_cm_tgt->clearImage();
+
+    std::vector<std::shared_ptr<const ContourManager>> ptr_cands;
+    std::vector<double> cand_corr;
+    std::vector<Eigen::Isometry2d> bev_tfs;
+    contour_db.queryRangedKNN(ptr_cm_tgt, thres_lb_, thres_ub_, ptr_cands, cand_corr, bev_tfs);
+    if (ptr_cands.size() >= 2) std::abort();  // CHECK(ptr_cands.size() < 2) (batch_bin_test.cpp:187)
+    if (!ptr_cands.empty()) {
+      n_pos++;
+      const Eigen::Isometry2d &T = bev_tfs[0];
+      const double est = ConstellCorrelation::getEstSensTF(T, cm_config).translation().norm();
+      std::printf("LC %d -> %d corr %.6f  T(bev) = [%.4f %.4f %.4f]  est. dist %.3f m\n", seq, ptr_cands[0]->getIntID(), cand_corr[0],
+                  T(0, 2), T(1, 2), std::atan2(T(1, 0), T(0, 0)), est);
+    } else {
+      std::printf("LC %d -> none\n", seq);
+    }
+    stp.start();
+    contour_db.addScan(ptr_cm_tgt, ts);
+    contour_db.pushAndBalance(seq, ts);
+    stp.record("Update database");
+    seq++;
+  }
+  std::printf("scans: %d, positive predictions: %d\n", seq, n_pos);
+  stp.printScreen();
+  return 0;
+}

@@ -1,0 +1,46 @@
+// cont2/contour_db.h (facade) — the reference's ContourDB surface (include/cont2/contour_db.h:658-845) over the C-ABI.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "cont2/contour_mng.h"
+#include "cont2/correlation.h"
+#include "tools/bm_util.h"
+
+extern SequentialTimeProfiler stp;  // defined by the executable, like the reference (contour_db.h:23)
+
+struct TreeBucketConfig {  // reference contour_db.h:54-57
+  double max_elapse_ = 25.0;
+  double min_elapse_ = 15.0;
+};
+
+struct CandidateScoreEnsemble {  // reference contour_db.h:244-250
+  ScoreConstellSim sim_constell;
+  ScorePairwiseSim sim_pair;
+  ScorePostProc sim_post;
+};
+
+struct ContourDBConfig {  // reference contour_db.h:658-669
+  int nnk_ = 50;
+  int max_fine_opt_ = 10;
+  std::vector<int> q_levels_;
+  ContourSimThresConfig cont_sim_cfg_;
+  TreeBucketConfig tb_cfg_;
+};
+
+class ContourDB {
+  const ContourDBConfig cfg_;
+  std::vector<std::shared_ptr<const ContourManager>> all_bevs_;
+
+ public:
+  ContourDB(const ContourDBConfig &config);
+
+  // reference contour_db.h:698-811. NOTE: the Ceres refinement of fineOptimize is not part of this build:
+  // the returned correlation / transform are the initial GMM-L2 correlation and the constellation transform.
+  void queryRangedKNN(const std::shared_ptr<const ContourManager> &q_ptr, const CandidateScoreEnsemble &thres_lb,
+                      const CandidateScoreEnsemble &thres_ub, std::vector<std::shared_ptr<const ContourManager>> &cand_ptrs,
+                      std::vector<double> &cand_corr, std::vector<Eigen::Isometry2d> &cand_tf) const;
+  void addScan(const std::shared_ptr<ContourManager> &added, double curr_timestamp);  // reference contour_db.h:814-824
+  void pushAndBalance(int seed, double curr_timestamp);                               // reference contour_db.h:827-843
+  size_t size() const { return all_bevs_.size(); }
+};

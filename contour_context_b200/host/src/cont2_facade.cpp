@@ -1,0 +1,257 @@
+// cont2_facade.cpp — ContourManager / ContourDB (reference names and call sequence) implemented on the C-ABI of
+// libc2g.so.  Error convention of the reference: no exceptions, CHECK-style abort on failure.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "cont2/contour_db.h"
+
+#define C2G_CHECK(expr)                                                              \
+  do {                                                                               \
+    int rc__ = (expr);                                                               \
+    if (rc__ != 0) {                                                                 \
+      std::fprintf(stderr, "CHECK failed: %s -> %d (%s:%d)\n", #expr, rc__, __FILE__, __LINE__); \
+      std::abort();                                                                  \
+    }                                                                                \
+  } while (0)
+
+namespace c2g_host {
+
+struct Runtime {
+  c2g_ctx *ctx = nullptr;
+  c2g_cm_config cm{};
+  c2g_db_config db{};
+  bool have_cm = false, have_db = false;
+  int capacity = 8192;
+  int n_staging = 64;          // slots [capacity - n_staging, capacity) hold scans that are not (yet) in the DB
+  std::vector<int> free_slots;
+
+  void setCm(const ContourManagerConfig &c) {
+    if (have_cm) return;
+    std::memset(&cm, 0, sizeof(cm));
+    if (c.lv_grads_.size() != C2G_NLEV) {
+      std::fprintf(stderr, "CHECK failed: lv_grads_ must have %d levels\n", C2G_NLEV);
+      std::abort();
+    }
+    for (int i = 0; i < C2G_NLEV; ++i) cm.lv_grads[i] = c.lv_grads_[i];
+    cm.n_levels = C2G_NLEV;
+    cm.reso_row = c.reso_row_;
+    cm.reso_col = c.reso_col_;
+    cm.n_row = c.n_row_;
+    cm.n_col = c.n_col_;
+    cm.lidar_height = c.lidar_height_;
+    cm.blind_sq = c.blind_sq_;
+    cm.min_cont_key_cnt = c.min_cont_key_cnt_;
+    cm.min_cont_cell_cnt = c.min_cont_cell_cnt_;
+    cm.piv_firsts = c.piv_firsts_;
+    cm.dist_firsts = c.dist_firsts_;
+    cm.roi_radius = c.roi_radius_;
+    ContourViewStatConfig vs;
+    cm.min_cell_cov = vs.min_cell_cov;
+    cm.point_sigma = vs.point_sigma;
+    cm.com_bias_thres = vs.com_bias_thres;
+    have_cm = true;
+  }
+  void setDb(const ContourDBConfig &c) {
+    if (have_db) return;
+    std::memset(&db, 0, sizeof(db));
+    db.nnk = c.nnk_;
+    db.max_fine_opt = c.max_fine_opt_;
+    db.n_q_levels = (int) c.q_levels_.size();
+    for (int i = 0; i < db.n_q_levels && i < C2G_NUM_Q_LEVELS_MAX; ++i) db.q_levels[i] = c.q_levels_[i];
+    db.cont_sim.ta_cell_cnt = c.cont_sim_cfg_.ta_cell_cnt;
+    db.cont_sim.tp_cell_cnt = c.cont_sim_cfg_.tp_cell_cnt;
+    db.cont_sim.tp_eigval = c.cont_sim_cfg_.tp_eigval;
+    db.cont_sim.ta_h_bar = c.cont_sim_cfg_.ta_h_bar;
+    db.cont_sim.ta_rcom = c.cont_sim_cfg_.ta_rcom;
+    db.cont_sim.tp_rcom = c.cont_sim_cfg_.tp_rcom;
+    db.max_elapse = c.tb_cfg_.max_elapse_;
+    db.min_elapse = c.tb_cfg_.min_elapse_;
+    have_db = true;
+  }
+  void ensure() {
+    if (ctx) return;
+    if (!have_cm) {
+      std::fprintf(stderr, "CHECK failed: no ContourManagerConfig seen before the first GPU call\n");
+      std::abort();
+    }
+    if (!have_db) {  // a ContourManager used without any ContourDB: defaults of config/batch_bin_test_config.yaml
+      ContourDBConfig d;
+      d.q_levels_ = {1, 2, 3};
+      setDb(d);
+    }
+    if (const char *e = std::getenv("C2G_SCAN_CAPACITY")) capacity = std::atoi(e);
+    int dev = 0;
+    if (const char *e = std::getenv("C2G_DEVICE")) dev = std::atoi(e);
+    C2G_CHECK(c2g_create(&cm, &db, dev, capacity, 1, 1 << 18, &ctx));
+    for (int s = capacity - 1; s >= capacity - n_staging; --s) free_slots.push_back(s);
+  }
+  int acquire() {
+    ensure();
+    if (free_slots.empty()) {
+      std::fprintf(stderr, "CHECK failed: more than %d scans alive outside the database\n", n_staging);
+      std::abort();
+    }
+    int s = free_slots.back();
+    free_slots.pop_back();
+    return s;
+  }
+  void release(int s) {
+    if (s >= capacity - n_staging) free_slots.push_back(s);
+  }
+  ~Runtime() {
+    if (ctx) c2g_destroy(ctx);
+  }
+};
+
+Runtime &runtime() {
+  static Runtime r;
+  return r;
+}
+
+}  // namespace c2g_host
+
+using c2g_host::runtime;
+
+// ---------------------------------------------------------------------------------------------------------------------
+ContourManager::ContourManager(const ContourManagerConfig &config, int int_id) : cfg_(config), int_id_(int_id) {
+  if (cfg_.n_col_ % 2 != 0 || cfg_.n_row_ % 2 != 0) {  // CHECKs of the reference constructor (contour_mng.h:479-480)
+    std::fprintf(stderr, "CHECK failed: n_row_/n_col_ must be even\n");
+    std::abort();
+  }
+  runtime().setCm(config);
+  std::memset(&head_, 0, sizeof(head_));
+  cont_views_.resize(cfg_.lv_grads_.size());
+  layer_keys_.resize(cfg_.lv_grads_.size());
+  layer_key_bcis_.resize(cfg_.lv_grads_.size());
+}
+
+ContourManager::~ContourManager() {
+  if (owns_slot_ && slot_ >= 0) runtime().release(slot_);
+}
+
+void ContourManager::makeBEVFromBin(const float *xyzi, size_t n_points, std::string str_id) {
+  pts_.assign(xyzi, xyzi + 4 * n_points);
+  str_id_ = std::move(str_id);
+}
+
+void ContourManager::makeContoursRecurs() {
+  if (pts_.size() / 4 <= 10) {  // CHECK_GT(ptr_gapc->size(), 10) of makeBEV (contour_mng.h:507)
+    std::fprintf(stderr, "CHECK failed: point cloud has <= 10 points\n");
+    std::abort();
+  }
+  auto &rt = runtime();
+  if (slot_ < 0) {
+    slot_ = rt.acquire();
+    owns_slot_ = true;
+  }
+  const long long offsets[2] = {0, (long long) (pts_.size() / 4)};
+  C2G_CHECK(c2g_ingest(rt.ctx, pts_.data(), offsets, 1, 0, slot_, &int_id_));
+  C2G_CHECK(c2g_get_heads(rt.ctx, slot_, 1, &head_));
+  if (head_.status != 0) {
+    std::fprintf(stderr, "CHECK failed: scan %d exceeded a descriptor capacity (status %d)\n", int_id_, head_.status);
+    std::abort();
+  }
+  std::vector<float>().swap(pts_);
+  views_loaded_ = false;
+  for (size_t ll = 0; ll < cfg_.lv_grads_.size(); ++ll) {
+    layer_keys_[ll].clear();
+    layer_key_bcis_[ll].clear();
+    for (int seq = 0; seq < cfg_.piv_firsts_; ++seq) {
+      RetrievalKey k;
+      for (int d = 0; d < RET_KEY_DIM; ++d) k[d] = head_.keys[ll][seq][d];
+      layer_keys_[ll].push_back(k);
+      const c2g_bci &b = head_.bcis[ll][seq];
+      BCI bci(b.piv_seq, b.level);
+      for (int w = 0; w < C2G_NUM_BIN_LAYERS; ++w)
+        for (int bit = 0; bit < 64; ++bit)
+          if ((b.dist_bin[w] >> bit) & 1ull) bci.dist_bin_.set(w * 64 + bit, true);
+      for (int i = 0; i < b.n_nei; ++i)
+        bci.nei_pts_.emplace_back(b.nei[i].level, b.nei[i].seq, b.nei[i].bit_pos, b.nei[i].r, b.nei[i].theta);
+      for (int i = 0; i < b.n_seg; ++i) bci.nei_idx_segs_.push_back(b.seg[i]);
+      layer_key_bcis_[ll].push_back(bci);
+    }
+  }
+}
+
+void ContourManager::loadViews() const {
+  if (views_loaded_ || slot_ < 0) return;
+  std::vector<c2g_view> raw(C2G_VIEW_CAP);
+  C2G_CHECK(c2g_get_views(runtime().ctx, slot_, raw.data()));
+  for (size_t ll = 0; ll < cfg_.lv_grads_.size(); ++ll) {
+    cont_views_[ll].clear();
+    for (int i = 0; i < head_.n_views[ll]; ++i)
+      cont_views_[ll].push_back(std::make_shared<ContourView>(raw[head_.view_off[ll] + i]));
+  }
+  views_loaded_ = true;
+}
+
+std::vector<float> ContourManager::getBevImage() const {
+  // only valid right after makeContoursRecurs of this scan (the dense BEV lives in per-batch scratch memory)
+  std::vector<float> bev((size_t) cfg_.n_row_ * cfg_.n_col_);
+  C2G_CHECK(c2g_get_bev(runtime().ctx, 0, bev.data(), nullptr, nullptr));
+  return bev;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+ContourDB::ContourDB(const ContourDBConfig &config) : cfg_(config) {
+  if (cfg_.q_levels_.empty()) {  // CHECK(!cfg_.q_levels_.empty()) (contour_db.h:683)
+    std::fprintf(stderr, "CHECK failed: q_levels_ empty\n");
+    std::abort();
+  }
+  runtime().setDb(config);
+}
+
+void ContourDB::addScan(const std::shared_ptr<ContourManager> &added, double curr_timestamp) {
+  auto &rt = runtime();
+  rt.ensure();
+  const int gidx = (int) all_bevs_.size();
+  if (gidx >= rt.capacity - rt.n_staging) {
+    std::fprintf(stderr, "CHECK failed: database capacity (C2G_SCAN_CAPACITY) exhausted\n");
+    std::abort();
+  }
+  // the descriptor moves from its staging slot to slot == gidx (IndexOfKey::gidx, contour_db.h:819)
+  C2G_CHECK(c2g_copy_slots(rt.ctx, added->slot_, gidx, 1));
+  if (added->owns_slot_) rt.release(added->slot_);
+  added->slot_ = gidx;
+  added->owns_slot_ = false;
+  C2G_CHECK(c2g_db_add_scans(rt.ctx, gidx, 1, &curr_timestamp));
+  all_bevs_.emplace_back(added);
+}
+
+void ContourDB::pushAndBalance(int seed, double curr_timestamp) { C2G_CHECK(c2g_db_push_and_balance(runtime().ctx, seed, curr_timestamp)); }
+
+void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_ptr, const CandidateScoreEnsemble &thres_lb,
+                               const CandidateScoreEnsemble &thres_ub, std::vector<std::shared_ptr<const ContourManager>> &cand_ptrs,
+                               std::vector<double> &cand_corr, std::vector<Eigen::Isometry2d> &cand_tf) const {
+  cand_ptrs.clear();
+  cand_corr.clear();
+  cand_tf.clear();
+  auto pack = [](const CandidateScoreEnsemble &e) {
+    c2g_score_ensemble s;
+    s.i_ovlp_sum = e.sim_constell.i_ovlp_sum;
+    s.i_ovlp_max_one = e.sim_constell.i_ovlp_max_one;
+    s.i_in_ang_rng = e.sim_constell.i_in_ang_rng;
+    s.i_indiv_sim = e.sim_pair.i_indiv_sim;
+    s.i_orie_sim = e.sim_pair.i_orie_sim;
+    s.correlation = e.sim_post.correlation;
+    s.area_perc = e.sim_post.area_perc;
+    s.neg_est_dist = e.sim_post.neg_est_dist;
+    return s;
+  };
+  const c2g_score_ensemble lb = pack(thres_lb), ub = pack(thres_ub);
+  c2g_query_result res;
+  stp.start();
+  C2G_CHECK(c2g_query(runtime().ctx, q_ptr->deviceSlot(), 1, &lb, &ub, &res, nullptr, nullptr));
+  stp.record("KNN search+Constell+L2 opt (GPU)");
+  if (res.n_cand > 0 && res.best >= 0) {  // ret_size = 1 (contour_db.h:639)
+    const c2g_cand &c = res.cand[res.best];
+    cand_ptrs.emplace_back(all_bevs_[c.cand_gidx]);
+    cand_corr.emplace_back((double) c.corr_init);
+    Eigen::Isometry2d T;
+    T.setIdentity();
+    T.rotate(std::atan2(c.T[1], c.T[0]));
+    T.pretranslate(V2D(c.T[2], c.T[3]));
+    cand_tf.emplace_back(T);
+  }
+}
