@@ -283,7 +283,7 @@ def run_b200(args):
                          "peak_source": peak_src,
                          "bev_scatter_only": {"achieved": ach_bev, "frac": ach_bev / peak, "ms": kern["bev_scatter_ms"]},
                          "kernel_ms": kern},
-            "sanity": {"queries_with_loop_candidate": n_found, "of": int(Q), "db_build_s": t_setup},
+            "sanity": {"queries_with_loop_candidate": n_found, "of": int(Q), "db_build_s": t_setup, "exp_mode": eng.exp_mode()},
         }
     if world > 1:
         dist.barrier()

@@ -8,6 +8,7 @@
 #include "../../include/c2g.h"
 #include "c2g_common.cuh"
 #include "c2g_ctx.cuh"
+#include "c2g_libm.cuh"
 #include "layer_db_host.h"
 #include "stdsort.cuh"
 
@@ -16,8 +17,8 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
                            c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream);
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
-                        cudaStream_t stream, long long *dbg);
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, uint16_t *cell_lists,
+                        int num_sms, cudaStream_t stream, long long *dbg);
 int c2g_query_alloc(c2g_ctx *ctx);
 void c2g_query_free(c2g_ctx *ctx);
 
@@ -45,6 +46,32 @@ int make_params(const c2g_cm_config &cfg, C2gIngestParams &P) {
   P.half_row_f = (float) P.half_row;
   P.half_col_f = (float) P.half_col;
   P.n_cells = cfg.n_row * cfg.n_col;
+  return 0;
+}
+
+// Which exp() does this host's libm implement? (x86-64 glibc dispatches to an FMA build on CPUs with FMA; the two differ in
+// ~0.07 % of results.)  The device then runs the same variant, so GPU keys match what the reference computes on THIS host.
+const uint64_t kExpTabHost[256] = C2G_EXP_TAB_INIT;
+int probe_exp_mode() {
+  int bad1 = 0, bad2 = 0;
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < 400000; ++i) {
+    st ^= st << 13;
+    st ^= st >> 7;
+    st ^= st << 17;
+    const double u = (double) (st >> 11) * (1.0 / 9007199254740992.0);
+    double x;
+    if (i & 1) {
+      const float t = (float) (u * 12.0);  // gaussPDF arguments: -0.5 * t * t with t a float difference
+      x = (-0.5 * (double) t) * (double) t;
+    } else
+      x = -70.0 * u;
+    const double ref = exp(x);
+    if (c2g_d2u(c2g_exp_glibc<false>(x, kExpTabHost)) != c2g_d2u(ref)) ++bad1;
+    if (c2g_d2u(c2g_exp_glibc<true>(x, kExpTabHost)) != c2g_d2u(ref)) ++bad2;
+  }
+  if (bad2 == 0) return 2;
+  if (bad1 == 0) return 1;
   return 0;
 }
 
@@ -98,6 +125,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
     delete ctx;
     return rc;
   }
+  ctx->P.exp_mode = probe_exp_mode();
   ctx->db = *db_cfg;
   ctx->device = device;
   ctx->scan_cap = scan_capacity;
@@ -141,6 +169,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_dbg, sizeof(long long) * 64);
+  ALLOC(ctx->d_cell_lists, sizeof(uint16_t) * C2G_NLEV * ncell * (size_t) ctx->num_sms);
 #undef ALLOC
   rc = c2g_query_alloc(ctx);
   if (rc) {
@@ -175,6 +204,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_heads);
   cudaFree(ctx->d_views);
   cudaFree(ctx->d_dbg);
+  cudaFree(ctx->d_cell_lists);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
@@ -215,7 +245,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
     ids_dev = ctx->d_int_ids;
   }
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -377,6 +407,26 @@ int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *se
     for (int d = 0; d < C2G_KEY_DIM; ++d) keys[i * C2G_KEY_DIM + d] = t[i].k[d];
     gidx[i] = t[i].gidx;
     seq[i] = t[i].seq;
+  }
+  return 0;
+}
+
+int c2g_exp_mode(c2g_ctx *ctx) { return ctx ? ctx->P.exp_mode : C2G_ERR_ARG; }
+
+/* host execution of the libm restatements in csrc/c2g_libm.cuh (tests): kind 0 exp (glibc, no FMA), 1 exp (glibc, FMA),
+ * 2 atan2f (in = y,x pairs), 3 acosf, 4 atanf, 5 = probe_exp_mode() (returns the mode, ignores the buffers) */
+int c2g_selftest_libm(int kind, int n, const void *in, void *out) {
+  if (kind == 5) return probe_exp_mode();
+  if (!in || !out || n < 0) return C2G_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    switch (kind) {
+      case 0: ((double *) out)[i] = c2g_exp_glibc<false>(((const double *) in)[i], kExpTabHost); break;
+      case 1: ((double *) out)[i] = c2g_exp_glibc<true>(((const double *) in)[i], kExpTabHost); break;
+      case 2: ((float *) out)[i] = c2g_atan2f(((const float *) in)[2 * i], ((const float *) in)[2 * i + 1]); break;
+      case 3: ((float *) out)[i] = c2g_acosf(((const float *) in)[i]); break;
+      case 4: ((float *) out)[i] = c2g_atanf(((const float *) in)[i]); break;
+      default: return C2G_ERR_ARG;
+    }
   }
   return 0;
 }

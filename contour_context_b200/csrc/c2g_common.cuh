@@ -22,6 +22,7 @@ struct C2gIngestParams {
   float half_row_f, half_col_f;                      // float(n_row / 2), float(n_col / 2)
   int half_row, half_col;
   int n_cells;
+  int exp_mode;  // which exp() the host's libm implements: 0 unknown (libdevice), 1 glibc, 2 glibc FMA variant (c2g_libm.cuh)
 };
 
 // Monotone map float -> uint32 (total order of finite floats and infinities; NaNs never reach it).

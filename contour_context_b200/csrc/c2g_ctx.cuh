@@ -30,6 +30,7 @@ struct c2g_ctx {
   c2g_scan_head *d_heads;
   c2g_view *d_views;
   long long *d_dbg;
+  uint16_t *d_cell_lists;  // per resident CTA: member cells of every component, level by level
   const float *last_pts;
   int last_B;
   long long launches;

@@ -28,6 +28,9 @@
 
 namespace {
 
+// glibc's __exp_data.tab (2 KB, read through L1); see c2g_libm.cuh
+__device__ const uint64_t c2g_exp_tab_dev[256] = C2G_EXP_TAB_INIT;
+
 constexpr int K2_THREADS = 1024;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int NC = 2048;        // components (any size) per level
@@ -57,7 +60,9 @@ struct Smem {
   int cnt_point[N_ANCH];
   int ncomp, nsig, status, n_occ;
   double red[K2_WARPS];
-  uint16_t wlist[K2_WARPS][WL_CAP];  // per-warp list of member cells of the component being walked
+  uint32_t t_off[C2G_VIEW_CAP];   // offset of every component's member-cell list in the CTA's global scratch
+  uint16_t t_poi[C2G_VIEW_CAP], t_cnt[C2G_VIEW_CAP], torder[C2G_VIEW_CAP];
+  int bucket_cnt[16], wq;
 };
 
 __device__ __forceinline__ uint32_t uf_find(volatile uint32_t *L, uint32_t c) {
@@ -264,7 +269,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
                int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
-               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, long long *__restrict__ dbg) {
+               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, uint16_t *__restrict__ cell_lists,
+               long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -331,36 +337,56 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
 
     C2G_DBG(1);
     // ---------------- phase B: levels ------------------------------------------------------------------------------
+    // Every thread owns a contiguous chunk of <= 32 cells and keeps, per level, the bitmask of its foreground cells in a
+    // register: the per-level passes below visit set bits only (a few percent of the BEV is above any threshold).
+    const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
+    const int cb0 = tid * chunk, cb1 = min(ncell, cb0 + chunk);
+    const int r_first = cb0 / ncol, c_first = cb0 - r_first * ncol;
+    uint32_t mk[C2G_NLEV];
+    uint32_t rowst = 0;  // cells of the chunk that sit in column 0 (a horizontal run cannot continue across them)
+    {
+#pragma unroll
+      for (int l = 0; l < C2G_NLEV; ++l) mk[l] = 0;
+      int col = c_first;
+      for (int k = 0; cb0 + k < cb1; ++k) {
+        const uint32_t m = S.msk[cb0 + k];
+#pragma unroll
+        for (int l = 0; l < C2G_NLEV; ++l) mk[l] |= ((m >> l) & 1u) << k;
+        if (col == 0) rowst |= 1u << k;
+        if (++col == ncol) col = 0;
+      }
+    }
+    uint16_t *const lists = cell_lists + (size_t) blockIdx.x * C2G_NLEV * ncell;  // per-CTA scratch: member cells per component
     int total_views = 0;
     for (int lev = 0; lev < C2G_NLEV; ++lev) {
       const uint8_t bit = (uint8_t) (1u << lev);
+      const uint32_t bits = mk[lev];
+      const uint32_t starts = bits & (~(bits << 1) | rowst);  // first cell of every horizontal run inside the chunk
       if (tid == 0) {
         S.ncomp = 0;
         S.nsig = 0;
       }
-      // B1 init label words (keep the upper half = rank of the enclosing component of the previous level). Every thread
-      // owns a contiguous chunk of cells; a horizontal run inside the chunk is linked straight to its first cell.
-      const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
-      const int cb0 = tid * chunk, cb1 = min(ncell, cb0 + chunk);
-      {
-        int runstart = -1;
-        for (int c = cb0; c < cb1; ++c) {
-          if (S.msk[c] & bit) {
-            if (runstart < 0 || (c % ncol) == 0) runstart = c;
-            S.L[c] = (S.L[c] & 0xFFFF0000u) | (uint32_t) runstart;
-          } else
-            runstart = -1;
-        }
+      // B1 label words: upper half keeps the rank of the enclosing component of the previous level, lower half links every
+      // cell straight to the first cell of its run
+      for (uint32_t bb = bits; bb; bb &= bb - 1) {
+        const int k = __ffs(bb) - 1;
+        const int rs = 31 - __clz(starts & ((2u << k) - 1u));
+        S.L[cb0 + k] = (S.L[cb0 + k] & 0xFFFF0000u) | (uint32_t) (cb0 + rs);
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 0);
-      // B2 unions. W: only where the run was cut by a chunk boundary. Row above: N if set (NW/NE then belong to N's run);
+      // B2 unions. W: only where a run was cut by the chunk boundary. Row above: N if set (NW/NE then belong to N's run);
       // otherwise NW and NE. A cell whose W neighbour is set skips what W already did (its N/NE are this cell's NW/N).
-      for (int c = cb0; c < cb1; ++c) {
-        if (!(S.msk[c] & bit)) continue;
-        const int r = c / ncol, cc = c - r * ncol;
-        const bool w_set = cc > 0 && (S.msk[c - 1] & bit);
-        if (w_set && c == cb0) uf_union(S.L, c, c - 1);
+      for (uint32_t bb = bits; bb; bb &= bb - 1) {
+        const int k = __ffs(bb) - 1;
+        const int c = cb0 + k;
+        int r = r_first, cc = c_first + k;
+        while (cc >= ncol) {
+          cc -= ncol;
+          ++r;
+        }
+        const bool w_set = cc > 0 && (k > 0 ? ((bits >> (k - 1)) & 1u) : (S.msk[c - 1] & bit));
+        if (w_set && k == 0) uf_union(S.L, c, c - 1);
         if (r > 0) {
           const int up = c - ncol;
           const bool n_set = (S.msk[up] & bit) != 0;
@@ -378,27 +404,29 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 1);
-      // B3 flatten
-      {
-        // one find per horizontal run of the chunk: the other cells of the run share its root by construction
-        uint32_t root = 0;
-        bool in_run = false;
-        for (int c = cb0; c < cb1; ++c) {
-          if (S.msk[c] & bit) {
-            if (!in_run || (c % ncol) == 0) root = uf_find_ro(S.L, c);
-            in_run = true;
-            S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
-          } else
-            in_run = false;
+      // B3 flatten: one read-only find per run, the whole run takes that root
+      for (uint32_t sb = starts; sb; sb &= sb - 1) {
+        const int k0 = __ffs(sb) - 1;
+        const uint32_t root = uf_find_ro(S.L, cb0 + k0);
+        const uint32_t run = ((bits >> k0) + 1u == 0u) ? 0xFFFFFFFFu : (((bits >> k0) ^ ((bits >> k0) + 1u)) >> 1);  // low ones of bits>>k0
+        uint32_t rb = run;
+        const uint32_t nxt = (starts >> k0) & ~1u;  // a row start inside the run splits it
+        if (nxt) rb &= (nxt & (0u - nxt)) - 1u;
+        for (; rb; rb &= rb - 1) {
+          const int c = cb0 + k0 + __ffs(rb) - 1;
+          S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
         }
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 2);
-      // B4 roots -> table slots (one shared-memory atomic per warp: same-address atomics serialise)
+      // B4 roots -> table slots. A root is the smallest cell index of its component, hence a run start. One shared-memory
+      // atomic per warp (same-address atomics serialise).
       {
         int nroot = 0;
-        for (int c = cb0; c < cb1; ++c)
-          if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) ++nroot;
+        for (uint32_t sb = starts; sb; sb &= sb - 1) {
+          const int c = cb0 + __ffs(sb) - 1;
+          if ((S.L[c] & 0xFFFFu) == (uint32_t) c) ++nroot;
+        }
         int incl = nroot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -409,8 +437,10 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         if (lane == 31 && incl > 0) base = atomicAdd(&S.ncomp, incl);
         base = __shfl_sync(0xFFFFFFFFu, base, 31);
         int slot_next = base + incl - nroot;
-        for (int c = cb0; c < cb1 && nroot > 0; ++c)
-          if ((S.msk[c] & bit) && (S.L[c] & 0xFFFFu) == (uint32_t) c) {
+        if (nroot > 0)
+          for (uint32_t sb = starts; sb; sb &= sb - 1) {
+            const int c = cb0 + __ffs(sb) - 1;
+            if ((S.L[c] & 0xFFFFu) != (uint32_t) c) continue;
             int slot = slot_next++;
             if (slot < NC) {
               S.c_area[slot] = 0;
@@ -431,36 +461,30 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 3);
-      // B5 per-component area / bbox / first-block key / last pixel, aggregated over horizontal runs per thread chunk
-      {
-        const int c0 = cb0, c1 = cb1;
-        int cur = -1, run_r = 0, run_c0 = 0, run_c1 = 0;
-        for (int c = c0; c <= c1; ++c) {
-          int slot = -1, r = 0, cc = 0;
-          if (c < c1 && (S.msk[c] & bit)) {
-            slot = slot_of(S.L, c);
-            if (slot == 0x7FFF) slot = -1;
-            r = c / ncol;
-            cc = c - r * ncol;
-          }
-          if (slot != cur || (slot >= 0 && r != run_r)) {
-            if (cur >= 0) {
-              atomicAdd(&S.c_area[cur], run_c1 - run_c0 + 1);
-              atomicMin(&S.c_minr[cur], run_r);
-              atomicMax(&S.c_maxr[cur], run_r);
-              atomicMin(&S.c_minc[cur], run_c0);
-              atomicMax(&S.c_maxc[cur], run_c1);
-              const int pc = S.c_pcid[cur];
-              const int x0 = lev ? (int) S.px0[pc & (NVL - 1)] : 0, y0 = lev ? (int) S.py0[pc & (NVL - 1)] : 0;
-              atomicMin(&S.c_key[cur], ((run_r - y0) >> 1) * 128 + ((run_c0 - x0) >> 1));
-              atomicMax(&S.c_poi[cur], run_r * ncol + run_c1);
-            }
-            cur = slot;
-            run_r = r;
-            run_c0 = cc;
-          }
-          run_c1 = cc;
+      // B5 per-component area / bbox / first-2x2-block key / last pixel: one flush per horizontal run of the chunk
+      for (uint32_t sb = starts; sb; sb &= sb - 1) {
+        const int k0 = __ffs(sb) - 1;
+        uint32_t run = ((bits >> k0) + 1u == 0u) ? 0xFFFFFFFFu : (((bits >> k0) ^ ((bits >> k0) + 1u)) >> 1);
+        const uint32_t nxt = (starts >> k0) & ~1u;
+        if (nxt) run &= (nxt & (0u - nxt)) - 1u;
+        const int len = __popc(run);
+        const int c = cb0 + k0;
+        int r = r_first, cc = c_first + k0;
+        while (cc >= ncol) {
+          cc -= ncol;
+          ++r;
         }
+        const int cur = slot_of(S.L, c);
+        if (cur == 0x7FFF) continue;
+        atomicAdd(&S.c_area[cur], len);
+        atomicMin(&S.c_minr[cur], r);
+        atomicMax(&S.c_maxr[cur], r);
+        atomicMin(&S.c_minc[cur], cc);
+        atomicMax(&S.c_maxc[cur], cc + len - 1);
+        const int pc = S.c_pcid[cur];
+        const int x0 = lev ? (int) S.px0[pc & (NVL - 1)] : 0, y0 = lev ? (int) S.py0[pc & (NVL - 1)] : 0;
+        atomicMin(&S.c_key[cur], ((r - y0) >> 1) * 128 + ((cc - x0) >> 1));
+        atomicMax(&S.c_poi[cur], c + len - 1);
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 4);
@@ -486,8 +510,11 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         int rank = 0;
         for (int j = 0; j < min(S.nsig, NVL); ++j) rank += (S.sig_key[j] < ki) ? 1 : 0;
         if (rank < nsig) {
-          S.order[rank] = S.sig_slot[i];
-          S.c_rank[S.sig_slot[i]] = (uint16_t) rank;
+          const int sl = S.sig_slot[i];
+          S.order[rank] = (uint16_t) sl;
+          S.c_rank[sl] = (uint16_t) rank;
+          S.sortbuf[total_views + rank] = ((uint32_t) S.c_area[sl] << 16) | (uint32_t) rank;
+          S.t_poi[total_views + rank] = (uint16_t) S.c_poi[sl];
         }
       }
       __syncthreads();
@@ -495,89 +522,51 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.n_views[lev] = nsig;
         S.view_off[lev] = total_views;
       }
+      // list offsets: exclusive prefix of the areas in rank order (one warp; nsig is a few dozen)
+      if (warp == 0) {
+        int run_off = lev * ncell;
+        for (int base = 0; base < nsig; base += 32) {
+          const int i = base + lane;
+          const int a = i < nsig ? (int) (S.sortbuf[total_views + i] >> 16) : 0;
+          int incl = a;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          if (i < nsig) S.t_off[total_views + i] = (uint32_t) (run_off + incl - a);
+          run_off += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+      }
+      __syncthreads();
       C2G_DBG(10 + lev * 8 + 5);
-      // B7 moments in bbox-raster order + calcStatVals: one warp per component, all lanes carry the same accumulators
+      // B7 member cells of every significant component in bbox-raster order -> global scratch list (shared memory only on
+      // the read side; the moment accumulation itself is deferred to the balanced task pool after the level loop)
       for (int rk = warp; rk < nsig; rk += K2_WARPS) {
         const int s = S.order[rk];
         const int r0 = S.c_minr[s], c0 = S.c_minc[s], w = S.c_maxc[s] - c0 + 1, hgt = S.c_maxr[s] - r0 + 1;
-        const int total = w * hgt;
-        // The seven double accumulators of RunningStatRecorder live in lanes 0..6: lane k adds a_k * b_k per member cell
-        // (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1, t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the
-        // FP64 pipe one DMUL + one DADD per warp instead of fifteen. Accumulation order = bbox-raster order.
-        const int selA = (lane == 0 || lane == 2 || lane == 3) ? 0 : (lane == 1 || lane == 4) ? 1 : (lane == 5 || lane == 6) ? 2 : 3;
-        const int selB = (lane == 2 || lane == 5) ? 0 : (lane == 3 || lane == 4 || lane == 6) ? 1 : 3;
-        double acc = 0.0;
-        float vol3 = 0.0f;
-        int cnt = 0;
-        uint16_t *wl = S.wlist[warp];
+        uint16_t *wl = lists + S.t_off[total_views + rk];
         int nlist = 0;
-        for (int base = 0; base < total; base += 32) {
-          // membership needs shared memory only; member cells are appended in bbox-raster order
-          const int i = base + lane;
+        int rr = r0, cc = c0 + lane;  // lane's cell inside the bbox, advanced by 32 cells per step without divisions
+        while (cc >= c0 + w) {
+          cc -= w;
+          ++rr;
+        }
+        for (int base = 0; base < w * hgt; base += 32) {
           bool member = false;
           int c = 0;
-          if (i < total) {
-            c = (r0 + i / w) * ncol + (c0 + i % w);
+          if (rr < r0 + hgt) {
+            c = rr * ncol + cc;
             member = (S.msk[c] & bit) && slot_of(S.L, c) == s;
           }
           const unsigned bal = __ballot_sync(0xFFFFFFFFu, member);
           if (member) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = (uint16_t) c;
           nlist += __popc(bal);
-          if (nlist > WL_CAP - 32 || base + 32 >= total) {
-            __syncwarp();
-            // flush: 4 groups of 32 cells in flight from L2 (converted to double at the source lane), then strictly
-            // sequential accumulation in list order
-            for (int g = 0; g < nlist; g += 128) {
-              float hv[4];
-              double rv[4], cv[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = g + u * 32 + lane;
-                hv[u] = 0.f;
-                rv[u] = cv[u] = 0.0;
-                if (j < nlist) {
-                  const int cc = wl[j];
-                  hv[u] = hg[cc];
-                  rv[u] = (double) rfg[cc];
-                  cv[u] = (double) cfp[cc];
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int cntu = min(32, nlist - (g + u * 32));
-                for (int src = 0; src < cntu; ++src) {
-                  const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
-                  const double v0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
-                  const double v1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
-                  const double hd = (double) hh;
-                  const double a = selA == 0 ? v0 : selA == 1 ? v1 : selA == 2 ? hd : 1.0;
-                  const double bb = selB == 0 ? v0 : selB == 1 ? v1 : 1.0;
-                  acc += a * bb;
-                  vol3 += hh;
-                }
-                cnt += max(cntu, 0);
-              }
-            }
-            __syncwarp();
-            nlist = 0;
+          cc += 32;
+          while (cc >= c0 + w) {
+            cc -= w;
+            ++rr;
           }
-        }
-        Moments m;
-        m.cnt = cnt;
-        m.vol3 = vol3;
-        m.s0 = __shfl_sync(0xFFFFFFFFu, acc, 0);
-        m.s1 = __shfl_sync(0xFFFFFFFFu, acc, 1);
-        m.t00 = __shfl_sync(0xFFFFFFFFu, acc, 2);
-        m.t01 = __shfl_sync(0xFFFFFFFFu, acc, 3);
-        m.t11 = __shfl_sync(0xFFFFFFFFu, acc, 4);
-        m.q0 = __shfl_sync(0xFFFFFFFFu, acc, 5);
-        m.q1 = __shfl_sync(0xFFFFFFFFu, acc, 6);
-        if (lane == 0) {
-          c2g_view v;
-          const int poi = S.c_poi[s];
-          calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, v);
-          presort[total_views + rk] = v;
-          S.sortbuf[total_views + rk] = ((uint32_t) m.cnt << 16) | (uint32_t) rk;
         }
       }
       C2G_DBG(10 + lev * 8 + 6);
@@ -587,26 +576,115 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.px0[i] = (uint8_t) S.c_minc[s];
         S.py0[i] = (uint8_t) S.c_minr[s];
       }
-      for (int c = tid; c < ncell; c += K2_THREADS)
-        if (S.msk[c] & bit) {
-          const int s = slot_of(S.L, c);
-          const uint32_t rk = (s == 0x7FFF) ? 0xFFFFu : (uint32_t) S.c_rank[s];
-          // written after the slot lookups of this thread's own cell only; other threads may still read the ROOT word's
-          // low half, which is preserved below
-          S.L[c] = (rk << 16) | (S.L[c] & 0xFFFFu);
-        }
+      for (uint32_t bb = bits; bb; bb &= bb - 1) {
+        const int c = cb0 + __ffs(bb) - 1;
+        const int s = slot_of(S.L, c);
+        const uint32_t rk = (s == 0x7FFF) ? 0xFFFFu : (uint32_t) S.c_rank[s];
+        S.L[c] = (rk << 16) | (S.L[c] & 0xFFFFu);  // the low half (slot / root link) is what concurrent readers use
+      }
       total_views += nsig;
       __syncthreads();
     }
 
     C2G_DBG(2);
-    // ---------------- phase C: per-level std::sort replay (cell_cnt descending), sorted views to the arena ----------
+    // ---------------- phase C: balanced task pool: per-level std::sort replays + moments / calcStatVals per component -----
+    // Tasks are ordered by decreasing size class (floor(log2(area))) so the longest sequential accumulations start first.
+    if (tid < 16) S.bucket_cnt[tid] = 0;
+    if (tid == 0) S.wq = 0;
+    __syncthreads();
+    for (int v = tid; v < total_views; v += K2_THREADS) atomicAdd(&S.bucket_cnt[31 - __clz((int) (S.sortbuf[v] >> 16))], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int acc_n = 0;
+      for (int bkt = 15; bkt >= 0; --bkt) {
+        const int n = S.bucket_cnt[bkt];
+        S.bucket_cnt[bkt] = acc_n;
+        acc_n += n;
+      }
+    }
+    __syncthreads();
+    for (int v = tid; v < total_views; v += K2_THREADS) {
+      const int pos = atomicAdd(&S.bucket_cnt[31 - __clz((int) (S.sortbuf[v] >> 16))], 1);
+      S.torder[pos] = (uint16_t) v;
+    }
+    __syncthreads();
+    // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
+    // (contour_mng.h:596-599); the walk tasks below read the areas from t_cnt copies taken before the sort starts
+    for (int v = tid; v < total_views; v += K2_THREADS) S.t_cnt[v] = (uint16_t) (S.sortbuf[v] >> 16);
+    __syncthreads();
     if (lane == 0 && warp < C2G_NLEV) {  // one warp per level: the six serial replays run on different schedulers
       uint32_t *first = S.sortbuf + S.view_off[warp];
       c2g_sort::std_sort(first, (long) S.n_views[warp], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
       int sum = 0;
       for (int i = 0; i < S.n_views[warp]; ++i) sum += (int) (first[i] >> 16);
       S.layer_cnt[warp] = sum;
+    }
+    {
+      // The seven double accumulators of RunningStatRecorder live in lanes 0..6: lane k adds a_k * b_k per member cell
+      // (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1, t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the
+      // FP64 pipe one DMUL + one DADD per warp. Accumulation order = list order = bbox-raster order.
+      const int selA = (lane == 0 || lane == 2 || lane == 3) ? 0 : (lane == 1 || lane == 4) ? 1 : (lane == 5 || lane == 6) ? 2 : 3;
+      const int selB = (lane == 2 || lane == 5) ? 0 : (lane == 3 || lane == 4 || lane == 6) ? 1 : 3;
+      while (true) {
+        int ti = 0;
+        if (lane == 0) ti = atomicAdd(&S.wq, 1);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= total_views) break;
+        const int v = S.torder[ti];
+        int lev = 0;
+        for (int l = 0; l < C2G_NLEV; ++l)
+          if (v >= S.view_off[l] && v < S.view_off[l] + S.n_views[l]) lev = l;
+        const int n = S.t_cnt[v];
+        const uint16_t *wl = lists + S.t_off[v];
+        double acc = 0.0;
+        float vol3 = 0.0f;
+        for (int g = 0; g < n; g += 128) {
+          float hv[4];
+          double rv[4], cv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = g + u * 32 + lane;
+            hv[u] = 0.f;
+            rv[u] = cv[u] = 0.0;
+            if (j < n) {
+              const int cc = wl[j];
+              hv[u] = hg[cc];
+              rv[u] = (double) rfg[cc];
+              cv[u] = (double) cfp[cc];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cntu = min(32, n - (g + u * 32));
+            for (int src = 0; src < cntu; ++src) {
+              const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
+              const double v0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
+              const double v1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
+              const double hd = (double) hh;
+              const double a = selA == 0 ? v0 : selA == 1 ? v1 : selA == 2 ? hd : 1.0;
+              const double bb2 = selB == 0 ? v0 : selB == 1 ? v1 : 1.0;
+              acc += a * bb2;
+              vol3 += hh;
+            }
+          }
+        }
+        Moments m;
+        m.cnt = n;
+        m.vol3 = vol3;
+        m.s0 = __shfl_sync(0xFFFFFFFFu, acc, 0);
+        m.s1 = __shfl_sync(0xFFFFFFFFu, acc, 1);
+        m.t00 = __shfl_sync(0xFFFFFFFFu, acc, 2);
+        m.t01 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        m.t11 = __shfl_sync(0xFFFFFFFFu, acc, 4);
+        m.q0 = __shfl_sync(0xFFFFFFFFu, acc, 5);
+        m.q1 = __shfl_sync(0xFFFFFFFFu, acc, 6);
+        if (lane == 0) {
+          c2g_view vw;
+          const int poi = S.t_poi[v];
+          calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, vw);
+          presort[v] = vw;
+        }
+      }
     }
     __syncthreads();
     C2G_DBG(3);
@@ -708,7 +786,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           for (int k = 0; k < n; ++k) {
             const float t = (x - dl[k]) / 1.0f;
             const double q = (-0.5 * (double) t) * (double) t;
-            const float g = (float) (c2g_exp(q) / inv_norm_den);
+            const float g = (float) (c2g_exp(q, P.exp_mode, c2g_exp_tab_dev) / inv_norm_den);
             acc += (float) hl[k] * g;
           }
         }
@@ -862,7 +940,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         const double det = c00 * c11 - c01 * c10;
         const double invdet = 1.0 / det;
         const double qf = mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my);
-        acc += (double) A.cell_cnt * (double) Bv.cell_cnt / sqrt(det) * exp(-0.5 * qf);
+        acc += (double) A.cell_cnt * (double) Bv.cell_cnt / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
       }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
@@ -896,8 +974,8 @@ size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, int num_sms,
-                        cudaStream_t stream, long long *dbg) {
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, uint16_t *cell_lists,
+                        int num_sms, cudaStream_t stream, long long *dbg) {
   static bool attr_set = false;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -906,7 +984,7 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, dbg);
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, cell_lists, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -462,6 +462,7 @@ struct EllD {
   float maj, w;
 };
 constexpr int ELL_CAP = 128;
+constexpr int FIN_WARPS = 4;  // warps per CTA of the finish kernel: one query scan per CTA, candidates spread over warps
 
 struct Prop {
   double T[4];  // cos, sin, tx, ty
@@ -482,7 +483,8 @@ struct FinishScratch {
   uint32_t ord[C2G_MAX_CAND];
   float corr[C2G_MAX_CAND];
   uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64];  // hint indices that reached addProposal, in order
-  EllD es[ELL_CAP], et[ELL_CAP];                                // one level's ellipses of candidate / query
+  EllD es[FIN_WARPS][ELL_CAP], et[FIN_WARPS][ELL_CAP];          // per warp: one level's ellipses of candidate / query
+  int aft[3], overflow;
 };
 
 __device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
@@ -596,68 +598,72 @@ __device__ void add_proposal(CandState &cs, const double Tp[4], const uint64_t b
   np.area_perc = 0.0f;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FIN_WARPS * 32)
 finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int B, QueryParams Q,
               int max_fine_opt, const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores,
               c2g_query_result *__restrict__ results) {
   extern __shared__ __align__(16) unsigned char fsm_raw[];
-  FinishScratch *all = reinterpret_cast<FinishScratch *>(fsm_raw);
+  FinishScratch &F = *reinterpret_cast<FinishScratch *>(fsm_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = blockIdx.x * (blockDim.x >> 5) + w;
+  const int q = blockIdx.x;  // one query scan per CTA
   if (q >= B) return;
-  FinishScratch &F = all[w];
   const int q_slot = first_slot + q;
   const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
   const c2g_hint *hq = hints + (size_t) q * per_q;
   const c2g_pair_score *sq = scores + (size_t) q * per_q;
-  int aft1 = 0, aft2 = 0, aft3 = 0, overflow = 0;
-  // all lanes scan the hint records; only the few that reached addProposal are replayed sequentially
-  int n_pass = 0;
-  for (long long base = 0; base < per_q; base += 32) {
-    const long long i = base + lane;
-    int p = 0;
-    if (i < per_q && hq[i].cand_gidx >= 0) p = sq[i].passed;
-    const bool valid = i < per_q && hq[i].cand_gidx >= 0;
-    aft1 += __popc(__ballot_sync(0xFFFFFFFFu, valid && p != 0));
-    aft2 += __popc(__ballot_sync(0xFFFFFFFFu, valid && (p == 1 || p == -2)));
-    const unsigned pm = __ballot_sync(0xFFFFFFFFu, valid && p == 1);
-    if (valid && p == 1) F.passlist[n_pass + __popc(pm & ((1u << lane) - 1u))] = (uint16_t) i;
-    n_pass += __popc(pm);
-  }
-  aft3 = n_pass;
-  __syncwarp();
-  if (lane == 0) {
-    F.n_cand = 0;
-    // replay checkCandWithHint's bookkeeping in reference order: (q-level, query seq, ascending distance)
-    for (int k0 = 0; k0 < n_pass; ++k0) {
-      const int i = F.passlist[k0];
-      const c2g_pair_score &r = sq[i];
-      const int gidx = hq[i].cand_gidx;
-      int ci = -1;
-      for (int k = 0; k < F.n_cand; ++k)
-        if (F.cand[k].gidx == gidx) {
-          ci = k;
-          break;
+  if (w == 0) {
+    int aft1 = 0, aft2 = 0, overflow = 0;
+    // all lanes scan the hint records; only the few that reached addProposal are replayed sequentially
+    int n_pass = 0;
+    for (long long base = 0; base < per_q; base += 32) {
+      const long long i = base + lane;
+      int p = 0;
+      if (i < per_q && hq[i].cand_gidx >= 0) p = sq[i].passed;
+      const bool valid = i < per_q && hq[i].cand_gidx >= 0;
+      aft1 += __popc(__ballot_sync(0xFFFFFFFFu, valid && p != 0));
+      aft2 += __popc(__ballot_sync(0xFFFFFFFFu, valid && (p == 1 || p == -2)));
+      const unsigned pm = __ballot_sync(0xFFFFFFFFu, valid && p == 1);
+      if (valid && p == 1) F.passlist[n_pass + __popc(pm & ((1u << lane) - 1u))] = (uint16_t) i;
+      n_pass += __popc(pm);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      F.n_cand = 0;
+      // replay checkCandWithHint's bookkeeping in reference order: (q-level, query seq, ascending distance)
+      for (int k0 = 0; k0 < n_pass; ++k0) {
+        const int i = F.passlist[k0];
+        const c2g_pair_score &r = sq[i];
+        const int gidx = hq[i].cand_gidx;
+        int ci = -1;
+        for (int k = 0; k < F.n_cand; ++k)
+          if (F.cand[k].gidx == gidx) {
+            ci = k;
+            break;
+          }
+        if (ci < 0) {
+          if (F.n_cand >= C2G_MAX_CAND) {
+            overflow = 1;
+            continue;
+          }
+          ci = F.n_cand++;
+          F.cand[ci].gidx = gidx;
+          F.cand[ci].n_prop = 0;
+          F.cand[ci].corr_init = 0.0f;
+          F.cand[ci].alive = 0;
+          F.cand[ci].neg_est_dist = 0.0;
         }
-      if (ci < 0) {
-        if (F.n_cand >= C2G_MAX_CAND) {
-          overflow = 1;
-          continue;
-        }
-        ci = F.n_cand++;
-        F.cand[ci].gidx = gidx;
-        F.cand[ci].n_prop = 0;
-        F.cand[ci].corr_init = 0.0f;
-        F.cand[ci].alive = 0;
-        F.cand[ci].neg_est_dist = 0.0;
+        add_proposal(F.cand[ci], r.T, r.pair_bits, r.n_pairs);
       }
-      add_proposal(F.cand[ci], r.T, r.pair_bits, r.n_pairs);
+      F.aft[0] = aft1;
+      F.aft[1] = aft2;
+      F.aft[2] = n_pass;
+      F.overflow = overflow;
     }
   }
-  __syncwarp();
+  __syncthreads();
   const int n_before = F.n_cand;
   // tidyUpCandidates
-  for (int ci = 0; ci < n_before; ++ci) {
+  for (int ci = w; ci < n_before; ci += FIN_WARPS) {  // candidate poses are independent: one warp each
     CandState &cs = F.cand[ci];
     int pass = 0;
     // area_perc of every proposal: lanes evaluate the per-pair percentages of 32 map entries at a time, the float sums
@@ -710,7 +716,7 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
     pass = __shfl_sync(0xFFFFFFFFu, pass, 0);
     if (pass) {
       __syncwarp();
-      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane, F.es, F.et);
+      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane, F.es[w], F.et[w]);
       if (lane == 0) {
         cs.corr_init = (float) corr;
         cs.alive = (cs.corr_init < Q.lb.correlation) ? 0 : 1;
@@ -718,7 +724,9 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
     }
     __syncwarp();
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (w == 0 && lane == 0) {
+    const int aft1 = F.aft[0], aft2 = F.aft[1], aft3 = F.aft[2], overflow = F.overflow;
     // swap-compaction of the survivors exactly as contour_db.h:580-592
     int p1 = 0, p2 = n_before - 1;
     while (p1 <= p2) {
@@ -801,13 +809,12 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
 
 int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores) {
   static bool attr_set = false;
-  const int warps = 2;
-  const size_t smem = sizeof(FinishScratch) * warps;
+  const size_t smem = sizeof(FinishScratch);
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
-  finish_kernel<<<(B + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q,
+  finish_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q,
                                                                             ctx->db.max_fine_opt, hints, scores, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;

@@ -164,5 +164,9 @@ class Engine:
                                                      C.c_void_p(scores_dev), capi.ptr(res)), "c2g_finish_from_scores")
         return res
 
+    def exp_mode(self) -> int:
+        """Which glibc exp() variant the device reproduces (0 = none matched the host libm: libdevice exp, keys may differ by 1 ulp)."""
+        return int(capi.lib().c2g_exp_mode(self.h))
+
     def launch_count(self) -> int:
         return int(capi.lib().c2g_launch_count(self.h))

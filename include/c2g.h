@@ -117,6 +117,11 @@ int c2g_hostdb_balance(void *h, int seed, double ts);
 int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes);
 int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq);
 
+/* Which exp() variant the device runs to match this host's libm (csrc/c2g_libm.cuh): 0 libdevice, 1 glibc, 2 glibc+FMA. */
+int c2g_exp_mode(c2g_ctx *ctx);
+/* Host execution of the libm restatements (tests only). */
+int c2g_selftest_libm(int kind, int n, const void *in, void *out);
+
 /* Developer aid: clock64() stamps of the contour kernel's phases (64 values). */
 int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host);
 

@@ -229,3 +229,17 @@ extern "C" int c2o_uses_nanoflann() {
   return 0;
 #endif
 }
+
+// vector versions of the host libm calls the reference makes (std::exp(double), std::atan2(float,float), std::acos(float),
+// atanf) — the ground truth tests/test_libm.py compares the product's restatements with
+extern "C" void c2o_vec_libm(int kind, int n, const void *in, void *out) {
+  for (int i = 0; i < n; ++i) {
+    switch (kind) {
+      case 0:
+      case 1: ((double *) out)[i] = std::exp(((const double *) in)[i]); break;
+      case 2: ((float *) out)[i] = std::atan2(((const float *) in)[2 * i], ((const float *) in)[2 * i + 1]); break;
+      case 3: ((float *) out)[i] = std::acos(((const float *) in)[i]); break;
+      case 4: ((float *) out)[i] = std::atan(((const float *) in)[i]); break;
+    }
+  }
+}

@@ -1,8 +1,9 @@
 """GPU parity of the ingest path (BEV -> contours -> views -> keys -> BCI) against the CPU oracle, through the C-ABI.
 
-Bar (BASELINE.json north_star): bit-exact BEV cells, contour order, ContourView fields; retrieval keys bit-exact up to the
-documented libm caveat (device exp vs glibc exp differ by <= 1 ulp in double, which can flip the float rounding of one
-gaussPDF term with probability ~1e-8 per call; mismatches are COUNTED and bounded, never ignored)."""
+Bar (BASELINE.json north_star): bit-exact BEV cells, contour order, ContourView fields, retrieval keys and BCIs.  The libm
+calls that reach keys / BCIs (exp, atan2f) run as bit-exact glibc restatements on the device (csrc/c2g_libm.cuh,
+tests/test_libm.py); if the host's exp() is not one of the two glibc variants the context reports exp_mode 0 and the key
+comparison falls back to a counted <= 2 ulp bound."""
 import numpy as np
 import pytest
 
@@ -64,7 +65,7 @@ def test_views_keys_bci(engine, oracle):
         nan_g, nan_o = np.isnan(gk), np.isnan(ok)
         assert np.array_equal(nan_g, nan_o)
         d = ulp_diff(np.where(nan_g, 0, gk), np.where(nan_o, 0, ok))
-        assert d.max() <= 2, f"scan {b}: key differs by {d.max()} ulp"
+        assert d.max() <= (2 if engine.exp_mode() == 0 else 0), f"scan {b}: key differs by {d.max()} ulp"
         key_ulp_bad += int((d > 0).sum())
         # BCI: bitsets, neighbour identity and order, segments exact; r exact; theta within 1 ulp (atan2f libm caveat)
         gb_, ob_ = gh["bcis"], oh["bcis"]
@@ -74,7 +75,7 @@ def test_views_keys_bci(engine, oracle):
         for f in ("level", "seq", "bit_pos"):
             assert np.array_equal(gb_["nei"][f], ob_["nei"][f]), f
         assert gb_["nei"]["r"].tobytes() == ob_["nei"]["r"].tobytes()
-        assert ulp_diff(gb_["nei"]["theta"], ob_["nei"]["theta"]).max() <= 2
+        assert gb_["nei"]["theta"].tobytes() == ob_["nei"]["theta"].tobytes()  # glibc atan2f restated on the device
         assert abs(gh["gmm_auto_corr"] - oh["gmm_auto_corr"]) <= 1e-9 * abs(oh["gmm_auto_corr"])
     # at most a handful of 1-ulp key entries over 6 scans x 360 key entries
     assert key_ulp_bad <= 4, f"{key_ulp_bad} key entries differ from the oracle"
@@ -104,7 +105,7 @@ def test_ragged_and_degenerate_inputs(engine, oracle):
             assert not view_fields_equal(gviews[lev], s.views(lev)), (b, lev)
         gk, ok = heads[b]["keys"], oh["keys"]
         assert np.array_equal(np.isnan(gk), np.isnan(ok))
-        assert ulp_diff(np.nan_to_num(gk), np.nan_to_num(ok)).max() <= 2
+        assert ulp_diff(np.nan_to_num(gk), np.nan_to_num(ok)).max() <= (2 if engine.exp_mode() == 0 else 0)
 
 
 def test_device_resident_input_matches_host_input(engine):
