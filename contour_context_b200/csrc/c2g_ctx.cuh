@@ -39,6 +39,7 @@ struct c2g_ctx {
   c2g_hint *d_hints;
   c2g_pair_score *d_scores;
   c2g_query_result *d_results;
+  int *d_survivors, *d_nsurv;  // hint slots that pass the thread-per-hint prefilter, and their count
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state

@@ -331,7 +331,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           S.L[c] = 0u;
         }
       }
-      if (occ) atomicAdd(&S.n_occ, occ);
+      for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xFFFFFFFFu, occ, o);
+      if (lane == 0 && occ) atomicAdd(&S.n_occ, occ);  // one same-address shared atomic per warp, not per thread
     }
     __syncthreads();
 
@@ -589,23 +590,28 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     C2G_DBG(2);
     // ---------------- phase C: balanced task pool: per-level std::sort replays + moments / calcStatVals per component -----
     // Tasks are ordered by decreasing size class (floor(log2(area))) so the longest sequential accumulations start first.
-    if (tid < 16) S.bucket_cnt[tid] = 0;
-    if (tid == 0) S.wq = 0;
-    __syncthreads();
-    for (int v = tid; v < total_views; v += K2_THREADS) atomicAdd(&S.bucket_cnt[31 - __clz((int) (S.sortbuf[v] >> 16))], 1);
-    __syncthreads();
+    // Big components (>= 48 cells) go to the front of the task order, small ones fill it from the back; positions are
+    // claimed with one shared atomic per warp and class (same-address shared atomics serialise).
     if (tid == 0) {
-      int acc_n = 0;
-      for (int bkt = 15; bkt >= 0; --bkt) {
-        const int n = S.bucket_cnt[bkt];
-        S.bucket_cnt[bkt] = acc_n;
-        acc_n += n;
-      }
+      S.wq = 0;
+      S.bucket_cnt[0] = 0;             // next free slot at the front
+      S.bucket_cnt[1] = total_views;   // one past the last free slot at the back
     }
     __syncthreads();
-    for (int v = tid; v < total_views; v += K2_THREADS) {
-      const int pos = atomicAdd(&S.bucket_cnt[31 - __clz((int) (S.sortbuf[v] >> 16))], 1);
-      S.torder[pos] = (uint16_t) v;
+    for (int v0 = warp * 32; v0 < total_views; v0 += K2_THREADS) {
+      const int v = v0 + lane;
+      const bool valid = v < total_views;
+      const bool big = valid && (S.sortbuf[v] >> 16) >= 48u;
+      const unsigned mb = __ballot_sync(0xFFFFFFFFu, big), ms = __ballot_sync(0xFFFFFFFFu, valid && !big);
+      int fb = 0, bb2 = 0;
+      if (lane == 0) {
+        if (mb) fb = atomicAdd(&S.bucket_cnt[0], __popc(mb));
+        if (ms) bb2 = atomicSub(&S.bucket_cnt[1], __popc(ms));
+      }
+      fb = __shfl_sync(0xFFFFFFFFu, fb, 0);
+      bb2 = __shfl_sync(0xFFFFFFFFu, bb2, 0);
+      if (big) S.torder[fb + __popc(mb & ((1u << lane) - 1u))] = (uint16_t) v;
+      if (valid && !big) S.torder[bb2 - 1 - __popc(ms & ((1u << lane) - 1u))] = (uint16_t) v;
     }
     __syncthreads();
     // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]

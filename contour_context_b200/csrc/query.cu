@@ -431,14 +431,17 @@ __device__ void score_hint(const c2g_scan_head *heads, const c2g_view *views, in
   }
 }
 
-__global__ void __launch_bounds__(SC_WARPS * 32)
-score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, long long n_hints,
-             QueryParams Q, const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores) {
-  __shared__ ScoreScratch scratch[SC_WARPS];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long hid = (long long) blockIdx.x * SC_WARPS + w;
-  if (hid >= n_hints) return;
-  if (lane == 0) {
+// Stage 1 of the hint cascade, one THREAD per hint slot: the anchor similarity gate (contour_db.h:388) and the 256-bit
+// popcount gate of BCI::checkConstellSim (contour_mng.h:291-307) kill ~85 % of the hints with two 80-byte and two 32-byte
+// reads each; the record of a dead hint is final here, survivors are queued for the warp-per-hint stage.
+__global__ void __launch_bounds__(256)
+prefilter_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, long long n_hints,
+                 QueryParams Q, const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores,
+                 int *__restrict__ survivors, int *__restrict__ n_surv) {
+  const long long hid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool survive = false;
+  if (hid < n_hints) {
     const c2g_hint h = hints[hid];
     c2g_pair_score rec;
     rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
@@ -449,8 +452,66 @@ score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict
     rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
     for (int i = 0; i < C2G_PAIR_WORDS; ++i) rec.pair_bits[i] = 0ull;
     rec.pad2_ = 0ull;
-    if (h.cand_gidx >= 0) score_hint(heads, views, first_slot + h.q_idx, h, Q, scratch[w], rec);
-    scores[hid] = rec;
+    if (h.cand_gidx >= 0) {
+      const int q_slot = first_slot + h.q_idx;
+      if (check_sim(view_at(heads, views, h.cand_gidx, h.level, h.cand_seq), view_at(heads, views, q_slot, h.level, h.q_seq), Q.sim)) {
+        const c2g_bci &src = heads[h.cand_gidx].bcis[h.level][h.cand_seq];
+        const c2g_bci &tgt = heads[q_slot].bcis[h.level][h.q_seq];
+        int ov1 = 0, ov2 = 0, ov3 = 0;
+        unsigned long long s4[4], t4[4];
+        for (int i = 0; i < 4; ++i) {
+          s4[i] = src.dist_bin[i];
+          t4[i] = tgt.dist_bin[i];
+        }
+        for (int i = 0; i < 4; ++i) {
+          const unsigned long long sl = (s4[i] << 1) | (i > 0 ? (s4[i - 1] >> 63) : 0ull);
+          const unsigned long long sr = (s4[i] >> 1) | (i < 3 ? (s4[i + 1] << 63) : 0ull);
+          ov1 += __popcll(s4[i] & t4[i]);
+          ov2 += __popcll(sl & t4[i]);
+          ov3 += __popcll(sr & t4[i]);
+        }
+        rec.constell[0] = ov1 + ov2 + ov3;
+        rec.constell[1] = max(ov1, max(ov2, ov3));
+        rec.passed = -1;
+        survive = rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one;
+      }
+    }
+    if (!survive) scores[hid] = rec;  // survivors' records are written by score_kernel
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, survive);
+  if (m) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(n_surv, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (survive) survivors[base + __popc(m & ((1u << lane) - 1u))] = (int) hid;
+  }
+}
+
+// Stage 2, one WARP per surviving hint (lane 0 runs the sequential cascade on the warp's shared scratch), grid-stride.
+__global__ void __launch_bounds__(SC_WARPS * 32)
+score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, QueryParams Q,
+             const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores, const int *__restrict__ survivors,
+             const int *__restrict__ n_surv) {
+  __shared__ ScoreScratch scratch[SC_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = *n_surv;
+  for (int i = blockIdx.x * SC_WARPS + w; i < n; i += gridDim.x * SC_WARPS) {
+    if (lane == 0) {
+      const int hid = survivors[i];
+      const c2g_hint h = hints[hid];
+      c2g_pair_score rec;
+      rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
+      rec.pairwise[0] = rec.pairwise[1] = 0;
+      rec.passed = 0;
+      rec.n_pairs = 0;
+      rec.pad_ = 0;
+      rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
+      for (int k = 0; k < C2G_PAIR_WORDS; ++k) rec.pair_bits[k] = 0ull;
+      rec.pad2_ = 0ull;
+      score_hint(heads, views, first_slot + h.q_idx, h, Q, scratch[w], rec);
+      scores[hid] = rec;
+    }
+    __syncwarp();
   }
 }
 
@@ -828,6 +889,8 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_hints, sizeof(c2g_hint) * (size_t) ctx->n_hint_slots));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_scores, sizeof(c2g_pair_score) * (size_t) ctx->n_hint_slots));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_results, sizeof(c2g_query_result) * (size_t) ctx->max_batch));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_survivors, sizeof(int) * (size_t) ctx->n_hint_slots));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int)));
   for (int i = 0; i < ctx->db.n_q_levels; ++i) {
     C2gLayerTable &t = ctx->layers[i];
     t.cap = ctx->scan_cap * C2G_MAX_PIV;
@@ -847,6 +910,8 @@ void c2g_query_free(c2g_ctx *ctx) {
   cudaFree(ctx->d_hints);
   cudaFree(ctx->d_scores);
   cudaFree(ctx->d_results);
+  cudaFree(ctx->d_survivors);
+  cudaFree(ctx->d_nsurv);
   for (int i = 0; i < C2G_NUM_Q_LEVELS_MAX; ++i) {
     cudaFree(ctx->layers[i].keys_t);
     cudaFree(ctx->layers[i].gidx);
@@ -921,10 +986,18 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, first_slot, B, Q, ctx->d_hints);
   C2G_CUDA_TRY(cudaGetLastError());
   const long long n_hints = (long long) n_keys * Q.nnk;
-  score_kernel<<<(unsigned) ((n_hints + SC_WARPS - 1) / SC_WARPS), SC_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot,
-                                                                                                    n_hints, Q, ctx->d_hints, ctx->d_scores);
+  C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int), ctx->stream));
+  prefilter_kernel<<<(unsigned) ((n_hints + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, n_hints, Q, ctx->d_hints,
+                                                                               ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
   C2G_CUDA_TRY(cudaGetLastError());
-  ctx->launches += 2;
+  {
+    const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
+    const long long cap = (long long) ctx->num_sms * 16;
+    score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints,
+                                                                                       ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
+  }
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 3;
   return launch_finish(ctx, first_slot, B, Q, ctx->d_hints, ctx->d_scores);
 }
 
