@@ -85,8 +85,9 @@ int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, 
     *pts_dev = pts;
   } else {
     if (offsets_host[B] > ctx->max_points) return C2G_ERR_CAPACITY;
-    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage, pts, sizeof(float) * 4 * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
-    *pts_dev = ctx->d_pts_stage;
+    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage2[0], pts, sizeof(float) * 4 * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
+    C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[0], ctx->stream));
+    *pts_dev = ctx->d_pts_stage2[0];
   }
   return 0;
 }
@@ -158,7 +159,19 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
     return -(int) e;
   }
   ctx->stream = ctx->own_stream;
-  ALLOC(ctx->d_pts_stage, sizeof(float) * 4 * (size_t) max_points);
+  ALLOC(ctx->d_pts_stage2[0], sizeof(float) * 4 * (size_t) max_points);
+  ALLOC(ctx->d_pts_stage2[1], sizeof(float) * 4 * (size_t) max_points);
+  e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    c2g_destroy(ctx);
+    return -(int) e;
+  }
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_stage_free[i], cudaEventDisableTiming);
+  for (int i = 0; i < C2G_MAX_CHUNK_EVENTS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    c2g_destroy(ctx);
+    return -(int) e;
+  }
   ALLOC(ctx->d_offsets, sizeof(long long) * (max_batch + 1));
   ALLOC(ctx->d_int_ids, sizeof(int) * max_batch);
   ALLOC(ctx->d_tiles, sizeof(c2g_cellkey) * ncell * max_batch);
@@ -193,7 +206,13 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaDeviceSynchronize();
   c2g_query_free(ctx);
   delete ctx->hostdb;
-  cudaFree(ctx->d_pts_stage);
+  cudaFree(ctx->d_pts_stage2[0]);
+  cudaFree(ctx->d_pts_stage2[1]);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->ev_stage_free[i]) cudaEventDestroy(ctx->ev_stage_free[i]);
+  for (int i = 0; i < C2G_MAX_CHUNK_EVENTS; ++i)
+    if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_offsets);
   cudaFree(ctx->d_int_ids);
   cudaFree(ctx->d_tiles);
@@ -234,16 +253,55 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
   return 0;
 }
 
+// Host inputs: the batch is cut into chunks of one wave (num_sms scans); chunk k+1 crosses PCIe on the copy stream while the
+// kernels of chunk k run, and the two staging buffers alternate between calls so that the copy of the NEXT call starts while
+// this call's query kernels are still running.  Device inputs: two launches for the whole batch.
+static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *ids_dev) {
+  if (offsets_host[B] - offsets_host[0] > ctx->max_points) return C2G_ERR_CAPACITY;
+  const size_t ncell = ctx->P.n_cells;
+  const int cur = ctx->stage_sel;
+  ctx->stage_sel ^= 1;
+  float *stage = ctx->d_pts_stage2[cur];
+  // offsets relative to the staging buffer
+  std::vector<long long> rel((size_t) B + 1);
+  for (int i = 0; i <= B; ++i) rel[i] = offsets_host[i] - offsets_host[0];
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_offsets, rel.data(), sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  // the copy stream may overwrite this staging buffer only after the kernels that last read it have finished
+  C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_free[cur], 0));
+  const int CH = ctx->num_sms;
+  int k = 0;
+  for (int b0 = 0; b0 < B; b0 += CH, ++k) {
+    const int n = (B - b0 < CH) ? (B - b0) : CH;
+    const size_t p0 = (size_t) rel[b0], p1 = (size_t) rel[b0 + n];
+    C2G_CUDA_TRY(cudaMemcpyAsync(stage + 4 * p0, pts + 4 * ((size_t) offsets_host[0] + p0), sizeof(float) * 4 * (p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
+    cudaEvent_t ev = ctx->ev_chunk[k % C2G_MAX_CHUNK_EVENTS];
+    C2G_CUDA_TRY(cudaEventRecord(ev, ctx->copy_stream));
+    C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, ctx->d_tiles + ncell * b0, ctx->num_sms, ctx->stream);
+    if (rc) return rc;
+    rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0,
+                             ctx->d_bev_h + ncell * b0, ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads,
+                             ctx->d_views, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
+    if (rc) return rc;
+    ctx->launches += 2;
+  }
+  C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[cur], ctx->stream));
+  ctx->last_B = B;
+  ctx->last_pts = stage;
+  return 0;
+}
+
 int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
                const int *int_ids_host) {
-  if (!ctx || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
-  int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
-  if (rc) return rc;
+  if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
   const int *ids_dev = nullptr;
   if (int_ids_host) {
     C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids, int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
     ids_dev = ctx->d_int_ids;
   }
+  if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev);
+  int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
+  if (rc) return rc;
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
                            ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;

@@ -2,6 +2,8 @@
 #pragma once
 #include "c2g_common.cuh"
 
+#define C2G_MAX_CHUNK_EVENTS 64
+
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
   float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans, bucket-major, tree order inside a bucket
   int *gidx;             // IndexOfKey::gidx
@@ -21,7 +23,11 @@ struct c2g_ctx {
   long long max_points;
   cudaStream_t own_stream, stream;
   // ingest buffers
-  float *d_pts_stage;
+  float *d_pts_stage2[2];              // double-buffered staging of host point batches
+  int stage_sel;
+  cudaStream_t copy_stream;            // H2D of chunk k+1 overlaps the kernels of chunk k
+  cudaEvent_t ev_stage_free[2];        // recorded when the kernels reading a staging buffer are done
+  cudaEvent_t ev_chunk[C2G_MAX_CHUNK_EVENTS];
   long long *d_offsets;
   int *d_int_ids;
   c2g_cellkey *d_tiles;

@@ -637,60 +637,65 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
         if (ti >= total_views) break;
         const int v = S.torder[ti];
-        int lev = 0;
-        for (int l = 0; l < C2G_NLEV; ++l)
-          if (v >= S.view_off[l] && v < S.view_off[l] + S.n_views[l]) lev = l;
         const int n = S.t_cnt[v];
         const uint16_t *wl = lists + S.t_off[v];
         double acc = 0.0;
         float vol3 = 0.0f;
         for (int g = 0; g < n; g += 128) {
-          float hv[4];
-          double rv[4], cv[4];
+          float hv[4], rv[4], cv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = g + u * 32 + lane;
-            hv[u] = 0.f;
-            rv[u] = cv[u] = 0.0;
+            hv[u] = rv[u] = cv[u] = 0.f;
             if (j < n) {
               const int cc = wl[j];
               hv[u] = hg[cc];
-              rv[u] = (double) rfg[cc];
-              cv[u] = (double) cfp[cc];
+              rv[u] = rfg[cc];
+              cv[u] = cfp[cc];
             }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int cntu = min(32, n - (g + u * 32));
             for (int src = 0; src < cntu; ++src) {
+              // three 32-bit shuffles per cell; every lane converts only the two operands its accumulator needs
               const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
-              const double v0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
-              const double v1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
-              const double hd = (double) hh;
-              const double a = selA == 0 ? v0 : selA == 1 ? v1 : selA == 2 ? hd : 1.0;
-              const double bb2 = selB == 0 ? v0 : selB == 1 ? v1 : 1.0;
-              acc += a * bb2;
+              const float f0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
+              const float f1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
+              const float fa = selA == 0 ? f0 : selA == 1 ? f1 : selA == 2 ? hh : 1.0f;
+              const float fb = selB == 0 ? f0 : selB == 1 ? f1 : 1.0f;
+              acc += (double) fa * (double) fb;
               vol3 += hh;
             }
           }
         }
-        Moments m;
-        m.cnt = n;
-        m.vol3 = vol3;
-        m.s0 = __shfl_sync(0xFFFFFFFFu, acc, 0);
-        m.s1 = __shfl_sync(0xFFFFFFFFu, acc, 1);
-        m.t00 = __shfl_sync(0xFFFFFFFFu, acc, 2);
-        m.t01 = __shfl_sync(0xFFFFFFFFu, acc, 3);
-        m.t11 = __shfl_sync(0xFFFFFFFFu, acc, 4);
-        m.q0 = __shfl_sync(0xFFFFFFFFu, acc, 5);
-        m.q1 = __shfl_sync(0xFFFFFFFFu, acc, 6);
-        if (lane == 0) {
-          c2g_view vw;
-          const int poi = S.t_poi[v];
-          calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, vw);
-          presort[v] = vw;
-        }
+        // raw moments go to the component's (still unused) 80-byte presort record: doubles 0..6 from lanes 0..6, the
+        // float height sum in word 14; calcStatVals for all components runs afterwards with one thread per component
+        double *raw = reinterpret_cast<double *>(presort + v);
+        if (lane < 7) raw[lane] = acc;
+        if (lane == 7) reinterpret_cast<float *>(raw + 7)[0] = vol3;
       }
+    }
+    __syncthreads();
+    for (int v = tid; v < total_views; v += K2_THREADS) {
+      const double *raw = reinterpret_cast<const double *>(presort + v);
+      Moments m;
+      m.cnt = S.t_cnt[v];
+      m.s0 = raw[0];
+      m.s1 = raw[1];
+      m.t00 = raw[2];
+      m.t01 = raw[3];
+      m.t11 = raw[4];
+      m.q0 = raw[5];
+      m.q1 = raw[6];
+      m.vol3 = reinterpret_cast<const float *>(raw + 7)[0];
+      int lev = 0;
+      for (int l = 0; l < C2G_NLEV; ++l)
+        if (v >= S.view_off[l] && v < S.view_off[l] + S.n_views[l]) lev = l;
+      c2g_view vw;
+      const int poi = S.t_poi[v];
+      calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, vw);
+      presort[v] = vw;  // in place: this thread is the only reader and writer of the record
     }
     __syncthreads();
     C2G_DBG(3);
