@@ -145,6 +145,8 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner to stdout otherwise (the JSON line must be alone)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
         g.build_c2g()

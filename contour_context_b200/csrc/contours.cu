@@ -405,7 +405,11 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
       __syncthreads();
       C2G_DBG(10 + lev * 8 + 1);
-      // B3 flatten: one read-only find per run, the whole run takes that root
+      // B3 flatten, phase 1: compressing finds (path halving) on the run starts shorten every chain; no cell is finalised yet,
+      // so a halving store can never clobber a final root
+      for (uint32_t sb = starts; sb; sb &= sb - 1) (void) uf_find(S.L, cb0 + __ffs(sb) - 1);
+      __syncthreads();
+      // phase 2: one read-only find per run (now a hop or two), the whole run takes that root
       for (uint32_t sb = starts; sb; sb &= sb - 1) {
         const int k0 = __ffs(sb) - 1;
         const uint32_t root = uf_find_ro(S.L, cb0 + k0);
@@ -590,7 +594,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     C2G_DBG(2);
     // ---------------- phase C: balanced task pool: per-level std::sort replays + moments / calcStatVals per component -----
     // Tasks are ordered by decreasing size class (floor(log2(area))) so the longest sequential accumulations start first.
-    // Big components (>= 48 cells) go to the front of the task order, small ones fill it from the back; positions are
+    // Big components (> 32 cells) go to the front of the task order, small ones fill it from the back; positions are
     // claimed with one shared atomic per warp and class (same-address shared atomics serialise).
     if (tid == 0) {
       S.wq = 0;
@@ -601,7 +605,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     for (int v0 = warp * 32; v0 < total_views; v0 += K2_THREADS) {
       const int v = v0 + lane;
       const bool valid = v < total_views;
-      const bool big = valid && (S.sortbuf[v] >> 16) >= 48u;
+      const bool big = valid && (S.sortbuf[v] >> 16) > 32u;
       const unsigned mb = __ballot_sync(0xFFFFFFFFu, big), ms = __ballot_sync(0xFFFFFFFFu, valid && !big);
       int fb = 0, bb2 = 0;
       if (lane == 0) {
@@ -625,17 +629,54 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       for (int i = 0; i < S.n_views[warp]; ++i) sum += (int) (first[i] >> 16);
       S.layer_cnt[warp] = sum;
     }
+    C2G_DBG(58);
+    const int n_big = S.bucket_cnt[0];  // torder[0, n_big) = components of more than 32 cells, the rest follow
+    // Small components: one THREAD per component walks its own member list (<= 32 cells) with the seven double
+    // accumulators of RunningStatRecorder in registers, 32 components per warp instruction. Warps 0..5 are busy with the
+    // per-level sorts above, warps 6..31 take the small components.
+    if (warp >= C2G_NLEV) {
+      for (int i = n_big + (tid - C2G_NLEV * 32); i < total_views; i += K2_THREADS - C2G_NLEV * 32) {
+        const int v = S.torder[i];
+        const int n = S.t_cnt[v];
+        const uint16_t *wl = lists + S.t_off[v];
+        double s0 = 0, s1 = 0, t00 = 0, t01 = 0, t11 = 0, q0 = 0, q1 = 0;
+        float vol3 = 0.0f;
+        for (int j = 0; j < n; ++j) {
+          const int cc = wl[j];
+          const float hh = hg[cc];
+          const double v0 = (double) rfg[cc], v1 = (double) cfp[cc], hd = (double) hh;
+          s0 += v0;
+          s1 += v1;
+          t00 += v0 * v0;
+          t01 += v0 * v1;
+          t11 += v1 * v1;
+          vol3 += hh;
+          q0 += hd * v0;
+          q1 += hd * v1;
+        }
+        double *raw = reinterpret_cast<double *>(presort + v);
+        raw[0] = s0;
+        raw[1] = s1;
+        raw[2] = t00;
+        raw[3] = t01;
+        raw[4] = t11;
+        raw[5] = q0;
+        raw[6] = q1;
+        reinterpret_cast<float *>(raw + 7)[0] = vol3;
+      }
+    }
     {
-      // The seven double accumulators of RunningStatRecorder live in lanes 0..6: lane k adds a_k * b_k per member cell
-      // (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1, t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the
-      // FP64 pipe one DMUL + one DADD per warp. Accumulation order = list order = bbox-raster order.
+      // Big components: one WARP per component from a shared queue (largest size class first). The seven double
+      // accumulators live in lanes 0..6: lane k adds a_k * b_k per member cell (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1,
+      // t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the FP64 pipe one DMUL + one DADD per warp.
+      // Accumulation order = list order = bbox-raster order.
       const int selA = (lane == 0 || lane == 2 || lane == 3) ? 0 : (lane == 1 || lane == 4) ? 1 : (lane == 5 || lane == 6) ? 2 : 3;
       const int selB = (lane == 2 || lane == 5) ? 0 : (lane == 3 || lane == 4 || lane == 6) ? 1 : 3;
       while (true) {
         int ti = 0;
         if (lane == 0) ti = atomicAdd(&S.wq, 1);
         ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
-        if (ti >= total_views) break;
+        if (ti >= n_big) break;
         const int v = S.torder[ti];
         const int n = S.t_cnt[v];
         const uint16_t *wl = lists + S.t_off[v];
@@ -676,7 +717,9 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         if (lane == 7) reinterpret_cast<float *>(raw + 7)[0] = vol3;
       }
     }
+    C2G_DBG(59);
     __syncthreads();
+    C2G_DBG(60);
     for (int v = tid; v < total_views; v += K2_THREADS) {
       const double *raw = reinterpret_cast<const double *>(presort + v);
       Moments m;

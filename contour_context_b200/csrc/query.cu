@@ -522,7 +522,7 @@ struct EllD {
   double mx, my, c00, c10, c01, c11;
   float maj, w;
 };
-constexpr int ELL_CAP = 128;
+constexpr int ELL_CAP = 64;
 constexpr int FIN_WARPS = 4;  // warps per CTA of the finish kernel: one query scan per CTA, candidates spread over warps
 
 struct Prop {
@@ -543,9 +543,10 @@ struct FinishScratch {
   int n_cand;
   uint32_t ord[C2G_MAX_CAND];
   float corr[C2G_MAX_CAND];
-  uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64];  // hint indices that reached addProposal, in order
+  uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64 + 8];  // hint indices that reached addProposal: one sublist per warp
   EllD es[FIN_WARPS][ELL_CAP], et[FIN_WARPS][ELL_CAP];          // per warp: one level's ellipses of candidate / query
   int aft[3], overflow;
+  int w_aft1[FIN_WARPS], w_aft2[FIN_WARPS], w_npass[FIN_WARPS];
 };
 
 __device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
@@ -601,8 +602,8 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *view
         stage_ellipses(sv + s0, cs_, es, lane);
         stage_ellipses(tv + t0, ct_, et, lane);
         __syncwarp();
-        for (int w = lane; w < cs_ * ct_; w += 32) {
-          const int si = w / ct_, ti = w - si * ct_;
+        for (int si = 0; si < cs_; ++si)
+        for (int ti = lane; ti < ct_; ti += 32) {
           const EllD a = es[si];
           const EllD b = et[ti];
           const double qx = (T[0] * a.mx + (-T[1]) * a.my) + T[2], qy = (T[1] * a.mx + T[0] * a.my) + T[3];
@@ -672,27 +673,46 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
   const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
   const c2g_hint *hq = hints + (size_t) q * per_q;
   const c2g_pair_score *sq = scores + (size_t) q * per_q;
-  if (w == 0) {
-    int aft1 = 0, aft2 = 0, overflow = 0;
-    // all lanes scan the hint records; only the few that reached addProposal are replayed sequentially
-    int n_pass = 0;
-    for (long long base = 0; base < per_q; base += 32) {
+  // all four warps scan a quarter of the hint records each (in order); only the few hints that reached addProposal are
+  // replayed sequentially afterwards
+  {
+    const int quarter = (int) ((per_q + FIN_WARPS - 1) / FIN_WARPS);
+    const long long beg = (long long) w * quarter, end = beg + quarter < per_q ? beg + quarter : per_q;
+    uint16_t *pl = F.passlist + w * quarter;
+    int aft1 = 0, aft2 = 0, n_pass = 0;
+    for (long long base = beg; base < end; base += 32) {
       const long long i = base + lane;
       int p = 0;
-      if (i < per_q && hq[i].cand_gidx >= 0) p = sq[i].passed;
-      const bool valid = i < per_q && hq[i].cand_gidx >= 0;
+      const bool valid = i < end && hq[i].cand_gidx >= 0;
+      if (valid) p = sq[i].passed;
       aft1 += __popc(__ballot_sync(0xFFFFFFFFu, valid && p != 0));
       aft2 += __popc(__ballot_sync(0xFFFFFFFFu, valid && (p == 1 || p == -2)));
       const unsigned pm = __ballot_sync(0xFFFFFFFFu, valid && p == 1);
-      if (valid && p == 1) F.passlist[n_pass + __popc(pm & ((1u << lane) - 1u))] = (uint16_t) i;
+      if (valid && p == 1) pl[n_pass + __popc(pm & ((1u << lane) - 1u))] = (uint16_t) i;
       n_pass += __popc(pm);
     }
-    __syncwarp();
+    if (lane == 0) {
+      F.w_aft1[w] = aft1;
+      F.w_aft2[w] = aft2;
+      F.w_npass[w] = n_pass;
+    }
+  }
+  __syncthreads();
+  if (w == 0) {
+    int overflow = 0;
+    const int quarter = (int) ((per_q + FIN_WARPS - 1) / FIN_WARPS);
     if (lane == 0) {
       F.n_cand = 0;
       // replay checkCandWithHint's bookkeeping in reference order: (q-level, query seq, ascending distance)
-      for (int k0 = 0; k0 < n_pass; ++k0) {
-        const int i = F.passlist[k0];
+      int aft1 = 0, aft2 = 0, n_pass = 0;
+      for (int ww = 0; ww < FIN_WARPS; ++ww) {
+        aft1 += F.w_aft1[ww];
+        aft2 += F.w_aft2[ww];
+        n_pass += F.w_npass[ww];
+      }
+      for (int ww = 0; ww < FIN_WARPS; ++ww)
+      for (int k0 = 0; k0 < F.w_npass[ww]; ++k0) {
+        const int i = F.passlist[ww * quarter + k0];
         const c2g_pair_score &r = sq[i];
         const int gidx = hq[i].cand_gidx;
         int ci = -1;

@@ -48,6 +48,7 @@ capi.lib().c2g_debug_clocks(eng.h, clk.ctypes.data_as(C.c_void_p))
 names = {0:'start',1:'A done',2:'levels done',3:'sort done',4:'views copied',5:'D1 done',6:'D2+keys done',7:'BCI done',8:'GMM done',9:'end'}
 t0 = clk[0]
 for i in range(10): print(f"  {names[i]:14s} {(clk[i]-t0)/1e3:9.1f} kcyc")
+print(f'  phaseC: order+prep {(clk[58]-clk[2])/1e3:.1f}?  sort(tid0) end {(clk[58]-clk[2])/1e3:.1f}  own walk end {(clk[59]-clk[2])/1e3:.1f}  barrier {(clk[60]-clk[2])/1e3:.1f}  calcstat {(clk[3]-clk[60])/1e3:.1f} kcyc')
 for lev in range(6):
     s = clk[10+lev*8: 10+lev*8+7]
     base = clk[1] if lev == 0 else clk[10+(lev-1)*8+6]
