@@ -8,6 +8,7 @@ struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (hos
   float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans, bucket-major, tree order inside a bucket
   int *gidx;             // IndexOfKey::gidx
   signed char *seq;      // IndexOfKey::seq
+  int *orank;            // flat tree-order index of every entry (tie-break rank; the mirror itself is sorted by key[0] inside a bucket)
   int n, cap;
   int bucket_off[C2G_NUM_BUCKETS + 1];
   float ranges[C2G_NUM_BUCKETS + 1];

@@ -16,6 +16,9 @@
 // (q-level, query seq, ascending key distance).
 #include "../../include/c2g.h"
 #include "c2g_ctx.cuh"
+#include <algorithm>
+#include <vector>
+
 #include "stdsort.cuh"
 #include "c2g_libm.cuh"
 
@@ -30,8 +33,9 @@ struct LayerDev {
   const float *keys_t;  // [KEY_DIM][cap]
   const int *gidx;
   const signed char *seq;
+  const int *orank;     // flat index in bucket-major TREE order (what the entry's position would be without the key[0] sort)
   int cap;
-  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1])
+  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1]), sorted by key[0]
   float ranges[C2G_NUM_BUCKETS + 1];
 };
 struct QueryParams {
@@ -73,6 +77,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, Query
   }
   float bd[2] = {3.0e38f, 3.0e38f};  // top-k distances (sorted ascending across slots), empty = +big
   int bi[2] = {-1, -1};
+  int bo[2] = {0x7FFFFFFF, 0x7FFFFFFF};  // original flat index (bucket-major tree order) of every kept entry: tie order
   int count = 0;
   const int K = Q.nnk;  // <= 64
   if (seq < Q.piv && ksum != 0.0f) {  // `q_keys[seq].sum() != 0` (contour_db.h:726); NaN keys search and find nothing
@@ -100,62 +105,118 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, Query
       else if (mid + i < C2G_NUM_BUCKETS)
         visit |= 1u << (mid + i);
     }
-    float thr = dist_ub;  // strict `dist < worst` (nanoflann.hpp:1575); NaN dist_ub admits nothing
+    // Admission key = (distance, original flat index) in lexicographic order; initial worst = (dist_ub, -1): strict
+    // `dist < worst` (nanoflann.hpp:1575), NaN dist_ub admits nothing. Inside a bucket the mirror is sorted by key[0]
+    // (c2g_db_set_layer), so the scan starts at the query's key[0] and walks outwards in both directions; a side stops
+    // as soon as (q0 - k0)^2 alone reaches the current K-th distance (every other term of the metric is >= 0).
+    float thr = dist_ub;
+    int thr_o = -1;
+    const float *k0col = T.keys_t;
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
       if (!((visit >> bk) & 1u)) continue;
       const int beg = T.bucket_off[bk], end = T.bucket_off[bk + 1];
-      for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
-        float dist = 3.0e38f;
-        if (i < end) {
-          float df[C2G_KEY_DIM];
-#pragma unroll
-          for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
-          // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
-          float r = 0.0f;
-          r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
-          r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
-          r += df[8] * df[8];
-          r += df[9] * df[9];
-          dist = r;
+      if (beg >= end) continue;
+      // warp-parallel 32-way search for the first entry with k0 >= q0
+      int lo = beg, hi = end;  // invariant: k0[i] < q0 for i < lo; k0[hi] >= q0 or hi == end
+      while (lo < hi) {
+        const int step = (hi - lo + 31) / 32;
+        const int probe = lo + lane * step;
+        const bool ge = probe < hi ? (k0col[probe] >= key[0]) : true;
+        const int first = __ffs(__ballot_sync(0xFFFFFFFFu, ge)) - 1;
+        if (first < 0) {
+          lo = lo + 31 * step + 1;  // all 32 probes are below q0
+        } else {
+          const int nhi = min(hi, lo + first * step);                     // probe[first] >= q0 (or past the range)
+          const int nlo = first == 0 ? lo : lo + (first - 1) * step + 1;  // probe[first - 1] < q0
+          lo = nlo;
+          hi = nhi;
         }
-        unsigned cand = __ballot_sync(0xFFFFFFFFu, i < end && dist < thr);
-        while (cand) {
-          const int src = __ffs(cand) - 1;
-          cand &= cand - 1;
-          const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
-          const int ni = base + src;
-          if (!(nd < thr)) continue;  // threshold may have tightened since the ballot
-          // position = number of kept entries with distance <= nd (equal distances keep the earlier index first)
-          const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] <= nd);
-          const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] <= nd);
-          const int pos = __popc(le0) + __popc(le1);
-          // shift slots [pos, K-1) up by one: slot j takes slot j-1
-          const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
-          const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
-          const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
-          const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31);
-          const int j0 = lane, j1 = lane + 32;
-          if (j1 > pos) {
-            bd[1] = (lane == 0) ? last0 : up1;
-            bi[1] = (lane == 0) ? lasti0 : ui1;
+      }
+      const int center = lo;  // first index with k0 >= q0 (== end if none)
+      int R = center, Lp = center - 1;
+      bool r_live = R < end, l_live = Lp >= beg;
+      while (r_live || l_live) {
+        for (int side = 0; side < 2; ++side) {
+          int base;
+          if (side == 0) {
+            if (!r_live) continue;
+            base = R;
+          } else {
+            if (!l_live) continue;
+            base = Lp - 31;
           }
-          if (j0 > pos) {
-            bd[0] = up0;
-            bi[0] = ui0;
+          const int i = base + lane;
+          const bool in = i >= beg && i < end && (side == 0 ? true : i <= Lp);
+          float dist = 3.0e38f, d0sq = 3.0e38f;
+          int orig = 0x7FFFFFFF;
+          if (in) {
+            float df[C2G_KEY_DIM];
+#pragma unroll
+            for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
+            d0sq = df[0] * df[0];
+            // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
+            float r = 0.0f;
+            r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
+            r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
+            r += df[8] * df[8];
+            r += df[9] * df[9];
+            dist = r;
+            orig = T.orank[i];
           }
-          if (j0 == pos) {
-            bd[0] = nd;
-            bi[0] = ni;
+          unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
+          while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
+            const int no = __shfl_sync(0xFFFFFFFFu, orig, src);
+            const int ni = base + src;
+            if (!(nd < thr || (nd == thr && no < thr_o))) continue;  // the worst kept entry may have tightened meanwhile
+            // position = number of kept entries that precede (nd, no)
+            const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] < nd || (bd[0] == nd && bo[0] < no));
+            const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] < nd || (bd[1] == nd && bo[1] < no));
+            const int pos = __popc(le0) + __popc(le1);
+            const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
+            const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
+            const int uo0 = __shfl_up_sync(0xFFFFFFFFu, bo[0], 1), uo1 = __shfl_up_sync(0xFFFFFFFFu, bo[1], 1);
+            const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
+            const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31), lasto0 = __shfl_sync(0xFFFFFFFFu, bo[0], 31);
+            const int j0 = lane, j1 = lane + 32;
+            if (j1 > pos) {
+              bd[1] = (lane == 0) ? last0 : up1;
+              bi[1] = (lane == 0) ? lasti0 : ui1;
+              bo[1] = (lane == 0) ? lasto0 : uo1;
+            }
+            if (j0 > pos) {
+              bd[0] = up0;
+              bi[0] = ui0;
+              bo[0] = uo0;
+            }
+            if (j0 == pos) {
+              bd[0] = nd;
+              bi[0] = ni;
+              bo[0] = no;
+            }
+            if (j1 == pos) {
+              bd[1] = nd;
+              bi[1] = ni;
+              bo[1] = no;
+            }
+            if (count < K) ++count;
+            if (count == K) {  // worst kept entry = K-th best
+              const int ks = K - 1;
+              thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
+              thr_o = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bo[0] : bo[1], ks & 31);
+            }
           }
-          if (j1 == pos) {
-            bd[1] = nd;
-            bi[1] = ni;
-          }
-          if (count < K) ++count;
-          if (count == K) {  // threshold = K-th best
-            const int ks = K - 1;
-            thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
+          // advance this side; it dies when exhausted or when its next key is already too far in key[0] alone
+          if (side == 0) {
+            R += 32;
+            const float edge = __shfl_sync(0xFFFFFFFFu, d0sq, 31);  // farthest key of the chunk just scanned
+            r_live = R < end && !(edge >= thr);
+          } else {
+            Lp -= 32;
+            const float edge = __shfl_sync(0xFFFFFFFFu, d0sq, 0);
+            l_live = Lp >= beg && !(edge >= thr);
           }
         }
       }
@@ -211,11 +272,34 @@ struct CPairD {
   int8_t level, seq_src, seq_tgt;
 };
 
+// What the cascade reads of a ContourView (contour.h:106-119), staged in shared memory per warp
+struct ViewLite {
+  float mean0, mean1, eig0, eig1, vol3_mean, com0, com1, evx, evy;  // evx/evy = eig_vecs.col(1)
+  int16_t cell_cnt;
+  uint8_t ecc_feat, valid;
+};
+__device__ __forceinline__ bool check_sim_lite(const ViewLite &s, const ViewLite &t, const c2g_sim_config &th) {
+  const float sc = (float) s.cell_cnt, tc = (float) t.cell_cnt;
+  if (diff_perc_f(sc, tc, th.tp_cell_cnt) && diff_delt_f(sc, tc, th.ta_cell_cnt)) return false;
+  if ((double) fmaxf(s.eig1, t.eig1) > 2.0 && diff_perc_f(sqrtf(s.eig1), sqrtf(t.eig1), th.tp_eigval)) return false;
+  if ((double) fmaxf(s.eig0, t.eig0) > 2.0 && diff_perc_f(sqrtf(s.eig0), sqrtf(t.eig0), th.tp_eigval)) return false;
+  if (max((int) s.cell_cnt, (int) t.cell_cnt) > 15 && diff_delt_f(s.vol3_mean, t.vol3_mean, th.ta_h_bar)) return false;
+  const float sx = s.com0 - s.mean0, sy = s.com1 - s.mean1;
+  const float tx = t.com0 - t.mean0, ty = t.com1 - t.mean1;
+  const float r1 = sqrtf(sx * sx + sy * sy), r2 = sqrtf(tx * tx + ty * ty);
+  if (diff_delt_f(r1, r2, th.ta_rcom) && diff_perc_f(r1, r2, th.tp_rcom)) return false;
+  return true;
+}
+
+constexpr int SV_PER_SCAN = C2G_NUM_BIN_LAYERS * C2G_MAX_DIST_FIRSTS;  // levels 1..4 x top-10 contours
 struct ScoreScratch {
   PotPair pot[MAX_POT_PAIRS];
   uint32_t ord[MAX_POT_PAIRS];  // sort permutation (indices into pot)
   CPairD c1[MAX_POT_PAIRS + 1];
   CPairD c2[MAX_POT_PAIRS + 1];
+  uint8_t drop[MAX_POT_PAIRS + 1];  // orientation filter verdict per entry of c2
+  c2g_bci bs, bt;                   // BCI of the candidate (src) and of the query (tgt) anchor
+  ViewLite vs[SV_PER_SCAN], vt[SV_PER_SCAN];
 };
 
 __device__ __forceinline__ float clamp_ang_f(float ang) {  // clampAng<float>: double arithmetic, stored to float
@@ -233,201 +317,263 @@ __device__ __forceinline__ void normalized2(float x, float y, float &ox, float &
   }
 }
 
-// lane 0 of the warp runs the sequential cascade; `sc` is the warp's shared scratch
+__device__ __forceinline__ void stage_views(const c2g_scan_head *heads, const c2g_view *views, int slot, ViewLite *dst, int lane) {
+  for (int i = lane; i < SV_PER_SCAN; i += 32) {
+    const int level = i / C2G_MAX_DIST_FIRSTS + 1, seq = i % C2G_MAX_DIST_FIRSTS;
+    ViewLite v;
+    v.valid = 0;
+    v.mean0 = v.mean1 = v.eig0 = v.eig1 = v.vol3_mean = v.com0 = v.com1 = v.evx = v.evy = 0.f;
+    v.cell_cnt = 0;
+    v.ecc_feat = 0;
+    if (seq < heads[slot].n_views[level]) {
+      const c2g_view &g = views[(size_t) slot * C2G_VIEW_CAP + heads[slot].view_off[level] + seq];
+      v.valid = 1;
+      v.mean0 = g.pos_mean[0];
+      v.mean1 = g.pos_mean[1];
+      v.eig0 = g.eig_vals[0];
+      v.eig1 = g.eig_vals[1];
+      v.vol3_mean = g.vol3_mean;
+      v.com0 = g.com[0];
+      v.com1 = g.com[1];
+      v.evx = g.eig_vecs[2];
+      v.evy = g.eig_vecs[3];
+      v.cell_cnt = g.cell_cnt;
+      v.ecc_feat = g.ecc_feat;
+    }
+    dst[i] = v;
+  }
+}
+__device__ __forceinline__ const ViewLite &lite(const ViewLite *arr, int level, int seq) { return arr[(level - 1) * C2G_MAX_DIST_FIRSTS + seq]; }
+
+// One warp per surviving hint. All lanes stage the two BCIs and the top-10 views of levels 1..4 of both scans into shared
+// memory (coalesced / parallel global reads); the order-dependent parts of the cascade then run on lane 0 out of shared
+// memory only, the per-pair similarity and orientation tests run one pair per lane.
 __device__ void score_hint(const c2g_scan_head *heads, const c2g_view *views, int q_slot, const c2g_hint &hint, const QueryParams &Q,
-                           ScoreScratch &sc, c2g_pair_score &rec) {
+                           ScoreScratch &sc, c2g_pair_score &rec, int lane) {
   const int cand = hint.cand_gidx, level = hint.level, cseq = hint.cand_seq, qseq = hint.q_seq;
-  // (1/4) anchor similarity
-  if (!check_sim(view_at(heads, views, cand, level, cseq), view_at(heads, views, q_slot, level, qseq), Q.sim)) {
-    rec.passed = 0;
-    return;
-  }
-  // (2/4) BCI::checkConstellSim(src = candidate, tgt = query)
-  const c2g_bci &src = heads[cand].bcis[level][cseq];
-  const c2g_bci &tgt = heads[q_slot].bcis[level][qseq];
-  int ov1 = 0, ov2 = 0, ov3 = 0;
   {
-    unsigned long long s4[4], t4[4];
-    for (int i = 0; i < 4; ++i) {
-      s4[i] = src.dist_bin[i];
-      t4[i] = tgt.dist_bin[i];
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(&heads[cand].bcis[level][cseq]);
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(&heads[q_slot].bcis[level][qseq]);
+    uint32_t *ds = reinterpret_cast<uint32_t *>(&sc.bs), *dt = reinterpret_cast<uint32_t *>(&sc.bt);
+    for (int i = lane; i < (int) (sizeof(c2g_bci) / 4); i += 32) {
+      ds[i] = s32[i];
+      dt[i] = t32[i];
     }
+    stage_views(heads, views, cand, sc.vs, lane);
+    stage_views(heads, views, q_slot, sc.vt, lane);
+  }
+  __syncwarp();
+  const c2g_bci &src = sc.bs;
+  const c2g_bci &tgt = sc.bt;
+  int state = 1;  // 1 = continue, <= 0 = final `passed` code
+  int npot = 0, n1 = 0;
+  if (lane == 0) {
+    // (1/4) anchor similarity and (2/4) popcount gate were evaluated by the prefilter; recompute the counts for the record
+    int ov1 = 0, ov2 = 0, ov3 = 0;
     for (int i = 0; i < 4; ++i) {
-      const unsigned long long sl = (s4[i] << 1) | (i > 0 ? (s4[i - 1] >> 63) : 0ull);
-      const unsigned long long sr = (s4[i] >> 1) | (i < 3 ? (s4[i + 1] << 63) : 0ull);
-      ov1 += __popcll(s4[i] & t4[i]);
-      ov2 += __popcll(sl & t4[i]);
-      ov3 += __popcll(sr & t4[i]);
+      const unsigned long long s_i = src.dist_bin[i], t_i = tgt.dist_bin[i];
+      const unsigned long long sl = (s_i << 1) | (i > 0 ? (src.dist_bin[i - 1] >> 63) : 0ull);
+      const unsigned long long sr = (s_i >> 1) | (i < 3 ? (src.dist_bin[i + 1] << 63) : 0ull);
+      ov1 += __popcll(s_i & t_i);
+      ov2 += __popcll(sl & t_i);
+      ov3 += __popcll(sr & t_i);
     }
-  }
-  rec.constell[0] = ov1 + ov2 + ov3;
-  rec.constell[1] = max(ov1, max(ov2, ov3));
-  rec.constell[2] = 0;
-  if (!(rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one)) {
-    rec.passed = -1;
-    return;
-  }
-  int npot = 0;
-  {
-    const int n_sseg = src.n_seg, n_tseg = tgt.n_seg;
-    int p11 = 0, p12;
-    for (int p2 = 0; p2 < n_tseg - 1; p2++) {
-      const int tb = tgt.nei[tgt.seg[p2]].bit_pos;
-      while (p11 < n_sseg - 1 && src.nei[src.seg[p11]].bit_pos < tb - 1) p11++;
-      p12 = p11;
-      while (p12 < n_sseg - 1 && src.nei[src.seg[p12]].bit_pos <= tb + 1) p12++;
-      for (int i = tgt.seg[p2]; i < tgt.seg[p2 + 1]; i++)
-        for (int j = src.seg[p11]; j < src.seg[p12]; j++) {
-          if (npot < MAX_POT_PAIRS) {
-            PotPair pp;
-            pp.orie_diff = clamp_ang_f(tgt.nei[i].theta - src.nei[j].theta);
-            pp.seq_src = src.nei[j].seq;
-            pp.seq_tgt = tgt.nei[i].seq;
-            pp.level = src.nei[j].level;
-            pp.pad = 0;
-            sc.pot[npot] = pp;
-            sc.ord[npot] = (uint32_t) npot;
-            ++npot;
+    rec.constell[0] = ov1 + ov2 + ov3;
+    rec.constell[1] = max(ov1, max(ov2, ov3));
+    rec.constell[2] = 0;
+    if (!check_sim_lite(lite(sc.vs, level, cseq), lite(sc.vt, level, qseq), Q.sim)) {
+      state = 0;  // cannot happen for prefilter survivors; keep the record of an anchor failure all-zero
+      rec.constell[0] = rec.constell[1] = 0;
+    }
+    else if (!(rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one))
+      state = -1;
+    if (state == 1) {
+      const int n_sseg = src.n_seg, n_tseg = tgt.n_seg;
+      int p11 = 0, p12;
+      for (int p2 = 0; p2 < n_tseg - 1; p2++) {
+        const int tb = tgt.nei[tgt.seg[p2]].bit_pos;
+        while (p11 < n_sseg - 1 && src.nei[src.seg[p11]].bit_pos < tb - 1) p11++;
+        p12 = p11;
+        while (p12 < n_sseg - 1 && src.nei[src.seg[p12]].bit_pos <= tb + 1) p12++;
+        for (int i = tgt.seg[p2]; i < tgt.seg[p2 + 1]; i++)
+          for (int j = src.seg[p11]; j < src.seg[p12]; j++) {
+            if (npot < MAX_POT_PAIRS) {
+              PotPair pp;
+              pp.orie_diff = clamp_ang_f(tgt.nei[i].theta - src.nei[j].theta);
+              pp.seq_src = src.nei[j].seq;
+              pp.seq_tgt = tgt.nei[i].seq;
+              pp.level = src.nei[j].level;
+              pp.pad = 0;
+              sc.pot[npot] = pp;
+              sc.ord[npot] = (uint32_t) npot;
+              ++npot;
+            }
           }
+      }
+      // std::sort by orie_diff (contour_mng.h:340-342): sort the index permutation with the same comparator
+      const PotPair *pot = sc.pot;
+      c2g_sort::std_sort(sc.ord, (long) npot, [pot](uint32_t a, uint32_t b) { return pot[a].orie_diff < pot[b].orie_diff; });
+      int longest = 1, longest_beg = 0;
+      const float angular_range = (float) (C2G_PI / 16);
+      int p1 = 0, p2 = 0;
+      const int pot_sz = npot;
+      while (p1 < pot_sz) {
+        const float dd = sc.pot[sc.ord[p2 % pot_sz]].orie_diff - sc.pot[sc.ord[p1]].orie_diff;
+        if ((double) dd + 2 * C2G_PI * (double) (p2 / pot_sz) > (double) angular_range)
+          p1++;
+        else {
+          if (p2 - p1 + 1 > longest) {
+            longest = p2 - p1 + 1;
+            longest_beg = p1;
+          }
+          p2++;
         }
-    }
-  }
-  // std::sort by orie_diff (contour_mng.h:340-342): sort the index permutation with the same comparator
-  {
-    const PotPair *pot = sc.pot;
-    c2g_sort::std_sort(sc.ord, (long) npot, [pot](uint32_t a, uint32_t b) { return pot[a].orie_diff < pot[b].orie_diff; });
-  }
-  int longest = 1, longest_beg = 0;
-  {
-    const float angular_range = (float) (C2G_PI / 16);
-    int p1 = 0, p2 = 0;
-    const int pot_sz = npot;
-    while (p1 < pot_sz) {
-      const float dd = sc.pot[sc.ord[p2 % pot_sz]].orie_diff - sc.pot[sc.ord[p1]].orie_diff;
-      if ((double) dd + 2 * C2G_PI * (double) (p2 / pot_sz) > (double) angular_range)
-        p1++;
+      }
+      rec.constell[2] = longest;
+      if (longest < Q.lb.i_in_ang_rng)
+        state = -1;
       else {
-        if (p2 - p1 + 1 > longest) {
-          longest = p2 - p1 + 1;
-          longest_beg = p1;
+        for (int i = longest_beg; i < longest + longest_beg; i++) {
+          const PotPair &pp = sc.pot[sc.ord[i % npot]];
+          sc.c1[n1].level = pp.level;
+          sc.c1[n1].seq_src = pp.seq_src;
+          sc.c1[n1].seq_tgt = pp.seq_tgt;
+          ++n1;
         }
-        p2++;
+        sc.c1[n1].level = src.level;
+        sc.c1[n1].seq_src = src.piv_seq;
+        sc.c1[n1].seq_tgt = tgt.piv_seq;
+        ++n1;
       }
     }
   }
-  rec.constell[2] = longest;
-  if (longest < Q.lb.i_in_ang_rng) {
-    rec.passed = -1;
+  state = __shfl_sync(0xFFFFFFFFu, state, 0);
+  if (state != 1) {
+    if (lane == 0) rec.passed = state;
     return;
   }
-  int n1 = 0;
-  for (int i = longest_beg; i < longest + longest_beg; i++) {
-    const PotPair &pp = sc.pot[sc.ord[i % npot]];
-    sc.c1[n1].level = pp.level;
-    sc.c1[n1].seq_src = pp.seq_src;
-    sc.c1[n1].seq_tgt = pp.seq_tgt;
-    ++n1;
-  }
-  sc.c1[n1].level = src.level;
-  sc.c1[n1].seq_src = src.piv_seq;
-  sc.c1[n1].seq_tgt = tgt.piv_seq;
-  ++n1;
-  // (3/4) checkConstellCorrespSim
+  n1 = __shfl_sync(0xFFFFFFFFu, n1, 0);
+  __syncwarp();
+  // (3/4) checkConstellCorrespSim step 1: individual similarity, one pair per lane, order-preserving compaction
   int n2 = 0;
-  for (int i = 0; i < n1; ++i) {
-    const CPairD pr = sc.c1[i];
-    if (check_sim(view_at(heads, views, cand, pr.level, pr.seq_src), view_at(heads, views, q_slot, pr.level, pr.seq_tgt), Q.sim))
-      sc.c2[n2++] = pr;
+  for (int base = 0; base < n1; base += 32) {
+    const int i = base + lane;
+    bool ok = false;
+    CPairD pr;
+    pr.level = pr.seq_src = pr.seq_tgt = 0;
+    if (i < n1) {
+      pr = sc.c1[i];
+      ok = check_sim_lite(lite(sc.vs, pr.level, pr.seq_src), lite(sc.vt, pr.level, pr.seq_tgt), Q.sim);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+    if (ok) sc.c2[n2 + __popc(m & ((1u << lane) - 1u))] = pr;
+    n2 += __popc(m);
   }
-  rec.pairwise[0] = n2;
-  rec.pairwise[1] = 0;
+  __syncwarp();
+  if (lane == 0) {
+    rec.pairwise[0] = n2;
+    rec.pairwise[1] = 0;
+  }
   if (n2 < Q.lb.i_indiv_sim) {
-    rec.passed = -2;
+    if (lane == 0) rec.passed = -2;
     return;
   }
+  // step 2.1: the "shaft" (the last qualifying (i, j) among the first <= 10 pairs wins, see SURVEY.md §8a' #6)
   float ssx = 0.f, ssy = 0.f, stx = 0.f, sty = 0.f;
-  for (int i = 1; i < min(n2, 10); i++)
-    for (int j = 0; j < i; j++) {
-      const float *mi = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
-      const float *mj = view_at(heads, views, cand, sc.c2[j].level, sc.c2[j].seq_src).pos_mean;
-      const float cx = mi[0] - mj[0], cy = mi[1] - mj[1];
-      if (sqrtf(cx * cx + cy * cy) > sqrtf(ssx * ssx + ssy * ssy)) {
-        normalized2(cx, cy, ssx, ssy);
-        const float *ti = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
-        const float *tj = view_at(heads, views, q_slot, sc.c2[j].level, sc.c2[j].seq_tgt).pos_mean;
-        normalized2(ti[0] - tj[0], ti[1] - tj[1], stx, sty);
+  if (lane == 0) {
+    for (int i = 1; i < min(n2, 10); i++)
+      for (int j = 0; j < i; j++) {
+        const ViewLite &mi = lite(sc.vs, sc.c2[i].level, sc.c2[i].seq_src), &mj = lite(sc.vs, sc.c2[j].level, sc.c2[j].seq_src);
+        const float cx = mi.mean0 - mj.mean0, cy = mi.mean1 - mj.mean1;
+        if (sqrtf(cx * cx + cy * cy) > sqrtf(ssx * ssx + ssy * ssy)) {
+          normalized2(cx, cy, ssx, ssy);
+          const ViewLite &ti = lite(sc.vt, sc.c2[i].level, sc.c2[i].seq_tgt), &tj = lite(sc.vt, sc.c2[j].level, sc.c2[j].seq_tgt);
+          normalized2(ti.mean0 - tj.mean0, ti.mean1 - tj.mean1, stx, sty);
+        }
       }
-    }
-  int num_sim = n2;
-  for (int i = 0; i < num_sim;) {
-    const c2g_view &sc1 = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src);
-    const c2g_view &tc1 = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt);
+  }
+  ssx = __shfl_sync(0xFFFFFFFFu, ssx, 0);
+  ssy = __shfl_sync(0xFFFFFFFFu, ssy, 0);
+  stx = __shfl_sync(0xFFFFFFFFu, stx, 0);
+  sty = __shfl_sync(0xFFFFFFFFu, sty, 0);
+  // step 2.2: orientation verdict per pair (depends on the pair and the fixed shaft only), one pair per lane
+  for (int i = lane; i < n2; i += 32) {
+    const ViewLite &sc1 = lite(sc.vs, sc.c2[i].level, sc.c2[i].seq_src), &tc1 = lite(sc.vt, sc.c2[i].level, sc.c2[i].seq_tgt);
+    uint8_t d = 0;
     if (sc1.ecc_feat && tc1.ecc_feat) {
-      const float theta_s = c2g_acosf(ssx * sc1.eig_vecs[2] + ssy * sc1.eig_vecs[3]);
-      const float theta_t = c2g_acosf(stx * tc1.eig_vecs[2] + sty * tc1.eig_vecs[3]);
+      const float theta_s = c2g_acosf(ssx * sc1.evx + ssy * sc1.evy);
+      const float theta_t = c2g_acosf(stx * tc1.evx + sty * tc1.evy);
       const float pi6 = (float) (C2G_PI / 6);
-      if (diff_delt_f(theta_s, theta_t, pi6) && diff_delt_f((float) (C2G_PI - (double) theta_s), theta_t, pi6)) {
+      d = (diff_delt_f(theta_s, theta_t, pi6) && diff_delt_f((float) (C2G_PI - (double) theta_s), theta_t, pi6)) ? 1 : 0;
+    }
+    sc.drop[i] = d;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // the reference's swap-with-last removal loop (contour_mng.h:1187-1201), verdicts travel with their entries
+    int num_sim = n2;
+    for (int i = 0; i < num_sim;) {
+      if (sc.drop[i]) {
         const CPairD tmp = sc.c2[i];
         sc.c2[i] = sc.c2[num_sim - 1];
         sc.c2[num_sim - 1] = tmp;
+        const uint8_t td = sc.drop[i];
+        sc.drop[i] = sc.drop[num_sim - 1];
+        sc.drop[num_sim - 1] = td;
         num_sim--;
         continue;
       }
+      i++;
     }
-    i++;
-  }
-  n2 = num_sim;
-  rec.pairwise[1] = n2;
-  if (n2 < Q.lb.i_orie_sim) {
-    rec.passed = -2;
-    return;
-  }
-  // getTFFromConstell: 2-D Umeyama without scaling, closed form (double)
-  {
-    const double inv_n = 1.0 / (double) n2;
-    double sm0 = 0, sm1 = 0, dm0 = 0, dm1 = 0;
-    for (int i = 0; i < n2; ++i) {
-      const float *ps = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
-      const float *pt = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
-      sm0 += (double) ps[0];
-      sm1 += (double) ps[1];
-      dm0 += (double) pt[0];
-      dm1 += (double) pt[1];
+    n2 = num_sim;
+    rec.pairwise[1] = n2;
+    if (n2 < Q.lb.i_orie_sim) {
+      rec.passed = -2;
+    } else {
+      // getTFFromConstell: 2-D Umeyama without scaling, closed form (double), sums in list order
+      const double inv_n = 1.0 / (double) n2;
+      double sm0 = 0, sm1 = 0, dm0 = 0, dm1 = 0;
+      for (int i = 0; i < n2; ++i) {
+        const ViewLite &ps = lite(sc.vs, sc.c2[i].level, sc.c2[i].seq_src), &pt = lite(sc.vt, sc.c2[i].level, sc.c2[i].seq_tgt);
+        sm0 += (double) ps.mean0;
+        sm1 += (double) ps.mean1;
+        dm0 += (double) pt.mean0;
+        dm1 += (double) pt.mean1;
+      }
+      sm0 *= inv_n;
+      sm1 *= inv_n;
+      dm0 *= inv_n;
+      dm1 *= inv_n;
+      double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+      for (int i = 0; i < n2; ++i) {
+        const ViewLite &ps = lite(sc.vs, sc.c2[i].level, sc.c2[i].seq_src), &pt = lite(sc.vt, sc.c2[i].level, sc.c2[i].seq_tgt);
+        const double sx = (double) ps.mean0 - sm0, sy = (double) ps.mean1 - sm1;
+        const double dx = (double) pt.mean0 - dm0, dy = (double) pt.mean1 - dm1;
+        s00 += dx * sx;
+        s01 += dx * sy;
+        s10 += dy * sx;
+        s11 += dy * sy;
+      }
+      s00 *= inv_n;
+      s01 *= inv_n;
+      s10 *= inv_n;
+      s11 *= inv_n;
+      const double ang0 = atan2(s10 - s01, s00 + s11);
+      const double c0 = cos(ang0), s0 = sin(ang0);
+      const double tx = dm0 - (c0 * sm0 - s0 * sm1);
+      const double ty = dm1 - (s0 * sm0 + c0 * sm1);
+      const double ang = atan2(s0, c0);
+      rec.T[0] = cos(ang);
+      rec.T[1] = sin(ang);
+      rec.T[2] = tx;
+      rec.T[3] = ty;
+      rec.passed = 1;
+      rec.n_pairs = n2;
+      for (int i = 0; i < n2; ++i) {
+        const int bit = (sc.c2[i].level - 1) * 100 + sc.c2[i].seq_src * 10 + sc.c2[i].seq_tgt;
+        rec.pair_bits[bit >> 6] |= 1ull << (bit & 63);
+      }
     }
-    sm0 *= inv_n;
-    sm1 *= inv_n;
-    dm0 *= inv_n;
-    dm1 *= inv_n;
-    double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-    for (int i = 0; i < n2; ++i) {
-      const float *ps = view_at(heads, views, cand, sc.c2[i].level, sc.c2[i].seq_src).pos_mean;
-      const float *pt = view_at(heads, views, q_slot, sc.c2[i].level, sc.c2[i].seq_tgt).pos_mean;
-      const double sx = (double) ps[0] - sm0, sy = (double) ps[1] - sm1;
-      const double dx = (double) pt[0] - dm0, dy = (double) pt[1] - dm1;
-      s00 += dx * sx;
-      s01 += dx * sy;
-      s10 += dy * sx;
-      s11 += dy * sy;
-    }
-    s00 *= inv_n;
-    s01 *= inv_n;
-    s10 *= inv_n;
-    s11 *= inv_n;
-    const double ang0 = atan2(s10 - s01, s00 + s11);
-    const double c0 = cos(ang0), s0 = sin(ang0);
-    const double tx = dm0 - (c0 * sm0 - s0 * sm1);
-    const double ty = dm1 - (s0 * sm0 + c0 * sm1);
-    const double ang = atan2(s0, c0);
-    rec.T[0] = cos(ang);
-    rec.T[1] = sin(ang);
-    rec.T[2] = tx;
-    rec.T[3] = ty;
-  }
-  rec.passed = 1;
-  rec.n_pairs = n2;
-  for (int i = 0; i < n2; ++i) {
-    const int bit = (sc.c2[i].level - 1) * 100 + sc.c2[i].seq_src * 10 + sc.c2[i].seq_tgt;
-    rec.pair_bits[bit >> 6] |= 1ull << (bit & 63);
   }
 }
 
@@ -487,30 +633,29 @@ prefilter_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__rest
   }
 }
 
-// Stage 2, one WARP per surviving hint (lane 0 runs the sequential cascade on the warp's shared scratch), grid-stride.
+// Stage 2, one WARP per surviving hint, grid-stride over the survivor list.
 __global__ void __launch_bounds__(SC_WARPS * 32)
 score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, QueryParams Q,
              const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores, const int *__restrict__ survivors,
              const int *__restrict__ n_surv) {
-  __shared__ ScoreScratch scratch[SC_WARPS];
+  extern __shared__ __align__(16) unsigned char sc_raw[];
+  ScoreScratch *scratch = reinterpret_cast<ScoreScratch *>(sc_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = *n_surv;
   for (int i = blockIdx.x * SC_WARPS + w; i < n; i += gridDim.x * SC_WARPS) {
-    if (lane == 0) {
-      const int hid = survivors[i];
-      const c2g_hint h = hints[hid];
-      c2g_pair_score rec;
-      rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
-      rec.pairwise[0] = rec.pairwise[1] = 0;
-      rec.passed = 0;
-      rec.n_pairs = 0;
-      rec.pad_ = 0;
-      rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
-      for (int k = 0; k < C2G_PAIR_WORDS; ++k) rec.pair_bits[k] = 0ull;
-      rec.pad2_ = 0ull;
-      score_hint(heads, views, first_slot + h.q_idx, h, Q, scratch[w], rec);
-      scores[hid] = rec;
-    }
+    const int hid = survivors[i];
+    const c2g_hint h = hints[hid];
+    c2g_pair_score rec;
+    rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
+    rec.pairwise[0] = rec.pairwise[1] = 0;
+    rec.passed = 0;
+    rec.n_pairs = 0;
+    rec.pad_ = 0;
+    rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
+    for (int k = 0; k < C2G_PAIR_WORDS; ++k) rec.pair_bits[k] = 0ull;
+    rec.pad2_ = 0ull;
+    score_hint(heads, views, first_slot + h.q_idx, h, Q, scratch[w], rec, lane);
+    if (lane == 0) scores[hid] = rec;
     __syncwarp();
   }
 }
@@ -873,6 +1018,7 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
     Q.layer[i].keys_t = t.keys_t;
     Q.layer[i].gidx = t.gidx;
     Q.layer[i].seq = t.seq;
+    Q.layer[i].orank = t.orank;
     Q.layer[i].cap = t.cap;
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
       Q.layer[i].bucket_off[k] = t.bucket_off[k];
@@ -918,6 +1064,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     C2G_CUDA_TRY(cudaMalloc((void **) &t.keys_t, sizeof(float) * C2G_KEY_DIM * (size_t) t.cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * (size_t) t.cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, (size_t) t.cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.orank, sizeof(int) * (size_t) t.cap));
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
       t.bucket_off[k] = 0;
       t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
@@ -936,6 +1083,7 @@ void c2g_query_free(c2g_ctx *ctx) {
     cudaFree(ctx->layers[i].keys_t);
     cudaFree(ctx->layers[i].gidx);
     cudaFree(ctx->layers[i].seq);
+    cudaFree(ctx->layers[i].orank);
   }
 }
 
@@ -969,23 +1117,47 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
     free(sq);
     return C2G_ERR_CAPACITY;
   }
-  int pos[C2G_NUM_BUCKETS];
-  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) pos[k] = cnt[k];
-  for (int i = 0; i < n; ++i) {
-    const int p = pos[bucket_host[i]]++;
+  // bucket-major positions in tree order first (the tie-break rank), then a stable sort by key[0] inside every bucket
+  std::vector<int> perm((size_t) n), rank_of((size_t) n);
+  {
+    int pos[C2G_NUM_BUCKETS];
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) pos[k] = cnt[k];
+    for (int i = 0; i < n; ++i) {
+      const int p = pos[bucket_host[i]]++;
+      perm[p] = i;  // flat tree-order position p holds input key i
+    }
+    std::vector<int> order((size_t) n);
+    for (int p = 0; p < n; ++p) order[p] = p;
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k)
+      std::stable_sort(order.begin() + cnt[k], order.begin() + cnt[k + 1],
+                       [&](int a, int b) { return keys_host[(size_t) perm[a] * C2G_KEY_DIM] < keys_host[(size_t) perm[b] * C2G_KEY_DIM]; });
+    for (int p = 0; p < n; ++p) rank_of[p] = order[p];  // sorted position p holds flat tree-order position order[p]
+  }
+  int *ork = (int *) malloc(sizeof(int) * (size_t) n);
+  if (!ork) {
+    free(kt);
+    free(gi);
+    free(sq);
+    return C2G_ERR_CAPACITY;
+  }
+  for (int p = 0; p < n; ++p) {
+    const int flat = rank_of[p], i = perm[flat];
     for (int d = 0; d < C2G_KEY_DIM; ++d) kt[(size_t) d * n + p] = keys_host[(size_t) i * C2G_KEY_DIM + d];
     gi[p] = gidx_host[i];
     sq[p] = seq_host[i];
+    ork[p] = flat;
   }
   cudaError_t e = cudaSuccess;
   for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d)
     e = cudaMemcpyAsync(t.keys_t + (size_t) d * t.cap, kt + (size_t) d * n, sizeof(float) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(t.gidx, gi, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(t.seq, sq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(t.orank, ork, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   free(kt);
   free(gi);
   free(sq);
+  free(ork);
   return e == cudaSuccess ? 0 : -(int) e;
 }
 
@@ -1013,8 +1185,14 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   {
     const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
     const long long cap = (long long) ctx->num_sms * 16;
-    score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints,
-                                                                                       ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
+    static bool sc_attr = false;
+    const size_t sc_smem = sizeof(ScoreScratch) * SC_WARPS;
+    if (!sc_attr) {
+      C2G_CUDA_TRY(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem));
+      sc_attr = true;
+    }
+    score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, sc_smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints,
+                                                                                             ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
   }
   C2G_CUDA_TRY(cudaGetLastError());
   ctx->launches += 3;
