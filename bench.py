@@ -34,6 +34,11 @@ N_PTS = 120000
 VISITS = 4
 
 
+# DRAM traffic per 120k-point scan measured by `ncu --set full` (profiles/r1_ncu_full_summary.csv, one 296-scan launch each):
+# (dram__bytes_read.sum + dram__bytes_write.sum) / 296.  Algorithmic bytes are 1.92 MB (K1) and 1.98 MB (K1+K2) per scan.
+NCU_DRAM_BYTES_PER_SCAN = {"bev_scatter_kernel": (568.490752e6 + 7.416064e6) / 296, "contour_kernel": (375.015424e6 + 92.196096e6) / 296}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,12 +280,16 @@ def run_b200(args):
                        "db_scans": n_db, "queries_per_rank_per_step": Q, "points_per_scan": n_pts,
                        "parallelism": f"query batches sharded over {world} rank(s), DB replicated, 1 NCCL all-gather of pair scores",
                        "l2": "inputs larger than L2 (each step streams %.2f GB of points)" % (Q * n_pts * 16 / 1e9),
-                       "refine": "Ceres L-BFGS refinement not included (SURVEY.md §8f)"},
+                       "refine": "fineOptimize's L-BFGS refinement of <=10 candidates per query included (refine.cu)"},
             "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": int(Q * n_pts * 16 + (Q + 1) * 8),
                     "d2h_bytes_per_step": int(res_host.nbytes), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": Q * (NCU_DRAM_BYTES_PER_SCAN["bev_scatter_kernel"] + NCU_DRAM_BYTES_PER_SCAN["contour_kernel"])
+                         if n_pts == 120000 else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per scan from the ncu --set full capture in "
+                                           "profiles/r1_ncu_full_summary.csv (296-scan launch), scaled to this launch's scan count",
                          "kernel": "bev_scatter_kernel + contour_kernel (ingest pair, 1.98 MB algorithmic bytes per scan)",
                          "peak_source": peak_src,
                          "bev_scatter_only": {"achieved": ach_bev, "frac": ach_bev / peak, "ms": kern["bev_scatter_ms"]},

@@ -17,10 +17,12 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
                            c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream);
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, uint16_t *cell_lists,
-                        int num_sms, cudaStream_t stream, long long *dbg);
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
+                        uint16_t *cell_lists, int num_sms, cudaStream_t stream, long long *dbg);
 int c2g_query_alloc(c2g_ctx *ctx);
 void c2g_query_free(c2g_ctx *ctx);
+int c2g_refine_alloc(c2g_ctx *ctx);  // refine.cu
+void c2g_refine_free(c2g_ctx *ctx);
 
 namespace {
 
@@ -181,10 +183,12 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) ctx->num_sms);
   ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
+  ALLOC(ctx->d_ells, sizeof(c2g_ell) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_dbg, sizeof(long long) * 64);
   ALLOC(ctx->d_cell_lists, sizeof(uint16_t) * C2G_NLEV * ncell * (size_t) ctx->num_sms);
 #undef ALLOC
   rc = c2g_query_alloc(ctx);
+  if (!rc) rc = c2g_refine_alloc(ctx);
   if (rc) {
     c2g_destroy(ctx);
     return rc;
@@ -205,6 +209,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   c2g_query_free(ctx);
+  c2g_refine_free(ctx);
   delete ctx->hostdb;
   cudaFree(ctx->d_pts_stage2[0]);
   cudaFree(ctx->d_pts_stage2[1]);
@@ -222,6 +227,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_presort);
   cudaFree(ctx->d_heads);
   cudaFree(ctx->d_views);
+  cudaFree(ctx->d_ells);
   cudaFree(ctx->d_dbg);
   cudaFree(ctx->d_cell_lists);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -281,7 +287,7 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     if (rc) return rc;
     rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0,
                              ctx->d_bev_h + ncell * b0, ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads,
-                             ctx->d_views, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                             ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
   }
@@ -303,7 +309,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
   int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
   if (rc) return rc;
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -347,6 +353,8 @@ int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n) {
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_heads + dst_first, ctx->d_heads + src_first, sizeof(c2g_scan_head) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_views + (size_t) dst_first * C2G_VIEW_CAP, ctx->d_views + (size_t) src_first * C2G_VIEW_CAP,
                                sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_ells + (size_t) dst_first * C2G_VIEW_CAP, ctx->d_ells + (size_t) src_first * C2G_VIEW_CAP,
+                               sizeof(c2g_ell) * C2G_VIEW_CAP * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 

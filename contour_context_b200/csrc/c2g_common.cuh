@@ -57,3 +57,10 @@ __host__ __device__ __forceinline__ float c2g_from_orderable(uint32_t o) {
 // A max over these keys implements "highest point wins, the earliest point in file order wins ties"
 // (strict `<` in include/cont2/contour_mng.h:517).
 typedef unsigned long long c2g_cellkey;
+
+// Compact GMM ellipse of one contour view (GMMPair::GMMEllipse, include/cont2/correlation.h:24-33): one 32-byte sector per
+// view, written next to the view by the contour kernel, read by the GMM-L2 kernels instead of the 80-byte view record.
+// cov = ContourView::getManualCov() (float, column-major), w = cell_cnt, maj = sqrtf(eig_vals[1]) (correlation.h:64,72).
+struct __align__(32) c2g_ell {
+  float mx, my, c00, c10, c01, c11, w, maj;
+};

@@ -4,12 +4,18 @@
 
 #define C2G_MAX_CHUNK_EVENTS 64
 
+struct C2gKdCache;  // host-side memo of the kd ordering of every bucket (query.cu)
+
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
   float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans, bucket-major, tree order inside a bucket
   int *gidx;             // IndexOfKey::gidx
   signed char *seq;      // IndexOfKey::seq
-  int *orank;            // flat tree-order index of every entry (tie-break rank; the mirror itself is sorted by key[0] inside a bucket)
-  int n, cap;
+  int *orank;            // flat tree-order index of every entry (tie-break rank; the mirror itself is kd-ordered inside a bucket)
+  float *box_min, *box_max;  // [C2G_KEY_DIM][blk_cap]: bounding box of every 32-key block (block j of bucket k = keys
+                             // [bucket_off[k] + 32 j, +32) clipped to the bucket), blocks numbered bucket-major
+  C2gKdCache *kd_cache;
+  int n, cap, blk_cap;
+  int blk_off[C2G_NUM_BUCKETS + 1];
   int bucket_off[C2G_NUM_BUCKETS + 1];
   float ranges[C2G_NUM_BUCKETS + 1];
 };
@@ -36,6 +42,7 @@ struct c2g_ctx {
   c2g_view *d_presort;
   c2g_scan_head *d_heads;
   c2g_view *d_views;
+  c2g_ell *d_ells;           // [scan_cap][C2G_VIEW_CAP], same indexing as d_views
   long long *d_dbg;
   uint16_t *d_cell_lists;  // per resident CTA: member cells of every component, level by level
   const float *last_pts;
@@ -47,6 +54,8 @@ struct c2g_ctx {
   c2g_pair_score *d_scores;
   c2g_query_result *d_results;
   int *d_survivors, *d_nsurv;  // hint slots that pass the thread-per-hint prefilter, and their count
+  uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
+  int pair_cap;
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state

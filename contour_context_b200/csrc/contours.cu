@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
                int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
-               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, uint16_t *__restrict__ cell_lists,
-               long long *__restrict__ dbg) {
+               c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
+               uint16_t *__restrict__ cell_lists, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -283,6 +283,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     const float *hg = bev_h + cbase, *rfg = bev_rf + cbase, *cfp = bev_cf + cbase;
     c2g_scan_head *head = heads + (first_slot + b);
     c2g_view *vout = views + (size_t) (first_slot + b) * C2G_VIEW_CAP;
+    c2g_ell *eout = ells + (size_t) (first_slot + b) * C2G_VIEW_CAP;
 
 #define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0) dbg[i] = clock64(); } while (0)
     C2G_DBG(0);
@@ -755,6 +756,28 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           dst[(size_t) (off + j) * WPV + wd] = src[(size_t) from * WPV + wd];
         }
       }
+      // compact GMM ellipse next to every view of the levels the GMM-L2 stages use (1..4)
+      {
+        const int e0 = S.view_off[1], e1 = S.view_off[C2G_NUM_BIN_LAYERS] + S.n_views[C2G_NUM_BIN_LAYERS];
+        for (int v = e0 + tid; v < e1; v += K2_THREADS) {
+          int lev = 1;
+          for (int l = 2; l <= C2G_NUM_BIN_LAYERS; ++l)
+            if (v >= S.view_off[l]) lev = l;
+          const c2g_view &pv = presort[S.view_off[lev] + (int) (S.sortbuf[v] & 0xFFFFu)];
+          float cv[4];
+          manual_cov(pv.eig_vals, pv.eig_vecs, cv);
+          c2g_ell e;
+          e.mx = pv.pos_mean[0];
+          e.my = pv.pos_mean[1];
+          e.c00 = cv[0];
+          e.c10 = cv[1];
+          e.c01 = cv[2];
+          e.c11 = cv[3];
+          e.w = (float) pv.cell_cnt;
+          e.maj = sqrtf(pv.eig_vals[1]);
+          eout[v] = e;
+        }
+      }
       for (int i = tid; i < C2G_NLEV * C2G_MAX_DIST_FIRSTS; i += K2_THREADS) {
         const int lev = i / C2G_MAX_DIST_FIRSTS, j = i % C2G_MAX_DIST_FIRSTS;
         TopView t;
@@ -981,20 +1004,17 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     double acc = 0.0;
     for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
       const int n = n_ell_s[li];
-      const c2g_view *lv = vout + S.view_off[li + 1];
+      const c2g_ell *le = eout + S.view_off[li + 1];
       for (int w = tid; w < n * n; w += K2_THREADS) {
         const int i = w / n, j = w - i * n;
-        const c2g_view &A = lv[i], &Bv = lv[j];
-        float ca[4], cb[4];
-        manual_cov(A.eig_vals, A.eig_vecs, ca);
-        manual_cov(Bv.eig_vals, Bv.eig_vecs, cb);
-        const double c00 = 2.0 * ((double) ca[0] + (double) cb[0]), c10 = 2.0 * ((double) ca[1] + (double) cb[1]);
-        const double c01 = 2.0 * ((double) ca[2] + (double) cb[2]), c11 = 2.0 * ((double) ca[3] + (double) cb[3]);
-        const double mx = (double) A.pos_mean[0] - (double) Bv.pos_mean[0], my = (double) A.pos_mean[1] - (double) Bv.pos_mean[1];
+        const c2g_ell A = le[i], Bv = le[j];
+        const double c00 = 2.0 * ((double) A.c00 + (double) Bv.c00), c10 = 2.0 * ((double) A.c10 + (double) Bv.c10);
+        const double c01 = 2.0 * ((double) A.c01 + (double) Bv.c01), c11 = 2.0 * ((double) A.c11 + (double) Bv.c11);
+        const double mx = (double) A.mx - (double) Bv.mx, my = (double) A.my - (double) Bv.my;
         const double det = c00 * c11 - c01 * c10;
         const double invdet = 1.0 / det;
         const double qf = mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my);
-        acc += (double) A.cell_cnt * (double) Bv.cell_cnt / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
+        acc += (double) A.w * (double) Bv.w / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
       }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
@@ -1028,8 +1048,8 @@ size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, uint16_t *cell_lists,
-                        int num_sms, cudaStream_t stream, long long *dbg) {
+                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
+                        uint16_t *cell_lists, int num_sms, cudaStream_t stream, long long *dbg) {
   static bool attr_set = false;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -1038,7 +1058,7 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, cell_lists, dbg);
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, cell_lists, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -33,9 +33,11 @@ struct LayerDev {
   const float *keys_t;  // [KEY_DIM][cap]
   const int *gidx;
   const signed char *seq;
-  const int *orank;     // flat index in bucket-major TREE order (what the entry's position would be without the key[0] sort)
-  int cap;
-  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1]), sorted by key[0]
+  const int *orank;     // flat index in bucket-major TREE order (what the entry's position would be without the kd ordering)
+  const float *box_min, *box_max;  // [KEY_DIM][blk_cap] bounding boxes of the 32-key blocks
+  int cap, blk_cap;
+  int blk_off[C2G_NUM_BUCKETS + 1];
+  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1]), kd-ordered in blocks of 32
   float ranges[C2G_NUM_BUCKETS + 1];
 };
 struct QueryParams {
@@ -106,118 +108,127 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, Query
         visit |= 1u << (mid + i);
     }
     // Admission key = (distance, original flat index) in lexicographic order; initial worst = (dist_ub, -1): strict
-    // `dist < worst` (nanoflann.hpp:1575), NaN dist_ub admits nothing. Inside a bucket the mirror is sorted by key[0]
-    // (c2g_db_set_layer), so the scan starts at the query's key[0] and walks outwards in both directions; a side stops
-    // as soon as (q0 - k0)^2 alone reaches the current K-th distance (every other term of the metric is >= 0).
+    // `dist < worst` (nanoflann.hpp:1575), NaN dist_ub admits nothing.  Inside a bucket the mirror is cut into kd-ordered
+    // blocks of 32 keys with a 10-D bounding box each (c2g_db_set_layer).  The box distance is accumulated in the same
+    // order as the metric, and every term is <= the matching term of any key in the box, so (rounding being monotone)
+    // box_dist <= dist holds for the COMPUTED values too: a block is skipped iff box_dist > current K-th distance.
     float thr = dist_ub;
     int thr_o = -1;
-    const float *k0col = T.keys_t;
+    auto box_dist = [&](int blk) -> float {
+      float g[C2G_KEY_DIM];
+#pragma unroll
+      for (int d = 0; d < C2G_KEY_DIM; ++d) {
+        const float lo = T.box_min[(size_t) d * T.blk_cap + blk], hi = T.box_max[(size_t) d * T.blk_cap + blk];
+        g[d] = fmaxf(fmaxf(lo - key[d], key[d] - hi), 0.0f);
+      }
+      float r = 0.0f;
+      r += ((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3];
+      r += ((g[4] * g[4] + g[5] * g[5]) + g[6] * g[6]) + g[7] * g[7];
+      r += g[8] * g[8];
+      r += g[9] * g[9];
+      return r;
+    };
+    auto scan_block = [&](int base, int end) {
+      const int i = base + lane;
+      const bool in = i < end;
+      float dist = 3.0e38f;
+      int orig = 0x7FFFFFFF;
+      if (in) {
+        float df[C2G_KEY_DIM];
+#pragma unroll
+        for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
+        // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
+        float r = 0.0f;
+        r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
+        r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
+        r += df[8] * df[8];
+        r += df[9] * df[9];
+        dist = r;
+        orig = T.orank[i];
+      }
+      unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
+      while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
+        const int no = __shfl_sync(0xFFFFFFFFu, orig, src);
+        const int ni = base + src;
+        if (!(nd < thr || (nd == thr && no < thr_o))) continue;  // the worst kept entry may have tightened meanwhile
+        // position = number of kept entries that precede (nd, no)
+        const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] < nd || (bd[0] == nd && bo[0] < no));
+        const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] < nd || (bd[1] == nd && bo[1] < no));
+        const int pos = __popc(le0) + __popc(le1);
+        const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
+        const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
+        const int uo0 = __shfl_up_sync(0xFFFFFFFFu, bo[0], 1), uo1 = __shfl_up_sync(0xFFFFFFFFu, bo[1], 1);
+        const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
+        const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31), lasto0 = __shfl_sync(0xFFFFFFFFu, bo[0], 31);
+        const int j0 = lane, j1 = lane + 32;
+        if (j1 > pos) {
+          bd[1] = (lane == 0) ? last0 : up1;
+          bi[1] = (lane == 0) ? lasti0 : ui1;
+          bo[1] = (lane == 0) ? lasto0 : uo1;
+        }
+        if (j0 > pos) {
+          bd[0] = up0;
+          bi[0] = ui0;
+          bo[0] = uo0;
+        }
+        if (j0 == pos) {
+          bd[0] = nd;
+          bi[0] = ni;
+          bo[0] = no;
+        }
+        if (j1 == pos) {
+          bd[1] = nd;
+          bi[1] = ni;
+          bo[1] = no;
+        }
+        if (count < K) ++count;
+        if (count == K) {  // worst kept entry = K-th best
+          const int ks = K - 1;
+          thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
+          thr_o = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bo[0] : bo[1], ks & 31);
+        }
+      }
+    };
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
       if (!((visit >> bk) & 1u)) continue;
       const int beg = T.bucket_off[bk], end = T.bucket_off[bk + 1];
       if (beg >= end) continue;
-      // warp-parallel 32-way search for the first entry with k0 >= q0
-      int lo = beg, hi = end;  // invariant: k0[i] < q0 for i < lo; k0[hi] >= q0 or hi == end
-      while (lo < hi) {
-        const int step = (hi - lo + 31) / 32;
-        const int probe = lo + lane * step;
-        const bool ge = probe < hi ? (k0col[probe] >= key[0]) : true;
-        const int first = __ffs(__ballot_sync(0xFFFFFFFFu, ge)) - 1;
-        if (first < 0) {
-          lo = lo + 31 * step + 1;  // all 32 probes are below q0
-        } else {
-          const int nhi = min(hi, lo + first * step);                     // probe[first] >= q0 (or past the range)
-          const int nlo = first == 0 ? lo : lo + (first - 1) * step + 1;  // probe[first - 1] < q0
-          lo = nlo;
-          hi = nhi;
+      const int b0 = T.blk_off[bk], nb = T.blk_off[bk + 1] - b0;
+      // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
+      float best = 3.0e38f;
+      int best_j = 0x7FFFFFFF;
+      for (int j = lane; j < nb; j += 32) {
+        const float bdist = box_dist(b0 + j);
+        if (bdist < best) {
+          best = bdist;
+          best_j = j;
         }
       }
-      const int center = lo;  // first index with k0 >= q0 (== end if none)
-      int R = center, Lp = center - 1;
-      bool r_live = R < end, l_live = Lp >= beg;
-      while (r_live || l_live) {
-        for (int side = 0; side < 2; ++side) {
-          int base;
-          if (side == 0) {
-            if (!r_live) continue;
-            base = R;
-          } else {
-            if (!l_live) continue;
-            base = Lp - 31;
-          }
-          const int i = base + lane;
-          const bool in = i >= beg && i < end && (side == 0 ? true : i <= Lp);
-          float dist = 3.0e38f, d0sq = 3.0e38f;
-          int orig = 0x7FFFFFFF;
-          if (in) {
-            float df[C2G_KEY_DIM];
-#pragma unroll
-            for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
-            d0sq = df[0] * df[0];
-            // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
-            float r = 0.0f;
-            r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
-            r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
-            r += df[8] * df[8];
-            r += df[9] * df[9];
-            dist = r;
-            orig = T.orank[i];
-          }
-          unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
-          while (cand) {
-            const int src = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
-            const int no = __shfl_sync(0xFFFFFFFFu, orig, src);
-            const int ni = base + src;
-            if (!(nd < thr || (nd == thr && no < thr_o))) continue;  // the worst kept entry may have tightened meanwhile
-            // position = number of kept entries that precede (nd, no)
-            const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] < nd || (bd[0] == nd && bo[0] < no));
-            const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] < nd || (bd[1] == nd && bo[1] < no));
-            const int pos = __popc(le0) + __popc(le1);
-            const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
-            const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
-            const int uo0 = __shfl_up_sync(0xFFFFFFFFu, bo[0], 1), uo1 = __shfl_up_sync(0xFFFFFFFFu, bo[1], 1);
-            const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
-            const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31), lasto0 = __shfl_sync(0xFFFFFFFFu, bo[0], 31);
-            const int j0 = lane, j1 = lane + 32;
-            if (j1 > pos) {
-              bd[1] = (lane == 0) ? last0 : up1;
-              bi[1] = (lane == 0) ? lasti0 : ui1;
-              bo[1] = (lane == 0) ? lasto0 : uo1;
-            }
-            if (j0 > pos) {
-              bd[0] = up0;
-              bi[0] = ui0;
-              bo[0] = uo0;
-            }
-            if (j0 == pos) {
-              bd[0] = nd;
-              bi[0] = ni;
-              bo[0] = no;
-            }
-            if (j1 == pos) {
-              bd[1] = nd;
-              bi[1] = ni;
-              bo[1] = no;
-            }
-            if (count < K) ++count;
-            if (count == K) {  // worst kept entry = K-th best
-              const int ks = K - 1;
-              thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
-              thr_o = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bo[0] : bo[1], ks & 31);
-            }
-          }
-          // advance this side; it dies when exhausted or when its next key is already too far in key[0] alone
-          if (side == 0) {
-            R += 32;
-            const float edge = __shfl_sync(0xFFFFFFFFu, d0sq, 31);  // farthest key of the chunk just scanned
-            r_live = R < end && !(edge >= thr);
-          } else {
-            Lp -= 32;
-            const float edge = __shfl_sync(0xFFFFFFFFu, d0sq, 0);
-            l_live = Lp >= beg && !(edge >= thr);
-          }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int oj = __shfl_xor_sync(0xFFFFFFFFu, best_j, o);
+        if (ob < best || (ob == best && oj < best_j)) {
+          best = ob;
+          best_j = oj;
+        }
+      }
+      const int seed = best_j;  // 0x7FFFFFFF when every box distance is NaN (NaN query key): nothing is admitted anyway
+      if (seed < nb && best <= thr) scan_block(beg + seed * 32, min(end, beg + seed * 32 + 32));
+      // pass 2: every other block whose box can still hold an admissible key
+      for (int j0 = 0; j0 < nb; j0 += 32) {
+        const int j = j0 + lane;
+        const float bdist = j < nb ? box_dist(b0 + j) : 3.0e38f;
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, j < nb && j != seed && bdist <= thr);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const float bsrc = __shfl_sync(0xFFFFFFFFu, bdist, src);
+          if (!(bsrc <= thr)) continue;  // the bound tightened while earlier blocks of this group were scanned
+          const int base = beg + (j0 + src) * 32;
+          scan_block(base, min(end, base + 32));
         }
       }
     }
@@ -663,11 +674,6 @@ score_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict
 // ------------------------------------------------------------------------------------------------------------------
 // Proposal replay + tidy-up + GMM-L2 initial correlation, one warp per query scan
 // ------------------------------------------------------------------------------------------------------------------
-struct EllD {
-  double mx, my, c00, c10, c01, c11;
-  float maj, w;
-};
-constexpr int ELL_CAP = 64;
 constexpr int FIN_WARPS = 4;  // warps per CTA of the finish kernel: one query scan per CTA, candidates spread over warps
 
 struct Prop {
@@ -689,7 +695,6 @@ struct FinishScratch {
   uint32_t ord[C2G_MAX_CAND];
   float corr[C2G_MAX_CAND];
   uint16_t passlist[C2G_NUM_Q_LEVELS_MAX * C2G_MAX_PIV * 64 + 8];  // hint indices that reached addProposal: one sublist per warp
-  EllD es[FIN_WARPS][ELL_CAP], et[FIN_WARPS][ELL_CAP];          // per warp: one level's ellipses of candidate / query
   int aft[3], overflow;
   int w_aft1[FIN_WARPS], w_aft2[FIN_WARPS], w_npass[FIN_WARPS];
 };
@@ -699,73 +704,40 @@ __device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g
   return (float) view_at(heads, views, slot, level, seq).cell_cnt * 1.0f / (float) heads[slot].layer_cell_cnt[level];
 }
 
-__device__ __forceinline__ void manual_cov_d(const c2g_view &v, double out[4]) {
-  const float vd00 = v.eig_vecs[0] * v.eig_vals[0], vd10 = v.eig_vecs[1] * v.eig_vals[0];
-  const float vd01 = v.eig_vecs[2] * v.eig_vals[1], vd11 = v.eig_vecs[3] * v.eig_vals[1];
-  out[0] = (double) (vd00 * v.eig_vecs[0] + vd01 * v.eig_vecs[2]);
-  out[1] = (double) (vd10 * v.eig_vecs[0] + vd11 * v.eig_vecs[2]);
-  out[2] = (double) (vd00 * v.eig_vecs[1] + vd01 * v.eig_vecs[3]);
-  out[3] = (double) (vd10 * v.eig_vecs[1] + vd11 * v.eig_vecs[3]);
-}
-
 // GMM-L2 initial correlation (correlation.h:84-96,125-152,196-202); all lanes of the warp cooperate, every lane returns
-// the same value.  src = candidate, tgt = query.  The ellipses of one level are staged in shared memory first (mean,
-// dilatable covariance, pre-selection radius, weight), so the O(n_src * n_tgt) pre-selection runs out of shared memory.
-
-__device__ __forceinline__ void stage_ellipses(const c2g_view *v, int n, EllD *dst, int lane) {
-  for (int i = lane; i < n; i += 32) {
-    const c2g_view &a = v[i];
-    double c[4];
-    manual_cov_d(a, c);
-    EllD e;
-    e.mx = (double) a.pos_mean[0];
-    e.my = (double) a.pos_mean[1];
-    e.c00 = c[0];
-    e.c10 = c[1];
-    e.c01 = c[2];
-    e.c11 = c[3];
-    e.maj = sqrtf(a.eig_vals[1]);
-    e.w = (float) a.cell_cnt;
-    dst[i] = e;
-  }
-}
-
-__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_view *views, int src_slot, int tgt_slot, const double T[4], int lane,
-                                EllD *es, EllD *et) {
+// the same value.  src = candidate, tgt = query.  Ellipses come from the compact per-view table the contour kernel wrote
+// (one 32-byte sector each): the source ellipse is a warp-wide broadcast load, the lanes stride over the targets.
+__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells, int src_slot, int tgt_slot, const double T[4], int lane) {
   const double theta = atan2(T[1], T[0]);
   const double c = cos(theta), s = sin(theta);
   double cost = 0.0;
   for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
     const int lev = li + 1;
     const int ns = heads[src_slot].n_ell[li], nt = heads[tgt_slot].n_ell[li];
-    const c2g_view *sv = views + (size_t) src_slot * C2G_VIEW_CAP + heads[src_slot].view_off[lev];
-    const c2g_view *tv = views + (size_t) tgt_slot * C2G_VIEW_CAP + heads[tgt_slot].view_off[lev];
-    for (int s0 = 0; s0 < ns; s0 += ELL_CAP)
-      for (int t0 = 0; t0 < nt; t0 += ELL_CAP) {
-        const int cs_ = min(ELL_CAP, ns - s0), ct_ = min(ELL_CAP, nt - t0);
-        __syncwarp();
-        stage_ellipses(sv + s0, cs_, es, lane);
-        stage_ellipses(tv + t0, ct_, et, lane);
-        __syncwarp();
-        for (int si = 0; si < cs_; ++si)
-        for (int ti = lane; ti < ct_; ti += 32) {
-          const EllD a = es[si];
-          const EllD b = et[ti];
-          const double qx = (T[0] * a.mx + (-T[1]) * a.my) + T[2], qy = (T[1] * a.mx + T[0] * a.my) + T[3];
-          const double ddx = qx - b.mx, ddy = qy - b.my;
-          if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + b.maj))) continue;
-          const double t00 = c * a.c00 + (-s) * a.c10, t01 = c * a.c01 + (-s) * a.c11;
-          const double t10 = s * a.c00 + c * a.c10, t11 = s * a.c01 + c * a.c11;
-          const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
-          const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
-          const double c00 = 2.0 * (ra00 + b.c00), c10 = 2.0 * (ra10 + b.c10), c01 = 2.0 * (ra01 + b.c01), c11 = 2.0 * (ra11 + b.c11);
-          const double mx = (c * a.mx + (-s) * a.my) + T[2] - b.mx;
-          const double my = (s * a.mx + c * a.my) + T[3] - b.my;
-          const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
-          const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
-          cost += -(double) b.w * (double) a.w * 1.0 / sqrt(det) * exp(qua);
-        }
+    const c2g_ell *se = ells + (size_t) src_slot * C2G_VIEW_CAP + heads[src_slot].view_off[lev];
+    const c2g_ell *te = ells + (size_t) tgt_slot * C2G_VIEW_CAP + heads[tgt_slot].view_off[lev];
+    for (int si = 0; si < ns; ++si) {
+      const c2g_ell a = se[si];
+      const double amx = (double) a.mx, amy = (double) a.my;
+      const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
+      for (int ti = lane; ti < nt; ti += 32) {
+        const c2g_ell b = te[ti];
+        const double ddx = qx - (double) b.mx, ddy = qy - (double) b.my;
+        if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + b.maj))) continue;
+        const double a00 = a.c00, a10 = a.c10, a01 = a.c01, a11 = a.c11;
+        const double t00 = c * a00 + (-s) * a10, t01 = c * a01 + (-s) * a11;
+        const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
+        const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
+        const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
+        const double c00 = 2.0 * (ra00 + (double) b.c00), c10 = 2.0 * (ra10 + (double) b.c10);
+        const double c01 = 2.0 * (ra01 + (double) b.c01), c11 = 2.0 * (ra11 + (double) b.c11);
+        const double mx = (c * amx + (-s) * amy) + T[2] - (double) b.mx;
+        const double my = (s * amx + c * amy) + T[3] - (double) b.my;
+        const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
+        const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
+        cost += -(double) b.w * (double) a.w * 1.0 / sqrt(det) * exp(qua);
       }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
   return -cost / sqrt(heads[src_slot].gmm_auto_corr * heads[tgt_slot].gmm_auto_corr);
@@ -806,7 +778,7 @@ __device__ void add_proposal(CandState &cs, const double Tp[4], const uint64_t b
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int B, QueryParams Q,
+finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, const c2g_ell *__restrict__ ells, int first_slot, int B, QueryParams Q,
               int max_fine_opt, const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores,
               c2g_query_result *__restrict__ results) {
   extern __shared__ __align__(16) unsigned char fsm_raw[];
@@ -942,7 +914,7 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
     pass = __shfl_sync(0xFFFFFFFFu, pass, 0);
     if (pass) {
       __syncwarp();
-      const double corr = gmm_init_corr(heads, views, cs.gidx, q_slot, cs.prop[0].T, lane, F.es[w], F.et[w]);
+      const double corr = gmm_init_corr(heads, ells, cs.gidx, q_slot, cs.prop[0].T, lane);
       if (lane == 0) {
         cs.corr_init = (float) corr;
         cs.alive = (cs.corr_init < Q.lb.correlation) ? 0 : 1;
@@ -968,16 +940,15 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
       }
     }
     const int n = p2 + 1;
-    // fineOptimize: std::sort on correlation_ (all zero here), "optimise" the first max_fine_opt (identity), sort those
+    // fineOptimize, first half (contour_db.h:616-621): std::sort on correlation_, which is still 0 for every candidate
+    // here.  The records leave this kernel in that order; refine.cu optimises the first max_fine_opt of them and sorts
+    // those by the refined correlation.
     for (int i = 0; i < n; ++i) {
       F.ord[i] = (uint32_t) i;
       F.corr[i] = 0.0f;
     }
     const float *corr = F.corr;
     c2g_sort::std_sort(F.ord, (long) n, [corr](uint32_t a, uint32_t b) { return corr[a] > corr[b]; });
-    const int pre = min(max_fine_opt, n);
-    for (int i = 0; i < pre; ++i) F.corr[F.ord[i]] = F.cand[F.ord[i]].corr_init;
-    c2g_sort::std_sort(F.ord, (long) pre, [corr](uint32_t a, uint32_t b) { return corr[a] > corr[b]; });
     c2g_query_result &R = results[q];
     R.n_cand = n;
     R.n_pose_before = n_before;
@@ -995,6 +966,10 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
       c.corr_init = 0.f;
       c.neg_est_dist = 0.0;
       c.T[0] = c.T[1] = c.T[2] = c.T[3] = 0.0;
+      c.corr_fine = 0.f;
+      c.fine_iters = -1;
+      c.fine_term = 0;
+      c.fine_flags = 0;
       if (i < n) {
         const CandState &cs = F.cand[F.ord[i]];
         c.cand_gidx = cs.gidx;
@@ -1004,10 +979,15 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
         c.neg_est_dist = cs.neg_est_dist;
         for (int k = 0; k < 4; ++k) c.T[k] = cs.prop[0].T[k];
       }
+      for (int k = 0; k < 4; ++k) c.T_fine[k] = c.T[k];
       R.cand[i] = c;
     }
   }
 }
+
+}  // namespace
+int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int B);  // refine.cu
+namespace {
 
 int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &Q) {
   memset(&Q, 0, sizeof(Q));
@@ -1019,9 +999,13 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
     Q.layer[i].gidx = t.gidx;
     Q.layer[i].seq = t.seq;
     Q.layer[i].orank = t.orank;
+    Q.layer[i].box_min = t.box_min;
+    Q.layer[i].box_max = t.box_max;
+    Q.layer[i].blk_cap = t.blk_cap;
     Q.layer[i].cap = t.cap;
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
       Q.layer[i].bucket_off[k] = t.bucket_off[k];
+      Q.layer[i].blk_off[k] = t.blk_off[k];
       Q.layer[i].ranges[k] = t.ranges[k];
     }
   }
@@ -1041,14 +1025,24 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, con
     C2G_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
-  finish_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q,
+  finish_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, ctx->d_ells, first_slot, B, Q,
                                                                             ctx->db.max_fine_opt, hints, scores, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
-  return 0;
+  return c2g_launch_refine(ctx, first_slot, B);
 }
 
 }  // namespace
+
+// kd ordering of one bucket, memoised by content: a growing database changes one or two buckets per pushAndBalance
+// (contour_db.cpp:63-317), the others keep their blocks
+struct C2gKdCache {
+  uint64_t hash[C2G_NUM_BUCKETS];
+  std::vector<int> order[C2G_NUM_BUCKETS];  // bucket-relative tree positions in mirror order
+  C2gKdCache() {
+    for (auto &h : hash) h = 0;
+  }
+};
 
 int c2g_query_alloc(c2g_ctx *ctx) {
   ctx->n_hint_slots = (long long) ctx->max_batch * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
@@ -1065,8 +1059,14 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * (size_t) t.cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, (size_t) t.cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.orank, sizeof(int) * (size_t) t.cap));
+    t.kd_cache = new (std::nothrow) C2gKdCache();
+    if (!t.kd_cache) return C2G_ERR_CAPACITY;
+    t.blk_cap = t.cap / 32 + C2G_NUM_BUCKETS + 1;
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_min, sizeof(float) * C2G_KEY_DIM * (size_t) t.blk_cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_max, sizeof(float) * C2G_KEY_DIM * (size_t) t.blk_cap));
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
       t.bucket_off[k] = 0;
+      t.blk_off[k] = 0;
       t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
     }
   }
@@ -1084,6 +1084,10 @@ void c2g_query_free(c2g_ctx *ctx) {
     cudaFree(ctx->layers[i].gidx);
     cudaFree(ctx->layers[i].seq);
     cudaFree(ctx->layers[i].orank);
+    cudaFree(ctx->layers[i].box_min);
+    cudaFree(ctx->layers[i].box_max);
+    delete ctx->layers[i].kd_cache;
+    ctx->layers[i].kd_cache = nullptr;
   }
 }
 
@@ -1106,6 +1110,8 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
     t.bucket_off[k] = cnt[k];
     t.ranges[k] = bucket_ranges_host[k];
   }
+  t.blk_off[0] = 0;
+  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) t.blk_off[k + 1] = t.blk_off[k] + (cnt[k + 1] - cnt[k] + 31) / 32;
   t.n = n;
   if (n == 0) return 0;
   float *kt = (float *) malloc(sizeof(float) * C2G_KEY_DIM * (size_t) n);
@@ -1117,7 +1123,8 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
     free(sq);
     return C2G_ERR_CAPACITY;
   }
-  // bucket-major positions in tree order first (the tie-break rank), then a stable sort by key[0] inside every bucket
+  // bucket-major positions in tree order first (the tie-break rank), then a kd ordering inside every bucket: the range is
+  // split at a multiple of 32 keys along its widest dimension (nth_element), recursively, until one 32-key block remains
   std::vector<int> perm((size_t) n), rank_of((size_t) n);
   {
     int pos[C2G_NUM_BUCKETS];
@@ -1128,10 +1135,64 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
     }
     std::vector<int> order((size_t) n);
     for (int p = 0; p < n; ++p) order[p] = p;
-    for (int k = 0; k < C2G_NUM_BUCKETS; ++k)
-      std::stable_sort(order.begin() + cnt[k], order.begin() + cnt[k + 1],
-                       [&](int a, int b) { return keys_host[(size_t) perm[a] * C2G_KEY_DIM] < keys_host[(size_t) perm[b] * C2G_KEY_DIM]; });
-    for (int p = 0; p < n; ++p) rank_of[p] = order[p];  // sorted position p holds flat tree-order position order[p]
+    std::vector<float> fk((size_t) n * C2G_KEY_DIM);  // keys in flat tree order: one indirection less in the loops below
+    for (int p = 0; p < n; ++p)
+      for (int d = 0; d < C2G_KEY_DIM; ++d) fk[(size_t) p * C2G_KEY_DIM + d] = keys_host[(size_t) perm[p] * C2G_KEY_DIM + d];
+    auto key_of = [&](int flat, int d) { return fk[(size_t) flat * C2G_KEY_DIM + d]; };
+    std::vector<std::pair<int, int>> stack;
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+      // content hash of the bucket's tree (keys, gidx, seq in tree order); an unchanged bucket reuses its ordering
+      uint64_t h = 1469598103934665603ull ^ (uint64_t) (cnt[k + 1] - cnt[k]);
+      for (int p = cnt[k]; p < cnt[k + 1]; ++p) {
+        const int i = perm[p];
+        uint32_t w[C2G_KEY_DIM + 2];
+        memcpy(w, &fk[(size_t) p * C2G_KEY_DIM], sizeof(float) * C2G_KEY_DIM);
+        w[C2G_KEY_DIM] = (uint32_t) gidx_host[i];
+        w[C2G_KEY_DIM + 1] = (uint32_t) (unsigned char) seq_host[i];
+        for (int q = 0; q < C2G_KEY_DIM + 2; ++q) h = (h ^ w[q]) * 1099511628211ull;
+      }
+      h |= 1ull;  // 0 = empty cache slot
+      C2gKdCache &kc = *t.kd_cache;
+      if (kc.hash[k] == h && (int) kc.order[k].size() == cnt[k + 1] - cnt[k]) {
+        for (int p = cnt[k]; p < cnt[k + 1]; ++p) order[p] = cnt[k] + kc.order[k][p - cnt[k]];
+        continue;
+      }
+      stack.clear();
+      stack.emplace_back(cnt[k], cnt[k + 1]);
+      while (!stack.empty()) {
+        const int lo = stack.back().first, hi = stack.back().second;
+        stack.pop_back();
+        const int m = hi - lo;
+        if (m <= 32) continue;
+        float mn[C2G_KEY_DIM], mx[C2G_KEY_DIM];
+        for (int d = 0; d < C2G_KEY_DIM; ++d) mn[d] = mx[d] = key_of(order[lo], d);
+        for (int p = lo + 1; p < hi; ++p) {
+          const float *kp = &fk[(size_t) order[p] * C2G_KEY_DIM];
+          for (int d = 0; d < C2G_KEY_DIM; ++d) {
+            mn[d] = kp[d] < mn[d] ? kp[d] : mn[d];
+            mx[d] = kp[d] > mx[d] ? kp[d] : mx[d];
+          }
+        }
+        int wd = 0;
+        float wspan = -1.0f;
+        for (int d = 0; d < C2G_KEY_DIM; ++d)
+          if (mx[d] - mn[d] > wspan) {
+            wspan = mx[d] - mn[d];
+            wd = d;
+          }
+        const int nblk = (m + 31) / 32, left = (nblk / 2) * 32;
+        std::nth_element(order.begin() + lo, order.begin() + lo + left, order.begin() + hi, [&](int a, int b) {
+          const float ka = key_of(a, wd), kb = key_of(b, wd);
+          return ka < kb || (ka == kb && a < b);
+        });
+        stack.emplace_back(lo, lo + left);
+        stack.emplace_back(lo + left, hi);
+      }
+      kc.hash[k] = h;
+      kc.order[k].resize((size_t) (cnt[k + 1] - cnt[k]));
+      for (int p = cnt[k]; p < cnt[k + 1]; ++p) kc.order[k][p - cnt[k]] = order[p] - cnt[k];
+    }
+    for (int p = 0; p < n; ++p) rank_of[p] = order[p];  // mirror position p holds flat tree-order position order[p]
   }
   int *ork = (int *) malloc(sizeof(int) * (size_t) n);
   if (!ork) {
@@ -1147,7 +1208,31 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
     sq[p] = seq_host[i];
     ork[p] = flat;
   }
+  // bounding box of every 32-key block
+  const int nblk_total = t.blk_off[C2G_NUM_BUCKETS];
+  std::vector<float> bmin((size_t) C2G_KEY_DIM * nblk_total), bmax((size_t) C2G_KEY_DIM * nblk_total);
+  for (int k = 0; k < C2G_NUM_BUCKETS; ++k)
+    for (int j = 0; j < t.blk_off[k + 1] - t.blk_off[k]; ++j) {
+      const int p0 = cnt[k] + 32 * j, p1 = p0 + 32 < cnt[k + 1] ? p0 + 32 : cnt[k + 1];
+      for (int d = 0; d < C2G_KEY_DIM; ++d) {
+        float mn = kt[(size_t) d * n + p0], mx = mn;  // NaN keys never match anything; min/max below ignore them
+        for (int p = p0 + 1; p < p1; ++p) {
+          const float v = kt[(size_t) d * n + p];
+          mn = fminf(mn, v);
+          mx = fmaxf(mx, v);
+        }
+        bmin[(size_t) d * nblk_total + t.blk_off[k] + j] = mn;
+        bmax[(size_t) d * nblk_total + t.blk_off[k] + j] = mx;
+      }
+    }
   cudaError_t e = cudaSuccess;
+  for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d) {
+    e = cudaMemcpyAsync(t.box_min + (size_t) d * t.blk_cap, bmin.data() + (size_t) d * nblk_total, sizeof(float) * (size_t) nblk_total,
+                        cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(t.box_max + (size_t) d * t.blk_cap, bmax.data() + (size_t) d * nblk_total, sizeof(float) * (size_t) nblk_total,
+                          cudaMemcpyHostToDevice, ctx->stream);
+  }
   for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d)
     e = cudaMemcpyAsync(t.keys_t + (size_t) d * t.cap, kt + (size_t) d * n, sizeof(float) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(t.gidx, gi, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);

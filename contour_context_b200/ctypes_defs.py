@@ -175,9 +175,14 @@ CAND_DTYPE = np.dtype(
         ("corr_init", "<f4"),
         ("neg_est_dist", "<f8"),
         ("T", "<f8", (4,)),
+        ("corr_fine", "<f4"),
+        ("fine_iters", "<i2"),
+        ("fine_term", "i1"),
+        ("fine_flags", "i1"),
+        ("T_fine", "<f8", (4,)),
     ]
 )
-assert CAND_DTYPE.itemsize == 56
+assert CAND_DTYPE.itemsize == 96
 
 QUERY_RESULT_DTYPE = np.dtype(
     [
@@ -190,7 +195,7 @@ QUERY_RESULT_DTYPE = np.dtype(
         ("cand", CAND_DTYPE, (MAX_CAND,)),
     ]
 )
-assert QUERY_RESULT_DTYPE.itemsize == 32 + 56 * MAX_CAND
+assert QUERY_RESULT_DTYPE.itemsize == 32 + 96 * MAX_CAND
 
 
 def kitti_cm_config(mulran: bool = False) -> CmConfig:

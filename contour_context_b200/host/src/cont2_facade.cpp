@@ -247,11 +247,13 @@ void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_pt
   if (res.n_cand > 0 && res.best >= 0) {  // ret_size = 1 (contour_db.h:639)
     const c2g_cand &c = res.cand[res.best];
     cand_ptrs.emplace_back(all_bevs_[c.cand_gidx]);
-    cand_corr.emplace_back((double) c.corr_init);
+    // anch_props_[0].correlation_ / T_delta_ after fineOptimize (contour_db.h:626-627,642-643)
+    if (c.fine_flags != 0) C2G_CHECK(C2G_ERR_CAPACITY);
+    cand_corr.emplace_back((double) c.corr_fine);
     Eigen::Isometry2d T;
     T.setIdentity();
-    T.rotate(std::atan2(c.T[1], c.T[0]));
-    T.pretranslate(V2D(c.T[2], c.T[3]));
+    T.rotate(std::atan2(c.T_fine[1], c.T_fine[0]));
+    T.pretranslate(V2D(c.T_fine[2], c.T_fine[3]));
     cand_tf.emplace_back(T);
   }
 }

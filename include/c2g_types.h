@@ -169,7 +169,16 @@ typedef struct c2g_cand {
   float area_perc;
   float corr_init;
   double neg_est_dist;
-  double T[4]; /* best proposal's T_delta_ as (cos, sin, tx, ty) */
+  double T[4]; /* best proposal's T_delta_ as (cos, sin, tx, ty): the constellation estimate, input of the refinement */
+  /* ConstellCorrelation::calcCorrelation (include/cont2/correlation.h:206-238), filled for the first
+   * min(max_fine_opt, n_cand) entries (CandidateManager::fineOptimize, contour_db.h:604-648); others keep
+   * corr_fine = 0, fine_iters = -1 and T_fine = T.  After fineOptimize the reference's anch_props_[0].correlation_ /
+   * T_delta_ are exactly (corr_fine, T_fine). */
+  float corr_fine;
+  int16_t fine_iters; /* line-search iterations performed, -1 = not refined */
+  int8_t fine_term;   /* 0 iteration cap, 1 converged, 2 solver failure (parameters stay at T, final cost -1) */
+  int8_t fine_flags;  /* bit 0: the pre-selected pair list overflowed the device scratch (result invalid) */
+  double T_fine[4];   /* refined (cos, sin, tx, ty) */
 } c2g_cand;
 
 /* Per query scan: outcome of the candidate cascade. */
@@ -193,7 +202,7 @@ static_assert(sizeof(c2g_relpt) == 12, "c2g_relpt layout");
 static_assert(sizeof(c2g_bci) == 608, "c2g_bci layout");
 static_assert(sizeof(c2g_hint) == 16, "c2g_hint layout");
 static_assert(sizeof(c2g_pair_score) == 128, "c2g_pair_score layout");
-static_assert(sizeof(c2g_cand) == 56, "c2g_cand layout");
+static_assert(sizeof(c2g_cand) == 96, "c2g_cand layout");
 static_assert(sizeof(c2g_scan_head) % 8 == 0, "c2g_scan_head alignment");
 #endif
 

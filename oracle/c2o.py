@@ -20,7 +20,7 @@ _REF = None
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("c2o_capi.cpp", "c2o_ingest.hpp", "c2o_query.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("c2o_capi.cpp", "c2o_ingest.hpp", "c2o_query.hpp", "c2o_refine.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "c2g_types.h"))
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
@@ -115,6 +115,29 @@ def ref_lib():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def refine_eval(src: "Scan", tgt: "Scan", T, p):
+    """Jet cost + gradient of the GMM-L2 problem (pairs selected at T = (cos, sin, tx, ty)) at p = (x, y, theta).
+    Returns (cost, grad[3], n_pairs)."""
+    L = lib()
+    L.c2o_refine_hook.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    T = np.ascontiguousarray(T, np.float64)
+    p = np.ascontiguousarray(p, np.float64)
+    out = np.zeros(16, np.float64)
+    L.c2o_refine_hook(0, src.h, tgt.h, _ptr(T), _ptr(p), _ptr(out))
+    return out[0], out[1:4].copy(), int(out[4])
+
+
+def refine_solve(src: "Scan", tgt: "Scan", T):
+    """ConstellCorrelation::calcCorrelation restated (c2o_refine.hpp) from T = (cos, sin, tx, ty)."""
+    L = lib()
+    L.c2o_refine_hook.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    T = np.ascontiguousarray(T, np.float64)
+    out = np.zeros(16, np.float64)
+    L.c2o_refine_hook(1, src.h, tgt.h, _ptr(T), None, _ptr(out))
+    return dict(correlation=out[0], x=out[1:4].copy(), initial_cost=out[4], final_cost=out[5], iterations=int(out[6]),
+                termination=int(out[7]), n_eval=int(out[8]), n_pairs=int(out[9]), norm=out[10])
 
 
 class Scan:

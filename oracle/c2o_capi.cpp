@@ -243,3 +243,43 @@ extern "C" void c2o_vec_libm(int kind, int n, const void *in, void *out) {
     }
   }
 }
+
+// ---- refinement hooks (c2o_refine.hpp) ------------------------------------------------------------------------------
+// src/tgt are Scan handles; T = (cos, sin, tx, ty).  mode 0: evaluate the Jet cost at params p (pairs selected at T):
+// out = {cost, d/dx, d/dy, d/dtheta, n_pairs}.  mode 1: calcCorrelation from T: out = {correlation, x, y, theta,
+// initial_cost, final_cost, iterations, termination, n_eval, n_pairs}.  mode 2: double-precision (non-Jet) normalised
+// correlation at p with pairs selected at T (tryProblem).
+extern "C" void c2o_refine_hook(int mode, void *src_h, void *tgt_h, const double *T, const double *p, double *out) {
+  const Scan &src = **(ScanPtr *) src_h, &tgt = **(ScanPtr *) tgt_h;
+  const GMMScanData gs = buildGMMScan(src), gt = buildGMMScan(tgt);
+  Iso2 Ti;
+  Ti.m00 = T[0];
+  Ti.m10 = T[1];
+  Ti.m01 = -T[1];
+  Ti.m11 = T[0];
+  Ti.tx = T[2];
+  Ti.ty = T[3];
+  if (mode == 0) {
+    refine::Problem P = refine::makeProblem(gs, gt, Ti);
+    const refine::J3 f = refine::evalJet(P, p);
+    out[0] = f.a;
+    out[1] = f.v[0];
+    out[2] = f.v[1];
+    out[3] = f.v[2];
+    out[4] = (double) P.pairs.size();
+  } else if (mode == 1) {
+    const refine::CorrResult r = refine::calcCorrelation(gs, gt, Ti);
+    refine::Problem P = refine::makeProblem(gs, gt, Ti);
+    out[0] = r.correlation;
+    out[1] = r.opt.x[0];
+    out[2] = r.opt.x[1];
+    out[3] = r.opt.x[2];
+    out[4] = r.opt.initial_cost;
+    out[5] = r.opt.final_cost;
+    out[6] = r.opt.iterations;
+    out[7] = r.opt.termination;
+    out[8] = r.opt.n_eval;
+    out[9] = (double) P.pairs.size();
+    out[10] = std::sqrt(gs.auto_corr * gt.auto_corr);
+  }
+}

@@ -15,9 +15,8 @@
 //    reference's vendored nanoflann to cross-check this.
 //  * Eigen::umeyama (JacobiSVD inside) is replaced by the closed-form 2-D Kabsch/Umeyama rotation; agreement is at
 //    double round-off level, not bit level.
-//  * Ceres L-BFGS refinement (correlation.h:206-238) is NOT restated (Ceres is un-vendored and absent; SURVEY.md §8f
-//    ranks it "next"): fineOptimize() here keeps the reference's control flow (both sorts, pre-selection of
-//    max_fine_opt candidates, top-1 return) but each "optimised" correlation / transform is the initial one.
+//  * Ceres (correlation.h:206-238) is un-vendored and absent: the L-BFGS refinement inside fineOptimize() is the
+//    restatement of Ceres' default line-search minimizer in c2o_refine.hpp (parity unpinned, see its header).
 #pragma once
 
 #include <array>
@@ -400,6 +399,10 @@ inline Iso2 getEstSensTF(const Iso2 &T_delta, const c2g_cm_config &cfg) {
   T_so.ty = cfg.n_col / 2 - 0.5;
   return T_so.inverse() * T_delta * T_so;
 }
+
+}  // namespace c2o
+#include "c2o_refine.hpp"
+namespace c2o {
 
 // ---------------------------------------------------------------------------------------------------------------
 // TreeBucket / LayerDB (contour_db.h:54-217, contour_db.cpp:63-403)
@@ -803,6 +806,8 @@ struct CandidateManager {
     bool has_corr_est = false;  // corr_est_ != nullptr
     float corr_init = 0;
     double neg_est_dist = 0;
+    Iso2 T_init;  // anch_props_[0].T_delta_ before the refinement overwrote it
+    int fine_iters = -1, fine_term = 0;
     std::vector<CandidateAnchorProp> anch_props_;
     void addProposal(const Iso2 &T_prop, const std::vector<CPair> &sim_pairs, const std::vector<float> &sim_area_perc) {
       for (size_t i = 0; i < anch_props_.size(); i++) {
@@ -948,15 +953,22 @@ struct CandidateManager {
     candidates_.erase(candidates_.begin() + p2 + 1, candidates_.end());
   }
 
-  // fineOptimize (contour_db.h:604-648) with the Ceres step replaced by identity (see header). Returns index of the
-  // top-1 in candidates_ order after the sorts, or -1.
-  int fineOptimize(int max_fine_opt) {
+  // fineOptimize (contour_db.h:604-648). Returns index of the top-1 in candidates_ order after the sorts, or -1.
+  int fineOptimize(int max_fine_opt, const std::function<const GMMScanData &(const Scan *)> &gmm_of) {
     if (candidates_.empty()) return -1;
+    for (auto &c : candidates_) c.T_init = c.anch_props_[0].T_delta_;
     std::sort(candidates_.begin(), candidates_.end(), [](const CandidatePoseData &d1, const CandidatePoseData &d2) {
       return d1.anch_props_[0].correlation_ > d2.anch_props_[0].correlation_;
     });
     int pre_sel_size = std::min(max_fine_opt, (int) candidates_.size());
-    for (int i = 0; i < pre_sel_size; i++) candidates_[i].anch_props_[0].correlation_ = candidates_[i].corr_init;
+    for (int i = 0; i < pre_sel_size; i++) {
+      auto &c = candidates_[i];
+      const refine::CorrResult r = refine::calcCorrelation(gmm_of(c.cm_cand_.get()), gmm_of(cm_tgt_.get()), c.anch_props_[0].T_delta_);
+      c.anch_props_[0].correlation_ = (float) r.correlation;
+      c.anch_props_[0].T_delta_ = r.T;
+      c.fine_iters = r.opt.iterations;
+      c.fine_term = r.opt.termination;
+    }
     std::sort(candidates_.begin(), candidates_.begin() + pre_sel_size, [](const CandidatePoseData &d1, const CandidatePoseData &d2) {
       return d1.anch_props_[0].correlation_ > d2.anch_props_[0].correlation_;
     });
@@ -1038,14 +1050,15 @@ struct ContourDB {
     double t2 = now();
     std::unique_ptr<GMMScanData> q_gmm;
     const Scan *q_raw = q_ptr.get();
-    cand_mng.tidyUpCandidates([this, &q_gmm, q_raw](const Scan *s) -> const GMMScanData & {
+    const std::function<const GMMScanData &(const Scan *)> gmm_of = [this, &q_gmm, q_raw](const Scan *s) -> const GMMScanData & {
       if (s == q_raw) {
         if (!q_gmm) q_gmm.reset(new GMMScanData(buildGMMScan(*s)));
         return *q_gmm;
       }
       return gmmOfDb(s);
-    });
-    cand_mng.fineOptimize(cfg_.max_fine_opt);
+    };
+    cand_mng.tidyUpCandidates(gmm_of);
+    cand_mng.fineOptimize(cfg_.max_fine_opt, gmm_of);
     if (t_l2) *t_l2 += now() - t2;
     out.n_pose_before = cand_mng.n_pose_before;
     out.cand_aft_check[0] = cand_mng.cand_aft_check1;
@@ -1060,10 +1073,18 @@ struct ContourDB {
       out.cand[i].area_perc = c.anch_props_[0].area_perc_;
       out.cand[i].corr_init = c.corr_init;
       out.cand[i].neg_est_dist = c.neg_est_dist;
-      out.cand[i].T[0] = c.anch_props_[0].T_delta_.m00;
-      out.cand[i].T[1] = c.anch_props_[0].T_delta_.m10;
-      out.cand[i].T[2] = c.anch_props_[0].T_delta_.tx;
-      out.cand[i].T[3] = c.anch_props_[0].T_delta_.ty;
+      out.cand[i].T[0] = c.T_init.m00;
+      out.cand[i].T[1] = c.T_init.m10;
+      out.cand[i].T[2] = c.T_init.tx;
+      out.cand[i].T[3] = c.T_init.ty;
+      out.cand[i].corr_fine = c.anch_props_[0].correlation_;
+      out.cand[i].fine_iters = (int16_t) c.fine_iters;
+      out.cand[i].fine_term = (int8_t) c.fine_term;
+      out.cand[i].fine_flags = 0;
+      out.cand[i].T_fine[0] = c.anch_props_[0].T_delta_.m00;
+      out.cand[i].T_fine[1] = c.anch_props_[0].T_delta_.m10;
+      out.cand[i].T_fine[2] = c.anch_props_[0].T_delta_.tx;
+      out.cand[i].T_fine[3] = c.anch_props_[0].T_delta_.ty;
     }
     out.best = out.n_cand > 0 ? 0 : -1;
   }

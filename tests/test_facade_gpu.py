@@ -48,7 +48,7 @@ def test_batch_driver_matches_python_mirror(built_lib, tmp_path):
         if res["n_cand"] > 0:
             n_pos += 1
             assert got[i][0] == int(res["cand"][0]["cand_gidx"]), (i, got[i], res["cand"][0]["cand_gidx"])
-            assert abs(got[i][1] - float(res["cand"][0]["corr_init"])) < 2e-6
+            assert abs(got[i][1] - float(res["cand"][0]["corr_fine"])) < 2e-6
         else:
             assert got[i][0] is None, (i, got[i])
         eng.copy_slots(40, i, 1)

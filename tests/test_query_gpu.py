@@ -1,5 +1,6 @@
 """GPU parity of the database/query path against the CPU oracle, through the C-ABI:
-growing DB bookkeeping -> ranged kNN hints -> per-hint cascade scores -> candidate poses -> GMM-L2 initial correlation.
+growing DB bookkeeping -> ranged kNN hints -> per-hint cascade scores -> candidate poses -> GMM-L2 initial correlation
+-> L-BFGS refinement (fineOptimize) -> final ranking.
 
 Bar: hint identity/order and squared key distances bit-exact; constellation / pairwise integer scores equal; matched-pair
 sets equal; SE(2) proposals, area_perc and correlation within 1e-5 (north_star)."""
@@ -72,7 +73,7 @@ def test_hints_scores_candidates(world):
     lb, ub = D.kitti_thres()
     res, hints, scores = eng.query(q_first, N_SCENES, lb, ub, want_trace=True)
     per_q = eng.hint_slots(1)
-    n_pass_total = n_cand_total = 0
+    n_pass_total = n_cand_total = n_refined = 0
     for j in range(N_SCENES):
         ores, ohints, oscores = odb.query(oq[j], lb, ub)
         gh = hints[j * per_q:(j + 1) * per_q]
@@ -110,9 +111,22 @@ def test_hints_scores_candidates(world):
             assert np.abs(gc["corr_init"] - oc["corr_init"]).max() <= 1e-5
             assert np.abs(gc["neg_est_dist"] - oc["neg_est_dist"]).max() <= 1e-8
             assert np.abs(gc["T"] - oc["T"]).max() <= 1e-8
+            # --- fineOptimize: L-BFGS refinement of the first max_fine_opt candidates + final ranking
+            pre = min(n, eng.db_cfg.max_fine_opt)
+            assert (gc["fine_flags"] == 0).all()
+            assert np.array_equal(gc["fine_iters"], oc["fine_iters"]), (j, gc["fine_iters"], oc["fine_iters"])
+            assert np.array_equal(gc["fine_term"], oc["fine_term"])
+            assert (gc["fine_iters"][:pre] >= 0).all() and (gc["fine_iters"][pre:] == -1).all()
+            assert np.abs(gc["corr_fine"] - oc["corr_fine"]).max() <= 1e-5
+            assert np.abs(gc["T_fine"] - oc["T_fine"]).max() <= 1e-6
+            n_refined += pre
+            # the refinement never lowers the correlation of a usable solution
+            usable = gc["fine_term"][:pre] != 2
+            assert (gc["corr_fine"][:pre][usable] >= gc["corr_init"][:pre][usable] - 1e-5).all()
     # the synthetic revisits must actually exercise the whole cascade
     assert n_pass_total >= 50, n_pass_total
     assert n_cand_total >= 8, n_cand_total
+    assert n_refined >= 8, n_refined
 
 
 def test_query_is_deterministic_and_async_path_agrees(world):
