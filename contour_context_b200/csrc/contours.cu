@@ -852,6 +852,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     {
       const float div_len = cfg.roi_radius / (float) ((C2G_KEY_DIM - 3) * 5);
       const double inv_norm_den = sqrt(2 * 3.14159265358979323846 * 1.0f * 1.0f);
+      const double rcp_norm_den = 1.0 / inv_norm_den;
       for (int w = tid; w < N_ANCH * N_DIVS; w += K2_THREADS) {
         const int a = w / N_DIVS, d = w - a * N_DIVS;
         const int n = min(S.cnt_point[a], KEY_LIST_CAP);
@@ -863,7 +864,14 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           for (int k = 0; k < n; ++k) {
             const float t = (x - dl[k]) / 1.0f;
             const double q = (-0.5 * (double) t) * (double) t;
-            const float g = (float) (c2g_exp(q, P.exp_mode, c2g_exp_tab_dev) / inv_norm_den);
+            const double e = c2g_exp(q, P.exp_mode, c2g_exp_tab_dev);
+            // (float) (e / den): the product with the rounded reciprocal is within 2.5 ulp of the correctly rounded
+            // quotient, so both round to the same float unless the product sits within a few ulp of a float rounding
+            // midpoint (low 29 mantissa bits == 0x10000000); only then is the real division executed.
+            double pq = e * rcp_norm_den;
+            const unsigned long long low = (unsigned long long) __double_as_longlong(pq) & 0x1FFFFFFFull;
+            if (low - 0x0FFFFFF8ull <= 0x10ull) pq = e / inv_norm_den;
+            const float g = (float) pq;
             acc += (float) hl[k] * g;
           }
         }

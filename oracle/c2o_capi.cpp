@@ -283,3 +283,23 @@ extern "C" void c2o_refine_hook(int mode, void *src_h, void *tgt_h, const double
     out[10] = std::sqrt(gs.auto_corr * gt.auto_corr);
   }
 }
+
+// test hook: fill the trees of q-level ll with arbitrary (key, gidx, seq) entries in the given buckets and set the bucket
+// ranges (large synthetic key tables for the kNN parity test)
+extern "C" void c2o_test_fill_layer2(void *db, int ll, const float *keys, const int32_t *gidx, const int8_t *seq, const uint8_t *bucket,
+                                     int n, const float *ranges) {
+  LayerDB &L = ((ContourDB *) db)->layer_db_[ll];
+  for (int b = 0; b < LayerDB::max_num_backets_; ++b) {
+    L.buckets_[b].data_tree.clear();
+    L.buckets_[b].gkidx_tree.clear();
+  }
+  for (int i = 0; i < n; ++i) {
+    Key k;
+    for (int d = 0; d < C2G_KEY_DIM; ++d) k[d] = keys[i * C2G_KEY_DIM + d];
+    TreeBucket &b = L.buckets_[bucket[i]];
+    b.data_tree.push_back(k);
+    b.gkidx_tree.push_back(IndexOfKey{(size_t) gidx[i], ((ContourDB *) db)->cfg_.q_levels[ll], (int) seq[i]});
+  }
+  for (int b = 0; b <= LayerDB::max_num_backets_; ++b) L.bucket_ranges_[b] = ranges[b];
+  for (int b = 0; b < LayerDB::max_num_backets_; ++b) L.buckets_[b].rebuildTree();
+}
