@@ -64,3 +64,12 @@ typedef unsigned long long c2g_cellkey;
 struct __align__(32) c2g_ell {
   float mx, my, c00, c10, c01, c11, w, maj;
 };
+
+// `sqrt(x) < y` with IEEE semantics (y >= 0 or NaN) without the square root in all but borderline cases: fl(sqrt(x)) is within
+// half an ulp of the real root, so the comparison is decided by x against y^2 whenever they differ by more than a few ulp.
+__device__ __forceinline__ bool c2g_sqrt_lt(double x, double y) {
+  const double y2 = y * y;
+  if (x < y2 * (1.0 - 1e-15)) return true;
+  if (x > y2 * (1.0 + 1e-15)) return false;
+  return sqrt(x) < y;
+}

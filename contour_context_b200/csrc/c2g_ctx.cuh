@@ -53,6 +53,7 @@ struct c2g_ctx {
   c2g_hint *d_hints;
   c2g_pair_score *d_scores;
   c2g_query_result *d_results;
+  void *d_fin_head, *d_fin_cand;  // per query / per candidate pose state between the finish kernels (query.cu)
   int *d_survivors, *d_nsurv;  // hint slots that pass the thread-per-hint prefilter, and their count
   uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
   int pair_cap;

@@ -8,8 +8,10 @@
 //                    BCI::checkConstellSim                                 include/cont2/contour_mng.h:288-388
 //                    ContourManager::checkConstellCorrespSim               include/cont2/contour_mng.h:1124-1242
 //                    ContourManager::getTFFromConstell                     include/cont2/contour_mng.h:1251-1277
-//   finish_kernel  CandidatePoseData::addProposal replay (:286-338), tidyUpCandidates (:494-596) with the GMM-L2 initial
-//                  correlation (include/cont2/correlation.h:42-202) and fineOptimize's ordering (:604-648, no Ceres step).
+//   finish_replay_kernel / finish_corr_kernel / finish_output_kernel
+//                  CandidatePoseData::addProposal replay (:286-338), tidyUpCandidates (:494-596) with the GMM-L2 initial
+//                  correlation (include/cont2/correlation.h:42-202) and fineOptimize's first ordering (:604-621); the
+//                  refinement itself is refine.cu.
 //
 // With DYNAMIC_THRES=0 (CMakeLists.txt:21) every hint check is independent, so hints are scored in parallel (one warp
 // each) and only the small order-dependent proposal merge is replayed sequentially per query scan, in reference order
@@ -588,6 +590,233 @@ __device__ void score_hint(const c2g_scan_head *heads, const c2g_view *views, in
   }
 }
 
+// The same cascade, one THREAD per surviving hint (the warp-per-hint version above spends most of its instructions on
+// lane 0: order-dependent list building, the std::sort replay, the two-pointer window, the shaft walk, the removal loop and
+// the Umeyama sums are all sequential in the reference).  Per-thread lists live in local memory (4.8 KB per thread);
+// descriptors are read straight from the head / view arenas (L1/L2 resident: the hints of one query share their target).
+__device__ __forceinline__ const c2g_view &view_of(const c2g_scan_head *heads, const c2g_view *views, int slot, int level, int seq) {
+  return views[(size_t) slot * C2G_VIEW_CAP + heads[slot].view_off[level] + seq];
+}
+
+__device__ void score_hint_serial(const c2g_scan_head *heads, const c2g_view *views, int q_slot, const c2g_hint &hint, const QueryParams &Q,
+                                  c2g_pair_score &rec) {
+  const int cand = hint.cand_gidx, level = hint.level, cseq = hint.cand_seq, qseq = hint.q_seq;
+  const c2g_bci &src = heads[cand].bcis[level][cseq];
+  const c2g_bci &tgt = heads[q_slot].bcis[level][qseq];
+  unsigned long long pot[MAX_POT_PAIRS];  // (orie_diff bits << 32) | level << 16 | seq_src << 8 | seq_tgt
+  CPairD c2[MAX_POT_PAIRS + 1];
+  uint8_t drop[MAX_POT_PAIRS + 1];
+  {
+    int ov1 = 0, ov2 = 0, ov3 = 0;
+    for (int i = 0; i < 4; ++i) {
+      const unsigned long long s_i = src.dist_bin[i], t_i = tgt.dist_bin[i];
+      const unsigned long long sl = (s_i << 1) | (i > 0 ? (src.dist_bin[i - 1] >> 63) : 0ull);
+      const unsigned long long sr = (s_i >> 1) | (i < 3 ? (src.dist_bin[i + 1] << 63) : 0ull);
+      ov1 += __popcll(s_i & t_i);
+      ov2 += __popcll(sl & t_i);
+      ov3 += __popcll(sr & t_i);
+    }
+    rec.constell[0] = ov1 + ov2 + ov3;
+    rec.constell[1] = max(ov1, max(ov2, ov3));
+    rec.constell[2] = 0;
+  }
+  if (!check_sim(view_of(heads, views, cand, level, cseq), view_of(heads, views, q_slot, level, qseq), Q.sim)) {
+    rec.constell[0] = rec.constell[1] = 0;  // cannot happen for prefilter survivors; an anchor failure keeps an all-zero record
+    rec.passed = 0;
+    return;
+  }
+  if (!(rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one)) {
+    rec.passed = -1;
+    return;
+  }
+  // (2/4) BCI::checkConstellSim (contour_mng.h:309-388): potential pairs, sort by orientation difference, circular window
+  int npot = 0;
+  {
+    const int n_sseg = src.n_seg, n_tseg = tgt.n_seg;
+    int p11 = 0, p12;
+    for (int p2 = 0; p2 < n_tseg - 1; p2++) {
+      const int tb = tgt.nei[tgt.seg[p2]].bit_pos;
+      while (p11 < n_sseg - 1 && src.nei[src.seg[p11]].bit_pos < tb - 1) p11++;
+      p12 = p11;
+      while (p12 < n_sseg - 1 && src.nei[src.seg[p12]].bit_pos <= tb + 1) p12++;
+      const int j0 = src.seg[p11], j1 = src.seg[p12];
+      for (int i = tgt.seg[p2]; i < tgt.seg[p2 + 1]; i++) {
+        const c2g_relpt ti = tgt.nei[i];
+        for (int j = j0; j < j1; j++) {
+          if (npot < MAX_POT_PAIRS) {
+            const c2g_relpt sj = src.nei[j];
+            const float od = clamp_ang_f(ti.theta - sj.theta);
+            pot[npot++] = ((unsigned long long) __float_as_uint(od) << 32) | ((unsigned long long) (uint8_t) sj.level << 16) |
+                          ((unsigned long long) (uint8_t) sj.seq << 8) | (unsigned long long) (uint8_t) ti.seq;
+          }
+        }
+      }
+    }
+  }
+  // std::sort by orie_diff (contour_mng.h:340-342): the records themselves are moved, the comparator reads the key only
+  c2g_sort::std_sort(pot, (long) npot, [](unsigned long long a, unsigned long long b) {
+    return __uint_as_float((unsigned) (a >> 32)) < __uint_as_float((unsigned) (b >> 32));
+  });
+  int longest = 1, longest_beg = 0;
+  {
+    const float angular_range = (float) (C2G_PI / 16);
+    int p1 = 0, p2 = 0;
+    const int pot_sz = npot;
+    while (p1 < pot_sz) {
+      const float dd = __uint_as_float((unsigned) (pot[p2 % pot_sz] >> 32)) - __uint_as_float((unsigned) (pot[p1] >> 32));
+      if ((double) dd + 2 * C2G_PI * (double) (p2 / pot_sz) > (double) angular_range)
+        p1++;
+      else {
+        if (p2 - p1 + 1 > longest) {
+          longest = p2 - p1 + 1;
+          longest_beg = p1;
+        }
+        p2++;
+      }
+    }
+  }
+  rec.constell[2] = longest;
+  if (longest < Q.lb.i_in_ang_rng) {
+    rec.passed = -1;
+    return;
+  }
+  // (3/4) checkConstellCorrespSim step 1 (contour_mng.h:1135-1152): individual similarity of the window's pairs + the anchor
+  int n2 = 0;
+  for (int i = longest_beg; i <= longest + longest_beg; i++) {
+    CPairD pr;
+    if (i < longest + longest_beg) {
+      const unsigned long long w = pot[i % npot];
+      pr.level = (int8_t) ((w >> 16) & 0xFF);
+      pr.seq_src = (int8_t) ((w >> 8) & 0xFF);
+      pr.seq_tgt = (int8_t) (w & 0xFF);
+    } else {
+      pr.level = src.level;
+      pr.seq_src = src.piv_seq;
+      pr.seq_tgt = tgt.piv_seq;
+    }
+    if (check_sim(view_of(heads, views, cand, pr.level, pr.seq_src), view_of(heads, views, q_slot, pr.level, pr.seq_tgt), Q.sim)) c2[n2++] = pr;
+  }
+  rec.pairwise[0] = n2;
+  rec.pairwise[1] = 0;
+  if (n2 < Q.lb.i_indiv_sim) {
+    rec.passed = -2;
+    return;
+  }
+  // step 2.1: the "shaft" (the last qualifying (i, j) among the first <= 10 pairs wins, see SURVEY.md §8a' #6)
+  float ssx = 0.f, ssy = 0.f, stx = 0.f, sty = 0.f;
+  for (int i = 1; i < min(n2, 10); i++)
+    for (int j = 0; j < i; j++) {
+      const c2g_view &mi = view_of(heads, views, cand, c2[i].level, c2[i].seq_src), &mj = view_of(heads, views, cand, c2[j].level, c2[j].seq_src);
+      const float cx = mi.pos_mean[0] - mj.pos_mean[0], cy = mi.pos_mean[1] - mj.pos_mean[1];
+      if (sqrtf(cx * cx + cy * cy) > sqrtf(ssx * ssx + ssy * ssy)) {
+        normalized2(cx, cy, ssx, ssy);
+        const c2g_view &ti = view_of(heads, views, q_slot, c2[i].level, c2[i].seq_tgt), &tj = view_of(heads, views, q_slot, c2[j].level, c2[j].seq_tgt);
+        normalized2(ti.pos_mean[0] - tj.pos_mean[0], ti.pos_mean[1] - tj.pos_mean[1], stx, sty);
+      }
+    }
+  // step 2.2: orientation verdict per pair (depends on the pair and the fixed shaft only)
+  for (int i = 0; i < n2; ++i) {
+    const c2g_view &sc1 = view_of(heads, views, cand, c2[i].level, c2[i].seq_src), &tc1 = view_of(heads, views, q_slot, c2[i].level, c2[i].seq_tgt);
+    uint8_t d = 0;
+    if (sc1.ecc_feat && tc1.ecc_feat) {
+      const float theta_s = c2g_acosf(ssx * sc1.eig_vecs[2] + ssy * sc1.eig_vecs[3]);
+      const float theta_t = c2g_acosf(stx * tc1.eig_vecs[2] + sty * tc1.eig_vecs[3]);
+      const float pi6 = (float) (C2G_PI / 6);
+      d = (diff_delt_f(theta_s, theta_t, pi6) && diff_delt_f((float) (C2G_PI - (double) theta_s), theta_t, pi6)) ? 1 : 0;
+    }
+    drop[i] = d;
+  }
+  {
+    // the reference's swap-with-last removal loop (contour_mng.h:1187-1201), verdicts travel with their entries
+    int num_sim = n2;
+    for (int i = 0; i < num_sim;) {
+      if (drop[i]) {
+        const CPairD tmp = c2[i];
+        c2[i] = c2[num_sim - 1];
+        c2[num_sim - 1] = tmp;
+        const uint8_t td = drop[i];
+        drop[i] = drop[num_sim - 1];
+        drop[num_sim - 1] = td;
+        num_sim--;
+        continue;
+      }
+      i++;
+    }
+    n2 = num_sim;
+  }
+  rec.pairwise[1] = n2;
+  if (n2 < Q.lb.i_orie_sim) {
+    rec.passed = -2;
+    return;
+  }
+  // getTFFromConstell: 2-D Umeyama without scaling, closed form (double), sums in list order
+  const double inv_n = 1.0 / (double) n2;
+  double sm0 = 0, sm1 = 0, dm0 = 0, dm1 = 0;
+  for (int i = 0; i < n2; ++i) {
+    const c2g_view &ps = view_of(heads, views, cand, c2[i].level, c2[i].seq_src), &pt = view_of(heads, views, q_slot, c2[i].level, c2[i].seq_tgt);
+    sm0 += (double) ps.pos_mean[0];
+    sm1 += (double) ps.pos_mean[1];
+    dm0 += (double) pt.pos_mean[0];
+    dm1 += (double) pt.pos_mean[1];
+  }
+  sm0 *= inv_n;
+  sm1 *= inv_n;
+  dm0 *= inv_n;
+  dm1 *= inv_n;
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+  for (int i = 0; i < n2; ++i) {
+    const c2g_view &ps = view_of(heads, views, cand, c2[i].level, c2[i].seq_src), &pt = view_of(heads, views, q_slot, c2[i].level, c2[i].seq_tgt);
+    const double sx = (double) ps.pos_mean[0] - sm0, sy = (double) ps.pos_mean[1] - sm1;
+    const double dx = (double) pt.pos_mean[0] - dm0, dy = (double) pt.pos_mean[1] - dm1;
+    s00 += dx * sx;
+    s01 += dx * sy;
+    s10 += dy * sx;
+    s11 += dy * sy;
+  }
+  s00 *= inv_n;
+  s01 *= inv_n;
+  s10 *= inv_n;
+  s11 *= inv_n;
+  const double ang0 = atan2(s10 - s01, s00 + s11);
+  const double c0 = cos(ang0), s0 = sin(ang0);
+  const double tx = dm0 - (c0 * sm0 - s0 * sm1);
+  const double ty = dm1 - (s0 * sm0 + c0 * sm1);
+  const double ang = atan2(s0, c0);
+  rec.T[0] = cos(ang);
+  rec.T[1] = sin(ang);
+  rec.T[2] = tx;
+  rec.T[3] = ty;
+  rec.passed = 1;
+  rec.n_pairs = n2;
+  for (int i = 0; i < n2; ++i) {
+    const int bit = (c2[i].level - 1) * 100 + c2[i].seq_src * 10 + c2[i].seq_tgt;
+    rec.pair_bits[bit >> 6] |= 1ull << (bit & 63);
+  }
+}
+
+// Stage 2 (thread version): one THREAD per surviving hint.
+__global__ void __launch_bounds__(128)
+score_thread_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, QueryParams Q,
+                    const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores, const int *__restrict__ survivors,
+                    const int *__restrict__ n_surv) {
+  const int n = *n_surv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int hid = survivors[i];
+    const c2g_hint h = hints[hid];
+    c2g_pair_score rec;
+    rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
+    rec.pairwise[0] = rec.pairwise[1] = 0;
+    rec.passed = 0;
+    rec.n_pairs = 0;
+    rec.pad_ = 0;
+    rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
+    for (int k = 0; k < C2G_PAIR_WORDS; ++k) rec.pair_bits[k] = 0ull;
+    rec.pad2_ = 0ull;
+    score_hint_serial(heads, views, first_slot + h.q_idx, h, Q, rec);
+    scores[hid] = rec;
+  }
+}
+
 // Stage 1 of the hint cascade, one THREAD per hint slot: the anchor similarity gate (contour_db.h:388) and the 256-bit
 // popcount gate of BCI::checkConstellSim (contour_mng.h:291-307) kill ~85 % of the hints with two 80-byte and two 32-byte
 // reads each; the record of a dead hint is final here, survivors are queued for the warp-per-hint stage.
@@ -689,6 +918,19 @@ struct CandState {
   double neg_est_dist;
   Prop prop[C2G_MAX_PROP];
 };
+// What survives the proposal replay per candidate pose: its selected proposal.  Written by finish_replay_kernel, completed by
+// finish_corr_kernel (corr_init, alive), consumed by finish_output_kernel.
+struct FinCand {
+  int gidx, vote_cnt;
+  float area_perc, corr_init;
+  double neg_est_dist;
+  double T[4];
+  int pass;   // passed the area_perc and neg_est_dist gates of tidyUpCandidates: the GMM-L2 initial correlation is due
+  int alive;  // passed the correlation gate too
+};
+struct FinHead {
+  int n_before, aft[3], overflow, pad_[3];
+};
 struct FinishScratch {
   CandState cand[C2G_MAX_CAND];
   int n_cand;
@@ -723,7 +965,7 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells,
       for (int ti = lane; ti < nt; ti += 32) {
         const c2g_ell b = te[ti];
         const double ddx = qx - (double) b.mx, ddy = qy - (double) b.my;
-        if (!(sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + b.maj))) continue;
+        if (!c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + b.maj))) continue;
         const double a00 = a.c00, a10 = a.c10, a01 = a.c01, a11 = a.c11;
         const double t00 = c * a00 + (-s) * a10, t01 = c * a01 + (-s) * a11;
         const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
@@ -778,9 +1020,9 @@ __device__ void add_proposal(CandState &cs, const double Tp[4], const uint64_t b
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, const c2g_ell *__restrict__ ells, int first_slot, int B, QueryParams Q,
-              int max_fine_opt, const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores,
-              c2g_query_result *__restrict__ results) {
+finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int B, QueryParams Q,
+                     const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores, FinHead *__restrict__ fin_head,
+                     FinCand *__restrict__ fin_cand) {
   extern __shared__ __align__(16) unsigned char fsm_raw[];
   FinishScratch &F = *reinterpret_cast<FinishScratch *>(fsm_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -790,7 +1032,7 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
   const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
   const c2g_hint *hq = hints + (size_t) q * per_q;
   const c2g_pair_score *sq = scores + (size_t) q * per_q;
-  // all four warps scan a quarter of the hint records each (in order); only the few hints that reached addProposal are
+  // the warps scan an equal share of the hint records each (in order); only the few hints that reached addProposal are
   // replayed sequentially afterwards
   {
     const int quarter = (int) ((per_q + FIN_WARPS - 1) / FIN_WARPS);
@@ -911,78 +1153,124 @@ finish_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restric
         if (cs.neg_est_dist < (double) Q.lb.neg_est_dist) pass = 0;
       }
     }
-    pass = __shfl_sync(0xFFFFFFFFu, pass, 0);
-    if (pass) {
-      __syncwarp();
-      const double corr = gmm_init_corr(heads, ells, cs.gidx, q_slot, cs.prop[0].T, lane);
-      if (lane == 0) {
-        cs.corr_init = (float) corr;
-        cs.alive = (cs.corr_init < Q.lb.correlation) ? 0 : 1;
-      }
+    if (lane == 0) {
+      FinCand fc;
+      fc.gidx = cs.gidx;
+      fc.vote_cnt = cs.prop[0].vote_cnt;
+      fc.area_perc = cs.prop[0].area_perc;
+      fc.corr_init = 0.0f;
+      fc.neg_est_dist = cs.neg_est_dist;
+      for (int k = 0; k < 4; ++k) fc.T[k] = cs.prop[0].T[k];
+      fc.pass = pass;
+      fc.alive = 0;
+      fin_cand[(size_t) q * C2G_MAX_CAND + ci] = fc;
     }
     __syncwarp();
   }
-  __syncthreads();
-  if (w == 0 && lane == 0) {
-    const int aft1 = F.aft[0], aft2 = F.aft[1], aft3 = F.aft[2], overflow = F.overflow;
-    // swap-compaction of the survivors exactly as contour_db.h:580-592
-    int p1 = 0, p2 = n_before - 1;
+  if (threadIdx.x == 0) {
+    FinHead h;
+    h.n_before = n_before;
+    h.aft[0] = F.aft[0];
+    h.aft[1] = F.aft[1];
+    h.aft[2] = F.aft[2];
+    h.overflow = F.overflow;
+    h.pad_[0] = h.pad_[1] = h.pad_[2] = 0;
+    fin_head[q] = h;
+  }
+}
+
+// tidyUpCandidates' GMM-L2 gate (contour_db.h:553-577): one warp per (query scan, candidate pose)
+__global__ void __launch_bounds__(256)
+finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int B, float lb_correlation,
+                   const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int q = wg / C2G_MAX_CAND, ci = wg % C2G_MAX_CAND;
+  if (q >= B || ci >= fin_head[q].n_before) return;
+  FinCand &fc = fin_cand[(size_t) q * C2G_MAX_CAND + ci];
+  if (!fc.pass) return;
+  const double T[4] = {fc.T[0], fc.T[1], fc.T[2], fc.T[3]};
+  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane);
+  if (lane == 0) {
+    fc.corr_init = (float) corr;
+    fc.alive = (fc.corr_init < lb_correlation) ? 0 : 1;
+  }
+}
+
+// swap-compaction of the survivors (contour_db.h:580-592), fineOptimize's first std::sort (contour_db.h:616-621; correlation_
+// is still 0 for every candidate) and the result records; one warp per query scan.  refine.cu optimises the first
+// max_fine_opt records and sorts those by the refined correlation.
+__global__ void __launch_bounds__(128)
+finish_output_kernel(int B, const FinHead *__restrict__ fin_head, const FinCand *__restrict__ fin_cand, c2g_query_result *__restrict__ results) {
+  __shared__ uint32_t ord_s[4][C2G_MAX_CAND];
+  __shared__ int n_s[4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= B) return;
+  const FinHead h = fin_head[q];
+  const FinCand *fc = fin_cand + (size_t) q * C2G_MAX_CAND;
+  if (lane == 0) {
+    uint32_t idx[C2G_MAX_CAND];
+    for (int i = 0; i < h.n_before; ++i) idx[i] = (uint32_t) i;
+    int p1 = 0, p2 = h.n_before - 1;
     while (p1 <= p2) {
-      if (!F.cand[p1].alive && F.cand[p2].alive) {
-        const CandState tmp = F.cand[p1];
-        F.cand[p1] = F.cand[p2];
-        F.cand[p2] = tmp;
+      if (!fc[idx[p1]].alive && fc[idx[p2]].alive) {
+        const uint32_t tmp = idx[p1];
+        idx[p1] = idx[p2];
+        idx[p2] = tmp;
         p1++;
         p2--;
       } else {
-        if (F.cand[p1].alive) p1++;
-        if (!F.cand[p2].alive) p2--;
+        if (fc[idx[p1]].alive) p1++;
+        if (!fc[idx[p2]].alive) p2--;
       }
     }
     const int n = p2 + 1;
-    // fineOptimize, first half (contour_db.h:616-621): std::sort on correlation_, which is still 0 for every candidate
-    // here.  The records leave this kernel in that order; refine.cu optimises the first max_fine_opt of them and sorts
-    // those by the refined correlation.
+    uint32_t ord[C2G_MAX_CAND];
+    float corr[C2G_MAX_CAND];
     for (int i = 0; i < n; ++i) {
-      F.ord[i] = (uint32_t) i;
-      F.corr[i] = 0.0f;
+      ord[i] = (uint32_t) i;
+      corr[i] = 0.0f;
     }
-    const float *corr = F.corr;
-    c2g_sort::std_sort(F.ord, (long) n, [corr](uint32_t a, uint32_t b) { return corr[a] > corr[b]; });
+    const float *cp = corr;
+    c2g_sort::std_sort(ord, (long) n, [cp](uint32_t a, uint32_t b) { return cp[a] > cp[b]; });
+    for (int i = 0; i < n; ++i) ord_s[w][i] = idx[ord[i]];
+    n_s[w] = n;
     c2g_query_result &R = results[q];
     R.n_cand = n;
-    R.n_pose_before = n_before;
-    R.cand_aft_check[0] = aft1;
-    R.cand_aft_check[1] = aft2;
-    R.cand_aft_check[2] = aft3;
-    R.overflow = overflow;
+    R.n_pose_before = h.n_before;
+    R.cand_aft_check[0] = h.aft[0];
+    R.cand_aft_check[1] = h.aft[1];
+    R.cand_aft_check[2] = h.aft[2];
+    R.overflow = h.overflow;
     R.best = n > 0 ? 0 : -1;
     R.pad_ = 0;
-    for (int i = 0; i < C2G_MAX_CAND; ++i) {
-      c2g_cand c;
-      c.cand_gidx = -1;
-      c.vote_cnt = 0;
-      c.area_perc = 0.f;
-      c.corr_init = 0.f;
-      c.neg_est_dist = 0.0;
-      c.T[0] = c.T[1] = c.T[2] = c.T[3] = 0.0;
-      c.corr_fine = 0.f;
-      c.fine_iters = -1;
-      c.fine_term = 0;
-      c.fine_flags = 0;
-      if (i < n) {
-        const CandState &cs = F.cand[F.ord[i]];
-        c.cand_gidx = cs.gidx;
-        c.vote_cnt = cs.prop[0].vote_cnt;
-        c.area_perc = cs.prop[0].area_perc;
-        c.corr_init = cs.corr_init;
-        c.neg_est_dist = cs.neg_est_dist;
-        for (int k = 0; k < 4; ++k) c.T[k] = cs.prop[0].T[k];
-      }
-      for (int k = 0; k < 4; ++k) c.T_fine[k] = c.T[k];
-      R.cand[i] = c;
-    }
   }
+  __syncwarp();
+  const int n = n_s[w];
+  static_assert(C2G_MAX_CAND == 32, "one result record per lane");
+  c2g_cand c;
+  c.cand_gidx = -1;
+  c.vote_cnt = 0;
+  c.area_perc = 0.f;
+  c.corr_init = 0.f;
+  c.neg_est_dist = 0.0;
+  c.T[0] = c.T[1] = c.T[2] = c.T[3] = 0.0;
+  c.corr_fine = 0.f;
+  c.fine_iters = -1;
+  c.fine_term = 0;
+  c.fine_flags = 0;
+  if (lane < n) {
+    const FinCand &cs = fc[ord_s[w][lane]];
+    c.cand_gidx = cs.gidx;
+    c.vote_cnt = cs.vote_cnt;
+    c.area_perc = cs.area_perc;
+    c.corr_init = cs.corr_init;
+    c.neg_est_dist = cs.neg_est_dist;
+    for (int k = 0; k < 4; ++k) c.T[k] = cs.T[k];
+  }
+  for (int k = 0; k < 4; ++k) c.T_fine[k] = c.T[k];
+  results[q].cand[lane] = c;
 }
 
 }  // namespace
@@ -1022,13 +1310,18 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, con
   static bool attr_set = false;
   const size_t smem = sizeof(FinishScratch);
   if (!attr_set) {
-    C2G_CUDA_TRY(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    C2G_CUDA_TRY(cudaFuncSetAttribute(finish_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
-  finish_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, ctx->d_ells, first_slot, B, Q,
-                                                                            ctx->db.max_fine_opt, hints, scores, ctx->d_results);
+  FinHead *fh = (FinHead *) ctx->d_fin_head;
+  FinCand *fcd = (FinCand *) ctx->d_fin_cand;
+  finish_replay_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
-  ctx->launches += 1;
+  finish_corr_kernel<<<(B * C2G_MAX_CAND + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, Q.lb.correlation, fh, fcd);
+  C2G_CUDA_TRY(cudaGetLastError());
+  finish_output_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, fh, fcd, ctx->d_results);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 3;
   return c2g_launch_refine(ctx, first_slot, B);
 }
 
@@ -1051,6 +1344,8 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_results, sizeof(c2g_query_result) * (size_t) ctx->max_batch));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_survivors, sizeof(int) * (size_t) ctx->n_hint_slots));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int)));
+  C2G_CUDA_TRY(cudaMalloc(&ctx->d_fin_head, sizeof(FinHead) * (size_t) ctx->max_batch));
+  C2G_CUDA_TRY(cudaMalloc(&ctx->d_fin_cand, sizeof(FinCand) * (size_t) ctx->max_batch * C2G_MAX_CAND));
   for (int i = 0; i < ctx->db.n_q_levels; ++i) {
     C2gLayerTable &t = ctx->layers[i];
     t.cap = ctx->scan_cap * C2G_MAX_PIV;
@@ -1079,6 +1374,8 @@ void c2g_query_free(c2g_ctx *ctx) {
   cudaFree(ctx->d_results);
   cudaFree(ctx->d_survivors);
   cudaFree(ctx->d_nsurv);
+  cudaFree(ctx->d_fin_head);
+  cudaFree(ctx->d_fin_cand);
   for (int i = 0; i < C2G_NUM_Q_LEVELS_MAX; ++i) {
     cudaFree(ctx->layers[i].keys_t);
     cudaFree(ctx->layers[i].gidx);
@@ -1267,7 +1564,15 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   prefilter_kernel<<<(unsigned) ((n_hints + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, n_hints, Q, ctx->d_hints,
                                                                                ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
   C2G_CUDA_TRY(cudaGetLastError());
-  {
+  // thread-per-survivor scoring: the survivor count lives on the device, so the grid covers the worst case sparsely and
+  // strides (about 15 % of the hints survive the prefilter).  C2G_SCORE_WARP=1 selects the warp-per-survivor variant.
+  static const bool warp_variant = getenv("C2G_SCORE_WARP") && atoi(getenv("C2G_SCORE_WARP")) != 0;
+  if (!warp_variant) {
+    const long long want = (n_hints + 127) / 128;
+    const long long cap = (long long) ctx->num_sms * 8;
+    score_thread_kernel<<<(unsigned) (want < cap ? want : cap), 128, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores,
+                                                                                      ctx->d_survivors, ctx->d_nsurv);
+  } else {
     const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
     const long long cap = (long long) ctx->num_sms * 16;
     static bool sc_attr = false;

@@ -1,7 +1,7 @@
 // refine.cu — ConstellCorrelation::calcCorrelation on the device (include/cont2/correlation.h:206-238) and the second half
 // of CandidateManager::fineOptimize (include/cont2/contour_db.h:604-648).
 //
-//   refine_kernel  one warp per (query scan, pre-selected candidate): builds the pair list GMMPair's constructor selects at
+//   refine_kernel  one CTA (4 warps) per (query scan, pre-selected candidate): builds the pair list GMMPair's constructor selects at
 //                  T_init (correlation.h:84-96), then minimises GMMPair::operator() (correlation.h:125-152) over
 //                  (x, y, theta) with the solver ceres::Solve runs for a GradientProblem with default options and
 //                  max_num_iterations = 10: L-BFGS direction + strong-Wolfe line search with cubic interpolation.
@@ -24,7 +24,8 @@ namespace {
 
 __device__ const uint64_t rf_exp_tab[256] = C2G_EXP_TAB_INIT;
 
-constexpr int RF_WARPS = 1;  // one candidate per CTA: a slot is released the moment its solver terminates (run lengths vary a lot)
+constexpr int RF_WARPS = 4;  // warps per candidate (one CTA each): the pair terms of one evaluation are split over 128 lanes, which
+                             // shortens the sequential evaluation chain of the long problems that set the kernel's makespan
 
 // value + gradient of the cost at one point
 struct D3 {
@@ -34,11 +35,13 @@ struct D3 {
 
 struct Prob {
   const c2g_ell *se, *te;  // ellipse tables of the candidate (src) and the query (tgt) scan, indexed like their views
-  const uint32_t *pairs;   // (src view index << 16) | tgt view index, in the reference's (level, src, tgt) order
-  int n_pairs, exp_mode, lane;
+  const uint32_t *pairs;   // this warp's share of the pre-selected pairs: (src view index << 16) | tgt view index
+  double (*red)[4];        // [RF_WARPS][4] shared-memory slots of the block reduction
+  int n_pairs, exp_mode, lane, warp;
 };
 
-// GMMPair::operator() (correlation.h:125-152) and its gradient; all lanes call, all lanes get the same result.
+// GMMPair::operator() (correlation.h:125-152) and its gradient; all threads of the CTA call, all get the same result
+// (fixed reduction order: butterfly inside a warp, then warps 0..RF_WARPS-1).
 // The VALUE of every pair term is computed with the operation sequence of the reference's expression (2x2 products
 // coefficient by coefficient, inverse = adjugate * (1 / det), -0.5 mu^T Sigma^-1 mu, K / sqrt(det) * exp(.)).
 // The GRADIENT is the closed form of what the reference obtains by automatic differentiation:
@@ -85,6 +88,25 @@ __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
     g1 += __shfl_xor_sync(0xFFFFFFFFu, g1, o);
     g2 += __shfl_xor_sync(0xFFFFFFFFu, g2, o);
   }
+  if (P.lane == 0) {
+    P.red[P.warp][0] = fa;
+    P.red[P.warp][1] = g0;
+    P.red[P.warp][2] = g1;
+    P.red[P.warp][3] = g2;
+  }
+  __syncthreads();
+  fa = P.red[0][0];
+  g0 = P.red[0][1];
+  g1 = P.red[0][2];
+  g2 = P.red[0][3];
+#pragma unroll
+  for (int w = 1; w < RF_WARPS; ++w) {
+    fa += P.red[w][0];
+    g0 += P.red[w][1];
+    g1 += P.red[w][2];
+    g2 += P.red[w][3];
+  }
+  __syncthreads();  // the slots are rewritten by the next evaluation
   return D3{fa, g0, g1, g2};
 }
 
@@ -532,11 +554,12 @@ __device__ RfOut rf_minimize(const Prob &P, const double x0[3]) {
   return R;
 }
 
-__global__ void __launch_bounds__(RF_WARPS * 32)
+__global__ void __launch_bounds__(RF_WARPS * 32, 5)
 refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int B, int max_fine_opt,
               int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results) {
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * RF_WARPS + (threadIdx.x >> 5);
+  __shared__ double red[RF_WARPS][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wg = blockIdx.x;  // one (query, candidate rank) per CTA; the exits below are CTA-uniform
   const int q = wg / max_fine_opt, ci = wg % max_fine_opt;
   if (q >= B) return;
   c2g_query_result &R = results[q];
@@ -545,10 +568,12 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   c2g_cand &C = R.cand[ci];
   const int src = C.cand_gidx, tgt = first_slot + q;
   const double T[4] = {C.T[0], C.T[1], C.T[2], C.T[3]};
-  uint32_t *pairs = pair_scratch + (size_t) wg * pair_cap;
+  const int warp_cap = pair_cap / RF_WARPS;
+  uint32_t *pairs = pair_scratch + (size_t) wg * pair_cap + (size_t) warp * warp_cap;
   const c2g_ell *se = ells + (size_t) src * C2G_VIEW_CAP, *te = ells + (size_t) tgt * C2G_VIEW_CAP;
-  // pre-selection at T_init (correlation.h:84-96): |T_init * mu_s - mu_t| < 3 (sqrt(eig_s) + sqrt(eig_t)), reference order.
-  // Lanes hold 32 target ellipses of the level in registers while the sources stream by.
+  // pre-selection at T_init (correlation.h:84-96): |T_init * mu_s - mu_t| < 3 (sqrt(eig_s) + sqrt(eig_t)).  Warp w takes the
+  // source ellipses w, w + RF_WARPS, ... of every level and keeps its own pair list; lanes hold 32 target ellipses of the
+  // level in registers while the sources stream by.
   int n_pairs = 0, overflow = 0;
   for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
     const int lev = li + 1;
@@ -563,21 +588,21 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
         by = (double) b.my;
         bmaj = b.maj;
       }
-      for (int si = 0; si < ns; ++si) {
+      for (int si = warp; si < ns; si += RF_WARPS) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
         const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
         const double ddx = qx - bx, ddy = qy - by;
-        const bool sel = lane < nt && sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + bmaj);
+        const bool sel = lane < nt && c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + bmaj));
         const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
         if (sel) {
           const int pos = n_pairs + __popc(m & ((1u << lane) - 1u));
-          if (pos < pair_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + lane);
+          if (pos < warp_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + lane);
         }
         n_pairs += __popc(m);
       }
     } else {
-      for (int si = 0; si < ns; ++si) {
+      for (int si = warp; si < ns; si += RF_WARPS) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
         const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
@@ -587,24 +612,26 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
           if (ti < nt) {
             const c2g_ell b = te[to + ti];
             const double ddx = qx - (double) b.mx, ddy = qy - (double) b.my;
-            sel = sqrt(ddx * ddx + ddy * ddy) < 3.0 * (double) (a.maj + b.maj);
+            sel = c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + b.maj));
           }
           const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
           if (sel) {
             const int pos = n_pairs + __popc(m & ((1u << lane) - 1u));
-            if (pos < pair_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + ti);
+            if (pos < warp_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + ti);
           }
           n_pairs += __popc(m);
         }
       }
     }
   }
-  if (n_pairs > pair_cap) {
+  if (n_pairs > warp_cap) {
     overflow = 1;
-    n_pairs = pair_cap;
+    n_pairs = warp_cap;
   }
-  __syncwarp();
+  overflow = __syncthreads_or(overflow);  // also orders the pair lists before the first evaluation
   Prob P;
+  P.red = red;
+  P.warp = warp;
   P.se = se;
   P.te = te;
   P.pairs = pairs;
@@ -613,7 +640,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   P.lane = lane;
   const double p0[3] = {T[2], T[3], atan2(T[1], T[0])};
   const RfOut o = rf_minimize(P, p0);
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     const double corr = -o.final_cost / sqrt(heads[src].gmm_auto_corr * heads[tgt].gmm_auto_corr);
     C.corr_fine = (float) corr;  // CandidateAnchorProp::correlation_ is a float (contour_db.h:270)
     C.fine_iters = (int16_t) o.iterations;
@@ -662,7 +689,7 @@ __global__ void rank_kernel(int B, int max_fine_opt, c2g_query_result *__restric
 }  // namespace
 
 int c2g_refine_alloc(c2g_ctx *ctx) {
-  ctx->pair_cap = 4096;
+  ctx->pair_cap = 8192;  // per candidate, split evenly over the warps of its CTA
   const size_t n = (size_t) ctx->max_batch * (size_t) (ctx->db.max_fine_opt > 0 ? ctx->db.max_fine_opt : 1) * (size_t) ctx->pair_cap;
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_pair_scratch, sizeof(uint32_t) * n));
   return 0;
@@ -673,8 +700,7 @@ void c2g_refine_free(c2g_ctx *ctx) { cudaFree(ctx->d_pair_scratch); }
 int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int B) {
   const int mfo = ctx->db.max_fine_opt;
   if (mfo <= 0) return 0;
-  const int warps = B * mfo;
-  refine_kernel<<<(warps + RF_WARPS - 1) / RF_WARPS, RF_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, mfo, ctx->P.exp_mode,
+  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, mfo, ctx->P.exp_mode,
                                                                                      ctx->d_pair_scratch, ctx->pair_cap, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
   rank_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, mfo, ctx->d_results);

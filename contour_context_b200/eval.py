@@ -103,7 +103,8 @@ def eval_metric_est(T_delta: np.ndarray, gt_src_3d: np.ndarray, gt_tgt_3d: np.nd
     nrm2 = float(ax @ ax)
     if nrm2 > 0:
         ax = ax / math.sqrt(nrm2)
-    ang = math.acos(float(z0 @ z1))
+    with np.errstate(invalid="ignore"):
+        ang = float(np.arccos(np.float64(z0 @ z1)))  # NaN beyond [-1, 1], like std::acos in the reference
     # AngleAxisd(-ang, ax).matrix()
     a = -ang
     c, s = math.cos(a), math.sin(a)

@@ -3,12 +3,17 @@
 // same call sequence.  Input: a text file with one "<timestamp> <path/to/scan.bin>" per line (the layout of the
 // reference's ts-lidar_bins-*.txt lists) and, optionally, MulRan/KITTI parameter selection by argv.
 //   usage: cont2_batch_bin <list.txt> [kitti|mulran]
+// With --eval the full harness of the reference runs (ContLCDEvaluator, test/batch_bin_test.cpp:131-237): ground-truth poses
+// are associated to the scans, every prediction is classified TP/FP/TN/FN and the outcome file of scripts/pr_mpe.py is
+// written.
+//   usage: cont2_batch_bin --eval <ts-sens_pose.txt> <ts-lidar_bins.txt> <outcome.txt> [kitti|mulran] [correlation_thres]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
 
 #include "cont2/contour_db.h"
+#include "eval/evaluator.h"
 
 SequentialTimeProfiler stp;  // the library's stage timers write here, like the reference executable
 
@@ -28,10 +33,17 @@ static std::vector<float> readKITTIBin(const std::string &path) {  // tools/poin
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    std::printf("usage: %s <ts-lidar_bins.txt> [kitti|mulran]\n", argv[0]);
+    std::printf("usage: %s <ts-lidar_bins.txt> [kitti|mulran]\n       %s --eval <ts-sens_pose.txt> <ts-lidar_bins.txt> <outcome.txt> [kitti|mulran] [corr_thres]\n",
+                argv[0], argv[0]);
     return 1;
   }
-  const bool mulran = argc > 2 && std::string(argv[2]) == "mulran";
+  const bool eval_mode = std::string(argv[1]) == "--eval";
+  if (eval_mode && argc < 5) {
+    std::printf("--eval needs <ts-sens_pose.txt> <ts-lidar_bins.txt> <outcome.txt>\n");
+    return 1;
+  }
+  const int dataset_arg = eval_mode ? 5 : 2;
+  const bool mulran = argc > dataset_arg && std::string(argv[dataset_arg]) == "mulran";
   ContourManagerConfig cm_config;  // config/batch_bin_test_config.yaml:28-46
   cm_config.lv_grads_ = mulran ? std::vector<float>{1.0f, 2.5f, 4.0f, 5.5f, 7.0f, 8.5f} : std::vector<float>{1.5f, 2.f, 2.5f, 3.f, 3.5f, 4.f};
   ContourDBConfig db_config;       // config/batch_bin_test_config.yaml:6-23
@@ -46,6 +58,45 @@ int main(int argc, char **argv) {
   thres_ub_.sim_post.correlation = 0.75f, thres_ub_.sim_post.area_perc = 0.15f, thres_ub_.sim_post.neg_est_dist = -5.0f;
 
   ContourDB contour_db(db_config);
+  if (eval_mode) {  // BatchBinSpinner::spinOnce (test/batch_bin_test.cpp:105-247) without ROS
+    const double corr_thres = argc > 6 ? std::atof(argv[6]) : 0.0;  // correlation_thres of the yaml (config/batch_bin_test_config.yaml:2)
+    ContLCDEvaluator evaluator(argv[2], argv[3], corr_thres);
+    int cnt_tp = 0, cnt_fn = 0, cnt_fp = 0;
+    while (evaluator.loadNewScan()) {
+      const auto laser_info_tgt = evaluator.getCurrScanInfo();
+      stp.lap();
+      stp.start();
+      std::shared_ptr<ContourManager> ptr_cm_tgt = evaluator.getCurrContourManager(cm_config);
+      stp.record("make bev");
+      ptr_cm_tgt->clearImage();
+      std::vector<std::shared_ptr<const ContourManager>> ptr_cands;
+      std::vector<double> cand_corr;
+      std::vector<Eigen::Isometry2d> bev_tfs;
+      contour_db.queryRangedKNN(ptr_cm_tgt, thres_lb_, thres_ub_, ptr_cands, cand_corr, bev_tfs);
+      if (ptr_cands.size() >= 2) std::abort();  // CHECK(ptr_cands.size() < 2) (batch_bin_test.cpp:187)
+      PredictionOutcome pred_res;
+      if (ptr_cands.empty())
+        pred_res = evaluator.addPrediction(ptr_cm_tgt, 0.0);
+      else
+        pred_res = evaluator.addPrediction(ptr_cm_tgt, cand_corr[0], ptr_cands[0], bev_tfs[0]);
+      switch (pred_res.tfpn) {
+        case PredictionOutcome::TP: std::printf("Prediction outcome: TP\n"); cnt_tp++; break;
+        case PredictionOutcome::FP: std::printf("Prediction outcome: FP\n"); cnt_fp++; break;
+        case PredictionOutcome::TN: std::printf("Prediction outcome: TN\n"); break;
+        case PredictionOutcome::FN: std::printf("Prediction outcome: FN\n"); cnt_fn++; break;
+      }
+      std::printf("TP Error mean: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPMeanTrans(), evaluator.getTPMeanRot());
+      std::printf("TP Error rmse: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPRMSETrans(), evaluator.getTPRMSERot());
+      std::printf("Accumulated tp poses: %d\nAccumulated fn poses: %d\nAccumulated fp poses: %d\n", cnt_tp, cnt_fn, cnt_fp);
+      stp.start();
+      contour_db.addScan(ptr_cm_tgt, laser_info_tgt.ts);
+      contour_db.pushAndBalance(laser_info_tgt.seq, laser_info_tgt.ts);
+      stp.record("Update database");
+    }
+    evaluator.savePredictionResults(argv[4]);
+    stp.printScreen();
+    return 0;
+  }
   std::ifstream list(argv[1]);
   std::string line;
   int seq = 0, n_pos = 0;

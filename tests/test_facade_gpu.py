@@ -56,3 +56,81 @@ def test_batch_driver_matches_python_mirror(built_lib, tmp_path):
         eng.db_push_and_balance(i, 30.0 * i)
     assert n_pos >= 3, "the revisits should produce loop closures"
     eng.close()
+
+
+def _world_pose(seed, visit, k):
+    """Ground-truth sensor pose of a synthetic scan: scene k sits at x = 1000 k; synth.sensor_pose is the pose in the scene."""
+    import math
+
+    sx, sy, th = synth.sensor_pose(seed, visit)
+    c, s = math.cos(th), math.sin(th)
+    return [c, -s, 0.0, 1000.0 * k + sx, s, c, 0.0, sy, 0.0, 0.0, 1.0, 0.0]
+
+
+def test_eval_harness_matches_python_evaluator_over_oracle(built_lib, oracle, tmp_path):
+    """cont2_batch_bin --eval (C++ facade + ContLCDEvaluator on the GPU path) writes the same outcome file as the Python
+    evaluator fed with the CPU oracle's predictions for the same synthetic trajectory with revisits: identical
+    TP/FP/TN/FN labels and pairings, correlation within 1e-5, metric pose errors within 1e-3 (m, rad).  The PR metrics of
+    both files (scripts/pr_mpe.py logic) agree and the revisits are recovered with centimetre-level error."""
+    from contour_context_b200 import eval as ev
+
+    exe = os.path.join(ROOT, "contour_context_b200", "host", "cont2_batch_bin")
+    assert os.path.exists(exe), "host facade not built (run __graft_entry__.build())"
+    scenes = (50, 51, 52, 53)
+    order = [(s, v) for v in range(3) for s in scenes]  # 12 scans, every scene revisited twice, 30 s apart
+    pts = synth.make_scans([s for s, _ in order], [v for _, v in order], 60000).numpy()
+    pose_lines, bin_lines = [], []
+    for i, (s, v) in enumerate(order):
+        f = tmp_path / f"{i:06d}.bin"
+        pts[i].astype(np.float32).tofile(f)
+        ts = 30.0 * i
+        pose_lines.append("%f " % ts + " ".join("%.9f" % x for x in _world_pose(s, v, scenes.index(s))))
+        bin_lines.append("%f %d %s" % (ts, i, f))
+    fp_pose, fp_bins = tmp_path / "pose.txt", tmp_path / "bins.txt"
+    fp_pose.write_text("\n".join(pose_lines) + "\n")
+    fp_bins.write_text("\n".join(bin_lines) + "\n")
+    out_gpu, out_cpu = tmp_path / "outcome_gpu.txt", tmp_path / "outcome_cpu.txt"
+    bar = 0.65
+    env = dict(os.environ, C2G_SCAN_CAPACITY="256")
+    run = subprocess.run([exe, "--eval", str(fp_pose), str(fp_bins), str(out_gpu), "kitti", str(bar)], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    # the same loop on the CPU oracle, recorded by the Python evaluator
+    cfg, dbc = D.kitti_cm_config(), D.kitti_db_config()
+    lb, ub = D.kitti_thres()
+    odb = oracle.DB(dbc)
+    e = ev.ContLCDEvaluator(str(fp_pose), str(fp_bins), bar)
+    i = 0
+    while e.load_new_scan():
+        info = e.curr_scan_info()
+        sc = oracle.Scan(cfg, info.seq).ingest(np.ascontiguousarray(pts[i]))
+        res, _, _ = odb.query(sc, lb, ub)
+        if res["n_cand"] > 0:
+            c = res["cand"][0]
+            e.add_prediction(info.seq, float(c["corr_fine"]), int(c["cand_gidx"]), ev.iso2_from_cs(c["T_fine"]))
+        else:
+            e.add_prediction(info.seq, 0.0)
+        odb.add_scan(sc, info.ts)
+        odb.push_and_balance(info.seq, info.ts)
+        i += 1
+    e.save_prediction_results(str(out_cpu))
+    g, c = ev.read_outcome(str(out_gpu)), ev.read_outcome(str(out_cpu))
+    assert len(g[0]) == len(order) == len(c[0])
+    assert np.array_equal(g[0], c[0]) and np.array_equal(g[1], c[1]) and np.array_equal(g[2], c[2])  # tfpn, ids
+    assert np.abs(g[3] - c[3]).max() <= 1e-5
+    assert np.abs(g[4] - c[4]).max() <= 1e-3
+    # every revisit (visits 1, 2) closes the loop on an earlier visit of its own scene, with small metric error
+    n_tp = 0
+    for k, (s, v) in enumerate(order):
+        if v == 0:
+            assert g[2][k] == -1 and g[0][k] == ev.TN
+        else:
+            assert g[2][k] >= 0 and order[g[2][k]][0] == s, (k, g[2][k])
+            # two revisits of one scene can be more than 5 m apart (each is within 4.3 m of visit 0): then the pairing is an FP
+            assert np.hypot(g[4][k][0], g[4][k][1]) < 0.5 and abs(g[4][k][2]) < 0.02
+            n_tp += g[0][k] == ev.TP
+    assert n_tp >= 6
+    gt_xyz = np.array([[p[3], p[7], p[11]] for p in (_world_pose(s, v, scenes.index(s)) for s, v in order)])
+    mg = ev.pr_metrics(gt_xyz, g[1], g[2], g[3], g[4], excl_frames=0)
+    mc = ev.pr_metrics(gt_xyz, c[1], c[2], c[3], c[4], excl_frames=0)
+    assert mg["max_f1"] == mc["max_f1"] and mg["max_f1"] > 0.8 and mg["tp_count"] == mc["tp_count"]
