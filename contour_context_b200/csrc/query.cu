@@ -948,39 +948,82 @@ __device__ __forceinline__ float cont_perc(const c2g_scan_head *heads, const c2g
 
 // GMM-L2 initial correlation (correlation.h:84-96,125-152,196-202); all lanes of the warp cooperate, every lane returns
 // the same value.  src = candidate, tgt = query.  Ellipses come from the compact per-view table the contour kernel wrote
-// (one 32-byte sector each): the source ellipse is a warp-wide broadcast load, the lanes stride over the targets.
-__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells, int src_slot, int tgt_slot, const double T[4], int lane) {
+// (one 32-byte sector each).  Two interleaved phases keep the lanes busy: the pre-selection test streams over (source,
+// 32 targets) tiles and appends the selected pairs to a small shared-memory queue; whenever 32 pairs are queued their
+// (expensive, FP64) terms are evaluated one per lane.
+//
+// Pre-selection `sqrt(|T mu_s - mu_t|^2) < 3 (sigma_s + sigma_t)`: a float comparison with a 1e-4 relative guard band decides
+// all but borderline pairs (float error of both sides is < 1e-5 relative for BEV coordinates), those take the exact path.
+__device__ __forceinline__ bool gmm_pair_selected(double qx, double qy, float qxf, float qyf, float amaj, const c2g_ell &b) {
+  const float fx = qxf - b.mx, fy = qyf - b.my;
+  const float d2 = fx * fx + fy * fy;
+  const float y = 3.0f * (amaj + b.maj);
+  const float y2 = y * y;
+  if (d2 > y2 * 1.0001f) return false;
+  if (d2 < y2 * 0.9999f) return true;
+  const double ddx = qx - (double) b.mx, ddy = qy - (double) b.my;
+  return c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (amaj + b.maj));
+}
+
+__device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells, int src_slot, int tgt_slot, const double T[4], int lane,
+                                uint32_t *queue /* 64 words of shared memory owned by this warp */) {
   const double theta = atan2(T[1], T[0]);
   const double c = cos(theta), s = sin(theta);
+  const c2g_ell *se_all = ells + (size_t) src_slot * C2G_VIEW_CAP, *te_all = ells + (size_t) tgt_slot * C2G_VIEW_CAP;
   double cost = 0.0;
+  int qn = 0;
+  auto eval_queued = [&](int cnt) {
+    if (lane < cnt) {
+      const uint32_t pr = queue[lane];
+      const c2g_ell a = se_all[pr >> 16], b = te_all[pr & 0xFFFFu];
+      const double amx = (double) a.mx, amy = (double) a.my;
+      const double a00 = a.c00, a10 = a.c10, a01 = a.c01, a11 = a.c11;
+      const double t00 = c * a00 + (-s) * a10, t01 = c * a01 + (-s) * a11;
+      const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
+      const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
+      const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
+      const double c00 = 2.0 * (ra00 + (double) b.c00), c10 = 2.0 * (ra10 + (double) b.c10);
+      const double c01 = 2.0 * (ra01 + (double) b.c01), c11 = 2.0 * (ra11 + (double) b.c11);
+      const double mx = (c * amx + (-s) * amy) + T[2] - (double) b.mx;
+      const double my = (s * amx + c * amy) + T[3] - (double) b.my;
+      const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
+      const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
+      cost += -(double) b.w * (double) a.w * 1.0 / sqrt(det) * exp(qua);
+    }
+  };
   for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
     const int lev = li + 1;
     const int ns = heads[src_slot].n_ell[li], nt = heads[tgt_slot].n_ell[li];
-    const c2g_ell *se = ells + (size_t) src_slot * C2G_VIEW_CAP + heads[src_slot].view_off[lev];
-    const c2g_ell *te = ells + (size_t) tgt_slot * C2G_VIEW_CAP + heads[tgt_slot].view_off[lev];
-    for (int si = 0; si < ns; ++si) {
-      const c2g_ell a = se[si];
-      const double amx = (double) a.mx, amy = (double) a.my;
-      const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
-      for (int ti = lane; ti < nt; ti += 32) {
-        const c2g_ell b = te[ti];
-        const double ddx = qx - (double) b.mx, ddy = qy - (double) b.my;
-        if (!c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + b.maj))) continue;
-        const double a00 = a.c00, a10 = a.c10, a01 = a.c01, a11 = a.c11;
-        const double t00 = c * a00 + (-s) * a10, t01 = c * a01 + (-s) * a11;
-        const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
-        const double ra00 = t00 * c + t01 * (-s), ra01 = t00 * s + t01 * c;
-        const double ra10 = t10 * c + t11 * (-s), ra11 = t10 * s + t11 * c;
-        const double c00 = 2.0 * (ra00 + (double) b.c00), c10 = 2.0 * (ra10 + (double) b.c10);
-        const double c01 = 2.0 * (ra01 + (double) b.c01), c11 = 2.0 * (ra11 + (double) b.c11);
-        const double mx = (c * amx + (-s) * amy) + T[2] - (double) b.mx;
-        const double my = (s * amx + c * amy) + T[3] - (double) b.my;
-        const double det = c00 * c11 - c01 * c10, invdet = 1.0 / det;
-        const double qua = -0.5 * (mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my));
-        cost += -(double) b.w * (double) a.w * 1.0 / sqrt(det) * exp(qua);
+    const int so = heads[src_slot].view_off[lev], to = heads[tgt_slot].view_off[lev];
+    for (int t0 = 0; t0 < nt; t0 += 32) {  // the lane keeps one target ellipse in registers while the sources stream by
+      const int ti = t0 + lane;
+      c2g_ell b;
+      b.mx = b.my = 1.0e30f;
+      b.maj = 0.0f;
+      if (ti < nt) b = te_all[to + ti];
+      for (int si = 0; si < ns; ++si) {
+        const c2g_ell a = se_all[so + si];  // warp-wide broadcast
+        const double amx = (double) a.mx, amy = (double) a.my;
+        const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
+        const bool sel = ti < nt && gmm_pair_selected(qx, qy, (float) qx, (float) qy, a.maj, b);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
+        if (m == 0u) continue;
+        if (sel) queue[qn + __popc(m & ((1u << lane) - 1u))] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + ti);
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          eval_queued(32);
+          __syncwarp();
+          const uint32_t keep = (lane < qn - 32) ? queue[32 + lane] : 0u;
+          __syncwarp();
+          if (lane < qn - 32) queue[lane] = keep;
+          qn -= 32;
+          __syncwarp();
+        }
       }
     }
   }
+  eval_queued(qn);
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
   return -cost / sqrt(heads[src_slot].gmm_auto_corr * heads[tgt_slot].gmm_auto_corr);
 }
@@ -1180,17 +1223,18 @@ finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__
 }
 
 // tidyUpCandidates' GMM-L2 gate (contour_db.h:553-577): one warp per (query scan, candidate pose)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32)
 finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int B, float lb_correlation,
                    const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand) {
-  const int lane = threadIdx.x & 31;
-  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ uint32_t queue[64];
+  const int lane = threadIdx.x;
+  const int wg = blockIdx.x;  // one warp per CTA: a slot is released as soon as its pose is done (most poses exit at once)
   const int q = wg / C2G_MAX_CAND, ci = wg % C2G_MAX_CAND;
   if (q >= B || ci >= fin_head[q].n_before) return;
   FinCand &fc = fin_cand[(size_t) q * C2G_MAX_CAND + ci];
   if (!fc.pass) return;
   const double T[4] = {fc.T[0], fc.T[1], fc.T[2], fc.T[3]};
-  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane);
+  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane, queue);
   if (lane == 0) {
     fc.corr_init = (float) corr;
     fc.alive = (fc.corr_init < lb_correlation) ? 0 : 1;
@@ -1317,7 +1361,7 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, con
   FinCand *fcd = (FinCand *) ctx->d_fin_cand;
   finish_replay_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
-  finish_corr_kernel<<<(B * C2G_MAX_CAND + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, Q.lb.correlation, fh, fcd);
+  finish_corr_kernel<<<B * C2G_MAX_CAND, 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, Q.lb.correlation, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   finish_output_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, fh, fcd, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());

@@ -42,8 +42,8 @@ struct Prob {
 
 // GMMPair::operator() (correlation.h:125-152) and its gradient; all threads of the CTA call, all get the same result
 // (fixed reduction order: butterfly inside a warp, then warps 0..RF_WARPS-1).
-// The VALUE of every pair term is computed with the operation sequence of the reference's expression (2x2 products
-// coefficient by coefficient, inverse = adjugate * (1 / det), -0.5 mu^T Sigma^-1 mu, K / sqrt(det) * exp(.)).
+// The VALUE of every pair term follows the reference's expression (2x2 products coefficient by coefficient, inverse =
+// adjugate / det, -0.5 mu^T Sigma^-1 mu, K det^-1/2 exp(.)) with det^-1/2 evaluated once.
 // The GRADIENT is the closed form of what the reference obtains by automatic differentiation:
 //   Sigma = 2 (R A R^T + B), mu = R a + t - b, f = K det(Sigma)^-1/2 exp(-1/2 mu^T Sigma^-1 mu), w = Sigma^-1 mu
 //   df/dt     = -f w
@@ -52,6 +52,7 @@ __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
   const double c = cos(p[2]), s = sin(p[2]), ns = -s;
   const double x = p[0], y = p[1];
   double fa = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll 2
   for (int i = P.lane; i < P.n_pairs; i += 32) {
     const uint32_t pr = P.pairs[i];
     const c2g_ell ea = P.se[pr >> 16], eb = P.te[pr & 0xFFFFu];
@@ -65,12 +66,15 @@ __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
     const double rax = c * ax + ns * ay, ray = s * ax + c * ay;
     const double mux = rax + x - (double) eb.mx, muy = ray + y - (double) eb.my;
     const double det = c00 * c11 - c10 * c01;
-    const double invdet = 1.0 / det;
+    // det^-1/2 once (MUFU.RSQ64H + Newton) instead of the reference's 1/det, sqrt(det) and K/sqrt(det): three long-latency
+    // subroutines on the critical path of every pair term; the few-ulp difference is far below the solver's tolerances
+    const double rs = rsqrt(det);
+    const double invdet = rs * rs;
     const double i00 = c11 * invdet, i10 = -c10 * invdet, i01 = -c01 * invdet, i11 = c00 * invdet;
     const double r0 = -0.5 * mux, r1 = -0.5 * muy;
     const double q0 = r0 * i00 + r1 * i10, q1 = r0 * i01 + r1 * i11;  // -1/2 mu^T Sigma^-1
     const double qua = q0 * mux + q1 * muy;
-    const double f = ((-(double) eb.w * (double) ea.w * 1.0) / sqrt(det)) * c2g_exp(qua, P.exp_mode, rf_exp_tab);
+    const double f = ((-(double) eb.w * (double) ea.w) * rs) * c2g_exp(qua, P.exp_mode, rf_exp_tab);
     fa += f;
     const double f2 = 2.0 * f;
     g0 += f2 * q0;  // -f w_x, w = -2 q
@@ -581,19 +585,31 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
     const int so = heads[src].view_off[lev], to = heads[tgt].view_off[lev];
     if (nt <= 32) {
       double bx = 0.0, by = 0.0;
-      float bmaj = 0.f;
+      float bmaj = 0.f, bxf = 0.f, byf = 0.f;
       if (lane < nt) {
         const c2g_ell b = te[to + lane];
         bx = (double) b.mx;
         by = (double) b.my;
+        bxf = b.mx;
+        byf = b.my;
         bmaj = b.maj;
       }
+#pragma unroll 4
       for (int si = warp; si < ns; si += RF_WARPS) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
         const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
-        const double ddx = qx - bx, ddy = qy - by;
-        const bool sel = lane < nt && c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + bmaj));
+        bool sel = false;
+        if (lane < nt) {
+          const float fx = (float) qx - bxf, fy = (float) qy - byf;
+          const float d2 = fx * fx + fy * fy, yy = 3.0f * (a.maj + bmaj), y2 = yy * yy;
+          if (d2 < y2 * 0.9999f)
+            sel = true;
+          else if (!(d2 > y2 * 1.0001f)) {  // borderline (or NaN): the exact double test
+            const double ddx = qx - bx, ddy = qy - by;
+            sel = c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + bmaj));
+          }
+        }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
         if (sel) {
           const int pos = n_pairs + __popc(m & ((1u << lane) - 1u));
