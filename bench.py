@@ -183,6 +183,13 @@ def run_b200(args):
         sc_all = torch.empty(world * sc_local.numel(), dtype=torch.uint8, device="cuda")
         hi_all = torch.empty(world * hi_local.numel(), dtype=torch.uint8, device="cuda")
 
+    pending = []  # NCCL work handles of the previous step's all-gather
+
+    def drain():
+        with torch.cuda.stream(stream):
+            while pending:
+                pending.pop().wait()  # stream-level wait: `stream` continues after the collective has finished
+
     def step(host_inputs: bool):
         with torch.cuda.stream(stream):
             if host_inputs:
@@ -190,16 +197,20 @@ def run_b200(args):
             else:
                 eng.ingest(q_dev, offsets, first_slot=q_first, on_device=True)
             eng.query_async(q_first, Q, lb, ub)
-            if world > 1:  # the path's one exchange step: publish per-pair score records to every rank
+            if world > 1:
+                # the path's one exchange step: publish the per-pair score records to every rank.  The collective runs on
+                # NCCL's stream and overlaps the NEXT step's ingest + kNN; the send buffers are reused only after it is done.
+                drain()
                 eng.query_export(Q, hi_local, sc_local, None)
-                dist.all_gather_into_tensor(sc_all, sc_local)
-                dist.all_gather_into_tensor(hi_all, hi_local)
+                pending.append(dist.all_gather_into_tensor(sc_all, sc_local, async_op=True))
+                pending.append(dist.all_gather_into_tensor(hi_all, hi_local, async_op=True))
             if host_inputs:
                 eng.query_export(Q, None, None, res_pinned)                        # D2H of the step's results
 
     def timed(host_inputs: bool, steps: int, warmup: int):
         for _ in range(warmup):
             step(host_inputs)
+        drain()
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -209,6 +220,7 @@ def run_b200(args):
         e0.record(stream)
         for _ in range(steps):
             step(host_inputs)
+        drain()  # the last step's all-gather is inside the timed region
         e1.record(stream)
         stream.synchronize()
         if world > 1:
