@@ -260,6 +260,15 @@ def run_b200(args):
         kern["ingest_ms"] = ev_time(lambda: eng.ingest(q_dev, offsets, first_slot=q_first, on_device=True))
         kern["contours_ms"] = kern["ingest_ms"] - kern["bev_scatter_ms"]
         kern["query_ms"] = ev_time(lambda: eng.query_async(q_first, Q, lb, ub))
+        eng.query_profile(True)
+        acc = {}
+        for _ in range(3):
+            with torch.cuda.stream(stream):
+                eng.query_async(q_first, Q, lb, ub)
+            for k, v in eng.query_profile(True, read=True).items():
+                acc.setdefault(k, []).append(v)
+        eng.query_profile(False)
+        kern["query_kernels_ms"] = {k: float(np.mean(v[1:])) for k, v in acc.items()}
 
     # sanity: the timed work produced real loop closures (not measured; guards against timing an empty path)
     res = eng.query(q_first, Q, lb, ub)

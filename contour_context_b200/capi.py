@@ -66,6 +66,7 @@ def lib():
         L.c2g_exp_mode.argtypes = [vp]
         L.c2g_selftest_libm.argtypes = [ip, ip, vp, vp]
         L.c2g_launch_count.restype = ll
+        L.c2g_query_profile.argtypes = [vp, C.c_int, vp]
         L.c2g_launch_count.argtypes = [vp]
         L.c2g_selftest_stdsort.argtypes = [vp, ip, ip]
         sizes = [D.SCAN_HEAD_DTYPE.itemsize, D.VIEW_DTYPE.itemsize, D.BCI_DTYPE.itemsize, D.HINT_DTYPE.itemsize,

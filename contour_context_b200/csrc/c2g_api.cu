@@ -499,6 +499,23 @@ int c2g_selftest_libm(int kind, int n, const void *in, void *out) {
 
 long long c2g_launch_count(c2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (ms_out) {  // durations of the last profiled c2g_query_async: knn, prefilter, score, replay, corr, output, refine, rank
+    if (!ctx->prof_on) return C2G_ERR_STATE;
+    C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 8; ++k) C2G_CUDA_TRY(cudaEventElapsedTime(&ms_out[k], ctx->prof_ev[k], ctx->prof_ev[k + 1]));
+  }
+  if (enable && !ctx->prof_on) {
+    for (int k = 0; k <= C2G_QPROF_N; ++k) C2G_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[k]));
+    ctx->prof_on = 1;
+  } else if (!enable && ctx->prof_on) {
+    for (int k = 0; k <= C2G_QPROF_N; ++k) cudaEventDestroy(ctx->prof_ev[k]);
+    ctx->prof_on = 0;
+  }
+  return 0;
+}
+
 /* developer aid: per-phase clock64() stamps of CTA 0's first scan in the last contour kernel (64 values) */
 int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host) {
   if (!ctx || !out_host) return C2G_ERR_ARG;

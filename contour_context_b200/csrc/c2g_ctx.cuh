@@ -3,6 +3,7 @@
 #include "c2g_common.cuh"
 
 #define C2G_MAX_CHUNK_EVENTS 64
+#define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
 struct C2gKdCache;  // host-side memo of the kd ordering of every bucket (query.cu)
 
@@ -60,4 +61,7 @@ struct c2g_ctx {
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state
+  // optional per-kernel timing of the query path (c2g_query_profile): event k is recorded after kernel k - 1
+  int prof_on;
+  cudaEvent_t prof_ev[C2G_QPROF_N + 1];
 };

@@ -24,6 +24,8 @@
 #include "stdsort.cuh"
 #include "c2g_libm.cuh"
 
+#define C2G_QPROF(ctx, k) do { if ((ctx)->prof_on) cudaEventRecord((ctx)->prof_ev[k], (ctx)->stream); } while (0)
+
 namespace {
 
 constexpr int QK_WARPS = 8;           // warps per CTA in the kNN kernel
@@ -1361,10 +1363,13 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, con
   FinCand *fcd = (FinCand *) ctx->d_fin_cand;
   finish_replay_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 4);
   finish_corr_kernel<<<B * C2G_MAX_CAND, 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, Q.lb.correlation, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 5);
   finish_output_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, fh, fcd, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 6);
   ctx->launches += 3;
   return c2g_launch_refine(ctx, first_slot, B);
 }
@@ -1601,13 +1606,16 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   QueryParams Q;
   build_query_params(ctx, lb, Q);
   const int n_keys = B * Q.n_q_levels * C2G_MAX_PIV;
+  C2G_QPROF(ctx, 0);
   knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, first_slot, B, Q, ctx->d_hints);
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 1);
   const long long n_hints = (long long) n_keys * Q.nnk;
   C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int), ctx->stream));
   prefilter_kernel<<<(unsigned) ((n_hints + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, n_hints, Q, ctx->d_hints,
                                                                                ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 2);
   // thread-per-survivor scoring: the survivor count lives on the device, so the grid covers the worst case sparsely and
   // strides (about 15 % of the hints survive the prefilter).  C2G_SCORE_WARP=1 selects the warp-per-survivor variant.
   static const bool warp_variant = getenv("C2G_SCORE_WARP") && atoi(getenv("C2G_SCORE_WARP")) != 0;
@@ -1629,6 +1637,7 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
                                                                                              ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
   }
   C2G_CUDA_TRY(cudaGetLastError());
+  C2G_QPROF(ctx, 3);
   ctx->launches += 3;
   return launch_finish(ctx, first_slot, B, Q, ctx->d_hints, ctx->d_scores);
 }

@@ -52,7 +52,6 @@ __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
   const double c = cos(p[2]), s = sin(p[2]), ns = -s;
   const double x = p[0], y = p[1];
   double fa = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll 2
   for (int i = P.lane; i < P.n_pairs; i += 32) {
     const uint32_t pr = P.pairs[i];
     const c2g_ell ea = P.se[pr >> 16], eb = P.te[pr & 0xFFFFu];
@@ -574,6 +573,8 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   const double T[4] = {C.T[0], C.T[1], C.T[2], C.T[3]};
   const int warp_cap = pair_cap / RF_WARPS;
   uint32_t *pairs = pair_scratch + (size_t) wg * pair_cap + (size_t) warp * warp_cap;
+  // (staging both ellipse tables in shared memory was measured 30 % slower: 32-byte records at random indices conflict on the
+  // banks, while the 32-byte sectors are served well by L1)
   const c2g_ell *se = ells + (size_t) src * C2G_VIEW_CAP, *te = ells + (size_t) tgt * C2G_VIEW_CAP;
   // pre-selection at T_init (correlation.h:84-96): |T_init * mu_s - mu_t| < 3 (sqrt(eig_s) + sqrt(eig_t)).  Warp w takes the
   // source ellipses w, w + RF_WARPS, ... of every level and keeps its own pair list; lanes hold 32 target ellipses of the
@@ -716,11 +717,13 @@ void c2g_refine_free(c2g_ctx *ctx) { cudaFree(ctx->d_pair_scratch); }
 int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int B) {
   const int mfo = ctx->db.max_fine_opt;
   if (mfo <= 0) return 0;
-  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, mfo, ctx->P.exp_mode,
-                                                                                     ctx->d_pair_scratch, ctx->pair_cap, ctx->d_results);
+  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch,
+                                                            ctx->pair_cap, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
+  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[7], ctx->stream);
   rank_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, mfo, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
+  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[8], ctx->stream);
   ctx->launches += 2;
   return 0;
 }

@@ -164,6 +164,14 @@ class Engine:
                                                      C.c_void_p(scores_dev), capi.ptr(res)), "c2g_finish_from_scores")
         return res
 
+    QUERY_KERNELS = ("knn", "prefilter", "score", "replay", "gmm_gate", "output", "refine", "rank")
+
+    def query_profile(self, enable: bool = True, read: bool = False):
+        """Per-kernel CUDA-event timing of query_async (ms per kernel of the last profiled call when read=True)."""
+        ms = np.zeros(8, np.float32) if read else None
+        capi.check(capi.lib().c2g_query_profile(self.h, int(enable), capi.ptr(ms)), "c2g_query_profile")
+        return dict(zip(self.QUERY_KERNELS, (float(v) for v in ms))) if read else None
+
     def exp_mode(self) -> int:
         """Which glibc exp() variant the device reproduces (0 = none matched the host libm: libdevice exp, keys may differ by 1 ulp)."""
         return int(capi.lib().c2g_exp_mode(self.h))

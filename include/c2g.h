@@ -127,6 +127,10 @@ int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host);
 
 /* Counters: kernels launched by this context since creation (bench.py's gpu_launches). */
 long long c2g_launch_count(c2g_ctx *ctx);
+/* Measurement aid (no reference counterpart): with enable != 0, c2g_query_async brackets each of its kernels with CUDA events
+ * on the context's stream.  When ms_out != NULL the durations (ms) of the last profiled query are written first:
+ * ms_out[8] = knn, prefilter, score, proposal replay, GMM-L2 gate, output, refinement, ranking.  Synchronises the stream. */
+int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out);
 
 /* Host-side replay of libstdc++ std::sort used by the kernels (tests only): sorts `n` packed (key << 16 | index)
  * words with comparator key-descending (desc != 0) or key-ascending. */
