@@ -18,7 +18,7 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        uint16_t *cell_lists, int num_sms, cudaStream_t stream, long long *dbg);
+                        uint16_t *cell_lists, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg);
 int c2g_query_alloc(c2g_ctx *ctx);
 void c2g_query_free(c2g_ctx *ctx);
 int c2g_refine_alloc(c2g_ctx *ctx);  // refine.cu
@@ -185,6 +185,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_ells, sizeof(c2g_ell) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_dbg, sizeof(long long) * 64);
+  ALLOC(ctx->d_work_counter, sizeof(int));
   ALLOC(ctx->d_cell_lists, sizeof(uint16_t) * C2G_NLEV * ncell * (size_t) ctx->num_sms);
 #undef ALLOC
   rc = c2g_query_alloc(ctx);
@@ -229,6 +230,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_views);
   cudaFree(ctx->d_ells);
   cudaFree(ctx->d_dbg);
+  cudaFree(ctx->d_work_counter);
   cudaFree(ctx->d_cell_lists);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -287,7 +289,7 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     if (rc) return rc;
     rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0,
                              ctx->d_bev_h + ncell * b0, ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads,
-                             ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                             ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
   }
@@ -309,7 +311,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
   int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
   if (rc) return rc;
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;

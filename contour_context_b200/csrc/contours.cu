@@ -270,7 +270,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
                int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
-               uint16_t *__restrict__ cell_lists, long long *__restrict__ dbg) {
+               uint16_t *__restrict__ cell_lists, int *__restrict__ work_counter, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,7 +278,14 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
   const c2g_cm_config &cfg = P.cfg;
   c2g_view *const presort = presort_scratch + (size_t) blockIdx.x * C2G_VIEW_CAP;
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  // scans are handed out dynamically (their cost varies 2x with the scene, and a CTA that starts late - e.g. behind a
+  // co-running collective - must not leave a static share of the batch unprocessed until the end)
+  __shared__ int next_scan;
+  while (true) {
+    if (tid == 0) next_scan = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int b = next_scan;
+    if (b >= B) break;
     const size_t cbase = (size_t) b * ncell;
     const float *hg = bev_h + cbase, *rfg = bev_rf + cbase, *cfp = bev_cf + cbase;
     c2g_scan_head *head = heads + (first_slot + b);
@@ -1057,7 +1064,7 @@ size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        uint16_t *cell_lists, int num_sms, cudaStream_t stream, long long *dbg) {
+                        uint16_t *cell_lists, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
   static bool attr_set = false;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -1065,8 +1072,10 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   }
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;
+  C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, cell_lists, dbg);
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, cell_lists,
+                                                             work_counter, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }
