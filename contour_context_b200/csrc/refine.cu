@@ -595,7 +595,6 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
         byf = b.my;
         bmaj = b.maj;
       }
-#pragma unroll 4
       for (int si = warp; si < ns; si += RF_WARPS) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
