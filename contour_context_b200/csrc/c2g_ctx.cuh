@@ -3,6 +3,7 @@
 #include "c2g_common.cuh"
 
 #define C2G_MAX_CHUNK_EVENTS 64
+#define C2G_QUERY_STREAMS 4  // sub-batches of one c2g_query_async call that may run concurrently
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
 struct C2gKdCache;  // host-side memo of the kd ordering of every bucket (query.cu)
@@ -56,6 +57,8 @@ struct c2g_ctx {
   c2g_pair_score *d_scores;
   c2g_query_result *d_results;
   void *d_fin_head, *d_fin_cand;  // per query / per candidate pose state between the finish kernels (query.cu)
+  cudaStream_t qstream[C2G_QUERY_STREAMS];
+  cudaEvent_t ev_qfork, ev_qjoin[C2G_QUERY_STREAMS];
   int *d_survivors, *d_nsurv;  // hint slots that pass the thread-per-hint prefilter, and their count
   uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
   int pair_cap;

@@ -62,7 +62,7 @@ __device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, c
 // across the warp's registers (slot j lives in lane j % 32, register j / 32) and updated by warp-cooperative insertion.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QK_WARPS * 32)
-knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, QueryParams Q, c2g_hint *__restrict__ hints) {
+knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, c2g_hint *__restrict__ hints) {
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * QK_WARPS + (threadIdx.x >> 5);
   const int keys_per_scan = Q.n_q_levels * C2G_MAX_PIV;
@@ -70,7 +70,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, Query
   // layer-major ordering of the work so that the warps of one CTA scan the same table
   const int ll = wglobal / (B * C2G_MAX_PIV);
   const int rem = wglobal - ll * (B * C2G_MAX_PIV);
-  const int q = rem / C2G_MAX_PIV, seq = rem - q * C2G_MAX_PIV;
+  const int q = q0 + rem / C2G_MAX_PIV, seq = rem - (rem / C2G_MAX_PIV) * C2G_MAX_PIV;  // queries [q0, q0 + B) of the batch
   const int level = Q.q_levels[ll];
   c2g_hint *out = hints + ((size_t) (q * Q.n_q_levels + ll) * C2G_MAX_PIV + seq) * Q.nnk;
   const float *qk = heads[first_slot + q].keys[level][seq];
@@ -142,6 +142,8 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int B, Query
 #pragma unroll
         for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
         // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
+        // (stopping after the first group when it alone exceeds the bound for the whole block was measured 15 % slower:
+        // the kd blocks are not tight enough in those four dimensions for the vote to pass often)
         float r = 0.0f;
         r += ((df[0] * df[0] + df[1] * df[1]) + df[2] * df[2]) + df[3] * df[3];
         r += ((df[4] * df[4] + df[5] * df[5]) + df[6] * df[6]) + df[7] * df[7];
@@ -823,13 +825,13 @@ score_thread_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__r
 // popcount gate of BCI::checkConstellSim (contour_mng.h:291-307) kill ~85 % of the hints with two 80-byte and two 32-byte
 // reads each; the record of a dead hint is final here, survivors are queued for the warp-per-hint stage.
 __global__ void __launch_bounds__(256)
-prefilter_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, long long n_hints,
+prefilter_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, long long hid0, long long n_hints,
                  QueryParams Q, const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores,
                  int *__restrict__ survivors, int *__restrict__ n_surv) {
-  const long long hid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long hid = hid0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;  // hint slots [hid0, hid0 + n_hints)
   const int lane = threadIdx.x & 31;
   bool survive = false;
-  if (hid < n_hints) {
+  if (hid < hid0 + n_hints) {
     const c2g_hint h = hints[hid];
     c2g_pair_score rec;
     rec.constell[0] = rec.constell[1] = rec.constell[2] = 0;
@@ -1065,14 +1067,14 @@ __device__ void add_proposal(CandState &cs, const double Tp[4], const uint64_t b
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int B, QueryParams Q,
+finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, int q0, int B, QueryParams Q,
                      const c2g_hint *__restrict__ hints, const c2g_pair_score *__restrict__ scores, FinHead *__restrict__ fin_head,
                      FinCand *__restrict__ fin_cand) {
   extern __shared__ __align__(16) unsigned char fsm_raw[];
   FinishScratch &F = *reinterpret_cast<FinishScratch *>(fsm_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = blockIdx.x;  // one query scan per CTA
-  if (q >= B) return;
+  const int q = q0 + blockIdx.x;  // one query scan per CTA
+  if (q >= q0 + B) return;
   const int q_slot = first_slot + q;
   const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
   const c2g_hint *hq = hints + (size_t) q * per_q;
@@ -1226,13 +1228,13 @@ finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__
 
 // tidyUpCandidates' GMM-L2 gate (contour_db.h:553-577): one warp per (query scan, candidate pose)
 __global__ void __launch_bounds__(32)
-finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int B, float lb_correlation,
+finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, float lb_correlation,
                    const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand) {
   __shared__ uint32_t queue[64];
   const int lane = threadIdx.x;
   const int wg = blockIdx.x;  // one warp per CTA: a slot is released as soon as its pose is done (most poses exit at once)
-  const int q = wg / C2G_MAX_CAND, ci = wg % C2G_MAX_CAND;
-  if (q >= B || ci >= fin_head[q].n_before) return;
+  const int q = q0 + wg / C2G_MAX_CAND, ci = wg % C2G_MAX_CAND;
+  if (q >= q0 + B || ci >= fin_head[q].n_before) return;
   FinCand &fc = fin_cand[(size_t) q * C2G_MAX_CAND + ci];
   if (!fc.pass) return;
   const double T[4] = {fc.T[0], fc.T[1], fc.T[2], fc.T[3]};
@@ -1247,12 +1249,12 @@ finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__res
 // is still 0 for every candidate) and the result records; one warp per query scan.  refine.cu optimises the first
 // max_fine_opt records and sorts those by the refined correlation.
 __global__ void __launch_bounds__(128)
-finish_output_kernel(int B, const FinHead *__restrict__ fin_head, const FinCand *__restrict__ fin_cand, c2g_query_result *__restrict__ results) {
+finish_output_kernel(int q0, int B, const FinHead *__restrict__ fin_head, const FinCand *__restrict__ fin_cand, c2g_query_result *__restrict__ results) {
   __shared__ uint32_t ord_s[4][C2G_MAX_CAND];
   __shared__ int n_s[4];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = blockIdx.x * 4 + w;
-  if (q >= B) return;
+  const int q = q0 + blockIdx.x * 4 + w;
+  if (q >= q0 + B) return;
   const FinHead h = fin_head[q];
   const FinCand *fc = fin_cand + (size_t) q * C2G_MAX_CAND;
   if (lane == 0) {
@@ -1320,7 +1322,7 @@ finish_output_kernel(int B, const FinHead *__restrict__ fin_head, const FinCand 
 }
 
 }  // namespace
-int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int B);  // refine.cu
+int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int q0, int B, cudaStream_t st);  // refine.cu
 namespace {
 
 int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &Q) {
@@ -1352,7 +1354,9 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
   return 0;
 }
 
-int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores) {
+// proposal replay -> GMM-L2 gate -> output -> refinement -> ranking for queries [q0, q0 + B) of the batch, on `st`
+int launch_finish(c2g_ctx *ctx, int first_slot, int q0, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores,
+                  cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = sizeof(FinishScratch);
   if (!attr_set) {
@@ -1361,17 +1365,17 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, con
   }
   FinHead *fh = (FinHead *) ctx->d_fin_head;
   FinCand *fcd = (FinCand *) ctx->d_fin_cand;
-  finish_replay_kernel<<<B, FIN_WARPS * 32, smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, B, Q, hints, scores, fh, fcd);
+  finish_replay_kernel<<<B, FIN_WARPS * 32, smem, st>>>(ctx->d_heads, ctx->d_views, first_slot, q0, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 4);
-  finish_corr_kernel<<<B * C2G_MAX_CAND, 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, Q.lb.correlation, fh, fcd);
+  finish_corr_kernel<<<B * C2G_MAX_CAND, 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, Q.lb.correlation, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 5);
-  finish_output_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, fh, fcd, ctx->d_results);
+  finish_output_kernel<<<(B + 3) / 4, 128, 0, st>>>(q0, B, fh, fcd, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 6);
   ctx->launches += 3;
-  return c2g_launch_refine(ctx, first_slot, B);
+  return c2g_launch_refine(ctx, first_slot, q0, B, st);
 }
 
 }  // namespace
@@ -1392,7 +1396,12 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_scores, sizeof(c2g_pair_score) * (size_t) ctx->n_hint_slots));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_results, sizeof(c2g_query_result) * (size_t) ctx->max_batch));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_survivors, sizeof(int) * (size_t) ctx->n_hint_slots));
-  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int)));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int) * C2G_QUERY_STREAMS));
+  for (int i = 0; i < C2G_QUERY_STREAMS; ++i) {
+    C2G_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->qstream[i], cudaStreamNonBlocking));
+    C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_qjoin[i], cudaEventDisableTiming));
+  }
+  C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_qfork, cudaEventDisableTiming));
   C2G_CUDA_TRY(cudaMalloc(&ctx->d_fin_head, sizeof(FinHead) * (size_t) ctx->max_batch));
   C2G_CUDA_TRY(cudaMalloc(&ctx->d_fin_cand, sizeof(FinCand) * (size_t) ctx->max_batch * C2G_MAX_CAND));
   for (int i = 0; i < ctx->db.n_q_levels; ++i) {
@@ -1423,6 +1432,11 @@ void c2g_query_free(c2g_ctx *ctx) {
   cudaFree(ctx->d_results);
   cudaFree(ctx->d_survivors);
   cudaFree(ctx->d_nsurv);
+  for (int i = 0; i < C2G_QUERY_STREAMS; ++i) {
+    if (ctx->qstream[i]) cudaStreamDestroy(ctx->qstream[i]);
+    if (ctx->ev_qjoin[i]) cudaEventDestroy(ctx->ev_qjoin[i]);
+  }
+  if (ctx->ev_qfork) cudaEventDestroy(ctx->ev_qfork);
   cudaFree(ctx->d_fin_head);
   cudaFree(ctx->d_fin_cand);
   for (int i = 0; i < C2G_NUM_Q_LEVELS_MAX; ++i) {
@@ -1605,41 +1619,61 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   }
   QueryParams Q;
   build_query_params(ctx, lb, Q);
-  const int n_keys = B * Q.n_q_levels * C2G_MAX_PIV;
-  C2G_QPROF(ctx, 0);
-  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, first_slot, B, Q, ctx->d_hints);
-  C2G_CUDA_TRY(cudaGetLastError());
-  C2G_QPROF(ctx, 1);
-  const long long n_hints = (long long) n_keys * Q.nnk;
-  C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int), ctx->stream));
-  prefilter_kernel<<<(unsigned) ((n_hints + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, n_hints, Q, ctx->d_hints,
-                                                                               ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
-  C2G_CUDA_TRY(cudaGetLastError());
-  C2G_QPROF(ctx, 2);
-  // thread-per-survivor scoring: the survivor count lives on the device, so the grid covers the worst case sparsely and
-  // strides (about 15 % of the hints survive the prefilter).  C2G_SCORE_WARP=1 selects the warp-per-survivor variant.
-  static const bool warp_variant = getenv("C2G_SCORE_WARP") && atoi(getenv("C2G_SCORE_WARP")) != 0;
-  if (!warp_variant) {
-    const long long want = (n_hints + 127) / 128;
-    const long long cap = (long long) ctx->num_sms * 8;
-    score_thread_kernel<<<(unsigned) (want < cap ? want : cap), 128, 0, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores,
-                                                                                      ctx->d_survivors, ctx->d_nsurv);
-  } else {
-    const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
-    const long long cap = (long long) ctx->num_sms * 16;
-    static bool sc_attr = false;
-    const size_t sc_smem = sizeof(ScoreScratch) * SC_WARPS;
-    if (!sc_attr) {
-      C2G_CUDA_TRY(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem));
-      sc_attr = true;
+  // The batch is cut into sub-batches that run the whole kernel chain on their own streams: most kernels of the chain are
+  // latency-bound (sequential solver / replay logic) and leave issue slots idle that the kernels of the other sub-batch
+  // fill.  C2G_QUERY_SPLIT=1 (or an active c2g_query_profile) keeps everything on the context's stream.
+  static const int split_env = getenv("C2G_QUERY_SPLIT") ? atoi(getenv("C2G_QUERY_SPLIT")) : 4;
+  int n_sub = ctx->prof_on ? 1 : (split_env < 1 ? 1 : (split_env > C2G_QUERY_STREAMS ? C2G_QUERY_STREAMS : split_env));
+  if (B < 2 * n_sub) n_sub = 1;
+  C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int) * C2G_QUERY_STREAMS, ctx->stream));
+  if (n_sub > 1) C2G_CUDA_TRY(cudaEventRecord(ctx->ev_qfork, ctx->stream));
+  const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
+  for (int sb = 0; sb < n_sub; ++sb) {
+    const int q0 = (int) ((long long) B * sb / n_sub), q1 = (int) ((long long) B * (sb + 1) / n_sub), Bs = q1 - q0;
+    cudaStream_t st = n_sub > 1 ? ctx->qstream[sb] : ctx->stream;
+    if (n_sub > 1) C2G_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_qfork, 0));
+    const int n_keys = Bs * Q.n_q_levels * C2G_MAX_PIV;
+    C2G_QPROF(ctx, 0);
+    knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ctx->d_hints);
+    C2G_CUDA_TRY(cudaGetLastError());
+    C2G_QPROF(ctx, 1);
+    const long long hid0 = (long long) q0 * per_q, n_hints = (long long) Bs * per_q;
+    int *surv = ctx->d_survivors + hid0, *nsurv = ctx->d_nsurv + sb;
+    prefilter_kernel<<<(unsigned) ((n_hints + 255) / 256), 256, 0, st>>>(ctx->d_heads, ctx->d_views, first_slot, hid0, n_hints, Q, ctx->d_hints,
+                                                                        ctx->d_scores, surv, nsurv);
+    C2G_CUDA_TRY(cudaGetLastError());
+    C2G_QPROF(ctx, 2);
+    // thread-per-survivor scoring: the survivor count lives on the device, so the grid covers the worst case sparsely and
+    // strides (about 15 % of the hints survive the prefilter).  C2G_SCORE_WARP=1 selects the warp-per-survivor variant.
+    static const bool warp_variant = getenv("C2G_SCORE_WARP") && atoi(getenv("C2G_SCORE_WARP")) != 0;
+    if (!warp_variant) {
+      const long long want = (n_hints + 127) / 128;
+      const long long cap = (long long) ctx->num_sms * 8;
+      score_thread_kernel<<<(unsigned) (want < cap ? want : cap), 128, 0, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores, surv,
+                                                                               nsurv);
+    } else {
+      const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
+      const long long cap = (long long) ctx->num_sms * 16;
+      static bool sc_attr = false;
+      const size_t sc_smem = sizeof(ScoreScratch) * SC_WARPS;
+      if (!sc_attr) {
+        C2G_CUDA_TRY(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem));
+        sc_attr = true;
+      }
+      score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, sc_smem, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores,
+                                                                                      surv, nsurv);
     }
-    score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, sc_smem, ctx->stream>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints,
-                                                                                             ctx->d_scores, ctx->d_survivors, ctx->d_nsurv);
+    C2G_CUDA_TRY(cudaGetLastError());
+    C2G_QPROF(ctx, 3);
+    ctx->launches += 3;
+    int rc = launch_finish(ctx, first_slot, q0, Bs, Q, ctx->d_hints, ctx->d_scores, st);
+    if (rc) return rc;
+    if (n_sub > 1) {
+      C2G_CUDA_TRY(cudaEventRecord(ctx->ev_qjoin[sb], st));
+      C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_qjoin[sb], 0));
+    }
   }
-  C2G_CUDA_TRY(cudaGetLastError());
-  C2G_QPROF(ctx, 3);
-  ctx->launches += 3;
-  return launch_finish(ctx, first_slot, B, Q, ctx->d_hints, ctx->d_scores);
+  return 0;
 }
 
 int c2g_query(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
@@ -1679,7 +1713,7 @@ int c2g_finish_from_scores(c2g_ctx *ctx, int first_slot, int B, const c2g_score_
   if (!ctx || !lb || !hints_dev || !scores_dev || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
   QueryParams Q;
   build_query_params(ctx, lb, Q);
-  int rc = launch_finish(ctx, first_slot, B, Q, (const c2g_hint *) hints_dev, (const c2g_pair_score *) scores_dev);
+  int rc = launch_finish(ctx, first_slot, 0, B, Q, (const c2g_hint *) hints_dev, (const c2g_pair_score *) scores_dev, ctx->stream);
   if (rc) return rc;
   if (results_host) {
     C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDeviceToHost, ctx->stream));

@@ -558,13 +558,13 @@ __device__ RfOut rf_minimize(const Prob &P, const double x0[3]) {
 }
 
 __global__ void __launch_bounds__(RF_WARPS * 32, 5)
-refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int B, int max_fine_opt,
+refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, int max_fine_opt,
               int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results) {
   __shared__ double red[RF_WARPS][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wg = blockIdx.x;  // one (query, candidate rank) per CTA; the exits below are CTA-uniform
+  const int wg = q0 * max_fine_opt + blockIdx.x;  // one (query, candidate rank) per CTA; the exits below are CTA-uniform
   const int q = wg / max_fine_opt, ci = wg % max_fine_opt;
-  if (q >= B) return;
+  if (q >= q0 + B) return;
   c2g_query_result &R = results[q];
   const int pre = min(max_fine_opt, R.n_cand);
   if (ci >= pre) return;
@@ -670,9 +670,9 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
 }
 
 // second std::sort of fineOptimize (contour_db.h:630-636) over the first min(max_fine_opt, n_cand) candidates
-__global__ void rank_kernel(int B, int max_fine_opt, c2g_query_result *__restrict__ results) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= B) return;
+__global__ void rank_kernel(int q0, int B, int max_fine_opt, c2g_query_result *__restrict__ results) {
+  const int q = q0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q0 + B) return;
   c2g_query_result &R = results[q];
   const int pre = min(max_fine_opt, R.n_cand);
   if (pre <= 1) return;
@@ -713,16 +713,16 @@ int c2g_refine_alloc(c2g_ctx *ctx) {
 
 void c2g_refine_free(c2g_ctx *ctx) { cudaFree(ctx->d_pair_scratch); }
 
-int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int B) {
+int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int q0, int B, cudaStream_t st) {
   const int mfo = ctx->db.max_fine_opt;
   if (mfo <= 0) return 0;
-  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, ctx->stream>>>(ctx->d_heads, ctx->d_ells, first_slot, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch,
-                                                            ctx->pair_cap, ctx->d_results);
+  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch, ctx->pair_cap,
+                                                   ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
-  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[7], ctx->stream);
-  rank_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, mfo, ctx->d_results);
+  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[7], st);
+  rank_kernel<<<(B + 127) / 128, 128, 0, st>>>(q0, B, mfo, ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
-  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[8], ctx->stream);
+  if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[8], st);
   ctx->launches += 2;
   return 0;
 }
