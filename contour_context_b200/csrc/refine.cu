@@ -24,7 +24,8 @@ namespace {
 
 __device__ const uint64_t rf_exp_tab[256] = C2G_EXP_TAB_INIT;
 
-constexpr int RF_WARPS = 4;  // warps per candidate (one CTA each): the pair terms of one evaluation are split over 128 lanes, which
+constexpr int RF_MAX_WARPS = 4;
+constexpr int RF_WARPS = 2;  // default warps per candidate (measured best of 1..4: 1.41 / 1.18 / 1.27 / 1.41 ms per 592-query batch) (one CTA each): the pair terms of one evaluation are split over 128 lanes, which
                              // shortens the sequential evaluation chain of the long problems that set the kernel's makespan
 
 // value + gradient of the cost at one point
@@ -37,7 +38,7 @@ struct Prob {
   const c2g_ell *se, *te;  // ellipse tables of the candidate (src) and the query (tgt) scan, indexed like their views
   const uint32_t *pairs;   // this warp's share of the pre-selected pairs: (src view index << 16) | tgt view index
   double (*red)[4];        // [RF_WARPS][4] shared-memory slots of the block reduction
-  int n_pairs, exp_mode, lane, warp;
+  int n_pairs, exp_mode, lane, warp, n_warps;
 };
 
 // GMMPair::operator() (correlation.h:125-152) and its gradient; all threads of the CTA call, all get the same result
@@ -102,8 +103,7 @@ __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
   g0 = P.red[0][1];
   g1 = P.red[0][2];
   g2 = P.red[0][3];
-#pragma unroll
-  for (int w = 1; w < RF_WARPS; ++w) {
+  for (int w = 1; w < P.n_warps; ++w) {
     fa += P.red[w][0];
     g0 += P.red[w][1];
     g1 += P.red[w][2];
@@ -557,10 +557,11 @@ __device__ RfOut rf_minimize(const Prob &P, const double x0[3]) {
   return R;
 }
 
-__global__ void __launch_bounds__(RF_WARPS * 32, 5)
+__global__ void __launch_bounds__(RF_MAX_WARPS * 32, 5)
 refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, int max_fine_opt,
               int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results) {
-  __shared__ double red[RF_WARPS][4];
+  __shared__ double red[RF_MAX_WARPS][4];
+  const int n_warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wg = q0 * max_fine_opt + blockIdx.x;  // one (query, candidate rank) per CTA; the exits below are CTA-uniform
   const int q = wg / max_fine_opt, ci = wg % max_fine_opt;
@@ -571,7 +572,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   c2g_cand &C = R.cand[ci];
   const int src = C.cand_gidx, tgt = first_slot + q;
   const double T[4] = {C.T[0], C.T[1], C.T[2], C.T[3]};
-  const int warp_cap = pair_cap / RF_WARPS;
+  const int warp_cap = pair_cap / n_warps;
   uint32_t *pairs = pair_scratch + (size_t) wg * pair_cap + (size_t) warp * warp_cap;
   // (staging both ellipse tables in shared memory was measured 30 % slower: 32-byte records at random indices conflict on the
   // banks, while the 32-byte sectors are served well by L1)
@@ -595,7 +596,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
         byf = b.my;
         bmaj = b.maj;
       }
-      for (int si = warp; si < ns; si += RF_WARPS) {
+      for (int si = warp; si < ns; si += n_warps) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
         const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
@@ -618,7 +619,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
         n_pairs += __popc(m);
       }
     } else {
-      for (int si = warp; si < ns; si += RF_WARPS) {
+      for (int si = warp; si < ns; si += n_warps) {
         const c2g_ell a = se[so + si];
         const double ax = (double) a.mx, ay = (double) a.my;
         const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
@@ -648,6 +649,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   Prob P;
   P.red = red;
   P.warp = warp;
+  P.n_warps = n_warps;
   P.se = se;
   P.te = te;
   P.pairs = pairs;
@@ -716,7 +718,8 @@ void c2g_refine_free(c2g_ctx *ctx) { cudaFree(ctx->d_pair_scratch); }
 int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int q0, int B, cudaStream_t st) {
   const int mfo = ctx->db.max_fine_opt;
   if (mfo <= 0) return 0;
-  refine_kernel<<<B * mfo, RF_WARPS * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch, ctx->pair_cap,
+  static const int rf_warps = getenv("C2G_REFINE_WARPS") ? max(1, min(RF_MAX_WARPS, atoi(getenv("C2G_REFINE_WARPS")))) : RF_WARPS;
+  refine_kernel<<<B * mfo, rf_warps * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch, ctx->pair_cap,
                                                    ctx->d_results);
   C2G_CUDA_TRY(cudaGetLastError());
   if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[7], st);
