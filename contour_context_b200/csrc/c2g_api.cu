@@ -18,7 +18,9 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        uint16_t *cell_lists, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg);
+                        unsigned char *k2_scratch, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg);
+int c2g_contour_max_ctas(int num_sms);
+size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row);
 int c2g_query_alloc(c2g_ctx *ctx);
 void c2g_query_free(c2g_ctx *ctx);
 int c2g_refine_alloc(c2g_ctx *ctx);  // refine.cu
@@ -31,6 +33,7 @@ int make_params(const c2g_cm_config &cfg, C2gIngestParams &P) {
   if (cfg.n_row <= 0 || cfg.n_col <= 0 || cfg.n_row * cfg.n_col > C2G_MAX_CELLS) return C2G_ERR_ARG;
   if (cfg.n_row % 2 || cfg.n_col % 2) return C2G_ERR_ARG;  // CHECK in contour_mng.h:479-480
   if (cfg.n_row > 255 || cfg.n_col > 255) return C2G_ERR_ARG;
+  if (cfg.n_row * ((cfg.n_col + 31) / 32) > 800) return C2G_ERR_ARG;  // bit-plane capacity of the contour kernel (150 x 5 = 750)
   if (cfg.piv_firsts < 0 || cfg.piv_firsts > C2G_MAX_PIV) return C2G_ERR_ARG;
   if (cfg.dist_firsts < 0 || cfg.dist_firsts > C2G_MAX_DIST_FIRSTS) return C2G_ERR_ARG;
   if (!(cfg.roi_radius > 0.0f) || cfg.roi_radius > 10.0f) return C2G_ERR_ARG;  // key window list capacity
@@ -180,13 +183,21 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ALLOC(ctx->d_bev_h, sizeof(float) * ncell * max_batch);
   ALLOC(ctx->d_bev_rf, sizeof(float) * ncell * max_batch);
   ALLOC(ctx->d_bev_cf, sizeof(float) * ncell * max_batch);
-  ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) ctx->num_sms);
+  ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) c2g_contour_max_ctas(ctx->num_sms));
   ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_ells, sizeof(c2g_ell) * C2G_VIEW_CAP * (size_t) scan_capacity);
   ALLOC(ctx->d_dbg, sizeof(long long) * 64);
   ALLOC(ctx->d_work_counter, sizeof(int));
-  ALLOC(ctx->d_cell_lists, sizeof(uint16_t) * C2G_NLEV * ncell * (size_t) ctx->num_sms);
+  {
+    const size_t k2b = c2g_contour_scratch_bytes(ctx->num_sms, ctx->P.n_cells, ctx->P.cfg.n_row);
+    ALLOC(ctx->d_k2_scratch, k2b);
+    e = cudaMemset(ctx->d_k2_scratch, 0, k2b);  // the arena locks start free
+    if (e != cudaSuccess) {
+      c2g_destroy(ctx);
+      return -(int) e;
+    }
+  }
 #undef ALLOC
   rc = c2g_query_alloc(ctx);
   if (!rc) rc = c2g_refine_alloc(ctx);
@@ -231,7 +242,7 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_ells);
   cudaFree(ctx->d_dbg);
   cudaFree(ctx->d_work_counter);
-  cudaFree(ctx->d_cell_lists);
+  cudaFree(ctx->d_k2_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
@@ -289,7 +300,7 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     if (rc) return rc;
     rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0,
                              ctx->d_bev_h + ncell * b0, ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads,
-                             ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                             ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
   }
@@ -311,7 +322,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
   int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
   if (rc) return rc;
   rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_cell_lists, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
+                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;

@@ -47,7 +47,7 @@ struct c2g_ctx {
   c2g_ell *d_ells;           // [scan_cap][C2G_VIEW_CAP], same indexing as d_views
   long long *d_dbg;
   int *d_work_counter;     // next scan of the running contour_kernel launch
-  uint16_t *d_cell_lists;  // per resident CTA: member cells of every component, level by level
+  unsigned char *d_k2_scratch;  // contour kernel: per resident CTA key-window lists + overflow arenas (contours.cu)
   const float *last_pts;
   int last_B;
   long long launches;

@@ -1,6 +1,6 @@
 // contours.cu — K2: BEV tile -> multi-level contours -> ContourView statistics -> per-level order -> retrieval keys ->
-// BCIs -> per-scan GMM terms.  One persistent CTA per SM, one scan per CTA iteration, everything between the BEV tile and
-// the finished descriptor stays in shared memory / L2.
+// BCIs -> per-scan GMM terms.  Persistent CTAs of 384 threads, TWO resident per SM (<= 113 KB of shared memory each), one
+// scan per CTA iteration; everything between the BEV tile and the finished descriptor stays in shared memory / L1 / L2.
 //
 // Reference functions restated here (paths relative to the reference repo):
 //   ContourManager::makeContourRecursiveHelper   src/cont2/contour_mng.cpp:274-353
@@ -11,15 +11,24 @@
 //
 // How the recursion becomes data-parallel: a level-(L+1) component is a connected component of {bev > lv[L+1]} and is
 // contained in exactly one level-L component, so a GLOBAL 8-connected labelling per level finds the same pixel sets as
-// the reference's recursive ROI-by-ROI labelling.  What the recursion adds is ORDER: cont_views_[L] is filled in DFS
-// order, children of one parent in OpenCV label order, which is the block-raster order of each component's first 2x2
-// block with blocks aligned to the parent's bounding-box origin (SURVEY.md §7 hard part 2).  Hence
+// the reference's recursive ROI-by-ROI labelling, and the six labellings are independent of each other.  What the
+// recursion adds is ORDER: cont_views_[L] is filled in DFS order, children of one parent in OpenCV label order, which is
+// the block-raster order of each component's first 2x2 block with blocks aligned to the parent's bounding-box origin
+// (SURVEY.md §7 hard part 2).  Hence
 //   order(level L) = sort by (rank of parent in level L-1, min over pixels of ((r-y0)>>1, (c-x0)>>1)).
-// Per-pixel label words pack (rank of the enclosing level-(L-1) component) << 16 | union-find parent pixel, so one native
-// 32-bit shared atomicMin implements the union (all words of one tree share the upper half).
+//
+// Data structures (round 1e): the thresholded image of every level is a bit-plane (one 32-bit word per 32 columns of a
+// row, built with warp ballots while the tile is decoded); the union-find runs over horizontal RUNS of set bits, not
+// over pixels (a 150 x 150 KITTI BEV has ~1 400 foreground cells but only ~600 runs and ~80 components per level).  One
+// warp labels one level (six levels at once, no block barrier inside), runs are numbered in raster order so that
+//   * the smallest run id of a component is its first pixel in raster order (the root of min-linking union-find),
+//   * the largest run id ends in the component's last pixel (ContourView::poi),
+//   * walking a component's runs in id order visits its cells in the reference's accumulation order (bbox-raster order
+//     restricted to members == raster order of members).
+// Per-component statistics are reduced inside the warp (__match_any_sync + redux) and kept in 16-byte records.
 //
 // Bit-exactness rules: float/double sums that feed views and keys are accumulated in the reference's raster order by a
-// single logical accumulator (warp-redundant), never by tree reductions; compiled with -fmad=false.
+// single logical accumulator, never by tree reductions; compiled with -fmad=false.
 #include <math_constants.h>
 
 #include "c2g_common.cuh"
@@ -31,82 +40,110 @@ namespace {
 // glibc's __exp_data.tab (2 KB, read through L1); see c2g_libm.cuh
 __device__ const uint64_t c2g_exp_tab_dev[256] = C2G_EXP_TAB_INIT;
 
-constexpr int K2_THREADS = 1024;
+constexpr int K2_THREADS = 384;
 constexpr int K2_WARPS = K2_THREADS / 32;
-constexpr int NC = 2048;        // components (any size) per level
-constexpr int NVL = 1024;       // significant components (area >= min_cont_cell_cnt) per level
-constexpr int KEY_LIST_CAP = 400;  // cells of one key window that can lie inside the 9.99-cell radius
+constexpr int K2_CTAS_PER_SM = 2;
+constexpr int PLANE_WORDS = 800;  // n_row * ceil(n_col / 32) (checked by make_params): 150 x 5 = 750 for both shipped configs
+constexpr int WCHUNK = 5;         // 32-column words of a row decoded per batch in phase A
+constexpr int R_POOL = 5120;      // runs of all six levels that fit in shared memory (else: global arena)
+constexpr int C_POOL = 1536;      // components of all six levels that fit in shared memory (else: global arena)
+constexpr int NVL = 1024;         // significant components (area >= min_cont_cell_cnt) per level
+constexpr int KEY_LIST_CAP = 400; // cells of one key window that can lie inside the 9.99-cell radius
 constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
 constexpr int N_DIVS = 35;
-constexpr int WL_CAP = 256;
+constexpr int N_ARENAS = 8;
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct TopView {  // what keys / BCI / GMM need from a sorted view
   float mean0, mean1, eig0, eig1;
   int cnt;
 };
 
-struct Smem {
-  uint32_t L[C2G_MAX_CELLS];      // label words; reused as scratch after the level loop
-  uint8_t msk[C2G_MAX_CELLS + 28];  // bit e: bev > lv_grads[e]
-  int c_area[NC], c_minr[NC], c_minc[NC], c_maxr[NC], c_maxc[NC], c_key[NC], c_poi[NC];
-  uint16_t c_rank[NC], c_pcid[NC];
-  uint16_t sig_slot[NVL], order[NVL];
-  uint32_t sig_key[NVL];
-  uint8_t px0[NVL], py0[NVL];          // bbox origin of the previous level's components, by rank
-  uint32_t sortbuf[C2G_VIEW_CAP];      // (cell_cnt << 16 | presort index), all levels back to back
-  int n_views[C2G_NLEV], view_off[C2G_NLEV], layer_cnt[C2G_NLEV];
-  TopView top[C2G_NLEV][C2G_MAX_DIST_FIRSTS];
-  float divs[N_ANCH][N_DIVS];
-  int cnt_point[N_ANCH];
-  int ncomp, nsig, status, n_occ;
-  double red[K2_WARPS];
-  uint32_t t_off[C2G_VIEW_CAP];   // offset of every component's member-cell list in the CTA's global scratch
-  uint16_t t_poi[C2G_VIEW_CAP], t_cnt[C2G_VIEW_CAP], torder[C2G_VIEW_CAP];
-  int bucket_cnt[16], wq;
+// One connected component of one level. `root` / `last`: first / last run (level-local run ids, raster order).
+struct __align__(16) Comp {
+  uint16_t area, last, root, key, pcomp, rank;
+  uint8_t minc, maxc, y0, x0;  // y0, x0: bounding-box origin of the enclosing component of the previous level
 };
+static_assert(sizeof(Comp) == 16, "Comp layout");
 
-__device__ __forceinline__ uint32_t uf_find(volatile uint32_t *L, uint32_t c) {
-  uint32_t w = L[c];
-  uint32_t p = w & 0xFFFFu;
+struct Smem {
+  uint32_t plane[C2G_NLEV][PLANE_WORDS];  // bit (c & 31) of word r * WPR + (c >> 5): bev(r, c) > lv_grads[level]
+  union {
+    uint16_t wpre[C2G_NLEV][PLANE_WORDS];  // number of runs that start before this word (labelling, parent lookup)
+    struct {
+      uint32_t key[NVL];   // (rank of the parent << 16) | first-2x2-block key
+      uint16_t comp[NVL];
+    } sig;                 // ranking step
+  };
+  union {
+    uint32_t run_par[R_POOL];  // union-find parent (run id); after the flatten: root id, or 0x80000000 | component for roots
+    unsigned char bci_scratch[K2_WARPS * 736];
+  };
+  union {
+    uint32_t run_inf[R_POOL];  // row | c0 << 8 | len << 16 | (distance to the next run of the same component, 255 = search) << 24
+    float divs[N_ANCH][N_DIVS];
+  };
+  Comp comp[C_POOL];
+  uint32_t sortbuf[C2G_VIEW_CAP];  // (cell_cnt << 16 | presort index), all levels back to back
+  uint16_t vcomp[C2G_VIEW_CAP];    // level-local component of every presort view
+  int n_views[C2G_NLEV], view_off[C2G_NLEV], layer_cnt[C2G_NLEV];
+  int n_runs[C2G_NLEV], run_off[C2G_NLEV], n_comp[C2G_NLEV], comp_off[C2G_NLEV];
+  TopView top[C2G_NLEV][C2G_MAX_DIST_FIRSTS];
+  int cnt_point[N_ANCH];
+  int n_ell[C2G_NUM_BIN_LAYERS];
+  int nsig, status, n_occ, wq, next_scan;
+  int runs_in_arena, comps_in_arena, arena;  // arena: index of the claimed global arena, -1 = none
+  double red[K2_WARPS];
+};
+static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs per SM");
+
+// ---- union-find over run ids (links only go from a larger to a smaller id) ------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(volatile uint32_t *P, uint32_t c) {
+  uint32_t p = P[c];
   while (p != c) {
-    const uint32_t gp = L[p] & 0xFFFFu;
-    if (gp != p) L[c] = (w & 0xFFFF0000u) | gp;  // path halving: any ancestor is a valid parent (links only go down)
+    const uint32_t gp = P[p];
+    if (gp != p) P[c] = gp;  // path halving: any ancestor is a valid parent
     c = p;
-    w = L[c];
-    p = w & 0xFFFFu;
+    p = gp;
   }
   return c;
 }
-// read-only variant for the flatten phase: there every thread stores the final root into its OWN cells, and a path-halving
-// store from another thread could overwrite that root with a stale ancestor
-__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t *L, uint32_t c) {
-  uint32_t p = L[c] & 0xFFFFu;
+// read-only variant for the flatten: there every lane stores the final root into its OWN entry, and a path-halving store
+// from another lane could overwrite that root with a stale ancestor
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t *P, uint32_t c) {
+  uint32_t p = P[c];
   while (p != c) {
     c = p;
-    p = L[c] & 0xFFFFu;
+    p = P[c];
   }
   return c;
 }
-__device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void uf_union(uint32_t *P, uint32_t a, uint32_t b) {
   while (true) {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
+    a = uf_find(P, a);
+    b = uf_find(P, b);
     if (a == b) return;
     if (a < b) {
-      uint32_t t = a;
+      const uint32_t t = a;
       a = b;
       b = t;
     }
-    const uint32_t hi = ((volatile uint32_t *) L)[a] & 0xFFFF0000u;
-    const uint32_t old = atomicMin(&L[a], hi | b);
-    if ((old & 0xFFFFu) == a) return;
-    a = old & 0xFFFFu;
+    const uint32_t old = atomicMin(&P[a], b);
+    if (old == a) return;
+    a = old;
   }
 }
-__device__ __forceinline__ int slot_of(const uint32_t *L, int c) {
-  uint32_t low = L[c] & 0xFFFFu;
-  if (!(low & 0x8000u)) low = L[low] & 0xFFFFu;
-  return (int) (low & 0x7FFFu);
+// component of a run once the roots carry 0x80000000 | component
+__device__ __forceinline__ uint32_t comp_of(const uint32_t *P, uint32_t id) {
+  uint32_t v = P[id];
+  if (!(v & 0x80000000u)) v = P[v];
+  return v & 0x7FFFFFFFu;
+}
+// bits of word `wi` of a plane row where a horizontal run starts
+__device__ __forceinline__ uint32_t run_starts(const uint32_t *row_words, int wi) {
+  const uint32_t bits = row_words[wi];
+  const uint32_t prev = wi ? (row_words[wi - 1] >> 31) : 0u;
+  return bits & ~((bits << 1) | prev);
 }
 
 // ---- Eigen::SelfAdjointEigenSolver<Matrix2f> (Eigen 3.3.7 iterative path), device restatement ----------------------
@@ -265,26 +302,38 @@ __device__ __forceinline__ void manual_cov(const float ev[2], const float vec[4]
   out[3] = vd10 * vec[1] + vd11 * vec[3];
 }
 
-__global__ void __launch_bounds__(K2_THREADS, 1)
+// per-CTA slice of the global scratch: key-window lists of phase D (distance f32 + higher-level count u8 per listed cell)
+constexpr size_t KLIST_BYTES = ((size_t) N_ANCH * KEY_LIST_CAP * 5 + 255) / 256 * 256;
+
+__host__ __device__ inline int arena_level_cap(int n_cells, int n_row) { return n_cells / 2 + n_row; }  // runs (>= components) of one level
+__host__ __device__ inline size_t arena_bytes(int n_cells, int n_row) {
+  return (size_t) C2G_NLEV * arena_level_cap(n_cells, n_row) * (4 + 4 + sizeof(Comp));
+}
+
+__global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM)
 contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
                int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
-               uint16_t *__restrict__ cell_lists, int *__restrict__ work_counter, long long *__restrict__ dbg) {
+               unsigned char *__restrict__ klist_scratch, int *__restrict__ arena_locks, unsigned char *__restrict__ arenas,
+               int *__restrict__ work_counter, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncell = P.n_cells, ncol = P.cfg.n_col, nrow = P.cfg.n_row;
+  const int WPR = (ncol + 31) >> 5, nwords = nrow * WPR;
   const c2g_cm_config &cfg = P.cfg;
   c2g_view *const presort = presort_scratch + (size_t) blockIdx.x * C2G_VIEW_CAP;
+  float *const klist_dist = reinterpret_cast<float *>(klist_scratch + (size_t) blockIdx.x * KLIST_BYTES);  // [N_ANCH][KEY_LIST_CAP]
+  uint8_t *const klist_hc = reinterpret_cast<uint8_t *>(klist_dist + N_ANCH * KEY_LIST_CAP);               // [N_ANCH][KEY_LIST_CAP]
+  const int ARL = arena_level_cap(ncell, nrow);
 
   // scans are handed out dynamically (their cost varies 2x with the scene, and a CTA that starts late - e.g. behind a
   // co-running collective - must not leave a static share of the batch unprocessed until the end)
-  __shared__ int next_scan;
   while (true) {
-    if (tid == 0) next_scan = atomicAdd(work_counter, 1);
+    if (tid == 0) S.next_scan = atomicAdd(work_counter, 1);
     __syncthreads();
-    const int b = next_scan;
+    const int b = S.next_scan;
     if (b >= B) break;
     const size_t cbase = (size_t) b * ncell;
     const float *hg = bev_h + cbase, *rfg = bev_rf + cbase, *cfp = bev_cf + cbase;
@@ -294,444 +343,451 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
 
 #define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0) dbg[i] = clock64(); } while (0)
     C2G_DBG(0);
-    // ---------------- phase A: decode the tile, gather the winner's continuous coordinates -------------------------
+    // ---------------- phase A: decode the tile, gather the winner's continuous coordinates, build the bit-planes ------
     if (tid == 0) {
       S.status = 0;
       S.n_occ = 0;
+      S.arena = -1;
+      S.runs_in_arena = 0;
+      S.comps_in_arena = 0;
     }
     __syncthreads();
     {
       const float4 *p = pts + offsets[b];
       int occ = 0;
-      constexpr int PA = 6;  // cells per thread per batch: all tile loads, then all gathers, then the stores
-      for (int c0 = tid; c0 < ncell; c0 += K2_THREADS * PA) {
-        c2g_cellkey k[PA];
-        float2 xy[PA];
+      for (int r = warp; r < nrow; r += K2_WARPS) {
+        const size_t rbase = cbase + (size_t) r * ncol;
+        for (int u0 = 0; u0 < WPR; u0 += WCHUNK) {
+          c2g_cellkey k[WCHUNK];
+          float2 xy[WCHUNK];
 #pragma unroll
-        for (int u = 0; u < PA; ++u) {
-          const int c = c0 + u * K2_THREADS;
-          k[u] = c < ncell ? tiles[cbase + c] : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < PA; ++u) {
-          xy[u] = make_float2(0.f, 0.f);
-          if (k[u] != 0ull) xy[u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[u]));
-        }
-#pragma unroll
-        for (int u = 0; u < PA; ++u) {
-          const int c = c0 + u * K2_THREADS;
-          if (c >= ncell) continue;
-          float h = -1000.0f, rf = -1.0f, cf = -1.0f;
-          uint8_t m = 0;
-          if (k[u] != 0ull) {
-            h = c2g_from_orderable((uint32_t) (k[u] >> 32));
-            // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
-            rf = (xy[u].x / cfg.reso_row + P.half_row_f) - 0.5f;
-            cf = (xy[u].y / cfg.reso_col + P.half_col_f) - 0.5f;
-#pragma unroll
-            for (int e = 0; e < C2G_NLEV; ++e) m |= (h > cfg.lv_grads[e]) ? (1u << e) : 0u;
-            occ++;
+          for (int u = 0; u < WCHUNK; ++u) {
+            const int c = (u0 + u) * 32 + lane;
+            k[u] = c < ncol ? tiles[rbase + c] : 0ull;
           }
-          bev_h[cbase + c] = h;
-          bev_rf[cbase + c] = rf;
-          bev_cf[cbase + c] = cf;
-          S.msk[c] = m;
-          S.L[c] = 0u;
+#pragma unroll
+          for (int u = 0; u < WCHUNK; ++u) {
+            xy[u] = make_float2(0.f, 0.f);
+            if (k[u] != 0ull) xy[u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < WCHUNK; ++u) {
+            const int c = (u0 + u) * 32 + lane;
+            float h = -1000.0f, rf = -1.0f, cf = -1.0f;
+            const bool has = k[u] != 0ull;
+            if (has) {
+              h = c2g_from_orderable((uint32_t) (k[u] >> 32));
+              // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
+              rf = (xy[u].x / cfg.reso_row + P.half_row_f) - 0.5f;
+              cf = (xy[u].y / cfg.reso_col + P.half_col_f) - 0.5f;
+            }
+            if (c < ncol) {
+              bev_h[rbase + c] = h;
+              bev_rf[rbase + c] = rf;
+              bev_cf[rbase + c] = cf;
+            }
+            occ += __popc(__ballot_sync(FULL, has));
+            uint32_t mine = 0;
+#pragma unroll
+            for (int e = 0; e < C2G_NLEV; ++e) {
+              const uint32_t bal = __ballot_sync(FULL, has && h > cfg.lv_grads[e]);
+              if (lane == e) mine = bal;
+            }
+            if (lane < C2G_NLEV && u0 + u < WPR) S.plane[lane][r * WPR + u0 + u] = mine;
+          }
         }
       }
-      for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(0xFFFFFFFFu, occ, o);
-      if (lane == 0 && occ) atomicAdd(&S.n_occ, occ);  // one same-address shared atomic per warp, not per thread
+      if (lane == 0 && occ) atomicAdd(&S.n_occ, occ);  // one same-address shared atomic per warp
     }
     __syncthreads();
-
     C2G_DBG(1);
-    // ---------------- phase B: levels ------------------------------------------------------------------------------
-    // Every thread owns a contiguous chunk of <= 32 cells and keeps, per level, the bitmask of its foreground cells in a
-    // register: the per-level passes below visit set bits only (a few percent of the BEV is above any threshold).
-    const int chunk = (ncell + K2_THREADS - 1) / K2_THREADS;
-    const int cb0 = tid * chunk, cb1 = min(ncell, cb0 + chunk);
-    const int r_first = cb0 / ncol, c_first = cb0 - r_first * ncol;
-    uint32_t mk[C2G_NLEV];
-    uint32_t rowst = 0;  // cells of the chunk that sit in column 0 (a horizontal run cannot continue across them)
-    {
-#pragma unroll
-      for (int l = 0; l < C2G_NLEV; ++l) mk[l] = 0;
-      int col = c_first;
-      for (int k = 0; cb0 + k < cb1; ++k) {
-        const uint32_t m = S.msk[cb0 + k];
-#pragma unroll
-        for (int l = 0; l < C2G_NLEV; ++l) mk[l] |= ((m >> l) & 1u) << k;
-        if (col == 0) rowst |= 1u << k;
-        if (++col == ncol) col = 0;
-      }
-    }
-    uint16_t *const lists = cell_lists + (size_t) blockIdx.x * C2G_NLEV * ncell;  // per-CTA scratch: member cells per component
-    int total_views = 0;
-    for (int lev = 0; lev < C2G_NLEV; ++lev) {
-      const uint8_t bit = (uint8_t) (1u << lev);
-      const uint32_t bits = mk[lev];
-      const uint32_t starts = bits & (~(bits << 1) | rowst);  // first cell of every horizontal run inside the chunk
-      if (tid == 0) {
-        S.ncomp = 0;
-        S.nsig = 0;
-      }
-      // B1 label words: upper half keeps the rank of the enclosing component of the previous level, lower half links every
-      // cell straight to the first cell of its run
-      for (uint32_t bb = bits; bb; bb &= bb - 1) {
-        const int k = __ffs(bb) - 1;
-        const int rs = 31 - __clz(starts & ((2u << k) - 1u));
-        S.L[cb0 + k] = (S.L[cb0 + k] & 0xFFFF0000u) | (uint32_t) (cb0 + rs);
-      }
-      __syncthreads();
-      C2G_DBG(10 + lev * 8 + 0);
-      // B2 unions. W: only where a run was cut by the chunk boundary. Row above: N if set (NW/NE then belong to N's run);
-      // otherwise NW and NE. A cell whose W neighbour is set skips what W already did (its N/NE are this cell's NW/N).
-      for (uint32_t bb = bits; bb; bb &= bb - 1) {
-        const int k = __ffs(bb) - 1;
-        const int c = cb0 + k;
-        int r = r_first, cc = c_first + k;
-        while (cc >= ncol) {
-          cc -= ncol;
-          ++r;
+
+    // ---------------- phase B: six independent run-based labellings, one warp per level -------------------------------
+    const int lev_w = warp;  // level of this warp in the per-level phases (warps >= C2G_NLEV wait at the barriers)
+    if (warp < C2G_NLEV) {
+      // B1 runs per word -> exclusive prefix (run ids are raster order)
+      const uint32_t *pl = S.plane[lev_w];
+      int base = 0;
+      for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int w = w0 + lane;
+        int cnt = 0;
+        if (w < nwords) {
+          const int row = w / WPR;
+          cnt = __popc(run_starts(pl + row * WPR, w - row * WPR));
         }
-        const bool w_set = cc > 0 && (k > 0 ? ((bits >> (k - 1)) & 1u) : (S.msk[c - 1] & bit));
-        if (w_set && k == 0) uf_union(S.L, c, c - 1);
-        if (r > 0) {
-          const int up = c - ncol;
-          const bool n_set = (S.msk[up] & bit) != 0;
-          const bool ne_set = cc + 1 < ncol && (S.msk[up + 1] & bit);
-          if (!w_set) {
-            if (n_set)
-              uf_union(S.L, c, up);
-            else {
-              if (cc > 0 && (S.msk[up - 1] & bit)) uf_union(S.L, c, up - 1);
-              if (ne_set) uf_union(S.L, c, up + 1);
-            }
-          } else if (!n_set && ne_set)
-            uf_union(S.L, c, up + 1);
-        }
-      }
-      __syncthreads();
-      C2G_DBG(10 + lev * 8 + 1);
-      // B3 flatten, phase 1: compressing finds (path halving) on the run starts shorten every chain; no cell is finalised yet,
-      // so a halving store can never clobber a final root
-      for (uint32_t sb = starts; sb; sb &= sb - 1) (void) uf_find(S.L, cb0 + __ffs(sb) - 1);
-      __syncthreads();
-      // phase 2: one read-only find per run (now a hop or two), the whole run takes that root
-      for (uint32_t sb = starts; sb; sb &= sb - 1) {
-        const int k0 = __ffs(sb) - 1;
-        const uint32_t root = uf_find_ro(S.L, cb0 + k0);
-        const uint32_t run = ((bits >> k0) + 1u == 0u) ? 0xFFFFFFFFu : (((bits >> k0) ^ ((bits >> k0) + 1u)) >> 1);  // low ones of bits>>k0
-        uint32_t rb = run;
-        const uint32_t nxt = (starts >> k0) & ~1u;  // a row start inside the run splits it
-        if (nxt) rb &= (nxt & (0u - nxt)) - 1u;
-        for (; rb; rb &= rb - 1) {
-          const int c = cb0 + k0 + __ffs(rb) - 1;
-          S.L[c] = (S.L[c] & 0xFFFF0000u) | root;
-        }
-      }
-      __syncthreads();
-      C2G_DBG(10 + lev * 8 + 2);
-      // B4 roots -> table slots. A root is the smallest cell index of its component, hence a run start. One shared-memory
-      // atomic per warp (same-address atomics serialise).
-      {
-        int nroot = 0;
-        for (uint32_t sb = starts; sb; sb &= sb - 1) {
-          const int c = cb0 + __ffs(sb) - 1;
-          if ((S.L[c] & 0xFFFFu) == (uint32_t) c) ++nroot;
-        }
-        int incl = nroot;
+        int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          const int t = __shfl_up_sync(FULL, incl, o);
           if (lane >= o) incl += t;
         }
-        int base = 0;
-        if (lane == 31 && incl > 0) base = atomicAdd(&S.ncomp, incl);
-        base = __shfl_sync(0xFFFFFFFFu, base, 31);
-        int slot_next = base + incl - nroot;
-        if (nroot > 0)
-          for (uint32_t sb = starts; sb; sb &= sb - 1) {
-            const int c = cb0 + __ffs(sb) - 1;
-            if ((S.L[c] & 0xFFFFu) != (uint32_t) c) continue;
-            int slot = slot_next++;
-            if (slot < NC) {
-              S.c_area[slot] = 0;
-              S.c_minr[slot] = 1 << 20;
-              S.c_minc[slot] = 1 << 20;
-              S.c_maxr[slot] = -1;
-              S.c_maxc[slot] = -1;
-              S.c_key[slot] = 1 << 30;
-              S.c_poi[slot] = -1;
-              S.c_pcid[slot] = (uint16_t) (S.L[c] >> 16);
-              S.c_rank[slot] = 0xFFFFu;
-            } else {
-              slot = 0x7FFF;
-              atomicOr(&S.status, 2);
-            }
-            S.L[c] = (S.L[c] & 0xFFFF0000u) | 0x8000u | (uint32_t) slot;
-          }
+        if (w < nwords) S.wpre[lev_w][w] = (uint16_t) (base + incl - cnt);
+        base += __shfl_sync(FULL, incl, 31);
       }
-      __syncthreads();
-      C2G_DBG(10 + lev * 8 + 3);
-      // B5 per-component area / bbox / first-2x2-block key / last pixel: one flush per horizontal run of the chunk
-      for (uint32_t sb = starts; sb; sb &= sb - 1) {
-        const int k0 = __ffs(sb) - 1;
-        uint32_t run = ((bits >> k0) + 1u == 0u) ? 0xFFFFFFFFu : (((bits >> k0) ^ ((bits >> k0) + 1u)) >> 1);
-        const uint32_t nxt = (starts >> k0) & ~1u;
-        if (nxt) run &= (nxt & (0u - nxt)) - 1u;
-        const int len = __popc(run);
-        const int c = cb0 + k0;
-        int r = r_first, cc = c_first + k0;
-        while (cc >= ncol) {
-          cc -= ncol;
-          ++r;
+      if (lane == 0) S.n_runs[lev_w] = base;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int l = 0; l < C2G_NLEV; ++l) {
+        S.run_off[l] = tot;
+        tot += S.n_runs[l];
+      }
+      if (tot > R_POOL) {  // rare: the run tables of this scan live in a global arena (claimed until the scan is done)
+        int a = blockIdx.x % N_ARENAS;
+        while (atomicCAS(&arena_locks[a], 0, 1) != 0) {
+          a = (a + 1) % N_ARENAS;
+          __nanosleep(200);
         }
-        const int cur = slot_of(S.L, c);
-        if (cur == 0x7FFF) continue;
-        atomicAdd(&S.c_area[cur], len);
-        atomicMin(&S.c_minr[cur], r);
-        atomicMax(&S.c_maxr[cur], r);
-        atomicMin(&S.c_minc[cur], cc);
-        atomicMax(&S.c_maxc[cur], cc + len - 1);
-        const int pc = S.c_pcid[cur];
-        const int x0 = lev ? (int) S.px0[pc & (NVL - 1)] : 0, y0 = lev ? (int) S.py0[pc & (NVL - 1)] : 0;
-        atomicMin(&S.c_key[cur], ((r - y0) >> 1) * 128 + ((cc - x0) >> 1));
-        atomicMax(&S.c_poi[cur], c + len - 1);
+        S.arena = a;
+        S.runs_in_arena = 1;
+        for (int l = 0; l < C2G_NLEV; ++l) S.run_off[l] = l * ARL;
       }
+    }
+    __syncthreads();
+    uint32_t *RP = S.run_par, *RI = S.run_inf;
+    if (S.runs_in_arena) {
+      RP = reinterpret_cast<uint32_t *>(arenas + (size_t) S.arena * arena_bytes(ncell, nrow));
+      RI = RP + (size_t) C2G_NLEV * ARL;
+    }
+    if (warp < C2G_NLEV) {
+      const uint32_t *pl = S.plane[lev_w];
+      const uint16_t *wp = S.wpre[lev_w];
+      uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
+      const int n = S.n_runs[lev_w];
+      // B2 run records
+      for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int w = w0 + lane;
+        if (w >= nwords) continue;
+        const int row = w / WPR, wi = w - row * WPR;
+        const uint32_t bits = pl[w];
+        uint32_t starts = run_starts(pl + row * WPR, wi);
+        uint32_t id = wp[w];
+        while (starts) {
+          const int bpos = __ffs(starts) - 1;
+          starts &= starts - 1;
+          const uint32_t t = ~(bits >> bpos);  // the bits shifted in from the top are zeros, i.e. ones of t
+          int len = t ? __ffs(t) - 1 : 32;
+          if (bpos + len == 32) {
+            for (int w2 = wi + 1; w2 < WPR; ++w2) {
+              const uint32_t t2 = ~pl[row * WPR + w2];
+              const int add = t2 ? __ffs(t2) - 1 : 32;
+              len += add;
+              if (add < 32) break;
+            }
+          }
+          ri[id] = (uint32_t) row | ((uint32_t) (wi * 32 + bpos) << 8) | ((uint32_t) len << 16);
+          rp[id] = id;
+          ++id;
+        }
+      }
+      __syncwarp();
+      // B3 unions with the runs of the row above that touch [c0 - 1, c0 + len] (8-connectivity): consecutive run ids
+      for (int id0 = 0; id0 < n; id0 += 32) {
+        const int id = id0 + lane;
+        if (id >= n) continue;
+        const uint32_t inf = ri[id];
+        const int row = inf & 255, c0 = (inf >> 8) & 255, len = (inf >> 16) & 255;
+        if (row == 0) continue;
+        const int lo = max(c0 - 1, 0), hi = min(c0 + len, ncol - 1);
+        const uint32_t *pr = pl + (row - 1) * WPR;
+        const uint16_t *wpr = wp + (row - 1) * WPR;
+        int first = -1, extra = 0;
+        for (int wi = lo >> 5; wi <= (hi >> 5); ++wi) {
+          uint32_t m = pr[wi];
+          if (wi == (lo >> 5)) m &= FULL << (lo & 31);
+          if (wi == (hi >> 5)) m &= FULL >> (31 - (hi & 31));
+          if (!m) continue;
+          const uint32_t st = run_starts(pr, wi);
+          if (first < 0) {
+            const int pb = __ffs(m) - 1;
+            first = (int) wpr[wi] + __popc(st & (FULL >> (31 - pb))) - 1;  // the run that contains bit pb
+            extra += __popc(st & m & ~(FULL >> (31 - pb)));                // runs that start further right inside the window
+          } else
+            extra += __popc(st & m);
+        }
+        if (first >= 0)
+          for (int j = 0; j <= extra; ++j) uf_union(rp, (uint32_t) id, (uint32_t) (first + j));
+      }
+      __syncwarp();
+      // B4 flatten: compressing finds first (no entry is final yet), then one read-only find per run
+      for (int id = lane; id < n; id += 32) (void) uf_find(rp, (uint32_t) id);
+      __syncwarp();
+      int ncomp = 0;
+      for (int id0 = 0; id0 < n; id0 += 32) {
+        const int id = id0 + lane;
+        bool is_root = false;
+        if (id < n) {
+          const uint32_t root = uf_find_ro(rp, (uint32_t) id);
+          rp[id] = root;
+          is_root = root == (uint32_t) id;
+        }
+        ncomp += __popc(__ballot_sync(FULL, is_root));
+      }
+      if (lane == 0) S.n_comp[lev_w] = ncomp;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int l = 0; l < C2G_NLEV; ++l) {
+        S.comp_off[l] = tot;
+        tot += S.n_comp[l];
+      }
+      if (tot > C_POOL) {
+        if (S.arena < 0) {
+          int a = blockIdx.x % N_ARENAS;
+          while (atomicCAS(&arena_locks[a], 0, 1) != 0) {
+            a = (a + 1) % N_ARENAS;
+            __nanosleep(200);
+          }
+          S.arena = a;
+        }
+        S.comps_in_arena = 1;
+        for (int l = 0; l < C2G_NLEV; ++l) S.comp_off[l] = l * ARL;
+      }
+    }
+    __syncthreads();
+    Comp *CP = S.comp;
+    if (S.comps_in_arena)
+      CP = reinterpret_cast<Comp *>(arenas + (size_t) S.arena * arena_bytes(ncell, nrow) + (size_t) C2G_NLEV * ARL * 8);
+    if (warp < C2G_NLEV) {
+      uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
+      Comp *cp = CP + S.comp_off[lev_w];
+      const int n = S.n_runs[lev_w];
+      // B5 roots -> components, numbered in raster order of their first pixel
+      int cnext = 0;
+      for (int id0 = 0; id0 < n; id0 += 32) {
+        const int id = id0 + lane;
+        const bool is_root = id < n && rp[id] == (uint32_t) id;
+        const unsigned bal = __ballot_sync(FULL, is_root);
+        if (is_root) {
+          const int ci = cnext + __popc(bal & ((1u << lane) - 1u));
+          Comp e;
+          e.area = 0;
+          e.last = (uint16_t) id;
+          e.root = (uint16_t) id;
+          e.key = 0xFFFFu;
+          e.pcomp = 0xFFFFu;
+          e.rank = 0xFFFFu;
+          e.minc = 255;
+          e.maxc = 0;
+          e.y0 = 0;
+          e.x0 = 0;
+          cp[ci] = e;
+          rp[id] = 0x80000000u | (uint32_t) ci;
+        }
+        cnext += __popc(bal);
+      }
+      __syncwarp();
+      // B6 area / column extent / last run per component, and the in-component run chain (distance to the next run)
+      for (int id0 = 0; id0 < n; id0 += 32) {
+        const int id = id0 + lane;
+        const bool act = id < n;
+        uint32_t ci = 0xFFFFFFFFu;
+        int c0 = 0, len = 0;
+        if (act) {
+          const uint32_t inf = ri[id];
+          c0 = (inf >> 8) & 255;
+          len = (inf >> 16) & 255;
+          ci = comp_of(rp, (uint32_t) id);
+        }
+        const unsigned grp = __match_any_sync(FULL, ci);
+        const int a_sum = __reduce_add_sync(grp, len);
+        const int c_min = __reduce_min_sync(grp, c0);
+        const int c_max = __reduce_max_sync(grp, c0 + len - 1);
+        const int id_max = __reduce_max_sync(grp, id);
+        const unsigned below = grp & ((1u << lane) - 1u);
+        if (act) {
+          int pred = -1;
+          if (below)
+            pred = id0 + (31 - __clz(below));
+          else {  // first run of the component in this round: its predecessor is the last run of the earlier rounds
+            Comp e = cp[ci];
+            if (e.area) pred = e.last;
+            e.area = (uint16_t) (e.area + a_sum);
+            e.minc = (uint8_t) min((int) e.minc, c_min);
+            e.maxc = (uint8_t) max((int) e.maxc, c_max);
+            e.last = (uint16_t) id_max;
+            cp[ci] = e;
+          }
+          if (pred >= 0) ri[pred] |= (uint32_t) min(id - pred, 255) << 24;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    C2G_DBG(2);
+    if (warp < C2G_NLEV) {
+      uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
+      Comp *cp = CP + S.comp_off[lev_w];
+      const int n = S.n_runs[lev_w], nc = S.n_comp[lev_w];
+      // B7 enclosing component of the previous level (looked up at the first pixel) and its bounding-box origin
+      if (lev_w > 0) {
+        const uint32_t *plp = S.plane[lev_w - 1];
+        const uint16_t *wpp = S.wpre[lev_w - 1];
+        const uint32_t *rpp = RP + S.run_off[lev_w - 1], *rip = RI + S.run_off[lev_w - 1];
+        const Comp *cpp = CP + S.comp_off[lev_w - 1];
+        for (int ci = lane; ci < nc; ci += 32) {
+          const uint32_t inf = ri[cp[ci].root];
+          const int row = inf & 255, c0 = (inf >> 8) & 255;
+          const int wi = c0 >> 5;
+          const uint32_t st = run_starts(plp + row * WPR, wi);
+          if (!((plp[row * WPR + wi] >> (c0 & 31)) & 1u)) continue;  // only if lv_grads is not increasing: no parent (pcomp stays 0xFFFF)
+          const int rid = (int) wpp[row * WPR + wi] + __popc(st & (FULL >> (31 - (c0 & 31)))) - 1;
+          const uint32_t pc = comp_of(rpp, (uint32_t) rid);
+          const Comp pe = cpp[pc];
+          cp[ci].pcomp = (uint16_t) pc;
+          cp[ci].y0 = (uint8_t) (rip[pe.root] & 255);
+          cp[ci].x0 = pe.minc;
+        }
+        __syncwarp();
+      }
+      // B8 first-2x2-block key relative to that origin: min over the runs (a run's minimum is at its first cell)
+      for (int id0 = 0; id0 < n; id0 += 32) {
+        const int id = id0 + lane;
+        const bool act = id < n;
+        uint32_t ci = 0xFFFFFFFFu;
+        int key = 0xFFFF;
+        if (act) {
+          const uint32_t inf = ri[id];
+          ci = comp_of(rp, (uint32_t) id);
+          const Comp e = cp[ci];
+          key = ((((int) (inf & 255) - (int) e.y0) >> 1) << 7) + ((((int) ((inf >> 8) & 255)) - (int) e.x0) >> 1);
+        }
+        const unsigned grp = __match_any_sync(FULL, ci);
+        const int kmin = __reduce_min_sync(grp, key);
+        if (act && !(grp & ((1u << lane) - 1u)) && kmin < (int) cp[ci].key) cp[ci].key = (uint16_t) kmin;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // B9 DFS order rank, level by level (the rank of a component needs the rank of its parent)
+    int total_views = 0;
+    for (int lev = 0; lev < C2G_NLEV; ++lev) {
+      Comp *cp = CP + S.comp_off[lev];
+      const Comp *cpp = lev ? CP + S.comp_off[lev - 1] : nullptr;
+      const int nc = S.n_comp[lev];
+      if (tid == 0) S.nsig = 0;
       __syncthreads();
-      C2G_DBG(10 + lev * 8 + 4);
-      // B6 significant components -> DFS order rank
-      const int ncomp = min(S.ncomp, NC);
-      for (int s = tid; s < ncomp; s += K2_THREADS)
-        if (S.c_area[s] >= cfg.min_cont_cell_cnt) {
+      for (int ci = tid; ci < nc; ci += K2_THREADS) {
+        const Comp e = cp[ci];
+        if ((int) e.area >= cfg.min_cont_cell_cnt) {
           const int i = atomicAdd(&S.nsig, 1);
           if (i < NVL) {
-            S.sig_slot[i] = (uint16_t) s;
-            S.sig_key[i] = ((uint32_t) S.c_pcid[s] << 16) | (uint32_t) S.c_key[s];
+            const uint32_t prank = !lev ? 0u : e.pcomp == 0xFFFFu ? 0xFFFFu : (uint32_t) cpp[e.pcomp].rank;
+            S.sig.key[i] = (prank << 16) | (uint32_t) e.key;
+            S.sig.comp[i] = (uint16_t) ci;
           } else
             atomicOr(&S.status, 2);
         }
+      }
       __syncthreads();
-      int nsig = min(S.nsig, NVL);
+      const int nsig_all = min(S.nsig, NVL);
+      int nsig = nsig_all;
       if (total_views + nsig > C2G_VIEW_CAP) {
         nsig = C2G_VIEW_CAP - total_views;
         if (tid == 0) atomicOr(&S.status, 1);
       }
-      for (int i = tid; i < min(S.nsig, NVL); i += K2_THREADS) {
-        const uint32_t ki = S.sig_key[i];
+      for (int i = tid; i < nsig_all; i += K2_THREADS) {
+        const uint32_t ki = S.sig.key[i];
         int rank = 0;
-        for (int j = 0; j < min(S.nsig, NVL); ++j) rank += (S.sig_key[j] < ki) ? 1 : 0;
+        for (int j = 0; j < nsig_all; ++j) rank += (S.sig.key[j] < ki) ? 1 : 0;
         if (rank < nsig) {
-          const int sl = S.sig_slot[i];
-          S.order[rank] = (uint16_t) sl;
-          S.c_rank[sl] = (uint16_t) rank;
-          S.sortbuf[total_views + rank] = ((uint32_t) S.c_area[sl] << 16) | (uint32_t) rank;
-          S.t_poi[total_views + rank] = (uint16_t) S.c_poi[sl];
+          const int ci = S.sig.comp[i];
+          cp[ci].rank = (uint16_t) rank;
+          S.sortbuf[total_views + rank] = ((uint32_t) cp[ci].area << 16) | (uint32_t) rank;
+          S.vcomp[total_views + rank] = (uint16_t) ci;
         }
       }
-      __syncthreads();
       if (tid == 0) {
         S.n_views[lev] = nsig;
         S.view_off[lev] = total_views;
       }
-      // list offsets: exclusive prefix of the areas in rank order (one warp; nsig is a few dozen)
-      if (warp == 0) {
-        int run_off = lev * ncell;
-        for (int base = 0; base < nsig; base += 32) {
-          const int i = base + lane;
-          const int a = i < nsig ? (int) (S.sortbuf[total_views + i] >> 16) : 0;
-          int incl = a;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          if (i < nsig) S.t_off[total_views + i] = (uint32_t) (run_off + incl - a);
-          run_off += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-      }
-      __syncthreads();
-      C2G_DBG(10 + lev * 8 + 5);
-      // B7 member cells of every significant component in bbox-raster order -> global scratch list (shared memory only on
-      // the read side; the moment accumulation itself is deferred to the balanced task pool after the level loop)
-      for (int rk = warp; rk < nsig; rk += K2_WARPS) {
-        const int s = S.order[rk];
-        const int r0 = S.c_minr[s], c0 = S.c_minc[s], w = S.c_maxc[s] - c0 + 1, hgt = S.c_maxr[s] - r0 + 1;
-        uint16_t *wl = lists + S.t_off[total_views + rk];
-        int nlist = 0;
-        int rr = r0, cc = c0 + lane;  // lane's cell inside the bbox, advanced by 32 cells per step without divisions
-        while (cc >= c0 + w) {
-          cc -= w;
-          ++rr;
-        }
-        for (int base = 0; base < w * hgt; base += 32) {
-          bool member = false;
-          int c = 0;
-          if (rr < r0 + hgt) {
-            c = rr * ncol + cc;
-            member = (S.msk[c] & bit) && slot_of(S.L, c) == s;
-          }
-          const unsigned bal = __ballot_sync(0xFFFFFFFFu, member);
-          if (member) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = (uint16_t) c;
-          nlist += __popc(bal);
-          cc += 32;
-          while (cc >= c0 + w) {
-            cc -= w;
-            ++rr;
-          }
-        }
-      }
-      C2G_DBG(10 + lev * 8 + 6);
-      // B8 hand the ranks down: upper half of every foreground word = rank of its component (0xFFFF if insignificant)
-      for (int i = tid; i < nsig; i += K2_THREADS) {
-        const int s = S.order[i];
-        S.px0[i] = (uint8_t) S.c_minc[s];
-        S.py0[i] = (uint8_t) S.c_minr[s];
-      }
-      for (uint32_t bb = bits; bb; bb &= bb - 1) {
-        const int c = cb0 + __ffs(bb) - 1;
-        const int s = slot_of(S.L, c);
-        const uint32_t rk = (s == 0x7FFF) ? 0xFFFFu : (uint32_t) S.c_rank[s];
-        S.L[c] = (rk << 16) | (S.L[c] & 0xFFFFu);  // the low half (slot / root link) is what concurrent readers use
-      }
       total_views += nsig;
       __syncthreads();
     }
+    C2G_DBG(3);
 
-    C2G_DBG(2);
-    // ---------------- phase C: balanced task pool: per-level std::sort replays + moments / calcStatVals per component -----
-    // Tasks are ordered by decreasing size class (floor(log2(area))) so the longest sequential accumulations start first.
-    // Big components (> 32 cells) go to the front of the task order, small ones fill it from the back; positions are
-    // claimed with one shared atomic per warp and class (same-address shared atomics serialise).
-    if (tid == 0) {
-      S.wq = 0;
-      S.bucket_cnt[0] = 0;             // next free slot at the front
-      S.bucket_cnt[1] = total_views;   // one past the last free slot at the back
-    }
-    __syncthreads();
-    for (int v0 = warp * 32; v0 < total_views; v0 += K2_THREADS) {
-      const int v = v0 + lane;
-      const bool valid = v < total_views;
-      const bool big = valid && (S.sortbuf[v] >> 16) > 32u;
-      const unsigned mb = __ballot_sync(0xFFFFFFFFu, big), ms = __ballot_sync(0xFFFFFFFFu, valid && !big);
-      int fb = 0, bb2 = 0;
-      if (lane == 0) {
-        if (mb) fb = atomicAdd(&S.bucket_cnt[0], __popc(mb));
-        if (ms) bb2 = atomicSub(&S.bucket_cnt[1], __popc(ms));
-      }
-      fb = __shfl_sync(0xFFFFFFFFu, fb, 0);
-      bb2 = __shfl_sync(0xFFFFFFFFu, bb2, 0);
-      if (big) S.torder[fb + __popc(mb & ((1u << lane) - 1u))] = (uint16_t) v;
-      if (valid && !big) S.torder[bb2 - 1 - __popc(ms & ((1u << lane) - 1u))] = (uint16_t) v;
-    }
+    // ---------------- phase C: per-level std::sort replays + moments / calcStatVals per component --------------------
+    if (tid == 0) S.wq = 0;
     __syncthreads();
     // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
-    // (contour_mng.h:596-599); the walk tasks below read the areas from t_cnt copies taken before the sort starts
-    for (int v = tid; v < total_views; v += K2_THREADS) S.t_cnt[v] = (uint16_t) (S.sortbuf[v] >> 16);
-    __syncthreads();
-    if (lane == 0 && warp < C2G_NLEV) {  // one warp per level: the six serial replays run on different schedulers
+    // (contour_mng.h:596-599); one lane per level, on six different warps
+    if (lane == 0 && warp < C2G_NLEV) {
       uint32_t *first = S.sortbuf + S.view_off[warp];
-      c2g_sort::std_sort(first, (long) S.n_views[warp], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
       int sum = 0;
       for (int i = 0; i < S.n_views[warp]; ++i) sum += (int) (first[i] >> 16);
       S.layer_cnt[warp] = sum;
+      c2g_sort::std_sort(first, (long) S.n_views[warp], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
     }
-    C2G_DBG(58);
-    const int n_big = S.bucket_cnt[0];  // torder[0, n_big) = components of more than 32 cells, the rest follow
-    // Small components: one THREAD per component walks its own member list (<= 32 cells) with the seven double
-    // accumulators of RunningStatRecorder in registers, 32 components per warp instruction. Warps 0..5 are busy with the
-    // per-level sorts above, warps 6..31 take the small components.
-    if (warp >= C2G_NLEV) {
-      for (int i = n_big + (tid - C2G_NLEV * 32); i < total_views; i += K2_THREADS - C2G_NLEV * 32) {
-        const int v = S.torder[i];
-        const int n = S.t_cnt[v];
-        const uint16_t *wl = lists + S.t_off[v];
-        double s0 = 0, s1 = 0, t00 = 0, t01 = 0, t11 = 0, q0 = 0, q1 = 0;
-        float vol3 = 0.0f;
-        for (int j = 0; j < n; ++j) {
-          const int cc = wl[j];
-          const float hh = hg[cc];
-          const double v0 = (double) rfg[cc], v1 = (double) cfp[cc], hd = (double) hh;
-          s0 += v0;
-          s1 += v1;
-          t00 += v0 * v0;
-          t01 += v0 * v1;
-          t11 += v1 * v1;
-          vol3 += hh;
-          q0 += hd * v0;
-          q1 += hd * v1;
-        }
-        double *raw = reinterpret_cast<double *>(presort + v);
-        raw[0] = s0;
-        raw[1] = s1;
-        raw[2] = t00;
-        raw[3] = t01;
-        raw[4] = t11;
-        raw[5] = q0;
-        raw[6] = q1;
-        reinterpret_cast<float *>(raw + 7)[0] = vol3;
-      }
-    }
+    __syncwarp();
     {
-      // Big components: one WARP per component from a shared queue (largest size class first). The seven double
-      // accumulators live in lanes 0..6: lane k adds a_k * b_k per member cell (s0: v0*1, s1: v1*1, t00: v0*v0, t01: v0*v1,
-      // t11: v1*v1, q0: h*v0, q1: h*v1; x*1.0 is exact), so a cell costs the FP64 pipe one DMUL + one DADD per warp.
-      // Accumulation order = list order = bbox-raster order.
-      const int selA = (lane == 0 || lane == 2 || lane == 3) ? 0 : (lane == 1 || lane == 4) ? 1 : (lane == 5 || lane == 6) ? 2 : 3;
-      const int selB = (lane == 2 || lane == 5) ? 0 : (lane == 3 || lane == 4 || lane == 6) ? 1 : 3;
+      // Moments: eight lanes per component, four components per warp step, handed out from a shared counter. Lane k of a
+      // group keeps ONE accumulator of RunningStatRecorder: sum of a_k * b_k over the member cells in raster order with
+      // (a, b) = (v0,1) (v1,1) (v0,v0) (v0,v1) (v1,v1) (h,v0) (h,v1); x * 1.0 is exact, the product of two floats is exact in
+      // double, so every lane performs exactly the reference's sequence of double additions.
+      const int k8 = lane & 7, grp4 = lane >> 3;
+      const uint32_t mA0 = (k8 == 0 || k8 == 2 || k8 == 3) ? FULL : 0u, mA1 = (k8 == 1 || k8 == 4) ? FULL : 0u,
+                     mAh = (k8 == 5 || k8 == 6) ? FULL : 0u, mAc = (k8 == 7) ? FULL : 0u;
+      const uint32_t mB0 = (k8 == 2 || k8 == 5) ? FULL : 0u, mB1 = (k8 == 3 || k8 == 4 || k8 == 6) ? FULL : 0u,
+                     mBc = (k8 == 0 || k8 == 1 || k8 == 7) ? FULL : 0u;
+      const uint32_t one = __float_as_uint(1.0f);
       while (true) {
-        int ti = 0;
-        if (lane == 0) ti = atomicAdd(&S.wq, 1);
-        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
-        if (ti >= n_big) break;
-        const int v = S.torder[ti];
-        const int n = S.t_cnt[v];
-        const uint16_t *wl = lists + S.t_off[v];
-        double acc = 0.0;
-        float vol3 = 0.0f;
-        for (int g = 0; g < n; g += 128) {
-          float hv[4], rv[4], cv[4];
+        int v0 = 0;
+        if (lane == 0) v0 = atomicAdd(&S.wq, 4);
+        v0 = __shfl_sync(FULL, v0, 0);
+        if (v0 >= total_views) break;
+        const int v = v0 + grp4;
+        if (v < total_views) {
+          int lev = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = g + u * 32 + lane;
-            hv[u] = rv[u] = cv[u] = 0.f;
-            if (j < n) {
-              const int cc = wl[j];
-              hv[u] = hg[cc];
-              rv[u] = rfg[cc];
-              cv[u] = cfp[cc];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int cntu = min(32, n - (g + u * 32));
-            for (int src = 0; src < cntu; ++src) {
-              // three 32-bit shuffles per cell; every lane converts only the two operands its accumulator needs
-              const float hh = __shfl_sync(0xFFFFFFFFu, hv[u], src);
-              const float f0 = __shfl_sync(0xFFFFFFFFu, rv[u], src);
-              const float f1 = __shfl_sync(0xFFFFFFFFu, cv[u], src);
-              const float fa = selA == 0 ? f0 : selA == 1 ? f1 : selA == 2 ? hh : 1.0f;
-              const float fb = selB == 0 ? f0 : selB == 1 ? f1 : 1.0f;
+          for (int l = 1; l < C2G_NLEV; ++l)
+            if (v >= S.view_off[l]) lev = l;
+          const uint32_t *rp = RP + S.run_off[lev], *ri = RI + S.run_off[lev];
+          const uint32_t ci = S.vcomp[v];
+          const Comp e = (CP + S.comp_off[lev])[ci];
+          uint32_t rid = e.root;
+          double acc = 0.0;
+          float vol3 = 0.0f;
+          while (true) {
+            const uint32_t inf = ri[rid];
+            const int cell = (int) (inf & 255) * ncol + (int) ((inf >> 8) & 255), len = (inf >> 16) & 255;
+            for (int j = 0; j < len; ++j) {
+              const float hh = hg[cell + j];
+              const uint32_t f0 = __float_as_uint(rfg[cell + j]), f1 = __float_as_uint(cfp[cell + j]), fh = __float_as_uint(hh);
+              const float fa = __uint_as_float((f0 & mA0) | (f1 & mA1) | (fh & mAh) | (one & mAc));
+              const float fb = __uint_as_float((f0 & mB0) | (f1 & mB1) | (one & mBc));
               acc += (double) fa * (double) fb;
               vol3 += hh;
             }
+            if (rid == e.last) break;
+            const uint32_t d = inf >> 24;
+            rid += d;
+            if (d == 255)
+              while (comp_of(rp, rid) != ci) ++rid;
           }
+          // raw moments go to the component's (still unused) 80-byte presort record: doubles 0..6 from lanes 0..6 of the
+          // group, the float height sum in word 14
+          double *raw = reinterpret_cast<double *>(presort + v);
+          if (k8 < 7)
+            raw[k8] = acc;
+          else
+            reinterpret_cast<float *>(raw + 7)[0] = vol3;
         }
-        // raw moments go to the component's (still unused) 80-byte presort record: doubles 0..6 from lanes 0..6, the
-        // float height sum in word 14; calcStatVals for all components runs afterwards with one thread per component
-        double *raw = reinterpret_cast<double *>(presort + v);
-        if (lane < 7) raw[lane] = acc;
-        if (lane == 7) reinterpret_cast<float *>(raw + 7)[0] = vol3;
       }
     }
-    C2G_DBG(59);
     __syncthreads();
-    C2G_DBG(60);
+    C2G_DBG(4);
     for (int v = tid; v < total_views; v += K2_THREADS) {
+      int lev = 0;
+#pragma unroll
+      for (int l = 1; l < C2G_NLEV; ++l)
+        if (v >= S.view_off[l]) lev = l;
+      const Comp e = (CP + S.comp_off[lev])[S.vcomp[v]];
+      const uint32_t linf = (RI + S.run_off[lev])[e.last];
       const double *raw = reinterpret_cast<const double *>(presort + v);
       Moments m;
-      m.cnt = S.t_cnt[v];
+      m.cnt = e.area;
       m.s0 = raw[0];
       m.s1 = raw[1];
       m.t00 = raw[2];
@@ -740,16 +796,15 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       m.q0 = raw[5];
       m.q1 = raw[6];
       m.vol3 = reinterpret_cast<const float *>(raw + 7)[0];
-      int lev = 0;
-      for (int l = 0; l < C2G_NLEV; ++l)
-        if (v >= S.view_off[l] && v < S.view_off[l] + S.n_views[l]) lev = l;
       c2g_view vw;
-      const int poi = S.t_poi[v];
-      calc_stat_vals(m, cfg, lev, poi / ncol, poi % ncol, vw);
+      calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
       presort[v] = vw;  // in place: this thread is the only reader and writer of the record
     }
     __syncthreads();
-    C2G_DBG(3);
+    if (tid == 0 && S.arena >= 0) {  // the run / component tables are dead from here on
+      __threadfence();
+      atomicExch(&arena_locks[S.arena], 0);
+    }
     {
       // copy 80-byte records as 20 x 4-byte words: sorted position j of level l <- presort index (sortbuf & 0xFFFF)
       const uint32_t *src = reinterpret_cast<const uint32_t *>(presort);
@@ -803,12 +858,9 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     }
     __syncthreads();
 
-    C2G_DBG(4);
+    C2G_DBG(5);
     // ---------------- phase D: retrieval keys (contour_mng.h:693-830) ------------------------------------------------
     // D1: per anchor, ordered list of the window cells that contribute: (dist, higher_cnt). One warp per anchor.
-    float *klist_dist = reinterpret_cast<float *>(S.L);                               // [N_ANCH][KEY_LIST_CAP]
-    uint8_t *klist_hc = reinterpret_cast<uint8_t *>(klist_dist + N_ANCH * KEY_LIST_CAP);  // [N_ANCH][KEY_LIST_CAP]
-    static_assert(N_ANCH * KEY_LIST_CAP * 5 <= sizeof(uint32_t) * C2G_MAX_CELLS, "key lists must fit in the label array");
     const int piv = cfg.piv_firsts;
     const int roi_pad = (int) ceilf(cfg.roi_radius + 1.0f);
     for (int a = warp; a < N_ANCH; a += K2_WARPS) {
@@ -822,24 +874,31 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         const int c_min = max(0, c_cen - roi_pad), c_max = min(ncol - 1, c_cen + roi_pad);
         const int w = c_max - c_min + 1, total = w * (r_max - r_min + 1);
         const double rad = (double) cfg.roi_radius - 1e-2;
+        int rr = r_min, cc = c_min + lane;  // lane's cell inside the window, advanced by 32 cells per step without divisions
+        while (cc > c_max) {
+          cc -= w;
+          ++rr;
+        }
         for (int base = 0; base < total; base += 32) {
-          const int i = base + lane;
           bool pass = false;
           float dist = 0.f;
           uint8_t hc = 0;
-          if (i < total) {
-            const int c = (r_min + i / w) * ncol + (c_min + i % w);
-            const uint8_t m = S.msk[c];
-            if (m & 2u) {  // bev > lv_grads[1]  (cells with bev == lv_grads[1] pass the first test but fail this one)
+          if (rr <= r_max) {
+            const int wd = rr * WPR + (cc >> 5), sh = cc & 31;
+            if ((S.plane[1][wd] >> sh) & 1u) {  // bev > lv_grads[1]  (cells with bev == lv_grads[1] pass the first test but fail this one)
+              const int c = rr * ncol + cc;
               const float dx = rfg[c] - cx, dy = cfp[c] - cy;
               dist = sqrtf(dx * dx + dy * dy);
               if ((double) dist < rad) {
                 pass = true;
-                hc = (uint8_t) __popc((unsigned) (m & 0x3Eu));
+                int h2 = 1;
+#pragma unroll
+                for (int l = 2; l < C2G_NLEV; ++l) h2 += (int) ((S.plane[l][wd] >> sh) & 1u);
+                hc = (uint8_t) h2;
               }
             }
           }
-          const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+          const unsigned bal = __ballot_sync(FULL, pass);
           if (pass) {
             const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
             if (pos < KEY_LIST_CAP) {
@@ -848,13 +907,18 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
             }
           }
           cnt += __popc(bal);
+          cc += 32;
+          while (cc > c_max) {
+            cc -= w;
+            ++rr;
+          }
         }
         if (cnt > KEY_LIST_CAP && lane == 0) atomicOr(&S.status, 4);
       }
       if (lane == 0) S.cnt_point[a] = valid ? cnt : -1;
     }
     __syncthreads();
-    C2G_DBG(5);
+    C2G_DBG(6);
     // D2: one thread per (anchor, division): sequential float accumulation in raster order
     {
       const float div_len = cfg.roi_radius / (float) ((C2G_KEY_DIM - 3) * 5);
@@ -912,17 +976,16 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       head->keys[ll][seq][kd] = val;
     }
 
-    C2G_DBG(6);
+    C2G_DBG(7);
     // ---------------- phase E: BCIs (contour_mng.h:848-883), one warp per anchor ------------------------------------
     // candidate t = bl * 10 + j (reference loop order) is evaluated by lane t % 32; kept neighbours are compacted in
     // that order, lane 0 replays std::sort on bit_pos and builds the run boundaries, all lanes write the record.
     {
-      c2g_relpt *nei_all = reinterpret_cast<c2g_relpt *>(S.L);                                         // [warps][40]
-      uint32_t *ord_all = reinterpret_cast<uint32_t *>(nei_all + K2_WARPS * C2G_MAX_NEI);              // [warps][40]
-      uint16_t *seg_all = reinterpret_cast<uint16_t *>(ord_all + K2_WARPS * C2G_MAX_NEI);              // [warps][42]
-      c2g_relpt *nei = nei_all + warp * C2G_MAX_NEI;
-      uint32_t *ord = ord_all + warp * C2G_MAX_NEI;
-      uint16_t *segv = seg_all + warp * (C2G_MAX_NEI + 2);
+      unsigned char *scr = S.bci_scratch + warp * 736;  // the run tables are dead: [40] relpt, [40] u32, [42] u16
+      c2g_relpt *nei = reinterpret_cast<c2g_relpt *>(scr);
+      uint32_t *ord = reinterpret_cast<uint32_t *>(scr + C2G_MAX_NEI * sizeof(c2g_relpt));
+      uint16_t *segv = reinterpret_cast<uint16_t *>(scr + C2G_MAX_NEI * (sizeof(c2g_relpt) + 4));
+      static_assert(C2G_MAX_NEI * (sizeof(c2g_relpt) + 4) + (C2G_MAX_NEI + 2) * 2 <= 736, "BCI scratch");
       for (int a = warp; a < N_ANCH; a += K2_WARPS) {
         const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
         if (seq >= piv) continue;
@@ -955,7 +1018,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
                 }
               }
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            const unsigned bal = __ballot_sync(FULL, keep);
             if (keep) {
               const int pos = n + __popc(bal & ((1u << lane) - 1u));
               nei[pos] = rp;
@@ -985,7 +1048,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           bci.level = (int8_t) ll;
           for (int i = 0; i < 6; ++i) bci.pad_[i] = 0;
         }
-        nseg = __shfl_sync(0xFFFFFFFFu, nseg, 0);
+        nseg = __shfl_sync(FULL, nseg, 0);
         __syncwarp();
         for (int i = lane; i < C2G_MAX_NEI; i += 32) {
           c2g_relpt rp;
@@ -1001,9 +1064,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         __syncwarp();
       }
     }
-    C2G_DBG(7);
+    C2G_DBG(8);
     // ---------------- phase F: scan-only GMM terms (correlation.h:49-82,102-119) -----------------------------------
-    __shared__ int n_ell_s[C2G_NUM_BIN_LAYERS];
     if (tid < C2G_NUM_BIN_LAYERS) {
       const int lev = tid + 1;
       const int full = S.layer_cnt[lev];
@@ -1013,12 +1075,12 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         if ((double) run * 1.0 / (double) full >= 0.95) break;
         run += (int) (sb[k] >> 16);
       }
-      n_ell_s[tid] = k;
+      S.n_ell[tid] = k;
     }
     __syncthreads();
     double acc = 0.0;
     for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
-      const int n = n_ell_s[li];
+      const int n = S.n_ell[li];
       const c2g_ell *le = eout + S.view_off[li + 1];
       for (int w = tid; w < n * n; w += K2_THREADS) {
         const int i = w / n, j = w - i * n;
@@ -1032,10 +1094,9 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         acc += (double) A.w * (double) Bv.w / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
       }
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
     if (lane == 0) S.red[warp] = acc;
     __syncthreads();
-    C2G_DBG(8);
     // ---------------- phase G: head ------------------------------------------------------------------------------------
     if (tid == 0) {
       double tot = 0.0;
@@ -1047,7 +1108,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         head->view_off[l] = S.view_off[l];
         head->layer_cell_cnt[l] = S.layer_cnt[l];
       }
-      for (int l = 0; l < C2G_NUM_BIN_LAYERS; ++l) head->n_ell[l] = n_ell_s[l];
+      for (int l = 0; l < C2G_NUM_BIN_LAYERS; ++l) head->n_ell[l] = S.n_ell[l];
       head->n_occupied = S.n_occ;
       head->pad_ = 0;
       head->gmm_auto_corr = tot;
@@ -1060,22 +1121,32 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
 }  // namespace
 
 size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
+int c2g_contour_max_ctas(int num_sms) { return K2_CTAS_PER_SM * num_sms; }
+// layout of the global scratch: [max_ctas][KLIST_BYTES] key-window lists | [N_ARENAS] locks (zeroed at creation) | arenas
+size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row) {
+  return (size_t) c2g_contour_max_ctas(num_sms) * KLIST_BYTES + 256 + (size_t) N_ARENAS * arena_bytes(n_cells, n_row);
+}
 
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        uint16_t *cell_lists, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
+                        unsigned char *k2_scratch, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
   static bool attr_set = false;
   if (!attr_set) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
+    C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  const int grid = B < num_sms ? B : num_sms;
+  const int max_ctas = c2g_contour_max_ctas(num_sms);
+  const int grid = B < max_ctas ? B : max_ctas;
   if (grid <= 0) return 0;
+  unsigned char *klists = k2_scratch;
+  int *locks = reinterpret_cast<int *>(k2_scratch + (size_t) max_ctas * KLIST_BYTES);
+  unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES + 256;
   C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, cell_lists,
-                                                             work_counter, dbg);
+                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, klists,
+                                                             locks, arenas, work_counter, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

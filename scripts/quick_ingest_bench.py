@@ -45,11 +45,6 @@ from contour_context_b200 import capi
 clk = np.zeros(64, np.int64)
 capi.lib().c2g_debug_clocks.argtypes = [C.c_void_p, C.c_void_p]
 capi.lib().c2g_debug_clocks(eng.h, clk.ctypes.data_as(C.c_void_p))
-names = {0:'start',1:'A done',2:'levels done',3:'sort done',4:'views copied',5:'D1 done',6:'D2+keys done',7:'BCI done',8:'GMM done',9:'end'}
+names = {0:'start',1:'A done',2:'label+stats',3:'ranks done',4:'sort+moments',5:'calcstat+copy',6:'D1 done',7:'D2+keys done',8:'BCI done',9:'GMM/end'}
 t0 = clk[0]
-for i in range(10): print(f"  {names[i]:14s} {(clk[i]-t0)/1e3:9.1f} kcyc")
-print(f'  phaseC: order+prep {(clk[58]-clk[2])/1e3:.1f}?  sort(tid0) end {(clk[58]-clk[2])/1e3:.1f}  own walk end {(clk[59]-clk[2])/1e3:.1f}  barrier {(clk[60]-clk[2])/1e3:.1f}  calcstat {(clk[3]-clk[60])/1e3:.1f} kcyc')
-for lev in range(6):
-    s = clk[10+lev*8: 10+lev*8+7]
-    base = clk[1] if lev == 0 else clk[10+(lev-1)*8+6]
-    print(f"  lev{lev}: init {(s[0]-base)/1e3:.1f} union {(s[1]-s[0])/1e3:.1f} flatten {(s[2]-s[1])/1e3:.1f} roots {(s[3]-s[2])/1e3:.1f} tables {(s[4]-s[3])/1e3:.1f} rank {(s[5]-s[4])/1e3:.1f} walk {(s[6]-s[5])/1e3:.1f} kcyc")
+for i in range(10): print(f"  {names[i]:14s} {(clk[i]-t0)/1e3:9.1f} kcyc  (+{(clk[i]-clk[max(i-1,0)])/1e3:.1f})")

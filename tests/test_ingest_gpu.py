@@ -119,3 +119,45 @@ def test_device_resident_input_matches_host_input(engine):
     h_dev = engine.heads(2, 2)
     for f in ("n_views", "layer_cell_cnt", "keys", "n_ell"):
         assert h_host[f].tobytes() == h_dev[f].tobytes(), f
+
+
+def _cells_to_points(h, rng):
+    """One point per occupied cell (jittered inside the cell), z so that lidar_height + z == h."""
+    rows, cols = np.nonzero(h > -999.0)
+    n = len(rows)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rows - 75 + rng.uniform(0.1, 0.9, n)
+    pts[:, 1] = cols - 75 + rng.uniform(0.1, 0.9, n)
+    pts[:, 2] = h[rows, cols] - 2.0
+    return pts[rng.permutation(n)]
+
+
+def test_cluttered_scans_use_the_overflow_arenas(engine, oracle):
+    """Salt-and-pepper BEVs: ~5 000 runs per level (run tables spill to the global arena), one 16 000-cell component, and a
+    second scan with ~4 500 components (component tables spill too).  Everything must still match the oracle bit for bit."""
+    rng = np.random.default_rng(5)
+    scans = []
+    for (a, b, frac, cmax) in [(-1.0, 9.0, 1.0, 150), (0.5, 8.5, 0.45, 85), (1.0, 6.0, 0.12, 150)]:
+        h = np.full((150, 150), -1000.0)
+        m = rng.random((150, 150)) < frac
+        m[:, cmax:] = False
+        h[m] = rng.uniform(a, b, int(m.sum()))
+        scans.append(_cells_to_points(h, rng))
+    base, _ = make_batch([21], [0], 60000)
+    scans.append(base)                            # an ordinary scan in the same batch (shared-memory tables)
+    pts = np.ascontiguousarray(np.concatenate(scans))
+    offsets = np.cumsum([0] + [len(s) for s in scans]).astype(np.int64)
+    engine.ingest(pts, offsets, first_slot=0)
+    heads = engine.heads(0, len(scans))
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        oh = s.head()
+        assert heads[b]["status"] == 0, (b, heads[b]["status"], oh["n_views"])
+        assert np.array_equal(heads[b]["n_views"], oh["n_views"]), (b, heads[b]["n_views"], oh["n_views"])
+        assert np.array_equal(heads[b]["layer_cell_cnt"], oh["layer_cell_cnt"])
+        gviews = engine.views(b, heads[b])
+        for lev in range(D.NLEV):
+            assert not view_fields_equal(gviews[lev], s.views(lev)), (b, lev)
+        gk, ok = heads[b]["keys"], oh["keys"]
+        assert np.array_equal(np.isnan(gk), np.isnan(ok))
+        assert ulp_diff(np.nan_to_num(gk), np.nan_to_num(ok)).max() <= (2 if engine.exp_mode() == 0 else 0)
+        assert heads[b]["bcis"]["dist_bin"].tobytes() == oh["bcis"]["dist_bin"].tobytes()
