@@ -15,6 +15,8 @@
 // launchers implemented in the kernel translation units
 int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P,
                            c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream);
+int c2g_launch_bev_fill(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
+                        float *bev_h, float *bev_rf, float *bev_cf, cudaStream_t stream);
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
@@ -298,9 +300,9 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
     int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, ctx->d_tiles + ncell * b0, ctx->num_sms, ctx->stream);
     if (rc) return rc;
-    rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0,
-                             ctx->d_bev_h + ncell * b0, ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads,
-                             ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
+    rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_bev_h + ncell * b0,
+                             ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
+                             ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
   }
@@ -321,8 +323,8 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
   if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev);
   int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
   if (rc) return rc;
-  rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h,
-                           ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
+  rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads,
+                           ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -345,6 +347,14 @@ int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host) {
 int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f) {
   if (!ctx || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
   const size_t n = ctx->P.n_cells, off = n * batch_index;
+  // the contour kernel only fills the cells that belong to a contour; the full dense image (getBevImage, bev_pixfs_) is
+  // produced on demand from the tile and the points of the last batch (still resident: staging buffer or caller's buffer)
+  if (!ctx->last_pts) return C2G_ERR_STATE;
+  {
+    int rc = c2g_launch_bev_fill(ctx->d_tiles + off, ctx->last_pts, ctx->d_offsets, batch_index, ctx->P, ctx->d_bev_h + off,
+                                 ctx->d_bev_rf + off, ctx->d_bev_cf + off, ctx->stream);
+    if (rc) return rc;
+  }
   if (bev) C2G_CUDA_TRY(cudaMemcpyAsync(bev, ctx->d_bev_h + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (row_f) C2G_CUDA_TRY(cudaMemcpyAsync(row_f, ctx->d_bev_rf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (col_f) C2G_CUDA_TRY(cudaMemcpyAsync(col_f, ctx->d_bev_cf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));

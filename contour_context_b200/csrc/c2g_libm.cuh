@@ -106,6 +106,36 @@ C2G_LM double c2g_exp_glibc(double x, const uint64_t *tab) {
   return FMA ? fma(scale, tmp, scale) : scale + scale * tmp;
 }
 
+// Main path of c2g_exp_glibc without its range branches (straight-line code that the compiler can interleave over several
+// independent arguments): *special is set when the argument needs the full function (|x| < 2^-54, |x| >= 512, NaN / Inf);
+// the value returned in that case is meaningless but its computation is harmless.
+template <bool FMA>
+C2G_LM double c2g_exp_glibc_main(double x, const uint64_t *tab, bool *special) {
+  const uint32_t abstop = (uint32_t) (c2g_d2u(x) >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u >= 0x408u - 0x3c9u) *special = true;
+  const double z = C2G_EXP_INVLN2N * x;
+  double kd = z + C2G_EXP_SHIFT;
+  const uint64_t ki = c2g_d2u(kd);
+  kd -= C2G_EXP_SHIFT;
+  double r;
+  if (FMA)
+    r = fma(kd, C2G_EXP_NEGLN2LON, fma(kd, C2G_EXP_NEGLN2HIN, x));
+  else
+    r = x + kd * C2G_EXP_NEGLN2HIN + kd * C2G_EXP_NEGLN2LON;
+  const uint64_t idx = 2 * (ki % 128);
+  const uint64_t top = ki << (52 - 7);
+  const double tail = c2g_u2d(tab[idx]);
+  const uint64_t sbits = tab[idx + 1] + top;
+  const double r2 = r * r;
+  double tmp;
+  if (FMA)
+    tmp = fma(r2 * r2, fma(r, C2G_EXP_C5, C2G_EXP_C4), fma(r2, fma(r, C2G_EXP_C3, C2G_EXP_C2), tail + r));
+  else
+    tmp = tail + r + r2 * (C2G_EXP_C2 + r * C2G_EXP_C3) + r2 * r2 * (C2G_EXP_C4 + r * C2G_EXP_C5);
+  const double scale = c2g_u2d(sbits);
+  return FMA ? fma(scale, tmp, scale) : scale + scale * tmp;
+}
+
 // mode: 0 libdevice/libm exp, 1 glibc algorithm without FMA, 2 glibc algorithm with FMA (x86-64 __exp_fma)
 C2G_LM double c2g_exp(double x, int mode, const uint64_t *tab) {
   if (mode == 2) return c2g_exp_glibc<true>(x, tab);

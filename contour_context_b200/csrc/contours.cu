@@ -25,11 +25,14 @@
 //   * the largest run id ends in the component's last pixel (ContourView::poi),
 //   * walking a component's runs in id order visits its cells in the reference's accumulation order (bbox-raster order
 //     restricted to members == raster order of members).
-// Per-component statistics are reduced inside the warp (__match_any_sync + redux) and kept in 16-byte records.
+// Two warps share a level (named barriers between them); per-component statistics are native 32-bit shared atomics on
+// four packed words per component.
 //
 // Bit-exactness rules: float/double sums that feed views and keys are accumulated in the reference's raster order by a
 // single logical accumulator, never by tree reductions; compiled with -fmad=false.
 #include <math_constants.h>
+
+#include <type_traits>
 
 #include "c2g_common.cuh"
 #include "stdsort.cuh"
@@ -45,6 +48,7 @@ constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_CTAS_PER_SM = 2;
 constexpr int PLANE_WORDS = 800;  // n_row * ceil(n_col / 32) (checked by make_params): 150 x 5 = 750 for both shipped configs
 constexpr int WCHUNK = 5;         // 32-column words of a row decoded per batch in phase A
+constexpr int ROWS_A = 2;         // rows per warp per batch in phase A (2 x 5 independent loads in flight per lane)
 constexpr int R_POOL = 5120;      // runs of all six levels that fit in shared memory (else: global arena)
 constexpr int C_POOL = 1536;      // components of all six levels that fit in shared memory (else: global arena)
 constexpr int NVL = 1024;         // significant components (area >= min_cont_cell_cnt) per level
@@ -59,12 +63,15 @@ struct TopView {  // what keys / BCI / GMM need from a sorted view
   int cnt;
 };
 
-// One connected component of one level. `root` / `last`: first / last run (level-local run ids, raster order).
-struct __align__(16) Comp {
-  uint16_t area, last, root, key, pcomp, rank;
-  uint8_t minc, maxc, y0, x0;  // y0, x0: bounding-box origin of the enclosing component of the previous level
-};
-static_assert(sizeof(Comp) == 16, "Comp layout");
+// One connected component of one level = four 32-bit words, every field that several lanes update concurrently sits where
+// one native atomic can maintain it (root / last: first / last run of the component, level-local run ids in raster order):
+//   w0 = root << 16 | area                  area: atomicAdd (<= 22 500 cells, never carries into the upper half)
+//   w1 = last << 16 | key                   last: atomicMax with the low half 0xFFFF; key (first 2x2 block, relative to the
+//                                           parent's bounding-box origin): atomicMin once `last` is final
+//   w2 = (255 - minc) << 24 | pcomp         minc: atomicMax with the low bits 0xFFFFFF; pcomp = enclosing component of the
+//                                           previous level (0xFFFF = none), written afterwards by one lane
+//   w3 = rank << 16 | y0 << 8 | x0          DFS rank (0xFFFF = not a view) and the parent's bounding-box origin
+constexpr int CW = 4;
 
 struct Smem {
   uint32_t plane[C2G_NLEV][PLANE_WORDS];  // bit (c & 31) of word r * WPR + (c >> 5): bev(r, c) > lv_grads[level]
@@ -76,18 +83,20 @@ struct Smem {
     } sig;                 // ranking step
   };
   union {
-    uint32_t run_par[R_POOL];  // union-find parent (run id); after the flatten: root id, or 0x80000000 | component for roots
+    uint32_t run_par[R_POOL];  // union-find parent (run id); after the flatten: root id; finally 0x80000000 | component
     unsigned char bci_scratch[K2_WARPS * 736];
   };
   union {
-    uint32_t run_inf[R_POOL];  // row | c0 << 8 | len << 16 | (distance to the next run of the same component, 255 = search) << 24
+    uint32_t run_inf[R_POOL];  // row | c0 << 8 | len << 16
     float divs[N_ANCH][N_DIVS];
   };
-  Comp comp[C_POOL];
+  uint32_t comp[C_POOL * CW];
   uint32_t sortbuf[C2G_VIEW_CAP];  // (cell_cnt << 16 | presort index), all levels back to back
   uint16_t vcomp[C2G_VIEW_CAP];    // level-local component of every presort view
+  uint16_t torder[C2G_VIEW_CAP];   // presort views by decreasing size class (moment tasks)
   int n_views[C2G_NLEV], view_off[C2G_NLEV], layer_cnt[C2G_NLEV];
   int n_runs[C2G_NLEV], run_off[C2G_NLEV], n_comp[C2G_NLEV], comp_off[C2G_NLEV];
+  int half_runs[C2G_NLEV][2], half_roots[C2G_NLEV][2], comp_cnt[C2G_NLEV], cls_cnt[16];
   TopView top[C2G_NLEV][C2G_MAX_DIST_FIRSTS];
   int cnt_point[N_ANCH];
   int n_ell[C2G_NUM_BIN_LAYERS];
@@ -138,6 +147,17 @@ __device__ __forceinline__ uint32_t comp_of(const uint32_t *P, uint32_t id) {
   uint32_t v = P[id];
   if (!(v & 0x80000000u)) v = P[v];
   return v & 0x7FFFFFFFu;
+}
+// the two warps of a level meet at named barrier 1 + level (barrier 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int level) {
+  switch (level) {  // literal ids: ptxas reserves all 16 barriers for a register operand
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+  }
 }
 // bits of word `wi` of a plane row where a horizontal run starts
 __device__ __forceinline__ uint32_t run_starts(const uint32_t *row_words, int wi) {
@@ -307,12 +327,14 @@ constexpr size_t KLIST_BYTES = ((size_t) N_ANCH * KEY_LIST_CAP * 5 + 255) / 256 
 
 __host__ __device__ inline int arena_level_cap(int n_cells, int n_row) { return n_cells / 2 + n_row; }  // runs (>= components) of one level
 __host__ __device__ inline size_t arena_bytes(int n_cells, int n_row) {
-  return (size_t) C2G_NLEV * arena_level_cap(n_cells, n_row) * (4 + 4 + sizeof(Comp));
+  return (size_t) C2G_NLEV * arena_level_cap(n_cells, n_row) * (4 + 4 + 4 * CW);
 }
 
+static_assert(K2_WARPS == 2 * C2G_NLEV, "two warps per level in the labelling phases");
+
 __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM)
-contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets,
-               int B, C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
+contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B,
+               C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
                unsigned char *__restrict__ klist_scratch, int *__restrict__ arena_locks, unsigned char *__restrict__ arenas,
@@ -327,6 +349,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
   float *const klist_dist = reinterpret_cast<float *>(klist_scratch + (size_t) blockIdx.x * KLIST_BYTES);  // [N_ANCH][KEY_LIST_CAP]
   uint8_t *const klist_hc = reinterpret_cast<uint8_t *>(klist_dist + N_ANCH * KEY_LIST_CAP);               // [N_ANCH][KEY_LIST_CAP]
   const int ARL = arena_level_cap(ncell, nrow);
+  const int lev_w = warp >> 1, half = warp & 1;  // level and half of this warp in the labelling phases
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   // scans are handed out dynamically (their cost varies 2x with the scene, and a CTA that starts late - e.g. behind a
   // co-running collective - must not leave a static share of the batch unprocessed until the end)
@@ -343,7 +367,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
 
 #define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0) dbg[i] = clock64(); } while (0)
     C2G_DBG(0);
-    // ---------------- phase A: decode the tile, gather the winner's continuous coordinates, build the bit-planes ------
+    // ---------------- phase A: decode the tile -> one bit-plane per level; cells above the lowest threshold (the only ones
+    // moments and keys ever read) get their height and the winner's continuous coordinates (8-byte gather from the points)
     if (tid == 0) {
       S.status = 0;
       S.n_occ = 0;
@@ -355,46 +380,54 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     {
       const float4 *p = pts + offsets[b];
       int occ = 0;
-      for (int r = warp; r < nrow; r += K2_WARPS) {
-        const size_t rbase = cbase + (size_t) r * ncol;
+      for (int r0 = warp * ROWS_A; r0 < nrow; r0 += K2_WARPS * ROWS_A) {
         for (int u0 = 0; u0 < WPR; u0 += WCHUNK) {
-          c2g_cellkey k[WCHUNK];
-          float2 xy[WCHUNK];
+          c2g_cellkey k[ROWS_A][WCHUNK];
 #pragma unroll
-          for (int u = 0; u < WCHUNK; ++u) {
-            const int c = (u0 + u) * 32 + lane;
-            k[u] = c < ncol ? tiles[rbase + c] : 0ull;
-          }
+          for (int q = 0; q < ROWS_A; ++q)
 #pragma unroll
-          for (int u = 0; u < WCHUNK; ++u) {
-            xy[u] = make_float2(0.f, 0.f);
-            if (k[u] != 0ull) xy[u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[u]));
-          }
-#pragma unroll
-          for (int u = 0; u < WCHUNK; ++u) {
-            const int c = (u0 + u) * 32 + lane;
-            float h = -1000.0f, rf = -1.0f, cf = -1.0f;
-            const bool has = k[u] != 0ull;
-            if (has) {
-              h = c2g_from_orderable((uint32_t) (k[u] >> 32));
-              // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
-              rf = (xy[u].x / cfg.reso_row + P.half_row_f) - 0.5f;
-              cf = (xy[u].y / cfg.reso_col + P.half_col_f) - 0.5f;
+            for (int u = 0; u < WCHUNK; ++u) {
+              const int c = (u0 + u) * 32 + lane;
+              k[q][u] = (r0 + q < nrow && c < ncol) ? tiles[cbase + (size_t) (r0 + q) * ncol + c] : 0ull;
             }
-            if (c < ncol) {
-              bev_h[rbase + c] = h;
-              bev_rf[rbase + c] = rf;
-              bev_cf[rbase + c] = cf;
-            }
-            occ += __popc(__ballot_sync(FULL, has));
-            uint32_t mine = 0;
+          float2 xy[ROWS_A][WCHUNK];
+          float hv[ROWS_A][WCHUNK];
+          uint32_t fgm = 0;  // bit q * WCHUNK + u: this lane's cell is above some threshold
 #pragma unroll
-            for (int e = 0; e < C2G_NLEV; ++e) {
-              const uint32_t bal = __ballot_sync(FULL, has && h > cfg.lv_grads[e]);
-              if (lane == e) mine = bal;
+          for (int q = 0; q < ROWS_A; ++q)
+#pragma unroll
+            for (int u = 0; u < WCHUNK; ++u) {
+              const bool has = k[q][u] != 0ull;
+              const float h = has ? c2g_from_orderable((uint32_t) (k[q][u] >> 32)) : -1000.0f;
+              hv[q][u] = h;
+              occ += __popc(__ballot_sync(FULL, has));
+              uint32_t mine = 0;
+              bool fg = false;
+#pragma unroll
+              for (int e = 0; e < C2G_NLEV; ++e) {
+                const bool above = has && h > cfg.lv_grads[e];
+                fg |= above;
+                const uint32_t bal = __ballot_sync(FULL, above);
+                if (lane == e) mine = bal;
+              }
+              if (lane < C2G_NLEV && u0 + u < WPR && r0 + q < nrow) S.plane[lane][(r0 + q) * WPR + u0 + u] = mine;
+              xy[q][u] = make_float2(0.f, 0.f);
+              if (fg) {
+                fgm |= 1u << (q * WCHUNK + u);
+                xy[q][u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[q][u]));
+              }
             }
-            if (lane < C2G_NLEV && u0 + u < WPR) S.plane[lane][r * WPR + u0 + u] = mine;
-          }
+#pragma unroll
+          for (int q = 0; q < ROWS_A; ++q)
+#pragma unroll
+            for (int u = 0; u < WCHUNK; ++u)
+              if (fgm & (1u << (q * WCHUNK + u))) {
+                const size_t c = cbase + (size_t) (r0 + q) * ncol + (u0 + u) * 32 + lane;
+                bev_h[c] = hv[q][u];
+                // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
+                bev_rf[c] = (xy[q][u].x / cfg.reso_row + P.half_row_f) - 0.5f;
+                bev_cf[c] = (xy[q][u].y / cfg.reso_col + P.half_col_f) - 0.5f;
+              }
         }
       }
       if (lane == 0 && occ) atomicAdd(&S.n_occ, occ);  // one same-address shared atomic per warp
@@ -402,16 +435,17 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     __syncthreads();
     C2G_DBG(1);
 
-    // ---------------- phase B: six independent run-based labellings, one warp per level -------------------------------
-    const int lev_w = warp;  // level of this warp in the per-level phases (warps >= C2G_NLEV wait at the barriers)
-    if (warp < C2G_NLEV) {
-      // B1 runs per word -> exclusive prefix (run ids are raster order)
+    // ---------------- phase B: six independent run-based labellings, two warps per level ------------------------------
+    // B1 runs per word -> exclusive prefix (run ids are raster order); each warp scans half of the words
+    const int wh = min(nwords, ((nwords / 2 + 31) >> 5) << 5);
+    const int wbeg = half ? wh : 0, wend = half ? nwords : wh;
+    {
       const uint32_t *pl = S.plane[lev_w];
       int base = 0;
-      for (int w0 = 0; w0 < nwords; w0 += 32) {
+      for (int w0 = wbeg; w0 < wend; w0 += 32) {
         const int w = w0 + lane;
         int cnt = 0;
-        if (w < nwords) {
+        if (w < wend) {
           const int row = w / WPR;
           cnt = __popc(run_starts(pl + row * WPR, w - row * WPR));
         }
@@ -421,12 +455,19 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           const int t = __shfl_up_sync(FULL, incl, o);
           if (lane >= o) incl += t;
         }
-        if (w < nwords) S.wpre[lev_w][w] = (uint16_t) (base + incl - cnt);
+        if (w < wend) S.wpre[lev_w][w] = (uint16_t) (base + incl - cnt);
         base += __shfl_sync(FULL, incl, 31);
       }
-      if (lane == 0) S.n_runs[lev_w] = base;
+      if (lane == 0) S.half_runs[lev_w][half] = base;
+      pair_sync(lev_w);
+      if (half) {
+        const int off = S.half_runs[lev_w][0];
+        for (int w = wbeg + lane; w < wend; w += 32) S.wpre[lev_w][w] = (uint16_t) (S.wpre[lev_w][w] + off);
+        if (lane == 0) S.n_runs[lev_w] = off + base;
+      }
     }
     __syncthreads();
+    C2G_DBG(10);
     if (tid == 0) {
       int tot = 0;
       for (int l = 0; l < C2G_NLEV; ++l) {
@@ -445,20 +486,21 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
     }
     __syncthreads();
-    uint32_t *RP = S.run_par, *RI = S.run_inf;
-    if (S.runs_in_arena) {
-      RP = reinterpret_cast<uint32_t *>(arenas + (size_t) S.arena * arena_bytes(ncell, nrow));
-      RI = RP + (size_t) C2G_NLEV * ARL;
-    }
-    if (warp < C2G_NLEV) {
+
+    // B2..B4; GEN = false: tables in shared memory (LDS / ATOMS), GEN = true: generic pointers (global arena)
+    auto stage1 = [&](auto gen_tag) {
+      constexpr bool GEN = decltype(gen_tag)::value;
+      uint32_t *RP = S.run_par, *RI = S.run_inf;
+      if (GEN) {
+        RP = reinterpret_cast<uint32_t *>(arenas + (size_t) S.arena * arena_bytes(ncell, nrow));
+        RI = RP + (size_t) C2G_NLEV * ARL;
+      }
       const uint32_t *pl = S.plane[lev_w];
       const uint16_t *wp = S.wpre[lev_w];
       uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
       const int n = S.n_runs[lev_w];
       // B2 run records
-      for (int w0 = 0; w0 < nwords; w0 += 32) {
-        const int w = w0 + lane;
-        if (w >= nwords) continue;
+      for (int w = wbeg + lane; w < wend; w += 32) {
         const int row = w / WPR, wi = w - row * WPR;
         const uint32_t bits = pl[w];
         uint32_t starts = run_starts(pl + row * WPR, wi);
@@ -481,11 +523,10 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           ++id;
         }
       }
-      __syncwarp();
+      pair_sync(lev_w);
+      C2G_DBG(12);
       // B3 unions with the runs of the row above that touch [c0 - 1, c0 + len] (8-connectivity): consecutive run ids
-      for (int id0 = 0; id0 < n; id0 += 32) {
-        const int id = id0 + lane;
-        if (id >= n) continue;
+      for (int id = half * 32 + lane; id < n; id += 64) {
         const uint32_t inf = ri[id];
         const int row = inf & 255, c0 = (inf >> 8) & 255, len = (inf >> 16) & 255;
         if (row == 0) continue;
@@ -509,12 +550,13 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         if (first >= 0)
           for (int j = 0; j <= extra; ++j) uf_union(rp, (uint32_t) id, (uint32_t) (first + j));
       }
-      __syncwarp();
+      pair_sync(lev_w);
+      C2G_DBG(13);
       // B4 flatten: compressing finds first (no entry is final yet), then one read-only find per run
-      for (int id = lane; id < n; id += 32) (void) uf_find(rp, (uint32_t) id);
-      __syncwarp();
-      int ncomp = 0;
-      for (int id0 = 0; id0 < n; id0 += 32) {
+      for (int id = half * 32 + lane; id < n; id += 64) (void) uf_find(rp, (uint32_t) id);
+      pair_sync(lev_w);
+      int nroot = 0;
+      for (int id0 = half * 32; id0 < n; id0 += 64) {
         const int id = id0 + lane;
         bool is_root = false;
         if (id < n) {
@@ -522,14 +564,21 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           rp[id] = root;
           is_root = root == (uint32_t) id;
         }
-        ncomp += __popc(__ballot_sync(FULL, is_root));
+        nroot += __popc(__ballot_sync(FULL, is_root));
       }
-      if (lane == 0) S.n_comp[lev_w] = ncomp;
-    }
+      if (lane == 0) S.half_roots[lev_w][half] = nroot;
+      C2G_DBG(14);
+    };
+    if (S.runs_in_arena)
+      stage1(std::true_type{});
+    else
+      stage1(std::false_type{});
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
       for (int l = 0; l < C2G_NLEV; ++l) {
+        S.n_comp[l] = S.half_roots[l][0] + S.half_roots[l][1];
+        S.comp_cnt[l] = 0;
         S.comp_off[l] = tot;
         tot += S.n_comp[l];
       }
@@ -547,259 +596,262 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       }
     }
     __syncthreads();
-    Comp *CP = S.comp;
-    if (S.comps_in_arena)
-      CP = reinterpret_cast<Comp *>(arenas + (size_t) S.arena * arena_bytes(ncell, nrow) + (size_t) C2G_NLEV * ARL * 8);
-    if (warp < C2G_NLEV) {
-      uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
-      Comp *cp = CP + S.comp_off[lev_w];
-      const int n = S.n_runs[lev_w];
-      // B5 roots -> components, numbered in raster order of their first pixel
-      int cnext = 0;
-      for (int id0 = 0; id0 < n; id0 += 32) {
-        const int id = id0 + lane;
-        const bool is_root = id < n && rp[id] == (uint32_t) id;
-        const unsigned bal = __ballot_sync(FULL, is_root);
-        if (is_root) {
-          const int ci = cnext + __popc(bal & ((1u << lane) - 1u));
-          Comp e;
-          e.area = 0;
-          e.last = (uint16_t) id;
-          e.root = (uint16_t) id;
-          e.key = 0xFFFFu;
-          e.pcomp = 0xFFFFu;
-          e.rank = 0xFFFFu;
-          e.minc = 255;
-          e.maxc = 0;
-          e.y0 = 0;
-          e.x0 = 0;
-          cp[ci] = e;
-          rp[id] = 0x80000000u | (uint32_t) ci;
+    C2G_DBG(15);
+
+    int total_views = 0;
+    // B5..B9, moments and calcStatVals: everything that reads the run / component tables
+    auto stage2 = [&](auto gen_tag) {
+      constexpr bool GEN = decltype(gen_tag)::value;
+      uint32_t *RP = S.run_par, *RI = S.run_inf, *CWP = S.comp;
+      if (GEN) {
+        unsigned char *ab = arenas + (size_t) (S.arena < 0 ? 0 : S.arena) * arena_bytes(ncell, nrow);
+        if (S.runs_in_arena) {
+          RP = reinterpret_cast<uint32_t *>(ab);
+          RI = RP + (size_t) C2G_NLEV * ARL;
         }
-        cnext += __popc(bal);
+        if (S.comps_in_arena) CWP = reinterpret_cast<uint32_t *>(ab + (size_t) C2G_NLEV * ARL * 8);
+      }
+      {
+        uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
+        uint32_t *cw = CWP + (size_t) S.comp_off[lev_w] * CW;
+        const int n = S.n_runs[lev_w], nc = S.n_comp[lev_w];
+        // B5 roots -> components (numbered in arrival order; only the DFS rank computed below carries meaning)
+        for (int id0 = half * 32; id0 < n; id0 += 64) {
+          const int id = id0 + lane;
+          const bool is_root = id < n && rp[id] == (uint32_t) id;
+          const unsigned bal = __ballot_sync(FULL, is_root);
+          int cb = 0;
+          if (lane == 0 && bal) cb = atomicAdd(&S.comp_cnt[lev_w], __popc(bal));
+          cb = __shfl_sync(FULL, cb, 0);
+          if (is_root) {
+            const int ci = cb + __popc(bal & lt_mask);
+            cw[ci * CW + 0] = (uint32_t) id << 16;
+            cw[ci * CW + 1] = ((uint32_t) id << 16) | 0xFFFFu;
+            cw[ci * CW + 2] = 0x00FFFFFFu;
+            cw[ci * CW + 3] = 0xFFFF0000u;
+            rp[id] = 0x80000000u | (uint32_t) ci;
+          }
+        }
+        pair_sync(lev_w);
+        C2G_DBG(16);
+        // B6 area / last run / leftmost column per component; every run now names its component directly
+        for (int id = half * 32 + lane; id < n; id += 64) {
+          const uint32_t inf = ri[id];
+          const uint32_t c0 = (inf >> 8) & 255, len = (inf >> 16) & 255;
+          const uint32_t ci = comp_of(rp, (uint32_t) id);
+          atomicAdd(&cw[ci * CW + 0], len);
+          atomicMax(&cw[ci * CW + 1], ((uint32_t) id << 16) | 0xFFFFu);
+          atomicMax(&cw[ci * CW + 2], ((255u - c0) << 24) | 0x00FFFFFFu);
+          rp[id] = 0x80000000u | ci;  // nobody reads a non-root entry but its own lane
+        }
+        __syncthreads();
+        C2G_DBG(2);
+        // B7 enclosing component of the previous level (looked up at the first pixel) and its bounding-box origin
+        if (lev_w > 0) {
+          const uint32_t *plp = S.plane[lev_w - 1];
+          const uint16_t *wpp = S.wpre[lev_w - 1];
+          const uint32_t *rpp = RP + S.run_off[lev_w - 1], *rip = RI + S.run_off[lev_w - 1];
+          const uint32_t *cwp = CWP + (size_t) S.comp_off[lev_w - 1] * CW;
+          for (int ci = half * 32 + lane; ci < nc; ci += 64) {
+            const uint32_t inf = ri[cw[ci * CW] >> 16];
+            const int row = inf & 255, c0 = (inf >> 8) & 255;
+            const int wi = c0 >> 5;
+            if (!((plp[row * WPR + wi] >> (c0 & 31)) & 1u)) continue;  // only if lv_grads is not increasing: no parent
+            const uint32_t st = run_starts(plp + row * WPR, wi);
+            const int rid = (int) wpp[row * WPR + wi] + __popc(st & (FULL >> (31 - (c0 & 31)))) - 1;
+            const uint32_t pc = rpp[rid] & 0x7FFFFFFFu;
+            const uint32_t y0 = rip[cwp[pc * CW] >> 16] & 255u, x0 = 255u - (cwp[pc * CW + 2] >> 24);
+            cw[ci * CW + 2] = (cw[ci * CW + 2] & 0xFF000000u) | pc;
+            cw[ci * CW + 3] = 0xFFFF0000u | (y0 << 8) | x0;
+          }
+        }
+        pair_sync(lev_w);
+        C2G_DBG(18);
+        // B8 first-2x2-block key relative to that origin: min over the runs (a run's minimum is at its first cell)
+        for (int id = half * 32 + lane; id < n; id += 64) {
+          const uint32_t inf = ri[id];
+          const uint32_t ci = rp[id] & 0x7FFFFFFFu;
+          const uint32_t w3 = cw[ci * CW + 3];
+          const int key = ((((int) (inf & 255) - (int) ((w3 >> 8) & 255)) >> 1) << 7) + (((int) ((inf >> 8) & 255) - (int) (w3 & 255)) >> 1);
+          const uint32_t w1 = *(volatile uint32_t *) &cw[ci * CW + 1];
+          if ((uint32_t) key < (w1 & 0xFFFFu)) atomicMin(&cw[ci * CW + 1], (w1 & 0xFFFF0000u) | (uint32_t) key);
+        }
+      }
+      __syncthreads();
+      C2G_DBG(19);
+      // B9 DFS order rank, level by level (the rank of a component needs the rank of its parent)
+      for (int lev = 0; lev < C2G_NLEV; ++lev) {
+        uint32_t *cw = CWP + (size_t) S.comp_off[lev] * CW;
+        const uint32_t *cwp = lev ? CWP + (size_t) S.comp_off[lev - 1] * CW : nullptr;
+        const int nc = S.n_comp[lev];
+        if (tid == 0) S.nsig = 0;
+        __syncthreads();
+        for (int ci = tid; ci < nc; ci += K2_THREADS) {
+          const uint32_t w0 = cw[ci * CW];
+          if ((int) (w0 & 0xFFFFu) >= cfg.min_cont_cell_cnt) {
+            const int i = atomicAdd(&S.nsig, 1);
+            if (i < NVL) {
+              const uint32_t pc = cw[ci * CW + 2] & 0xFFFFu;
+              const uint32_t prank = !lev ? 0u : pc == 0xFFFFu ? 0xFFFFu : (cwp[pc * CW + 3] >> 16);
+              S.sig.key[i] = (prank << 16) | (cw[ci * CW + 1] & 0xFFFFu);
+              S.sig.comp[i] = (uint16_t) ci;
+            } else
+              atomicOr(&S.status, 2);
+          }
+        }
+        __syncthreads();
+        const int nsig_all = min(S.nsig, NVL);
+        int nsig = nsig_all;
+        if (total_views + nsig > C2G_VIEW_CAP) {
+          nsig = C2G_VIEW_CAP - total_views;
+          if (tid == 0) atomicOr(&S.status, 1);
+        }
+        for (int i = tid; i < nsig_all; i += K2_THREADS) {
+          const uint32_t ki = S.sig.key[i];
+          int rank = 0;
+          for (int j = 0; j < nsig_all; ++j) rank += (S.sig.key[j] < ki) ? 1 : 0;
+          if (rank < nsig) {
+            const int ci = S.sig.comp[i];
+            cw[ci * CW + 3] = ((uint32_t) rank << 16) | (cw[ci * CW + 3] & 0xFFFFu);
+            S.sortbuf[total_views + rank] = ((cw[ci * CW] & 0xFFFFu) << 16) | (uint32_t) rank;
+            S.vcomp[total_views + rank] = (uint16_t) ci;
+          }
+        }
+        if (tid == 0) {
+          S.n_views[lev] = nsig;
+          S.view_off[lev] = total_views;
+        }
+        total_views += nsig;
+        __syncthreads();
+      }
+      C2G_DBG(3);
+
+      // ---------------- phase C: per-level std::sort replays + moments / calcStatVals per component ------------------
+      // moment tasks by decreasing size class floor(log2(area)): the four components a warp walks together are alike
+      if (tid < 16) S.cls_cnt[tid] = 0;
+      if (tid == 0) S.wq = 0;
+      __syncthreads();
+      for (int v = tid; v < total_views; v += K2_THREADS) atomicAdd(&S.cls_cnt[__clz(S.sortbuf[v] >> 16) - 16], 1);
+      __syncthreads();
+      if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < 16; ++i) {
+          const int c = S.cls_cnt[i];
+          S.cls_cnt[i] = run;
+          run += c;
+        }
+      }
+      __syncthreads();
+      for (int v = tid; v < total_views; v += K2_THREADS) S.torder[atomicAdd(&S.cls_cnt[__clz(S.sortbuf[v] >> 16) - 16], 1)] = (uint16_t) v;
+      __syncthreads();
+      // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
+      // (contour_mng.h:596-599); one lane per level, on six different warps
+      if (lane == 0 && half == 0) {
+        uint32_t *first = S.sortbuf + S.view_off[lev_w];
+        int sum = 0;
+        for (int i = 0; i < S.n_views[lev_w]; ++i) sum += (int) (first[i] >> 16);
+        S.layer_cnt[lev_w] = sum;
+        c2g_sort::std_sort(first, (long) S.n_views[lev_w], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
+        C2G_DBG(20);
       }
       __syncwarp();
-      // B6 area / column extent / last run per component, and the in-component run chain (distance to the next run)
-      for (int id0 = 0; id0 < n; id0 += 32) {
-        const int id = id0 + lane;
-        const bool act = id < n;
-        uint32_t ci = 0xFFFFFFFFu;
-        int c0 = 0, len = 0;
-        if (act) {
-          const uint32_t inf = ri[id];
-          c0 = (inf >> 8) & 255;
-          len = (inf >> 16) & 255;
-          ci = comp_of(rp, (uint32_t) id);
-        }
-        const unsigned grp = __match_any_sync(FULL, ci);
-        const int a_sum = __reduce_add_sync(grp, len);
-        const int c_min = __reduce_min_sync(grp, c0);
-        const int c_max = __reduce_max_sync(grp, c0 + len - 1);
-        const int id_max = __reduce_max_sync(grp, id);
-        const unsigned below = grp & ((1u << lane) - 1u);
-        if (act) {
-          int pred = -1;
-          if (below)
-            pred = id0 + (31 - __clz(below));
-          else {  // first run of the component in this round: its predecessor is the last run of the earlier rounds
-            Comp e = cp[ci];
-            if (e.area) pred = e.last;
-            e.area = (uint16_t) (e.area + a_sum);
-            e.minc = (uint8_t) min((int) e.minc, c_min);
-            e.maxc = (uint8_t) max((int) e.maxc, c_max);
-            e.last = (uint16_t) id_max;
-            cp[ci] = e;
-          }
-          if (pred >= 0) ri[pred] |= (uint32_t) min(id - pred, 255) << 24;
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    C2G_DBG(2);
-    if (warp < C2G_NLEV) {
-      uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
-      Comp *cp = CP + S.comp_off[lev_w];
-      const int n = S.n_runs[lev_w], nc = S.n_comp[lev_w];
-      // B7 enclosing component of the previous level (looked up at the first pixel) and its bounding-box origin
-      if (lev_w > 0) {
-        const uint32_t *plp = S.plane[lev_w - 1];
-        const uint16_t *wpp = S.wpre[lev_w - 1];
-        const uint32_t *rpp = RP + S.run_off[lev_w - 1], *rip = RI + S.run_off[lev_w - 1];
-        const Comp *cpp = CP + S.comp_off[lev_w - 1];
-        for (int ci = lane; ci < nc; ci += 32) {
-          const uint32_t inf = ri[cp[ci].root];
-          const int row = inf & 255, c0 = (inf >> 8) & 255;
-          const int wi = c0 >> 5;
-          const uint32_t st = run_starts(plp + row * WPR, wi);
-          if (!((plp[row * WPR + wi] >> (c0 & 31)) & 1u)) continue;  // only if lv_grads is not increasing: no parent (pcomp stays 0xFFFF)
-          const int rid = (int) wpp[row * WPR + wi] + __popc(st & (FULL >> (31 - (c0 & 31)))) - 1;
-          const uint32_t pc = comp_of(rpp, (uint32_t) rid);
-          const Comp pe = cpp[pc];
-          cp[ci].pcomp = (uint16_t) pc;
-          cp[ci].y0 = (uint8_t) (rip[pe.root] & 255);
-          cp[ci].x0 = pe.minc;
-        }
-        __syncwarp();
-      }
-      // B8 first-2x2-block key relative to that origin: min over the runs (a run's minimum is at its first cell)
-      for (int id0 = 0; id0 < n; id0 += 32) {
-        const int id = id0 + lane;
-        const bool act = id < n;
-        uint32_t ci = 0xFFFFFFFFu;
-        int key = 0xFFFF;
-        if (act) {
-          const uint32_t inf = ri[id];
-          ci = comp_of(rp, (uint32_t) id);
-          const Comp e = cp[ci];
-          key = ((((int) (inf & 255) - (int) e.y0) >> 1) << 7) + ((((int) ((inf >> 8) & 255)) - (int) e.x0) >> 1);
-        }
-        const unsigned grp = __match_any_sync(FULL, ci);
-        const int kmin = __reduce_min_sync(grp, key);
-        if (act && !(grp & ((1u << lane) - 1u)) && kmin < (int) cp[ci].key) cp[ci].key = (uint16_t) kmin;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // B9 DFS order rank, level by level (the rank of a component needs the rank of its parent)
-    int total_views = 0;
-    for (int lev = 0; lev < C2G_NLEV; ++lev) {
-      Comp *cp = CP + S.comp_off[lev];
-      const Comp *cpp = lev ? CP + S.comp_off[lev - 1] : nullptr;
-      const int nc = S.n_comp[lev];
-      if (tid == 0) S.nsig = 0;
-      __syncthreads();
-      for (int ci = tid; ci < nc; ci += K2_THREADS) {
-        const Comp e = cp[ci];
-        if ((int) e.area >= cfg.min_cont_cell_cnt) {
-          const int i = atomicAdd(&S.nsig, 1);
-          if (i < NVL) {
-            const uint32_t prank = !lev ? 0u : e.pcomp == 0xFFFFu ? 0xFFFFu : (uint32_t) cpp[e.pcomp].rank;
-            S.sig.key[i] = (prank << 16) | (uint32_t) e.key;
-            S.sig.comp[i] = (uint16_t) ci;
-          } else
-            atomicOr(&S.status, 2);
-        }
-      }
-      __syncthreads();
-      const int nsig_all = min(S.nsig, NVL);
-      int nsig = nsig_all;
-      if (total_views + nsig > C2G_VIEW_CAP) {
-        nsig = C2G_VIEW_CAP - total_views;
-        if (tid == 0) atomicOr(&S.status, 1);
-      }
-      for (int i = tid; i < nsig_all; i += K2_THREADS) {
-        const uint32_t ki = S.sig.key[i];
-        int rank = 0;
-        for (int j = 0; j < nsig_all; ++j) rank += (S.sig.key[j] < ki) ? 1 : 0;
-        if (rank < nsig) {
-          const int ci = S.sig.comp[i];
-          cp[ci].rank = (uint16_t) rank;
-          S.sortbuf[total_views + rank] = ((uint32_t) cp[ci].area << 16) | (uint32_t) rank;
-          S.vcomp[total_views + rank] = (uint16_t) ci;
-        }
-      }
-      if (tid == 0) {
-        S.n_views[lev] = nsig;
-        S.view_off[lev] = total_views;
-      }
-      total_views += nsig;
-      __syncthreads();
-    }
-    C2G_DBG(3);
-
-    // ---------------- phase C: per-level std::sort replays + moments / calcStatVals per component --------------------
-    if (tid == 0) S.wq = 0;
-    __syncthreads();
-    // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
-    // (contour_mng.h:596-599); one lane per level, on six different warps
-    if (lane == 0 && warp < C2G_NLEV) {
-      uint32_t *first = S.sortbuf + S.view_off[warp];
-      int sum = 0;
-      for (int i = 0; i < S.n_views[warp]; ++i) sum += (int) (first[i] >> 16);
-      S.layer_cnt[warp] = sum;
-      c2g_sort::std_sort(first, (long) S.n_views[warp], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
-    }
-    __syncwarp();
-    {
-      // Moments: eight lanes per component, four components per warp step, handed out from a shared counter. Lane k of a
-      // group keeps ONE accumulator of RunningStatRecorder: sum of a_k * b_k over the member cells in raster order with
-      // (a, b) = (v0,1) (v1,1) (v0,v0) (v0,v1) (v1,v1) (h,v0) (h,v1); x * 1.0 is exact, the product of two floats is exact in
-      // double, so every lane performs exactly the reference's sequence of double additions.
-      const int k8 = lane & 7, grp4 = lane >> 3;
-      const uint32_t mA0 = (k8 == 0 || k8 == 2 || k8 == 3) ? FULL : 0u, mA1 = (k8 == 1 || k8 == 4) ? FULL : 0u,
-                     mAh = (k8 == 5 || k8 == 6) ? FULL : 0u, mAc = (k8 == 7) ? FULL : 0u;
-      const uint32_t mB0 = (k8 == 2 || k8 == 5) ? FULL : 0u, mB1 = (k8 == 3 || k8 == 4 || k8 == 6) ? FULL : 0u,
-                     mBc = (k8 == 0 || k8 == 1 || k8 == 7) ? FULL : 0u;
-      const uint32_t one = __float_as_uint(1.0f);
-      while (true) {
-        int v0 = 0;
-        if (lane == 0) v0 = atomicAdd(&S.wq, 4);
-        v0 = __shfl_sync(FULL, v0, 0);
-        if (v0 >= total_views) break;
-        const int v = v0 + grp4;
-        if (v < total_views) {
-          int lev = 0;
+      {
+        // Moments: eight lanes per component, four components per warp step, handed out from a shared counter. Lane k of a
+        // group keeps ONE accumulator of RunningStatRecorder: sum of a_k * b_k over the member cells in raster order with
+        // (a, b) = (v0,1) (v1,1) (v0,v0) (v0,v1) (v1,v1) (h,v0) (h,v1); x * 1.0 is exact, the product of two floats is exact in
+        // double, so every lane performs exactly the reference's sequence of double additions.  Lane 7 sums the heights in
+        // float.  The runs of a component are found by scanning the run ids between its first and last run, eight
+        // candidates per step (one per lane of the group).
+        const int k8 = lane & 7, g4 = lane >> 3;
+        const float *pa = (k8 == 0 || k8 == 2 || k8 == 3) ? rfg : (k8 == 1 || k8 == 4) ? cfp : hg;
+        const float *pb = (k8 == 2 || k8 == 5) ? rfg : cfp;
+        const bool b_one = k8 == 0 || k8 == 1 || k8 == 7;
+        while (true) {
+          int t0 = 0;
+          if (lane == 0) t0 = atomicAdd(&S.wq, 4);
+          t0 = __shfl_sync(FULL, t0, 0);
+          if (t0 >= total_views) break;
+          const int t = t0 + g4;
+          bool active = t < total_views;
+          int v = 0;
+          uint32_t ci = 0, rid = 0, last = 0;
+          const uint32_t *rp = RP, *ri = RI;
+          if (active) {
+            v = S.torder[t];
+            int lev = 0;
 #pragma unroll
-          for (int l = 1; l < C2G_NLEV; ++l)
-            if (v >= S.view_off[l]) lev = l;
-          const uint32_t *rp = RP + S.run_off[lev], *ri = RI + S.run_off[lev];
-          const uint32_t ci = S.vcomp[v];
-          const Comp e = (CP + S.comp_off[lev])[ci];
-          uint32_t rid = e.root;
+            for (int l = 1; l < C2G_NLEV; ++l)
+              if (v >= S.view_off[l]) lev = l;
+            ci = S.vcomp[v];
+            const uint32_t *cw = CWP + ((size_t) S.comp_off[lev] + ci) * CW;
+            rid = cw[0] >> 16;
+            last = cw[1] >> 16;
+            rp = RP + S.run_off[lev];
+            ri = RI + S.run_off[lev];
+          }
           double acc = 0.0;
           float vol3 = 0.0f;
-          while (true) {
-            const uint32_t inf = ri[rid];
-            const int cell = (int) (inf & 255) * ncol + (int) ((inf >> 8) & 255), len = (inf >> 16) & 255;
-            for (int j = 0; j < len; ++j) {
-              const float hh = hg[cell + j];
-              const uint32_t f0 = __float_as_uint(rfg[cell + j]), f1 = __float_as_uint(cfp[cell + j]), fh = __float_as_uint(hh);
-              const float fa = __uint_as_float((f0 & mA0) | (f1 & mA1) | (fh & mAh) | (one & mAc));
-              const float fb = __uint_as_float((f0 & mB0) | (f1 & mB1) | (one & mBc));
-              acc += (double) fa * (double) fb;
-              vol3 += hh;
+          while (__any_sync(FULL, active)) {
+            const uint32_t cand = rid + k8;
+            const bool mem = active && cand <= last && (rp[cand] & 0x7FFFFFFFu) == ci;
+            const unsigned bal = __ballot_sync(FULL, mem);
+            unsigned gb = (bal >> (g4 * 8)) & 0xFFu;
+            while (gb) {
+              const int tt = __ffs(gb) - 1;
+              gb &= gb - 1;
+              const uint32_t inf = ri[rid + tt];
+              const int cell = (int) (inf & 255) * ncol + (int) ((inf >> 8) & 255), len = (inf >> 16) & 255;
+              for (int j = 0; j < len; ++j) {
+                const float va = pa[cell + j];
+                const float vb = b_one ? 1.0f : pb[cell + j];
+                acc += (double) va * (double) vb;
+                vol3 += va;
+              }
             }
-            if (rid == e.last) break;
-            const uint32_t d = inf >> 24;
-            rid += d;
-            if (d == 255)
-              while (comp_of(rp, rid) != ci) ++rid;
+            rid += 8;
+            if (rid > last) active = false;
           }
           // raw moments go to the component's (still unused) 80-byte presort record: doubles 0..6 from lanes 0..6 of the
           // group, the float height sum in word 14
-          double *raw = reinterpret_cast<double *>(presort + v);
-          if (k8 < 7)
-            raw[k8] = acc;
-          else
-            reinterpret_cast<float *>(raw + 7)[0] = vol3;
+          if (t < total_views) {
+            double *raw = reinterpret_cast<double *>(presort + v);
+            if (k8 < 7)
+              raw[k8] = acc;
+            else
+              reinterpret_cast<float *>(raw + 7)[0] = vol3;
+          }
         }
       }
-    }
-    __syncthreads();
-    C2G_DBG(4);
-    for (int v = tid; v < total_views; v += K2_THREADS) {
-      int lev = 0;
+      C2G_DBG(21);
+      __syncthreads();
+      C2G_DBG(4);
+      for (int v = tid; v < total_views; v += K2_THREADS) {
+        int lev = 0;
 #pragma unroll
-      for (int l = 1; l < C2G_NLEV; ++l)
-        if (v >= S.view_off[l]) lev = l;
-      const Comp e = (CP + S.comp_off[lev])[S.vcomp[v]];
-      const uint32_t linf = (RI + S.run_off[lev])[e.last];
-      const double *raw = reinterpret_cast<const double *>(presort + v);
-      Moments m;
-      m.cnt = e.area;
-      m.s0 = raw[0];
-      m.s1 = raw[1];
-      m.t00 = raw[2];
-      m.t01 = raw[3];
-      m.t11 = raw[4];
-      m.q0 = raw[5];
-      m.q1 = raw[6];
-      m.vol3 = reinterpret_cast<const float *>(raw + 7)[0];
-      c2g_view vw;
-      calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
-      presort[v] = vw;  // in place: this thread is the only reader and writer of the record
-    }
+        for (int l = 1; l < C2G_NLEV; ++l)
+          if (v >= S.view_off[l]) lev = l;
+        const uint32_t *cw = CWP + ((size_t) S.comp_off[lev] + S.vcomp[v]) * CW;
+        const uint32_t linf = (RI + S.run_off[lev])[cw[1] >> 16];
+        const double *raw = reinterpret_cast<const double *>(presort + v);
+        Moments m;
+        m.cnt = (int) (cw[0] & 0xFFFFu);
+        m.s0 = raw[0];
+        m.s1 = raw[1];
+        m.t00 = raw[2];
+        m.t01 = raw[3];
+        m.t11 = raw[4];
+        m.q0 = raw[5];
+        m.q1 = raw[6];
+        m.vol3 = reinterpret_cast<const float *>(raw + 7)[0];
+        c2g_view vw;
+        calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
+        presort[v] = vw;  // in place: this thread is the only reader and writer of the record
+      }
+    };
+    if (S.runs_in_arena || S.comps_in_arena)
+      stage2(std::true_type{});
+    else
+      stage2(std::false_type{});
     __syncthreads();
     if (tid == 0 && S.arena >= 0) {  // the run / component tables are dead from here on
       __threadfence();
@@ -900,7 +952,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
           }
           const unsigned bal = __ballot_sync(FULL, pass);
           if (pass) {
-            const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+            const int pos = cnt + __popc(bal & lt_mask);
             if (pos < KEY_LIST_CAP) {
               klist_dist[a * KEY_LIST_CAP + pos] = dist;
               klist_hc[a * KEY_LIST_CAP + pos] = hc;
@@ -919,35 +971,69 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     }
     __syncthreads();
     C2G_DBG(6);
-    // D2: one thread per (anchor, division): sequential float accumulation in raster order
+    // D2: one thread per (anchor, division): sequential float accumulation in raster order. The exp evaluations of four
+    // consecutive cells are independent straight-line code (the FP64 latency chains overlap); their float terms are then
+    // added in order.
     {
       const float div_len = cfg.roi_radius / (float) ((C2G_KEY_DIM - 3) * 5);
       const double inv_norm_den = sqrt(2 * 3.14159265358979323846 * 1.0f * 1.0f);
       const double rcp_norm_den = 1.0 / inv_norm_den;
-      for (int w = tid; w < N_ANCH * N_DIVS; w += K2_THREADS) {
-        const int a = w / N_DIVS, d = w - a * N_DIVS;
-        const int n = min(S.cnt_point[a], KEY_LIST_CAP);
-        float acc = 0.0f;
-        if (n > 0) {
-          const float x = (float) ((double) ((float) d * div_len) + 0.5 * (double) div_len);
-          const float *dl = klist_dist + a * KEY_LIST_CAP;
-          const uint8_t *hl = klist_hc + a * KEY_LIST_CAP;
-          for (int k = 0; k < n; ++k) {
-            const float t = (x - dl[k]) / 1.0f;
-            const double q = (-0.5 * (double) t) * (double) t;
-            const double e = c2g_exp(q, P.exp_mode, c2g_exp_tab_dev);
-            // (float) (e / den): the product with the rounded reciprocal is within 2.5 ulp of the correctly rounded
-            // quotient, so both round to the same float unless the product sits within a few ulp of a float rounding
-            // midpoint (low 29 mantissa bits == 0x10000000); only then is the real division executed.
-            double pq = e * rcp_norm_den;
-            const unsigned long long low = (unsigned long long) __double_as_longlong(pq) & 0x1FFFFFFFull;
-            if (low - 0x0FFFFFF8ull <= 0x10ull) pq = e / inv_norm_den;
-            const float g = (float) pq;
-            acc += (float) hl[k] * g;
+      // (float) (e / den): the product with the rounded reciprocal is within 2.5 ulp of the correctly rounded quotient, so
+      // both round to the same float unless the product sits within a few ulp of a float rounding midpoint (low 29
+      // mantissa bits == 0x10000000); only then is the real division executed.
+      auto near_mid = [](double pq) { return ((unsigned long long) __double_as_longlong(pq) & 0x1FFFFFFFull) - 0x0FFFFFF8ull <= 0x10ull; };
+      auto d2 = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int w = tid; w < N_ANCH * N_DIVS; w += K2_THREADS) {
+          const int a = w / N_DIVS, d = w - a * N_DIVS;
+          const int n = min(S.cnt_point[a], KEY_LIST_CAP);
+          float acc = 0.0f;
+          if (n > 0) {
+            const float x = (float) ((double) ((float) d * div_len) + 0.5 * (double) div_len);
+            const float *dl = klist_dist + a * KEY_LIST_CAP;
+            const uint8_t *hl = klist_hc + a * KEY_LIST_CAP;
+            int k = 0;
+            if (MODE != 0) {
+              for (; k + 4 <= n; k += 4) {
+                double q[4], pq[4];
+                bool special = false, mid = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float t = (x - dl[k + u]) / 1.0f;
+                  q[u] = (-0.5 * (double) t) * (double) t;
+                  pq[u] = c2g_exp_glibc_main<MODE == 2>(q[u], c2g_exp_tab_dev, &special) * rcp_norm_den;
+                  mid |= near_mid(pq[u]);
+                }
+                if (special || mid) {  // rare: redo the four terms through the full functions
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const double e = c2g_exp(q[u], MODE, c2g_exp_tab_dev);
+                    pq[u] = e * rcp_norm_den;
+                    if (near_mid(pq[u])) pq[u] = e / inv_norm_den;
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += (float) hl[k + u] * (float) pq[u];
+              }
+            }
+            for (; k < n; ++k) {
+              const float t = (x - dl[k]) / 1.0f;
+              const double q = (-0.5 * (double) t) * (double) t;
+              const double e = c2g_exp(q, MODE, c2g_exp_tab_dev);
+              double pq = e * rcp_norm_den;
+              if (near_mid(pq)) pq = e / inv_norm_den;
+              acc += (float) hl[k] * (float) pq;
+            }
           }
+          S.divs[a][d] = acc;
         }
-        S.divs[a][d] = acc;
-      }
+      };
+      if (P.exp_mode == 2)
+        d2(std::integral_constant<int, 2>{});
+      else if (P.exp_mode == 1)
+        d2(std::integral_constant<int, 1>{});
+      else
+        d2(std::integral_constant<int, 0>{});
     }
     __syncthreads();
     for (int w = tid; w < N_ANCH * C2G_KEY_DIM; w += K2_THREADS) {
@@ -1078,12 +1164,28 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       S.n_ell[tid] = k;
     }
     __syncthreads();
+    // The pair term is symmetric in (i, j) bit for bit, so only j >= i is evaluated (off-diagonal terms count twice); rows
+    // i and n - 1 - i are folded into one line of n + 1 entries to keep the index arithmetic division-only.
     double acc = 0.0;
     for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
       const int n = S.n_ell[li];
       const c2g_ell *le = eout + S.view_off[li + 1];
-      for (int w = tid; w < n * n; w += K2_THREADS) {
-        const int i = w / n, j = w - i * n;
+      const int R = n >> 1, folded = R * (n + 1), total = folded + (n & 1) * ((n + 1) >> 1);
+      for (int w = tid; w < total; w += K2_THREADS) {
+        int i, j;
+        if (w < folded) {
+          const int r = w / (n + 1), c = w - r * (n + 1);
+          if (c < n - r) {
+            i = r;
+            j = r + c;
+          } else {
+            i = n - 1 - r;
+            j = i + (c - (n - r));
+          }
+        } else {
+          i = R;
+          j = R + (w - folded);
+        }
         const c2g_ell A = le[i], Bv = le[j];
         const double c00 = 2.0 * ((double) A.c00 + (double) Bv.c00), c10 = 2.0 * ((double) A.c10 + (double) Bv.c10);
         const double c01 = 2.0 * ((double) A.c01 + (double) Bv.c01), c11 = 2.0 * ((double) A.c11 + (double) Bv.c11);
@@ -1091,7 +1193,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         const double det = c00 * c11 - c01 * c10;
         const double invdet = 1.0 / det;
         const double qf = mx * ((c11 * invdet) * mx + (-c01 * invdet) * my) + my * ((-c10 * invdet) * mx + (c00 * invdet) * my);
-        acc += (double) A.w * (double) Bv.w / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
+        const double term = (double) A.w * (double) Bv.w / sqrt(det) * c2g_exp(-0.5 * qf, P.exp_mode, c2g_exp_tab_dev);
+        acc += (i == j) ? term : 2.0 * term;
       }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
@@ -1117,6 +1220,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     C2G_DBG(9);
   }
 }
+
 
 }  // namespace
 
@@ -1144,9 +1248,38 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   int *locks = reinterpret_cast<int *>(k2_scratch + (size_t) max_ctas * KLIST_BYTES);
   unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES + 256;
   C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
-  contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev,
-                                                             first_slot, bev_h, bev_rf, bev_cf, presort_scratch, heads, views, ells, klists,
-                                                             locks, arenas, work_counter, dbg);
+  contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev, first_slot, bev_h,
+                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, locks, arenas,
+                                                             work_counter, dbg);
+  C2G_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Dense BEV image of ONE scan of the last batch, on demand (c2g_get_bev: ContourManager::getBevImage + bev_pixfs_): every
+// occupied cell gets its height and the winner's continuous coordinates, empty cells the reference's initial values.
+// `offsets[b]` is read on the device: the offsets of the last batch live there.
+namespace {
+__global__ void bev_fill_entry(const c2g_cellkey *tile, const float4 *pts, const long long *offsets, int b, C2gIngestParams P,
+                               float *bev_h, float *bev_rf, float *bev_cf) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.n_cells) return;
+  const float4 *p = pts + offsets[b];
+  const c2g_cellkey k = tile[c];
+  float h = -1000.0f, rf = -1.0f, cf = -1.0f;
+  if (k != 0ull) {
+    const float2 xy = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k));
+    h = c2g_from_orderable((uint32_t) (k >> 32));
+    rf = (xy.x / P.cfg.reso_row + P.half_row_f) - 0.5f;
+    cf = (xy.y / P.cfg.reso_col + P.half_col_f) - 0.5f;
+  }
+  bev_h[c] = h;
+  bev_rf[c] = rf;
+  bev_cf[c] = cf;
+}
+}  // namespace
+int c2g_launch_bev_fill(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
+                        float *bev_h, float *bev_rf, float *bev_cf, cudaStream_t stream) {
+  bev_fill_entry<<<(P.n_cells + 255) / 256, 256, 0, stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, b, P, bev_h, bev_rf, bev_cf);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

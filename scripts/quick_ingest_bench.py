@@ -48,3 +48,8 @@ capi.lib().c2g_debug_clocks(eng.h, clk.ctypes.data_as(C.c_void_p))
 names = {0:'start',1:'A done',2:'label+stats',3:'ranks done',4:'sort+moments',5:'calcstat+copy',6:'D1 done',7:'D2+keys done',8:'BCI done',9:'GMM/end'}
 t0 = clk[0]
 for i in range(10): print(f"  {names[i]:14s} {(clk[i]-t0)/1e3:9.1f} kcyc  (+{(clk[i]-clk[max(i-1,0)])/1e3:.1f})")
+fine = {10:'B1 count+barrier',12:'decide+B2 records',13:'B3 unions',14:'B4 flatten',15:'barrier+decide',16:'B5 slots',2:'B6 stats+barrier',18:'B7 parents',19:'B8 keys+barrier'}
+prev = clk[1]
+for i in [10,12,13,14,15,16,2,18,19]:
+    print(f"    {fine[i]:18s} +{(clk[i]-prev)/1e3:.1f} kcyc"); prev = clk[i]
+print(f"    ranks +{(clk[3]-clk[19])/1e3:.1f}; torder+sort(level 0) +{(clk[20]-clk[3])/1e3:.1f}; warp0 moments done +{(clk[21]-clk[20])/1e3:.1f}; barrier +{(clk[4]-clk[21])/1e3:.1f} kcyc")
