@@ -24,6 +24,7 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
 int c2g_contour_max_ctas(int num_sms);
 size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row);
 int c2g_query_alloc(c2g_ctx *ctx);
+int c2g_db_sync_mode(c2g_ctx *ctx, int want_kd);  // query.cu
 void c2g_query_free(c2g_ctx *ctx);
 int c2g_refine_alloc(c2g_ctx *ctx);  // refine.cu
 void c2g_refine_free(c2g_ctx *ctx);
@@ -214,6 +215,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   }
   c2g_hostdb_init(*ctx->hostdb, db_cfg->n_q_levels, db_cfg->max_elapse, db_cfg->min_elapse);
   ctx->db_dirty = 0;
+  ctx->db_not_kd = 0;
   *out = ctx;
   return 0;
 }
@@ -247,6 +249,17 @@ int c2g_destroy(c2g_ctx *ctx) {
   cudaFree(ctx->d_k2_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+  return 0;
+}
+
+int c2g_host_alloc(void **out, size_t bytes) {
+  if (!out || bytes == 0) return C2G_ERR_ARG;
+  C2G_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+
+int c2g_host_free(void *p) {
+  if (p) C2G_CUDA_TRY(cudaFreeHost(p));
   return 0;
 }
 
@@ -414,28 +427,11 @@ int c2g_db_size(c2g_ctx *ctx) { return ctx ? ctx->hostdb->n_scans : C2G_ERR_ARG;
 
 int c2g_db_sync(c2g_ctx *ctx) {
   if (!ctx) return C2G_ERR_ARG;
-  if (!ctx->db_dirty) return 0;
-  std::vector<float> keys;
-  std::vector<int> gidx;
-  std::vector<signed char> seq;
-  std::vector<unsigned char> bucket;
-  for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
-    const C2gLayerHost &L = ctx->hostdb->layers[ll];
-    keys.clear();
-    gidx.clear();
-    seq.clear();
-    bucket.clear();
-    for (int b = 0; b < C2G_NUM_BUCKETS; ++b)
-      for (const C2gKeyRec &r : L.buckets[b].tree) {
-        keys.insert(keys.end(), r.k, r.k + C2G_KEY_DIM);
-        gidx.push_back(r.gidx);
-        seq.push_back((signed char) r.seq);
-        bucket.push_back((unsigned char) b);
-      }
-    int rc = c2g_db_set_layer(ctx, ll, (int) gidx.size(), keys.data(), gidx.data(), seq.data(), bucket.data(), L.ranges);
-    if (rc) return rc;
-  }
+  if (!ctx->db_dirty && !ctx->db_not_kd) return 0;
+  int rc = c2g_db_sync_mode(ctx, 1);  // query.cu: patches the mirror, kd-blocks every bucket
+  if (rc) return rc;
   ctx->db_dirty = 0;
+  ctx->db_not_kd = 0;
   return 0;
 }
 

@@ -3,23 +3,25 @@
 #include "c2g_common.cuh"
 
 #define C2G_MAX_CHUNK_EVENTS 64
-#define C2G_QUERY_STREAMS 4  // sub-batches of one c2g_query_async call that may run concurrently
+#define C2G_QUERY_STREAMS 8  // sub-batches of one c2g_query_async call that may run concurrently
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
-struct C2gKdCache;  // host-side memo of the kd ordering of every bucket (query.cu)
-
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
-  float *keys_t;         // [C2G_KEY_DIM][cap] transposed for coalesced scans, bucket-major, tree order inside a bucket
+  // Bucket k owns the fixed region [k * cap_b, (k + 1) * cap_b) of every per-key array and [k * blkcap_b, ..) of the block
+  // arrays, so that a change in one bucket never moves the entries of another.
+  float *keys_t;         // [C2G_KEY_DIM][C2G_NUM_BUCKETS * cap_b] transposed for coalesced scans
   int *gidx;             // IndexOfKey::gidx
   signed char *seq;      // IndexOfKey::seq
-  int *orank;            // flat tree-order index of every entry (tie-break rank; the mirror itself is kd-ordered inside a bucket)
-  float *box_min, *box_max;  // [C2G_KEY_DIM][blk_cap]: bounding box of every 32-key block (block j of bucket k = keys
-                             // [bucket_off[k] + 32 j, +32) clipped to the bucket), blocks numbered bucket-major
-  C2gKdCache *kd_cache;
-  int n, cap, blk_cap;
-  int blk_off[C2G_NUM_BUCKETS + 1];
-  int bucket_off[C2G_NUM_BUCKETS + 1];
+  int *orank;            // region base + position in TREE order (tie-break rank; the mirror itself may be kd-ordered)
+  float *box_min, *box_max;  // [C2G_KEY_DIM][C2G_NUM_BUCKETS * blkcap_b]: bounding box of every 32-key block
+  int cap_b, blkcap_b;
+  int bucket_cnt[C2G_NUM_BUCKETS];
   float ranges[C2G_NUM_BUCKETS + 1];
+  // what the mirror currently holds per bucket (c2g_db_sync patches the difference to the host trees)
+  int m_n[C2G_NUM_BUCKETS];             // entries mirrored
+  unsigned m_rv[C2G_NUM_BUCKETS];       // C2gBucket::restructured at that time
+  unsigned char m_kd[C2G_NUM_BUCKETS];  // mirrored in kd-blocked order (batch queries) or in tree order (online loop)
+  unsigned char m_valid[C2G_NUM_BUCKETS];
 };
 
 struct C2gHostDB;  // host-side LayerDB state (layer_db_host.h)
@@ -63,8 +65,12 @@ struct c2g_ctx {
   uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
   int pair_cap;
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
+  void *h_patch, *d_patch;     // staging of mirror patches (records + block descriptors), pinned host / device
+  size_t patch_cap;
+  cudaEvent_t ev_patch;        // the last patch upload has left h_patch
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state
+  int db_not_kd;           // some buckets of the mirror are in tree order (fine for the online loop, slow for big batches)
   // optional per-kernel timing of the query path (c2g_query_profile): event k is recorded after kernel k - 1
   int prof_on;
   cudaEvent_t prof_ev[C2G_QPROF_N + 1];

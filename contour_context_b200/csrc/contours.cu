@@ -534,18 +534,33 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         const uint32_t *pr = pl + (row - 1) * WPR;
         const uint16_t *wpr = wp + (row - 1) * WPR;
         int first = -1, extra = 0;
-        for (int wi = lo >> 5; wi <= (hi >> 5); ++wi) {
-          uint32_t m = pr[wi];
-          if (wi == (lo >> 5)) m &= FULL << (lo & 31);
-          if (wi == (hi >> 5)) m &= FULL >> (31 - (hi & 31));
-          if (!m) continue;
-          const uint32_t st = run_starts(pr, wi);
-          if (first < 0) {
-            const int pb = __ffs(m) - 1;
-            first = (int) wpr[wi] + __popc(st & (FULL >> (31 - pb))) - 1;  // the run that contains bit pb
-            extra += __popc(st & m & ~(FULL >> (31 - pb)));                // runs that start further right inside the window
-          } else
-            extra += __popc(st & m);
+        const int w0 = lo >> 5;
+        if ((hi >> 5) <= w0 + 1) {
+          // common case, branch-free: the window lies inside two adjacent words of the row above
+          const uint64_t two = (uint64_t) pr[w0] | ((uint64_t) (w0 + 1 < WPR ? pr[w0 + 1] : 0u) << 32);
+          const uint64_t st = two & ~((two << 1) | (uint64_t) (w0 ? pr[w0 - 1] >> 31 : 0u));
+          const int sh = lo & 31, wl = hi - lo + 1;
+          const uint64_t m = two & ((wl >= 64 ? ~0ull : ((1ull << wl) - 1ull)) << sh);
+          if (m) {
+            const int pb = __ffsll((long long) m) - 1;
+            const uint64_t upto = ~0ull >> (63 - pb);
+            first = (int) wpr[w0] + __popcll(st & upto) - 1;  // the run that contains bit pb
+            extra = __popcll(st & m & ~upto);                 // runs that start further right inside the window
+          }
+        } else {
+          for (int wi = w0; wi <= (hi >> 5); ++wi) {
+            uint32_t m = pr[wi];
+            if (wi == w0) m &= FULL << (lo & 31);
+            if (wi == (hi >> 5)) m &= FULL >> (31 - (hi & 31));
+            if (!m) continue;
+            const uint32_t st = run_starts(pr, wi);
+            if (first < 0) {
+              const int pb = __ffs(m) - 1;
+              first = (int) wpr[wi] + __popc(st & (FULL >> (31 - pb))) - 1;
+              extra += __popc(st & m & ~(FULL >> (31 - pb)));
+            } else
+              extra += __popc(st & m);
+          }
         }
         if (first >= 0)
           for (int j = 0; j <= extra; ++j) uf_union(rp, (uint32_t) id, (uint32_t) (first + j));
@@ -801,11 +816,19 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
               gb &= gb - 1;
               const uint32_t inf = ri[rid + tt];
               const int cell = (int) (inf & 255) * ncol + (int) ((inf >> 8) & 255), len = (inf >> 16) & 255;
-              for (int j = 0; j < len; ++j) {
-                const float va = pa[cell + j];
-                const float vb = b_one ? 1.0f : pb[cell + j];
-                acc += (double) va * (double) vb;
-                vol3 += va;
+              for (int j0 = 0; j0 < len; j0 += 4) {  // four independent loads in flight; a padding term adds 0 * 1 = +0.0
+                float va[4], vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const bool in = j0 + u < len;
+                  va[u] = in ? pa[cell + j0 + u] : 0.0f;
+                  vb[u] = (in && !b_one) ? pb[cell + j0 + u] : 1.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  acc += (double) va[u] * (double) vb[u];
+                  vol3 += va[u];
+                }
               }
             }
             rid += 8;

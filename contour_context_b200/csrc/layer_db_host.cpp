@@ -141,7 +141,8 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
     }
     return;
   }
-  move_tail(big, lit, perm, num_to_move, split_val, donor_is_lower);
+  move_tail(big, lit, perm, num_to_move, split_val, donor_is_lower);  // `big` is permuted and cut, `lit` only grows
+  big.restructured++;
   move_buffer(big, lit, split_val, donor_is_lower);
   tr1.end = tr2.beg = split_val;
   L.ranges[idx_t1 + 1] = split_val;
@@ -163,6 +164,7 @@ void c2g_hostdb_init(C2gHostDB &db, int n_layers, double max_elapse, double min_
     C2gLayerHost &L = db.layers[l];
     for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
       L.buckets[i].tree.clear();
+      L.buckets[i].restructured++;
       L.buckets[i].buffer.clear();
       L.buckets[i].beg = L.buckets[i].end = kMaxBucketVal;
       L.ranges[i] = kMaxBucketVal;

@@ -27,6 +27,9 @@ struct C2gBucket {
   float beg, end;
   std::vector<C2gKeyRec> tree;    // data_tree_ + gkidx_tree_
   std::vector<C2gBufRec> buffer;  // buffer_
+  // bumped whenever existing tree entries move or disappear; between two bumps the tree only grows at its end, which is
+  // what lets the device mirror (query.cu) be patched instead of rebuilt
+  unsigned restructured = 0;
 };
 struct C2gLayerHost {
   C2gBucket buckets[C2G_NUM_BUCKETS];

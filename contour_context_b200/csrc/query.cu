@@ -18,6 +18,7 @@
 // (q-level, query seq, ascending key distance).
 #include "../../include/c2g.h"
 #include "c2g_ctx.cuh"
+#include "layer_db_host.h"
 #include <algorithm>
 #include <vector>
 
@@ -37,11 +38,11 @@ struct LayerDev {
   const float *keys_t;  // [KEY_DIM][cap]
   const int *gidx;
   const signed char *seq;
-  const int *orank;     // flat index in bucket-major TREE order (what the entry's position would be without the kd ordering)
+  const int *orank;     // bucket-major TREE order rank (what the entry's position would be without the kd ordering)
   const float *box_min, *box_max;  // [KEY_DIM][blk_cap] bounding boxes of the 32-key blocks
-  int cap, blk_cap;
-  int blk_off[C2G_NUM_BUCKETS + 1];
-  int bucket_off[C2G_NUM_BUCKETS + 1];  // keys of bucket k occupy [bucket_off[k], bucket_off[k+1]), kd-ordered in blocks of 32
+  int cap, blk_cap;     // row strides of keys_t / box_*: C2G_NUM_BUCKETS * cap_b, C2G_NUM_BUCKETS * blkcap_b
+  int cap_b, blkcap_b;  // keys of bucket k occupy [k * cap_b, k * cap_b + bucket_cnt[k]), in blocks of 32 from k * blkcap_b
+  int bucket_cnt[C2G_NUM_BUCKETS];
   float ranges[C2G_NUM_BUCKETS + 1];
 };
 struct QueryParams {
@@ -200,9 +201,9 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
     };
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
       if (!((visit >> bk) & 1u)) continue;
-      const int beg = T.bucket_off[bk], end = T.bucket_off[bk + 1];
+      const int beg = bk * T.cap_b, end = beg + T.bucket_cnt[bk];
       if (beg >= end) continue;
-      const int b0 = T.blk_off[bk], nb = T.blk_off[bk + 1] - b0;
+      const int b0 = bk * T.blkcap_b, nb = (T.bucket_cnt[bk] + 31) >> 5;
       // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
       float best = 3.0e38f;
       int best_j = 0x7FFFFFFF;
@@ -1323,6 +1324,7 @@ finish_output_kernel(int q0, int B, const FinHead *__restrict__ fin_head, const 
 
 }  // namespace
 int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int q0, int B, cudaStream_t st);  // refine.cu
+int c2g_db_sync_mode(c2g_ctx *ctx, int want_kd);
 namespace {
 
 int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &Q) {
@@ -1337,13 +1339,12 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
     Q.layer[i].orank = t.orank;
     Q.layer[i].box_min = t.box_min;
     Q.layer[i].box_max = t.box_max;
-    Q.layer[i].blk_cap = t.blk_cap;
-    Q.layer[i].cap = t.cap;
-    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
-      Q.layer[i].bucket_off[k] = t.bucket_off[k];
-      Q.layer[i].blk_off[k] = t.blk_off[k];
-      Q.layer[i].ranges[k] = t.ranges[k];
-    }
+    Q.layer[i].cap_b = t.cap_b;
+    Q.layer[i].blkcap_b = t.blkcap_b;
+    Q.layer[i].cap = C2G_NUM_BUCKETS * t.cap_b;
+    Q.layer[i].blk_cap = C2G_NUM_BUCKETS * t.blkcap_b;
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) Q.layer[i].bucket_cnt[k] = t.bucket_cnt[k];
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) Q.layer[i].ranges[k] = t.ranges[k];
   }
   Q.nnk = ctx->db.nnk;
   Q.piv = ctx->P.cfg.piv_firsts;
@@ -1382,13 +1383,47 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int q0, int B, const QueryParams
 
 // kd ordering of one bucket, memoised by content: a growing database changes one or two buckets per pushAndBalance
 // (contour_db.cpp:63-317), the others keep their blocks
-struct C2gKdCache {
-  uint64_t hash[C2G_NUM_BUCKETS];
-  std::vector<int> order[C2G_NUM_BUCKETS];  // bucket-relative tree positions in mirror order
-  C2gKdCache() {
-    for (auto &h : hash) h = 0;
-  }
+// ---- device mirror of the LayerDB trees: patch records + kernels ------------------------------------------------------------
+struct PatchRec {  // one key entering (or moving inside) the mirror
+  float k[C2G_KEY_DIM];
+  int gidx, pos, orank, seq;
 };
+struct PatchBlk {  // one 32-key block whose bounding box must be recomputed
+  int blk, p0, cnt;
+};
+static_assert(sizeof(PatchRec) == 56 && sizeof(PatchBlk) == 12, "patch layout");
+
+__global__ void mirror_patch_kernel(const PatchRec *__restrict__ recs, int n, float *__restrict__ keys_t, int stride, int *__restrict__ gidx,
+                                    signed char *__restrict__ seq, int *__restrict__ orank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PatchRec r = recs[i];
+#pragma unroll
+  for (int d = 0; d < C2G_KEY_DIM; ++d) keys_t[(size_t) d * stride + r.pos] = r.k[d];
+  gidx[r.pos] = r.gidx;
+  seq[r.pos] = (signed char) r.seq;
+  orank[r.pos] = r.orank;
+}
+// one warp per listed block: bounding box of its (<= 32) keys; NaN keys never match anything and fminf / fmaxf ignore them
+__global__ void mirror_box_kernel(const PatchBlk *__restrict__ blks, int n, const float *__restrict__ keys_t, int stride,
+                                  float *__restrict__ box_min, float *__restrict__ box_max, int blk_stride) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const PatchBlk b = blks[w];
+  for (int d = 0; d < C2G_KEY_DIM; ++d) {
+    const float first = keys_t[(size_t) d * stride + b.p0];
+    const float v = lane < b.cnt ? keys_t[(size_t) d * stride + b.p0 + lane] : first;
+    float mn = v, mx = v;
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    }
+    if (lane == 0) {
+      box_min[(size_t) d * blk_stride + b.blk] = mn;
+      box_max[(size_t) d * blk_stride + b.blk] = mx;
+    }
+  }
+}
 
 int c2g_query_alloc(c2g_ctx *ctx) {
   ctx->n_hint_slots = (long long) ctx->max_batch * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
@@ -1406,23 +1441,28 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   C2G_CUDA_TRY(cudaMalloc(&ctx->d_fin_cand, sizeof(FinCand) * (size_t) ctx->max_batch * C2G_MAX_CAND));
   for (int i = 0; i < ctx->db.n_q_levels; ++i) {
     C2gLayerTable &t = ctx->layers[i];
-    t.cap = ctx->scan_cap * C2G_MAX_PIV;
-    t.n = 0;
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.keys_t, sizeof(float) * C2G_KEY_DIM * (size_t) t.cap));
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * (size_t) t.cap));
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, (size_t) t.cap));
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.orank, sizeof(int) * (size_t) t.cap));
-    t.kd_cache = new (std::nothrow) C2gKdCache();
-    if (!t.kd_cache) return C2G_ERR_CAPACITY;
-    t.blk_cap = t.cap / 32 + C2G_NUM_BUCKETS + 1;
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_min, sizeof(float) * C2G_KEY_DIM * (size_t) t.blk_cap));
-    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_max, sizeof(float) * C2G_KEY_DIM * (size_t) t.blk_cap));
-    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
-      t.bucket_off[k] = 0;
-      t.blk_off[k] = 0;
-      t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
+    t.cap_b = ctx->scan_cap * C2G_MAX_PIV;  // any bucket may end up holding every key of the layer
+    t.blkcap_b = t.cap_b / 32 + 1;
+    const size_t cap = (size_t) C2G_NUM_BUCKETS * t.cap_b, bcap = (size_t) C2G_NUM_BUCKETS * t.blkcap_b;
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.keys_t, sizeof(float) * C2G_KEY_DIM * cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.orank, sizeof(int) * cap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_min, sizeof(float) * C2G_KEY_DIM * bcap));
+    C2G_CUDA_TRY(cudaMalloc((void **) &t.box_max, sizeof(float) * C2G_KEY_DIM * bcap));
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+      t.bucket_cnt[k] = 0;
+      t.m_n[k] = 0;
+      t.m_rv[k] = 0;
+      t.m_kd[k] = 0;
+      t.m_valid[k] = 0;
     }
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
   }
+  ctx->patch_cap = 1 << 20;
+  C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ctx->patch_cap, cudaHostAllocDefault));
+  C2G_CUDA_TRY(cudaMalloc(&ctx->d_patch, ctx->patch_cap));
+  C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_patch, cudaEventDisableTiming));
   return 0;
 }
 
@@ -1446,9 +1486,159 @@ void c2g_query_free(c2g_ctx *ctx) {
     cudaFree(ctx->layers[i].orank);
     cudaFree(ctx->layers[i].box_min);
     cudaFree(ctx->layers[i].box_max);
-    delete ctx->layers[i].kd_cache;
-    ctx->layers[i].kd_cache = nullptr;
   }
+  if (ctx->h_patch) cudaFreeHost(ctx->h_patch);
+  cudaFree(ctx->d_patch);
+  if (ctx->ev_patch) cudaEventDestroy(ctx->ev_patch);
+}
+
+extern "C" {
+
+}  // extern "C"
+
+namespace {
+
+// kd ordering of one bucket for batched queries: the range is split at a multiple of 32 keys along its widest dimension
+// (nth_element), recursively, until one 32-key block remains.  order[p] = tree position of the key mirrored at position p.
+void kd_order(const C2gKeyRec *tree, int n, std::vector<int> &order) {
+  order.resize((size_t) n);
+  for (int p = 0; p < n; ++p) order[p] = p;
+  std::vector<std::pair<int, int>> stack;
+  stack.emplace_back(0, n);
+  while (!stack.empty()) {
+    const int lo = stack.back().first, hi = stack.back().second;
+    stack.pop_back();
+    const int m = hi - lo;
+    if (m <= 32) continue;
+    float mn[C2G_KEY_DIM], mx[C2G_KEY_DIM];
+    for (int d = 0; d < C2G_KEY_DIM; ++d) mn[d] = mx[d] = tree[order[lo]].k[d];
+    for (int p = lo + 1; p < hi; ++p) {
+      const float *kp = tree[order[p]].k;
+      for (int d = 0; d < C2G_KEY_DIM; ++d) {
+        mn[d] = kp[d] < mn[d] ? kp[d] : mn[d];
+        mx[d] = kp[d] > mx[d] ? kp[d] : mx[d];
+      }
+    }
+    int wd = 0;
+    float wspan = -1.0f;
+    for (int d = 0; d < C2G_KEY_DIM; ++d)
+      if (mx[d] - mn[d] > wspan) {
+        wspan = mx[d] - mn[d];
+        wd = d;
+      }
+    const int nblk = (m + 31) / 32, left = (nblk / 2) * 32;
+    std::nth_element(order.begin() + lo, order.begin() + lo + left, order.begin() + hi, [&](int a, int b2) {
+      const float ka = tree[a].k[wd], kb = tree[b2].k[wd];
+      return ka < kb || (ka == kb && a < b2);
+    });
+    stack.emplace_back(lo, lo + left);
+    stack.emplace_back(lo + left, hi);
+  }
+}
+
+// Collects the patch of one layer in host vectors: bucket k of the mirror must end up holding `tree` (n keys).
+struct LayerPatch {
+  std::vector<PatchRec> recs;
+  std::vector<PatchBlk> blks;
+};
+void patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out) {
+  const int base = k * t.cap_b, bbase = k * t.blkcap_b;
+  const bool grown_only = t.m_valid[k] && t.m_rv[k] == rv && !t.m_kd[k] && n >= t.m_n[k];
+  const bool need_kd = want_kd && n > 32;  // a bucket of one block has nothing to order
+  int from = 0;
+  bool kd = false;
+  if (grown_only && !(need_kd && !t.m_kd[k])) {
+    if (n == t.m_n[k]) {
+      return;  // unchanged
+    }
+    from = t.m_n[k];  // append in tree order
+  } else if (t.m_valid[k] && t.m_rv[k] == rv && n == t.m_n[k] && (t.m_kd[k] || !need_kd)) {
+    return;  // unchanged (kd-ordered mirror of an unchanged tree)
+  } else {
+    kd = need_kd;
+  }
+  std::vector<int> order;
+  if (kd) kd_order(tree, n, order);
+  for (int p = from; p < n; ++p) {
+    const int tp = kd ? order[p] : p;
+    PatchRec r;
+    for (int d = 0; d < C2G_KEY_DIM; ++d) r.k[d] = tree[tp].k[d];
+    r.gidx = tree[tp].gidx;
+    r.seq = tree[tp].seq;
+    r.pos = base + p;
+    r.orank = base + tp;
+    out.recs.push_back(r);
+  }
+  for (int j = from / 32; j < (n + 31) / 32; ++j) {
+    PatchBlk bl;
+    bl.blk = bbase + j;
+    bl.p0 = base + 32 * j;
+    bl.cnt = n - 32 * j < 32 ? n - 32 * j : 32;
+    out.blks.push_back(bl);
+  }
+  t.bucket_cnt[k] = n;
+  t.m_n[k] = n;
+  t.m_rv[k] = rv;
+  t.m_kd[k] = kd ? 1 : 0;
+  t.m_valid[k] = 1;
+}
+
+// uploads one layer's patch and applies it on the context stream (everything asynchronous; the pinned staging buffer is
+// reused only after the previous upload has left it)
+int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
+  if (lp.recs.empty() && lp.blks.empty()) return 0;
+  const size_t rb = lp.recs.size() * sizeof(PatchRec), bb = lp.blks.size() * sizeof(PatchBlk), rb_al = (rb + 255) / 256 * 256;
+  if (rb_al + bb > ctx->patch_cap) {
+    C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    size_t ncap = ctx->patch_cap;
+    while (ncap < rb_al + bb) ncap *= 2;
+    cudaFreeHost(ctx->h_patch);
+    cudaFree(ctx->d_patch);
+    ctx->h_patch = ctx->d_patch = nullptr;
+    C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ncap, cudaHostAllocDefault));
+    C2G_CUDA_TRY(cudaMalloc(&ctx->d_patch, ncap));
+    ctx->patch_cap = ncap;
+  }
+  // the device staging buffer is free once the kernels of the previous patch are done: they run on the same stream
+  C2G_CUDA_TRY(cudaEventSynchronize(ctx->ev_patch));
+  memcpy(ctx->h_patch, lp.recs.data(), rb);
+  memcpy((char *) ctx->h_patch + rb_al, lp.blks.data(), bb);
+  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_patch, ctx->h_patch, rb_al + bb, cudaMemcpyHostToDevice, ctx->stream));
+  C2G_CUDA_TRY(cudaEventRecord(ctx->ev_patch, ctx->stream));
+  const int stride = C2G_NUM_BUCKETS * t.cap_b, bstride = C2G_NUM_BUCKETS * t.blkcap_b;
+  if (!lp.recs.empty())
+    mirror_patch_kernel<<<(unsigned) ((lp.recs.size() + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) ctx->d_patch, (int) lp.recs.size(), t.keys_t,
+                                                                                          stride, t.gidx, t.seq, t.orank);
+  if (!lp.blks.empty())
+    mirror_box_kernel<<<(unsigned) ((lp.blks.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>((const PatchBlk *) ((const char *) ctx->d_patch + rb_al),
+                                                                                             (int) lp.blks.size(), t.keys_t, stride, t.box_min, t.box_max, bstride);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 2;
+  return 0;
+}
+
+}  // namespace
+
+// Brings the device mirror up to date with the host trees by patching what changed since the last call: keys appended to a
+// tree (the common case of the online loop: LayerDB::rebuild pops aged buffer entries to the END of a tree) are appended to
+// the bucket's region; a bucket whose tree was permuted or cut by a rebalancing move is rewritten.  want_kd: kd-block the
+// buckets (worth it for batched queries over a static DB; the online loop mirrors in tree order).
+int c2g_db_sync_mode(c2g_ctx *ctx, int want_kd) {
+  if (!ctx) return C2G_ERR_ARG;
+  for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+    const C2gLayerHost &L = ctx->hostdb->layers[ll];
+    C2gLayerTable &t = ctx->layers[ll];
+    LayerPatch lp;
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+      const C2gBucket &bk = L.buckets[k];
+      if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
+      patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, want_kd != 0, lp);
+    }
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
+    int rc = apply_patch(ctx, t, lp);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 extern "C" {
@@ -1457,153 +1647,28 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
                      const unsigned char *bucket_host, const float *bucket_ranges_host) {
   if (!ctx || ll < 0 || ll >= ctx->db.n_q_levels || n < 0 || !bucket_ranges_host) return C2G_ERR_ARG;
   C2gLayerTable &t = ctx->layers[ll];
-  if (n > t.cap) return C2G_ERR_CAPACITY;
   if (n > 0 && (!keys_host || !gidx_host || !seq_host || !bucket_host)) return C2G_ERR_ARG;
-  // bucket-major, tree order inside a bucket (stable counting sort on the host), keys transposed for coalesced scans
-  int cnt[C2G_NUM_BUCKETS + 1] = {0};
+  std::vector<C2gKeyRec> trees[C2G_NUM_BUCKETS];
   for (int i = 0; i < n; ++i) {
     if (bucket_host[i] >= C2G_NUM_BUCKETS) return C2G_ERR_ARG;
-    cnt[bucket_host[i] + 1]++;
+    C2gKeyRec r;
+    for (int d = 0; d < C2G_KEY_DIM; ++d) r.k[d] = keys_host[(size_t) i * C2G_KEY_DIM + d];
+    r.gidx = gidx_host[i];
+    r.seq = seq_host[i];
+    trees[bucket_host[i]].push_back(r);
   }
-  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) cnt[k + 1] += cnt[k];
-  for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) {
-    t.bucket_off[k] = cnt[k];
-    t.ranges[k] = bucket_ranges_host[k];
+  LayerPatch lp;
+  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+    if ((int) trees[k].size() > t.cap_b) return C2G_ERR_CAPACITY;
+    t.m_valid[k] = 0;  // caller-provided contents: always rewritten, and the next c2g_db_sync rewrites them again
+    patch_bucket(t, k, trees[k].data(), (int) trees[k].size(), 0u, true, lp);
+    t.m_valid[k] = 0;
   }
-  t.blk_off[0] = 0;
-  for (int k = 0; k < C2G_NUM_BUCKETS; ++k) t.blk_off[k + 1] = t.blk_off[k] + (cnt[k + 1] - cnt[k] + 31) / 32;
-  t.n = n;
-  if (n == 0) return 0;
-  float *kt = (float *) malloc(sizeof(float) * C2G_KEY_DIM * (size_t) n);
-  int *gi = (int *) malloc(sizeof(int) * (size_t) n);
-  signed char *sq = (signed char *) malloc((size_t) n);
-  if (!kt || !gi || !sq) {
-    free(kt);
-    free(gi);
-    free(sq);
-    return C2G_ERR_CAPACITY;
-  }
-  // bucket-major positions in tree order first (the tie-break rank), then a kd ordering inside every bucket: the range is
-  // split at a multiple of 32 keys along its widest dimension (nth_element), recursively, until one 32-key block remains
-  std::vector<int> perm((size_t) n), rank_of((size_t) n);
-  {
-    int pos[C2G_NUM_BUCKETS];
-    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) pos[k] = cnt[k];
-    for (int i = 0; i < n; ++i) {
-      const int p = pos[bucket_host[i]]++;
-      perm[p] = i;  // flat tree-order position p holds input key i
-    }
-    std::vector<int> order((size_t) n);
-    for (int p = 0; p < n; ++p) order[p] = p;
-    std::vector<float> fk((size_t) n * C2G_KEY_DIM);  // keys in flat tree order: one indirection less in the loops below
-    for (int p = 0; p < n; ++p)
-      for (int d = 0; d < C2G_KEY_DIM; ++d) fk[(size_t) p * C2G_KEY_DIM + d] = keys_host[(size_t) perm[p] * C2G_KEY_DIM + d];
-    auto key_of = [&](int flat, int d) { return fk[(size_t) flat * C2G_KEY_DIM + d]; };
-    std::vector<std::pair<int, int>> stack;
-    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
-      // content hash of the bucket's tree (keys, gidx, seq in tree order); an unchanged bucket reuses its ordering
-      uint64_t h = 1469598103934665603ull ^ (uint64_t) (cnt[k + 1] - cnt[k]);
-      for (int p = cnt[k]; p < cnt[k + 1]; ++p) {
-        const int i = perm[p];
-        uint32_t w[C2G_KEY_DIM + 2];
-        memcpy(w, &fk[(size_t) p * C2G_KEY_DIM], sizeof(float) * C2G_KEY_DIM);
-        w[C2G_KEY_DIM] = (uint32_t) gidx_host[i];
-        w[C2G_KEY_DIM + 1] = (uint32_t) (unsigned char) seq_host[i];
-        for (int q = 0; q < C2G_KEY_DIM + 2; ++q) h = (h ^ w[q]) * 1099511628211ull;
-      }
-      h |= 1ull;  // 0 = empty cache slot
-      C2gKdCache &kc = *t.kd_cache;
-      if (kc.hash[k] == h && (int) kc.order[k].size() == cnt[k + 1] - cnt[k]) {
-        for (int p = cnt[k]; p < cnt[k + 1]; ++p) order[p] = cnt[k] + kc.order[k][p - cnt[k]];
-        continue;
-      }
-      stack.clear();
-      stack.emplace_back(cnt[k], cnt[k + 1]);
-      while (!stack.empty()) {
-        const int lo = stack.back().first, hi = stack.back().second;
-        stack.pop_back();
-        const int m = hi - lo;
-        if (m <= 32) continue;
-        float mn[C2G_KEY_DIM], mx[C2G_KEY_DIM];
-        for (int d = 0; d < C2G_KEY_DIM; ++d) mn[d] = mx[d] = key_of(order[lo], d);
-        for (int p = lo + 1; p < hi; ++p) {
-          const float *kp = &fk[(size_t) order[p] * C2G_KEY_DIM];
-          for (int d = 0; d < C2G_KEY_DIM; ++d) {
-            mn[d] = kp[d] < mn[d] ? kp[d] : mn[d];
-            mx[d] = kp[d] > mx[d] ? kp[d] : mx[d];
-          }
-        }
-        int wd = 0;
-        float wspan = -1.0f;
-        for (int d = 0; d < C2G_KEY_DIM; ++d)
-          if (mx[d] - mn[d] > wspan) {
-            wspan = mx[d] - mn[d];
-            wd = d;
-          }
-        const int nblk = (m + 31) / 32, left = (nblk / 2) * 32;
-        std::nth_element(order.begin() + lo, order.begin() + lo + left, order.begin() + hi, [&](int a, int b) {
-          const float ka = key_of(a, wd), kb = key_of(b, wd);
-          return ka < kb || (ka == kb && a < b);
-        });
-        stack.emplace_back(lo, lo + left);
-        stack.emplace_back(lo + left, hi);
-      }
-      kc.hash[k] = h;
-      kc.order[k].resize((size_t) (cnt[k + 1] - cnt[k]));
-      for (int p = cnt[k]; p < cnt[k + 1]; ++p) kc.order[k][p - cnt[k]] = order[p] - cnt[k];
-    }
-    for (int p = 0; p < n; ++p) rank_of[p] = order[p];  // mirror position p holds flat tree-order position order[p]
-  }
-  int *ork = (int *) malloc(sizeof(int) * (size_t) n);
-  if (!ork) {
-    free(kt);
-    free(gi);
-    free(sq);
-    return C2G_ERR_CAPACITY;
-  }
-  for (int p = 0; p < n; ++p) {
-    const int flat = rank_of[p], i = perm[flat];
-    for (int d = 0; d < C2G_KEY_DIM; ++d) kt[(size_t) d * n + p] = keys_host[(size_t) i * C2G_KEY_DIM + d];
-    gi[p] = gidx_host[i];
-    sq[p] = seq_host[i];
-    ork[p] = flat;
-  }
-  // bounding box of every 32-key block
-  const int nblk_total = t.blk_off[C2G_NUM_BUCKETS];
-  std::vector<float> bmin((size_t) C2G_KEY_DIM * nblk_total), bmax((size_t) C2G_KEY_DIM * nblk_total);
-  for (int k = 0; k < C2G_NUM_BUCKETS; ++k)
-    for (int j = 0; j < t.blk_off[k + 1] - t.blk_off[k]; ++j) {
-      const int p0 = cnt[k] + 32 * j, p1 = p0 + 32 < cnt[k + 1] ? p0 + 32 : cnt[k + 1];
-      for (int d = 0; d < C2G_KEY_DIM; ++d) {
-        float mn = kt[(size_t) d * n + p0], mx = mn;  // NaN keys never match anything; min/max below ignore them
-        for (int p = p0 + 1; p < p1; ++p) {
-          const float v = kt[(size_t) d * n + p];
-          mn = fminf(mn, v);
-          mx = fmaxf(mx, v);
-        }
-        bmin[(size_t) d * nblk_total + t.blk_off[k] + j] = mn;
-        bmax[(size_t) d * nblk_total + t.blk_off[k] + j] = mx;
-      }
-    }
-  cudaError_t e = cudaSuccess;
-  for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d) {
-    e = cudaMemcpyAsync(t.box_min + (size_t) d * t.blk_cap, bmin.data() + (size_t) d * nblk_total, sizeof(float) * (size_t) nblk_total,
-                        cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(t.box_max + (size_t) d * t.blk_cap, bmax.data() + (size_t) d * nblk_total, sizeof(float) * (size_t) nblk_total,
-                          cudaMemcpyHostToDevice, ctx->stream);
-  }
-  for (int d = 0; d < C2G_KEY_DIM && e == cudaSuccess; ++d)
-    e = cudaMemcpyAsync(t.keys_t + (size_t) d * t.cap, kt + (size_t) d * n, sizeof(float) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(t.gidx, gi, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(t.seq, sq, (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(t.orank, ork, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  free(kt);
-  free(gi);
-  free(sq);
-  free(ork);
-  return e == cudaSuccess ? 0 : -(int) e;
+  for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = bucket_ranges_host[k];
+  int rc = apply_patch(ctx, t, lp);
+  if (rc) return rc;
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub) {
@@ -1613,9 +1678,15 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
         lb->i_indiv_sim < ub->i_indiv_sim && lb->i_orie_sim < ub->i_orie_sim && lb->correlation < ub->correlation &&
         lb->area_perc < ub->area_perc && lb->neg_est_dist < ub->neg_est_dist))
     return C2G_ERR_ARG;
-  if (ctx->db_dirty) {
-    int rc = c2g_db_sync(ctx);
-    if (rc) return rc;
+  {
+    // the online loop (small B) mirrors the trees in tree order (cheap appends); batched queries kd-block the buckets once
+    const int want_kd = B >= 32;
+    if (ctx->db_dirty || (want_kd && ctx->db_not_kd)) {
+      int rc = c2g_db_sync_mode(ctx, want_kd);
+      if (rc) return rc;
+      ctx->db_dirty = 0;
+      ctx->db_not_kd = want_kd ? 0 : 1;
+    }
   }
   QueryParams Q;
   build_query_params(ctx, lb, Q);

@@ -17,18 +17,17 @@
 
 SequentialTimeProfiler stp;  // the library's stage timers write here, like the reference executable
 
-static std::vector<float> readKITTIBin(const std::string &path) {  // tools/pointcloud_util.h:12-50 (format: N x 4 f32)
-  std::vector<float> buf;
+// tools/pointcloud_util.h:12-50 (format: N x 4 f32, at most 1 000 000 floats): reads straight into the runtime's page-locked
+// scan buffer, returns the number of points
+static size_t readKITTIBin(const std::string &path, float *buf, size_t cap_floats) {
   FILE *f = std::fopen(path.c_str(), "rb");
   if (!f) {
     std::printf("Lidar bin file %s does not exist.\n", path.c_str());
     std::exit(-1);
   }
-  buf.resize(1000000);
-  size_t n = std::fread(buf.data(), sizeof(float), buf.size(), f) / 4;
+  const size_t n = std::fread(buf, sizeof(float), cap_floats, f) / 4;
   std::fclose(f);
-  buf.resize(n * 4);
-  return buf;
+  return n;
 }
 
 int main(int argc, char **argv) {
@@ -108,8 +107,9 @@ int main(int argc, char **argv) {
     stp.lap();
     stp.start();
     std::shared_ptr<ContourManager> ptr_cm_tgt(new ContourManager(cm_config, seq));
-    std::vector<float> bin = readKITTIBin(path);
-    ptr_cm_tgt->makeBEVFromBin(bin.data(), bin.size() / 4, "assigned_id_" + std::to_string(seq));
+    float *bin = ContourManager::pinnedScanBuffer(1000000);
+    const size_t n_points = readKITTIBin(path, bin, 1000000);
+    ptr_cm_tgt->makeBEVFromBin(bin, n_points, "assigned_id_" + std::to_string(seq));
     ptr_cm_tgt->makeContoursRecurs();
     stp.record("make bev");
     ptr_cm_tgt->clearImage();

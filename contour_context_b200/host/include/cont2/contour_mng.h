@@ -131,6 +131,8 @@ class ContourManager {
   std::string str_id_;
   int int_id_;
   std::vector<float> pts_;  // staged x, y, z, 0 of the scan between makeBEV and makeContoursRecurs
+  const float *ext_pts_ = nullptr;  // ... or the caller's pinned buffer (pinnedScanBuffer), not copied
+  size_t ext_n_ = 0;
   int slot_ = -1;           // device slot of the finished descriptor
   bool owns_slot_ = false;
   c2g_scan_head head_;
@@ -159,6 +161,11 @@ class ContourManager {
   }
   // makeBEV straight from a KITTI .bin buffer (N x 4 float32), skipping the PCL detour
   void makeBEVFromBin(const float *xyzi, size_t n_points, std::string str_id);
+  // A reusable page-locked buffer of `n_floats` floats for readKITTIPointCloudBin-style loaders (tools/pointcloud_util.h:17:
+  // the reference reads at most 1 000 000 floats per scan).  A scan handed to makeBEVFromBin from this buffer is not copied
+  // on the host: it goes to the device with one asynchronous PCIe transfer.  The buffer must stay untouched until
+  // makeContoursRecurs() of that scan has returned.
+  static float *pinnedScanBuffer(size_t n_floats = 1000000);
 
   void makeContoursRecurs();  // BEV + contours + keys + BCI on the GPU (c2g_ingest)
   void clearImage() {}        // the BEV never leaves device scratch memory

@@ -202,10 +202,18 @@ class ContLCDEvaluator {
   std::shared_ptr<ContourManager> getCurrContourManager(const ContourManagerConfig &config) const {  // evaluator.h:285-302
     const LaserScanInfo &info = getCurrScanInfo();
     std::shared_ptr<ContourManager> cmng_ptr(new ContourManager(config, info.seq));
-    const std::vector<float> bin = readKITTIPointCloudBinRaw(info.fpath);
+    // the .bin goes straight into the runtime's page-locked scan buffer (one asynchronous PCIe transfer, no host copy)
+    float *bin = ContourManager::pinnedScanBuffer(1000000);
+    FILE *f = std::fopen(info.fpath.c_str(), "rb");
+    if (!f) {
+      std::printf("Lidar bin file %s does not exist.\n", info.fpath.c_str());
+      std::exit(-1);
+    }
+    const size_t n_points = std::fread(bin, sizeof(float), 1000000, f) / 4;
+    std::fclose(f);
     std::string str_id = std::to_string(info.seq);
     str_id = "assigned_id_" + std::string(8 - std::min<size_t>(8, str_id.length()), '0') + str_id;
-    cmng_ptr->makeBEVFromBin(bin.data(), bin.size() / 4, str_id);
+    cmng_ptr->makeBEVFromBin(bin, n_points, str_id);
     cmng_ptr->makeContoursRecurs();
     return cmng_ptr;
   }

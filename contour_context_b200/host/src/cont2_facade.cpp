@@ -130,13 +130,38 @@ ContourManager::~ContourManager() {
   if (owns_slot_ && slot_ >= 0) runtime().release(slot_);
 }
 
+namespace {
+float *g_pinned_buf = nullptr;
+size_t g_pinned_floats = 0;
+}  // namespace
+
+float *ContourManager::pinnedScanBuffer(size_t n_floats) {
+  if (n_floats > g_pinned_floats) {
+    if (g_pinned_buf) C2G_CHECK(c2g_host_free(g_pinned_buf));
+    void *p = nullptr;
+    C2G_CHECK(c2g_host_alloc(&p, n_floats * sizeof(float)));
+    g_pinned_buf = static_cast<float *>(p);
+    g_pinned_floats = n_floats;
+  }
+  return g_pinned_buf;
+}
+
 void ContourManager::makeBEVFromBin(const float *xyzi, size_t n_points, std::string str_id) {
-  pts_.assign(xyzi, xyzi + 4 * n_points);
+  if (g_pinned_buf && xyzi >= g_pinned_buf && xyzi + 4 * n_points <= g_pinned_buf + g_pinned_floats) {
+    ext_pts_ = xyzi;  // page-locked and owned by the runtime: no host copy
+    ext_n_ = n_points;
+    pts_.clear();
+  } else {
+    ext_pts_ = nullptr;
+    pts_.assign(xyzi, xyzi + 4 * n_points);
+  }
   str_id_ = std::move(str_id);
 }
 
 void ContourManager::makeContoursRecurs() {
-  if (pts_.size() / 4 <= 10) {  // CHECK_GT(ptr_gapc->size(), 10) of makeBEV (contour_mng.h:507)
+  const float *src = ext_pts_ ? ext_pts_ : pts_.data();
+  const size_t n_points = ext_pts_ ? ext_n_ : pts_.size() / 4;
+  if (n_points <= 10) {  // CHECK_GT(ptr_gapc->size(), 10) of makeBEV (contour_mng.h:507)
     std::fprintf(stderr, "CHECK failed: point cloud has <= 10 points\n");
     std::abort();
   }
@@ -145,14 +170,15 @@ void ContourManager::makeContoursRecurs() {
     slot_ = rt.acquire();
     owns_slot_ = true;
   }
-  const long long offsets[2] = {0, (long long) (pts_.size() / 4)};
-  C2G_CHECK(c2g_ingest(rt.ctx, pts_.data(), offsets, 1, 0, slot_, &int_id_));
+  const long long offsets[2] = {0, (long long) n_points};
+  C2G_CHECK(c2g_ingest(rt.ctx, src, offsets, 1, 0, slot_, &int_id_));
   C2G_CHECK(c2g_get_heads(rt.ctx, slot_, 1, &head_));
   if (head_.status != 0) {
     std::fprintf(stderr, "CHECK failed: scan %d exceeded a descriptor capacity (status %d)\n", int_id_, head_.status);
     std::abort();
   }
   std::vector<float>().swap(pts_);
+  ext_pts_ = nullptr;
   views_loaded_ = false;
   for (size_t ll = 0; ll < cfg_.lv_grads_.size(); ++ll) {
     layer_keys_[ll].clear();

@@ -53,6 +53,12 @@ int c2g_sync(c2g_ctx *ctx);
 int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
                const int *int_ids_host);
 
+/* Page-locked host memory for point buffers handed to c2g_ingest (the buffer readKITTIPointCloudBin fills,
+ * include/tools/pointcloud_util.h:17-30): the host -> device copy of a pinned buffer runs at PCIe speed and asynchronously,
+ * a pageable one is bounced through driver staging. Plumbing only (cudaHostAlloc / cudaFreeHost). */
+int c2g_host_alloc(void **out, size_t bytes);
+int c2g_host_free(void *p);
+
 /* Individual stages of c2g_ingest for profiling and parity tests (same arguments; `first_slot` as above). */
 int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device);
 

@@ -145,3 +145,51 @@ def test_query_is_deterministic_and_async_path_agrees(world):
     _, h_dev, s_dev, _ = eng.query_buffers()
     c = eng.finish_from_scores(q_first, N_SCENES, lb, h_dev, s_dev)
     assert a.tobytes() == c.tobytes()
+
+
+def test_incremental_mirror_matches_full_rebuild(built_lib):
+    """The device mirror of the LayerDB trees is patched scan by scan in the online loop (tree order, appended keys only) and
+    kd-blocked for batched queries.  Every mode and every transition between them must answer a query identically:
+    engine A grows the DB with a single-scan query after every insertion (append patches, occasional bucket rewrites after a
+    rebalancing move), then serves a 40-scan batch (kd rewrite), more insertions and single-scan queries again; engine B
+    builds the same DB in one go."""
+    from contour_context_b200.engine import Engine
+
+    n_db, n_pts, n_probe = 96, 30000, 40
+    lb, ub = D.kitti_thres()
+    seeds, visits = synth.db_layout(n_db, 4, first_scene=300)
+    pts, offsets = make_batch(seeds, visits, n_pts, noise_seed=11)
+    probe, poff = make_batch(list(range(300, 300 + n_probe)), [5] * n_probe, n_pts, noise_seed=12)
+    a = Engine(scan_capacity=n_db + n_probe + 8, max_batch=n_probe, max_points=n_probe * 32768)
+    b = Engine(scan_capacity=n_db + n_probe + 8, max_batch=n_probe, max_points=n_probe * 32768)
+    try:
+        for e in (a, b):
+            e.ingest(probe, poff, first_slot=n_db, int_ids=np.arange(5000, 5000 + n_probe))
+        online = {}
+        ts = lambda i: 2.0 * i  # noqa: E731  (2 s apart: keys become searchable after a few scans, rebalancing moves happen)
+
+        def insert(e, i):
+            e.ingest(pts[offsets[i]:offsets[i + 1]], np.array([0, n_pts], np.int64), first_slot=i, int_ids=np.array([i]))
+            e.db_add_scans(i, 1, [ts(i)])
+            e.db_push_and_balance(i, ts(i))
+
+        for i in range(64):
+            insert(a, i)
+            online[i] = a.query(n_db + i % n_probe, 1, lb, ub).tobytes()   # tree-order mirror, patched every scan
+        batch_a64 = a.query(n_db, n_probe, lb, ub).tobytes()               # kd-blocked rewrite of every bucket
+        for i in range(64, n_db):
+            insert(a, i)
+            online[i] = a.query(n_db + i % n_probe, 1, lb, ub).tobytes()   # kd buckets that grow fall back to tree order
+        batch_a = a.query(n_db, n_probe, lb, ub).tobytes()
+        for i in range(n_db):
+            insert(b, i)
+            if i == 63:
+                assert b.query(n_db, n_probe, lb, ub).tobytes() == batch_a64
+            if i % 9 == 0 or i == n_db - 1:
+                assert b.query(n_db + i % n_probe, 1, lb, ub).tobytes() == online[i], f"single-scan query after insertion {i} differs"
+        assert b.query(n_db, n_probe, lb, ub).tobytes() == batch_a
+        res = np.frombuffer(batch_a, D.QUERY_RESULT_DTYPE)
+        assert int((res["n_cand"] > 0).sum()) >= n_probe // 4, "the comparison must cover real candidates"
+    finally:
+        a.close()
+        b.close()
