@@ -34,9 +34,9 @@ N_PTS = 120000
 VISITS = 4
 
 
-# DRAM traffic per 120k-point scan measured by `ncu --set full` (profiles/r1_ncu_full_summary.csv, one 296-scan launch each):
-# (dram__bytes_read.sum + dram__bytes_write.sum) / 296.  Algorithmic bytes are 1.92 MB (K1) and 1.98 MB (K1+K2) per scan.
-NCU_DRAM_BYTES_PER_SCAN = {"bev_scatter_kernel": (568.490752e6 + 7.416064e6) / 296, "contour_kernel": (375.015424e6 + 92.196096e6) / 296}
+# DRAM traffic per 120k-point scan measured by `ncu --set full` (profiles/r1e_ncu_full_summary.csv, one 592-scan launch each):
+# (dram__bytes_read.sum + dram__bytes_write.sum) / 592.  Algorithmic bytes are 1.92 MB (K1) and 1.98 MB (K1+K2) per scan.
+NCU_DRAM_BYTES_PER_SCAN = {"bev_scatter_kernel": (1.136680e9 + 51.249920e6) / 592, "contour_kernel": (0.305138e9 + 87.707648e6) / 592}
 
 
 def parse():
@@ -310,7 +310,7 @@ def run_b200(args):
                          "traffic": Q * (NCU_DRAM_BYTES_PER_SCAN["bev_scatter_kernel"] + NCU_DRAM_BYTES_PER_SCAN["contour_kernel"])
                          if n_pts == 120000 else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per scan from the ncu --set full capture in "
-                                           "profiles/r1_ncu_full_summary.csv (296-scan launch), scaled to this launch's scan count",
+                                           "profiles/r1e_ncu_full_summary.csv (592-scan launch), scaled to this launch's scan count",
                          "kernel": "bev_scatter_kernel + contour_kernel (ingest pair, 1.98 MB algorithmic bytes per scan)",
                          "peak_source": peak_src,
                          "bev_scatter_only": {"achieved": ach_bev, "frac": ach_bev / peak, "ms": kern["bev_scatter_ms"]},
