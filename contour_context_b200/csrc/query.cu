@@ -608,6 +608,16 @@ __device__ void score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
   const int cand = hint.cand_gidx, level = hint.level, cseq = hint.cand_seq, qseq = hint.q_seq;
   const c2g_bci &src = heads[cand].bcis[level][cseq];
   const c2g_bci &tgt = heads[q_slot].bcis[level][qseq];
+  {
+    // both 608-byte records are walked below through dependent indices (seg -> nei -> bit_pos): pull their lines into L1 now,
+    // with independent requests, instead of paying one L2 round trip per step of those chains
+    const char *ps = reinterpret_cast<const char *>(&src), *pt = reinterpret_cast<const char *>(&tgt);
+#pragma unroll
+    for (int o = 0; o < (int) sizeof(c2g_bci) + 127; o += 128) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (o < (int) sizeof(c2g_bci) ? o : (int) sizeof(c2g_bci) - 1)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pt + (o < (int) sizeof(c2g_bci) ? o : (int) sizeof(c2g_bci) - 1)));
+    }
+  }
   unsigned long long pot[MAX_POT_PAIRS];  // (orie_diff bits << 32) | level << 16 | seq_src << 8 | seq_tgt
   CPairD c2[MAX_POT_PAIRS + 1];
   uint8_t drop[MAX_POT_PAIRS + 1];
