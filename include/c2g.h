@@ -66,7 +66,9 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
 int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host);
 int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host /* C2G_VIEW_CAP records */);
 /* Dense BEV of scan `batch_index` of the LAST ingest batch: ContourManager::getBevImage (:573-586) plus the
- * continuous pillar coordinates bev_pixfs_ (:435); empty cells are -1000 / -1 / -1. Each array holds n_row*n_col. */
+ * continuous pillar coordinates bev_pixfs_ (:435); empty cells are -1000 / -1 / -1. Each array holds n_row*n_col.
+ * The image is assembled on demand from the batch's cell keys and its points (the ingest kernels only materialise the
+ * cells that belong to a contour), so a device-resident points buffer handed to the last c2g_ingest must still be alive. */
 int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f);
 /* Raw 64-bit BEV cell keys of the last batch (debug / K1 parity). */
 int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host);
