@@ -54,6 +54,20 @@ __device__ __forceinline__ void scatter_point(const float4 pt, const uint32_t id
   if (key > *(volatile c2g_cellkey *) cell) atomicMax(cell, key);
 }
 
+// Branch-free first half of scatter_point<true>: cell and key of a point, key 0 (never wins a max) for a rejected point.
+// Same tests in the same float arithmetic; a NaN coordinate fails the first comparison exactly like in the branchy form.
+__device__ __forceinline__ void point_key_unit(const float4 pt, const uint32_t idx, const C2gIngestParams &P, int &cell, c2g_cellkey &key) {
+  const float x = pt.x, y = pt.y;
+  bool ok = (fabsf(x) <= P.x_max_pad) && (fabsf(y) <= P.y_max_pad);
+  ok = ok && !(__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq);
+  const int row = __float2int_rd(x) + P.half_row, col = __float2int_rd(y) + P.half_col;
+  ok = ok && row > 0;  // `rc.first > 0` (contour_mng.h:515)
+  const float h = __fadd_rn(P.cfg.lidar_height, pt.z);
+  ok = ok && (h > -1000.0f);  // bev_ starts at -1000 and only strictly higher points are stored
+  cell = ok ? row * P.cfg.n_col + col : 0;
+  key = ok ? (((c2g_cellkey) c2g_orderable(h) << 32) | (c2g_cellkey) (0xFFFFFFFFu - idx)) : 0ull;
+}
+
 template <bool UNIT>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P,
@@ -74,8 +88,22 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
       float4 v[K1_UNROLL];
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) v[u] = ld_stream_f4(p + i + u * K1_THREADS);
+      if (UNIT) {
+        // keys of all UNROLL points first (straight-line code), then all filter reads of the tile, then the atomics: the
+        // shared-memory latencies of the eight points overlap instead of adding up behind five branches per point
+        int cell[K1_UNROLL];
+        c2g_cellkey key[K1_UNROLL], cur[K1_UNROLL];
 #pragma unroll
-      for (int u = 0; u < K1_UNROLL; ++u) scatter_point<UNIT>(v[u], (uint32_t) (i + u * K1_THREADS), P, tile);
+        for (int u = 0; u < K1_UNROLL; ++u) point_key_unit(v[u], (uint32_t) (i + u * K1_THREADS), P, cell[u], key[u]);
+#pragma unroll
+        for (int u = 0; u < K1_UNROLL; ++u) cur[u] = *(volatile c2g_cellkey *) (tile + cell[u]);
+#pragma unroll
+        for (int u = 0; u < K1_UNROLL; ++u)
+          if (key[u] > cur[u]) atomicMax(tile + cell[u], key[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < K1_UNROLL; ++u) scatter_point<UNIT>(v[u], (uint32_t) (i + u * K1_THREADS), P, tile);
+      }
     }
     for (; i < n; i += K1_THREADS) scatter_point<UNIT>(ld_stream_f4(p + i), (uint32_t) i, P, tile);
     __syncthreads();
