@@ -980,8 +980,11 @@ __device__ __forceinline__ bool gmm_pair_selected(double qx, double qy, float qx
   return c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (amaj + b.maj));
 }
 
+// The warps of the CTA share one pose: warp w takes the source ellipses w, w + n_warps, ... of every level (own queue, own
+// partial cost); the partial costs are added in warp order, so the result does not depend on scheduling.
 __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells, int src_slot, int tgt_slot, const double T[4], int lane,
-                                uint32_t *queue /* 64 words of shared memory owned by this warp */) {
+                                int warp, int n_warps, uint32_t *queue /* 64 words of shared memory owned by this warp */,
+                                double *partial /* n_warps doubles of shared memory */) {
   const double theta = atan2(T[1], T[0]);
   const double c = cos(theta), s = sin(theta);
   const c2g_ell *se_all = ells + (size_t) src_slot * C2G_VIEW_CAP, *te_all = ells + (size_t) tgt_slot * C2G_VIEW_CAP;
@@ -1016,7 +1019,7 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells,
       b.mx = b.my = 1.0e30f;
       b.maj = 0.0f;
       if (ti < nt) b = te_all[to + ti];
-      for (int si = 0; si < ns; ++si) {
+      for (int si = warp; si < ns; si += n_warps) {
         const c2g_ell a = se_all[so + si];  // warp-wide broadcast
         const double amx = (double) a.mx, amy = (double) a.my;
         const double qx = (T[0] * amx + (-T[1]) * amy) + T[2], qy = (T[1] * amx + T[0] * amy) + T[3];
@@ -1040,6 +1043,10 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells,
   }
   eval_queued(qn);
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+  if (lane == 0) partial[warp] = cost;
+  __syncthreads();
+  cost = partial[0];
+  for (int w = 1; w < n_warps; ++w) cost += partial[w];
   return -cost / sqrt(heads[src_slot].gmm_auto_corr * heads[tgt_slot].gmm_auto_corr);
 }
 
@@ -1238,19 +1245,21 @@ finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__
 }
 
 // tidyUpCandidates' GMM-L2 gate (contour_db.h:553-577): one warp per (query scan, candidate pose)
-__global__ void __launch_bounds__(32)
+constexpr int CORR_WARPS = 4;  // warps per pose: the long poses (50 x 50 ellipse pairs per level) set the kernel's makespan
+__global__ void __launch_bounds__(CORR_WARPS * 32)
 finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, float lb_correlation,
                    const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand) {
-  __shared__ uint32_t queue[64];
-  const int lane = threadIdx.x;
-  const int wg = blockIdx.x;  // one warp per CTA: a slot is released as soon as its pose is done (most poses exit at once)
+  __shared__ uint32_t queue[CORR_WARPS][64];
+  __shared__ double partial[CORR_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wg = blockIdx.x;  // one pose per CTA: a slot is released as soon as its pose is done (most poses exit at once)
   const int q = q0 + wg / C2G_MAX_CAND, ci = wg % C2G_MAX_CAND;
   if (q >= q0 + B || ci >= fin_head[q].n_before) return;
   FinCand &fc = fin_cand[(size_t) q * C2G_MAX_CAND + ci];
   if (!fc.pass) return;
   const double T[4] = {fc.T[0], fc.T[1], fc.T[2], fc.T[3]};
-  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane, queue);
-  if (lane == 0) {
+  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane, warp, CORR_WARPS, queue[warp], partial);
+  if (threadIdx.x == 0) {
     fc.corr_init = (float) corr;
     fc.alive = (fc.corr_init < lb_correlation) ? 0 : 1;
   }
@@ -1379,7 +1388,7 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int q0, int B, const QueryParams
   finish_replay_kernel<<<B, FIN_WARPS * 32, smem, st>>>(ctx->d_heads, ctx->d_views, first_slot, q0, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 4);
-  finish_corr_kernel<<<B * C2G_MAX_CAND, 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, Q.lb.correlation, fh, fcd);
+  finish_corr_kernel<<<B * C2G_MAX_CAND, CORR_WARPS * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, Q.lb.correlation, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 5);
   finish_output_kernel<<<(B + 3) / 4, 128, 0, st>>>(q0, B, fh, fcd, ctx->d_results);
