@@ -37,6 +37,10 @@ int make_params(const c2g_cm_config &cfg, C2gIngestParams &P) {
   if (cfg.n_row % 2 || cfg.n_col % 2) return C2G_ERR_ARG;  // CHECK in contour_mng.h:479-480
   if (cfg.n_row > 255 || cfg.n_col > 255) return C2G_ERR_ARG;
   if (cfg.n_row * ((cfg.n_col + 31) / 32) > 800) return C2G_ERR_ARG;  // bit-plane capacity of the contour kernel (150 x 5 = 750)
+  // a level-(l+1) contour must lie inside a level-l contour (the recursion of makeContourRecursiveHelper descends into the
+  // parent's ROI): the thresholds have to increase, as in both shipped configurations
+  for (int l = 1; l < C2G_NLEV; ++l)
+    if (!(cfg.lv_grads[l] > cfg.lv_grads[l - 1])) return C2G_ERR_ARG;
   if (cfg.piv_firsts < 0 || cfg.piv_firsts > C2G_MAX_PIV) return C2G_ERR_ARG;
   if (cfg.dist_firsts < 0 || cfg.dist_firsts > C2G_MAX_DIST_FIRSTS) return C2G_ERR_ARG;
   if (!(cfg.roi_radius > 0.0f) || cfg.roi_radius > 10.0f) return C2G_ERR_ARG;  // key window list capacity
