@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--db-scans", type=int, default=5000)
-    ap.add_argument("--queries", type=int, default=592, help="query scans per rank per step (4 x 148 SMs)")
+    ap.add_argument("--queries", type=int, default=1184,
+                    help="query scans per rank per step: SURVEY.md 8d config 3 asks for Q = 1 024; 8 x 148 SMs = 1 184 is the next multiple of the SM count")
     ap.add_argument("--points", type=int, default=N_PTS)
     ap.add_argument("--cpu-sample", type=int, default=96, help="query scans of the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
