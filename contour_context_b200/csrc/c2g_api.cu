@@ -500,6 +500,13 @@ int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *se
   return 0;
 }
 
+int c2g_hostdb_versions(void *h, int ll, unsigned int *restructured) {
+  if (!h || !restructured) return C2G_ERR_ARG;
+  const C2gLayerHost &L = ((C2gHostDB *) h)->layers[ll];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) restructured[i] = L.buckets[i].restructured;
+  return 0;
+}
+
 int c2g_exp_mode(c2g_ctx *ctx) { return ctx ? ctx->P.exp_mode : C2G_ERR_ARG; }
 
 /* host execution of the libm restatements in csrc/c2g_libm.cuh (tests): kind 0 exp (glibc, no FMA), 1 exp (glibc, FMA),

@@ -124,6 +124,9 @@ int c2g_hostdb_push_key(void *h, int ll, const float *key, double ts, int gidx, 
 int c2g_hostdb_balance(void *h, int seed, double ts);
 int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes);
 int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq);
+/* per bucket: how often existing tree entries were moved or removed (LayerDB::rebuild's balancing move); while the counter
+ * stands still a tree only grows at its END, which is what lets c2g_db_sync patch the device mirror instead of rebuilding it */
+int c2g_hostdb_versions(void *h, int ll, unsigned int *restructured /* [6] */);
 
 /* Which exp() variant the device runs to match this host's libm (csrc/c2g_libm.cuh): 0 libdevice, 1 glibc, 2 glibc+FMA. */
 int c2g_exp_mode(c2g_ctx *ctx);

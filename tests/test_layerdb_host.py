@@ -64,3 +64,45 @@ def test_rebalance_matches_oracle(built_lib, oracle, mode):
             assert ok.tobytes() == pk.tobytes() and np.array_equal(og, pg) and np.array_equal(osq, ps), (mode, ll, b)
     assert split_seen, "the test never exercised a bucket split"
     built_lib.c2g_hostdb_free(h)
+
+
+def test_trees_only_grow_at_the_end_between_restructures(built_lib):
+    """The incremental device mirror (query.cu: c2g_db_sync_mode) appends to a bucket's region as long as the bucket's
+    `restructured` counter stands still.  That is only correct if, between two bumps of the counter, the previous tree is a
+    PREFIX of the current one — checked here after every pushAndBalance of a 1 200-scan stream with rebalancing moves."""
+    rng = np.random.default_rng(7)
+    cfg = D.kitti_db_config()
+    h = built_lib.c2g_hostdb_create(cfg.n_q_levels, cfg.max_elapse, cfg.min_elapse)
+    built_lib.c2g_hostdb_versions.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    prev = {}
+    bumps = appends = 0
+    for i in range(1200):
+        ts = 0.25 * i
+        for ll in range(cfg.n_q_levels):
+            for seq in range(6):
+                key = (rng.random(10) * (10 + 0.02 * i) + 1).astype(np.float32)  # a drifting distribution forces rebalancing
+                assert built_lib.c2g_hostdb_push_key(h, ll, _p(key), ts, i, seq) == 0
+        assert built_lib.c2g_hostdb_balance(h, i, ts) == 0
+        for ll in range(cfg.n_q_levels):
+            ver = np.zeros(6, np.uint32)
+            assert built_lib.c2g_hostdb_versions(h, ll, _p(ver)) == 0
+            _, sizes, _ = _state_prod(built_lib, h, ll)
+            for b in range(6):
+                n = int(sizes[b])
+                keys = np.zeros((max(n, 1), 10), np.float32)
+                gidx = np.zeros(max(n, 1), np.int32)
+                sq = np.zeros(max(n, 1), np.int32)
+                assert built_lib.c2g_hostdb_tree(h, ll, b, _p(keys), _p(gidx), _p(sq)) == 0
+                cur = (int(ver[b]), keys[:n].tobytes() + gidx[:n].tobytes() + sq[:n].tobytes(), n, keys[:n].copy(), gidx[:n].copy(), sq[:n].copy())
+                if (ll, b) in prev:
+                    pv, _, pn, pk, pg, ps = prev[(ll, b)]
+                    if pv == cur[0]:
+                        assert n >= pn, (i, ll, b)
+                        assert pk.tobytes() == cur[3][:pn].tobytes() and np.array_equal(pg, cur[4][:pn]) and np.array_equal(ps, cur[5][:pn]), \
+                            f"scan {i} layer {ll} bucket {b}: the tree changed in place without a restructure bump"
+                        appends += int(n > pn)
+                    else:
+                        bumps += 1
+                prev[(ll, b)] = cur
+    assert bumps > 5 and appends > 100, (bumps, appends)  # both paths of the mirror were exercised
+    built_lib.c2g_hostdb_free(h)
