@@ -55,7 +55,6 @@ constexpr int NVL = 1024;         // significant components (area >= min_cont_ce
 constexpr int KEY_LIST_CAP = 400; // cells of one key window that can lie inside the 9.99-cell radius
 constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
 constexpr int N_DIVS = 35;
-constexpr int N_ARENAS = 8;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct TopView {  // what keys / BCI / GMM need from a sorted view
@@ -101,7 +100,7 @@ struct Smem {
   int cnt_point[N_ANCH];
   int n_ell[C2G_NUM_BIN_LAYERS];
   int nsig, status, n_occ, wq, next_scan;
-  int runs_in_arena, comps_in_arena, arena;  // arena: index of the claimed global arena, -1 = none
+  int runs_in_arena, comps_in_arena, arena;  // arena: this CTA's global overflow arena (= blockIdx.x) when in use, -1 = not used
   double red[K2_WARPS];
 };
 static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs per SM");
@@ -337,7 +336,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
                C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
-               unsigned char *__restrict__ klist_scratch, int *__restrict__ arena_locks, unsigned char *__restrict__ arenas,
+               unsigned char *__restrict__ klist_scratch, unsigned char *__restrict__ arenas,
                int *__restrict__ work_counter, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -478,13 +477,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.run_off[l] = tot;
         tot += S.n_runs[l];
       }
-      if (tot > R_POOL) {  // rare: the run tables of this scan live in a global arena (claimed until the scan is done)
-        int a = blockIdx.x % N_ARENAS;
-        while (atomicCAS(&arena_locks[a], 0, 1) != 0) {
-          a = (a + 1) % N_ARENAS;
-          __nanosleep(200);
-        }
-        S.arena = a;
+      if (tot > R_POOL) {  // the run tables of this scan live in this CTA's global arena (generic pointers, L2 latency)
+        S.arena = blockIdx.x;
         S.runs_in_arena = 1;
         for (int l = 0; l < C2G_NLEV; ++l) S.run_off[l] = l * ARL;
       }
@@ -602,14 +596,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         tot += S.n_comp[l];
       }
       if (tot > C_POOL) {
-        if (S.arena < 0) {
-          int a = blockIdx.x % N_ARENAS;
-          while (atomicCAS(&arena_locks[a], 0, 1) != 0) {
-            a = (a + 1) % N_ARENAS;
-            __nanosleep(200);
-          }
-          S.arena = a;
-        }
+        S.arena = blockIdx.x;
         S.comps_in_arena = 1;
         for (int l = 0; l < C2G_NLEV; ++l) S.comp_off[l] = l * ARL;
       }
@@ -880,10 +867,6 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     else
       stage2(std::false_type{});
     __syncthreads();
-    if (tid == 0 && S.arena >= 0) {  // the run / component tables are dead from here on
-      __threadfence();
-      atomicExch(&arena_locks[S.arena], 0);
-    }
     {
       // copy 80-byte records as 20 x 4-byte words: sorted position j of level l <- presort index (sortbuf & 0xFFFF)
       const uint32_t *src = reinterpret_cast<const uint32_t *>(presort);
@@ -1253,9 +1236,10 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
 
 size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 int c2g_contour_max_ctas(int num_sms) { return K2_CTAS_PER_SM * num_sms; }
-// layout of the global scratch: [max_ctas][KLIST_BYTES] key-window lists | [N_ARENAS] locks (zeroed at creation) | arenas
+// layout of the global scratch: [max_ctas][KLIST_BYTES] key-window lists | [max_ctas] overflow arenas (one per resident CTA: a batch of
+// cluttered scans must not serialise on a shared pool)
 size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row) {
-  return (size_t) c2g_contour_max_ctas(num_sms) * KLIST_BYTES + 256 + (size_t) N_ARENAS * arena_bytes(n_cells, n_row);
+  return (size_t) c2g_contour_max_ctas(num_sms) * (KLIST_BYTES + arena_bytes(n_cells, n_row));
 }
 
 int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
@@ -1272,11 +1256,10 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   const int grid = B < max_ctas ? B : max_ctas;
   if (grid <= 0) return 0;
   unsigned char *klists = k2_scratch;
-  int *locks = reinterpret_cast<int *>(k2_scratch + (size_t) max_ctas * KLIST_BYTES);
-  unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES + 256;
+  unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES;
   C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev, first_slot, bev_h,
-                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, locks, arenas,
+                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, arenas,
                                                              work_counter, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
