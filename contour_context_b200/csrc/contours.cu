@@ -32,6 +32,7 @@
 // single logical accumulator, never by tree reductions; compiled with -fmad=false.
 #include <math_constants.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "c2g_common.cuh"
@@ -336,7 +337,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
                C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
                float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
-               unsigned char *__restrict__ klist_scratch, unsigned char *__restrict__ arenas,
+               unsigned char *__restrict__ klist_scratch, unsigned char *__restrict__ arenas, int force_arena,
                int *__restrict__ work_counter, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -477,7 +478,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.run_off[l] = tot;
         tot += S.n_runs[l];
       }
-      if (tot > R_POOL) {  // the run tables of this scan live in this CTA's global arena (generic pointers, L2 latency)
+      if (tot > R_POOL || force_arena) {  // the run tables of this scan live in this CTA's global arena (generic pointers, L2 latency)
         S.arena = blockIdx.x;
         S.runs_in_arena = 1;
         for (int l = 0; l < C2G_NLEV; ++l) S.run_off[l] = l * ARL;
@@ -595,7 +596,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         S.comp_off[l] = tot;
         tot += S.n_comp[l];
       }
-      if (tot > C_POOL) {
+      if (tot > C_POOL || force_arena) {
         S.arena = blockIdx.x;
         S.comps_in_arena = 1;
         for (int l = 0; l < C2G_NLEV; ++l) S.comp_off[l] = l * ARL;
@@ -1257,9 +1258,10 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   if (grid <= 0) return 0;
   unsigned char *klists = k2_scratch;
   unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES;
+  static const int force_arena = getenv("C2G_K2_FORCE_ARENA") ? atoi(getenv("C2G_K2_FORCE_ARENA")) : 0;  // measurement / test hook
   C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
   contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev, first_slot, bev_h,
-                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, arenas,
+                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, arenas, force_arena,
                                                              work_counter, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
