@@ -44,7 +44,7 @@ namespace {
 // glibc's __exp_data.tab (2 KB, read through L1); see c2g_libm.cuh
 __device__ const uint64_t c2g_exp_tab_dev[256] = C2G_EXP_TAB_INIT;
 
-constexpr int K2_THREADS = 384;
+constexpr int K2_THREADS = 512;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_CTAS_PER_SM = 2;
 constexpr int PLANE_WORDS = 800;  // n_row * ceil(n_col / 32) (checked by make_params): 150 x 5 = 750 for both shipped configs
@@ -330,7 +330,7 @@ __host__ __device__ inline size_t arena_bytes(int n_cells, int n_row) {
   return (size_t) C2G_NLEV * arena_level_cap(n_cells, n_row) * (4 + 4 + 4 * CW);
 }
 
-static_assert(K2_WARPS == 2 * C2G_NLEV, "two warps per level in the labelling phases");
+static_assert(K2_WARPS >= 2 * C2G_NLEV, "two warps per level in the labelling phases (the other warps skip them)");
 
 __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM)
 contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B,
@@ -349,7 +349,8 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
   float *const klist_dist = reinterpret_cast<float *>(klist_scratch + (size_t) blockIdx.x * KLIST_BYTES);  // [N_ANCH][KEY_LIST_CAP]
   uint8_t *const klist_hc = reinterpret_cast<uint8_t *>(klist_dist + N_ANCH * KEY_LIST_CAP);               // [N_ANCH][KEY_LIST_CAP]
   const int ARL = arena_level_cap(ncell, nrow);
-  const int lev_w = warp >> 1, half = warp & 1;  // level and half of this warp in the labelling phases
+  const bool lvl_warp = warp < 2 * C2G_NLEV;  // warps 0..11 label (two per level); further warps only join the block-wide phases
+  const int lev_w = lvl_warp ? warp >> 1 : 0, half = warp & 1;  // level and half of this warp in the labelling phases
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // scans are handed out dynamically (their cost varies 2x with the scene, and a CTA that starts late - e.g. behind a
@@ -443,7 +444,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     // B1 runs per word -> exclusive prefix (run ids are raster order); each warp scans half of the words
     const int wh = min(nwords, ((nwords / 2 + 31) >> 5) << 5);
     const int wbeg = half ? wh : 0, wend = half ? nwords : wh;
-    {
+    if (lvl_warp) {
       const uint32_t *pl = S.plane[lev_w];
       int base = 0;
       for (int w0 = wbeg; w0 < wend; w0 += 32) {
@@ -583,10 +584,12 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       if (lane == 0) S.half_roots[lev_w][half] = nroot;
       C2G_DBG(14);
     };
-    if (S.runs_in_arena)
-      stage1(std::true_type{});
-    else
-      stage1(std::false_type{});
+    if (lvl_warp) {
+      if (S.runs_in_arena)
+        stage1(std::true_type{});
+      else
+        stage1(std::false_type{});
+    }
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
@@ -621,7 +624,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       {
         uint32_t *rp = RP + S.run_off[lev_w], *ri = RI + S.run_off[lev_w];
         uint32_t *cw = CWP + (size_t) S.comp_off[lev_w] * CW;
-        const int n = S.n_runs[lev_w], nc = S.n_comp[lev_w];
+        const int n = lvl_warp ? S.n_runs[lev_w] : 0, nc = lvl_warp ? S.n_comp[lev_w] : 0;
         // B5 roots -> components (numbered in arrival order; only the DFS rank computed below carries meaning)
         for (int id0 = half * 32; id0 < n; id0 += 64) {
           const int id = id0 + lane;
@@ -639,7 +642,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
             rp[id] = 0x80000000u | (uint32_t) ci;
           }
         }
-        pair_sync(lev_w);
+        if (lvl_warp) pair_sync(lev_w);
         C2G_DBG(16);
         // B6 area / last run / leftmost column per component; every run now names its component directly
         for (int id = half * 32 + lane; id < n; id += 64) {
@@ -654,7 +657,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
         __syncthreads();
         C2G_DBG(2);
         // B7 enclosing component of the previous level (looked up at the first pixel) and its bounding-box origin
-        if (lev_w > 0) {
+        if (lvl_warp && lev_w > 0) {
           const uint32_t *plp = S.plane[lev_w - 1];
           const uint16_t *wpp = S.wpre[lev_w - 1];
           const uint32_t *rpp = RP + S.run_off[lev_w - 1], *rip = RI + S.run_off[lev_w - 1];
@@ -672,7 +675,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
             cw[ci * CW + 3] = 0xFFFF0000u | (y0 << 8) | x0;
           }
         }
-        pair_sync(lev_w);
+        if (lvl_warp) pair_sync(lev_w);
         C2G_DBG(18);
         // B8 first-2x2-block key relative to that origin: min over the runs (a run's minimum is at its first cell)
         for (int id = half * 32 + lane; id < n; id += 64) {
@@ -753,7 +756,7 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
       __syncthreads();
       // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
       // (contour_mng.h:596-599); one lane per level, on six different warps
-      if (lane == 0 && half == 0) {
+      if (lane == 0 && half == 0 && lvl_warp) {
         uint32_t *first = S.sortbuf + S.view_off[lev_w];
         int sum = 0;
         for (int i = 0; i < S.n_views[lev_w]; ++i) sum += (int) (first[i] >> 16);
