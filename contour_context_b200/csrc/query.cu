@@ -64,6 +64,8 @@ __device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, c
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QK_WARPS * 32)
 knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, c2g_hint *__restrict__ hints) {
+  __shared__ float merge_d[QK_WARPS][64];
+  __shared__ int merge_i[QK_WARPS][64], merge_o[QK_WARPS][64];
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * QK_WARPS + (threadIdx.x >> 5);
   const int keys_per_scan = Q.n_q_levels * C2G_MAX_PIV;
@@ -153,50 +155,59 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
         dist = r;
         orig = T.orank[i];
       }
-      unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
-      while (cand) {
-        const int src = __ffs(cand) - 1;
-        cand &= cand - 1;
+      const unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
+      if (cand == 0u) return;
+      // Batch merge of the block's admissible keys into the sorted top-64: every (distance, tree rank) pair is unique, so the
+      // merged order is a permutation that each element can compute for itself -
+      //   kept entry in slot j        -> j + #candidates that precede it
+      //   candidate                   -> #kept entries that precede it + #candidates that precede it
+      // - from one broadcast round per candidate (the rounds are independent of each other, unlike insertion one by one);
+      // the permutation itself goes through 768 bytes of shared memory per warp.  Entries pushed past slot 63 fall off.
+      const bool mine = (cand >> lane) & 1u;
+      int sh0 = 0, sh1 = 0, before_new = 0, before_kept = 0;
+      for (unsigned m = cand; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
         const float nd = __shfl_sync(0xFFFFFFFFu, dist, src);
         const int no = __shfl_sync(0xFFFFFFFFu, orig, src);
-        const int ni = base + src;
-        if (!(nd < thr || (nd == thr && no < thr_o))) continue;  // the worst kept entry may have tightened meanwhile
-        // position = number of kept entries that precede (nd, no)
-        const unsigned le0 = __ballot_sync(0xFFFFFFFFu, bd[0] < nd || (bd[0] == nd && bo[0] < no));
-        const unsigned le1 = __ballot_sync(0xFFFFFFFFu, bd[1] < nd || (bd[1] == nd && bo[1] < no));
-        const int pos = __popc(le0) + __popc(le1);
-        const float up0 = __shfl_up_sync(0xFFFFFFFFu, bd[0], 1), up1 = __shfl_up_sync(0xFFFFFFFFu, bd[1], 1);
-        const int ui0 = __shfl_up_sync(0xFFFFFFFFu, bi[0], 1), ui1 = __shfl_up_sync(0xFFFFFFFFu, bi[1], 1);
-        const int uo0 = __shfl_up_sync(0xFFFFFFFFu, bo[0], 1), uo1 = __shfl_up_sync(0xFFFFFFFFu, bo[1], 1);
-        const float last0 = __shfl_sync(0xFFFFFFFFu, bd[0], 31);
-        const int lasti0 = __shfl_sync(0xFFFFFFFFu, bi[0], 31), lasto0 = __shfl_sync(0xFFFFFFFFu, bo[0], 31);
-        const int j0 = lane, j1 = lane + 32;
-        if (j1 > pos) {
-          bd[1] = (lane == 0) ? last0 : up1;
-          bi[1] = (lane == 0) ? lasti0 : ui1;
-          bo[1] = (lane == 0) ? lasto0 : uo1;
-        }
-        if (j0 > pos) {
-          bd[0] = up0;
-          bi[0] = ui0;
-          bo[0] = uo0;
-        }
-        if (j0 == pos) {
-          bd[0] = nd;
-          bi[0] = ni;
-          bo[0] = no;
-        }
-        if (j1 == pos) {
-          bd[1] = nd;
-          bi[1] = ni;
-          bo[1] = no;
-        }
-        if (count < K) ++count;
-        if (count == K) {  // worst kept entry = K-th best
-          const int ks = K - 1;
-          thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
-          thr_o = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bo[0] : bo[1], ks & 31);
-        }
+        const bool k0 = bd[0] < nd || (bd[0] == nd && bo[0] < no);  // my kept entries precede this candidate
+        const bool k1 = bd[1] < nd || (bd[1] == nd && bo[1] < no);
+        const unsigned le0 = __ballot_sync(0xFFFFFFFFu, k0), le1 = __ballot_sync(0xFFFFFFFFu, k1);
+        sh0 += k0 ? 0 : 1;
+        sh1 += k1 ? 0 : 1;
+        before_new += (mine && (nd < dist || (nd == dist && no < orig))) ? 1 : 0;
+        if (lane == src) before_kept = __popc(le0) + __popc(le1);
+      }
+      float *sd = merge_d[threadIdx.x >> 5];
+      int *si = merge_i[threadIdx.x >> 5], *so = merge_o[threadIdx.x >> 5];
+      const int p0 = lane + sh0, p1 = lane + 32 + sh1, pn = before_kept + before_new;
+      if (p0 < 64) {
+        sd[p0] = bd[0];
+        si[p0] = bi[0];
+        so[p0] = bo[0];
+      }
+      if (p1 < 64) {
+        sd[p1] = bd[1];
+        si[p1] = bi[1];
+        so[p1] = bo[1];
+      }
+      if (mine && pn < 64) {
+        sd[pn] = dist;
+        si[pn] = i;
+        so[pn] = orig;
+      }
+      __syncwarp();
+      bd[0] = sd[lane];
+      bi[0] = si[lane];
+      bo[0] = so[lane];
+      bd[1] = sd[lane + 32];
+      bi[1] = si[lane + 32];
+      bo[1] = so[lane + 32];
+      __syncwarp();
+      count = min(K, count + __popc(cand));
+      if (count == K) {  // worst kept entry = K-th best
+        const int ks = K - 1;
+        thr = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bd[0] : bd[1], ks & 31);
+        thr_o = __shfl_sync(0xFFFFFFFFu, ks < 32 ? bo[0] : bo[1], ks & 31);
       }
     };
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
