@@ -1,5 +1,5 @@
 // contours.cu — K2: BEV tile -> multi-level contours -> ContourView statistics -> per-level order -> retrieval keys ->
-// BCIs -> per-scan GMM terms.  Persistent CTAs of 384 threads, TWO resident per SM (<= 113 KB of shared memory each), one
+// BCIs -> per-scan GMM terms.  Persistent CTAs of 512 threads, TWO resident per SM (<= 113 KB of shared memory each), one
 // scan per CTA iteration; everything between the BEV tile and the finished descriptor stays in shared memory / L1 / L2.
 //
 // Reference functions restated here (paths relative to the reference repo):
