@@ -123,11 +123,10 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
 int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P,
                            c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream) {
   const size_t smem = (size_t) P.n_cells * sizeof(c2g_cellkey);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0ull;
+  if (c2g_first_use_on_device(attr_devs)) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (C2G_MAX_CELLS * sizeof(c2g_cellkey))));
     C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (C2G_MAX_CELLS * sizeof(c2g_cellkey))));
-    attr_set = true;
   }
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;

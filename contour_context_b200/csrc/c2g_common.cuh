@@ -73,3 +73,12 @@ __device__ __forceinline__ bool c2g_sqrt_lt(double x, double y) {
   if (x > y2 * (1.0 + 1e-15)) return false;
   return sqrt(x) < y;
 }
+
+// cudaFuncSetAttribute is per device: remember which devices of this process already have the attribute
+static inline bool c2g_first_use_on_device(unsigned long long &mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (mask & (1ull << dev)) return false;
+  mask |= 1ull << dev;
+  return true;
+}

@@ -1250,11 +1250,10 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
                         const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
                         float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
                         unsigned char *k2_scratch, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0ull;
+  if (c2g_first_use_on_device(attr_devs)) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   const int max_ctas = c2g_contour_max_ctas(num_sms);
   const int grid = B < max_ctas ? B : max_ctas;

@@ -1388,11 +1388,10 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
 // proposal replay -> GMM-L2 gate -> output -> refinement -> ranking for queries [q0, q0 + B) of the batch, on `st`
 int launch_finish(c2g_ctx *ctx, int first_slot, int q0, int B, const QueryParams &Q, const c2g_hint *hints, const c2g_pair_score *scores,
                   cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0ull;
   const size_t smem = sizeof(FinishScratch);
-  if (!attr_set) {
+  if (c2g_first_use_on_device(attr_devs)) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(finish_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
   }
   FinHead *fh = (FinHead *) ctx->d_fin_head;
   FinCand *fcd = (FinCand *) ctx->d_fin_cand;
@@ -1755,11 +1754,10 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
     } else {
       const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
       const long long cap = (long long) ctx->num_sms * 16;
-      static bool sc_attr = false;
+      static unsigned long long sc_attr_devs = 0ull;
       const size_t sc_smem = sizeof(ScoreScratch) * SC_WARPS;
-      if (!sc_attr) {
+      if (c2g_first_use_on_device(sc_attr_devs)) {
         C2G_CUDA_TRY(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sc_smem));
-        sc_attr = true;
       }
       score_kernel<<<(unsigned) (want < cap ? want : cap), SC_WARPS * 32, sc_smem, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores,
                                                                                       surv, nsurv);
