@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — scans/sec of the cont2contops hot path (ingest + query against a 5 000-scan database), BASELINE.json's metric.
+"""bench.py — scans/sec of the cont2contops hot path (ingest + query against a scan database), BASELINE.json's metric.
 
-Workload (BASELINE.json configs[2], the configuration the metric string is quoted on): synthetic 120 000-point scans in
-the KITTI .bin layout; a database of 5 000 scans (1 250 scenes x 4 visits) whose descriptors and retrieval-key tables are
-resident in HBM (replicated on every rank: 5 000 scans are ~0.2 GB of descriptors); one *step* = one batch of Q query
-scans per rank going through the whole path: BEV scatter -> contours/keys/BCI -> ranged kNN -> hint scoring cascade ->
-proposal merge + GMM-L2 -> (N > 1) one NCCL all-gather of the per-pair score records.
+  --config batched5k (default, the configuration the metric string "vs 5k-scan DB" is quoted on, BASELINE.json configs[2]):
+        synthetic 120 000-point scans in the KITTI .bin layout; a database of 5 000 scans (1 250 scenes x 4 visits) whose
+        descriptors and retrieval-key tables are resident in HBM (replicated on every rank); one *step* = one batch of Q
+        query scans per rank going through the whole path: BEV scatter -> contours/keys/BCI -> ranged kNN -> hint scoring
+        cascade -> proposal merge + GMM-L2 -> L-BFGS refinement -> (N > 1) ONE NCCL all-gather of the per-query results.
+  --config db20k  (configs[3]): the same step against a 20 000-scan database.
+  --config kitti08 (configs[1]): the online loop of test/batch_bin_test.cpp:179,234,237 on a KITTI-08-shaped sequence
+        (4 071 scans, ts = 0.104 s apart, revisits of earlier places): every scan is queried against the DB of all earlier
+        scans, then added, then pushAndBalance - through the windowed C-ABI (c2g_online_stage / c2g_online_commit), results
+        identical to the scan-by-scan loop; one *step* = one window of W scans, the timed region is the whole sequence.
 
-  value : Q*N / step time with the query points already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same step through the public C-ABI call with HOST buffers: pinned host -> device copy of the points and
+  value : scans / time with the points already resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e   : the same through the public C-ABI call with HOST buffers: pinned host -> device copy of the points and
           device -> host read of the results inside the timed region
+  parity: every run compares a sample of its GPU results with the CPU oracle on the same inputs and fails on a mismatch
   --impl reference : the CPU restatement of the reference path (oracle/, linked against the reference's own nanoflann when
-          oracle/_ref was built) on all host cores, same workload, bounded sample per step.
+          oracle/_ref was built) on --cpu-threads host threads, same workload, bounded sample per step.
 
-Weak scaling: per-rank work is fixed (Q queries per rank against the same 5 000-scan DB).
+Weak scaling: per-rank work is fixed (Q queries per rank against the same DB).
 """
 import argparse
 import ctypes as C
@@ -29,14 +35,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "scans/sec ingest+query vs 5k-scan DB"
 N_PTS = 120000
 VISITS = 4
+FP64_NOMINAL_TFLOPS = 40.0  # B200 FP64 vector peak (nominal; MEASURED_PEAKS.json holds no FP64 figure)
 
+# DRAM traffic per 120k-point scan measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of one launch,
+# divided by the scans of that launch); refreshed from profiles/ whenever the ingest kernels change.  Algorithmic bytes are
+# 1.92 MB (K1) and 1.98 MB (K1 + K2) per scan.
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ingest_dram_bytes_per_scan.json")
 
-# DRAM traffic per 120k-point scan measured by `ncu --set full` (profiles/r1e_ncu_full_summary.csv, one 592-scan launch each):
-# (dram__bytes_read.sum + dram__bytes_write.sum) / 592.  Algorithmic bytes are 1.92 MB (K1) and 1.98 MB (K1+K2) per scan.
-NCU_DRAM_BYTES_PER_SCAN = {"bev_scatter_kernel": (1.136680e9 + 51.249920e6) / 592, "contour_kernel": (0.305138e9 + 87.707648e6) / 592}
+WORKLOADS = {
+    "batched5k": "configs[2]: synthetic 120k-pt scans, 5k-scan DB, batched ingest+query on 1 GPU per rank",
+    "db20k": "configs[3]: synthetic 120k-pt scans, 20k-scan DB, query batches sharded over the ranks",
+    "kitti08": "configs[1]: KITTI-08-shaped sequence, query each scan vs the growing DB then add it (online loop)",
+}
 
 
 def parse():
@@ -45,13 +57,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--db-scans", type=int, default=5000)
+    ap.add_argument("--config", default="batched5k", choices=sorted(WORKLOADS))
+    ap.add_argument("--db-scans", type=int, default=None, help="database size (default: 5000, db20k: 20000)")
     ap.add_argument("--queries", type=int, default=1184,
                     help="query scans per rank per step: SURVEY.md 8d config 3 asks for Q = 1 024; 8 x 148 SMs = 1 184 is the next multiple of the SM count")
     ap.add_argument("--points", type=int, default=N_PTS)
-    ap.add_argument("--cpu-sample", type=int, default=96, help="query scans of the single-thread CPU baseline sample")
+    ap.add_argument("--seq-scans", type=int, default=4071, help="kitti08: length of the sequence")
+    ap.add_argument("--window", type=int, default=148, help="kitti08: scans per window of the online loop")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="query scans of the single-thread CPU baseline / parity sample")
+    ap.add_argument("--cpu-threads", type=int, default=16, help="--impl reference: host threads (fixed so that boxes compare; capped at the box's cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.db_scans is None:
+        a.db_scans = 20000 if a.config == "db20k" else 5000
+    return a
+
+
+def metric_name(args):
+    return "scans/sec ingest+query vs 5k-scan DB" if args.config == "batched5k" else \
+        ("scans/sec ingest+query vs 20k-scan DB" if args.config == "db20k" else "scans/sec ingest+query vs growing DB (online loop)")
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -88,6 +112,9 @@ class ClockSampler:
             pass
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # "under load": samples taken while the GPU drew clearly more than idle power
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        load = [s for s, p in zip(sm, pw) if p > 0.6 * max(pw)] if pw and len(pw) == len(sm) else sm
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -95,8 +122,35 @@ class ClockSampler:
                 for k, nm in enumerate(names):
                     if r[5 + k].lower().startswith("active"):
                         reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": float(np.median(load or sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_near_gpu(local_rank: int):
+    """Pin this rank's host threads (and therefore its first-touch pinned pages) to the CPUs of the GPU's NUMA node, so that
+    the host -> device copies of N ranks do not all cross one socket interconnect.  Returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devs = [d for d in os.listdir("/sys/bus/pci/devices") if d.lower().startswith(f"{dom:04x}:{bus:02x}:")]
+        if not devs:
+            return "pci device not found in sysfs"
+        base = os.path.join("/sys/bus/pci/devices", devs[0])
+        node = int(open(os.path.join(base, "numa_node")).read().strip())
+        cpus = open(os.path.join(base, "local_cpulist")).read().strip()
+        if node < 0 or not cpus:
+            return f"numa_node {node}: not bound"
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return f"numa node {node}, {len(ids)} cpus"
+    except Exception as e:  # plumbing only: never fail the bench on a sysfs quirk
+        return f"not bound ({type(e).__name__})"
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -104,9 +158,9 @@ def build_db(eng, synth, torch, n_db, n_pts, chunk=148):
     """Untimed setup: ingest the DB scans on the GPU and run ContourDB::addScan / pushAndBalance for each (growing DB
     bookkeeping, ts_i = 0.1 i), then flush every buffered key into its tree."""
     t0 = time.time()
+    seeds, visits = synth.db_layout(n_db, VISITS)
     for i0 in range(0, n_db, chunk):
         n = min(chunk, n_db - i0)
-        seeds, visits = synth.db_layout(n_db, VISITS)
         pts = synth.make_scans(seeds[i0:i0 + n], visits[i0:i0 + n], n_pts, device="cuda", noise_seed=i0).reshape(-1, 4)
         offsets = np.arange(n + 1, dtype=np.int64) * n_pts
         torch.cuda.synchronize()  # the generator ran on torch's stream, the context has its own
@@ -134,14 +188,88 @@ def make_queries(synth, torch, n_q, n_pts, first_scene, chunk=148):
     return torch.cat(outs).reshape(-1, 4).contiguous()
 
 
-def run_b200(args):
+def compare_results(g, o, tol=1e-5):
+    """One GPU c2g_query_result against the oracle's: integer fields equal, correlations within `tol` (north_star).
+    Returns (ok, max |corr diff|)."""
+    ok = (g["n_pose_before"] == o["n_pose_before"] and np.array_equal(g["cand_aft_check"], o["cand_aft_check"])
+          and g["n_cand"] == o["n_cand"] and g["best"] == o["best"] and g["overflow"] == 0)
+    md = 0.0
+    n = int(min(g["n_cand"], o["n_cand"]))
+    if ok and n:
+        gc, oc = g["cand"][:n], o["cand"][:n]
+        ok = (np.array_equal(gc["cand_gidx"], oc["cand_gidx"]) and np.array_equal(gc["vote_cnt"], oc["vote_cnt"])
+              and np.array_equal(gc["fine_iters"], oc["fine_iters"]) and np.array_equal(gc["fine_term"], oc["fine_term"])
+              and bool((gc["fine_flags"] == 0).all()))
+        md = float(max(np.abs(gc["corr_init"] - oc["corr_init"]).max(), np.abs(gc["corr_fine"] - oc["corr_fine"]).max()))
+        ok = ok and md <= tol and float(np.abs(gc["area_perc"] - oc["area_perc"]).max()) <= 1e-6
+    return bool(ok), md
+
+
+def compare_trace(gh, gs, oh, os_):
+    """Hint list + per-hint cascade records of one query: identity/order and squared distances bytes-equal, integer scores equal."""
+    keep = gh["cand_gidx"] >= 0
+    gh, gs = gh[keep], gs[keep]
+    if len(gh) != len(oh):
+        return False
+    for f in ("cand_gidx", "level", "cand_seq", "q_seq", "q_level_idx"):
+        if not np.array_equal(gh[f], oh[f]):
+            return False
+    if gh["dist_sq"].tobytes() != oh["dist_sq"].tobytes():
+        return False
+    return bool(np.array_equal(gs["passed"], os_["passed"]) and np.array_equal(gs["constell"], os_["constell"])
+                and np.array_equal(gs["pairwise"], os_["pairwise"]) and np.array_equal(gs["pair_bits"], os_["pair_bits"]))
+
+
+def oracle_db_from_gpu(eng, c2o, D, capi, n, ts_of, flush_from=None):
+    """CPU-side ContourDB holding the first n scans of the engine, rebuilt from the descriptors the GPU path produced
+    (descriptor parity is established by tests/), with the same addScan / pushAndBalance sequence."""
+    odb = c2o.DB(eng.db_cfg)
+    B = 128
+    for i0 in range(0, n, B):
+        m = min(B, n - i0)
+        heads = eng.heads(i0, m)
+        for j in range(m):
+            raw = np.zeros(D.VIEW_CAP, D.VIEW_DTYPE)
+            capi.check(capi.lib().c2g_get_views(eng.h, i0 + j, capi.ptr(raw)))
+            s = c2o.Scan.from_descriptor(eng.cm_cfg, heads[j], raw)
+            odb.add_scan(s, ts_of(i0 + j))
+            odb.push_and_balance(i0 + j, ts_of(i0 + j))
+    if flush_from is not None:
+        for k in range(16):
+            odb.push_and_balance(k, flush_from + k)
+    return odb
+
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s")
+
+
+def ingest_traffic(n_scans, n_pts):
+    """Measured DRAM bytes of the ingest pair, scaled to n_scans (None when no capture of the shipped kernels is committed)."""
+    try:
+        t = json.load(open(NCU_TRAFFIC_FILE))
+        if n_pts != t.get("points_per_scan", N_PTS):
+            return None, None
+        return n_scans * float(t["bytes_per_scan"]), t.get("source")
+    except Exception:
+        return None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_batched(args):
     import torch
     import torch.distributed as dist
 
     import __graft_entry__ as g
     from contour_context_b200 import capi
     from contour_context_b200 import ctypes_defs as D
-    from contour_context_b200 import synth
+    from contour_context_b200 import multi, synth
     from contour_context_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -150,6 +278,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner to stdout otherwise (the JSON line must be alone)
@@ -168,23 +297,24 @@ def run_b200(args):
     lb, ub = D.kitti_thres()
 
     t_setup = build_db(eng, synth, torch, n_db, n_pts)
-    # distinct query scenes per rank
-    q_dev = make_queries(synth, torch, Q, n_pts, first_scene=(rank * Q) % max(1, n_scenes - Q))
+    # distinct query scenes per rank while they last; with Q close to the scene count the ranks' scene ranges overlap
+    # (different noise would need a different visit index; irrelevant for timing: every rank does the same amount of work)
+    def first_scene_of(r):
+        return (r * Q) % max(1, n_scenes - Q)
+
+    q_dev = make_queries(synth, torch, Q, n_pts, first_scene=first_scene_of(rank))
     q_host = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
     q_host.copy_(q_dev)
     torch.cuda.synchronize()
     offsets = np.arange(Q + 1, dtype=np.int64) * n_pts
     q_first = n_db
-    res_host = np.zeros(Q, D.QUERY_RESULT_DTYPE)
-    res_pinned = torch.empty(res_host.nbytes, dtype=torch.uint8, pin_memory=True)
-    per_rank_hints = eng.hint_slots(Q)
+    res_bytes = Q * D.QUERY_RESULT_DTYPE.itemsize
+    res_pinned = torch.empty(res_bytes, dtype=torch.uint8, pin_memory=True)
     if world > 1:  # send / receive buffers of the all-gather (torch tensors: NCCL plumbing)
-        sc_local = torch.empty(per_rank_hints * D.PAIR_SCORE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        hi_local = torch.empty(per_rank_hints * D.HINT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        sc_all = torch.empty(world * sc_local.numel(), dtype=torch.uint8, device="cuda")
-        hi_all = torch.empty(world * hi_local.numel(), dtype=torch.uint8, device="cuda")
+        res_local = torch.empty(res_bytes, dtype=torch.uint8, device="cuda")
+        res_all = torch.empty(world * res_bytes, dtype=torch.uint8, device="cuda")
 
-    pending = []  # NCCL work handles of the previous step's all-gather
+    pending = []  # NCCL work handle of the previous step's all-gather
 
     def drain():
         with torch.cuda.stream(stream):
@@ -199,12 +329,12 @@ def run_b200(args):
                 eng.ingest(q_dev, offsets, first_slot=q_first, on_device=True)
             eng.query_async(q_first, Q, lb, ub)
             if world > 1:
-                # the path's one exchange step: publish the per-pair score records to every rank.  The collective runs on
-                # NCCL's stream and overlaps the NEXT step's ingest + kNN; the send buffers are reused only after it is done.
+                # the path's one exchange step: every rank publishes the outcome of its queries (3.1 KB per query scan) to all
+                # ranks.  The collective runs on NCCL's stream and overlaps the NEXT step's ingest; the send buffer is reused
+                # only after it is done.
                 drain()
-                eng.query_export(Q, hi_local, sc_local, None)
-                pending.append(dist.all_gather_into_tensor(sc_all, sc_local, async_op=True))
-                pending.append(dist.all_gather_into_tensor(hi_all, hi_local, async_op=True))
+                eng.query_export(Q, None, None, res_local)
+                pending.append(multi.all_gather_records(res_local, world, out=res_all, async_op=True)[1])
             if host_inputs:
                 eng.query_export(Q, None, None, res_pinned)                        # D2H of the step's results
 
@@ -242,7 +372,36 @@ def run_b200(args):
     ms_e2e, _ = timed(True, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel timings on rank 0 (CUDA events on the launching stream), for the roofline entry
+    # ---- the exchange did something: this rank recomputes the NEXT rank's queries on its own replica and compares them, byte
+    # for byte, with that rank's block of the gathered table (untimed)
+    exchange = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            step(False)
+            drain()
+        stream.synchronize()
+        gathered = multi.split_gathered(res_all, world, D.QUERY_RESULT_DTYPE)
+        other = (rank + 1) % world
+        q_other = make_queries(synth, torch, Q, n_pts, first_scene=first_scene_of(other))
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            eng.ingest(q_other, offsets, first_slot=q_first, on_device=True)
+        mine_of_other = eng.query(q_first, Q, lb, ub)
+        bad = multi.verify_foreign_block(gathered, other, mine_of_other)
+        own_bad = multi.verify_foreign_block(gathered, rank, res_pinned.numpy().view(D.QUERY_RESULT_DTYPE))
+        t = torch.tensor([bad + own_bad], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        exchange = {"records_per_rank": Q, "bytes_per_rank_per_step": res_bytes, "collectives_per_step": 1,
+                    "foreign_block_mismatches_all_ranks": int(t.item()),
+                    "loop_closures_in_gathered_table": len(multi.loop_closures(gathered.reshape(-1)))}
+        del q_other
+        with torch.cuda.stream(stream):  # back to this rank's own queries for the per-kernel timings below
+            eng.ingest(q_dev, offsets, first_slot=q_first, on_device=True)
+        stream.synchronize()
+        if exchange["foreign_block_mismatches_all_ranks"]:
+            raise RuntimeError(f"multi-GPU exchange check failed: {exchange}")
+
+    # per-kernel timings on rank 0 (CUDA events on the launching stream), for the roofline entries
     kern = {}
     if rank == 0:
         def ev_time(fn, reps=5):
@@ -270,22 +429,23 @@ def run_b200(args):
                 acc.setdefault(k, []).append(v)
         eng.query_profile(False)
         kern["query_kernels_ms"] = {k: float(np.mean(v[1:])) for k, v in acc.items()}
+        eng.work_counters(True)  # work actually done by one step's query kernels (device counters, one extra untimed step)
+        with torch.cuda.stream(stream):
+            eng.query_async(q_first, Q, lb, ub)
+        kern["work"] = eng.work_counters(False)
 
     # sanity: the timed work produced real loop closures (not measured; guards against timing an empty path)
+    S = min(args.cpu_sample, Q)
     res = eng.query(q_first, Q, lb, ub)
+    if int(res["overflow"].max()) != 0:
+        raise RuntimeError("a query proposed more candidate poses than C2G_MAX_CAND: results would differ from the reference")
     n_found = int((res["n_cand"] > 0).sum())
     heads_q = eng.heads(q_first, min(Q, 8))
     assert int(heads_q["status"].max()) == 0
 
     out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        peak, peak_src = load_peaks()
         total_q = Q * world
         value = total_q / (ms_dev / args.steps) * 1e3
         e2e_val = total_q / (ms_e2e / args.steps) * 1e3
@@ -294,85 +454,359 @@ def run_b200(args):
         alg_bytes_ingest = Q * (16.0 * n_pts + 60000.0)
         ach = alg_bytes_ingest / (kern["ingest_ms"] * 1e-3) / 1e9
         ach_bev = Q * 16.0 * n_pts / (kern["bev_scatter_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = ingest_traffic(Q, n_pts)
         out = {
-            "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (BEV/CCL/keys, no FMA) + f64 (moments, GMM-L2)", "data": "synthetic",
-            "config": {"workload": "configs[2]: synthetic 120k-pt scans, 5k-scan DB, batched ingest+query on 1 GPU per rank",
-                       "db_scans": n_db, "queries_per_rank_per_step": Q, "points_per_scan": n_pts,
-                       "parallelism": f"query batches sharded over {world} rank(s), DB replicated, 1 NCCL all-gather of pair scores",
+            "config": {"workload": WORKLOADS[args.config], "config": args.config,
+                       "db_scans": n_db, "queries_per_step": Q, "queries_per_rank_per_step": Q, "points_per_scan": n_pts,
+                       "parallelism": f"query batches sharded over {world} rank(s), DB replicated, 1 NCCL all-gather of the per-query results",
                        "l2": "inputs larger than L2 (each step streams %.2f GB of points)" % (Q * n_pts * 16 / 1e9),
-                       "refine": "fineOptimize's L-BFGS refinement of <=10 candidates per query included (refine.cu)"},
+                       "refine": "fineOptimize's L-BFGS refinement of <=10 candidates per query included (refine.cu)",
+                       "query_scenes": "rank r queries scenes [(r*Q) mod (n_scenes-Q), +Q): ranks' ranges overlap when Q is close to n_scenes",
+                       "host_binding": numa},
             "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": int(Q * n_pts * 16 + (Q + 1) * 8),
-                    "d2h_bytes_per_step": int(res_host.nbytes), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(res_bytes), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": Q * (NCU_DRAM_BYTES_PER_SCAN["bev_scatter_kernel"] + NCU_DRAM_BYTES_PER_SCAN["contour_kernel"])
-                         if n_pts == 120000 else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per scan from the ncu --set full capture in "
-                                           "profiles/r1e_ncu_full_summary.csv (592-scan launch), scaled to this launch's scan count",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "bev_scatter_kernel + contour_kernel (ingest pair, 1.98 MB algorithmic bytes per scan)",
                          "peak_source": peak_src,
                          "bev_scatter_only": {"achieved": ach_bev, "frac": ach_bev / peak, "ms": kern["bev_scatter_ms"]},
                          "kernel_ms": kern},
             "sanity": {"queries_with_loop_candidate": n_found, "of": int(Q), "db_build_s": t_setup, "exp_mode": eng.exp_mode()},
         }
+        if exchange is not None:
+            out["exchange"] = exchange
     if world > 1:
         dist.barrier()
-    eng_keep = eng  # keep the context alive until the CPU baseline has read the descriptors
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, eng_keep, q_host, offsets, lb, ub)
+    if rank == 0 and not args.no_cpu_baseline:
+        cb, parity, extra = cpu_baseline_batched(args, eng, q_host, offsets, lb, ub, res, S, do_time=(world == 1))
+        if cb is not None:
+            out["cpu_baseline"] = cb
+        out["parity"] = parity
+        out["roofline"]["kernels"] = query_rooflines(args, eng, kern, extra, load_peaks()[0])
+        covered = kern["ingest_ms"] + sum(r["ms"] for r in out["roofline"]["kernels"] if r["kernel"] not in ("bev_scatter_kernel", "contour_kernel"))
+        out["roofline"]["step_ms_covered_frac"] = covered / (ms_dev / args.steps)
     if rank == 0:
         print(json.dumps(out))
+        if out.get("parity", {}).get("mismatches", 0) > 0:
+            eng.close()
+            raise SystemExit("parity gate failed: GPU results differ from the CPU oracle on the same inputs")
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-def cpu_baseline(args, eng, q_host, offsets, lb, ub):
+def query_rooflines(args, eng, kern, extra, hbm_peak):
+    """Roofline entries of the query-half kernels: kNN = 40 B x keys of the visited buckets per query key against
+    HBM/L2 streaming; hint cascade = descriptor bytes actually touched per hint; GMM-L2 gate and refinement = FP64 flops
+    (60 per Gaussian term) against the nominal FP64 peak."""
+    Q = args.queries
+    qk = kern["query_kernels_ms"]
+    rows = [
+        {"kernel": "bev_scatter_kernel", "ms": kern["bev_scatter_ms"], "bound": "hbm", "unit": "GB/s",
+         "achieved": Q * 16.0 * args.points / (kern["bev_scatter_ms"] * 1e-3) / 1e9, "peak": hbm_peak},
+        {"kernel": "contour_kernel", "ms": kern["contours_ms"], "bound": "on-chip latency (shared memory / issue)", "unit": "GB/s",
+         "achieved": Q * 240000.0 / (kern["contours_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+         "note": "180 KB tile read + ~60 KB descriptor written per scan; HBM is not what bounds it"},
+    ]
+    if extra:
+        knn_bytes = extra["knn_visited_keys"] * 40.0
+        rows.append({"kernel": "knn_kernel", "ms": qk["knn"], "bound": "hbm/l2 streaming", "unit": "GB/s",
+                     "achieved": knn_bytes / (qk["knn"] * 1e-3) / 1e9, "peak": hbm_peak,
+                     "touched_gbs": (kern["work"]["knn_keys_evaluated"] * 44.0 + kern["work"]["knn_boxes_tested"] * 80.0) / (qk["knn"] * 1e-3) / 1e9,
+                     "note": "algorithmic = 40 B x keys of the visited buckets per query key (a flat scan); the kd-blocked mirror skips "
+                             "most blocks, so 'achieved' counts bytes the kernel did not have to read: > peak is possible"})
+        sc_ms = qk["prefilter"] + qk["score"]
+        rows.append({"kernel": "prefilter_kernel + score_thread_kernel", "ms": sc_ms, "bound": "latency (descriptor gathers)", "unit": "GB/s",
+                     "achieved": extra["hint_bytes"] / (sc_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                     "note": "192 B per hint that dies at the anchor gate, 1.4 KB at the popcount gate, 2 x 608 B BCIs + 128 B x pairs otherwise"})
+        w = kern["work"]
+        fin_ms = qk["replay"] + qk["gmm_gate"] + qk["output"]
+        rows.append({"kernel": "finish_replay + finish_corr + finish_output", "ms": fin_ms, "bound": "fp64 latency", "unit": "TFLOP/s",
+                     "achieved": (60.0 * w["gate_terms"] + 10.0 * w["gate_preselect_tests"]) / (fin_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS,
+                     "note": "device-counted work of one step: 60 flops x Gaussian terms (SURVEY.md 8d) + 10 flops x pre-selection tests of the poses "
+                             "that reach the GMM-L2 gate; peak = nominal FP64 (no measured figure)"})
+        rf_ms = qk["refine"] + qk["rank"]
+        rows.append({"kernel": "refine_kernel + rank_kernel", "ms": rf_ms, "bound": "fp64 latency (sequential L-BFGS evaluations)", "unit": "TFLOP/s",
+                     "achieved": (190.0 * w["refine_terms"] + 10.0 * w["refine_preselect_tests"]) / (rf_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS,
+                     "note": "device-counted: 190 flops (value + closed-form gradient) x selected pairs x evaluations, %d evaluations in the step; "
+                             "peak = nominal FP64" % w["refine_evaluations"]})
+    for r in rows:
+        r["frac"] = r["achieved"] / r["peak"]
+    return rows
+
+
+def cpu_baseline_batched(args, eng, q_host, offsets, lb, ub, gpu_res, S, do_time=True):
     """Single-thread CPU port (oracle, + the reference's own nanoflann KD-tree when oracle/_ref is present) on a bounded
     sample of the same workload: the DB is rebuilt on the CPU side from the descriptors the GPU path produced (descriptor
-    parity is established by tests/), then `cpu_sample` query scans go through ingest + query."""
+    parity is established by tests/), then `cpu_sample` query scans go through ingest + query.  The same results are the
+    PARITY GATE of the run: they must match the GPU's for the same queries."""
+    from contour_context_b200 import capi
     from contour_context_b200 import ctypes_defs as D
     from oracle import c2o
 
     nf = c2o.use_nanoflann_build()
     n_db = args.db_scans
-    odb = c2o.DB(eng.db_cfg)
     t0 = time.time()
-    B = 128
-    for i0 in range(0, n_db, B):
-        n = min(B, n_db - i0)
-        heads = eng.heads(i0, n)
-        for j in range(n):
-            raw = np.zeros(D.VIEW_CAP, D.VIEW_DTYPE)
-            from contour_context_b200 import capi
-            capi.check(capi.lib().c2g_get_views(eng.h, i0 + j, capi.ptr(raw)))
-            s = c2o.Scan.from_descriptor(eng.cm_cfg, heads[j], raw)
-            odb.add_scan(s, 0.1 * (i0 + j))
-            odb.push_and_balance(i0 + j, 0.1 * (i0 + j))
-    t_end = 0.1 * n_db + 525.0
-    for k in range(16):
-        odb.push_and_balance(k, t_end + k)
+    odb = oracle_db_from_gpu(eng, c2o, D, capi, n_db, lambda i: 0.1 * i, flush_from=0.1 * n_db + 525.0)
     t_build = time.time() - t0
-    S = min(args.cpu_sample, len(offsets) - 1)
     pts = q_host.numpy()[: offsets[S]]
     t1 = time.time()
     res, stages = c2o.run_loop(odb, eng.cm_cfg, pts, offsets[: S + 1], 100000, np.zeros(S), True, False, lb, ub)
     dt = time.time() - t1
-    return {"value": S / dt, "unit": "scans/s", "cores": 1, "kind": "port",
-            "sample": f"{S} query scans of the same batch, ingest+query vs the same {n_db}-scan DB (DB rebuilt from the GPU "
-                      f"descriptors in {t_build:.1f} s, untimed); kNN = " + ("reference's vendored nanoflann" if nf else "exhaustive scan"),
-            "stage_ms_per_scan": {"make bev": stages[0] / S * 1e3, "KNN search": stages[1] / S * 1e3,
-                                  "Constell": stages[2] / S * 1e3, "L2 opt": stages[3] / S * 1e3},
-            "host_cores_available": os.cpu_count()}
+    # ---- parity gate: results of all S sampled queries; hint lists + per-hint cascade records of the first T
+    mism, max_d = 0, 0.0
+    for j in range(S):
+        ok, md = compare_results(gpu_res[j], res[j])
+        max_d = max(max_d, md)
+        mism += 0 if ok else 1
+    T = min(32, S)
+    q_first = n_db
+    _, gh, gs = eng.query(q_first, T, lb, ub, want_trace=True)
+    per_q = eng.hint_slots(1)
+    trace_bad = 0
+    n_hints = n_alive = n_pop = n_passed_pairs = 0
+    for j in range(T):
+        s = c2o.Scan(eng.cm_cfg, 100000 + j).ingest(pts[offsets[j]:offsets[j + 1]])
+        _, oh, os_ = odb.query(s, lb, ub)
+        if not compare_trace(gh[j * per_q:(j + 1) * per_q], gs[j * per_q:(j + 1) * per_q], oh, os_):
+            trace_bad += 1
+        n_hints += len(oh)
+        n_alive += int((os_["passed"] != 0).sum())          # passed the anchor gate
+        n_pop += int(((os_["passed"] == 1) | (os_["passed"] == -2) | ((os_["passed"] == -1) & (os_["constell"][:, 2] > 0))).sum())
+        n_passed_pairs += int(os_["n_pairs"][os_["passed"] == 1].sum())
+    parity = {"checked": int(S), "mismatches": int(mism + trace_bad), "max_abs_corr_diff": max_d,
+              "result_mismatches": int(mism), "trace_checked": int(T), "trace_mismatches": int(trace_bad),
+              "what": "c2g_query_result of the sampled queries vs the CPU oracle on the same points and the same DB (integer fields equal, "
+                      "correlations <= 1e-5); hint lists, dist_sq bytes and per-hint integer scores of the first trace_checked queries"}
+    # ---- work counts for the roofline entries of the query kernels, scaled from the sample to the step
+    Q = args.queries
+    scale = Q / float(T)
+    extra = {}
+    # kNN: keys of the visited buckets per non-zero query key (the reference's one-sided bucket walk, contour_db.cpp:319-379)
+    heads = eng.heads(q_first, T)
+    visited = 0
+    for ll in range(eng.db_cfg.n_q_levels):
+        rng, tsz, _ = eng.db_layer_state(ll)
+        lev = eng.db_cfg.q_levels[ll]
+        for j in range(T):
+            for seq in range(eng.cm_cfg.piv_firsts):
+                key = heads[j]["keys"][lev][seq]
+                if not (key.sum() != 0):
+                    continue
+                mid = 0
+                for i in range(D.NUM_BUCKETS):
+                    if rng[i] <= key[0] < rng[i + 1]:
+                        mid = i
+                        break
+                vis = set()
+                for i in range(D.NUM_BUCKETS):
+                    if i == 0:
+                        vis.add(mid)
+                    elif mid - i >= 0:
+                        vis.add(mid - i)
+                    elif mid + i < D.NUM_BUCKETS:
+                        vis.add(mid + i)
+                visited += int(sum(tsz[b] for b in vis))
+    extra["knn_visited_keys"] = visited * scale
+    extra["hint_bytes"] = ((n_hints - n_alive) * 192.0 + (n_alive - n_pop) * 1400.0 + n_pop * (2 * 608.0 + 2 * 80.0) + n_passed_pairs * 160.0) * scale
+    cb = None
+    if do_time:
+        cb = {"value": S / dt, "unit": "scans/s", "cores": 1, "kind": "port",
+              "sample": f"{S} query scans of the same batch, ingest+query vs the same {n_db}-scan DB (DB rebuilt from the GPU "
+                        f"descriptors in {t_build:.1f} s, untimed); kNN = " + ("reference's vendored nanoflann" if nf else "exhaustive scan"),
+              "stage_ms_per_scan": {"make bev": stages[0] / S * 1e3, "KNN search": stages[1] / S * 1e3,
+                                    "Constell": stages[2] / S * 1e3, "L2 opt": stages[3] / S * 1e3},
+              "host_cores_available": os.cpu_count()}
+    return cb, parity, extra
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+def kitti08_layout(n):
+    """KITTI-08-shaped synthetic trajectory: n/4 places, the vehicle drives through all of them and comes back three more
+    times (visit-major order), so every scan of the later passes has true loop-closure partners ~n/4 scans (~106 s) earlier."""
+    n_scenes = (n + VISITS - 1) // VISITS
+    seeds = [i % n_scenes for i in range(n)]
+    visits = [i // n_scenes for i in range(n)]
+    return seeds, visits
+
+
+def run_kitti08(args):
+    import torch
+
+    import __graft_entry__ as g
+    from contour_context_b200 import capi
+    from contour_context_b200 import ctypes_defs as D
+    from contour_context_b200 import synth
+    from contour_context_b200.engine import Engine
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # the online loop is serial in the DB state (SURVEY.md §8e: only batches of independent queries shard): replicas only
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(0)
+    numa = bind_near_gpu(0)
+    g.build_c2g()
+    capi.lib()
+    n, W, n_pts = args.seq_scans, args.window, args.points
+    lb, ub = D.kitti_thres()
+    seeds, visits = kitti08_layout(n)
+    ts = 0.104 * np.arange(n)  # sample_data/ts-sens_pose-kitti08.txt:2-3
+    # the whole sequence: device-resident copy (value) and page-locked host copy (e2e)
+    t0 = time.time()
+    pts_host = torch.empty((n * n_pts, 4), dtype=torch.float32, pin_memory=True)
+    pts_dev = torch.empty((n * n_pts, 4), dtype=torch.float32, device="cuda")
+    for i0 in range(0, n, 148):
+        m = min(148, n - i0)
+        blk = synth.make_scans(seeds[i0:i0 + m], visits[i0:i0 + m], n_pts, device="cuda", noise_seed=i0).reshape(-1, 4)
+        pts_dev[i0 * n_pts:(i0 + m) * n_pts] = blk
+        del blk
+    pts_host.copy_(pts_dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    offsets = np.arange(n + 1, dtype=np.int64) * n_pts
+    wins = [(i0, min(W, n - i0)) for i0 in range(0, n, W)]
+    res_pinned = torch.empty(n * D.QUERY_RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    res_np = res_pinned.numpy().view(D.QUERY_RESULT_DTYPE)
+    stream = torch.cuda.Stream()
+    ids = np.arange(n, dtype=np.int32)
+
+    def run_sequence(host_inputs: bool, n_wins=None):
+        """Fresh context, whole sequence through the windowed loop: stage(k + 1) is issued before commit(k), so that the copy and
+        ingest of the next window overlap the bookkeeping and the queries of the current one."""
+        eng = Engine(device=0, scan_capacity=n + 8, max_batch=W, max_points=W * n_pts)
+        eng.set_stream(stream.cuda_stream)
+        src = pts_host if host_inputs else pts_dev
+        use = wins if n_wins is None else wins[:n_wins]
+
+        def stage(k):
+            i0, m = use[k]
+            eng.online_stage(src[i0 * n_pts:(i0 + m) * n_pts], offsets[i0:i0 + m + 1] - offsets[i0], int_ids=ids[i0:i0 + m],
+                             on_device=not host_inputs)
+
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        t_w = time.time()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            stage(0)
+            for k, (i0, m) in enumerate(use):
+                if k + 1 < len(use):
+                    stage(k + 1)
+                eng.online_commit(ts[i0:i0 + m], ids[i0:i0 + m], lb, ub, res_np[i0:i0 + m])
+            e1.record(stream)
+        stream.synchronize()
+        wall = time.time() - t_w
+        return eng, e0.elapsed_time(e1), wall, eng.launch_count() - l0, sum(m for _, m in use)
+
+    # warm-up: the first windows on a throw-away context (lazy module load, attribute setup, allocator)
+    for _ in range(max(1, min(args.warmup, 3))):
+        e, *_ = run_sequence(True, n_wins=min(4, len(wins)))
+        e.close()
+    sampler = ClockSampler(0)
+    sampler.start()
+    eng_d, ms_dev, wall_dev, launches, n_done = run_sequence(False)
+    res_dev = res_np.copy()
+    eng_d.close()
+    eng, ms_e2e, wall_e2e, _, _ = run_sequence(True)
+    clocks = sampler.stop()
+    res = res_np.copy()
+    if res.tobytes() != res_dev.tobytes():
+        raise RuntimeError("device-input and host-input runs of the sequence returned different results")
+    if int(res["overflow"].max()) != 0:
+        raise RuntimeError("a query proposed more candidate poses than C2G_MAX_CAND")
+    n_lc = int((res["n_cand"] > 0).sum())
+    # ingest pair on one window (device-resident points), for the roofline entry
+    i0, m = wins[len(wins) // 2]
+    probe = Engine(device=0, scan_capacity=W + 8, max_batch=W, max_points=W * n_pts)
+    probe.set_stream(stream.cuda_stream)
+
+    def ev_time(fn, reps=5):
+        out = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                a.record(stream)
+                fn()
+                b.record(stream)
+            stream.synchronize()
+            out.append(a.elapsed_time(b))
+        return float(np.mean(out[1:]))
+
+    win_pts, win_off = pts_dev[i0 * n_pts:(i0 + m) * n_pts], offsets[i0:i0 + m + 1] - offsets[i0]
+    k1_ms = ev_time(lambda: probe.ingest_bev_only(win_pts, win_off, on_device=True))
+    ing_ms = ev_time(lambda: probe.ingest(win_pts, win_off, first_slot=0, on_device=True))
+    probe.close()
+    peak, peak_src = load_peaks()
+    ach = m * (16.0 * n_pts + 60000.0) / (ing_ms * 1e-3) / 1e9
+    traffic, traffic_src = ingest_traffic(m, n_pts)
+    out = {
+        "metric": metric_name(args), "value": n / (ms_dev * 1e-3), "unit": "scans/s", "n_gpus": 1, "steps": len(wins), "warmup": args.warmup,
+        "ms_per_step": ms_dev / len(wins), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (BEV/CCL/keys, no FMA) + f64 (moments, GMM-L2)", "data": "synthetic",
+        "config": {"workload": WORKLOADS["kitti08"], "config": "kitti08", "seq_scans": n, "window": W, "points_per_scan": n_pts,
+                   "ts_step_s": 0.104, "steps_are": "windows of the sequence; the timed region is the whole sequence on a fresh context "
+                   "(a warm-up run of the first windows on a throw-away context precedes it)",
+                   "l2": "inputs larger than L2 (each window streams %.2f GB of points)" % (W * n_pts * 16 / 1e9),
+                   "trajectory": f"{(n + VISITS - 1) // VISITS} places driven through {VISITS} times (revisits ~{0.104 * ((n + VISITS - 1) // VISITS):.0f} s later)",
+                   "host_binding": numa, "data_gen_s": t_gen},
+        "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": int(W * n_pts * 16 + (W + 1) * 8),
+                "d2h_bytes_per_step": int(W * (D.QUERY_RESULT_DTYPE.itemsize + 1440)), "ms_per_step": ms_e2e / len(wins),
+                "wall_s": wall_e2e},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": f"bev_scatter_kernel + contour_kernel on one {m}-scan window (1.98 MB algorithmic bytes per scan)",
+                     "kernel_ms": {"bev_scatter_ms": k1_ms, "ingest_ms": ing_ms}},
+        "sanity": {"scans_with_loop_candidate": n_lc, "of": n, "knn_runs": eng.online_runs(), "windows": len(wins),
+                   "wall_s_device_inputs": wall_dev, "exp_mode": eng.exp_mode()},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import c2o
+
+        nf = c2o.use_nanoflann_build()
+        S = min(args.cpu_sample, n // 2)
+        start = (n // 2 // W) * W  # mid-sequence (average DB size), aligned to a window
+        t0 = time.time()
+        odb = oracle_db_from_gpu(eng, c2o, D, capi, start, lambda i: float(ts[i]))
+        t_build = time.time() - t0
+        p = pts_host.numpy()[start * n_pts:(start + S) * n_pts]
+        t1 = time.time()
+        ores, stages = c2o.run_loop(odb, eng.cm_cfg, p, offsets[start:start + S + 1] - offsets[start], start, ts[start:start + S], True, True, lb, ub)
+        dt = time.time() - t1
+        mism, max_d = 0, 0.0
+        for j in range(S):
+            ok, md = compare_results(res[start + j], ores[j])
+            max_d = max(max_d, md)
+            mism += 0 if ok else 1
+        out["parity"] = {"checked": int(S), "mismatches": int(mism), "max_abs_corr_diff": max_d,
+                         "what": f"scans {start}..{start + S - 1} of the sequence: windowed GPU loop vs the CPU oracle's scan-by-scan loop "
+                                 "(query -> addScan -> pushAndBalance) continued from the same DB state"}
+        out["cpu_baseline"] = {"value": S / dt, "unit": "scans/s", "cores": 1, "kind": "port",
+                               "sample": f"{S} consecutive scans from mid-sequence (scan {start}), ingest + query + addScan + pushAndBalance, DB of the first "
+                                         f"{start} scans rebuilt from the GPU descriptors in {t_build:.1f} s (untimed); kNN = "
+                                         + ("reference's vendored nanoflann" if nf else "exhaustive scan"),
+                               "stage_ms_per_scan": {"make bev": stages[0] / S * 1e3, "KNN search": stages[1] / S * 1e3, "Constell": stages[2] / S * 1e3,
+                                                     "L2 opt": stages[3] / S * 1e3, "Update database": stages[4] / S * 1e3},
+                               "host_cores_available": os.cpu_count()}
+        out["speedup_vs_cpu_1thread"] = {"e2e": out["e2e"]["value"] / out["cpu_baseline"]["value"], "value": out["value"] / out["cpu_baseline"]["value"]}
+    print(json.dumps(out))
+    eng.close()
+    if out.get("parity", {}).get("mismatches", 0) > 0:
+        raise SystemExit("parity gate failed: GPU results differ from the CPU oracle on the same inputs")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated in oracle/, KD-tree = the reference's vendored nanoflann when
-    oracle/_ref exists) on all host cores. Rank 0 only; other ranks exit."""
+    oracle/_ref exists) on --cpu-threads host threads. Rank 0 only; other ranks exit."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
@@ -384,40 +818,65 @@ def run_reference(args):
     nf = c2o.use_nanoflann_build()
     cfg, dbc = D.kitti_cm_config(), D.kitti_db_config()
     lb, ub = D.kitti_thres()
-    n_db, n_pts = args.db_scans, args.points
-    threads = os.cpu_count() or 1
+    n_pts = args.points
+    threads = max(1, min(args.cpu_threads, os.cpu_count() or 1))
     dev = "cuda" if torch.cuda.is_available() else "cpu"  # torch only generates the synthetic input data here
     odb = c2o.DB(dbc)
     from concurrent.futures import ThreadPoolExecutor
 
     pool = ThreadPoolExecutor(threads)
     t0 = time.time()
-    seeds, visits = synth.db_layout(n_db, VISITS)
+    online = args.config == "kitti08"
+    if online:
+        n_seq = args.seq_scans
+        seeds, visits = kitti08_layout(n_seq)
+        n_db = (n_seq // 2 // args.window) * args.window  # mid-sequence DB, like the GPU arm's cpu_baseline sample
+        ts_of = lambda i: 0.104 * i  # noqa: E731
+    else:
+        n_db = args.db_scans
+        seeds, visits = synth.db_layout(n_db, VISITS)
+        ts_of = lambda i: 0.1 * i  # noqa: E731
     chunk = 148
     for i0 in range(0, n_db, chunk):
         n = min(chunk, n_db - i0)
         pts = synth.make_scans(seeds[i0:i0 + n], visits[i0:i0 + n], n_pts, device=dev, noise_seed=i0).cpu().numpy()
         scans = list(pool.map(lambda j: c2o.Scan(cfg, i0 + j).ingest(pts[j]), range(n)))
         for j, s in enumerate(scans):
-            odb.add_scan(s, 0.1 * (i0 + j))
-            odb.push_and_balance(i0 + j, 0.1 * (i0 + j))
-    for k in range(16):
-        odb.push_and_balance(k, 0.1 * n_db + 525.0 + k)
+            odb.add_scan(s, ts_of(i0 + j))
+            odb.push_and_balance(i0 + j, ts_of(i0 + j))
+    if not online:
+        for k in range(16):
+            odb.push_and_balance(k, 0.1 * n_db + 525.0 + k)
     t_build = time.time() - t0
     S = max(threads, min(args.queries, 4 * threads))  # bounded sample per step
-    n_scenes = n_db // VISITS
-    q = synth.make_scans(list(range(S)), [VISITS] * S, n_pts, device=dev, noise_seed=777).cpu().numpy().reshape(-1, 4)
-    offsets = np.arange(S + 1, dtype=np.int64) * n_pts
-    parts = np.array_split(np.arange(S), threads)
+    if online:
+        # the loop is serial in the DB state: ingest of the step's scans on all threads, then query -> add -> balance in order;
+        # every step continues the sequence (S new scans), so steps are not repeats of each other
+        total = S * (args.steps + args.warmup)
+        q = synth.make_scans(seeds[n_db:n_db + total], visits[n_db:n_db + total], n_pts, device=dev, noise_seed=n_db).cpu().numpy()
+        cursor = [0]
 
-    def work(idx):
-        if len(idx) == 0:
-            return
-        a, b = idx[0], idx[-1] + 1
-        c2o.run_loop(odb, cfg, q[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], 100000 + a, np.zeros(b - a), True, False, lb, ub)
+        def step():
+            a = cursor[0]
+            scans = list(pool.map(lambda j: c2o.Scan(cfg, n_db + j).ingest(q[j]), range(a, a + S)))
+            for j, s in enumerate(scans):
+                odb.query(s, lb, ub)
+                odb.add_scan(s, ts_of(n_db + a + j))
+                odb.push_and_balance(n_db + a + j, ts_of(n_db + a + j))
+            cursor[0] = a + S
+    else:
+        q = synth.make_scans(list(range(S)), [VISITS] * S, n_pts, device=dev, noise_seed=777).cpu().numpy().reshape(-1, 4)
+        offsets = np.arange(S + 1, dtype=np.int64) * n_pts
+        parts = np.array_split(np.arange(S), threads)
 
-    def step():
-        list(pool.map(work, parts))
+        def work(idx):
+            if len(idx) == 0:
+                return
+            a, b = idx[0], idx[-1] + 1
+            c2o.run_loop(odb, cfg, q[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], 100000 + a, np.zeros(b - a), True, False, lb, ub)
+
+        def step():
+            list(pool.map(work, parts))
 
     for _ in range(args.warmup):
         step()
@@ -426,14 +885,20 @@ def run_reference(args):
         step()
     dt = time.time() - t1
     value = S * args.steps / dt
+    cfg_out = {"workload": WORKLOADS[args.config], "config": args.config, "points_per_scan": n_pts, "queries_per_step": S,
+               "cpu_threads": threads}
+    if online:
+        cfg_out.update({"seq_scans": args.seq_scans, "window": args.window, "db_scans_at_start": n_db})
+    else:
+        cfg_out.update({"db_scans": n_db, "queries_per_rank_per_step": S})
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 + f64 (CPU, no FMA contraction)", "data": "synthetic",
-        "config": {"workload": "configs[2]: synthetic 120k-pt scans, 5k-scan DB", "db_scans": n_db, "points_per_scan": n_pts,
-                   "queries_per_step": S},
+        "config": cfg_out,
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": threads, "kind": "port",
-                         "sample": f"{S} query scans per step over {threads} threads vs the {n_db}-scan DB (built on the CPU in {t_build:.0f} s); "
+                         "sample": f"{S} scans per step over {threads} threads vs the {n_db}-scan DB (built on the CPU in {t_build:.0f} s); "
+                                   "a bounded sample of the GPU arm's step (same DB, same points per scan, same per-scan work); "
                                    + ("kNN through the reference's own vendored nanoflann (oracle/_ref)" if nf else "exhaustive-scan kNN")},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -443,5 +908,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "kitti08":
+        run_kitti08(a)
     else:
-        run_b200(a)
+        run_batched(a)

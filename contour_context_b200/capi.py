@@ -52,6 +52,12 @@ def lib():
         L.c2g_db_add_scans.argtypes = [vp, ip, ip, vp]
         L.c2g_db_push_and_balance.argtypes = [vp, ip, C.c_double]
         L.c2g_db_size.argtypes = [vp]
+        L.c2g_online_stage.argtypes = [vp, vp, vp, ip, ip, vp]
+        L.c2g_online_commit.argtypes = [vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
+        L.c2g_online_window.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
+        L.c2g_work_counters.argtypes = [vp, ip, vp]
+        L.c2g_online_runs.restype = ll
+        L.c2g_online_runs.argtypes = [vp]
         L.c2g_db_sync.argtypes = [vp]
         L.c2g_db_layer_state.argtypes = [vp, ip, vp, vp, vp]
         L.c2g_db_bucket_tree.argtypes = [vp, ip, ip, vp, vp, vp]

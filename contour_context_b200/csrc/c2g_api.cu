@@ -26,6 +26,8 @@ size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row);
 int c2g_query_alloc(c2g_ctx *ctx);
 int c2g_db_sync_mode(c2g_ctx *ctx, int want_kd);  // query.cu
 void c2g_query_free(c2g_ctx *ctx);
+int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *keys_host, const double *ts_host, const int *seeds_host,
+                           const c2g_score_ensemble *lb, const c2g_score_ensemble *ub, c2g_query_result *results_host);  // query.cu
 int c2g_refine_alloc(c2g_ctx *ctx);  // refine.cu
 void c2g_refine_free(c2g_ctx *ctx);
 
@@ -97,8 +99,9 @@ int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, 
     *pts_dev = pts;
   } else {
     if (offsets_host[B] > ctx->max_points) return C2G_ERR_CAPACITY;
+    // staging buffer 0 may still be the target of an earlier pipelined ingest's copy stream or be read by its kernels
+    C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free[0], 0));
     C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage2[0], pts, sizeof(float) * 4 * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
-    C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[0], ctx->stream));
     *pts_dev = ctx->d_pts_stage2[0];
   }
   return 0;
@@ -144,11 +147,14 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   ctx->scan_cap = scan_capacity;
   ctx->max_batch = max_batch;
   ctx->max_points = max_points;
-  cudaError_t e = cudaSetDevice(device);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e == cudaSuccess && (device < 0 || device >= n_dev)) e = cudaErrorInvalidDevice;
   if (e != cudaSuccess) {
     delete ctx;
     return -(int) e;
   }
+  C2gDeviceGuard guard(device);  // the caller's current device is restored on every exit path
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) {
@@ -212,6 +218,14 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
     c2g_destroy(ctx);
     return rc;
   }
+  for (int i = 0; i < 2; ++i) {
+    e = cudaHostAlloc((void **) &ctx->staged[i].h_keys, sizeof(float) * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM * (size_t) max_batch, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->staged[i].ev_keys, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      c2g_destroy(ctx);
+      return -(int) e;
+    }
+  }
   ctx->hostdb = new (std::nothrow) C2gHostDB();
   if (!ctx->hostdb) {
     c2g_destroy(ctx);
@@ -226,11 +240,15 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
 
 int c2g_destroy(c2g_ctx *ctx) {
   if (!ctx) return 0;
-  cudaSetDevice(ctx->device);
+  C2gDeviceGuard guard(ctx->device);
   cudaDeviceSynchronize();
   c2g_query_free(ctx);
   c2g_refine_free(ctx);
   delete ctx->hostdb;
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->staged[i].h_keys) cudaFreeHost(ctx->staged[i].h_keys);
+    if (ctx->staged[i].ev_keys) cudaEventDestroy(ctx->staged[i].ev_keys);
+  }
   cudaFree(ctx->d_pts_stage2[0]);
   cudaFree(ctx->d_pts_stage2[1]);
   for (int i = 0; i < 2; ++i)
@@ -275,16 +293,22 @@ int c2g_set_stream(c2g_ctx *ctx, void *cuda_stream) {
 
 int c2g_sync(c2g_ctx *ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device) {
+  if (!ctx) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   const float *pts_dev = nullptr;
   int rc = stage_inputs(ctx, pts, offsets_host, B, pts_on_device, &pts_dev);
   if (rc) return rc;
   rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, ctx->d_tiles, ctx->num_sms, ctx->stream);
   if (rc) return rc;
+  // the staging buffer is free again once the kernel that reads it has run (a later c2g_get_bev of this batch is ordered
+  // behind it on the same stream; a later pipelined ingest waits for this event before its copy stream overwrites the buffer)
+  if (!pts_on_device) C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[0], ctx->stream));
   ctx->launches += 1;
   ctx->last_B = B;
   ctx->last_pts = pts_dev;
@@ -332,6 +356,7 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
 int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
                const int *int_ids_host) {
   if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   const int *ids_dev = nullptr;
   if (int_ids_host) {
     C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids, int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
@@ -349,6 +374,7 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
 
 int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host) {
   if (!ctx || !out_host || first_slot < 0 || n < 0 || first_slot + n > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_heads + first_slot, sizeof(c2g_scan_head) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -356,6 +382,7 @@ int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host) 
 
 int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host) {
   if (!ctx || !out_host || slot < 0 || slot >= ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_views + (size_t) slot * C2G_VIEW_CAP, sizeof(c2g_view) * C2G_VIEW_CAP, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -363,6 +390,7 @@ int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host) {
 
 int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f) {
   if (!ctx || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   const size_t n = ctx->P.n_cells, off = n * batch_index;
   // the contour kernel only fills the cells that belong to a contour; the full dense image (getBevImage, bev_pixfs_) is
   // produced on demand from the tile and the points of the last batch (still resident: staging buffer or caller's buffer)
@@ -381,6 +409,7 @@ int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *
 
 int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host) {
   if (!ctx || !out_host || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   const size_t n = ctx->P.n_cells;
   C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_tiles + n * batch_index, sizeof(c2g_cellkey) * n, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -389,6 +418,7 @@ int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host) {
 
 int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n) {
   if (!ctx || n < 0 || src_first < 0 || dst_first < 0 || src_first + n > ctx->scan_cap || dst_first + n > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   if (n == 0 || src_first == dst_first) return 0;
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_heads + dst_first, ctx->d_heads + src_first, sizeof(c2g_scan_head) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_views + (size_t) dst_first * C2G_VIEW_CAP, ctx->d_views + (size_t) src_first * C2G_VIEW_CAP,
@@ -400,8 +430,9 @@ int c2g_copy_slots(c2g_ctx *ctx, int src_first, int dst_first, int n) {
 
 int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host) {
   if (!ctx || !ts_host || n <= 0 || first_slot < 0 || first_slot + n > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2gHostDB &db = *ctx->hostdb;
-  if (first_slot != db.n_scans) return C2G_ERR_STATE;  // gidx == all_bevs_.size() at the time of addScan
+  if (first_slot != db.n_scans || ctx->n_staged) return C2G_ERR_STATE;  // gidx == all_bevs_.size() at the time of addScan
   std::vector<float> keys((size_t) n * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM);
   const size_t kbytes = sizeof(float) * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
   C2G_CUDA_TRY(cudaMemcpy2DAsync(keys.data(), kbytes, (const char *) (ctx->d_heads + first_slot) + offsetof(c2g_scan_head, keys),
@@ -420,6 +451,66 @@ int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host)
   return 0;
 }
 
+int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host) {
+  if (!ctx || W <= 0 || W > ctx->max_batch) return C2G_ERR_ARG;
+  if (ctx->n_staged >= 2) return C2G_ERR_STATE;
+  int first_slot = ctx->hostdb->n_scans;
+  for (int k = 0; k < ctx->n_staged; ++k) first_slot += ctx->staged[(ctx->staged_head + k) & 1].W;
+  if (first_slot + W > ctx->scan_cap) return C2G_ERR_CAPACITY;
+  int rc = c2g_ingest(ctx, pts, offsets_host, W, pts_on_device, first_slot, int_ids_host);
+  if (rc) return rc;
+  C2gDeviceGuard guard(ctx->device);
+  auto &st = ctx->staged[(ctx->staged_head + ctx->n_staged) & 1];
+  st.first_slot = first_slot;
+  st.W = W;
+  const size_t kbytes = sizeof(float) * C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
+  C2G_CUDA_TRY(cudaMemcpy2DAsync(st.h_keys, kbytes, (const char *) (ctx->d_heads + first_slot) + offsetof(c2g_scan_head, keys), sizeof(c2g_scan_head), kbytes,
+                                 (size_t) W, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaEventRecord(st.ev_keys, ctx->stream));
+  ctx->n_staged++;
+  return 0;
+}
+
+int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+                      c2g_query_result *results_host) {
+  if (!ctx || !ts_host || !seeds_host || !lb || !ub) return C2G_ERR_ARG;
+  if (ctx->n_staged <= 0) return C2G_ERR_STATE;
+  C2gDeviceGuard guard(ctx->device);
+  auto &st = ctx->staged[ctx->staged_head];
+  C2G_CUDA_TRY(cudaEventSynchronize(st.ev_keys));  // the only wait of the window: its 1.4 KB of keys per scan
+  int rc = c2g_online_commit_impl(ctx, st.first_slot, st.W, st.h_keys, ts_host, seeds_host, lb, ub, results_host);
+  if (rc) return rc;
+  ctx->staged_head ^= 1;
+  ctx->n_staged--;
+  ctx->db_dirty = 1;  // the trees may have changed after the window's last run was launched
+  return 0;
+}
+
+int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host,
+                      const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+                      c2g_query_result *results_host) {
+  if (ctx && ctx->n_staged != 0) return C2G_ERR_STATE;
+  int rc = c2g_online_stage(ctx, pts, offsets_host, W, pts_on_device, int_ids_host);
+  if (rc) return rc;
+  rc = c2g_online_commit(ctx, ts_host, seeds_host, lb, ub, results_host);
+  if (rc) return rc;
+  C2gDeviceGuard guard(ctx->device);
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+long long c2g_online_runs(c2g_ctx *ctx) { return ctx ? ctx->online_runs : 0; }
+
+int c2g_work_counters(c2g_ctx *ctx, int enable, unsigned long long *out_host) {
+  if (!ctx) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (out_host) C2G_CUDA_TRY(cudaMemcpy(out_host, ctx->d_work, sizeof(unsigned long long) * C2G_WORK_N, cudaMemcpyDeviceToHost));
+  C2G_CUDA_TRY(cudaMemset(ctx->d_work, 0, sizeof(unsigned long long) * C2G_WORK_N));
+  ctx->count_work = enable ? 1 : 0;
+  return 0;
+}
+
 int c2g_db_push_and_balance(c2g_ctx *ctx, int seed, double ts) {
   if (!ctx) return C2G_ERR_ARG;
   c2g_hostdb_push_and_balance(*ctx->hostdb, seed, ts);
@@ -431,6 +522,7 @@ int c2g_db_size(c2g_ctx *ctx) { return ctx ? ctx->hostdb->n_scans : C2G_ERR_ARG;
 
 int c2g_db_sync(c2g_ctx *ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   if (!ctx->db_dirty && !ctx->db_not_kd) return 0;
   int rc = c2g_db_sync_mode(ctx, 1);  // query.cu: patches the mirror, kd-blocks every bucket
   if (rc) return rc;
@@ -531,6 +623,7 @@ long long c2g_launch_count(c2g_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out) {
   if (!ctx) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   if (ms_out) {  // durations of the last profiled c2g_query_async: knn, prefilter, score, replay, corr, output, refine, rank
     if (!ctx->prof_on) return C2G_ERR_STATE;
     C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -549,6 +642,7 @@ int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out) {
 /* developer aid: per-phase clock64() stamps of CTA 0's first scan in the last contour kernel (64 values) */
 int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host) {
   if (!ctx || !out_host) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;

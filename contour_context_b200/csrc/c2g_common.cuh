@@ -74,7 +74,23 @@ __device__ __forceinline__ bool c2g_sqrt_lt(double x, double y) {
   return sqrt(x) < y;
 }
 
-// cudaFuncSetAttribute is per device: remember which devices of this process already have the attribute
+// Every extern "C" entry point that touches CUDA makes the context's device current for its duration and restores the
+// caller's device on exit: a process may own contexts on several GPUs (streams, events and kernel attributes are per device).
+struct C2gDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit C2gDeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~C2gDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  C2gDeviceGuard(const C2gDeviceGuard &) = delete;
+  C2gDeviceGuard &operator=(const C2gDeviceGuard &) = delete;
+};
+
+// cudaFuncSetAttribute is per device: remember which devices of this process already have the attribute (the current device
+// is the context's: C2gDeviceGuard)
 static inline bool c2g_first_use_on_device(unsigned long long &mask) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;

@@ -4,6 +4,8 @@
 
 #define C2G_MAX_CHUNK_EVENTS 64
 #define C2G_QUERY_STREAMS 8  // sub-batches of one c2g_query_async call that may run concurrently
+#define C2G_WORK_N 8   // knn keys evaluated, knn block boxes tested, gate pre-selection tests, gate terms, refine pre-selection tests,
+                       // refine pair terms (pairs x evaluations), refine evaluations, (spare)
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
@@ -71,6 +73,16 @@ struct c2g_ctx {
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state
   int db_not_kd;           // some buckets of the mirror are in tree order (fine for the online loop, slow for big batches)
+  // windowed online loop (c2g_online_stage / c2g_online_commit): staged = ingested, keys on their way to the host, not yet in the DB
+  struct {
+    int first_slot, W;
+    cudaEvent_t ev_keys;   // the keys of the window have arrived in h_keys
+    float *h_keys;         // pinned, [max_batch][C2G_NLEV][C2G_MAX_PIV][C2G_KEY_DIM]
+  } staged[2];
+  int n_staged, staged_head;  // FIFO of at most two windows (the next one is ingested while the current one is queried)
+  unsigned long long *d_work;  // [C2G_WORK_N] work counters of the query kernels (c2g_work_counters); handed to the kernels only while enabled
+  int count_work;
+  long long online_runs;      // kNN launches of the windowed loop so far (= runs of scans that saw identical trees)
   // optional per-kernel timing of the query path (c2g_query_profile): event k is recorded after kernel k - 1
   int prof_on;
   cudaEvent_t prof_ev[C2G_QPROF_N + 1];

@@ -19,11 +19,13 @@ bool need_pop(const C2gBucket &b, double curr_ts, double max_elapse) {
   return true;
 }
 
-void pop_buffer_max(C2gBucket &b, double curr_ts, double min_elapse) {
+// `changed` is set when the searchable contents of a tree change (C2gHostDB::tree_version)
+void pop_buffer_max(C2gBucket &b, double curr_ts, double min_elapse, bool &changed) {
   const double cutoff = curr_ts - min_elapse;
   size_t gap = 0;
   while (gap < b.buffer.size() && !(b.buffer[gap].ts >= cutoff)) ++gap;
   if (gap == 0) return;
+  changed = true;
   for (size_t i = 0; i < gap; ++i) b.tree.push_back(b.buffer[i].key);
   b.buffer.erase(b.buffer.begin(), b.buffer.begin() + (long) gap);
 }
@@ -69,7 +71,7 @@ void move_buffer(C2gBucket &from, C2gBucket &to, float split_val, bool donor_is_
   from.buffer.resize((size_t) rem);
 }
 
-void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elapse, double min_elapse) {
+void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elapse, double min_elapse, bool &changed) {
   C2gBucket &tr1 = L.buckets[idx_t1], &tr2 = L.buckets[idx_t1 + 1];
   const bool pb1 = need_pop(tr1, curr_ts, max_elapse), pb2 = need_pop(tr2, curr_ts, max_elapse);
   if (!pb1 && !pb2) return;
@@ -77,16 +79,16 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
   const double diff_ratio = 1.0 * std::abs(sz1 - sz2) / std::max(sz1, sz2);  // NaN for two empty trees, as in the reference
   const bool small = diff_ratio < kImbaDiffRatio || std::max(sz1, sz2) < kMinElemSplit;
   if (pb1 && !pb2 && small) {
-    pop_buffer_max(tr1, curr_ts, min_elapse);
+    pop_buffer_max(tr1, curr_ts, min_elapse, changed);
     return;
   }
   if (!pb1 && pb2 && small) {
-    pop_buffer_max(tr2, curr_ts, min_elapse);
+    pop_buffer_max(tr2, curr_ts, min_elapse, changed);
     return;
   }
   if (diff_ratio < 0.5 * kImbaDiffRatio) {
-    if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse);
-    if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse);
+    if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse, changed);
+    if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse, changed);
     return;
   }
   const bool donor_is_lower = sz1 > sz2;
@@ -94,8 +96,8 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
   C2gBucket &lit = donor_is_lower ? tr2 : tr1;
   const int szb = donor_is_lower ? sz1 : sz2, szl = donor_is_lower ? sz2 : sz1;
   if (szb == 0) {  // unreachable in the reference (it would index an empty vector); nothing to balance
-    if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse);
-    if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse);
+    if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse, changed);
+    if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse, changed);
     return;
   }
   const int to_move_max = int((szb - szl + kImbaDiffRatio * szl) / (2 - kImbaDiffRatio));
@@ -111,7 +113,10 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
 
   int num_to_move = 0;
   float split_val = tr1.end;
-  if (val(to_move_mid) != val(to_move_mid + 1)) {
+  // to_move_mid == 0 (sizes differ by one): the reference compares sort_permu[szb] - one past the end - with its neighbour;
+  // whatever that read returns, nothing below can produce num_to_move > 0, so it ends in the "cannot split" branch
+  if (to_move_mid == 0) {
+  } else if (val(to_move_mid) != val(to_move_mid + 1)) {
     num_to_move = to_move_mid;
     // lower donor: the smallest moved key becomes the boundary; upper donor: the smallest key that stays
     split_val = donor_is_lower ? val(to_move_mid) : val(to_move_mid + 1);
@@ -133,24 +138,25 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
   }
   if (num_to_move == 0) {  // a strip of equal bucket values prevents the split
     if (donor_is_lower) {
-      pop_buffer_max(tr1, curr_ts, min_elapse);
-      if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse);
+      pop_buffer_max(tr1, curr_ts, min_elapse, changed);
+      if (pb2) pop_buffer_max(tr2, curr_ts, min_elapse, changed);
     } else {
-      if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse);
-      pop_buffer_max(tr2, curr_ts, min_elapse);
+      if (pb1) pop_buffer_max(tr1, curr_ts, min_elapse, changed);
+      pop_buffer_max(tr2, curr_ts, min_elapse, changed);
     }
     return;
   }
   move_tail(big, lit, perm, num_to_move, split_val, donor_is_lower);  // `big` is permuted and cut, `lit` only grows
   big.restructured++;
+  changed = true;
   move_buffer(big, lit, split_val, donor_is_lower);
   tr1.end = tr2.beg = split_val;
   L.ranges[idx_t1 + 1] = split_val;
   auto by_ts = [](const C2gBufRec &a, const C2gBufRec &b) { return a.ts < b.ts; };
   std::sort(tr1.buffer.begin(), tr1.buffer.end(), by_ts);
   std::sort(tr2.buffer.begin(), tr2.buffer.end(), by_ts);
-  pop_buffer_max(tr1, curr_ts, min_elapse);
-  pop_buffer_max(tr2, curr_ts, min_elapse);
+  pop_buffer_max(tr1, curr_ts, min_elapse, changed);
+  pop_buffer_max(tr2, curr_ts, min_elapse, changed);
 }
 
 }  // namespace
@@ -197,5 +203,7 @@ void c2g_hostdb_push(C2gHostDB &db, int ll, const float *key, double ts, int gid
 void c2g_hostdb_push_and_balance(C2gHostDB &db, int seed, double ts) {
   int idx_t1 = std::abs(seed) % (2 * (C2G_NUM_BUCKETS - 2));
   if (idx_t1 > (C2G_NUM_BUCKETS - 2)) idx_t1 = 2 * (C2G_NUM_BUCKETS - 2) - idx_t1;
-  for (int l = 0; l < db.n_layers; ++l) rebuild_layer(db.layers[l], idx_t1, ts, db.max_elapse, db.min_elapse);
+  bool changed = false;
+  for (int l = 0; l < db.n_layers; ++l) rebuild_layer(db.layers[l], idx_t1, ts, db.max_elapse, db.min_elapse, changed);
+  if (changed) db.tree_version++;
 }

@@ -40,6 +40,9 @@ struct C2gHostDB {
   double max_elapse, min_elapse;
   C2gLayerHost layers[C2G_NUM_Q_LEVELS_MAX];
   int n_scans;  // all_bevs_.size()
+  // bumped whenever the searchable contents of any tree change (keys popped from a buffer, keys moved between buckets):
+  // consecutive scans of the online loop between two bumps see the same trees (c2g_online_commit's runs)
+  unsigned long long tree_version = 0;
 };
 
 void c2g_hostdb_init(C2gHostDB &db, int n_layers, double max_elapse, double min_elapse);

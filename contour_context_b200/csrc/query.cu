@@ -63,7 +63,8 @@ __device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, c
 // across the warp's registers (slot j lives in lane j % 32, register j / 32) and updated by warp-cooperative insertion.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QK_WARPS * 32)
-knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, c2g_hint *__restrict__ hints) {
+knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, c2g_hint *__restrict__ hints,
+           unsigned long long *__restrict__ work) {
   __shared__ float merge_d[QK_WARPS][64];
   __shared__ int merge_i[QK_WARPS][64], merge_o[QK_WARPS][64];
   const int lane = threadIdx.x & 31;
@@ -88,6 +89,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
   int bi[2] = {-1, -1};
   int bo[2] = {0x7FFFFFFF, 0x7FFFFFFF};  // original flat index (bucket-major tree order) of every kept entry: tie order
   int count = 0;
+  int n_keys_eval = 0, n_boxes = 0;  // work counters (c2g_work_counters)
   const int K = Q.nnk;  // <= 64
   if (seq < Q.piv && ksum != 0.0f) {  // `q_keys[seq].sum() != 0` (contour_db.h:726); NaN keys search and find nothing
     // dist_ub (contour_db.h:733-749): bounds stored as float, products with double literals evaluated in double
@@ -138,6 +140,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
     auto scan_block = [&](int base, int end) {
       const int i = base + lane;
       const bool in = i < end;
+      n_keys_eval += end - base;
       float dist = 3.0e38f;
       int orig = 0x7FFFFFFF;
       if (in) {
@@ -215,6 +218,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
       const int beg = bk * T.cap_b, end = beg + T.bucket_cnt[bk];
       if (beg >= end) continue;
       const int b0 = bk * T.blkcap_b, nb = (T.bucket_cnt[bk] + 31) >> 5;
+      n_boxes += 2 * nb;
       // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
       float best = 3.0e38f;
       int best_j = 0x7FFFFFFF;
@@ -251,6 +255,10 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
       }
     }
     // slots >= K may hold spill-over entries; they are never emitted
+    if (work && lane == 0) {
+      atomicAdd(work + 0, (unsigned long long) n_keys_eval);
+      atomicAdd(work + 1, (unsigned long long) n_boxes);
+    }
   }
   const int level8 = level;
   for (int j = lane; j < Q.nnk; j += 32) {
@@ -995,13 +1003,15 @@ __device__ __forceinline__ bool gmm_pair_selected(double qx, double qy, float qx
 // partial cost); the partial costs are added in warp order, so the result does not depend on scheduling.
 __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells, int src_slot, int tgt_slot, const double T[4], int lane,
                                 int warp, int n_warps, uint32_t *queue /* 64 words of shared memory owned by this warp */,
-                                double *partial /* n_warps doubles of shared memory */) {
+                                double *partial /* n_warps doubles of shared memory */, unsigned long long *work) {
   const double theta = atan2(T[1], T[0]);
   const double c = cos(theta), s = sin(theta);
   const c2g_ell *se_all = ells + (size_t) src_slot * C2G_VIEW_CAP, *te_all = ells + (size_t) tgt_slot * C2G_VIEW_CAP;
   double cost = 0.0;
   int qn = 0;
+  long long n_tests = 0, n_terms = 0;
   auto eval_queued = [&](int cnt) {
+    n_terms += cnt;
     if (lane < cnt) {
       const uint32_t pr = queue[lane];
       const c2g_ell a = se_all[pr >> 16], b = te_all[pr & 0xFFFFu];
@@ -1030,6 +1040,7 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells,
       b.mx = b.my = 1.0e30f;
       b.maj = 0.0f;
       if (ti < nt) b = te_all[to + ti];
+      n_tests += (long long) min(32, nt - t0) * ((ns - warp + n_warps - 1) / n_warps);
       for (int si = warp; si < ns; si += n_warps) {
         const c2g_ell a = se_all[so + si];  // warp-wide broadcast
         const double amx = (double) a.mx, amy = (double) a.my;
@@ -1054,6 +1065,10 @@ __device__ double gmm_init_corr(const c2g_scan_head *heads, const c2g_ell *ells,
   }
   eval_queued(qn);
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+  if (work && lane == 0) {
+    atomicAdd(work + 2, (unsigned long long) n_tests);
+    atomicAdd(work + 3, (unsigned long long) n_terms);
+  }
   if (lane == 0) partial[warp] = cost;
   __syncthreads();
   cost = partial[0];
@@ -1259,7 +1274,7 @@ finish_replay_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__
 constexpr int CORR_WARPS = 4;  // warps per pose: the long poses (50 x 50 ellipse pairs per level) set the kernel's makespan
 __global__ void __launch_bounds__(CORR_WARPS * 32)
 finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, float lb_correlation,
-                   const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand) {
+                   const FinHead *__restrict__ fin_head, FinCand *__restrict__ fin_cand, unsigned long long *__restrict__ work) {
   __shared__ uint32_t queue[CORR_WARPS][64];
   __shared__ double partial[CORR_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1269,7 +1284,7 @@ finish_corr_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__res
   FinCand &fc = fin_cand[(size_t) q * C2G_MAX_CAND + ci];
   if (!fc.pass) return;
   const double T[4] = {fc.T[0], fc.T[1], fc.T[2], fc.T[3]};
-  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane, warp, CORR_WARPS, queue[warp], partial);
+  const double corr = gmm_init_corr(heads, ells, fc.gidx, first_slot + q, T, lane, warp, CORR_WARPS, queue[warp], partial, work);
   if (threadIdx.x == 0) {
     fc.corr_init = (float) corr;
     fc.alive = (fc.corr_init < lb_correlation) ? 0 : 1;
@@ -1398,7 +1413,8 @@ int launch_finish(c2g_ctx *ctx, int first_slot, int q0, int B, const QueryParams
   finish_replay_kernel<<<B, FIN_WARPS * 32, smem, st>>>(ctx->d_heads, ctx->d_views, first_slot, q0, B, Q, hints, scores, fh, fcd);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 4);
-  finish_corr_kernel<<<B * C2G_MAX_CAND, CORR_WARPS * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, Q.lb.correlation, fh, fcd);
+  finish_corr_kernel<<<B * C2G_MAX_CAND, CORR_WARPS * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, Q.lb.correlation, fh, fcd,
+                                                                   ctx->count_work ? ctx->d_work : nullptr);
   C2G_CUDA_TRY(cudaGetLastError());
   C2G_QPROF(ctx, 5);
   finish_output_kernel<<<(B + 3) / 4, 128, 0, st>>>(q0, B, fh, fcd, ctx->d_results);
@@ -1488,6 +1504,8 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     }
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = (k == 0) ? -1000.0f : 1000.0f;
   }
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long) * C2G_WORK_N));
+  C2G_CUDA_TRY(cudaMemset(ctx->d_work, 0, sizeof(unsigned long long) * C2G_WORK_N));
   ctx->patch_cap = 1 << 20;
   C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ctx->patch_cap, cudaHostAllocDefault));
   C2G_CUDA_TRY(cudaMalloc(&ctx->d_patch, ctx->patch_cap));
@@ -1501,6 +1519,7 @@ void c2g_query_free(c2g_ctx *ctx) {
   cudaFree(ctx->d_results);
   cudaFree(ctx->d_survivors);
   cudaFree(ctx->d_nsurv);
+  cudaFree(ctx->d_work);
   for (int i = 0; i < C2G_QUERY_STREAMS; ++i) {
     if (ctx->qstream[i]) cudaStreamDestroy(ctx->qstream[i]);
     if (ctx->ev_qjoin[i]) cudaEventDestroy(ctx->ev_qjoin[i]);
@@ -1675,6 +1694,7 @@ extern "C" {
 int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const int *gidx_host, const signed char *seq_host,
                      const unsigned char *bucket_host, const float *bucket_ranges_host) {
   if (!ctx || ll < 0 || ll >= ctx->db.n_q_levels || n < 0 || !bucket_ranges_host) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   C2gLayerTable &t = ctx->layers[ll];
   if (n > 0 && (!keys_host || !gidx_host || !seq_host || !bucket_host)) return C2G_ERR_ARG;
   std::vector<C2gKeyRec> trees[C2G_NUM_BUCKETS];
@@ -1700,28 +1720,34 @@ int c2g_db_set_layer(c2g_ctx *ctx, int ll, int n, const float *keys_host, const 
   return 0;
 }
 
-int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub) {
-  if (!ctx || !lb || !ub || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+}  // extern "C"
+
+static bool thresholds_ok(const c2g_score_ensemble *lb, const c2g_score_ensemble *ub) {
   // CHECKs of the CandidateManager constructor (contour_db.h:365-367)
-  if (!(lb->i_ovlp_sum < ub->i_ovlp_sum && lb->i_ovlp_max_one < ub->i_ovlp_max_one && lb->i_in_ang_rng < ub->i_in_ang_rng &&
-        lb->i_indiv_sim < ub->i_indiv_sim && lb->i_orie_sim < ub->i_orie_sim && lb->correlation < ub->correlation &&
-        lb->area_perc < ub->area_perc && lb->neg_est_dist < ub->neg_est_dist))
-    return C2G_ERR_ARG;
-  {
-    // the online loop (small B) mirrors the trees in tree order (cheap appends); batched queries kd-block the buckets once
-    const int want_kd = B >= 32;
-    if (ctx->db_dirty || (want_kd && ctx->db_not_kd)) {
-      int rc = c2g_db_sync_mode(ctx, want_kd);
-      if (rc) return rc;
-      ctx->db_dirty = 0;
-      ctx->db_not_kd = want_kd ? 0 : 1;
-    }
-  }
-  QueryParams Q;
-  build_query_params(ctx, lb, Q);
-  // The batch is cut into sub-batches that run the whole kernel chain on their own streams: most kernels of the chain are
-  // latency-bound (sequential solver / replay logic) and leave issue slots idle that the kernels of the other sub-batch
-  // fill.  C2G_QUERY_SPLIT=1 (or an active c2g_query_profile) keeps everything on the context's stream.
+  return lb->i_ovlp_sum < ub->i_ovlp_sum && lb->i_ovlp_max_one < ub->i_ovlp_max_one && lb->i_in_ang_rng < ub->i_in_ang_rng &&
+         lb->i_indiv_sim < ub->i_indiv_sim && lb->i_orie_sim < ub->i_orie_sim && lb->correlation < ub->correlation &&
+         lb->area_perc < ub->area_perc && lb->neg_est_dist < ub->neg_est_dist;
+}
+
+// kNN of queries [q0, q0 + Bs) of the batch against the mirror AS IT IS NOW on `st` (the table sizes and bucket boundaries
+// travel by value in the launch parameters, so a later patch of the mirror does not affect this launch)
+static int launch_knn(c2g_ctx *ctx, int first_slot, int q0, int Bs, const QueryParams &Q, cudaStream_t st) {
+  const int n_keys = Bs * Q.n_q_levels * C2G_MAX_PIV;
+  if (n_keys <= 0) return 0;
+  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ctx->d_hints,
+                                                                          ctx->count_work ? ctx->d_work : nullptr);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+// The kernel chain of ContourDB::queryRangedKNN for the B query scans in slots first_slot.. : (kNN ->) prefilter -> score ->
+// proposal replay -> GMM-L2 gate -> output -> refinement -> ranking.  with_knn == 0: the hints are already in ctx->d_hints
+// (the windowed online loop fills them run by run, c2g_online_commit).
+// The batch is cut into sub-batches that run the whole chain on their own streams: most kernels of the chain are
+// latency-bound (sequential solver / replay logic) and leave issue slots idle that the kernels of the other sub-batches
+// fill.  C2G_QUERY_SPLIT=1 (or an active c2g_query_profile) keeps everything on the context's stream.
+static int launch_query_chain(c2g_ctx *ctx, int first_slot, int B, const QueryParams &Q, int with_knn) {
   static const int split_env = getenv("C2G_QUERY_SPLIT") ? atoi(getenv("C2G_QUERY_SPLIT")) : 4;
   int n_sub = ctx->prof_on ? 1 : (split_env < 1 ? 1 : (split_env > C2G_QUERY_STREAMS ? C2G_QUERY_STREAMS : split_env));
   if (B < 2 * n_sub) n_sub = 1;
@@ -1732,10 +1758,11 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
     const int q0 = (int) ((long long) B * sb / n_sub), q1 = (int) ((long long) B * (sb + 1) / n_sub), Bs = q1 - q0;
     cudaStream_t st = n_sub > 1 ? ctx->qstream[sb] : ctx->stream;
     if (n_sub > 1) C2G_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_qfork, 0));
-    const int n_keys = Bs * Q.n_q_levels * C2G_MAX_PIV;
     C2G_QPROF(ctx, 0);
-    knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ctx->d_hints);
-    C2G_CUDA_TRY(cudaGetLastError());
+    if (with_knn) {
+      int rc = launch_knn(ctx, first_slot, q0, Bs, Q, st);
+      if (rc) return rc;
+    }
     C2G_QPROF(ctx, 1);
     const long long hid0 = (long long) q0 * per_q, n_hints = (long long) Bs * per_q;
     int *surv = ctx->d_survivors + hid0, *nsurv = ctx->d_nsurv + sb;
@@ -1764,7 +1791,7 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
     }
     C2G_CUDA_TRY(cudaGetLastError());
     C2G_QPROF(ctx, 3);
-    ctx->launches += 3;
+    ctx->launches += 2;
     int rc = launch_finish(ctx, first_slot, q0, Bs, Q, ctx->d_hints, ctx->d_scores, st);
     if (rc) return rc;
     if (n_sub > 1) {
@@ -1775,9 +1802,94 @@ int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensembl
   return 0;
 }
 
+extern "C" int c2g_query_async(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub) {
+  if (!ctx || !lb || !ub || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+  if (!thresholds_ok(lb, ub)) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
+  {
+    // the online loop (small B) mirrors the trees in tree order (cheap appends); batched queries kd-block the buckets once
+    const int want_kd = B >= 32;
+    if (ctx->db_dirty || (want_kd && ctx->db_not_kd)) {
+      int rc = c2g_db_sync_mode(ctx, want_kd);
+      if (rc) return rc;
+      ctx->db_dirty = 0;
+      ctx->db_not_kd = want_kd ? 0 : 1;
+    }
+  }
+  QueryParams Q;
+  build_query_params(ctx, lb, Q);
+  return launch_query_chain(ctx, first_slot, B, Q, 1);
+}
+
+// ---- windowed online loop -------------------------------------------------------------------------------------------
+// W iterations of BatchBinSpinner::spinOnce's database half (test/batch_bin_test.cpp:179,234,237):
+//     queryRangedKNN(scan_i)  ->  addScan(scan_i, ts_i)  ->  pushAndBalance(seed_i, ts_i)
+// The loop is serial only in the DB state, and with DYNAMIC_THRES=0 (CMakeLists.txt:21) the only part of a query that
+// depends on that state is WHICH keys sit in WHICH tree at that instant (contour_db.cpp:63-317, contour_db.h:102-143): the
+// descriptors were ingested in one batch (c2g_online_stage), their keys are on the host, so the LayerDB bookkeeping of all W
+// scans is replayed here on the host; the window is cut into RUNS of consecutive scans that see the same trees; each run's kNN
+// is launched against the mirror in exactly that state, then the mirror is patched (appended keys, occasionally a rewritten
+// bucket) for the next run - everything in stream order, nothing waits for the GPU.  The rest of the chain (hint cascade,
+// proposal replay, GMM-L2, refinement) does not read the trees and runs ONCE for the whole window.
+int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *keys_host, const double *ts_host, const int *seeds_host,
+                           const c2g_score_ensemble *lb, const c2g_score_ensemble *ub, c2g_query_result *results_host) {
+  if (!thresholds_ok(lb, ub)) return C2G_ERR_ARG;
+  C2gHostDB &db = *ctx->hostdb;
+  if (first_slot != db.n_scans) return C2G_ERR_STATE;  // gidx == all_bevs_.size() at the time of addScan
+  auto sync_mirror = [&]() -> int {
+    int rc = c2g_db_sync_mode(ctx, 0);  // tree order: appends are patches of a few hundred bytes
+    if (rc) return rc;
+    ctx->db_dirty = 0;
+    ctx->db_not_kd = 1;
+    return 0;
+  };
+  if (ctx->db_dirty) {
+    int rc = sync_mirror();
+    if (rc) return rc;
+  }
+  QueryParams Q;
+  build_query_params(ctx, lb, Q);
+  int run_begin = 0, n_runs = 0;
+  const size_t kstride = (size_t) C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
+  for (int i = 0; i < W; ++i) {
+    const unsigned long long v0 = db.tree_version;
+    const float *sk = keys_host + (size_t) i * kstride;
+    for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+      const int lev = ctx->db.q_levels[ll];
+      for (int seq = 0; seq < ctx->P.cfg.piv_firsts; ++seq)
+        c2g_hostdb_push(db, ll, sk + ((size_t) lev * C2G_MAX_PIV + seq) * C2G_KEY_DIM, ts_host[i], first_slot + i, seq);
+    }
+    db.n_scans++;
+    c2g_hostdb_push_and_balance(db, seeds_host[i], ts_host[i]);
+    if (db.tree_version != v0) {  // scans run_begin..i saw the trees as mirrored now; scan i + 1 sees the new ones
+      int rc = launch_knn(ctx, first_slot, run_begin, i + 1 - run_begin, Q, ctx->stream);
+      if (rc) return rc;
+      ++n_runs;
+      run_begin = i + 1;
+      rc = sync_mirror();
+      if (rc) return rc;
+      build_query_params(ctx, lb, Q);
+    }
+  }
+  if (run_begin < W) {
+    int rc = launch_knn(ctx, first_slot, run_begin, W - run_begin, Q, ctx->stream);
+    if (rc) return rc;
+    ++n_runs;
+  }
+  ctx->online_runs += n_runs;
+  int rc = launch_query_chain(ctx, first_slot, W, Q, 0);
+  if (rc) return rc;
+  if (results_host)
+    C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) W, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+extern "C" {
+
 int c2g_query(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
               c2g_query_result *results_host, c2g_hint *hints_host, c2g_pair_score *scores_host) {
-  if (!results_host) return C2G_ERR_ARG;
+  if (!ctx || !results_host) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   int rc = c2g_query_async(ctx, first_slot, B, lb, ub);
   if (rc) return rc;
   const size_t nh = (size_t) B * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
@@ -1799,17 +1911,19 @@ int c2g_query_buffers(c2g_ctx *ctx, void **results_dev, void **hints_dev, void *
 
 int c2g_query_export(c2g_ctx *ctx, int B, void *hints_dst_dev, void *scores_dst_dev, void *results_dst_host) {
   if (!ctx || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   const size_t nh = (size_t) B * ctx->db.n_q_levels * C2G_MAX_PIV * ctx->db.nnk;
   if (hints_dst_dev) C2G_CUDA_TRY(cudaMemcpyAsync(hints_dst_dev, ctx->d_hints, sizeof(c2g_hint) * nh, cudaMemcpyDeviceToDevice, ctx->stream));
   if (scores_dst_dev) C2G_CUDA_TRY(cudaMemcpyAsync(scores_dst_dev, ctx->d_scores, sizeof(c2g_pair_score) * nh, cudaMemcpyDeviceToDevice, ctx->stream));
   if (results_dst_host)
-    C2G_CUDA_TRY(cudaMemcpyAsync(results_dst_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDeviceToHost, ctx->stream));
+    C2G_CUDA_TRY(cudaMemcpyAsync(results_dst_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) B, cudaMemcpyDefault, ctx->stream));
   return 0;
 }
 
 int c2g_finish_from_scores(c2g_ctx *ctx, int first_slot, int B, const c2g_score_ensemble *lb, const void *hints_dev,
                            const void *scores_dev, c2g_query_result *results_host) {
-  if (!ctx || !lb || !hints_dev || !scores_dev || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
+  if (!ctx || !lb || !hints_dev || !scores_dev || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
   QueryParams Q;
   build_query_params(ctx, lb, Q);
   int rc = launch_finish(ctx, first_slot, 0, B, Q, (const c2g_hint *) hints_dev, (const c2g_pair_score *) scores_dev, ctx->stream);

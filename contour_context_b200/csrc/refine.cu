@@ -39,6 +39,7 @@ struct Prob {
   const uint32_t *pairs;   // this warp's share of the pre-selected pairs: (src view index << 16) | tgt view index
   double (*red)[4];        // [RF_WARPS][4] shared-memory slots of the block reduction
   int n_pairs, exp_mode, lane, warp, n_warps;
+  int *n_eval;             // evaluations so far (work counter, per thread)
 };
 
 // GMMPair::operator() (correlation.h:125-152) and its gradient; all threads of the CTA call, all get the same result
@@ -52,6 +53,7 @@ struct Prob {
 __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
   const double c = cos(p[2]), s = sin(p[2]), ns = -s;
   const double x = p[0], y = p[1];
+  ++*P.n_eval;
   double fa = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
   for (int i = P.lane; i < P.n_pairs; i += 32) {
     const uint32_t pr = P.pairs[i];
@@ -559,7 +561,8 @@ __device__ RfOut rf_minimize(const Prob &P, const double x0[3]) {
 
 __global__ void __launch_bounds__(RF_MAX_WARPS * 32, 5)
 refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, int max_fine_opt,
-              int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results) {
+              int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results,
+              unsigned long long *__restrict__ work) {
   __shared__ double red[RF_MAX_WARPS][4];
   const int n_warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -580,10 +583,12 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   // pre-selection at T_init (correlation.h:84-96): |T_init * mu_s - mu_t| < 3 (sqrt(eig_s) + sqrt(eig_t)).  Warp w takes the
   // source ellipses w, w + RF_WARPS, ... of every level and keeps its own pair list; lanes hold 32 target ellipses of the
   // level in registers while the sources stream by.
-  int n_pairs = 0, overflow = 0;
+  int n_pairs = 0, overflow = 0, n_eval = 0;
+  long long n_tests = 0;
   for (int li = 0; li < C2G_NUM_BIN_LAYERS; ++li) {
     const int lev = li + 1;
     const int ns = heads[src].n_ell[li], nt = heads[tgt].n_ell[li];
+    n_tests += (long long) nt * ((ns - warp + n_warps - 1) / n_warps);
     const int so = heads[src].view_off[lev], to = heads[tgt].view_off[lev];
     if (nt <= 32) {
       double bx = 0.0, by = 0.0;
@@ -656,8 +661,14 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
   P.n_pairs = n_pairs;
   P.exp_mode = exp_mode;
   P.lane = lane;
+  P.n_eval = &n_eval;
   const double p0[3] = {T[2], T[3], atan2(T[1], T[0])};
   const RfOut o = rf_minimize(P, p0);
+  if (work && lane == 0) {
+    atomicAdd(work + 4, (unsigned long long) n_tests);
+    atomicAdd(work + 5, (unsigned long long) n_pairs * (unsigned long long) n_eval);
+    if (warp == 0) atomicAdd(work + 6, (unsigned long long) n_eval);
+  }
   if (threadIdx.x == 0) {
     const double corr = -o.final_cost / sqrt(heads[src].gmm_auto_corr * heads[tgt].gmm_auto_corr);
     C.corr_fine = (float) corr;  // CandidateAnchorProp::correlation_ is a float (contour_db.h:270)
@@ -720,7 +731,7 @@ int c2g_launch_refine(c2g_ctx *ctx, int first_slot, int q0, int B, cudaStream_t 
   if (mfo <= 0) return 0;
   static const int rf_warps = getenv("C2G_REFINE_WARPS") ? max(1, min(RF_MAX_WARPS, atoi(getenv("C2G_REFINE_WARPS")))) : RF_WARPS;
   refine_kernel<<<B * mfo, rf_warps * 32, 0, st>>>(ctx->d_heads, ctx->d_ells, first_slot, q0, B, mfo, ctx->P.exp_mode, ctx->d_pair_scratch, ctx->pair_cap,
-                                                   ctx->d_results);
+                                                   ctx->d_results, ctx->count_work ? ctx->d_work : nullptr);
   C2G_CUDA_TRY(cudaGetLastError());
   if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[7], st);
   rank_kernel<<<(B + 127) / 128, 128, 0, st>>>(q0, B, mfo, ctx->d_results);

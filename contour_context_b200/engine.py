@@ -97,6 +97,43 @@ class Engine:
     def db_push_and_balance(self, seed: int, ts: float):
         capi.check(capi.lib().c2g_db_push_and_balance(self.h, seed, float(ts)), "c2g_db_push_and_balance")
 
+    # ---- windowed online loop (query -> addScan -> pushAndBalance for W consecutive scans) ---------------------------------
+    def online_stage(self, pts, offsets, int_ids=None, on_device: bool = None):
+        """Ingest the next window into slots db_size.. and start reading its keys back (asynchronous)."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        if on_device is None:
+            on_device = bool(getattr(pts, "is_cuda", False))
+        ids = None if int_ids is None else np.ascontiguousarray(int_ids, np.int32)
+        capi.check(capi.lib().c2g_online_stage(self.h, capi.ptr(pts), capi.ptr(offsets), len(offsets) - 1, int(on_device),
+                                               capi.ptr(ids)), "c2g_online_stage")
+
+    def online_commit(self, ts, seeds, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble, results_out):
+        """Bookkeeping + queries of the oldest staged window; results_out (numpy QUERY_RESULT_DTYPE array or pinned torch uint8
+        tensor) is filled asynchronously: call sync() before reading it.  ts / seeds must stay alive only for the call."""
+        ts = np.ascontiguousarray(ts, np.float64)
+        seeds = np.ascontiguousarray(seeds, np.int32)
+        capi.check(capi.lib().c2g_online_commit(self.h, capi.ptr(ts), capi.ptr(seeds), C.byref(lb), C.byref(ub),
+                                                capi.ptr(results_out)), "c2g_online_commit")
+
+    def online_window(self, pts, offsets, ts, seeds, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble, int_ids=None, on_device: bool = None):
+        """W iterations of query -> addScan -> pushAndBalance, results identical to the scan-by-scan calls."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        W = len(offsets) - 1
+        if on_device is None:
+            on_device = bool(getattr(pts, "is_cuda", False))
+        ids = None if int_ids is None else np.ascontiguousarray(int_ids, np.int32)
+        ts = np.ascontiguousarray(ts, np.float64)
+        seeds = np.ascontiguousarray(seeds, np.int32)
+        assert len(ts) == W and len(seeds) == W
+        res = np.zeros(W, D.QUERY_RESULT_DTYPE)
+        capi.check(capi.lib().c2g_online_window(self.h, capi.ptr(pts), capi.ptr(offsets), W, int(on_device), capi.ptr(ids),
+                                                capi.ptr(ts), capi.ptr(seeds), C.byref(lb), C.byref(ub), capi.ptr(res)),
+                   "c2g_online_window")
+        return res
+
+    def online_runs(self) -> int:
+        return int(capi.lib().c2g_online_runs(self.h))
+
     def db_size(self) -> int:
         return int(capi.lib().c2g_db_size(self.h))
 
@@ -171,6 +208,15 @@ class Engine:
         ms = np.zeros(8, np.float32) if read else None
         capi.check(capi.lib().c2g_query_profile(self.h, int(enable), capi.ptr(ms)), "c2g_query_profile")
         return dict(zip(self.QUERY_KERNELS, (float(v) for v in ms))) if read else None
+
+    WORK_COUNTERS = ("knn_keys_evaluated", "knn_boxes_tested", "gate_preselect_tests", "gate_terms", "refine_preselect_tests",
+                     "refine_terms", "refine_evaluations", "spare")
+
+    def work_counters(self, enable: bool = True) -> dict:
+        """Read + clear the query kernels' work counters, then enable / disable counting (c2g_work_counters)."""
+        out = np.zeros(8, np.uint64)
+        capi.check(capi.lib().c2g_work_counters(self.h, int(enable), capi.ptr(out)), "c2g_work_counters")
+        return dict(zip(self.WORK_COUNTERS, (int(v) for v in out)))
 
     def exp_mode(self) -> int:
         """Which glibc exp() variant the device reproduces (0 = none matched the host libm: libdevice exp, keys may differ by 1 ulp)."""

@@ -83,6 +83,30 @@ int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host)
 /* Replaces ContourDB::pushAndBalance (include/cont2/contour_db.h:827-843, LayerDB::rebuild src/cont2/contour_db.cpp:63-317). */
 int c2g_db_push_and_balance(c2g_ctx *ctx, int seed, double ts);
 int c2g_db_size(c2g_ctx *ctx);
+
+/* Windowed online loop: replaces W consecutive iterations of BatchBinSpinner::spinOnce's database half
+ * (test/batch_bin_test.cpp:179,234,237), for i = 0 .. W-1 in order:
+ *     ContourDB::queryRangedKNN(scan_i)   include/cont2/contour_db.h:698-811
+ *     ContourDB::addScan(scan_i, ts[i])   include/cont2/contour_db.h:814-824
+ *     ContourDB::pushAndBalance(seeds[i], ts[i])   include/cont2/contour_db.h:827-843
+ * with results identical to the scan-by-scan calls (query i sees exactly the trees that exist after scans < i were added
+ * and balanced): the W scans are ingested in one batch into slots db_size .. db_size + W - 1, the host replays the LayerDB
+ * bookkeeping of the window from their keys, the kNN runs once per run of scans that see identical trees (the device mirror is
+ * patched between runs, in stream order), and the rest of the query chain runs once for the window.
+ *   c2g_online_stage   ingests the next window (arguments as c2g_ingest) and starts the read-back of its keys; asynchronous.
+ *                      At most two windows may be staged: stage window k+1, then commit window k, and the host -> device copy
+ *                      of k+1 overlaps the bookkeeping and the query kernels of k.
+ *   c2g_online_commit  oldest staged window: bookkeeping + queries; results_host[W] (pinned memory recommended) is filled
+ *                      asynchronously: valid after c2g_sync.
+ *   c2g_online_window  stage + commit + sync in one call.
+ *   c2g_online_runs    kNN launches issued by the windowed loop so far (runs of scans that saw identical trees). */
+int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host);
+int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb,
+                      const c2g_score_ensemble *ub, c2g_query_result *results_host);
+int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host,
+                      const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
+                      c2g_query_result *results_host);
+long long c2g_online_runs(c2g_ctx *ctx);
 /* Upload the host-side tree contents to the device tables if they changed (c2g_query* call it implicitly). */
 int c2g_db_sync(c2g_ctx *ctx);
 /* Introspection for parity tests: bucket boundaries [7], tree sizes [6], buffer sizes [6]; one bucket's tree in order. */
@@ -142,6 +166,13 @@ long long c2g_launch_count(c2g_ctx *ctx);
  * on the context's stream.  When ms_out != NULL the durations (ms) of the last profiled query are written first:
  * ms_out[8] = knn, prefilter, score, proposal replay, GMM-L2 gate, output, refinement, ranking.  Synchronises the stream. */
 int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out);
+
+/* Measurement aid (no reference counterpart): work actually done by the query kernels since the last call, for the roofline
+ * entries of bench.py.  out_host[8] (may be NULL) = kNN keys distance-evaluated, kNN block boxes tested, GMM-L2 gate pre-selection
+ * tests (correlation.h:85-96), GMM-L2 gate Gaussian terms (:138-149), refinement pre-selection tests, refinement Gaussian terms
+ * (pairs x cost+gradient evaluations), refinement evaluations, spare.  Reads and clears the counters, then enables / disables
+ * counting (one atomic per warp while enabled).  Synchronises the stream. */
+int c2g_work_counters(c2g_ctx *ctx, int enable, unsigned long long *out_host);
 
 /* Host-side replay of libstdc++ std::sort used by the kernels (tests only): sorts `n` packed (key << 16 | index)
  * words with comparator key-descending (desc != 0) or key-ascending. */

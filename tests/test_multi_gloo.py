@@ -1,7 +1,7 @@
-"""CPU-only, world_size 2 over gloo: the N > 1 host logic of the query path — query sharding and the all-gather of
-fixed-stride per-pair score records — reassembles exactly the table a single rank would have produced.  The records come
-from the oracle (each rank scores its own shard of the query scans), so this also checks that sharding by query leaves
-every per-query result unchanged (DYNAMIC_THRES=0 makes hint checks independent, CMakeLists.txt:21)."""
+"""CPU-only, world_size 2 over gloo: the N > 1 host logic of the query path — query sharding, the ONE all-gather of the
+per-query result records (c2g_query_result) and the foreign-block verification bench.py runs on hardware.  The records come
+from the oracle (each rank queries its own shard of the query scans against its replica), so this also checks that sharding
+by query leaves every per-query result unchanged (DYNAMIC_THRES=0 makes hint checks independent, CMakeLists.txt:21)."""
 import os
 import socket
 import sys
@@ -45,30 +45,27 @@ def _worker(rank, world, port, n_q, out_dir):
     for k in range(12):
         db.push_and_balance(k, 1000.0 + k)
     qpts, qoff = make_batch([500 + i % 4 for i in range(n_q)], [3 + i // 4 for i in range(n_q)], n_pts, noise_seed=5)
-    per_q = dbc.n_q_levels * D.MAX_PIV * dbc.nnk
 
-    def records(qi):
-        res, hints, scores = db.query(c2o.Scan(cfg, 100 + qi).ingest(qpts[qoff[qi]:qoff[qi + 1]]), lb, ub)
-        h = np.zeros(per_q, D.HINT_DTYPE)
-        h["cand_gidx"] = -1
-        s = np.zeros(per_q, D.PAIR_SCORE_DTYPE)
-        h[:len(hints)] = hints
-        s[:len(scores)] = scores
-        return h, s, res
+    def record(qi):
+        res, _, _ = db.query(c2o.Scan(cfg, 100 + qi).ingest(qpts[qoff[qi]:qoff[qi + 1]]), lb, ub)
+        return res
 
     beg, end = multi.shard_range(n_q, world, rank)
     assert end - beg == n_q // world
-    loc = [records(q) for q in range(beg, end)]
-    h_loc = torch.from_numpy(np.concatenate([x[0] for x in loc]).view(np.uint8).copy())
-    s_loc = torch.from_numpy(np.concatenate([x[1] for x in loc]).view(np.uint8).copy())
-    h_all = multi.split_gathered(multi.all_gather_records(h_loc, world), world, D.HINT_DTYPE)
-    s_all = multi.split_gathered(multi.all_gather_records(s_loc, world), world, D.PAIR_SCORE_DTYPE)
-    # every rank now holds the global table; compare with a single-rank run of ALL queries
-    full = [records(q) for q in range(n_q)]
-    h_full = np.concatenate([x[0] for x in full])
-    s_full = np.concatenate([x[1] for x in full])
-    ok = h_all.reshape(-1).tobytes() == h_full.tobytes() and s_all.reshape(-1).tobytes() == s_full.tobytes()
-    n_pass = int((s_full["passed"] == 1).sum())
+    loc = np.array([record(q) for q in range(beg, end)], D.QUERY_RESULT_DTYPE)
+    r_loc = torch.from_numpy(loc.view(np.uint8).reshape(-1).copy())
+    r_all = multi.split_gathered(multi.all_gather_records(r_loc, world), world, D.QUERY_RESULT_DTYPE)
+    # every rank now holds the outcome of the whole batch: (1) it equals a single-rank run of ALL queries, (2) the block of the
+    # other rank equals those queries recomputed on this rank's replica (the check bench.py runs under torch.distributed.run)
+    full = np.array([record(q) for q in range(n_q)], D.QUERY_RESULT_DTYPE)
+    ok = r_all.reshape(-1).tobytes() == full.tobytes()
+    other = (rank + 1) % world
+    ob, oe = multi.shard_range(n_q, world, other)
+    ok = ok and multi.verify_foreign_block(r_all, other, full[ob:oe]) == 0
+    tampered = r_all.copy()
+    tampered[other][0]["n_cand"] += 1
+    ok = ok and multi.verify_foreign_block(tampered, other, full[ob:oe]) == 1
+    n_pass = len(multi.loop_closures(r_all.reshape(-1)))
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write(f"{int(ok)} {n_pass}\n")
     dist.barrier()
@@ -87,7 +84,7 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_two_rank_gather_reassembles_single_rank_table(oracle, tmp_path):
+def test_two_rank_gather_of_results_and_foreign_block_check(oracle, tmp_path):
     import torch.multiprocessing as mp
 
     port = _free_port()
