@@ -35,8 +35,9 @@ class ContourDB {
  public:
   ContourDB(const ContourDBConfig &config);
 
-  // reference contour_db.h:698-811. NOTE: the Ceres refinement of fineOptimize is not part of this build:
-  // the returned correlation / transform are the initial GMM-L2 correlation and the constellation transform.
+  // reference contour_db.h:698-811.  fineOptimize's L-BFGS refinement runs on the device (csrc/refine.cu): the returned
+  // correlation / transform are anch_props_[0].correlation_ / T_delta_ after the refinement (contour_db.h:626-627,642-643),
+  // i.e. c2g_cand::corr_fine / T_fine.  Stage timers "KNN search", "Constell", "L2 opt" are booked in `stp` like the reference.
   void queryRangedKNN(const std::shared_ptr<const ContourManager> &q_ptr, const CandidateScoreEnsemble &thres_lb,
                       const CandidateScoreEnsemble &thres_ub, std::vector<std::shared_ptr<const ContourManager>> &cand_ptrs,
                       std::vector<double> &cand_corr, std::vector<Eigen::Isometry2d> &cand_tf) const;

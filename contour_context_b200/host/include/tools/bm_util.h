@@ -44,6 +44,15 @@ class SequentialTimeProfiler {
     e.sumsq += dt * dt;
     clk_.tic();
   }
+  // a duration measured elsewhere (CUDA events of the kernels that replace a stage), booked under the reference's stage name
+  void recordSeconds(const std::string &name, double dt) {
+    Entry &e = logs_[name];
+    if (e.count == 0) e.order = (int) logs_.size();
+    e.count++;
+    e.sum += dt;
+    e.sumsq += dt * dt;
+    clk_.tic();
+  }
   void lap() { loops_++; }
   void printScreen() const {
     std::vector<std::pair<std::string, Entry>> v(logs_.begin(), logs_.end());

@@ -26,8 +26,22 @@ struct Runtime {
   int n_staging = 64;          // slots [capacity - n_staging, capacity) hold scans that are not (yet) in the DB
   std::vector<int> free_slots;
 
+  // One context per process: every ContourManager / ContourDB of the process must carry the SAME configuration (the reference
+  // keeps a config per object; two different ones in one process - a KITTI and a MulRan manager, say - cannot share the
+  // device context, so that is a CHECK failure instead of silently running the second one with the first one's parameters).
+  static void checkSame(const void *a, const void *b, size_t n, const char *what) {
+    if (std::memcmp(a, b, n) != 0) {
+      std::fprintf(stderr, "CHECK failed: a second, different %s reached the GPU runtime (one configuration per process)\n", what);
+      std::abort();
+    }
+  }
   void setCm(const ContourManagerConfig &c) {
-    if (have_cm) return;
+    const c2g_cm_config prev = cm;
+    fillCm(c);
+    if (have_cm) checkSame(&prev, &cm, sizeof(cm), "ContourManagerConfig");
+    have_cm = true;
+  }
+  void fillCm(const ContourManagerConfig &c) {
     std::memset(&cm, 0, sizeof(cm));
     if (c.lv_grads_.size() != C2G_NLEV) {
       std::fprintf(stderr, "CHECK failed: lv_grads_ must have %d levels\n", C2G_NLEV);
@@ -50,10 +64,14 @@ struct Runtime {
     cm.min_cell_cov = vs.min_cell_cov;
     cm.point_sigma = vs.point_sigma;
     cm.com_bias_thres = vs.com_bias_thres;
-    have_cm = true;
   }
   void setDb(const ContourDBConfig &c) {
-    if (have_db) return;
+    const c2g_db_config prev = db;
+    fillDb(c);
+    if (have_db) checkSame(&prev, &db, sizeof(db), "ContourDBConfig");
+    have_db = true;
+  }
+  void fillDb(const ContourDBConfig &c) {
     std::memset(&db, 0, sizeof(db));
     db.nnk = c.nnk_;
     db.max_fine_opt = c.max_fine_opt_;
@@ -67,7 +85,6 @@ struct Runtime {
     db.cont_sim.tp_rcom = c.cont_sim_cfg_.tp_rcom;
     db.max_elapse = c.tb_cfg_.max_elapse_;
     db.min_elapse = c.tb_cfg_.min_elapse_;
-    have_db = true;
   }
   void ensure() {
     if (ctx) return;
@@ -75,8 +92,8 @@ struct Runtime {
       std::fprintf(stderr, "CHECK failed: no ContourManagerConfig seen before the first GPU call\n");
       std::abort();
     }
-    if (!have_db) {  // a ContourManager used without any ContourDB: defaults of config/batch_bin_test_config.yaml
-      ContourDBConfig d;
+    if (!have_db) {  // a ContourManager used before any ContourDB exists: defaults of config/batch_bin_test_config.yaml;
+      ContourDBConfig d;  // a ContourDB created later must then carry exactly these (checkSame)
       d.q_levels_ = {1, 2, 3};
       setDb(d);
     }
@@ -267,9 +284,24 @@ void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_pt
   };
   const c2g_score_ensemble lb = pack(thres_lb), ub = pack(thres_ub);
   c2g_query_result res;
-  stp.start();
+  // the reference's three stage timers (contour_db.h:729-787): the device times of the kernels that replace each stage
+  // (c2g_query_profile: knn | prefilter + score | proposal replay + GMM-L2 gate + output + refinement + ranking); the host
+  // overhead of the call (launches, result read-back) goes to "L2 opt", the stage that ends the query in the reference too
+  static bool prof_on = false;
+  if (!prof_on) {
+    C2G_CHECK(c2g_query_profile(runtime().ctx, 1, nullptr));
+    prof_on = true;
+  }
+  TicToc wall;
   C2G_CHECK(c2g_query(runtime().ctx, q_ptr->deviceSlot(), 1, &lb, &ub, &res, nullptr, nullptr));
-  stp.record("KNN search+Constell+L2 opt (GPU)");
+  const double t_wall = wall.toc();
+  float ms[8];
+  C2G_CHECK(c2g_query_profile(runtime().ctx, 1, ms));
+  const double t_knn = 1e-3 * ms[0], t_constell = 1e-3 * (ms[1] + ms[2]);
+  stp.recordSeconds("KNN search", t_knn);
+  stp.recordSeconds("Constell", t_constell);
+  stp.recordSeconds("L2 opt", t_wall - t_knn - t_constell > 0 ? t_wall - t_knn - t_constell : 0.0);
+  if (res.overflow) C2G_CHECK(C2G_ERR_CAPACITY);  // more candidate poses than C2G_MAX_CAND: the reference keeps them all
   if (res.n_cand > 0 && res.best >= 0) {  // ret_size = 1 (contour_db.h:639)
     const c2g_cand &c = res.cand[res.best];
     cand_ptrs.emplace_back(all_bevs_[c.cand_gidx]);
