@@ -1,19 +1,31 @@
 // bev_scatter.cu — K1: point cloud -> max-height BEV (ContourManager::makeBEV, include/cont2/contour_mng.h:505-556,
-// with hashPointToImage :448-463).
+// with hashPointToImage :448-463), handed to the contour kernel as what it consumes: one bit-plane per height level
+// (`bev > lv_grads[l]`, the cv::threshold of makeContourRecursiveHelper, src/cont2/contour_mng.cpp:283) and the compact,
+// raster-ordered list of the cells above the lowest threshold with their height and the winner's continuous coordinates
+// (bev_pixfs_, contour_mng.h:435,528-529) - the only cells contours, moments and keys ever read.
 //
-// B200 mapping: one persistent CTA per SM, one scan per CTA iteration.  The whole 150x150 BEV lives in shared memory as
+// B200 mapping: one persistent CTA per SM, scans handed out dynamically.  The whole 150x150 BEV lives in shared memory as
 // 64-bit cell keys (180 KB of the 227 KB carve-out), so the only HBM traffic is the streaming read of the points
-// (16 B/point, 128-bit ld.global.nc.L1::no_allocate, UNROLL independent loads in flight per thread) plus one coalesced
-// 180 KB write of the finished tile.  The reference's "if (bev < h) bev = h" with first-point-wins ties becomes a 64-bit
-// max over (orderable(h) << 32 | ~index); a plain shared-memory read filters the ~3/4 of the points that cannot raise
-// their cell any more before the atomic is issued (max is monotone, so a stale read can only cause a redundant atomic,
-// never a missed one).
+// (16 B/point, 128-bit ld.global.nc.L1::no_allocate, UNROLL independent loads in flight per thread) plus ~40 KB of output
+// per scan (round 1 wrote the 180 KB tile and the contour kernel read it back).  The reference's "if (bev < h) bev = h"
+// with first-point-wins ties becomes a 64-bit max over (orderable(h) << 32 | ~index); a plain shared-memory read filters
+// the points that cannot raise their cell any more before the atomic is issued (max is monotone, so a stale read can only
+// cause a redundant atomic, never a missed one).
+//
+// LOWFILTER (production): a point at or below the lowest threshold can never belong to a contour; all the path needs from
+// it is that its cell counts as occupied (bev_pixfs_.size()).  Such points (~2/3 of a scan: the ground) set one bit of a
+// 2.8 KB occupancy bitmap - a 32-bit read and, rarely, a native 32-bit atomicOr - instead of going through the 64-bit
+// compare-and-swap loop (there is no native 64-bit shared-memory max: ATOMS.CAST.SPIN.64), which was half of round 1's
+// instructions.  LOWFILTER = false keeps every point on the key path and additionally writes the full tile: the dense-image
+// getters (c2g_get_bev / c2g_get_tiles, ContourManager::getBevImage) and c2g_ingest_bev_only run that variant.
 #include "c2g_common.cuh"
 
 namespace {
 
 constexpr int K1_THREADS = 1024;
+constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_UNROLL = 8;
+constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   float4 r;
@@ -23,120 +35,235 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   return r;
 }
 
-// UNIT = true: reso_row == reso_col == 1.0f and the padded square is symmetric (the reference's only shipped setting,
-// config/batch_bin_test_config.yaml:33-37 "TODO: reso other than 1.0"): x / 1.0f == x exactly, |x| <= x_max_pad replaces the
-// two-sided test (and rejects NaN in the same compare), and the padded bounds already guarantee 0 <= row < n_row,
-// 0 <= col < n_col, so only the reference's `row > 0` test remains.  The K1 kernel is issue-bound, not HBM-bound, without
-// this diet (profiles/r1_ncu_full_summary.csv: 89 instructions per point, 54 % issue utilisation at 42 % DRAM).
-template <bool UNIT>
-__device__ __forceinline__ void scatter_point(const float4 pt, const uint32_t idx, const C2gIngestParams &P, c2g_cellkey *tile) {
+// What one point asks of the tile: `key` != 0: raise cell `cell` to `key`; `obit` != 0: mark bit `obit` of occupancy word `ow`.
+struct PointOp {
+  int cell, ow;
+  c2g_cellkey key;
+  uint32_t obit;
+};
+
+// hashPointToImage + the height of makeBEV.  UNIT = true: reso_row == reso_col == 1.0f and the padded square is symmetric (the
+// reference's only shipped setting, config/batch_bin_test_config.yaml:33-37 "TODO: reso other than 1.0"): x / 1.0f == x
+// exactly, |x| <= x_max_pad replaces the two-sided test (and rejects NaN in the same compare), and the padded bounds already
+// guarantee 0 <= row < n_row, 0 <= col < n_col, so only the reference's `row > 0` test remains (contour_mng.h:515).
+// Branch-free: a rejected point yields key == 0 (never wins a max) and obit == 0.
+template <bool UNIT, bool LOWFILTER>
+__device__ __forceinline__ PointOp point_op(const float4 pt, const uint32_t idx, const C2gIngestParams &P, const float lv_min, const int wpr) {
   const float x = pt.x, y = pt.y;
+  bool ok;
   int row, col;
   if (UNIT) {
-    if (!(fabsf(x) <= P.x_max_pad) || !(fabsf(y) <= P.y_max_pad)) return;
-    if (__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq) return;
+    ok = (fabsf(x) <= P.x_max_pad) && (fabsf(y) <= P.y_max_pad);
+    ok = ok && !(__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq);
     row = __float2int_rd(x) + P.half_row;
     col = __float2int_rd(y) + P.half_col;
-    if (row <= 0) return;  // `rc.first > 0` (contour_mng.h:515)
+    ok = ok && row > 0;  // `rc.first > 0` (contour_mng.h:515)
   } else {
-    // hashPointToImage: reject outside the padded square or inside the blind radius (NaN x/y are dropped)
-    if (x < P.x_min_pad || x > P.x_max_pad || y < P.y_min_pad || y > P.y_max_pad) return;
-    if (__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq) return;
-    if (!(x == x) || !(y == y)) return;
-    row = (int) floorf(__fdiv_rn(x, P.cfg.reso_row)) + P.half_row;
-    col = (int) floorf(__fdiv_rn(y, P.cfg.reso_col)) + P.half_col;
-    if (row <= 0 || row >= P.cfg.n_row || col < 0 || col >= P.cfg.n_col) return;
+    // reject outside the padded square or inside the blind radius; NaN x / y fail `==` and are dropped
+    ok = !(x < P.x_min_pad || x > P.x_max_pad || y < P.y_min_pad || y > P.y_max_pad) && (x == x) && (y == y);
+    ok = ok && !(__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq);
+    row = ok ? (int) floorf(__fdiv_rn(x, P.cfg.reso_row)) + P.half_row : 0;
+    col = ok ? (int) floorf(__fdiv_rn(y, P.cfg.reso_col)) + P.half_col : 0;
+    ok = ok && row > 0 && row < P.cfg.n_row && col >= 0 && col < P.cfg.n_col;
   }
   const float h = __fadd_rn(P.cfg.lidar_height, pt.z);
-  if (!(h > -1000.0f)) return;  // bev_ starts at -1000 and only strictly higher points are stored
-  const c2g_cellkey key = ((c2g_cellkey) c2g_orderable(h) << 32) | (c2g_cellkey) (0xFFFFFFFFu - idx);
-  c2g_cellkey *cell = tile + row * P.cfg.n_col + col;
-  if (key > *(volatile c2g_cellkey *) cell) atomicMax(cell, key);
+  ok = ok && (h > -1000.0f);  // bev_ starts at -1000 and only strictly higher points are stored (NaN z: never)
+  const bool hi = ok && (!LOWFILTER || h > lv_min);
+  const bool lo = ok && !hi;
+  PointOp op;
+  op.cell = hi ? row * P.cfg.n_col + col : 0;
+  op.key = hi ? (((c2g_cellkey) c2g_orderable(h) << 32) | (c2g_cellkey) (0xFFFFFFFFu - idx)) : 0ull;
+  op.ow = lo ? row * wpr + (col >> 5) : 0;
+  op.obit = lo ? (1u << (col & 31)) : 0u;
+  return op;
 }
 
-// Branch-free first half of scatter_point<true>: cell and key of a point, key 0 (never wins a max) for a rejected point.
-// Same tests in the same float arithmetic; a NaN coordinate fails the first comparison exactly like in the branchy form.
-__device__ __forceinline__ void point_key_unit(const float4 pt, const uint32_t idx, const C2gIngestParams &P, int &cell, c2g_cellkey &key) {
-  const float x = pt.x, y = pt.y;
-  bool ok = (fabsf(x) <= P.x_max_pad) && (fabsf(y) <= P.y_max_pad);
-  ok = ok && !(__fadd_rn(__fmul_rn(y, y), __fmul_rn(x, x)) < P.cfg.blind_sq);
-  const int row = __float2int_rd(x) + P.half_row, col = __float2int_rd(y) + P.half_col;
-  ok = ok && row > 0;  // `rc.first > 0` (contour_mng.h:515)
-  const float h = __fadd_rn(P.cfg.lidar_height, pt.z);
-  ok = ok && (h > -1000.0f);  // bev_ starts at -1000 and only strictly higher points are stored
-  cell = ok ? row * P.cfg.n_col + col : 0;
-  key = ok ? (((c2g_cellkey) c2g_orderable(h) << 32) | (c2g_cellkey) (0xFFFFFFFFu - idx)) : 0ull;
+template <bool LOWFILTER>
+__device__ __forceinline__ void apply_op(const PointOp &op, c2g_cellkey *tile, uint32_t *occ) {
+  if (op.key > *(volatile c2g_cellkey *) (tile + op.cell)) atomicMax(tile + op.cell, op.key);
+  if (LOWFILTER && (op.obit & ~*(volatile uint32_t *) (occ + op.ow))) atomicOr(occ + op.ow, op.obit);
 }
 
-template <bool UNIT>
+template <bool UNIT, bool LOWFILTER>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P,
-                   c2g_cellkey *__restrict__ tiles_out) {
-  extern __shared__ c2g_cellkey tile[];
-  const int tid = threadIdx.x;
-  const int ncell = P.n_cells;
+bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P, C2gBevOut out,
+                   int *__restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncell = P.n_cells, ncol = P.cfg.n_col, nrow = P.cfg.n_row;
+  const int wpr = (ncol + 31) >> 5, nwords = nrow * wpr;
+  c2g_cellkey *tile = reinterpret_cast<c2g_cellkey *>(k1_smem);                     // [ncell]
+  uint32_t *occ = reinterpret_cast<uint32_t *>(tile + ((ncell + 1) & ~1));           // [nwords] occupancy of the low cells
+  uint32_t *plane = occ + nwords;                                                    // [NLEV][nwords] staged for a coalesced write
+  uint16_t *wpre = reinterpret_cast<uint16_t *>(plane + C2G_NLEV * nwords);          // [nwords] fg cells before each word
+  __shared__ int s_next, s_warp_occ[K1_WARPS], s_nfg;
+  float lv_min = P.cfg.lv_grads[0];
+#pragma unroll
+  for (int e = 1; e < C2G_NLEV; ++e) lv_min = fminf(lv_min, P.cfg.lv_grads[e]);
   for (int c = tid; c < ncell; c += K1_THREADS) tile[c] = 0ull;
-  __syncthreads();
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (int w = tid; w < nwords; w += K1_THREADS) occ[w] = 0u;
+  // scans are handed out dynamically: a CTA that starts late (behind a co-running collective or the previous kernel's tail)
+  // must not leave a static share of the batch unprocessed until the end
+  while (true) {
+    if (tid == 0) s_next = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int b = s_next;
+    if (b >= B) break;
     const long long beg = offsets[b];
     const int n = (int) (offsets[b + 1] - beg);
     const float4 *p = pts + beg;
     int i = tid;
-    // main loop: UNROLL independent 128-bit loads per thread before any of them is consumed (a register double-buffered
-    // software pipeline was measured 5 % slower: the kernel is bound by shared-memory atomics, not by load latency)
+    // main loop: UNROLL independent 128-bit loads per thread before any of them is consumed; then the cell / key of all UNROLL
+    // points (straight-line code), then all filter reads of the tile, then the atomics: the shared-memory latencies of the
+    // eight points overlap instead of adding up behind five branches per point
     for (; i + (K1_UNROLL - 1) * K1_THREADS < n; i += K1_UNROLL * K1_THREADS) {
       float4 v[K1_UNROLL];
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) v[u] = ld_stream_f4(p + i + u * K1_THREADS);
-      if (UNIT) {
-        // keys of all UNROLL points first (straight-line code), then all filter reads of the tile, then the atomics: the
-        // shared-memory latencies of the eight points overlap instead of adding up behind five branches per point
-        int cell[K1_UNROLL];
-        c2g_cellkey key[K1_UNROLL], cur[K1_UNROLL];
+      PointOp op[K1_UNROLL];
+      c2g_cellkey cur[K1_UNROLL];
+      uint32_t ocur[K1_UNROLL];
 #pragma unroll
-        for (int u = 0; u < K1_UNROLL; ++u) point_key_unit(v[u], (uint32_t) (i + u * K1_THREADS), P, cell[u], key[u]);
+      for (int u = 0; u < K1_UNROLL; ++u) op[u] = point_op<UNIT, LOWFILTER>(v[u], (uint32_t) (i + u * K1_THREADS), P, lv_min, wpr);
 #pragma unroll
-        for (int u = 0; u < K1_UNROLL; ++u) cur[u] = *(volatile c2g_cellkey *) (tile + cell[u]);
+      for (int u = 0; u < K1_UNROLL; ++u) {
+        cur[u] = op[u].key ? *(volatile c2g_cellkey *) (tile + op[u].cell) : ~0ull;
+        if (LOWFILTER) ocur[u] = op[u].obit ? *(volatile uint32_t *) (occ + op[u].ow) : ~0u;
+      }
 #pragma unroll
-        for (int u = 0; u < K1_UNROLL; ++u)
-          if (key[u] > cur[u]) atomicMax(tile + cell[u], key[u]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < K1_UNROLL; ++u) scatter_point<UNIT>(v[u], (uint32_t) (i + u * K1_THREADS), P, tile);
+      for (int u = 0; u < K1_UNROLL; ++u) {
+        if (op[u].key > cur[u]) atomicMax(tile + op[u].cell, op[u].key);
+        if (LOWFILTER && (op[u].obit & ~ocur[u])) atomicOr(occ + op[u].ow, op[u].obit);
       }
     }
-    for (; i < n; i += K1_THREADS) scatter_point<UNIT>(ld_stream_f4(p + i), (uint32_t) i, P, tile);
+    for (; i < n; i += K1_THREADS) apply_op<LOWFILTER>(point_op<UNIT, LOWFILTER>(ld_stream_f4(p + i), (uint32_t) i, P, lv_min, wpr), tile, occ);
     __syncthreads();
-    // write the finished tile (coalesced 8 B / thread) and reset it for the next scan in the same pass
-    c2g_cellkey *out = tiles_out + (size_t) b * ncell;
-    for (int c = tid; c < ncell; c += K1_THREADS) {
-      out[c] = tile[c];
-      tile[c] = 0ull;
+
+    // ---- epilogue 1: bit-planes, occupancy and the number of foreground cells of every 32-column word
+    int occ_cnt = 0;
+    for (int w = warp; w < nwords; w += K1_WARPS) {
+      const int row = w / wpr, c = (w - row * wpr) * 32 + lane;
+      const c2g_cellkey k = c < ncol ? tile[row * ncol + c] : 0ull;
+      const bool has = k != 0ull;
+      const float h = has ? c2g_from_orderable((uint32_t) (k >> 32)) : -1000.0f;
+      const uint32_t occ_hi = __ballot_sync(FULLMASK, has);
+      uint32_t mine = 0;
+      // most 32-cell words hold no cell above the lowest threshold: one ballot settles all six planes
+      if (__ballot_sync(FULLMASK, has && h > lv_min)) {
+#pragma unroll
+        for (int e = 0; e < C2G_NLEV; ++e) {
+          const uint32_t bal = __ballot_sync(FULLMASK, has && h > P.cfg.lv_grads[e]);
+          if (lane == e) mine = bal;
+        }
+      }
+      if (lane < C2G_NLEV) plane[lane * nwords + w] = mine;
+      const uint32_t fgw = __shfl_sync(FULLMASK, mine, 0);  // lv_grads increase (checked at c2g_create): plane 0 = all foreground cells
+      if (lane == 0) {
+        wpre[w] = (uint16_t) __popc(fgw);
+        occ_cnt += __popc(occ_hi | (LOWFILTER ? occ[w] : 0u));
+      }
     }
+    if (lane == 0) s_warp_occ[warp] = occ_cnt;
+    __syncthreads();
+    // ---- epilogue 2: exclusive prefix of the per-word counts (raster order = the order moments are accumulated in)
+    if (warp == 0) {
+      int base = 0;
+      for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < nwords ? (int) wpre[w] : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULLMASK, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (w < nwords) wpre[w] = (uint16_t) (base + incl - cnt);
+        base += __shfl_sync(FULLMASK, incl, 31);
+      }
+      if (lane == 0) s_nfg = base;
+    }
+    __syncthreads();
+    // ---- epilogue 3: foreground records (height + the winner's continuous coordinates: an 8-byte gather from the points just
+    // streamed), coalesced write of the planes, reset of the tile for the next scan
+    float4 *fg = out.fg + (size_t) b * ncell;
+    for (int w = warp; w < nwords; w += K1_WARPS) {
+      const uint32_t fgw = plane[w];
+      if (fgw == 0u) continue;
+      if ((fgw >> lane) & 1u) {
+        const int row = w / wpr, c = (w - row * wpr) * 32 + lane;
+        const c2g_cellkey k = tile[row * ncol + c];
+        const float2 xy = __ldg(reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k)));
+        float4 rec;
+        rec.x = c2g_from_orderable((uint32_t) (k >> 32));
+        // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
+        rec.y = __fsub_rn(__fadd_rn(__fdiv_rn(xy.x, P.cfg.reso_row), P.half_row_f), 0.5f);
+        rec.z = __fsub_rn(__fadd_rn(__fdiv_rn(xy.y, P.cfg.reso_col), P.half_col_f), 0.5f);
+        rec.w = 0.0f;
+        fg[(int) wpre[w] + __popc(fgw & ((1u << lane) - 1u))] = rec;
+      }
+    }
+    {
+      uint32_t *pl_out = out.planes + (size_t) b * C2G_NLEV * nwords;
+      for (int j = tid; j < C2G_NLEV * nwords; j += K1_THREADS) pl_out[j] = plane[j];
+      if (tid == 0) {
+        int tot = 0;
+        for (int wq = 0; wq < K1_WARPS; ++wq) tot += s_warp_occ[wq];
+        out.hdr[b] = make_int2(tot, s_nfg);
+      }
+    }
+    __syncthreads();  // every reader of the tile is done
+    if (!LOWFILTER && out.tiles) {
+      c2g_cellkey *t_out = out.tiles + (size_t) b * ncell;
+      for (int c = tid; c < ncell; c += K1_THREADS) {
+        t_out[c] = tile[c];
+        tile[c] = 0ull;
+      }
+    } else {
+      for (int c = tid; c < ncell; c += K1_THREADS) tile[c] = 0ull;
+    }
+    for (int w = tid; w < nwords; w += K1_THREADS) occ[w] = 0u;
     __syncthreads();
   }
 }
 
+size_t k1_smem_bytes(int ncell, int nwords) {
+  return (size_t) ((ncell + 1) & ~1) * sizeof(c2g_cellkey) + (size_t) nwords * 4 * (1 + C2G_NLEV) + (size_t) nwords * 2 + 16;
+}
+
+template <bool UNIT, bool LOWFILTER>
+int launch_variant(const float4 *pts, const long long *offsets, int B, const C2gIngestParams &P, const C2gBevOut &out, int *work_counter, int grid,
+                   size_t smem, cudaStream_t stream) {
+  static unsigned long long attr_devs = 0ull;
+  if (c2g_first_use_on_device(attr_devs))
+    C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<UNIT, LOWFILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int) k1_smem_bytes(C2G_MAX_CELLS, 800)));
+  bev_scatter_kernel<UNIT, LOWFILTER><<<grid, K1_THREADS, smem, stream>>>(pts, offsets, B, P, out, work_counter);
+  return 0;
+}
+
 }  // namespace
 
-// host launcher (called from c2g_api.cu)
-int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P,
-                           c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream) {
-  const size_t smem = (size_t) P.n_cells * sizeof(c2g_cellkey);
-  static unsigned long long attr_devs = 0ull;
-  if (c2g_first_use_on_device(attr_devs)) {
-    C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (C2G_MAX_CELLS * sizeof(c2g_cellkey))));
-    C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (C2G_MAX_CELLS * sizeof(c2g_cellkey))));
-  }
+// host launcher (called from c2g_api.cu).  full_tile != 0: every point takes the 64-bit key path and the complete tile is
+// written to out.tiles as well (debug getters); otherwise the production variant with the low-point filter.
+int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P, const C2gBevOut &out,
+                           int full_tile, int *work_counter, int num_sms, cudaStream_t stream) {
+  const int nwords = P.cfg.n_row * ((P.cfg.n_col + 31) / 32);
+  const size_t smem = k1_smem_bytes(P.n_cells, nwords);
   const int grid = B < num_sms ? B : num_sms;
   if (grid <= 0) return 0;
+  C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
   // the fast path needs: unit resolution, symmetric padded bounds, and bounds that keep floor(x) + n/2 inside the image
   const bool unit = P.cfg.reso_row == 1.0f && P.cfg.reso_col == 1.0f && P.x_min_pad == -P.x_max_pad && P.y_min_pad == -P.y_max_pad &&
                     P.x_max_pad < (float) P.half_row && P.y_max_pad < (float) P.half_col;
+  const float4 *p4 = (const float4 *) pts_dev;
+  int rc;
   if (unit)
-    bev_scatter_kernel<true><<<grid, K1_THREADS, smem, stream>>>((const float4 *) pts_dev, offsets_dev, B, P, tiles_dev);
+    rc = full_tile ? launch_variant<true, false>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream)
+                   : launch_variant<true, true>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream);
   else
-    bev_scatter_kernel<false><<<grid, K1_THREADS, smem, stream>>>((const float4 *) pts_dev, offsets_dev, B, P, tiles_dev);
+    rc = full_tile ? launch_variant<false, false>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream)
+                   : launch_variant<false, true>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream);
+  if (rc) return rc;
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -58,6 +58,17 @@ __host__ __device__ __forceinline__ float c2g_from_orderable(uint32_t o) {
 // (strict `<` in include/cont2/contour_mng.h:517).
 typedef unsigned long long c2g_cellkey;
 
+// What the scatter kernel hands to the contour kernel per scan of a batch (bev_scatter.cu): bit (c & 31) of word
+// r * ceil(n_col / 32) + (c >> 5) of plane l = `bev(r, c) > lv_grads[l]`; fg = the cells of plane 0 in raster order as
+// (height, row_f, col_f, 0) with the continuous coordinates of the point that set the height (bev_pixfs_, contour_mng.h:435);
+// hdr = (occupied cells = bev_pixfs_.size(), foreground cells).  tiles: the raw 64-bit cells, full-tile variant only.
+struct C2gBevOut {
+  uint32_t *planes;    // [B][C2G_NLEV][n_row * ceil(n_col / 32)]
+  float4 *fg;          // [B][n_cells]
+  int2 *hdr;           // [B]
+  c2g_cellkey *tiles;  // [B][n_cells] or nullptr
+};
+
 // Compact GMM ellipse of one contour view (GMMPair::GMMEllipse, include/cont2/correlation.h:24-33): one 32-byte sector per
 // view, written next to the view by the contour kernel, read by the GMM-L2 kernels instead of the 80-byte view record.
 // cov = ContourView::getManualCov() (float, column-major), w = cell_cnt, maj = sqrtf(eig_vals[1]) (correlation.h:64,72).

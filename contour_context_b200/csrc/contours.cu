@@ -1,4 +1,4 @@
-// contours.cu — K2: BEV tile -> multi-level contours -> ContourView statistics -> per-level order -> retrieval keys ->
+// contours.cu — K2: BEV bit-planes + foreground cell list (bev_scatter.cu) -> multi-level contours -> ContourView statistics -> per-level order -> retrieval keys ->
 // BCIs -> per-scan GMM terms.  Persistent CTAs of 512 threads, TWO resident per SM (<= 113 KB of shared memory each), one
 // scan per CTA iteration; everything between the BEV tile and the finished descriptor stays in shared memory / L1 / L2.
 //
@@ -17,8 +17,10 @@
 // (SURVEY.md §7 hard part 2).  Hence
 //   order(level L) = sort by (rank of parent in level L-1, min over pixels of ((r-y0)>>1, (c-x0)>>1)).
 //
-// Data structures (round 1e): the thresholded image of every level is a bit-plane (one 32-bit word per 32 columns of a
-// row, built with warp ballots while the tile is decoded); the union-find runs over horizontal RUNS of set bits, not
+// Data structures: the thresholded image of every level is a bit-plane (one 32-bit word per 32 columns of a row, built by
+// the scatter kernel from its shared-memory tile - round 1 sent the 180 KB tile through HBM and decoded it here); the
+// heights and continuous coordinates of the ~6 % of cells above the lowest threshold arrive as a compact raster-ordered list
+// (16 B per cell, index = number of plane-0 bits before the cell), so a run of cells is a contiguous slice of it; the union-find runs over horizontal RUNS of set bits, not
 // over pixels (a 150 x 150 KITTI BEV has ~1 400 foreground cells but only ~600 runs and ~80 components per level).  One
 // warp labels one level (six levels at once, no block barrier inside), runs are numbered in raster order so that
 //   * the smallest run id of a component is its first pixel in raster order (the root of min-linking union-find),
@@ -48,10 +50,8 @@ constexpr int K2_THREADS = 512;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_CTAS_PER_SM = 2;
 constexpr int PLANE_WORDS = 800;  // n_row * ceil(n_col / 32) (checked by make_params): 150 x 5 = 750 for both shipped configs
-constexpr int WCHUNK = 5;         // 32-column words of a row decoded per batch in phase A
-constexpr int ROWS_A = 2;         // rows per warp per batch in phase A (2 x 5 independent loads in flight per lane)
 constexpr int R_POOL = 5120;      // runs of all six levels that fit in shared memory (else: global arena)
-constexpr int C_POOL = 1536;      // components of all six levels that fit in shared memory (else: global arena)
+constexpr int C_POOL = 1408;      // components of all six levels that fit in shared memory (else: global arena)
 constexpr int NVL = 1024;         // significant components (area >= min_cont_cell_cnt) per level
 constexpr int KEY_LIST_CAP = 400; // cells of one key window that can lie inside the 9.99-cell radius
 constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
@@ -75,6 +75,7 @@ constexpr int CW = 4;
 
 struct Smem {
   uint32_t plane[C2G_NLEV][PLANE_WORDS];  // bit (c & 31) of word r * WPR + (c >> 5): bev(r, c) > lv_grads[level]
+  uint16_t fgpre[PLANE_WORDS];            // plane-0 bits before each word = index of the word's first cell in the foreground list
   union {
     uint16_t wpre[C2G_NLEV][PLANE_WORDS];  // number of runs that start before this word (labelling, parent lookup)
     struct {
@@ -333,9 +334,8 @@ __host__ __device__ inline size_t arena_bytes(int n_cells, int n_row) {
 static_assert(K2_WARPS >= 2 * C2G_NLEV, "two warps per level in the labelling phases (the other warps skip them)");
 
 __global__ void __launch_bounds__(K2_THREADS, K2_CTAS_PER_SM)
-contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B,
-               C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, float *__restrict__ bev_h,
-               float *__restrict__ bev_rf, float *__restrict__ bev_cf, c2g_view *__restrict__ presort_scratch,
+contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict__ fg_in, const int2 *__restrict__ hdr_in, int B,
+               C2gIngestParams P, const int *__restrict__ int_ids, int first_slot, c2g_view *__restrict__ presort_scratch,
                c2g_scan_head *__restrict__ heads, c2g_view *__restrict__ views, c2g_ell *__restrict__ ells,
                unsigned char *__restrict__ klist_scratch, unsigned char *__restrict__ arenas, int force_arena,
                int *__restrict__ work_counter, long long *__restrict__ dbg) {
@@ -360,85 +360,45 @@ contour_kernel(const c2g_cellkey *__restrict__ tiles, const float4 *__restrict__
     __syncthreads();
     const int b = S.next_scan;
     if (b >= B) break;
-    const size_t cbase = (size_t) b * ncell;
-    const float *hg = bev_h + cbase, *rfg = bev_rf + cbase, *cfp = bev_cf + cbase;
+    const float4 *fg = fg_in + (size_t) b * ncell;  // (height, row_f, col_f, 0) of the foreground cells, raster order
     c2g_scan_head *head = heads + (first_slot + b);
     c2g_view *vout = views + (size_t) (first_slot + b) * C2G_VIEW_CAP;
     c2g_ell *eout = ells + (size_t) (first_slot + b) * C2G_VIEW_CAP;
 
 #define C2G_DBG(i) do { if (dbg && blockIdx.x == 0 && tid == 0) dbg[i] = clock64(); } while (0)
     C2G_DBG(0);
-    // ---------------- phase A: decode the tile -> one bit-plane per level; cells above the lowest threshold (the only ones
-    // moments and keys ever read) get their height and the winner's continuous coordinates (8-byte gather from the points)
+    // ---------------- phase A: the scatter kernel's bit-planes -> shared memory (18 KB, coalesced)
     if (tid == 0) {
       S.status = 0;
-      S.n_occ = 0;
+      S.n_occ = hdr_in[b].x;
       S.arena = -1;
       S.runs_in_arena = 0;
       S.comps_in_arena = 0;
     }
-    __syncthreads();
     {
-      const float4 *p = pts + offsets[b];
-      int occ = 0;
-      float lv_min = cfg.lv_grads[0];
+      const uint32_t *pl_in = planes_in + (size_t) b * C2G_NLEV * nwords;
 #pragma unroll
-      for (int e = 1; e < C2G_NLEV; ++e) lv_min = fminf(lv_min, cfg.lv_grads[e]);
-      for (int r0 = warp * ROWS_A; r0 < nrow; r0 += K2_WARPS * ROWS_A) {
-        for (int u0 = 0; u0 < WPR; u0 += WCHUNK) {
-          c2g_cellkey k[ROWS_A][WCHUNK];
-#pragma unroll
-          for (int q = 0; q < ROWS_A; ++q)
-#pragma unroll
-            for (int u = 0; u < WCHUNK; ++u) {
-              const int c = (u0 + u) * 32 + lane;
-              k[q][u] = (r0 + q < nrow && c < ncol) ? tiles[cbase + (size_t) (r0 + q) * ncol + c] : 0ull;
-            }
-          float2 xy[ROWS_A][WCHUNK];
-          float hv[ROWS_A][WCHUNK];
-          uint32_t fgm = 0;  // bit q * WCHUNK + u: this lane's cell is above some threshold
-#pragma unroll
-          for (int q = 0; q < ROWS_A; ++q)
-#pragma unroll
-            for (int u = 0; u < WCHUNK; ++u) {
-              const bool has = k[q][u] != 0ull;
-              const float h = has ? c2g_from_orderable((uint32_t) (k[q][u] >> 32)) : -1000.0f;
-              hv[q][u] = h;
-              occ += __popc(__ballot_sync(FULL, has));
-              uint32_t mine = 0;
-              // ~85 % of the 32-cell chunks hold no cell above the lowest threshold: one ballot settles all six planes
-              const bool fg = has && h > lv_min;
-              if (__ballot_sync(FULL, fg)) {
-#pragma unroll
-                for (int e = 0; e < C2G_NLEV; ++e) {
-                  const uint32_t bal = __ballot_sync(FULL, has && h > cfg.lv_grads[e]);
-                  if (lane == e) mine = bal;
-                }
-              }
-              if (lane < C2G_NLEV && u0 + u < WPR && r0 + q < nrow) S.plane[lane][(r0 + q) * WPR + u0 + u] = mine;
-              xy[q][u] = make_float2(0.f, 0.f);
-              if (fg) {
-                fgm |= 1u << (q * WCHUNK + u);
-                xy[q][u] = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k[q][u]));
-              }
-            }
-#pragma unroll
-          for (int q = 0; q < ROWS_A; ++q)
-#pragma unroll
-            for (int u = 0; u < WCHUNK; ++u)
-              if (fgm & (1u << (q * WCHUNK + u))) {
-                const size_t c = cbase + (size_t) (r0 + q) * ncol + (u0 + u) * 32 + lane;
-                bev_h[c] = hv[q][u];
-                // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
-                bev_rf[c] = (xy[q][u].x / cfg.reso_row + P.half_row_f) - 0.5f;
-                bev_cf[c] = (xy[q][u].y / cfg.reso_col + P.half_col_f) - 0.5f;
-              }
-        }
-      }
-      if (lane == 0 && occ) atomicAdd(&S.n_occ, occ);  // one same-address shared atomic per warp
+      for (int e = 0; e < C2G_NLEV; ++e)
+        for (int w = tid; w < nwords; w += K2_THREADS) S.plane[e][w] = pl_in[e * nwords + w];
     }
     __syncthreads();
     C2G_DBG(1);
+    // the warps that do not label (12..15) index the foreground list meanwhile: exclusive prefix of the plane-0 popcounts
+    if (warp == 2 * C2G_NLEV) {
+      int base = 0;
+      for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < nwords ? __popc(S.plane[0][w]) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (w < nwords) S.fgpre[w] = (uint16_t) (base + incl - cnt);
+        base += __shfl_sync(FULL, incl, 31);
+      }
+    }
 
     // ---------------- phase B: six independent run-based labellings, two warps per level ------------------------------
     // B1 runs per word -> exclusive prefix (run ids are raster order); each warp scans half of the words
