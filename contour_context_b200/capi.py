@@ -42,6 +42,7 @@ def lib():
         L.c2g_get_views.argtypes = [vp, ip, vp]
         L.c2g_get_bev.argtypes = [vp, ip, vp, vp, vp]
         L.c2g_get_tiles.argtypes = [vp, ip, vp]
+        L.c2g_get_bev_compact.argtypes = [vp, ip, ip, vp, vp, vp]
         L.c2g_copy_slots.argtypes = [vp, ip, ip, ip]
         L.c2g_db_set_layer.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
         L.c2g_query.argtypes = [vp, ip, ip, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp, vp, vp]
@@ -75,6 +76,7 @@ def lib():
         L.c2g_query_profile.argtypes = [vp, C.c_int, vp]
         L.c2g_launch_count.argtypes = [vp]
         L.c2g_selftest_stdsort.argtypes = [vp, ip, ip]
+        L.c2g_selftest_warpsort.argtypes = [vp, vp, ip, ip]
         sizes = [D.SCAN_HEAD_DTYPE.itemsize, D.VIEW_DTYPE.itemsize, D.BCI_DTYPE.itemsize, D.HINT_DTYPE.itemsize,
                  D.PAIR_SCORE_DTYPE.itemsize, D.QUERY_RESULT_DTYPE.itemsize, C.sizeof(D.CmConfig), C.sizeof(D.DbConfig)]
         for i, s in enumerate(sizes):

@@ -8,16 +8,16 @@
 // 64-bit cell keys (180 KB of the 227 KB carve-out), so the only HBM traffic is the streaming read of the points
 // (16 B/point, 128-bit ld.global.nc.L1::no_allocate, UNROLL independent loads in flight per thread) plus ~40 KB of output
 // per scan (round 1 wrote the 180 KB tile and the contour kernel read it back).  The reference's "if (bev < h) bev = h"
-// with first-point-wins ties becomes a 64-bit max over (orderable(h) << 32 | ~index); a plain shared-memory read filters
-// the points that cannot raise their cell any more before the atomic is issued (max is monotone, so a stale read can only
-// cause a redundant atomic, never a missed one).
+// with first-point-wins ties becomes a 64-bit max over (orderable(h) << 32 | ~index); a plain 32-bit shared-memory read of
+// the cell's height word filters the points that cannot raise their cell any more before the atomic is issued (max is
+// monotone, so a stale read can only cause a redundant atomic, never a missed one).
 //
-// LOWFILTER (production): a point at or below the lowest threshold can never belong to a contour; all the path needs from
-// it is that its cell counts as occupied (bev_pixfs_.size()).  Such points (~2/3 of a scan: the ground) set one bit of a
-// 2.8 KB occupancy bitmap - a 32-bit read and, rarely, a native 32-bit atomicOr - instead of going through the 64-bit
-// compare-and-swap loop (there is no native 64-bit shared-memory max: ATOMS.CAST.SPIN.64), which was half of round 1's
-// instructions.  LOWFILTER = false keeps every point on the key path and additionally writes the full tile: the dense-image
-// getters (c2g_get_bev / c2g_get_tiles, ContourManager::getBevImage) and c2g_ingest_bev_only run that variant.
+// Measured dead end (round 2, profiles/r2_k1_lowfilter.txt): routing the points at or below the lowest threshold (2/3 of a
+// scan: the ground) to a 2.8 KB occupancy bitmap with native 32-bit atomicOr instead of the 64-bit compare-and-swap loop.  A
+// warp still executes the CAS block of every unrolled point whenever ANY of its lanes needs it (always), so the split only
+// adds the second path: 0.87 ms instead of 0.84 ms per 1 184 scans.  The template parameter is kept for that measurement.
+#include <cstdlib>
+
 #include "c2g_common.cuh"
 
 namespace {
@@ -25,6 +25,7 @@ namespace {
 constexpr int K1_THREADS = 1024;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_UNROLL = 8;
+constexpr int K1_STASH = 2048;  // foreground cells staged between the epilogue passes (12 B each)
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
@@ -35,9 +36,10 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   return r;
 }
 
-// What one point asks of the tile: `key` != 0: raise cell `cell` to `key`; `obit` != 0: mark bit `obit` of occupancy word `ow`.
+// What one point asks of the tile: `key` != 0: raise cell `ix` to `key`; `obit` != 0: mark bit `obit` of occupancy word `ix`
+// (a point is one or the other, a rejected point neither).
 struct PointOp {
-  int cell, ow;
+  int ix;
   c2g_cellkey key;
   uint32_t obit;
 };
@@ -71,23 +73,25 @@ __device__ __forceinline__ PointOp point_op(const float4 pt, const uint32_t idx,
   const bool hi = ok && (!LOWFILTER || h > lv_min);
   const bool lo = ok && !hi;
   PointOp op;
-  op.cell = hi ? row * P.cfg.n_col + col : 0;
+  op.ix = hi ? row * P.cfg.n_col + col : (lo ? row * wpr + (col >> 5) : 0);
   op.key = hi ? (((c2g_cellkey) c2g_orderable(h) << 32) | (c2g_cellkey) (0xFFFFFFFFu - idx)) : 0ull;
-  op.ow = lo ? row * wpr + (col >> 5) : 0;
   op.obit = lo ? (1u << (col & 31)) : 0u;
   return op;
 }
 
 template <bool LOWFILTER>
 __device__ __forceinline__ void apply_op(const PointOp &op, c2g_cellkey *tile, uint32_t *occ) {
-  if (op.key > *(volatile c2g_cellkey *) (tile + op.cell)) atomicMax(tile + op.cell, op.key);
-  if (LOWFILTER && (op.obit & ~*(volatile uint32_t *) (occ + op.ow))) atomicOr(occ + op.ow, op.obit);
+  if (op.key) {
+    if (op.key > *(volatile c2g_cellkey *) (tile + op.ix)) atomicMax(tile + op.ix, op.key);
+  } else if (LOWFILTER && op.obit) {
+    if (op.obit & ~*(volatile uint32_t *) (occ + op.ix)) atomicOr(occ + op.ix, op.obit);
+  }
 }
 
 template <bool UNIT, bool LOWFILTER>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P, C2gBevOut out,
-                   int *__restrict__ work_counter) {
+                   int *__restrict__ work_counter, int variant) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncell = P.n_cells, ncol = P.cfg.n_col, nrow = P.cfg.n_row;
@@ -96,7 +100,11 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
   uint32_t *occ = reinterpret_cast<uint32_t *>(tile + ((ncell + 1) & ~1));           // [nwords] occupancy of the low cells
   uint32_t *plane = occ + nwords;                                                    // [NLEV][nwords] staged for a coalesced write
   uint16_t *wpre = reinterpret_cast<uint16_t *>(plane + C2G_NLEV * nwords);          // [nwords] fg cells before each word
-  __shared__ int s_next, s_warp_occ[K1_WARPS], s_nfg;
+  uint16_t *stash_loc = wpre + ((nwords + 3) & ~3);                                  // [K1_STASH] plane word << 5 | bit
+  c2g_cellkey *stash_key = reinterpret_cast<c2g_cellkey *>(stash_loc + K1_STASH);    // [K1_STASH]
+  __shared__ int s_next, s_warp_occ[K1_WARPS], s_wstash[K1_WARPS], s_nfg, s_iter, s_nstash;
+  static_assert((K1_STASH / K1_WARPS & (K1_STASH / K1_WARPS - 1)) == 0, "stash share per warp must be a power of two");
+  if (threadIdx.x == 0) s_iter = 0;
   float lv_min = P.cfg.lv_grads[0];
 #pragma unroll
   for (int e = 1; e < C2G_NLEV; ++e) lv_min = fminf(lv_min, P.cfg.lv_grads[e]);
@@ -105,10 +113,11 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
   // scans are handed out dynamically: a CTA that starts late (behind a co-running collective or the previous kernel's tail)
   // must not leave a static share of the batch unprocessed until the end
   while (true) {
-    if (tid == 0) s_next = atomicAdd(work_counter, 1);
+    if (tid == 0) s_next = (variant & 2) ? (s_iter++ * (int) gridDim.x + (int) blockIdx.x) : atomicAdd(work_counter, 1);
     __syncthreads();
     const int b = s_next;
     if (b >= B) break;
+    if (tid == 0) s_nstash = 0;  // (ordered before its uses by the barrier that ends the main loop)
     const long long beg = offsets[b];
     const int n = (int) (offsets[b + 1] - beg);
     const float4 *p = pts + beg;
@@ -121,56 +130,104 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) v[u] = ld_stream_f4(p + i + u * K1_THREADS);
       PointOp op[K1_UNROLL];
-      c2g_cellkey cur[K1_UNROLL];
-      uint32_t ocur[K1_UNROLL];
+      uint32_t cur[K1_UNROLL];  // height word of a high point's cell (upper half of the 64-bit key) / occupancy word of a low point
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) op[u] = point_op<UNIT, LOWFILTER>(v[u], (uint32_t) (i + u * K1_THREADS), P, lv_min, wpr);
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) {
-        cur[u] = op[u].key ? *(volatile c2g_cellkey *) (tile + op[u].cell) : ~0ull;
-        if (LOWFILTER) ocur[u] = op[u].obit ? *(volatile uint32_t *) (occ + op[u].ow) : ~0u;
+        // one unconditional 32-bit read per point (a rejected point reads word 1 of the tile and ignores it)
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tile) + 2 * op[u].ix + 1;
+        if (LOWFILTER && op[u].obit) src = occ + op[u].ix;
+        cur[u] = *(volatile const uint32_t *) src;
+      }
+      if (variant & 1) {  // experiment: the 64-bit filter read of round 1
+        c2g_cellkey c64[K1_UNROLL];
+#pragma unroll
+        for (int u = 0; u < K1_UNROLL; ++u) c64[u] = *(volatile c2g_cellkey *) (tile + op[u].ix);
+#pragma unroll
+        for (int u = 0; u < K1_UNROLL; ++u)
+          if (op[u].key > c64[u]) atomicMax(tile + op[u].ix, op[u].key);
+        continue;
       }
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) {
-        if (op[u].key > cur[u]) atomicMax(tile + op[u].cell, op[u].key);
-        if (LOWFILTER && (op[u].obit & ~ocur[u])) atomicOr(occ + op[u].ow, op[u].obit);
+        // equal heights go to the atomic too: the lower point index wins there.  key == 0 for low / rejected points.
+        if (op[u].key && (uint32_t) (op[u].key >> 32) >= cur[u]) atomicMax(tile + op[u].ix, op[u].key);
+        if (LOWFILTER && (op[u].obit & ~cur[u])) atomicOr(occ + op[u].ix, op[u].obit);  // obit == 0 for high points
       }
     }
     for (; i < n; i += K1_THREADS) apply_op<LOWFILTER>(point_op<UNIT, LOWFILTER>(ld_stream_f4(p + i), (uint32_t) i, P, lv_min, wpr), tile, occ);
     __syncthreads();
+    if (variant & 4) {  // experiment: main loop only (outputs are garbage)
+      for (int c = tid; c < ncell; c += K1_THREADS) tile[c] = 0ull;
+      __syncthreads();
+      continue;
+    }
 
-    // ---- epilogue 1: bit-planes, occupancy and the number of foreground cells of every 32-column word
+    // ---- epilogue 1: occupancy count, reset of the tile, bit-planes.  The cells above the lowest threshold (~5 % of the image)
+    // are moved to a small stash (key + plane word + bit; every warp fills its own share, positions from a ballot: no shared counter) so that the gather pass below is a
+    // dense, balanced loop over ~1 100 entries instead of a second walk over 22 500 cells with a few long-latency loads per
+    // thread; cells that do not fit the stash stay in the tile for a fall-back walk.
     int occ_cnt = 0;
-    for (int w = warp; w < nwords; w += K1_WARPS) {
-      const int row = w / wpr, c = (w - row * wpr) * 32 + lane;
-      const c2g_cellkey k = c < ncol ? tile[row * ncol + c] : 0ull;
-      const bool has = k != 0ull;
-      const float h = has ? c2g_from_orderable((uint32_t) (k >> 32)) : -1000.0f;
-      const uint32_t occ_hi = __ballot_sync(FULLMASK, has);
-      uint32_t mine = 0;
-      // most 32-cell words hold no cell above the lowest threshold: one ballot settles all six planes
-      if (__ballot_sync(FULLMASK, has && h > lv_min)) {
+    {
+      // one warp per 32-column plane word (lane = column): the plane bits are ballots, no shared atomics; word w advances by
+      // K1_WARPS words per step without a division
+      const int dr = K1_WARPS / wpr, dw = K1_WARPS - dr * wpr;
+      int row = warp / wpr, wi = warp - row * wpr;
+      c2g_cellkey *t_out = (!LOWFILTER && out.tiles) ? out.tiles + (size_t) b * ncell : nullptr;
+      int wcount = 0;  // stash slots this warp has used (warp-uniform): every warp owns K1_STASH / K1_WARPS slots, no shared counter
+      for (int w = warp; w < nwords; w += K1_WARPS) {
+        const int col = wi * 32 + lane, c = row * ncol + col;
+        const bool in = col < ncol;
+        const c2g_cellkey k = in ? tile[c] : 0ull;
+        if (t_out && in) t_out[c] = k;
+        const float h = k != 0ull ? c2g_from_orderable((uint32_t) (k >> 32)) : -1000.0f;
+        const bool isfg = k != 0ull && h > lv_min;
+        const unsigned occ_m = __ballot_sync(FULLMASK, k != 0ull);
+        const unsigned m = __ballot_sync(FULLMASK, isfg);  // lv_grads increase (checked at c2g_create): plane 0 = all foreground cells
+        uint32_t mine = 0;
+        if (m) {  // most words hold no cell above the lowest threshold
 #pragma unroll
-        for (int e = 0; e < C2G_NLEV; ++e) {
-          const uint32_t bal = __ballot_sync(FULLMASK, has && h > P.cfg.lv_grads[e]);
-          if (lane == e) mine = bal;
+          for (int e = 1; e < C2G_NLEV; ++e) {
+            const uint32_t bal = __ballot_sync(FULLMASK, isfg && h > P.cfg.lv_grads[e]);
+            if (lane == e) mine = bal;
+          }
+          if (lane == 0) mine = m;
+        }
+        if (lane < C2G_NLEV) plane[lane * nwords + w] = mine;
+        if (lane == 0) occ_cnt += __popc(occ_m | (LOWFILTER ? occ[w] : 0u));
+        bool keep = false;
+        if (isfg) {
+          const int pos = wcount + __popc(m & ((1u << lane) - 1u));
+          if (pos < K1_STASH / K1_WARPS) {
+            stash_key[warp * (K1_STASH / K1_WARPS) + pos] = k;
+            stash_loc[warp * (K1_STASH / K1_WARPS) + pos] = (uint16_t) ((w << 5) | lane);
+          } else
+            keep = true;  // stays in the tile for the fall-back walk
+        }
+        wcount += __popc(m);
+        if (k != 0ull && !keep) tile[c] = 0ull;
+        row += dr;
+        wi += dw;
+        if (wi >= wpr) {
+          wi -= wpr;
+          ++row;
         }
       }
-      if (lane < C2G_NLEV) plane[lane * nwords + w] = mine;
-      const uint32_t fgw = __shfl_sync(FULLMASK, mine, 0);  // lv_grads increase (checked at c2g_create): plane 0 = all foreground cells
       if (lane == 0) {
-        wpre[w] = (uint16_t) __popc(fgw);
-        occ_cnt += __popc(occ_hi | (LOWFILTER ? occ[w] : 0u));
+        s_wstash[warp] = wcount;
+        if (wcount > K1_STASH / K1_WARPS) s_nstash = 1;  // some cells stayed behind
       }
     }
     if (lane == 0) s_warp_occ[warp] = occ_cnt;
     __syncthreads();
-    // ---- epilogue 2: exclusive prefix of the per-word counts (raster order = the order moments are accumulated in)
-    if (warp == 0) {
+    // ---- epilogue 2: exclusive prefix of the per-word foreground counts (raster order = the order moments are accumulated in);
+    // lv_grads increase (checked at c2g_create), so plane 0 holds every foreground cell
+    if (warp == 0 && !(variant & 16)) {
       int base = 0;
       for (int w0 = 0; w0 < nwords; w0 += 32) {
         const int w = w0 + lane;
-        const int cnt = w < nwords ? (int) wpre[w] : 0;
+        const int cnt = w < nwords ? __popc(plane[w]) : 0;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -184,14 +241,10 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
     }
     __syncthreads();
     // ---- epilogue 3: foreground records (height + the winner's continuous coordinates: an 8-byte gather from the points just
-    // streamed), coalesced write of the planes, reset of the tile for the next scan
-    float4 *fg = out.fg + (size_t) b * ncell;
-    for (int w = warp; w < nwords; w += K1_WARPS) {
-      const uint32_t fgw = plane[w];
-      if (fgw == 0u) continue;
-      if ((fgw >> lane) & 1u) {
-        const int row = w / wpr, c = (w - row * wpr) * 32 + lane;
-        const c2g_cellkey k = tile[row * ncol + c];
+    // streamed) at their raster rank; coalesced write of the planes
+    {
+      float4 *fg = out.fg + (size_t) b * ncell;
+      auto emit = [&](c2g_cellkey k, int wd, int bit) {
         const float2 xy = __ldg(reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k)));
         float4 rec;
         rec.x = c2g_from_orderable((uint32_t) (k >> 32));
@@ -199,35 +252,45 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
         rec.y = __fsub_rn(__fadd_rn(__fdiv_rn(xy.x, P.cfg.reso_row), P.half_row_f), 0.5f);
         rec.z = __fsub_rn(__fadd_rn(__fdiv_rn(xy.y, P.cfg.reso_col), P.half_col_f), 0.5f);
         rec.w = 0.0f;
-        fg[(int) wpre[w] + __popc(fgw & ((1u << lane) - 1u))] = rec;
+        fg[(int) wpre[wd] + __popc(plane[wd] & ((1u << bit) - 1u))] = rec;
+      };
+      for (int e = tid; e < K1_STASH && !(variant & 8); e += K1_THREADS)
+        if ((e & (K1_STASH / K1_WARPS - 1)) < s_wstash[e / (K1_STASH / K1_WARPS)])
+          emit(stash_key[e], (int) (stash_loc[e] >> 5), (int) (stash_loc[e] & 31));
+      if (s_nstash) {  // cluttered scan: the cells that did not fit a warp's stash share are still in the tile
+        const int dr = K1_THREADS / ncol, dc = K1_THREADS - dr * ncol;
+        int row = tid / ncol, col = tid - row * ncol;
+        for (int c = tid; c < ncell; c += K1_THREADS) {
+          const c2g_cellkey k = tile[c];
+          if (k != 0ull) {
+            tile[c] = 0ull;
+            emit(k, row * wpr + (col >> 5), col & 31);
+          }
+          row += dr;
+          col += dc;
+          if (col >= ncol) {
+            col -= ncol;
+            ++row;
+          }
+        }
       }
-    }
-    {
       uint32_t *pl_out = out.planes + (size_t) b * C2G_NLEV * nwords;
-      for (int j = tid; j < C2G_NLEV * nwords; j += K1_THREADS) pl_out[j] = plane[j];
+      for (int j = tid; j < C2G_NLEV * nwords && !(variant & 32); j += K1_THREADS) pl_out[j] = plane[j];
+      if (LOWFILTER)
+        for (int w = tid; w < nwords; w += K1_THREADS) occ[w] = 0u;
       if (tid == 0) {
         int tot = 0;
         for (int wq = 0; wq < K1_WARPS; ++wq) tot += s_warp_occ[wq];
         out.hdr[b] = make_int2(tot, s_nfg);
       }
     }
-    __syncthreads();  // every reader of the tile is done
-    if (!LOWFILTER && out.tiles) {
-      c2g_cellkey *t_out = out.tiles + (size_t) b * ncell;
-      for (int c = tid; c < ncell; c += K1_THREADS) {
-        t_out[c] = tile[c];
-        tile[c] = 0ull;
-      }
-    } else {
-      for (int c = tid; c < ncell; c += K1_THREADS) tile[c] = 0ull;
-    }
-    for (int w = tid; w < nwords; w += K1_THREADS) occ[w] = 0u;
     __syncthreads();
   }
 }
 
 size_t k1_smem_bytes(int ncell, int nwords) {
-  return (size_t) ((ncell + 1) & ~1) * sizeof(c2g_cellkey) + (size_t) nwords * 4 * (1 + C2G_NLEV) + (size_t) nwords * 2 + 16;
+  return (size_t) ((ncell + 1) & ~1) * sizeof(c2g_cellkey) + (size_t) nwords * 4 * (1 + C2G_NLEV) + (size_t) ((nwords + 3) & ~3) * 2 +
+         (size_t) K1_STASH * (2 + sizeof(c2g_cellkey)) + 16;
 }
 
 template <bool UNIT, bool LOWFILTER>
@@ -237,14 +300,15 @@ int launch_variant(const float4 *pts, const long long *offsets, int B, const C2g
   if (c2g_first_use_on_device(attr_devs))
     C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<UNIT, LOWFILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int) k1_smem_bytes(C2G_MAX_CELLS, 800)));
-  bev_scatter_kernel<UNIT, LOWFILTER><<<grid, K1_THREADS, smem, stream>>>(pts, offsets, B, P, out, work_counter);
+  static const int variant = getenv("C2G_K1_VARIANT") ? atoi(getenv("C2G_K1_VARIANT")) : 0;  // measurement hook
+  bev_scatter_kernel<UNIT, LOWFILTER><<<grid, K1_THREADS, smem, stream>>>(pts, offsets, B, P, out, work_counter, variant);
   return 0;
 }
 
 }  // namespace
 
-// host launcher (called from c2g_api.cu).  full_tile != 0: every point takes the 64-bit key path and the complete tile is
-// written to out.tiles as well (debug getters); otherwise the production variant with the low-point filter.
+// host launcher (called from c2g_api.cu).  full_tile != 0: the complete 64-bit tile is written to out.tiles as well (dense-image
+// getters); otherwise only the bit-planes, the foreground list and the counts.
 int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P, const C2gBevOut &out,
                            int full_tile, int *work_counter, int num_sms, cudaStream_t stream) {
   const int nwords = P.cfg.n_row * ((P.cfg.n_col + 31) / 32);
@@ -256,6 +320,16 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
   const bool unit = P.cfg.reso_row == 1.0f && P.cfg.reso_col == 1.0f && P.x_min_pad == -P.x_max_pad && P.y_min_pad == -P.y_max_pad &&
                     P.x_max_pad < (float) P.half_row && P.y_max_pad < (float) P.half_col;
   const float4 *p4 = (const float4 *) pts_dev;
+  static const int lowfilter = getenv("C2G_K1_LOWFILTER") ? atoi(getenv("C2G_K1_LOWFILTER")) : 0;  // measurement hook (header comment)
+  if (!lowfilter && !full_tile) {  // production: the key path for every point, no tile write
+    C2gBevOut o2 = out;
+    o2.tiles = nullptr;
+    int rc2 = unit ? launch_variant<true, false>(p4, offsets_dev, B, P, o2, work_counter, grid, smem, stream)
+                   : launch_variant<false, false>(p4, offsets_dev, B, P, o2, work_counter, grid, smem, stream);
+    if (rc2) return rc2;
+    C2G_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   int rc;
   if (unit)
     rc = full_tile ? launch_variant<true, false>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream)

@@ -13,14 +13,14 @@
 #include "stdsort.cuh"
 
 // launchers implemented in the kernel translation units
-int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P,
-                           c2g_cellkey *tiles_dev, int num_sms, cudaStream_t stream);
-int c2g_launch_bev_fill(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
+int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P, const C2gBevOut &out,
+                           int full_tile, int *work_counter, int num_sms, cudaStream_t stream);
+int c2g_launch_bev_fill(const c2g_cellkey *tile1, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
                         float *bev_h, float *bev_rf, float *bev_cf, cudaStream_t stream);
-int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
-                        const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        unsigned char *k2_scratch, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg);
+int c2g_launch_contours(const C2gBevOut &bev, int B, const C2gIngestParams &P, const int *int_ids_dev, int first_slot,
+                        c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells, unsigned char *k2_scratch,
+                        int *work_counter, int num_sms, cudaStream_t stream, long long *dbg);
+int c2g_launch_warp_sort_selftest(uint32_t *words_dev, int n, int desc, cudaStream_t stream);  // contours.cu
 int c2g_contour_max_ctas(int num_sms);
 size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row);
 int c2g_query_alloc(c2g_ctx *ctx);
@@ -87,6 +87,17 @@ int probe_exp_mode() {
   if (bad2 == 0) return 2;
   if (bad1 == 0) return 1;
   return 0;
+}
+
+// the scatter -> contour hand-off buffers of scans b0.. of the current batch
+C2gBevOut bev_out(const c2g_ctx *ctx, int b0) {
+  const size_t nwords = (size_t) ctx->P.cfg.n_row * ((ctx->P.cfg.n_col + 31) / 32);
+  C2gBevOut o;
+  o.planes = ctx->d_planes + (size_t) b0 * C2G_NLEV * nwords;
+  o.fg = ctx->d_fg + (size_t) b0 * ctx->P.n_cells;
+  o.hdr = ctx->d_hdr + b0;
+  o.tiles = nullptr;
+  return o;
 }
 
 int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, const float **pts_dev) {
@@ -192,10 +203,20 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   }
   ALLOC(ctx->d_offsets, sizeof(long long) * (max_batch + 1));
   ALLOC(ctx->d_int_ids, sizeof(int) * max_batch);
-  ALLOC(ctx->d_tiles, sizeof(c2g_cellkey) * ncell * max_batch);
-  ALLOC(ctx->d_bev_h, sizeof(float) * ncell * max_batch);
-  ALLOC(ctx->d_bev_rf, sizeof(float) * ncell * max_batch);
-  ALLOC(ctx->d_bev_cf, sizeof(float) * ncell * max_batch);
+  {
+    const size_t nwords = (size_t) ctx->P.cfg.n_row * ((ctx->P.cfg.n_col + 31) / 32);
+    ALLOC(ctx->d_planes, sizeof(uint32_t) * C2G_NLEV * nwords * max_batch);
+    ALLOC(ctx->d_fg, sizeof(float4) * ncell * max_batch);
+    ALLOC(ctx->d_hdr, sizeof(int2) * max_batch);
+    ALLOC(ctx->d_work_counter_k1, sizeof(int));
+    ALLOC(ctx->d_tile1, sizeof(c2g_cellkey) * ncell);
+    ALLOC(ctx->d_planes1, sizeof(uint32_t) * C2G_NLEV * nwords);
+    ALLOC(ctx->d_fg1, sizeof(float4) * ncell);
+    ALLOC(ctx->d_hdr1, sizeof(int2));
+  }
+  ALLOC(ctx->d_bev_h, sizeof(float) * ncell);
+  ALLOC(ctx->d_bev_rf, sizeof(float) * ncell);
+  ALLOC(ctx->d_bev_cf, sizeof(float) * ncell);
   ALLOC(ctx->d_presort, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) c2g_contour_max_ctas(ctx->num_sms));
   ALLOC(ctx->d_heads, sizeof(c2g_scan_head) * (size_t) scan_capacity);
   ALLOC(ctx->d_views, sizeof(c2g_view) * C2G_VIEW_CAP * (size_t) scan_capacity);
@@ -258,7 +279,14 @@ int c2g_destroy(c2g_ctx *ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_offsets);
   cudaFree(ctx->d_int_ids);
-  cudaFree(ctx->d_tiles);
+  cudaFree(ctx->d_planes);
+  cudaFree(ctx->d_fg);
+  cudaFree(ctx->d_hdr);
+  cudaFree(ctx->d_work_counter_k1);
+  cudaFree(ctx->d_tile1);
+  cudaFree(ctx->d_planes1);
+  cudaFree(ctx->d_fg1);
+  cudaFree(ctx->d_hdr1);
   cudaFree(ctx->d_bev_h);
   cudaFree(ctx->d_bev_rf);
   cudaFree(ctx->d_bev_cf);
@@ -304,7 +332,7 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
   const float *pts_dev = nullptr;
   int rc = stage_inputs(ctx, pts, offsets_host, B, pts_on_device, &pts_dev);
   if (rc) return rc;
-  rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, ctx->d_tiles, ctx->num_sms, ctx->stream);
+  rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, bev_out(ctx, 0), 0, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
   if (rc) return rc;
   // the staging buffer is free again once the kernel that reads it has run (a later c2g_get_bev of this batch is ordered
   // behind it on the same stream; a later pipelined ingest waits for this event before its copy stream overwrites the buffer)
@@ -320,7 +348,6 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
 // this call's query kernels are still running.  Device inputs: two launches for the whole batch.
 static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *ids_dev) {
   if (offsets_host[B] - offsets_host[0] > ctx->max_points) return C2G_ERR_CAPACITY;
-  const size_t ncell = ctx->P.n_cells;
   const int cur = ctx->stage_sel;
   ctx->stage_sel ^= 1;
   float *stage = ctx->d_pts_stage2[cur];
@@ -339,10 +366,10 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     cudaEvent_t ev = ctx->ev_chunk[k % C2G_MAX_CHUNK_EVENTS];
     C2G_CUDA_TRY(cudaEventRecord(ev, ctx->copy_stream));
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
-    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, ctx->d_tiles + ncell * b0, ctx->num_sms, ctx->stream);
+    const C2gBevOut bo = bev_out(ctx, b0);
+    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, bo, 0, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
     if (rc) return rc;
-    rc = c2g_launch_contours(ctx->d_tiles + ncell * b0, stage, ctx->d_offsets + b0, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_bev_h + ncell * b0,
-                             ctx->d_bev_rf + ncell * b0, ctx->d_bev_cf + ncell * b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
+    rc = c2g_launch_contours(bo, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
                              ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
@@ -365,8 +392,8 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
   if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev);
   int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
   if (rc) return rc;
-  rc = c2g_launch_contours(ctx->d_tiles, ctx->last_pts, ctx->d_offsets, B, ctx->P, ids_dev, first_slot, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf, ctx->d_presort, ctx->d_heads,
-                           ctx->d_views, ctx->d_ells, ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
+  rc = c2g_launch_contours(bev_out(ctx, 0), B, ctx->P, ids_dev, first_slot, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_k2_scratch,
+                           ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -388,21 +415,34 @@ int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host) {
   return 0;
 }
 
+// The ingest kernels keep only what contours, moments and keys read (bit-planes + the foreground cells).  The dense image
+// (getBevImage, bev_pixfs_) and the raw 64-bit cells are produced on demand: the full-tile variant of the scatter kernel runs
+// again on the one requested scan of the last batch (its points are still resident: staging buffer or caller's buffer).
+static int rescatter_full(c2g_ctx *ctx, int batch_index) {
+  if (!ctx->last_pts) return C2G_ERR_STATE;
+  C2gBevOut o;
+  o.planes = ctx->d_planes1;
+  o.fg = ctx->d_fg1;
+  o.hdr = ctx->d_hdr1;
+  o.tiles = ctx->d_tile1;
+  int rc = c2g_launch_bev_scatter(ctx->last_pts, ctx->d_offsets + batch_index, 1, ctx->P, o, 1, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
+  if (rc) return rc;
+  ctx->launches += 1;
+  return 0;
+}
+
 int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f) {
   if (!ctx || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);
-  const size_t n = ctx->P.n_cells, off = n * batch_index;
-  // the contour kernel only fills the cells that belong to a contour; the full dense image (getBevImage, bev_pixfs_) is
-  // produced on demand from the tile and the points of the last batch (still resident: staging buffer or caller's buffer)
-  if (!ctx->last_pts) return C2G_ERR_STATE;
-  {
-    int rc = c2g_launch_bev_fill(ctx->d_tiles + off, ctx->last_pts, ctx->d_offsets, batch_index, ctx->P, ctx->d_bev_h + off,
-                                 ctx->d_bev_rf + off, ctx->d_bev_cf + off, ctx->stream);
-    if (rc) return rc;
-  }
-  if (bev) C2G_CUDA_TRY(cudaMemcpyAsync(bev, ctx->d_bev_h + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (row_f) C2G_CUDA_TRY(cudaMemcpyAsync(row_f, ctx->d_bev_rf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (col_f) C2G_CUDA_TRY(cudaMemcpyAsync(col_f, ctx->d_bev_cf + off, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n = ctx->P.n_cells;
+  int rc = rescatter_full(ctx, batch_index);
+  if (rc) return rc;
+  rc = c2g_launch_bev_fill(ctx->d_tile1, ctx->last_pts, ctx->d_offsets, batch_index, ctx->P, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf, ctx->stream);
+  if (rc) return rc;
+  ctx->launches += 1;
+  if (bev) C2G_CUDA_TRY(cudaMemcpyAsync(bev, ctx->d_bev_h, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (row_f) C2G_CUDA_TRY(cudaMemcpyAsync(row_f, ctx->d_bev_rf, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (col_f) C2G_CUDA_TRY(cudaMemcpyAsync(col_f, ctx->d_bev_cf, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -410,9 +450,38 @@ int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *
 int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host) {
   if (!ctx || !out_host || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);
-  const size_t n = ctx->P.n_cells;
-  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_tiles + n * batch_index, sizeof(c2g_cellkey) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = rescatter_full(ctx, batch_index);
+  if (rc) return rc;
+  C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_tile1, sizeof(c2g_cellkey) * (size_t) ctx->P.n_cells, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int c2g_get_bev_compact(c2g_ctx *ctx, int batch_index, int full_tile_variant, unsigned int *planes_host, float *fg_host, int *hdr_host) {
+  if (!ctx || batch_index < 0 || batch_index >= ctx->last_B) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
+  const size_t nwords = (size_t) ctx->P.cfg.n_row * ((ctx->P.cfg.n_col + 31) / 32), ncell = ctx->P.n_cells;
+  C2gBevOut o = bev_out(ctx, batch_index);
+  if (full_tile_variant) {
+    int rc = rescatter_full(ctx, batch_index);
+    if (rc) return rc;
+    o.planes = ctx->d_planes1;
+    o.fg = ctx->d_fg1;
+    o.hdr = ctx->d_hdr1;
+  }
+  int hdr[2] = {0, 0};
+  C2G_CUDA_TRY(cudaMemcpyAsync(hdr, o.hdr, sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+  if (planes_host) C2G_CUDA_TRY(cudaMemcpyAsync(planes_host, o.planes, sizeof(uint32_t) * C2G_NLEV * nwords, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (hdr[1] < 0 || (size_t) hdr[1] > ncell) return C2G_ERR_STATE;
+  if (fg_host && hdr[1] > 0) {
+    C2G_CUDA_TRY(cudaMemcpyAsync(fg_host, o.fg, sizeof(float4) * (size_t) hdr[1], cudaMemcpyDeviceToHost, ctx->stream));
+    C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (hdr_host) {
+    hdr_host[0] = hdr[0];
+    hdr_host[1] = hdr[1];
+  }
   return 0;
 }
 
@@ -646,6 +715,23 @@ int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host) {
   C2G_CUDA_TRY(cudaMemcpyAsync(out_host, ctx->d_dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int c2g_selftest_warpsort(c2g_ctx *ctx, unsigned int *words, int n, int desc) {
+  if (!ctx || !words || n < 0 || n > 20000) return C2G_ERR_ARG;
+  if (n == 0) return 0;
+  C2gDeviceGuard guard(ctx->device);
+  uint32_t *d = nullptr;
+  C2G_CUDA_TRY(cudaMalloc((void **) &d, sizeof(uint32_t) * (size_t) n));
+  cudaError_t e = cudaMemcpyAsync(d, words, sizeof(uint32_t) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? c2g_launch_warp_sort_selftest(d, n, desc, ctx->stream) : -(int) e;
+  if (!rc) {
+    e = cudaMemcpyAsync(words, d, sizeof(uint32_t) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = -(int) e;
+  }
+  cudaFree(d);
+  return rc;
 }
 
 int c2g_selftest_stdsort(unsigned int *words, int n, int desc) {

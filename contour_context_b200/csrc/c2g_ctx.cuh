@@ -43,8 +43,17 @@ struct c2g_ctx {
   cudaEvent_t ev_chunk[C2G_MAX_CHUNK_EVENTS];
   long long *d_offsets;
   int *d_int_ids;
-  c2g_cellkey *d_tiles;
-  float *d_bev_h, *d_bev_rf, *d_bev_cf;
+  // scatter kernel -> contour kernel hand-off of one batch: bit-planes, foreground cell lists, (occupied, foreground) counts
+  uint32_t *d_planes;      // [max_batch][C2G_NLEV][n_row * ceil(n_col / 32)]
+  float4 *d_fg;            // [max_batch][n_cells]
+  int2 *d_hdr;             // [max_batch]
+  int *d_work_counter_k1;  // next scan of the running scatter kernel launch
+  // one-scan scratch of the dense-image getters (c2g_get_bev / c2g_get_tiles: the full-tile scatter variant run on demand)
+  c2g_cellkey *d_tile1;
+  uint32_t *d_planes1;
+  float4 *d_fg1;
+  int2 *d_hdr1;
+  float *d_bev_h, *d_bev_rf, *d_bev_cf;  // [n_cells] each
   c2g_view *d_presort;
   c2g_scan_head *d_heads;
   c2g_view *d_views;

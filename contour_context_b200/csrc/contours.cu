@@ -50,9 +50,10 @@ constexpr int K2_THREADS = 512;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_CTAS_PER_SM = 2;
 constexpr int PLANE_WORDS = 800;  // n_row * ceil(n_col / 32) (checked by make_params): 150 x 5 = 750 for both shipped configs
-constexpr int R_POOL = 5120;      // runs of all six levels that fit in shared memory (else: global arena)
-constexpr int C_POOL = 1408;      // components of all six levels that fit in shared memory (else: global arena)
+constexpr int R_POOL = 4096;      // runs of all six levels that fit in shared memory (else: global arena)
+constexpr int C_POOL = 960;       // components of all six levels that fit in shared memory (else: global arena)
 constexpr int NVL = 1024;         // significant components (area >= min_cont_cell_cnt) per level
+constexpr int FG_CAP = 2048;       // foreground cells whose (height, row_f, col_f) are staged in shared memory (else: read from global)
 constexpr int KEY_LIST_CAP = 400; // cells of one key window that can lie inside the 9.99-cell radius
 constexpr int N_ANCH = C2G_NLEV * C2G_MAX_PIV;
 constexpr int N_DIVS = 35;
@@ -82,10 +83,12 @@ struct Smem {
       uint32_t key[NVL];   // (rank of the parent << 16) | first-2x2-block key
       uint16_t comp[NVL];
     } sig;                 // ranking step
+    float fg_h[FG_CAP];    // moments: heights of the foreground cells
   };
+  float fg_rf[FG_CAP], fg_cf[FG_CAP];  // continuous coordinates of the foreground cells (moments, key windows)
   union {
     uint32_t run_par[R_POOL];  // union-find parent (run id); after the flatten: root id; finally 0x80000000 | component
-    unsigned char bci_scratch[K2_WARPS * 736];
+    unsigned char bci_scratch[K2_WARPS * 896];
   };
   union {
     uint32_t run_inf[R_POOL];  // row | c0 << 8 | len << 16
@@ -101,7 +104,7 @@ struct Smem {
   TopView top[C2G_NLEV][C2G_MAX_DIST_FIRSTS];
   int cnt_point[N_ANCH];
   int n_ell[C2G_NUM_BIN_LAYERS];
-  int nsig, status, n_occ, wq, next_scan;
+  int nsig, status, n_occ, n_fg, wq, wq2, next_scan;
   int runs_in_arena, comps_in_arena, arena;  // arena: this CTA's global overflow arena (= blockIdx.x) when in use, -1 = not used
   double red[K2_WARPS];
 };
@@ -371,6 +374,7 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
     if (tid == 0) {
       S.status = 0;
       S.n_occ = hdr_in[b].x;
+      S.n_fg = hdr_in[b].y;
       S.arena = -1;
       S.runs_in_arena = 0;
       S.comps_in_arena = 0;
@@ -383,7 +387,16 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
     }
     __syncthreads();
     C2G_DBG(1);
-    // the warps that do not label (12..15) index the foreground list meanwhile: exclusive prefix of the plane-0 popcounts
+    // the warps that do not label stage the continuous coordinates of the foreground cells (12 B x ~1 100 cells) meanwhile;
+    // a scan with more than FG_CAP such cells reads them from global memory instead
+    const bool fg_smem = S.n_fg <= FG_CAP;
+    if (warp > 2 * C2G_NLEV && fg_smem)
+      for (int i = tid - (2 * C2G_NLEV + 1) * 32; i < S.n_fg; i += (K2_WARPS - 2 * C2G_NLEV - 1) * 32) {
+        const float4 rec = __ldg(fg + i);
+        S.fg_rf[i] = rec.y;
+        S.fg_cf[i] = rec.z;
+      }
+    // ... and one of them indexes the list: exclusive prefix of the plane-0 popcounts
     if (warp == 2 * C2G_NLEV) {
       int base = 0;
       for (int w0 = 0; w0 < nwords; w0 += 32) {
@@ -699,7 +712,7 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
       // ---------------- phase C: per-level std::sort replays + moments / calcStatVals per component ------------------
       // moment tasks by decreasing size class floor(log2(area)): the four components a warp walks together are alike
       if (tid < 16) S.cls_cnt[tid] = 0;
-      if (tid == 0) S.wq = 0;
+      if (tid == 0) S.wq = S.wq2 = 0;
       __syncthreads();
       for (int v = tid; v < total_views; v += K2_THREADS) atomicAdd(&S.cls_cnt[__clz(S.sortbuf[v] >> 16) - 16], 1);
       __syncthreads();
@@ -715,45 +728,69 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
       for (int v = tid; v < total_views; v += K2_THREADS) S.torder[atomicAdd(&S.cls_cnt[__clz(S.sortbuf[v] >> 16) - 16], 1)] = (uint16_t) v;
       __syncthreads();
       // sortbuf words of one level are (area << 16 | rank): sorting them in place is the std::sort of cont_views_[level]
-      // (contour_mng.h:596-599); one lane per level, on six different warps
-      if (lane == 0 && half == 0 && lvl_warp) {
+      // (contour_mng.h:596-599).  One WARP per level replays libstdc++'s introsort cooperatively (stdsort.cuh: same permutation as
+      // the serial replay, which was the critical path of this kernel); the ranking scratch is dead and serves as its work space.
+      if (half == 0 && lvl_warp) {
         uint32_t *first = S.sortbuf + S.view_off[lev_w];
+        const int n = S.n_views[lev_w];
         int sum = 0;
-        for (int i = 0; i < S.n_views[lev_w]; ++i) sum += (int) (first[i] >> 16);
-        S.layer_cnt[lev_w] = sum;
-        c2g_sort::std_sort(first, (long) S.n_views[lev_w], [](uint32_t a, uint32_t bb) { return (a >> 16) > (bb >> 16); });
+        for (int i = lane; i < n; i += 32) sum += (int) (first[i] >> 16);
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (lane == 0) S.layer_cnt[lev_w] = sum;
+        uint16_t *scr = reinterpret_cast<uint16_t *>(&S.wpre[0][0]);
+        static_assert(sizeof(S.wpre) >= 2 * C2G_VIEW_CAP * sizeof(uint16_t), "sort scratch");
+        c2g_sort::warp_std_sort<true>(first, n, scr + S.view_off[lev_w], scr + C2G_VIEW_CAP + S.view_off[lev_w], lane);
         C2G_DBG(20);
       }
-      __syncwarp();
+      __syncthreads();
+      if (fg_smem)  // ... and then takes the heights of the foreground cells
+        for (int i = tid; i < S.n_fg; i += K2_THREADS) S.fg_h[i] = __ldg(fg + i).x;
+      __syncthreads();
       {
-        // Moments: eight lanes per component, four components per warp step, handed out from a shared counter. Lane k of a
-        // group keeps ONE accumulator of RunningStatRecorder: sum of a_k * b_k over the member cells in raster order with
-        // (a, b) = (v0,1) (v1,1) (v0,v0) (v0,v1) (v1,v1) (h,v0) (h,v1); x * 1.0 is exact, the product of two floats is exact in
-        // double, so every lane performs exactly the reference's sequence of double additions.  Lane 7 sums the heights in
-        // float.  The runs of a component are found by scanning the run ids between its first and last run, eight
-        // candidates per step (one per lane of the group).
+        // Moments + calcStatVals.  Every accumulator of RunningStatRecorder is a sequential sum over the component's cells in
+        // raster order (bit-exactness: exactly the reference's sequence of double additions; x * 1.0 is exact, the product of two
+        // floats is exact in double), so a component offers at most eight-way parallelism: its eight accumulators.  The runs of a
+        // component are found by scanning the run ids between its first and last run; a run's cells are a contiguous slice of the
+        // foreground list.  Views are taken in decreasing size class (torder):
+        //  * the n_big views of >= 64 cells: EIGHT LANES per component, lane k keeps accumulator k (sum of a_k * b_k with
+        //    (a, b) = (v0,1) (v1,1) (v0,v0) (v0,v1) (v1,v1) (h,v0) (h,v1), lane 7 the float sum of h), the group tests eight run ids
+        //    per step and keeps four loads in flight; four components per warp step;
+        //  * the long tail of small views: ONE LANE per component with all accumulators (seven independent chains) - the lanes of a
+        //    warp walk components of similar size, so the nested run / cell loops diverge little.  (One lane per component for the
+        //    big ones too was measured: the warp holding the 32 largest components ran 5x longer than the rest of the phase.)
+        // (height, row_f, col_f) of foreground cell i = ph[i * fs], prf[i * fs], pcf[i * fs]: the shared-memory copies (stride 1) or,
+        // for a scan with more than FG_CAP foreground cells, the global records (stride 4 floats)
+        const float *gfg = reinterpret_cast<const float *>(fg);
+        const int fs = fg_smem ? 1 : 4;
+        const float *ph = fg_smem ? S.fg_h : gfg, *prf = fg_smem ? S.fg_rf : gfg + 1, *pcf = fg_smem ? S.fg_cf : gfg + 2;
+        auto view_level = [&](int v) {
+          int lev = 0;
+#pragma unroll
+          for (int l = 1; l < C2G_NLEV; ++l)
+            if (v >= S.view_off[l]) lev = l;
+          return lev;
+        };
+        const int n_big = min(S.cls_cnt[9], total_views);  // size classes 0..9 = areas >= 64 (cls_cnt holds the class END offsets now)
         const int k8 = lane & 7, g4 = lane >> 3;
-        const float *pa = (k8 == 0 || k8 == 2 || k8 == 3) ? rfg : (k8 == 1 || k8 == 4) ? cfp : hg;
-        const float *pb = (k8 == 2 || k8 == 5) ? rfg : cfp;
+        const float *pa = (k8 == 0 || k8 == 2 || k8 == 3) ? prf : (k8 == 1 || k8 == 4) ? pcf : ph;
+        const float *pb = (k8 == 2 || k8 == 5) ? prf : pcf;
         const bool b_one = k8 == 0 || k8 == 1 || k8 == 7;
         while (true) {
           int t0 = 0;
           if (lane == 0) t0 = atomicAdd(&S.wq, 4);
           t0 = __shfl_sync(FULL, t0, 0);
-          if (t0 >= total_views) break;
+          if (t0 >= n_big) break;
           const int t = t0 + g4;
-          bool active = t < total_views;
-          int v = 0;
+          bool active = t < n_big;
+          int v = 0, lev = 0;
           uint32_t ci = 0, rid = 0, last = 0;
           const uint32_t *rp = RP, *ri = RI;
+          const uint32_t *cw = CWP;
           if (active) {
             v = S.torder[t];
-            int lev = 0;
-#pragma unroll
-            for (int l = 1; l < C2G_NLEV; ++l)
-              if (v >= S.view_off[l]) lev = l;
+            lev = view_level(v);
             ci = S.vcomp[v];
-            const uint32_t *cw = CWP + ((size_t) S.comp_off[lev] + ci) * CW;
+            cw = CWP + ((size_t) S.comp_off[lev] + ci) * CW;
             rid = cw[0] >> 16;
             last = cw[1] >> 16;
             rp = RP + S.run_off[lev];
@@ -770,14 +807,16 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
               const int tt = __ffs(gb) - 1;
               gb &= gb - 1;
               const uint32_t inf = ri[rid + tt];
-              const int cell = (int) (inf & 255) * ncol + (int) ((inf >> 8) & 255), len = (inf >> 16) & 255;
+              const int row = (int) (inf & 255), c0 = (int) ((inf >> 8) & 255), len = (int) ((inf >> 16) & 255);
+              const int wd = row * WPR + (c0 >> 5);
+              const int cell0 = (int) S.fgpre[wd] + __popc(S.plane[0][wd] & ((1u << (c0 & 31)) - 1u));
               for (int j0 = 0; j0 < len; j0 += 4) {  // four independent loads in flight; a padding term adds 0 * 1 = +0.0
                 float va[4], vb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const bool in = j0 + u < len;
-                  va[u] = in ? pa[cell + j0 + u] : 0.0f;
-                  vb[u] = (in && !b_one) ? pb[cell + j0 + u] : 1.0f;
+                  va[u] = in ? pa[(cell0 + j0 + u) * fs] : 0.0f;
+                  vb[u] = (in && !b_one) ? pb[(cell0 + j0 + u) * fs] : 1.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -789,48 +828,103 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
             rid += 8;
             if (rid > last) active = false;
           }
-          // raw moments go to the component's (still unused) 80-byte presort record: doubles 0..6 from lanes 0..6 of the
-          // group, the float height sum in word 14
-          if (t < total_views) {
-            double *raw = reinterpret_cast<double *>(presort + v);
-            if (k8 < 7)
-              raw[k8] = acc;
-            else
-              reinterpret_cast<float *>(raw + 7)[0] = vol3;
+          // lane 0 of the group collects the eight accumulators and finishes the view
+          Moments m;
+          m.s0 = __shfl_sync(FULL, acc, g4 * 8 + 0);
+          m.s1 = __shfl_sync(FULL, acc, g4 * 8 + 1);
+          m.t00 = __shfl_sync(FULL, acc, g4 * 8 + 2);
+          m.t01 = __shfl_sync(FULL, acc, g4 * 8 + 3);
+          m.t11 = __shfl_sync(FULL, acc, g4 * 8 + 4);
+          m.q0 = __shfl_sync(FULL, acc, g4 * 8 + 5);
+          m.q1 = __shfl_sync(FULL, acc, g4 * 8 + 6);
+          m.vol3 = __shfl_sync(FULL, vol3, g4 * 8 + 7);
+          if (k8 == 0 && t < n_big) {
+            m.cnt = (int) (cw[0] & 0xFFFFu);
+            const uint32_t linf = ri[last];
+            c2g_view vw;
+            calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
+            presort[v] = vw;
+          }
+        }
+        __syncwarp();
+        while (true) {
+          int t0 = 0;
+          if (lane == 0) t0 = atomicAdd(&S.wq2, 32);
+          t0 = __shfl_sync(FULL, t0, 0) + n_big;
+          if (t0 >= total_views) break;
+          const int t = t0 + lane;
+          const bool have = t < total_views;
+          int v = 0, lev = 0;
+          uint32_t ci = 0, id = 1, last = 0;
+          const uint32_t *rp = RP, *ri = RI, *cw = CWP;
+          if (have) {
+            v = S.torder[t];
+            lev = view_level(v);
+            ci = S.vcomp[v];
+            cw = CWP + ((size_t) S.comp_off[lev] + ci) * CW;
+            id = cw[0] >> 16;  // the first run of a component is one of its own
+            last = cw[1] >> 16;
+            rp = RP + S.run_off[lev];
+            ri = RI + S.run_off[lev];
+          }
+          Moments m;
+          m.cnt = have ? (int) (cw[0] & 0xFFFFu) : 0;
+          m.s0 = m.s1 = m.t00 = m.t01 = m.t11 = m.q0 = m.q1 = 0.0;
+          m.vol3 = 0.0f;
+          // One flat loop instead of the nested run / cell loops: in every step each lane either consumes ONE cell of its current run
+          // or moves on to its next member run, so the lanes of the warp advance together whatever the shapes of their components
+          // (nested loops made the warp execute the union of all lanes' trip counts: 3.6 active lanes on average).
+          int cell = 0, left = 0;  // next foreground-list index / cells left in the current run
+          bool busy = have;
+          while (__any_sync(FULL, busy)) {
+            if (busy && left == 0) {
+              while (id <= last && (rp[id] & 0x7FFFFFFFu) != ci) ++id;
+              if (id > last)
+                busy = false;
+              else {
+                const uint32_t inf = ri[id];
+                const int row = (int) (inf & 255), c0 = (int) ((inf >> 8) & 255);
+                const int wd = row * WPR + (c0 >> 5);
+                left = (int) ((inf >> 16) & 255);
+                cell = (int) S.fgpre[wd] + __popc(S.plane[0][wd] & ((1u << (c0 & 31)) - 1u));
+                ++id;
+              }
+            }
+            if (busy) {
+              const float h = ph[cell * fs];
+              const double v0 = (double) prf[cell * fs], v1 = (double) pcf[cell * fs], hh = (double) h;
+              m.s0 += v0;
+              m.s1 += v1;
+              m.t00 += v0 * v0;
+              m.t01 += v0 * v1;
+              m.t11 += v1 * v1;
+              m.q0 += hh * v0;
+              m.q1 += hh * v1;
+              m.vol3 += h;
+              ++cell;
+              --left;
+            }
+          }
+          if (have) {
+            const uint32_t linf = ri[last];
+            c2g_view vw;
+            calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
+            presort[v] = vw;
           }
         }
       }
       C2G_DBG(21);
+      if (dbg && blockIdx.x == 0 && lane == 0) dbg[32 + warp] = clock64();
       __syncthreads();
+      if (dbg && blockIdx.x == 0 && lane == 0) dbg[48 + warp] = clock64();
       C2G_DBG(4);
-      for (int v = tid; v < total_views; v += K2_THREADS) {
-        int lev = 0;
-#pragma unroll
-        for (int l = 1; l < C2G_NLEV; ++l)
-          if (v >= S.view_off[l]) lev = l;
-        const uint32_t *cw = CWP + ((size_t) S.comp_off[lev] + S.vcomp[v]) * CW;
-        const uint32_t linf = (RI + S.run_off[lev])[cw[1] >> 16];
-        const double *raw = reinterpret_cast<const double *>(presort + v);
-        Moments m;
-        m.cnt = (int) (cw[0] & 0xFFFFu);
-        m.s0 = raw[0];
-        m.s1 = raw[1];
-        m.t00 = raw[2];
-        m.t01 = raw[3];
-        m.t11 = raw[4];
-        m.q0 = raw[5];
-        m.q1 = raw[6];
-        m.vol3 = reinterpret_cast<const float *>(raw + 7)[0];
-        c2g_view vw;
-        calc_stat_vals(m, cfg, lev, (int) (linf & 255), (int) ((linf >> 8) & 255) + (int) ((linf >> 16) & 255) - 1, vw);
-        presort[v] = vw;  // in place: this thread is the only reader and writer of the record
-      }
     };
     if (S.runs_in_arena || S.comps_in_arena)
       stage2(std::true_type{});
     else
       stage2(std::false_type{});
     __syncthreads();
+    C2G_DBG(24);
     {
       // copy 80-byte records as 20 x 4-byte words: sorted position j of level l <- presort index (sortbuf & 0xFFFF)
       const uint32_t *src = reinterpret_cast<const uint32_t *>(presort);
@@ -844,6 +938,7 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
           dst[(size_t) (off + j) * WPV + wd] = src[(size_t) from * WPV + wd];
         }
       }
+      C2G_DBG(22);
       // compact GMM ellipse next to every view of the levels the GMM-L2 stages use (1..4)
       {
         const int e0 = S.view_off[1], e1 = S.view_off[C2G_NUM_BIN_LAYERS] + S.n_views[C2G_NUM_BIN_LAYERS];
@@ -866,6 +961,7 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
           eout[v] = e;
         }
       }
+      C2G_DBG(23);
       for (int i = tid; i < C2G_NLEV * C2G_MAX_DIST_FIRSTS; i += K2_THREADS) {
         const int lev = i / C2G_MAX_DIST_FIRSTS, j = i % C2G_MAX_DIST_FIRSTS;
         TopView t;
@@ -898,46 +994,54 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
         const int r_cen = (int) cx, c_cen = (int) cy;
         const int r_min = max(0, r_cen - roi_pad), r_max = min(nrow - 1, r_cen + roi_pad);
         const int c_min = max(0, c_cen - roi_pad), c_max = min(ncol - 1, c_cen + roi_pad);
-        const int w = c_max - c_min + 1, total = w * (r_max - r_min + 1);
+        const int nr = r_max - r_min + 1, wbits = c_max - c_min + 1;  // <= 23 x 23 (roi_radius <= 10, checked at c2g_create)
         const double rad = (double) cfg.roi_radius - 1e-2;
-        int rr = r_min, cc = c_min + lane;  // lane's cell inside the window, advanced by 32 cells per step without divisions
-        while (cc > c_max) {
-          cc -= w;
-          ++rr;
+        // One lane per window ROW: the row's cells above lv_grads[1] are the set bits of plane 1 inside the column range
+        // (cells with bev == lv_grads[1] pass the reference's first test `bev < lv_grads[1] -> skip` but fail its second one,
+        // `bev > lv_grads[1]`), so only those ~2-5 cells per row are looked at instead of all 529 window cells.  Raster order
+        // of the list = row-major: a warp-wide exclusive scan of the per-row counts places every row's cells.
+        const int rr = r_min + lane;
+        uint32_t m1 = 0;  // bit i: cell (rr, c_min + i) is above lv_grads[1]
+        if (lane < nr) {
+          const int w0 = c_min >> 5, sh = c_min & 31;
+          const uint32_t *p1 = S.plane[1] + rr * WPR;
+          const uint64_t two = (uint64_t) p1[w0] | ((uint64_t) (w0 + 1 < WPR ? p1[w0 + 1] : 0u) << 32);
+          m1 = (uint32_t) (two >> sh) & (wbits >= 32 ? FULL : ((1u << wbits) - 1u));
         }
-        for (int base = 0; base < total; base += 32) {
-          bool pass = false;
-          float dist = 0.f;
-          uint8_t hc = 0;
-          if (rr <= r_max) {
-            const int wd = rr * WPR + (cc >> 5), sh = cc & 31;
-            if ((S.plane[1][wd] >> sh) & 1u) {  // bev > lv_grads[1]  (cells with bev == lv_grads[1] pass the first test but fail this one)
-              const int c = rr * ncol + cc;
-              const float dx = rfg[c] - cx, dy = cfp[c] - cy;
-              dist = sqrtf(dx * dx + dy * dy);
-              if ((double) dist < rad) {
-                pass = true;
-                int h2 = 1;
+        auto cell_rec = [&](int i) -> float4 {  // foreground record of window column i of this lane's row (.y, .z valid)
+          const int cc = c_min + i, wd = rr * WPR + (cc >> 5);
+          const int fi = (int) S.fgpre[wd] + __popc(S.plane[0][wd] & ((1u << (cc & 31)) - 1u));
+          if (fg_smem) return make_float4(0.f, S.fg_rf[fi], S.fg_cf[fi], 0.f);
+          return __ldg(fg + fi);
+        };
+        uint32_t pm = 0;  // ... and lies inside the radius
+        for (uint32_t m = m1; m; m &= m - 1) {
+          const int i = __ffs(m) - 1;
+          const float4 rec = cell_rec(i);
+          const float dx = rec.y - cx, dy = rec.z - cy;
+          const float dist = sqrtf(dx * dx + dy * dy);
+          if ((double) dist < rad) pm |= 1u << i;
+        }
+        const int mine = __popc(pm);
+        int incl = mine;
 #pragma unroll
-                for (int l = 2; l < C2G_NLEV; ++l) h2 += (int) ((S.plane[l][wd] >> sh) & 1u);
-                hc = (uint8_t) h2;
-              }
-            }
-          }
-          const unsigned bal = __ballot_sync(FULL, pass);
-          if (pass) {
-            const int pos = cnt + __popc(bal & lt_mask);
-            if (pos < KEY_LIST_CAP) {
-              klist_dist[a * KEY_LIST_CAP + pos] = dist;
-              klist_hc[a * KEY_LIST_CAP + pos] = hc;
-            }
-          }
-          cnt += __popc(bal);
-          cc += 32;
-          while (cc > c_max) {
-            cc -= w;
-            ++rr;
-          }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += t;
+        }
+        cnt = __shfl_sync(FULL, incl, 31);
+        int pos = incl - mine;
+        for (uint32_t m = pm; m; m &= m - 1, ++pos) {
+          const int i = __ffs(m) - 1;
+          if (pos >= KEY_LIST_CAP) break;
+          const float4 rec = cell_rec(i);
+          const float dx = rec.y - cx, dy = rec.z - cy;
+          const int cc = c_min + i, wd = rr * WPR + (cc >> 5), sh = cc & 31;
+          int h2 = 1;
+#pragma unroll
+          for (int l = 2; l < C2G_NLEV; ++l) h2 += (int) ((S.plane[l][wd] >> sh) & 1u);
+          klist_dist[a * KEY_LIST_CAP + pos] = sqrtf(dx * dx + dy * dy);
+          klist_hc[a * KEY_LIST_CAP + pos] = (uint8_t) h2;
         }
         if (cnt > KEY_LIST_CAP && lane == 0) atomicOr(&S.status, 4);
       }
@@ -1041,11 +1145,12 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
     // candidate t = bl * 10 + j (reference loop order) is evaluated by lane t % 32; kept neighbours are compacted in
     // that order, lane 0 replays std::sort on bit_pos and builds the run boundaries, all lanes write the record.
     {
-      unsigned char *scr = S.bci_scratch + warp * 736;  // the run tables are dead: [40] relpt, [40] u32, [42] u16
+      unsigned char *scr = S.bci_scratch + warp * 896;  // the run tables are dead: [40] relpt, [40] u32, [42] u16, 2 x [40] u16 sort scratch
       c2g_relpt *nei = reinterpret_cast<c2g_relpt *>(scr);
       uint32_t *ord = reinterpret_cast<uint32_t *>(scr + C2G_MAX_NEI * sizeof(c2g_relpt));
       uint16_t *segv = reinterpret_cast<uint16_t *>(scr + C2G_MAX_NEI * (sizeof(c2g_relpt) + 4));
-      static_assert(C2G_MAX_NEI * (sizeof(c2g_relpt) + 4) + (C2G_MAX_NEI + 2) * 2 <= 736, "BCI scratch");
+      uint16_t *sortL = segv + (C2G_MAX_NEI + 2), *sortR = sortL + C2G_MAX_NEI;
+      static_assert(C2G_MAX_NEI * (sizeof(c2g_relpt) + 4) + (C2G_MAX_NEI + 2) * 2 + 2 * C2G_MAX_NEI * 2 <= 896, "BCI scratch");
       for (int a = warp; a < N_ANCH; a += K2_WARPS) {
         const int ll = a / C2G_MAX_PIV, seq = a % C2G_MAX_PIV;
         if (seq >= piv) continue;
@@ -1088,10 +1193,10 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
           }
         }
         __syncwarp();
+        c2g_sort::warp_std_sort<false>(ord, n, sortL, sortR, lane);  // std::sort on bit_pos (contour_mng.h:871-874), the whole warp
         int nseg = 0;
         uint64_t bins[4] = {0, 0, 0, 0};
         if (lane == 0) {
-          c2g_sort::std_sort(ord, (long) n, [](uint32_t x, uint32_t y) { return (x >> 16) < (y >> 16); });
           if (n > 0) {
             segv[nseg++] = 0;
             for (int p1 = 0; p1 < n; ++p1) {
@@ -1198,6 +1303,33 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
 
 }  // namespace
 
+// test hook: the warp-cooperative std::sort replay on `n` packed words (one warp, shared memory like in the contour kernel)
+namespace {
+template <bool DESC>
+__global__ void warp_sort_selftest_kernel(uint32_t *words, int n) {
+  extern __shared__ __align__(16) unsigned char ws_raw[];
+  uint32_t *a = reinterpret_cast<uint32_t *>(ws_raw);
+  uint16_t *pl = reinterpret_cast<uint16_t *>(a + n), *pr = pl + n;
+  for (int i = threadIdx.x; i < n; i += 32) a[i] = words[i];
+  __syncwarp();
+  c2g_sort::warp_std_sort<DESC>(a, n, pl, pr, threadIdx.x);
+  for (int i = threadIdx.x; i < n; i += 32) words[i] = a[i];
+}
+}  // namespace
+int c2g_launch_warp_sort_selftest(uint32_t *words_dev, int n, int desc, cudaStream_t stream) {
+  const size_t smem = (size_t) n * 8 + 16;
+  if (smem > 200 * 1024) return -1000;
+  if (desc) {
+    C2G_CUDA_TRY(cudaFuncSetAttribute(warp_sort_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    warp_sort_selftest_kernel<true><<<1, 32, smem, stream>>>(words_dev, n);
+  } else {
+    C2G_CUDA_TRY(cudaFuncSetAttribute(warp_sort_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    warp_sort_selftest_kernel<false><<<1, 32, smem, stream>>>(words_dev, n);
+  }
+  C2G_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 size_t c2g_contour_smem_bytes() { return sizeof(Smem); }
 int c2g_contour_max_ctas(int num_sms) { return K2_CTAS_PER_SM * num_sms; }
 // layout of the global scratch: [max_ctas][KLIST_BYTES] key-window lists | [max_ctas] overflow arenas (one per resident CTA: a batch of
@@ -1206,10 +1338,9 @@ size_t c2g_contour_scratch_bytes(int num_sms, int n_cells, int n_row) {
   return (size_t) c2g_contour_max_ctas(num_sms) * (KLIST_BYTES + arena_bytes(n_cells, n_row));
 }
 
-int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int B,
-                        const C2gIngestParams &P, const int *int_ids_dev, int first_slot, float *bev_h, float *bev_rf,
-                        float *bev_cf, c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells,
-                        unsigned char *k2_scratch, int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
+int c2g_launch_contours(const C2gBevOut &bev, int B, const C2gIngestParams &P, const int *int_ids_dev, int first_slot,
+                        c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells, unsigned char *k2_scratch,
+                        int *work_counter, int num_sms, cudaStream_t stream, long long *dbg) {
   static unsigned long long attr_devs = 0ull;
   if (c2g_first_use_on_device(attr_devs)) {
     C2G_CUDA_TRY(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(Smem)));
@@ -1222,9 +1353,8 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
   unsigned char *arenas = k2_scratch + (size_t) max_ctas * KLIST_BYTES;
   static const int force_arena = getenv("C2G_K2_FORCE_ARENA") ? atoi(getenv("C2G_K2_FORCE_ARENA")) : 0;  // measurement / test hook
   C2G_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), stream));
-  contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, B, P, int_ids_dev, first_slot, bev_h,
-                                                             bev_rf, bev_cf, presort_scratch, heads, views, ells, klists, arenas, force_arena,
-                                                             work_counter, dbg);
+  contour_kernel<<<grid, K2_THREADS, sizeof(Smem), stream>>>(bev.planes, bev.fg, bev.hdr, B, P, int_ids_dev, first_slot, presort_scratch, heads, views,
+                                                             ells, klists, arenas, force_arena, work_counter, dbg);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1234,7 +1364,7 @@ int c2g_launch_contours(const c2g_cellkey *tiles, const float *pts_dev, const lo
 // `offsets[b]` is read on the device: the offsets of the last batch live there.
 namespace {
 __global__ void bev_fill_entry(const c2g_cellkey *tile, const float4 *pts, const long long *offsets, int b, C2gIngestParams P,
-                               float *bev_h, float *bev_rf, float *bev_cf) {
+                               float *bev_h, float *bev_rf, float *bev_cf) {  // tile: ONE scan (the full-tile scatter variant's output)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.n_cells) return;
   const float4 *p = pts + offsets[b];

@@ -180,3 +180,139 @@ C2G_HD void std_sort(T *first, long n, Cmp comp) {
 }
 
 }  // namespace c2g_sort
+
+#ifdef __CUDACC__
+// ---- warp-cooperative replay of the same std::sort ----------------------------------------------------------------------------
+// One lane replaying libstdc++'s introsort spends ~100 cycles per element move (dependent shared-memory reads and branches); six
+// such lanes were the critical path of the contour kernel in round 1.  The algorithm has a data-parallel reading that gives the
+// SAME permutation:
+//  * __unguarded_partition(first + 1, last, pivot at first): the left scan stops exactly at the elements x with !comp(x, pivot)
+//    ("left stoppers", ascending positions L_0 < L_1 < ..), the right scan at the elements with !comp(pivot, x) ("right stoppers",
+//    descending positions R_0 > R_1 > .., the pivot's own slot included).  Neither scan ever looks at a swapped slot again, so the
+//    k-th swap exchanges L_k and R_k for all k < K = #{k : L_k < R_k}, and the returned cut is min(L_K, R_{K-1}) (L_0 if K = 0).
+//    Stopper ranks come from ballots, the swaps are disjoint and run in parallel.  (Checked against the serial loop on 2e5
+//    tie-heavy inputs; tests/test_stdsort.py compares the whole replay with the real std::sort.)
+//  * __final_insertion_sort is a STABLE sort of whatever arrangement the partition phase left, and no element leaves its final
+//    segment of <= 16 slots (or its heap-sorted range), so the final slot of element i is
+//    max(i - 15, 0) + #{j in [i - 15, i + 15] : a_j before a_i, or equivalent to it with j < i}.
+// Elements are packed words (key << 16 | payload), DESC = larger key first; `a`, `posL`, `posR` are in shared memory (n entries
+// each); called by all 32 lanes of a warp.  Ranges of more than 128 elements (cluttered scans only) finish with the serial
+// insertion sort on one lane; the depth-limit heapsort fallback is serial too.
+namespace c2g_sort {
+
+template <bool DESC>
+__device__ __forceinline__ bool w_before(uint32_t x, uint32_t y) {
+  return DESC ? (x >> 16) > (y >> 16) : (x >> 16) < (y >> 16);
+}
+
+template <bool DESC>
+__device__ void warp_std_sort(uint32_t *a, int n, uint16_t *posL, uint16_t *posR, int lane) {
+  constexpr unsigned FULLW = 0xFFFFFFFFu;
+  const unsigned lt = (1u << lane) - 1u;
+  auto cmp = [](uint32_t x, uint32_t y) { return w_before<DESC>(x, y); };
+  if (n <= 1) return;
+  if (n > 16) {
+    int lg = 31 - __clz(n);
+    int st_lo[40], st_hi[40], st_d[40];  // at most one frame per level of the depth limit (2 lg n <= 22)
+    int sp = 0;
+    st_lo[0] = 0;
+    st_hi[0] = n;
+    st_d[0] = 2 * lg;
+    sp = 1;
+    while (sp > 0) {
+      --sp;
+      int lo = st_lo[sp], hi = st_hi[sp], depth = st_d[sp];
+      while (hi - lo > 16) {
+        if (depth == 0) {
+          if (lane == 0) heap_sort(a + lo, a + hi, cmp);
+          __syncwarp();
+          break;
+        }
+        --depth;
+        if (lane == 0) move_median_to_first(a + lo, a + lo + 1, a + lo + (hi - lo) / 2, a + hi - 1, cmp);
+        __syncwarp();
+        const uint32_t p = a[lo];
+        int nL = 0, nR = 0;
+        for (int c0 = lo + 1; c0 < hi; c0 += 32) {  // left stoppers, ascending
+          const int i = c0 + lane;
+          const bool is = i < hi && !w_before<DESC>(a[i], p);
+          const unsigned m = __ballot_sync(FULLW, is);
+          if (is) posL[lo + nL + __popc(m & lt)] = (uint16_t) i;
+          nL += __popc(m);
+        }
+        for (int c0 = 0; c0 < hi - lo; c0 += 32) {  // right stoppers, descending (the pivot's slot `lo` is the sentinel)
+          const int j = hi - 1 - (c0 + lane);
+          const bool is = j >= lo && !w_before<DESC>(p, a[j]);
+          const unsigned m = __ballot_sync(FULLW, is);
+          if (is) posR[lo + nR + __popc(m & lt)] = (uint16_t) j;
+          nR += __popc(m);
+        }
+        __syncwarp();
+        int K = 0;
+        const int nm = nL < nR ? nL : nR;
+        for (int k0 = 0; k0 < nm; k0 += 32) {  // L_k < R_k holds for a prefix of k
+          const int k = k0 + lane;
+          const unsigned m = __ballot_sync(FULLW, k < nm && posL[lo + k] < posR[lo + k]);
+          K += __popc(m);
+          if (m != FULLW) break;
+        }
+        int cut;
+        if (K > 0) {
+          cut = posR[lo + K - 1];
+          if (K < nL && (int) posL[lo + K] < cut) cut = posL[lo + K];
+        } else
+          cut = posL[lo];
+        for (int k = lane; k < K; k += 32) {
+          const int i = posL[lo + k], j = posR[lo + k];
+          const uint32_t t = a[i];
+          a[i] = a[j];
+          a[j] = t;
+        }
+        __syncwarp();
+        st_lo[sp] = lo;  // the left part waits on the stack, the right part is processed next (any order gives the same result)
+        st_hi[sp] = cut;
+        st_d[sp] = depth;
+        ++sp;
+        lo = cut;
+      }
+    }
+  }
+  if (n > 128) {  // __final_insertion_sort, serial
+    if (lane == 0) {
+      if (n > 16) {
+        insertion_sort(a, a + 16, cmp);
+        for (uint32_t *i = a + 16; i != a + n; ++i) unguarded_linear_insert(i, cmp);
+      } else
+        insertion_sort(a, a + n, cmp);
+    }
+    __syncwarp();
+    return;
+  }
+  uint32_t v[4];
+  int r[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    v[q] = 0u;
+    r[q] = -1;
+    if (i < n) {
+      const uint32_t x = a[i];
+      const int w0 = i - 15 > 0 ? i - 15 : 0, w1 = i + 16 < n ? i + 16 : n;
+      int rank = w0;
+      for (int j = w0; j < w1; ++j) {
+        const uint32_t y = a[j];
+        rank += (w_before<DESC>(y, x) || (!w_before<DESC>(x, y) && j < i)) ? 1 : 0;
+      }
+      v[q] = x;
+      r[q] = rank;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (r[q] >= 0) a[r[q]] = v[q];
+  __syncwarp();
+}
+
+}  // namespace c2g_sort
+#endif  // __CUDACC__

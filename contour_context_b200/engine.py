@@ -80,6 +80,17 @@ class Engine:
         capi.check(capi.lib().c2g_get_bev(self.h, batch_index, capi.ptr(b), capi.ptr(r), capi.ptr(c)), "c2g_get_bev")
         return b, r, c
 
+    def bev_compact(self, batch_index: int, full_tile_variant: bool = False):
+        """Scatter -> contour kernel hand-off of one scan of the last batch: (planes [NLEV, n_row, ceil(n_col/32)] uint32,
+        fg [n_fg, 4] float32 = (height, row_f, col_f, 0) in raster order, n_occupied)."""
+        wpr = (self.cm_cfg.n_col + 31) // 32
+        planes = np.zeros((D.NLEV, self.cm_cfg.n_row, wpr), np.uint32)
+        fg = np.zeros((self.n_cells, 4), np.float32)
+        hdr = np.zeros(2, np.int32)
+        capi.check(capi.lib().c2g_get_bev_compact(self.h, batch_index, int(full_tile_variant), capi.ptr(planes), capi.ptr(fg),
+                                                  capi.ptr(hdr)), "c2g_get_bev_compact")
+        return planes, fg[: int(hdr[1])].copy(), int(hdr[0])
+
     def tiles(self, batch_index: int):
         t = np.empty(self.n_cells, np.uint64)
         capi.check(capi.lib().c2g_get_tiles(self.h, batch_index, capi.ptr(t)), "c2g_get_tiles")

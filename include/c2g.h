@@ -59,16 +59,24 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
 int c2g_host_alloc(void **out, size_t bytes);
 int c2g_host_free(void *p);
 
-/* Individual stages of c2g_ingest for profiling and parity tests (same arguments; `first_slot` as above). */
+/* First stage of c2g_ingest alone (the BEV scatter kernel: makeBEV, contour_mng.h:505-556), for profiling and parity tests. */
 int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device);
+/* What the scatter kernel hands to the contour kernel for scan `batch_index` of the last batch (parity tests): the six
+ * bit-planes `bev > lv_grads[l]` (cv::threshold of makeContourRecursiveHelper, src/cont2/contour_mng.cpp:283; C2G_NLEV x n_row x
+ * ceil(n_col / 32) words, bit c & 31 of word r * ceil(n_col / 32) + (c >> 5)), the cells above the lowest threshold in raster
+ * order as (height, row_f, col_f, 0) (bev_ + bev_pixfs_, contour_mng.h:435,528-529; fg_host must hold 4 * n_row * n_col floats)
+ * and hdr_host[2] = (occupied cells = bev_pixfs_.size(), foreground cells).  full_tile_variant != 0: recomputed by the full-tile
+ * variant of the kernel (the one behind c2g_get_bev), which must agree bit for bit with the production variant. */
+int c2g_get_bev_compact(c2g_ctx *ctx, int batch_index, int full_tile_variant, unsigned int *planes_host, float *fg_host, int *hdr_host);
 
 /* Read back (synchronises the stream): ContourManager getters (include/cont2/contour_mng.h:1052-1106). */
 int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host);
 int c2g_get_views(c2g_ctx *ctx, int slot, c2g_view *out_host /* C2G_VIEW_CAP records */);
 /* Dense BEV of scan `batch_index` of the LAST ingest batch: ContourManager::getBevImage (:573-586) plus the
  * continuous pillar coordinates bev_pixfs_ (:435); empty cells are -1000 / -1 / -1. Each array holds n_row*n_col.
- * The image is assembled on demand from the batch's cell keys and its points (the ingest kernels only materialise the
- * cells that belong to a contour), so a device-resident points buffer handed to the last c2g_ingest must still be alive. */
+ * The image is produced on demand by re-running the scatter kernel's full-tile variant on that one scan (the ingest
+ * kernels only materialise the cells above the lowest threshold), so a device-resident points buffer handed to the last
+ * c2g_ingest must still be alive. */
 int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *col_f);
 /* Raw 64-bit BEV cell keys of the last batch (debug / K1 parity). */
 int c2g_get_tiles(c2g_ctx *ctx, int batch_index, unsigned long long *out_host);
@@ -177,6 +185,8 @@ int c2g_work_counters(c2g_ctx *ctx, int enable, unsigned long long *out_host);
 /* Host-side replay of libstdc++ std::sort used by the kernels (tests only): sorts `n` packed (key << 16 | index)
  * words with comparator key-descending (desc != 0) or key-ascending. */
 int c2g_selftest_stdsort(unsigned int *words, int n, int desc);
+/* The warp-cooperative replay of the same std::sort that the contour kernel runs (csrc/stdsort.cuh), on the device (tests only). */
+int c2g_selftest_warpsort(c2g_ctx *ctx, unsigned int *words, int n, int desc);
 
 #ifdef __cplusplus
 }

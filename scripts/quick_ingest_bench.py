@@ -52,4 +52,9 @@ fine = {10:'B1 count+barrier',12:'decide+B2 records',13:'B3 unions',14:'B4 flatt
 prev = clk[1]
 for i in [10,12,13,14,15,16,2,18,19]:
     print(f"    {fine[i]:18s} +{(clk[i]-prev)/1e3:.1f} kcyc"); prev = clk[i]
+print(f"    after-moments barrier -> lambda exit +{(clk[24]-clk[4])/1e3:.1f}; view copy +{(clk[22]-clk[24])/1e3:.1f}; ellipse table +{(clk[23]-clk[22])/1e3:.1f}; top + barrier +{(clk[5]-clk[23])/1e3:.1f} kcyc")
 print(f"    ranks +{(clk[3]-clk[19])/1e3:.1f}; torder+sort(level 0) +{(clk[20]-clk[3])/1e3:.1f}; warp0 moments done +{(clk[21]-clk[20])/1e3:.1f}; barrier +{(clk[4]-clk[21])/1e3:.1f} kcyc")
+
+print("per-warp arrival at the after-moments barrier (kcyc after 'ranks done'):", [round(float(clk[32 + w] - clk[3]) / 1e3, 1) for w in range(16)])
+print("per-warp departure from it                                            :", [round(float(clk[48 + w] - clk[3]) / 1e3, 1) for w in range(16)])
+print("DBG(4), DBG(24) rel:", round(float(clk[4]-clk[3])/1e3,1), round(float(clk[24]-clk[3])/1e3,1))

@@ -40,6 +40,44 @@ def test_bev_bit_exact(engine, oracle, n_pts):
         assert grf.tobytes() == orf.tobytes() and gcf.tobytes() == ocf.tobytes(), f"scan {b}: pillar coords differ"
 
 
+def _compact_from_dense(cfg, bev, rf, cf):
+    """What the scatter kernel must hand to the contour kernel, derived from the oracle's dense BEV."""
+    n_row, n_col = cfg.n_row, cfg.n_col
+    wpr = (n_col + 31) // 32
+    h = bev.reshape(n_row, n_col)
+    planes = np.zeros((D.NLEV, n_row, wpr), np.uint32)
+    for lev in range(D.NLEV):
+        rows, cols = np.nonzero(h > np.float32(cfg.lv_grads[lev]))
+        np.bitwise_or.at(planes[lev], (rows, cols >> 5), (np.uint32(1) << (cols & 31).astype(np.uint32)))
+    fgm = (h > np.float32(cfg.lv_grads[0])).reshape(-1)
+    fg = np.stack([bev[fgm], rf[fgm], cf[fgm], np.zeros(int(fgm.sum()), np.float32)], axis=1).astype(np.float32)
+    return planes, fg, int((bev > -999.0).sum())
+
+
+def test_scatter_handoff_planes_and_foreground_list(engine, oracle):
+    """K1's output (bit-planes, raster-ordered foreground list, occupied count) against the oracle's BEV, for the production
+    variant (low points only mark occupancy) and the full-tile variant behind c2g_get_bev; ragged / NaN / tie inputs included."""
+    base, _ = make_batch([20, 23], [0, 1], 70000)
+    scans = [base[:70000], base[70000:], base[:3000].copy(), base[:9000].copy(), base[:17].copy()]
+    scans[2][::5, 0] = np.nan
+    scans[3][:, 2] = np.round(scans[3][:, 2] * 2) / 2    # many exact height ties -> first point in file order wins
+    scans[4][:, :2] = 500.0                               # empty BEV
+    pts = np.ascontiguousarray(np.concatenate(scans))
+    offsets = np.cumsum([0] + [len(s) for s in scans]).astype(np.int64)
+    engine.ingest_bev_only(pts, offsets)
+    n_fg_total = 0
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        ob, orf, ocf = s.bev()
+        planes, fg, n_occ = _compact_from_dense(engine.cm_cfg, ob, orf, ocf)
+        for full in (False, True):
+            gp, gf, gocc = engine.bev_compact(b, full_tile_variant=full)
+            assert gocc == n_occ, (b, full, gocc, n_occ)
+            assert gp.tobytes() == planes.tobytes(), f"scan {b} full={full}: bit-planes differ"
+            assert gf.shape == fg.shape and gf.tobytes() == fg.tobytes(), f"scan {b} full={full}: foreground list differs"
+        n_fg_total += len(fg)
+    assert n_fg_total > 2000
+
+
 def test_views_keys_bci(engine, oracle):
     seeds, visits = [10, 10, 11, 12, 13, 13], [0, 1, 0, 0, 2, 3]
     pts, offsets = make_batch(seeds, visits, 120000)

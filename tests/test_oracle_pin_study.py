@@ -1,0 +1,39 @@
+"""CPU-only: bounds on the two restated third-party pieces that no reference-held vector pins (oracle/pin_study.py):
+the Eigen 2x2 self-adjoint solver against exact arithmetic, the L-BFGS refinement against two independent scipy optimisers.
+Reduced sample sizes; `python -m oracle.pin_study` runs the full ones (>= 10^6 matrices, >= 200 problems)."""
+import pytest
+
+
+@pytest.fixture(scope="module")
+def study(oracle):
+    from oracle import pin_study
+
+    return pin_study
+
+
+def test_eig2f_against_exact_arithmetic(study):
+    r = study.eig_study(n_total=120_000, n_scans=8)
+    assert r["compared"] > 100_000 and r["real_matrices"] > 2000
+    # backward stable: every eigenvalue within a few float ulps OF THE MATRIX SCALE of the exact one ...
+    assert r["eig_rel_err_max"] < 6e-7
+    # ... hence the dominant eigenvalue (key[0]) within a handful of ulps of its own magnitude
+    assert r["eig_ulp_max"]["lambda1"] <= 8
+    # the smaller one is clamped to point_sigma for most contours (thin shapes); where it survives it is accurate too
+    assert r["clamped_frac"] > 0.5
+    assert r["eig_ulp_max"]["lambda0_unclamped"] <= 64
+    # what a different-but-correct 2x2 solver could change in the retrieval keys: a few ulp in a minority of the entries
+    assert max(r["key_ulp_max"]) <= 16
+    assert max(r["key_bits_differ_frac"]) < 0.2
+
+
+def test_lbfgs_refinement_against_scipy(study):
+    r = study.refine_study(n_scenes=16)
+    assert r["problems"] >= 20
+    assert r["restated_solver_never_above_converged"]
+    # 10 iterations of the restated solver land on the converged optimum of an independent BFGS for almost every problem
+    assert r["gap_to_converged_optimum"]["median"] < 1e-8
+    assert r["gap_to_converged_optimum"]["max"] < 0.05
+    assert r["abs_dcorr_vs_scipy_bfgs_10it"]["p90"] < 1e-4
+    # the solver run inside the query path is the same solver (start = the candidate's constellation transform)
+    assert r["query_result_equals_standalone_solve_max_abs"] < 1e-6
+    assert r["decision_flips_at_thres"]["vs_converged"] <= max(1, r["problems"] // 20)
