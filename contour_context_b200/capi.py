@@ -37,6 +37,7 @@ def lib():
         L.c2g_set_stream.argtypes = [vp, vp]
         L.c2g_sync.argtypes = [vp]
         L.c2g_ingest.argtypes = [vp, vp, vp, ip, ip, ip, vp]
+        L.c2g_ingest_xyz.argtypes = [vp, vp, vp, ip, ip, ip, vp]
         L.c2g_ingest_bev_only.argtypes = [vp, vp, vp, ip, ip]
         L.c2g_get_heads.argtypes = [vp, ip, ip, vp]
         L.c2g_get_views.argtypes = [vp, ip, vp]

@@ -36,6 +36,18 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
   return r;
 }
 
+// XYZ layout (12 B per point, the separately reported input variant of SURVEY.md 8f-4: the intensity the path never reads is
+// dropped on the host): three 32-bit loads per point; consecutive lanes read consecutive points, so the three loads of a warp
+// cover the same 384 contiguous bytes and the second and third hit in L1.
+template <bool XYZ>
+__device__ __forceinline__ float4 ld_point(const float *base, long long i) {
+  if (XYZ) {
+    const float *q = base + 3 * i;
+    return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f);
+  }
+  return ld_stream_f4(reinterpret_cast<const float4 *>(base) + i);
+}
+
 // What one point asks of the tile: `key` != 0: raise cell `ix` to `key`; `obit` != 0: mark bit `obit` of occupancy word `ix`
 // (a point is one or the other, a rejected point neither).
 struct PointOp {
@@ -88,9 +100,9 @@ __device__ __forceinline__ void apply_op(const PointOp &op, c2g_cellkey *tile, u
   }
 }
 
-template <bool UNIT, bool LOWFILTER>
+template <bool UNIT, bool LOWFILTER, bool XYZ>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P, C2gBevOut out,
+bev_scatter_kernel(const float *__restrict__ pts, const long long *__restrict__ offsets, int B, C2gIngestParams P, C2gBevOut out,
                    int *__restrict__ work_counter, int variant) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,7 +132,7 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
     if (tid == 0) s_nstash = 0;  // (ordered before its uses by the barrier that ends the main loop)
     const long long beg = offsets[b];
     const int n = (int) (offsets[b + 1] - beg);
-    const float4 *p = pts + beg;
+    const float *p = pts + (XYZ ? 3 : 4) * beg;
     int i = tid;
     // main loop: UNROLL independent 128-bit loads per thread before any of them is consumed; then the cell / key of all UNROLL
     // points (straight-line code), then all filter reads of the tile, then the atomics: the shared-memory latencies of the
@@ -128,7 +140,7 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
     for (; i + (K1_UNROLL - 1) * K1_THREADS < n; i += K1_UNROLL * K1_THREADS) {
       float4 v[K1_UNROLL];
 #pragma unroll
-      for (int u = 0; u < K1_UNROLL; ++u) v[u] = ld_stream_f4(p + i + u * K1_THREADS);
+      for (int u = 0; u < K1_UNROLL; ++u) v[u] = ld_point<XYZ>(p, i + u * K1_THREADS);
       PointOp op[K1_UNROLL];
       uint32_t cur[K1_UNROLL];  // height word of a high point's cell (upper half of the 64-bit key) / occupancy word of a low point
 #pragma unroll
@@ -156,7 +168,7 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
         if (LOWFILTER && (op[u].obit & ~cur[u])) atomicOr(occ + op[u].ix, op[u].obit);  // obit == 0 for high points
       }
     }
-    for (; i < n; i += K1_THREADS) apply_op<LOWFILTER>(point_op<UNIT, LOWFILTER>(ld_stream_f4(p + i), (uint32_t) i, P, lv_min, wpr), tile, occ);
+    for (; i < n; i += K1_THREADS) apply_op<LOWFILTER>(point_op<UNIT, LOWFILTER>(ld_point<XYZ>(p, i), (uint32_t) i, P, lv_min, wpr), tile, occ);
     __syncthreads();
     if (variant & 4) {  // experiment: main loop only (outputs are garbage)
       for (int c = tid; c < ncell; c += K1_THREADS) tile[c] = 0ull;
@@ -245,7 +257,8 @@ bev_scatter_kernel(const float4 *__restrict__ pts, const long long *__restrict__
     {
       float4 *fg = out.fg + (size_t) b * ncell;
       auto emit = [&](c2g_cellkey k, int wd, int bit) {
-        const float2 xy = __ldg(reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k)));
+        const float *q = p + (size_t) (XYZ ? 3 : 4) * (0xFFFFFFFFu - (uint32_t) k);
+        const float2 xy = make_float2(__ldg(q), __ldg(q + 1));
         float4 rec;
         rec.x = c2g_from_orderable((uint32_t) (k >> 32));
         // pointToContRowCol (contour_mng.h:468-472): x / reso + n_row / 2 - 0.5f, left to right in float
@@ -293,15 +306,15 @@ size_t k1_smem_bytes(int ncell, int nwords) {
          (size_t) K1_STASH * (2 + sizeof(c2g_cellkey)) + 16;
 }
 
-template <bool UNIT, bool LOWFILTER>
-int launch_variant(const float4 *pts, const long long *offsets, int B, const C2gIngestParams &P, const C2gBevOut &out, int *work_counter, int grid,
+template <bool UNIT, bool LOWFILTER, bool XYZ>
+int launch_variant(const float *pts, const long long *offsets, int B, const C2gIngestParams &P, const C2gBevOut &out, int *work_counter, int grid,
                    size_t smem, cudaStream_t stream) {
   static unsigned long long attr_devs = 0ull;
   if (c2g_first_use_on_device(attr_devs))
-    C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<UNIT, LOWFILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    C2G_CUDA_TRY(cudaFuncSetAttribute(bev_scatter_kernel<UNIT, LOWFILTER, XYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int) k1_smem_bytes(C2G_MAX_CELLS, 800)));
   static const int variant = getenv("C2G_K1_VARIANT") ? atoi(getenv("C2G_K1_VARIANT")) : 0;  // measurement hook
-  bev_scatter_kernel<UNIT, LOWFILTER><<<grid, K1_THREADS, smem, stream>>>(pts, offsets, B, P, out, work_counter, variant);
+  bev_scatter_kernel<UNIT, LOWFILTER, XYZ><<<grid, K1_THREADS, smem, stream>>>(pts, offsets, B, P, out, work_counter, variant);
   return 0;
 }
 
@@ -310,7 +323,7 @@ int launch_variant(const float4 *pts, const long long *offsets, int B, const C2g
 // host launcher (called from c2g_api.cu).  full_tile != 0: the complete 64-bit tile is written to out.tiles as well (dense-image
 // getters); otherwise only the bit-planes, the foreground list and the counts.
 int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P, const C2gBevOut &out,
-                           int full_tile, int *work_counter, int num_sms, cudaStream_t stream) {
+                           int full_tile, int xyz, int *work_counter, int num_sms, cudaStream_t stream) {
   const int nwords = P.cfg.n_row * ((P.cfg.n_col + 31) / 32);
   const size_t smem = k1_smem_bytes(P.n_cells, nwords);
   const int grid = B < num_sms ? B : num_sms;
@@ -319,24 +332,18 @@ int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, i
   // the fast path needs: unit resolution, symmetric padded bounds, and bounds that keep floor(x) + n/2 inside the image
   const bool unit = P.cfg.reso_row == 1.0f && P.cfg.reso_col == 1.0f && P.x_min_pad == -P.x_max_pad && P.y_min_pad == -P.y_max_pad &&
                     P.x_max_pad < (float) P.half_row && P.y_max_pad < (float) P.half_col;
-  const float4 *p4 = (const float4 *) pts_dev;
   static const int lowfilter = getenv("C2G_K1_LOWFILTER") ? atoi(getenv("C2G_K1_LOWFILTER")) : 0;  // measurement hook (header comment)
-  if (!lowfilter && !full_tile) {  // production: the key path for every point, no tile write
-    C2gBevOut o2 = out;
-    o2.tiles = nullptr;
-    int rc2 = unit ? launch_variant<true, false>(p4, offsets_dev, B, P, o2, work_counter, grid, smem, stream)
-                   : launch_variant<false, false>(p4, offsets_dev, B, P, o2, work_counter, grid, smem, stream);
-    if (rc2) return rc2;
-    C2G_CUDA_TRY(cudaGetLastError());
-    return 0;
-  }
+  C2gBevOut o = out;
+  if (!full_tile) o.tiles = nullptr;  // production: bit-planes, foreground list and counts only
   int rc;
-  if (unit)
-    rc = full_tile ? launch_variant<true, false>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream)
-                   : launch_variant<true, true>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream);
+#define C2G_K1_GO(U, L, X) launch_variant<U, L, X>(pts_dev, offsets_dev, B, P, o, work_counter, grid, smem, stream)
+  if (lowfilter && !full_tile && !xyz)
+    rc = unit ? C2G_K1_GO(true, true, false) : C2G_K1_GO(false, true, false);
+  else if (xyz)
+    rc = unit ? C2G_K1_GO(true, false, true) : C2G_K1_GO(false, false, true);
   else
-    rc = full_tile ? launch_variant<false, false>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream)
-                   : launch_variant<false, true>(p4, offsets_dev, B, P, out, work_counter, grid, smem, stream);
+    rc = unit ? C2G_K1_GO(true, false, false) : C2G_K1_GO(false, false, false);
+#undef C2G_K1_GO
   if (rc) return rc;
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -14,8 +14,8 @@
 
 // launchers implemented in the kernel translation units
 int c2g_launch_bev_scatter(const float *pts_dev, const long long *offsets_dev, int B, const C2gIngestParams &P, const C2gBevOut &out,
-                           int full_tile, int *work_counter, int num_sms, cudaStream_t stream);
-int c2g_launch_bev_fill(const c2g_cellkey *tile1, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
+                           int full_tile, int xyz, int *work_counter, int num_sms, cudaStream_t stream);
+int c2g_launch_bev_fill(const c2g_cellkey *tile1, const float *pts_dev, const long long *offsets_dev, int b, int fpp, const C2gIngestParams &P,
                         float *bev_h, float *bev_rf, float *bev_cf, cudaStream_t stream);
 int c2g_launch_contours(const C2gBevOut &bev, int B, const C2gIngestParams &P, const int *int_ids_dev, int first_slot,
                         c2g_view *presort_scratch, c2g_scan_head *heads, c2g_view *views, c2g_ell *ells, unsigned char *k2_scratch,
@@ -100,19 +100,19 @@ C2gBevOut bev_out(const c2g_ctx *ctx, int b0) {
   return o;
 }
 
-int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, const float **pts_dev) {
+int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int fpp, const float **pts_dev) {
   if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch) return C2G_ERR_ARG;
   const long long total = offsets_host[B] - offsets_host[0];
   if (total < 0) return C2G_ERR_ARG;
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_offsets, offsets_host, sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (pts_on_device) {
-    if (((uintptr_t) pts) & 15) return C2G_ERR_ARG;
+    if (((uintptr_t) pts) & (fpp == 4 ? 15 : 3)) return C2G_ERR_ARG;
     *pts_dev = pts;
   } else {
     if (offsets_host[B] > ctx->max_points) return C2G_ERR_CAPACITY;
     // staging buffer 0 may still be the target of an earlier pipelined ingest's copy stream or be read by its kernels
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free[0], 0));
-    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage2[0], pts, sizeof(float) * 4 * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
+    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_pts_stage2[0], pts, sizeof(float) * fpp * (size_t) offsets_host[B], cudaMemcpyHostToDevice, ctx->stream));
     *pts_dev = ctx->d_pts_stage2[0];
   }
   return 0;
@@ -326,13 +326,13 @@ int c2g_sync(c2g_ctx *ctx) {
   return 0;
 }
 
-int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device) {
+static int bev_only_impl(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int fpp) {
   if (!ctx) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);
   const float *pts_dev = nullptr;
-  int rc = stage_inputs(ctx, pts, offsets_host, B, pts_on_device, &pts_dev);
+  int rc = stage_inputs(ctx, pts, offsets_host, B, pts_on_device, fpp, &pts_dev);
   if (rc) return rc;
-  rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, bev_out(ctx, 0), 0, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
+  rc = c2g_launch_bev_scatter(pts_dev, ctx->d_offsets, B, ctx->P, bev_out(ctx, 0), 0, fpp == 3, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
   if (rc) return rc;
   // the staging buffer is free again once the kernel that reads it has run (a later c2g_get_bev of this batch is ordered
   // behind it on the same stream; a later pipelined ingest waits for this event before its copy stream overwrites the buffer)
@@ -340,13 +340,18 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
   ctx->launches += 1;
   ctx->last_B = B;
   ctx->last_pts = pts_dev;
+  ctx->last_fpp = fpp;
   return 0;
+}
+
+int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device) {
+  return bev_only_impl(ctx, pts, offsets_host, B, pts_on_device, 4);
 }
 
 // Host inputs: the batch is cut into chunks of one wave (num_sms scans); chunk k+1 crosses PCIe on the copy stream while the
 // kernels of chunk k run, and the two staging buffers alternate between calls so that the copy of the NEXT call starts while
 // this call's query kernels are still running.  Device inputs: two launches for the whole batch.
-static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *ids_dev) {
+static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *ids_dev, int fpp) {
   if (offsets_host[B] - offsets_host[0] > ctx->max_points) return C2G_ERR_CAPACITY;
   const int cur = ctx->stage_sel;
   ctx->stage_sel ^= 1;
@@ -362,12 +367,12 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
   for (int b0 = 0; b0 < B; b0 += CH, ++k) {
     const int n = (B - b0 < CH) ? (B - b0) : CH;
     const size_t p0 = (size_t) rel[b0], p1 = (size_t) rel[b0 + n];
-    C2G_CUDA_TRY(cudaMemcpyAsync(stage + 4 * p0, pts + 4 * ((size_t) offsets_host[0] + p0), sizeof(float) * 4 * (p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
+    C2G_CUDA_TRY(cudaMemcpyAsync(stage + fpp * p0, pts + fpp * ((size_t) offsets_host[0] + p0), sizeof(float) * fpp * (p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
     cudaEvent_t ev = ctx->ev_chunk[k % C2G_MAX_CHUNK_EVENTS];
     C2G_CUDA_TRY(cudaEventRecord(ev, ctx->copy_stream));
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
     const C2gBevOut bo = bev_out(ctx, b0);
-    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, bo, 0, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
+    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, bo, 0, fpp == 3, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
     if (rc) return rc;
     rc = c2g_launch_contours(bo, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
                              ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
@@ -377,11 +382,12 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
   C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[cur], ctx->stream));
   ctx->last_B = B;
   ctx->last_pts = stage;
+  ctx->last_fpp = fpp;
   return 0;
 }
 
-int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
-               const int *int_ids_host) {
+static int ingest_impl(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
+                       const int *int_ids_host, int fpp) {
   if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);
   const int *ids_dev = nullptr;
@@ -389,14 +395,24 @@ int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, in
     C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids, int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
     ids_dev = ctx->d_int_ids;
   }
-  if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev);
-  int rc = c2g_ingest_bev_only(ctx, pts, offsets_host, B, pts_on_device);
+  if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev, fpp);
+  int rc = bev_only_impl(ctx, pts, offsets_host, B, pts_on_device, fpp);
   if (rc) return rc;
   rc = c2g_launch_contours(bev_out(ctx, 0), B, ctx->P, ids_dev, first_slot, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_k2_scratch,
                            ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
+}
+
+int c2g_ingest(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int pts_on_device, int first_slot,
+               const int *int_ids_host) {
+  return ingest_impl(ctx, pts, offsets_host, B, pts_on_device, first_slot, int_ids_host, 4);
+}
+
+int c2g_ingest_xyz(c2g_ctx *ctx, const float *xyz, const long long *offsets_host, int B, int pts_on_device, int first_slot,
+                   const int *int_ids_host) {
+  return ingest_impl(ctx, xyz, offsets_host, B, pts_on_device, first_slot, int_ids_host, 3);
 }
 
 int c2g_get_heads(c2g_ctx *ctx, int first_slot, int n, c2g_scan_head *out_host) {
@@ -425,7 +441,8 @@ static int rescatter_full(c2g_ctx *ctx, int batch_index) {
   o.fg = ctx->d_fg1;
   o.hdr = ctx->d_hdr1;
   o.tiles = ctx->d_tile1;
-  int rc = c2g_launch_bev_scatter(ctx->last_pts, ctx->d_offsets + batch_index, 1, ctx->P, o, 1, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
+  int rc = c2g_launch_bev_scatter(ctx->last_pts, ctx->d_offsets + batch_index, 1, ctx->P, o, 1, ctx->last_fpp == 3, ctx->d_work_counter_k1, ctx->num_sms,
+                                  ctx->stream);
   if (rc) return rc;
   ctx->launches += 1;
   return 0;
@@ -437,7 +454,8 @@ int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *
   const size_t n = ctx->P.n_cells;
   int rc = rescatter_full(ctx, batch_index);
   if (rc) return rc;
-  rc = c2g_launch_bev_fill(ctx->d_tile1, ctx->last_pts, ctx->d_offsets, batch_index, ctx->P, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf, ctx->stream);
+  rc = c2g_launch_bev_fill(ctx->d_tile1, ctx->last_pts, ctx->d_offsets, batch_index, ctx->last_fpp, ctx->P, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf,
+                           ctx->stream);
   if (rc) return rc;
   ctx->launches += 1;
   if (bev) C2G_CUDA_TRY(cudaMemcpyAsync(bev, ctx->d_bev_h, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));

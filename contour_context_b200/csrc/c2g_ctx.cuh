@@ -63,6 +63,7 @@ struct c2g_ctx {
   unsigned char *d_k2_scratch;  // contour kernel: per resident CTA key-window lists + overflow arenas (contours.cu)
   const float *last_pts;
   int last_B;
+  int last_fpp;  // floats per point of the last batch: 4 (KITTI .bin layout) or 3 (c2g_ingest_xyz)
   long long launches;
   // query buffers
   C2gLayerTable layers[C2G_NUM_Q_LEVELS_MAX];

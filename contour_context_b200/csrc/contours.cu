@@ -1363,15 +1363,16 @@ int c2g_launch_contours(const C2gBevOut &bev, int B, const C2gIngestParams &P, c
 // occupied cell gets its height and the winner's continuous coordinates, empty cells the reference's initial values.
 // `offsets[b]` is read on the device: the offsets of the last batch live there.
 namespace {
-__global__ void bev_fill_entry(const c2g_cellkey *tile, const float4 *pts, const long long *offsets, int b, C2gIngestParams P,
+__global__ void bev_fill_entry(const c2g_cellkey *tile, const float *pts, const long long *offsets, int b, int fpp, C2gIngestParams P,
                                float *bev_h, float *bev_rf, float *bev_cf) {  // tile: ONE scan (the full-tile scatter variant's output)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.n_cells) return;
-  const float4 *p = pts + offsets[b];
+  const float *p = pts + (size_t) fpp * offsets[b];  // fpp: floats per point (4 = KITTI .bin layout, 3 = xyz)
   const c2g_cellkey k = tile[c];
   float h = -1000.0f, rf = -1.0f, cf = -1.0f;
   if (k != 0ull) {
-    const float2 xy = *reinterpret_cast<const float2 *>(p + (0xFFFFFFFFu - (uint32_t) k));
+    const float *q = p + (size_t) fpp * (0xFFFFFFFFu - (uint32_t) k);
+    const float2 xy = make_float2(q[0], q[1]);
     h = c2g_from_orderable((uint32_t) (k >> 32));
     rf = (xy.x / P.cfg.reso_row + P.half_row_f) - 0.5f;
     cf = (xy.y / P.cfg.reso_col + P.half_col_f) - 0.5f;
@@ -1381,9 +1382,9 @@ __global__ void bev_fill_entry(const c2g_cellkey *tile, const float4 *pts, const
   bev_cf[c] = cf;
 }
 }  // namespace
-int c2g_launch_bev_fill(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int b, const C2gIngestParams &P,
+int c2g_launch_bev_fill(const c2g_cellkey *tiles, const float *pts_dev, const long long *offsets_dev, int b, int fpp, const C2gIngestParams &P,
                         float *bev_h, float *bev_rf, float *bev_cf, cudaStream_t stream) {
-  bev_fill_entry<<<(P.n_cells + 255) / 256, 256, 0, stream>>>(tiles, (const float4 *) pts_dev, offsets_dev, b, P, bev_h, bev_rf, bev_cf);
+  bev_fill_entry<<<(P.n_cells + 255) / 256, 256, 0, stream>>>(tiles, pts_dev, offsets_dev, b, fpp, P, bev_h, bev_rf, bev_cf);
   C2G_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -25,6 +25,7 @@ namespace {
 __device__ const uint64_t rf_exp_tab[256] = C2G_EXP_TAB_INIT;
 
 constexpr int RF_MAX_WARPS = 4;
+constexpr int RF_TGT_CAP = 128;  // target ellipses of one level staged in shared memory by the pair pre-selection
 constexpr int RF_WARPS = 2;  // default warps per candidate (measured best of 1..4: 1.41 / 1.18 / 1.27 / 1.41 ms per 592-query batch) (one CTA each): the pair terms of one evaluation are split over 128 lanes, which
                              // shortens the sequential evaluation chain of the long problems that set the kernel's makespan
 
@@ -50,44 +51,98 @@ struct Prob {
 //   Sigma = 2 (R A R^T + B), mu = R a + t - b, f = K det(Sigma)^-1/2 exp(-1/2 mu^T Sigma^-1 mu), w = Sigma^-1 mu
 //   df/dt     = -f w
 //   df/dtheta = f (-1/2 tr(Sigma^-1 Sigma') - mu'^T w + 1/2 w^T Sigma' w),  Sigma' = 2 (J C + C J^T), mu' = J R a, J = [0 -1; 1 0]
+// everything of one pair term that does not depend on exp(): the term is coef * exp(qua)
+struct PairPre {
+  double qua, coef, q0, q1, gfac;
+};
+RF_FN PairPre rf_pair_pre(const c2g_ell &ea, const c2g_ell &eb, double c, double s, double ns, double x, double y) {
+  const double a00 = ea.c00, a10 = ea.c10, a01 = ea.c01, a11 = ea.c11, ax = ea.mx, ay = ea.my;
+  const double t00 = c * a00 + ns * a10, t01 = c * a01 + ns * a11;
+  const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
+  const double m00 = t00 * c + t01 * ns, m01 = t00 * s + t01 * c;
+  const double m10 = t10 * c + t11 * ns, m11 = t10 * s + t11 * c;
+  const double c00 = 2.0 * (m00 + (double) eb.c00), c10 = 2.0 * (m10 + (double) eb.c10);
+  const double c01 = 2.0 * (m01 + (double) eb.c01), c11 = 2.0 * (m11 + (double) eb.c11);
+  const double rax = c * ax + ns * ay, ray = s * ax + c * ay;
+  const double mux = rax + x - (double) eb.mx, muy = ray + y - (double) eb.my;
+  const double det = c00 * c11 - c10 * c01;
+  // det^-1/2 once (MUFU.RSQ64H + Newton) instead of the reference's 1/det, sqrt(det) and K/sqrt(det): three long-latency
+  // subroutines on the critical path of every pair term; the few-ulp difference is far below the solver's tolerances
+  const double rs = rsqrt(det);
+  const double invdet = rs * rs;
+  const double i00 = c11 * invdet, i10 = -c10 * invdet, i01 = -c01 * invdet, i11 = c00 * invdet;
+  const double r0 = -0.5 * mux, r1 = -0.5 * muy;
+  PairPre o;
+  o.q0 = r0 * i00 + r1 * i10;  // -1/2 mu^T Sigma^-1
+  o.q1 = r0 * i01 + r1 * i11;
+  o.qua = o.q0 * mux + o.q1 * muy;
+  o.coef = (-(double) eb.w * (double) ea.w) * rs;
+  const double wx = -2.0 * o.q0, wy = -2.0 * o.q1;
+  const double s00 = -2.0 * (m10 + m01), s01 = 2.0 * (m00 - m11);  // Sigma' = [s00 s01; s01 -s00]
+  const double tr = (i00 - i11) * s00 + (i01 + i10) * s01;
+  const double mpw = rax * wy - ray * wx;
+  const double quad = s00 * (wx * wx - wy * wy) + 2.0 * s01 * (wx * wy);
+  o.gfac = 0.5 * (quad - tr) - mpw;
+  return o;
+}
+
+// Two pairs per lane and step: the two terms are independent straight-line code up to their exp() (branch-free main path of the
+// glibc restatement, the rare special arguments are redone through the full function), so their FP64 latency chains overlap.
+// They are ADDED in the order of the one-pair-per-step loop, so the sums are bit-identical to it.
+template <int MODE>
+__device__ __forceinline__ void rf_eval_pairs(const Prob &P, double c, double s, double ns, double x, double y, double &fa, double &g0,
+                                              double &g1, double &g2) {
+  int i = P.lane;
+  for (; i + 32 < P.n_pairs; i += 64) {
+    const uint32_t pr0 = P.pairs[i], pr1 = P.pairs[i + 32];
+    const c2g_ell ea0 = P.se[pr0 >> 16], eb0 = P.te[pr0 & 0xFFFFu], ea1 = P.se[pr1 >> 16], eb1 = P.te[pr1 & 0xFFFFu];
+    const PairPre t0 = rf_pair_pre(ea0, eb0, c, s, ns, x, y), t1 = rf_pair_pre(ea1, eb1, c, s, ns, x, y);
+    double e0, e1;
+    if (MODE != 0) {
+      bool special = false;
+      e0 = c2g_exp_glibc_main<MODE == 2>(t0.qua, rf_exp_tab, &special);
+      e1 = c2g_exp_glibc_main<MODE == 2>(t1.qua, rf_exp_tab, &special);
+      if (special) {
+        e0 = c2g_exp(t0.qua, MODE, rf_exp_tab);
+        e1 = c2g_exp(t1.qua, MODE, rf_exp_tab);
+      }
+    } else {
+      e0 = exp(t0.qua);
+      e1 = exp(t1.qua);
+    }
+    const double f0 = t0.coef * e0, f1 = t1.coef * e1;
+    fa += f0;
+    g0 += (2.0 * f0) * t0.q0;  // -f w_x, w = -2 q
+    g1 += (2.0 * f0) * t0.q1;
+    g2 += f0 * t0.gfac;
+    fa += f1;
+    g0 += (2.0 * f1) * t1.q0;
+    g1 += (2.0 * f1) * t1.q1;
+    g2 += f1 * t1.gfac;
+  }
+  for (; i < P.n_pairs; i += 32) {
+    const uint32_t pr = P.pairs[i];
+    const c2g_ell ea = P.se[pr >> 16], eb = P.te[pr & 0xFFFFu];
+    const PairPre t = rf_pair_pre(ea, eb, c, s, ns, x, y);
+    const double f = t.coef * c2g_exp(t.qua, MODE, rf_exp_tab);
+    fa += f;
+    g0 += (2.0 * f) * t.q0;
+    g1 += (2.0 * f) * t.q1;
+    g2 += f * t.gfac;
+  }
+}
+
 __device__ __noinline__ D3 rf_eval(const Prob &P, const double p[3]) {
   const double c = cos(p[2]), s = sin(p[2]), ns = -s;
   const double x = p[0], y = p[1];
   ++*P.n_eval;
   double fa = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-  for (int i = P.lane; i < P.n_pairs; i += 32) {
-    const uint32_t pr = P.pairs[i];
-    const c2g_ell ea = P.se[pr >> 16], eb = P.te[pr & 0xFFFFu];
-    const double a00 = ea.c00, a10 = ea.c10, a01 = ea.c01, a11 = ea.c11, ax = ea.mx, ay = ea.my;
-    const double t00 = c * a00 + ns * a10, t01 = c * a01 + ns * a11;
-    const double t10 = s * a00 + c * a10, t11 = s * a01 + c * a11;
-    const double m00 = t00 * c + t01 * ns, m01 = t00 * s + t01 * c;
-    const double m10 = t10 * c + t11 * ns, m11 = t10 * s + t11 * c;
-    const double c00 = 2.0 * (m00 + (double) eb.c00), c10 = 2.0 * (m10 + (double) eb.c10);
-    const double c01 = 2.0 * (m01 + (double) eb.c01), c11 = 2.0 * (m11 + (double) eb.c11);
-    const double rax = c * ax + ns * ay, ray = s * ax + c * ay;
-    const double mux = rax + x - (double) eb.mx, muy = ray + y - (double) eb.my;
-    const double det = c00 * c11 - c10 * c01;
-    // det^-1/2 once (MUFU.RSQ64H + Newton) instead of the reference's 1/det, sqrt(det) and K/sqrt(det): three long-latency
-    // subroutines on the critical path of every pair term; the few-ulp difference is far below the solver's tolerances
-    const double rs = rsqrt(det);
-    const double invdet = rs * rs;
-    const double i00 = c11 * invdet, i10 = -c10 * invdet, i01 = -c01 * invdet, i11 = c00 * invdet;
-    const double r0 = -0.5 * mux, r1 = -0.5 * muy;
-    const double q0 = r0 * i00 + r1 * i10, q1 = r0 * i01 + r1 * i11;  // -1/2 mu^T Sigma^-1
-    const double qua = q0 * mux + q1 * muy;
-    const double f = ((-(double) eb.w * (double) ea.w) * rs) * c2g_exp(qua, P.exp_mode, rf_exp_tab);
-    fa += f;
-    const double f2 = 2.0 * f;
-    g0 += f2 * q0;  // -f w_x, w = -2 q
-    g1 += f2 * q1;
-    const double wx = -2.0 * q0, wy = -2.0 * q1;
-    const double s00 = -2.0 * (m10 + m01), s01 = 2.0 * (m00 - m11);  // Sigma' = [s00 s01; s01 -s00]
-    const double tr = (i00 - i11) * s00 + (i01 + i10) * s01;
-    const double mpw = rax * wy - ray * wx;
-    const double quad = s00 * (wx * wx - wy * wy) + 2.0 * s01 * (wx * wy);
-    g2 += f * (0.5 * (quad - tr) - mpw);
-  }
+  if (P.exp_mode == 2)
+    rf_eval_pairs<2>(P, c, s, ns, x, y, fa, g0, g1, g2);
+  else if (P.exp_mode == 1)
+    rf_eval_pairs<1>(P, c, s, ns, x, y, fa, g0, g1, g2);
+  else
+    rf_eval_pairs<0>(P, c, s, ns, x, y, fa, g0, g1, g2);
   for (int o = 16; o > 0; o >>= 1) {
     fa += __shfl_xor_sync(0xFFFFFFFFu, fa, o);
     g0 += __shfl_xor_sync(0xFFFFFFFFu, g0, o);
@@ -143,71 +198,137 @@ RF_FN double ipow(double x, int e) {
   return r;
 }
 
-// n x n (n <= 4) solve through LU with complete pivoting, rank cut at eps * n * max pivot (Eigen FullPivLU::solve)
-__device__ __noinline__ void lu_solve(double *A, double *b, int n, double *x) {
-  int rowT[4], colT[4];
-  int nonzero = n;
+// n x n (n <= 4) solve through LU with complete pivoting, rank cut at eps * n * max pivot (Eigen FullPivLU::solve).
+// N is a template parameter and every loop is unrolled, so the matrix lives in REGISTERS: the data-dependent pivot position only
+// selects which (compile-time) rows / columns are exchanged.  Same operations in the same order as the array version of round 1
+// (which kept A in local memory and cost 18 % of the refinement kernel's stall samples).
+template <int N>
+RF_FN void lu_solve_n(const double *Ain, const double *bin, double *x) {
+  double A[N][N], b[N];
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    b[r] = bin[r];
+#pragma unroll
+    for (int cc = 0; cc < N; ++cc) A[r][cc] = Ain[r * 4 + cc];
+  }
+  int rowT[N], colT[N];
+  int nonzero = N;
   double maxpivot = 0.0;
-  for (int k = 0; k < n; ++k) {
-    int br = k, bc = k;
-    double best = -1.0;
-    for (int cc = k; cc < n; ++cc)
-      for (int r = k; r < n; ++r)
-        if (fabs(A[r * 4 + cc]) > best) {
-          best = fabs(A[r * 4 + cc]);
-          br = r;
-          bc = cc;
-        }
-    if (best == 0.0) {
-      nonzero = k;
-      for (int i = k; i < n; ++i) rowT[i] = colT[i] = i;
-      break;
+  bool stopped = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (!stopped) {
+      int br = k, bc = k;
+      double best = -1.0;
+#pragma unroll
+      for (int cc = k; cc < N; ++cc)
+#pragma unroll
+        for (int r = k; r < N; ++r)
+          if (fabs(A[r][cc]) > best) {
+            best = fabs(A[r][cc]);
+            br = r;
+            bc = cc;
+          }
+      if (best == 0.0) {
+        nonzero = k;
+#pragma unroll
+        for (int i = k; i < N; ++i) rowT[i] = colT[i] = i;
+        stopped = true;
+      } else {
+        if (best > maxpivot) maxpivot = best;
+        rowT[k] = br;
+        colT[k] = bc;
+#pragma unroll
+        for (int r2 = k + 1; r2 < N; ++r2)
+          if (r2 == br) {
+#pragma unroll
+            for (int cc = 0; cc < N; ++cc) {
+              const double t = A[k][cc];
+              A[k][cc] = A[r2][cc];
+              A[r2][cc] = t;
+            }
+          }
+#pragma unroll
+        for (int c2 = k + 1; c2 < N; ++c2)
+          if (c2 == bc) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+              const double t = A[r][k];
+              A[r][k] = A[r][c2];
+              A[r][c2] = t;
+            }
+          }
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) A[r][k] /= A[k][k];
+#pragma unroll
+        for (int cc = k + 1; cc < N; ++cc)
+#pragma unroll
+          for (int r = k + 1; r < N; ++r) A[r][cc] -= A[r][k] * A[k][cc];
+      }
     }
-    if (best > maxpivot) maxpivot = best;
-    rowT[k] = br;
-    colT[k] = bc;
-    if (br != k)
-      for (int cc = 0; cc < n; ++cc) {
-        const double t = A[k * 4 + cc];
-        A[k * 4 + cc] = A[br * 4 + cc];
-        A[br * 4 + cc] = t;
-      }
-    if (bc != k)
-      for (int r = 0; r < n; ++r) {
-        const double t = A[r * 4 + k];
-        A[r * 4 + k] = A[r * 4 + bc];
-        A[r * 4 + bc] = t;
-      }
-    for (int r = k + 1; r < n; ++r) A[r * 4 + k] /= A[k * 4 + k];
-    for (int cc = k + 1; cc < n; ++cc)
-      for (int r = k + 1; r < n; ++r) A[r * 4 + cc] -= A[r * 4 + k] * A[k * 4 + cc];
   }
-  const double thr = 2.220446049250313e-16 * n;
+  const double thr = 2.220446049250313e-16 * N;
   int rank = 0;
-  for (int i = 0; i < nonzero; ++i) rank += (fabs(A[i * 4 + i]) > thr * maxpivot);
-  for (int i = 0; i < n; ++i) x[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < nonzero) rank += (fabs(A[i][i]) > thr * maxpivot);
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = 0.0;
   if (rank == 0) return;
-  for (int k = 0; k < n; ++k)
-    if (rowT[k] != k) {
-      const double t = b[k];
-      b[k] = b[rowT[k]];
-      b[rowT[k]] = t;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {  // b = P b: exchange b[k] and b[rowT[k]] (rowT[k] >= k)
+#pragma unroll
+    for (int r2 = k + 1; r2 < N; ++r2)
+      if (rowT[k] == r2) {
+        const double t = b[k];
+        b[k] = b[r2];
+        b[r2] = t;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) b[i] -= A[i][j] * b[j];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i)
+    if (i < rank) {
+#pragma unroll
+      for (int j = i + 1; j < N; ++j)
+        if (j < rank) b[i] -= A[i][j] * b[j];
+      b[i] /= A[i][i];
     }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < i; ++j) b[i] -= A[i * 4 + j] * b[j];
-  for (int i = rank - 1; i >= 0; --i) {
-    for (int j = i + 1; j < rank; ++j) b[i] -= A[i * 4 + j] * b[j];
-    b[i] /= A[i * 4 + i];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i >= rank) b[i] = 0.0;
+  int perm[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) perm[i] = i;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {  // perm[k] <-> perm[colT[k]] (colT[k] >= k)
+#pragma unroll
+    for (int c2 = k + 1; c2 < N; ++c2)
+      if (colT[k] == c2) {
+        const int t = perm[k];
+        perm[k] = perm[c2];
+        perm[c2] = t;
+      }
   }
-  for (int i = rank; i < n; ++i) b[i] = 0.0;
-  int perm[4];
-  for (int i = 0; i < n; ++i) perm[i] = i;
-  for (int k = 0; k < n; ++k) {
-    const int t = perm[k];
-    perm[k] = perm[colT[k]];
-    perm[colT[k]] = t;
-  }
-  for (int i = 0; i < n; ++i) x[perm[i]] = b[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (perm[i] == j) x[j] = b[i];
+}
+
+__device__ __noinline__ void lu_solve(double *A, double *b, int n, double *x) {
+  if (n == 4)
+    lu_solve_n<4>(A, b, x);
+  else if (n == 3)
+    lu_solve_n<3>(A, b, x);
+  else if (n == 2)
+    lu_solve_n<2>(A, b, x);
+  else if (n == 1)
+    lu_solve_n<1>(A, b, x);
 }
 
 // LineSearch::InterpolatingPolynomialMinimizingStepSize, CUBIC, two samples
@@ -564,6 +685,7 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
               int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results,
               unsigned long long *__restrict__ work) {
   __shared__ double red[RF_MAX_WARPS][4];
+  __shared__ float4 tgt_s[RF_TGT_CAP];
   const int n_warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wg = q0 * max_fine_opt + blockIdx.x;  // one (query, candidate rank) per CTA; the exits below are CTA-uniform
@@ -622,6 +744,45 @@ refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict
           if (pos < warp_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + lane);
         }
         n_pairs += __popc(m);
+      }
+    } else if (nt <= RF_TGT_CAP) {
+      // the level's target ellipses (mean, sigma) staged once per CTA as floats; the float test with a 1e-4 guard band decides
+      // all but borderline pairs, those take the exact double test.  Pair order as before: own sources ascending, targets ascending.
+      __syncthreads();  // the previous level's readers are done
+      for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        const c2g_ell b = te[to + i];
+        tgt_s[i] = make_float4(b.mx, b.my, b.maj, 0.f);
+      }
+      __syncthreads();
+      c2g_ell a_next;
+      if (warp < ns) a_next = se[so + warp];
+      for (int si = warp; si < ns; si += n_warps) {
+        const c2g_ell a = a_next;
+        if (si + n_warps < ns) a_next = se[so + si + n_warps];  // the next source's record travels while this one is tested
+        const double ax = (double) a.mx, ay = (double) a.my;
+        const double qx = (T[0] * ax + (-T[1]) * ay) + T[2], qy = (T[1] * ax + T[0] * ay) + T[3];
+        const float qxf = (float) qx, qyf = (float) qy;
+        for (int t0 = 0; t0 < nt; t0 += 32) {
+          const int ti = t0 + lane;
+          bool sel = false;
+          if (ti < nt) {
+            const float4 b = tgt_s[ti];
+            const float fx = qxf - b.x, fy = qyf - b.y;
+            const float d2 = fx * fx + fy * fy, yy = 3.0f * (a.maj + b.z), y2 = yy * yy;
+            if (d2 < y2 * 0.9999f)
+              sel = true;
+            else if (!(d2 > y2 * 1.0001f)) {  // borderline (or NaN): the exact double test
+              const double ddx = qx - (double) b.x, ddy = qy - (double) b.y;
+              sel = c2g_sqrt_lt(ddx * ddx + ddy * ddy, 3.0 * (double) (a.maj + b.z));
+            }
+          }
+          const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
+          if (sel) {
+            const int pos = n_pairs + __popc(m & ((1u << lane) - 1u));
+            if (pos < warp_cap) pairs[pos] = ((uint32_t) (so + si) << 16) | (uint32_t) (to + ti);
+          }
+          n_pairs += __popc(m);
+        }
       }
     } else {
       for (int si = warp; si < ns; si += n_warps) {

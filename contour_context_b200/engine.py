@@ -55,6 +55,17 @@ class Engine:
                                          capi.ptr(ids)), "c2g_ingest")
         return B
 
+    def ingest_xyz(self, xyz, offsets, first_slot: int = 0, int_ids=None, on_device: bool = None):
+        """Like ingest with 12 bytes per point: xyz is float32 [sum_n, 3] (the intensity column of the .bin record dropped)."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        B = len(offsets) - 1
+        if on_device is None:
+            on_device = bool(getattr(xyz, "is_cuda", False))
+        ids = None if int_ids is None else np.ascontiguousarray(int_ids, np.int32)
+        capi.check(capi.lib().c2g_ingest_xyz(self.h, capi.ptr(xyz), capi.ptr(offsets), B, int(on_device), first_slot,
+                                             capi.ptr(ids)), "c2g_ingest_xyz")
+        return B
+
     def ingest_bev_only(self, pts, offsets, on_device: bool = None):
         offsets = np.ascontiguousarray(offsets, np.int64)
         if on_device is None:

@@ -44,4 +44,19 @@ class ContourDB {
   void addScan(const std::shared_ptr<ContourManager> &added, double curr_timestamp);  // reference contour_db.h:814-824
   void pushAndBalance(int seed, double curr_timestamp);                               // reference contour_db.h:827-843
   size_t size() const { return all_bevs_.size(); }
+
+  // Extension (no reference counterpart; C-ABI c2g_online_window): W consecutive iterations of
+  //     queryRangedKNN(scan_i) -> addScan(scan_i, ts[i]) -> pushAndBalance(seeds[i], ts[i])        (test/batch_bin_test.cpp:179,234,237)
+  // in one call, with exactly the results of the scan-by-scan calls: the scans are ingested as one batch, the LayerDB bookkeeping of the
+  // window is replayed on the host, every scan is searched against the trees as they stand after its predecessors.  The scans must
+  // carry their points (makeBEV / makeBEVFromBin) but not have run makeContoursRecurs(); at most C2G_WINDOW scans (environment
+  // variable read when the runtime starts).  out[i].found == false: no candidate (queryRangedKNN would return empty vectors).
+  struct WindowResult {
+    bool found = false;
+    std::shared_ptr<const ContourManager> cand;
+    double corr = 0.0;
+    Eigen::Isometry2d tf;
+  };
+  void queryAddBalanceWindow(std::vector<std::shared_ptr<ContourManager>> &scans, const std::vector<double> &ts, const std::vector<int> &seeds,
+                             const CandidateScoreEnsemble &thres_lb, const CandidateScoreEnsemble &thres_ub, std::vector<WindowResult> &out);
 };

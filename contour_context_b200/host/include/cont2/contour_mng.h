@@ -142,6 +142,7 @@ class ContourManager {
   mutable std::vector<std::vector<BCI>> layer_key_bcis_;
   friend class ContourDB;
   void loadViews() const;
+  void adoptHead();  // head_ (read back from the device) -> layer_keys_ / layer_key_bcis_
 
  public:
   explicit ContourManager(const ContourManagerConfig &config, int int_id);

@@ -24,6 +24,7 @@ struct Runtime {
   bool have_cm = false, have_db = false;
   int capacity = 8192;
   int n_staging = 64;          // slots [capacity - n_staging, capacity) hold scans that are not (yet) in the DB
+  int max_window = 1;          // C2G_WINDOW
   std::vector<int> free_slots;
 
   // One context per process: every ContourManager / ContourDB of the process must carry the SAME configuration (the reference
@@ -100,7 +101,10 @@ struct Runtime {
     if (const char *e = std::getenv("C2G_SCAN_CAPACITY")) capacity = std::atoi(e);
     int dev = 0;
     if (const char *e = std::getenv("C2G_DEVICE")) dev = std::atoi(e);
-    C2G_CHECK(c2g_create(&cm, &db, dev, capacity, 1, 1 << 18, &ctx));
+    // the largest window ContourDB::queryAddBalanceWindow may be given (1 = scan-by-scan calls only); a scan holds at most
+    // 1 000 000 floats = 250 000 points (tools/pointcloud_util.h:17)
+    if (const char *e = std::getenv("C2G_WINDOW")) max_window = std::atoi(e) > 1 ? std::atoi(e) : 1;
+    C2G_CHECK(c2g_create(&cm, &db, dev, capacity, max_window, (long long) max_window * (1 << 18), &ctx));
     for (int s = capacity - 1; s >= capacity - n_staging; --s) free_slots.push_back(s);
   }
   int acquire() {
@@ -190,6 +194,10 @@ void ContourManager::makeContoursRecurs() {
   const long long offsets[2] = {0, (long long) n_points};
   C2G_CHECK(c2g_ingest(rt.ctx, src, offsets, 1, 0, slot_, &int_id_));
   C2G_CHECK(c2g_get_heads(rt.ctx, slot_, 1, &head_));
+  adoptHead();
+}
+
+void ContourManager::adoptHead() {
   if (head_.status != 0) {
     std::fprintf(stderr, "CHECK failed: scan %d exceeded a descriptor capacity (status %d)\n", int_id_, head_.status);
     std::abort();
@@ -262,6 +270,98 @@ void ContourDB::addScan(const std::shared_ptr<ContourManager> &added, double cur
   all_bevs_.emplace_back(added);
 }
 
+static c2g_score_ensemble packEnsemble(const CandidateScoreEnsemble &e) {
+  c2g_score_ensemble s;
+  s.i_ovlp_sum = e.sim_constell.i_ovlp_sum;
+  s.i_ovlp_max_one = e.sim_constell.i_ovlp_max_one;
+  s.i_in_ang_rng = e.sim_constell.i_in_ang_rng;
+  s.i_indiv_sim = e.sim_pair.i_indiv_sim;
+  s.i_orie_sim = e.sim_pair.i_orie_sim;
+  s.correlation = e.sim_post.correlation;
+  s.area_perc = e.sim_post.area_perc;
+  s.neg_est_dist = e.sim_post.neg_est_dist;
+  return s;
+}
+
+// anch_props_[0].correlation_ / T_delta_ of the returned candidate after fineOptimize (contour_db.h:626-627,642-643)
+static bool unpackBest(const c2g_query_result &res, int &gidx, double &corr, Eigen::Isometry2d &T) {
+  if (res.overflow) C2G_CHECK(C2G_ERR_CAPACITY);  // more candidate poses than C2G_MAX_CAND: the reference keeps them all
+  if (!(res.n_cand > 0 && res.best >= 0)) return false;  // ret_size = 1 (contour_db.h:639)
+  const c2g_cand &c = res.cand[res.best];
+  if (c.fine_flags != 0) C2G_CHECK(C2G_ERR_CAPACITY);
+  gidx = c.cand_gidx;
+  corr = (double) c.corr_fine;
+  T.setIdentity();
+  T.rotate(std::atan2(c.T_fine[1], c.T_fine[0]));
+  T.pretranslate(V2D(c.T_fine[2], c.T_fine[3]));
+  return true;
+}
+
+void ContourDB::queryAddBalanceWindow(std::vector<std::shared_ptr<ContourManager>> &scans, const std::vector<double> &ts, const std::vector<int> &seeds,
+                                      const CandidateScoreEnsemble &thres_lb, const CandidateScoreEnsemble &thres_ub,
+                                      std::vector<WindowResult> &out) {
+  auto &rt = runtime();
+  rt.ensure();
+  const int W = (int) scans.size();
+  out.assign((size_t) W, WindowResult());
+  if (W == 0) return;
+  if (W > rt.max_window || (int) ts.size() != W || (int) seeds.size() != W) {
+    std::fprintf(stderr, "CHECK failed: window of %d scans (C2G_WINDOW = %d), %zu timestamps, %zu seeds\n", W, rt.max_window, ts.size(), seeds.size());
+    std::abort();
+  }
+  const int first = (int) all_bevs_.size();
+  if (first + W > rt.capacity - rt.n_staging) {
+    std::fprintf(stderr, "CHECK failed: database capacity (C2G_SCAN_CAPACITY) exhausted\n");
+    std::abort();
+  }
+  // the points of the window as one buffer: used in place when the scans were read back to back into the pinned buffer
+  // (pinnedScanBuffer + makeBEVFromBin), gathered into a staging vector otherwise
+  std::vector<long long> offsets((size_t) W + 1, 0);
+  std::vector<int> ids((size_t) W);
+  bool contiguous = true;
+  for (int i = 0; i < W; ++i) {
+    ContourManager &cm = *scans[i];
+    const size_t n = cm.ext_pts_ ? cm.ext_n_ : cm.pts_.size() / 4;
+    if (n <= 10 || cm.slot_ >= 0) {
+      std::fprintf(stderr, "CHECK failed: scan %d of the window has <= 10 points or was already processed\n", cm.int_id_);
+      std::abort();
+    }
+    offsets[i + 1] = offsets[i] + (long long) n;
+    ids[i] = cm.int_id_;
+    contiguous = contiguous && cm.ext_pts_ && (i == 0 || cm.ext_pts_ == scans[i - 1]->ext_pts_ + 4 * scans[i - 1]->ext_n_);
+  }
+  const float *pts = scans[0]->ext_pts_;
+  std::vector<float> gathered;
+  if (!contiguous) {
+    gathered.resize(4 * (size_t) offsets[W]);
+    for (int i = 0; i < W; ++i) {
+      const ContourManager &cm = *scans[i];
+      std::memcpy(gathered.data() + 4 * offsets[i], cm.ext_pts_ ? cm.ext_pts_ : cm.pts_.data(), sizeof(float) * 4 * (size_t) (offsets[i + 1] - offsets[i]));
+    }
+    pts = gathered.data();
+  }
+  const c2g_score_ensemble lb = packEnsemble(thres_lb), ub = packEnsemble(thres_ub);
+  std::vector<c2g_query_result> res((size_t) W);
+  stp.start();
+  C2G_CHECK(c2g_online_window(rt.ctx, pts, offsets.data(), W, 0, ids.data(), ts.data(), seeds.data(), &lb, &ub, res.data()));
+  stp.record("window: make bev + query + update (GPU)");
+  std::vector<c2g_scan_head> heads((size_t) W);
+  C2G_CHECK(c2g_get_heads(rt.ctx, first, W, heads.data()));
+  for (int i = 0; i < W; ++i) {
+    ContourManager &cm = *scans[i];
+    cm.slot_ = first + i;  // IndexOfKey::gidx (contour_db.h:819): the descriptor was ingested straight into its DB slot
+    cm.owns_slot_ = false;
+    cm.head_ = heads[i];
+    cm.adoptHead();
+    all_bevs_.emplace_back(scans[i]);
+  }
+  for (int i = 0; i < W; ++i) {  // candidates are scans added before scan i (possibly earlier scans of this window)
+    int gidx = -1;
+    out[i].found = unpackBest(res[i], gidx, out[i].corr, out[i].tf);
+    if (out[i].found) out[i].cand = all_bevs_[gidx];
+  }
+}
+
 void ContourDB::pushAndBalance(int seed, double curr_timestamp) { C2G_CHECK(c2g_db_push_and_balance(runtime().ctx, seed, curr_timestamp)); }
 
 void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_ptr, const CandidateScoreEnsemble &thres_lb,
@@ -270,19 +370,7 @@ void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_pt
   cand_ptrs.clear();
   cand_corr.clear();
   cand_tf.clear();
-  auto pack = [](const CandidateScoreEnsemble &e) {
-    c2g_score_ensemble s;
-    s.i_ovlp_sum = e.sim_constell.i_ovlp_sum;
-    s.i_ovlp_max_one = e.sim_constell.i_ovlp_max_one;
-    s.i_in_ang_rng = e.sim_constell.i_in_ang_rng;
-    s.i_indiv_sim = e.sim_pair.i_indiv_sim;
-    s.i_orie_sim = e.sim_pair.i_orie_sim;
-    s.correlation = e.sim_post.correlation;
-    s.area_perc = e.sim_post.area_perc;
-    s.neg_est_dist = e.sim_post.neg_est_dist;
-    return s;
-  };
-  const c2g_score_ensemble lb = pack(thres_lb), ub = pack(thres_ub);
+  const c2g_score_ensemble lb = packEnsemble(thres_lb), ub = packEnsemble(thres_ub);
   c2g_query_result res;
   // the reference's three stage timers (contour_db.h:729-787): the device times of the kernels that replace each stage
   // (c2g_query_profile: knn | prefilter + score | proposal replay + GMM-L2 gate + output + refinement + ranking); the host
@@ -301,17 +389,12 @@ void ContourDB::queryRangedKNN(const std::shared_ptr<const ContourManager> &q_pt
   stp.recordSeconds("KNN search", t_knn);
   stp.recordSeconds("Constell", t_constell);
   stp.recordSeconds("L2 opt", t_wall - t_knn - t_constell > 0 ? t_wall - t_knn - t_constell : 0.0);
-  if (res.overflow) C2G_CHECK(C2G_ERR_CAPACITY);  // more candidate poses than C2G_MAX_CAND: the reference keeps them all
-  if (res.n_cand > 0 && res.best >= 0) {  // ret_size = 1 (contour_db.h:639)
-    const c2g_cand &c = res.cand[res.best];
-    cand_ptrs.emplace_back(all_bevs_[c.cand_gidx]);
-    // anch_props_[0].correlation_ / T_delta_ after fineOptimize (contour_db.h:626-627,642-643)
-    if (c.fine_flags != 0) C2G_CHECK(C2G_ERR_CAPACITY);
-    cand_corr.emplace_back((double) c.corr_fine);
-    Eigen::Isometry2d T;
-    T.setIdentity();
-    T.rotate(std::atan2(c.T_fine[1], c.T_fine[0]));
-    T.pretranslate(V2D(c.T_fine[2], c.T_fine[3]));
+  int gidx = -1;
+  double corr = 0.0;
+  Eigen::Isometry2d T;
+  if (unpackBest(res, gidx, corr, T)) {
+    cand_ptrs.emplace_back(all_bevs_[gidx]);
+    cand_corr.emplace_back(corr);
     cand_tf.emplace_back(T);
   }
 }

@@ -159,6 +159,31 @@ def test_device_resident_input_matches_host_input(engine):
         assert h_host[f].tobytes() == h_dev[f].tobytes(), f
 
 
+def test_xyz_input_variant_matches_xyzi(engine):
+    """c2g_ingest_xyz (12 B per point, intensity dropped on the host) must give byte-identical descriptors, from host and device
+    buffers, ragged batches included, and the dense-image getter must work on such a batch."""
+    import torch
+
+    base, _ = make_batch([40, 41, 42], [0, 1, 2], 50000)
+    scans = [base[:50000], base[50000:87001], base[100000:100017]]
+    pts = np.ascontiguousarray(np.concatenate(scans))
+    offsets = np.cumsum([0] + [len(s) for s in scans]).astype(np.int64)
+    xyz = np.ascontiguousarray(pts[:, :3])
+    engine.ingest(pts, offsets, first_slot=0, int_ids=np.arange(3))
+    ref_h = engine.heads(0, 3).copy()
+    ref_v = [np.concatenate(engine.views(b, ref_h[b])).tobytes() for b in range(3)]
+    ref_bev = [engine.bev(b) for b in range(3)]
+    for dev in (False, True):
+        src = torch.from_numpy(xyz).cuda() if dev else xyz
+        engine.ingest_xyz(src, offsets, first_slot=4, int_ids=np.arange(3))
+        h = engine.heads(4, 3)
+        assert h.tobytes() == ref_h.tobytes(), f"device={dev}: heads differ"
+        for b in range(3):
+            assert np.concatenate(engine.views(4 + b, h[b])).tobytes() == ref_v[b]
+            got = engine.bev(b)
+            assert all(a.tobytes() == r.tobytes() for a, r in zip(got, ref_bev[b]))
+
+
 def _cells_to_points(h, rng):
     """One point per occupied cell (jittered inside the cell), z so that lidar_height + z == h."""
     rows, cols = np.nonzero(h > -999.0)
