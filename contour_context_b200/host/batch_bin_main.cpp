@@ -7,6 +7,10 @@
 // are associated to the scans, every prediction is classified TP/FP/TN/FN and the outcome file of scripts/pr_mpe.py is
 // written.
 //   usage: cont2_batch_bin --eval <ts-sens_pose.txt> <ts-lidar_bins.txt> <outcome.txt> [kitti|mulran] [correlation_thres]
+// With --window W (first argument pair, either mode) the loop runs W scans at a time through ContourDB::queryAddBalanceWindow: the
+// scans of a window are read back to back into one page-locked buffer, ingested as one batch and queried against exactly the
+// database state the scan-by-scan loop would have shown each of them; the printed lines and the outcome file are the same.
+//   usage: cont2_batch_bin --window 148 <list.txt> ...   |   cont2_batch_bin --window 148 --eval ...
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -30,7 +34,39 @@ static size_t readKITTIBin(const std::string &path, float *buf, size_t cap_float
   return n;
 }
 
+static void printOutcome(const PredictionOutcome &pred_res, const ContLCDEvaluator &evaluator, int &cnt_tp, int &cnt_fn, int &cnt_fp) {
+  switch (pred_res.tfpn) {
+    case PredictionOutcome::TP: std::printf("Prediction outcome: TP\n"); cnt_tp++; break;
+    case PredictionOutcome::FP: std::printf("Prediction outcome: FP\n"); cnt_fp++; break;
+    case PredictionOutcome::TN: std::printf("Prediction outcome: TN\n"); break;
+    case PredictionOutcome::FN: std::printf("Prediction outcome: FN\n"); cnt_fn++; break;
+  }
+  std::printf("TP Error mean: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPMeanTrans(), evaluator.getTPMeanRot());
+  std::printf("TP Error rmse: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPRMSETrans(), evaluator.getTPRMSERot());
+  std::printf("Accumulated tp poses: %d\nAccumulated fn poses: %d\nAccumulated fp poses: %d\n", cnt_tp, cnt_fn, cnt_fp);
+}
+
+static void printLC(int seq, const ContourManagerConfig &cm_config, bool found, const std::shared_ptr<const ContourManager> &cand, double corr,
+                    const Eigen::Isometry2d &T, int &n_pos) {
+  if (found) {
+    n_pos++;
+    const double est = ConstellCorrelation::getEstSensTF(T, cm_config).translation().norm();
+    std::printf("LC %d -> %d corr %.6f  T(bev) = [%.4f %.4f %.4f]  est. dist %.3f m\n", seq, cand->getIntID(), corr, T(0, 2), T(1, 2),
+                std::atan2(T(1, 0), T(0, 0)), est);
+  } else {
+    std::printf("LC %d -> none\n", seq);
+  }
+}
+
 int main(int argc, char **argv) {
+  int window = 1;
+  if (argc >= 3 && std::string(argv[1]) == "--window") {
+    window = std::atoi(argv[2]);
+    if (window < 1) window = 1;
+    setenv("C2G_WINDOW", argv[2], 1);  // read by the runtime when the context is created
+    argv += 2;
+    argc -= 2;
+  }
   if (argc < 2) {
     std::printf("usage: %s <ts-lidar_bins.txt> [kitti|mulran]\n       %s --eval <ts-sens_pose.txt> <ts-lidar_bins.txt> <outcome.txt> [kitti|mulran] [corr_thres]\n",
                 argv[0], argv[0]);
@@ -61,6 +97,38 @@ int main(int argc, char **argv) {
     const double corr_thres = argc > 6 ? std::atof(argv[6]) : 0.0;  // correlation_thres of the yaml (config/batch_bin_test_config.yaml:2)
     ContLCDEvaluator evaluator(argv[2], argv[3], corr_thres);
     int cnt_tp = 0, cnt_fn = 0, cnt_fp = 0;
+    if (window > 1) {
+      float *bins = ContourManager::pinnedScanBuffer((size_t) window * 1000000);
+      bool more = true;
+      while (more) {
+        std::vector<std::shared_ptr<ContourManager>> scans;
+        std::vector<double> tss;
+        std::vector<int> seeds;
+        size_t used = 0;
+        stp.lap();
+        stp.start();
+        while ((int) scans.size() < window && (more = evaluator.loadNewScan())) {
+          const auto info = evaluator.getCurrScanInfo();
+          size_t n_points = 0;
+          scans.push_back(evaluator.loadCurrScanInto(cm_config, bins + used, &n_points));
+          used += 4 * n_points;
+          tss.push_back(info.ts);
+          seeds.push_back(info.seq);
+        }
+        stp.record("read scans");
+        if (scans.empty()) break;
+        std::vector<ContourDB::WindowResult> res;
+        contour_db.queryAddBalanceWindow(scans, tss, seeds, thres_lb_, thres_ub_, res);
+        for (size_t i = 0; i < scans.size(); ++i) {
+          const PredictionOutcome pred_res = res[i].found ? evaluator.addPrediction(scans[i], res[i].corr, res[i].cand, res[i].tf)
+                                                          : evaluator.addPrediction(scans[i], 0.0);
+          printOutcome(pred_res, evaluator, cnt_tp, cnt_fn, cnt_fp);
+        }
+      }
+      evaluator.savePredictionResults(argv[4]);
+      stp.printScreen();
+      return 0;
+    }
     while (evaluator.loadNewScan()) {
       const auto laser_info_tgt = evaluator.getCurrScanInfo();
       stp.lap();
@@ -78,15 +146,7 @@ int main(int argc, char **argv) {
         pred_res = evaluator.addPrediction(ptr_cm_tgt, 0.0);
       else
         pred_res = evaluator.addPrediction(ptr_cm_tgt, cand_corr[0], ptr_cands[0], bev_tfs[0]);
-      switch (pred_res.tfpn) {
-        case PredictionOutcome::TP: std::printf("Prediction outcome: TP\n"); cnt_tp++; break;
-        case PredictionOutcome::FP: std::printf("Prediction outcome: FP\n"); cnt_fp++; break;
-        case PredictionOutcome::TN: std::printf("Prediction outcome: TN\n"); break;
-        case PredictionOutcome::FN: std::printf("Prediction outcome: FN\n"); cnt_fn++; break;
-      }
-      std::printf("TP Error mean: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPMeanTrans(), evaluator.getTPMeanRot());
-      std::printf("TP Error rmse: t:%7.4f m, r:%7.4f rad\n", evaluator.getTPRMSETrans(), evaluator.getTPRMSERot());
-      std::printf("Accumulated tp poses: %d\nAccumulated fn poses: %d\nAccumulated fp poses: %d\n", cnt_tp, cnt_fn, cnt_fp);
+      printOutcome(pred_res, evaluator, cnt_tp, cnt_fn, cnt_fp);
       stp.start();
       contour_db.addScan(ptr_cm_tgt, laser_info_tgt.ts);
       contour_db.pushAndBalance(laser_info_tgt.seq, laser_info_tgt.ts);
@@ -99,6 +159,40 @@ int main(int argc, char **argv) {
   std::ifstream list(argv[1]);
   std::string line;
   int seq = 0, n_pos = 0;
+  if (window > 1) {
+    float *bins = ContourManager::pinnedScanBuffer((size_t) window * 1000000);
+    bool more = true;
+    while (more) {
+      std::vector<std::shared_ptr<ContourManager>> scans;
+      std::vector<double> tss;
+      std::vector<int> seeds;
+      size_t used = 0;
+      stp.lap();
+      stp.start();
+      while ((int) scans.size() < window && (more = (bool) std::getline(list, line))) {
+        std::istringstream ss(line);
+        double ts;
+        std::string path;
+        if (!(ss >> ts >> path)) continue;
+        std::shared_ptr<ContourManager> cm(new ContourManager(cm_config, seq));
+        const size_t n_points = readKITTIBin(path, bins + used, 1000000);
+        cm->makeBEVFromBin(bins + used, n_points, "assigned_id_" + std::to_string(seq));
+        used += 4 * n_points;
+        scans.push_back(cm);
+        tss.push_back(ts);
+        seeds.push_back(seq);
+        seq++;
+      }
+      stp.record("read scans");
+      if (scans.empty()) break;
+      std::vector<ContourDB::WindowResult> res;
+      contour_db.queryAddBalanceWindow(scans, tss, seeds, thres_lb_, thres_ub_, res);
+      for (size_t i = 0; i < scans.size(); ++i) printLC(scans[i]->getIntID(), cm_config, res[i].found, res[i].cand, res[i].corr, res[i].tf, n_pos);
+    }
+    std::printf("scans: %d, positive predictions: %d\n", seq, n_pos);
+    stp.printScreen();
+    return 0;
+  }
   while (std::getline(list, line)) {
     std::istringstream ss(line);
     double ts;
@@ -119,15 +213,8 @@ int main(int argc, char **argv) {
     std::vector<Eigen::Isometry2d> bev_tfs;
     contour_db.queryRangedKNN(ptr_cm_tgt, thres_lb_, thres_ub_, ptr_cands, cand_corr, bev_tfs);
     if (ptr_cands.size() >= 2) std::abort();  // CHECK(ptr_cands.size() < 2) (batch_bin_test.cpp:187)
-    if (!ptr_cands.empty()) {
-      n_pos++;
-      const Eigen::Isometry2d &T = bev_tfs[0];
-      const double est = ConstellCorrelation::getEstSensTF(T, cm_config).translation().norm();
-      std::printf("LC %d -> %d corr %.6f  T(bev) = [%.4f %.4f %.4f]  est. dist %.3f m\n", seq, ptr_cands[0]->getIntID(), cand_corr[0],
-                  T(0, 2), T(1, 2), std::atan2(T(1, 0), T(0, 0)), est);
-    } else {
-      std::printf("LC %d -> none\n", seq);
-    }
+    printLC(seq, cm_config, !ptr_cands.empty(), ptr_cands.empty() ? nullptr : ptr_cands[0], ptr_cands.empty() ? 0.0 : cand_corr[0],
+            ptr_cands.empty() ? Eigen::Isometry2d() : bev_tfs[0], n_pos);
     stp.start();
     contour_db.addScan(ptr_cm_tgt, ts);
     contour_db.pushAndBalance(seq, ts);

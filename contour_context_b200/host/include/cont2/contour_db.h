@@ -14,6 +14,13 @@ struct TreeBucketConfig {  // reference contour_db.h:54-57
   double min_elapse_ = 15.0;
 };
 
+struct IndexOfKey {  // reference contour_db.h:59-65: where a retrieval key comes from: global scan index, level, sequence at that level
+  size_t gidx{};
+  int level{};
+  int seq{};
+  IndexOfKey(size_t g, int l, int s) : gidx(g), level(l), seq(s) {}
+};
+
 struct CandidateScoreEnsemble {  // reference contour_db.h:244-250
   ScoreConstellSim sim_constell;
   ScorePairwiseSim sim_pair;

@@ -97,7 +97,37 @@ union ScorePostProc {  // reference contour_mng.h:188-219
   }
 };
 
-struct BCI {  // reference contour_mng.h:243-280 (data members; the similarity check runs on the device)
+union ConstellationPair {  // reference contour_mng.h:221-240: a pair of "matched" contours of two scans at one level
+  struct {
+    int8_t level;
+    int8_t seq_src;
+    int8_t seq_tgt;
+  };
+  int data[1]{};
+  ConstellationPair(int8_t l, int8_t s, int8_t t) : level(l), seq_src(s), seq_tgt(t) {}
+  bool operator<(const ConstellationPair &a) const {
+    return level < a.level || (level == a.level && seq_src < a.seq_src) || (level == a.level && seq_src == a.seq_src && seq_tgt < a.seq_tgt);
+  }
+  bool operator==(const ConstellationPair &a) const { return level == a.level && seq_src == a.seq_src && seq_tgt == a.seq_tgt; }
+};
+
+union Pixelf {  // reference contour_mng.h:392-411: 2.5-D continuous pixel (bev_pixfs_)
+  struct {
+    float row_f;
+    float col_f;
+    float elev;
+  };
+  int data[3]{};
+  Pixelf(float r, float c, float e) : row_f(r), col_f(c), elev(e) {}
+  Pixelf() {
+    row_f = -1;
+    col_f = -1;
+    elev = -1;
+  }
+  bool operator<(const Pixelf &b) const { return row_f < b.row_f; }
+};
+
+struct BCI {  // reference contour_mng.h:243-389 (the hot path runs checkConstellSim on the device: csrc/query.cu)
   union RelativePoint {
     struct {
       int8_t level;
@@ -114,6 +144,19 @@ struct BCI {  // reference contour_mng.h:243-280 (data members; the similarity c
   std::vector<uint16_t> nei_idx_segs_;
   int8_t piv_seq_, level_;
   explicit BCI(int8_t seq, int8_t lev) : dist_bin_(0), piv_seq_(seq), level_(lev) {}
+
+  union DistSimPair {  // reference contour_mng.h:260-271
+    struct {
+      float orie_diff;
+      int8_t seq_src;
+      int8_t seq_tgt;
+      int8_t level;
+    };
+    int data[2]{};
+    DistSimPair(int8_t l, int8_t s, int8_t t, float o) : orie_diff(o), seq_src(s), seq_tgt(t), level(l) {}
+  };
+  // reference contour_mng.h:288-388 (host restatement, for callers outside the query path; defined in cont2_facade.cpp)
+  static ScoreConstellSim checkConstellSim(const BCI &src, const BCI &tgt, const ScoreConstellSim &lb, std::vector<ConstellationPair> &constell_res);
 };
 
 namespace c2g_host {
@@ -121,6 +164,7 @@ namespace c2g_host {
 // ContourManagerConfig / ContourDBConfig seen.  Capacity via C2G_SCAN_CAPACITY (default 8192 scans).
 struct Runtime;
 Runtime &runtime();
+c2g_ctx *context();  // the process-wide C-ABI context (created on first use); for callers that mix facade objects and c2g.h calls
 }  // namespace c2g_host
 
 class ContourDB;
@@ -189,4 +233,22 @@ class ContourManager {
     return cont_views_[lev][seq]->cell_cnt_ * 1.0f / head_.layer_cell_cnt[lev];
   }
   int deviceSlot() const { return slot_; }
+
+  // Public statics of the reference (host restatements over the descriptors read back from the device; the query path itself runs
+  // the same cascade in csrc/query.cu).  reference contour_mng.h:1124-1242, :1251-1277, :1279-1284.
+  static ScorePairwiseSim checkConstellCorrespSim(const ContourManager &src, const ContourManager &tgt, const std::vector<ConstellationPair> &cstl_in,
+                                                  const ScorePairwiseSim &lb, const ContourSimThresConfig &cont_sim,
+                                                  std::vector<ConstellationPair> &cstl_out, std::vector<float> &area_perc);
+  template <typename Iter>
+  static Eigen::Isometry2d getTFFromConstell(const ContourManager &src, const ContourManager &tgt, Iter cstl_beg, Iter cstl_end) {
+    std::vector<ConstellationPair> v(cstl_beg, cstl_end);
+    return tfFromConstell(src, tgt, v.data(), (int) v.size());
+  }
+  static bool checkContPairSim(const ContourManager &src, const ContourManager &tgt, const ConstellationPair &cstl,
+                               const ContourSimThresConfig &cont_sim) {
+    return ContourView::checkSim(*src.getLevContours(cstl.level)[cstl.seq_src], *tgt.getLevContours(cstl.level)[cstl.seq_tgt], cont_sim);
+  }
+
+ private:
+  static Eigen::Isometry2d tfFromConstell(const ContourManager &src, const ContourManager &tgt, const ConstellationPair *cstl, int n);
 };

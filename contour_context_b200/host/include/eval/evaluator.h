@@ -218,6 +218,26 @@ class ContLCDEvaluator {
     return cmng_ptr;
   }
 
+  // Windowed loop (ContourDB::queryAddBalanceWindow): the current scan's .bin is read into `bin` (room for 1 000 000 floats, inside
+  // the runtime's page-locked buffer) and handed to a new ContourManager WITHOUT running makeContoursRecurs - the window call
+  // ingests all its scans as one batch.  Returns the number of points read.
+  std::shared_ptr<ContourManager> loadCurrScanInto(const ContourManagerConfig &config, float *bin, size_t *n_points_out) const {
+    const LaserScanInfo &info = getCurrScanInfo();
+    std::shared_ptr<ContourManager> cmng_ptr(new ContourManager(config, info.seq));
+    FILE *f = std::fopen(info.fpath.c_str(), "rb");
+    if (!f) {
+      std::printf("Lidar bin file %s does not exist.\n", info.fpath.c_str());
+      std::exit(-1);
+    }
+    const size_t n_points = std::fread(bin, sizeof(float), 1000000, f) / 4;
+    std::fclose(f);
+    std::string str_id = std::to_string(info.seq);
+    str_id = "assigned_id_" + std::string(8 - std::min<size_t>(8, str_id.length()), '0') + str_id;
+    cmng_ptr->makeBEVFromBin(bin, n_points, str_id);
+    if (n_points_out) *n_points_out = n_points;
+    return cmng_ptr;
+  }
+
   PredictionOutcome addPrediction(const std::shared_ptr<const ContourManager> &q_mng, double est_corr,
                                   const std::shared_ptr<const ContourManager> &cand_mng = nullptr,
                                   const Eigen::Isometry2d &T_est_delta_2d = Eigen::Isometry2d::Identity()) {  // evaluator.h:305-373

@@ -1,5 +1,7 @@
 // cont2_facade.cpp — ContourManager / ContourDB (reference names and call sequence) implemented on the C-ABI of
 // libc2g.so.  Error convention of the reference: no exceptions, CHECK-style abort on failure.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -130,6 +132,11 @@ Runtime &runtime() {
   return r;
 }
 
+c2g_ctx *context() {
+  runtime().ensure();
+  return runtime().ctx;
+}
+
 }  // namespace c2g_host
 
 using c2g_host::runtime;
@@ -242,6 +249,149 @@ std::vector<float> ContourManager::getBevImage() const {
   std::vector<float> bev((size_t) cfg_.n_row_ * cfg_.n_col_);
   C2G_CHECK(c2g_get_bev(runtime().ctx, 0, bev.data(), nullptr, nullptr));
   return bev;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host restatements of the reference's public statics (the query path runs the same cascade on the device, csrc/query.cu;
+// tests/test_facade_gpu.py checks these against the device's per-hint records).
+namespace {
+inline float clampAngF(float ang) {  // clampAng<float> (include/tools/algos.h:49-51): double arithmetic, stored to float
+  return (float) ((double) ang - std::floor(((double) ang + M_PI) / (2 * M_PI)) * 2 * M_PI);
+}
+inline void normalize2(float x, float y, float &ox, float &oy) {  // Eigen's normalized(): unchanged when the norm is zero
+  const float n2 = x * x + y * y;
+  if (n2 > 0.0f) {
+    const float n = std::sqrt(n2);
+    ox = x / n;
+    oy = y / n;
+  } else {
+    ox = x;
+    oy = y;
+  }
+}
+}  // namespace
+
+ScoreConstellSim BCI::checkConstellSim(const BCI &src, const BCI &tgt, const ScoreConstellSim &lb, std::vector<ConstellationPair> &constell_res) {
+  const auto and1 = src.dist_bin_ & tgt.dist_bin_, and2 = (src.dist_bin_ << 1) & tgt.dist_bin_, and3 = (src.dist_bin_ >> 1) & tgt.dist_bin_;
+  const int ovlp1 = (int) and1.count(), ovlp2 = (int) and2.count(), ovlp3 = (int) and3.count();
+  ScoreConstellSim ret;
+  ret.i_ovlp_sum = ovlp1 + ovlp2 + ovlp3;
+  ret.i_ovlp_max_one = std::max(ovlp1, std::max(ovlp2, ovlp3));
+  if (!(ret.i_ovlp_sum >= lb.i_ovlp_sum && ret.i_ovlp_max_one >= lb.i_ovlp_max_one)) return ret;
+  // neighbours of the two anchors whose distance bits differ by at most one: two-pointer walk over the bit-position segments
+  std::vector<DistSimPair> pot;
+  const int n_s = (int) src.nei_idx_segs_.size(), n_t = (int) tgt.nei_idx_segs_.size();
+  int p11 = 0;
+  for (int p2 = 0; p2 < n_t - 1; p2++) {
+    const int tb = tgt.nei_pts_[tgt.nei_idx_segs_[p2]].bit_pos;
+    while (p11 < n_s - 1 && src.nei_pts_[src.nei_idx_segs_[p11]].bit_pos < tb - 1) p11++;
+    int p12 = p11;
+    while (p12 < n_s - 1 && src.nei_pts_[src.nei_idx_segs_[p12]].bit_pos <= tb + 1) p12++;
+    for (int i = tgt.nei_idx_segs_[p2]; i < tgt.nei_idx_segs_[p2 + 1]; i++)
+      for (int j = src.nei_idx_segs_[p11]; j < src.nei_idx_segs_[p12]; j++)
+        pot.emplace_back(src.nei_pts_[j].level, src.nei_pts_[j].seq, tgt.nei_pts_[i].seq, clampAngF(tgt.nei_pts_[i].theta - src.nei_pts_[j].theta));
+  }
+  std::sort(pot.begin(), pot.end(), [](const DistSimPair &a, const DistSimPair &b) { return a.orie_diff < b.orie_diff; });
+  // longest run of orientation differences inside a circular window of pi / 16
+  const float angular_range = M_PI / 16;
+  int beg = 0, longest = 1, p1 = 0, p2 = 0;
+  const int sz = (int) pot.size();
+  while (p1 < sz) {
+    if (pot[p2 % sz].orie_diff - pot[p1].orie_diff + 2 * M_PI * int(p2 / sz) > angular_range)
+      p1++;
+    else {
+      if (p2 - p1 + 1 > longest) {
+        longest = p2 - p1 + 1;
+        beg = p1;
+      }
+      p2++;
+    }
+  }
+  ret.i_in_ang_rng = longest;
+  if (longest < lb.i_in_ang_rng) return ret;
+  constell_res.clear();
+  for (int i = beg; i < longest + beg; i++) constell_res.emplace_back(pot[i % sz].level, pot[i % sz].seq_src, pot[i % sz].seq_tgt);
+  constell_res.emplace_back(src.level_, src.piv_seq_, tgt.piv_seq_);  // the anchors are a pair too
+  return ret;
+}
+
+ScorePairwiseSim ContourManager::checkConstellCorrespSim(const ContourManager &src, const ContourManager &tgt, const std::vector<ConstellationPair> &cstl_in,
+                                                         const ScorePairwiseSim &lb, const ContourSimThresConfig &cont_sim,
+                                                         std::vector<ConstellationPair> &cstl_out, std::vector<float> &area_perc) {
+  ScorePairwiseSim ret;
+  cstl_out.clear();
+  area_perc.clear();
+  for (const auto &pr : cstl_in)  // 1. individual similarity
+    if (checkContPairSim(src, tgt, pr, cont_sim)) cstl_out.push_back(pr);
+  ret.i_indiv_sim = (int) cstl_out.size();
+  if (ret.i_indiv_sim < lb.i_indiv_sim) return ret;
+  auto sv = [&](const ConstellationPair &p) -> const ContourView & { return *src.getLevContours(p.level)[p.seq_src]; };
+  auto tv = [&](const ConstellationPair &p) -> const ContourView & { return *tgt.getLevContours(p.level)[p.seq_tgt]; };
+  // 2.1 the "shaft": the comparison is made against the ALREADY NORMALISED previous shaft (contour_mng.h:1178-1179), so the last
+  // qualifying pair among the first <= 10 wins, not the longest (SURVEY.md 8a' #6)
+  float ssx = 0.f, ssy = 0.f, stx = 0.f, sty = 0.f;
+  const int num_sim0 = (int) cstl_out.size();
+  for (int i = 1; i < std::min(num_sim0, 10); i++)
+    for (int j = 0; j < i; j++) {
+      const float cx = sv(cstl_out[i]).pos_mean_(0) - sv(cstl_out[j]).pos_mean_(0), cy = sv(cstl_out[i]).pos_mean_(1) - sv(cstl_out[j]).pos_mean_(1);
+      if (std::sqrt(cx * cx + cy * cy) > std::sqrt(ssx * ssx + ssy * ssy)) {
+        normalize2(cx, cy, ssx, ssy);
+        normalize2(tv(cstl_out[i]).pos_mean_(0) - tv(cstl_out[j]).pos_mean_(0), tv(cstl_out[i]).pos_mean_(1) - tv(cstl_out[j]).pos_mean_(1), stx, sty);
+      }
+    }
+  // 2.2 drop pairs of two elongated contours whose major axes disagree with the shaft by more than pi / 6 both ways
+  int num_sim = num_sim0;
+  for (int i = 0; i < num_sim;) {
+    const ContourView &sc1 = sv(cstl_out[i]), &tc1 = tv(cstl_out[i]);
+    if (sc1.ecc_feat_ && tc1.ecc_feat_) {
+      const float theta_s = std::acos(ssx * sc1.eig_vecs_(0, 1) + ssy * sc1.eig_vecs_(1, 1));
+      const float theta_t = std::acos(stx * tc1.eig_vecs_(0, 1) + sty * tc1.eig_vecs_(1, 1));
+      const float pi6 = M_PI / 6;
+      if (std::fabs(theta_s - theta_t) > pi6 && std::fabs((float) (M_PI - theta_s) - theta_t) > pi6) {
+        std::swap(cstl_out[i], cstl_out[num_sim - 1]);
+        num_sim--;
+        continue;
+      }
+    }
+    i++;
+  }
+  cstl_out.erase(cstl_out.begin() + num_sim, cstl_out.end());
+  ret.i_orie_sim = num_sim;
+  if (ret.i_orie_sim < lb.i_orie_sim) return ret;
+  for (const auto &pr : cstl_out) area_perc.push_back(0.5f * (src.getAreaPerc(pr.level, pr.seq_src) + tgt.getAreaPerc(pr.level, pr.seq_tgt)));
+  return ret;
+}
+
+// Eigen::umeyama(src, tgt, no scaling) for 2-D point sets, closed form in double (as in csrc/query.cu)
+Eigen::Isometry2d ContourManager::tfFromConstell(const ContourManager &src, const ContourManager &tgt, const ConstellationPair *cstl, int n) {
+  if (n <= 2) {  // CHECK_GT(num_elem, 2)
+    std::fprintf(stderr, "CHECK failed: getTFFromConstell needs more than 2 pairs\n");
+    std::abort();
+  }
+  const double inv_n = 1.0 / (double) n;
+  double sm0 = 0, sm1 = 0, dm0 = 0, dm1 = 0;
+  for (int i = 0; i < n; ++i) {
+    const ContourView &ps = *src.getLevContours(cstl[i].level)[cstl[i].seq_src], &pt = *tgt.getLevContours(cstl[i].level)[cstl[i].seq_tgt];
+    sm0 += (double) ps.pos_mean_(0);
+    sm1 += (double) ps.pos_mean_(1);
+    dm0 += (double) pt.pos_mean_(0);
+    dm1 += (double) pt.pos_mean_(1);
+  }
+  sm0 *= inv_n, sm1 *= inv_n, dm0 *= inv_n, dm1 *= inv_n;
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+  for (int i = 0; i < n; ++i) {
+    const ContourView &ps = *src.getLevContours(cstl[i].level)[cstl[i].seq_src], &pt = *tgt.getLevContours(cstl[i].level)[cstl[i].seq_tgt];
+    const double sx = (double) ps.pos_mean_(0) - sm0, sy = (double) ps.pos_mean_(1) - sm1;
+    const double dx = (double) pt.pos_mean_(0) - dm0, dy = (double) pt.pos_mean_(1) - dm1;
+    s00 += dx * sx, s01 += dx * sy, s10 += dy * sx, s11 += dy * sy;
+  }
+  const double ang0 = std::atan2(s10 * inv_n - s01 * inv_n, s00 * inv_n + s11 * inv_n);
+  const double c0 = std::cos(ang0), s0 = std::sin(ang0);
+  Eigen::Isometry2d ret;
+  ret.setIdentity();
+  ret.rotate(std::atan2(s0, c0));
+  ret.pretranslate(V2D(dm0 - (c0 * sm0 - s0 * sm1), dm1 - (s0 * sm0 + c0 * sm1)));
+  return ret;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
