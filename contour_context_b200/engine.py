@@ -151,6 +151,7 @@ class Engine:
         capi.check(capi.lib().c2g_online_window(self.h, capi.ptr(pts), capi.ptr(offsets), W, int(on_device), capi.ptr(ids),
                                                 capi.ptr(ts), capi.ptr(seeds), C.byref(lb), C.byref(ub), capi.ptr(res)),
                    "c2g_online_window")
+        self.check_results(res)
         return res
 
     def online_runs(self) -> int:
@@ -202,7 +203,22 @@ class Engine:
             scores = np.zeros(self.hint_slots(B), D.PAIR_SCORE_DTYPE)
         capi.check(capi.lib().c2g_query(self.h, first_slot, B, C.byref(lb), C.byref(ub), capi.ptr(res), capi.ptr(hints),
                                         capi.ptr(scores)), "c2g_query")
+        self.check_results(res)
         return (res, hints, scores) if want_trace else res
+
+    @staticmethod
+    def check_results(res: np.ndarray, allow_overflow: bool = False):
+        """The reference's CandidateManager keeps every candidate pose (contour_db.h:352-363); the device keeps C2G_MAX_CAND per
+        query scan and flags the rest.  A dropped pose can change which loop closure is returned, so an overflow is an error,
+        like a refinement whose pair list did not fit (fine_flags)."""
+        if not allow_overflow and int(res["overflow"].max(initial=0)) != 0:
+            bad = np.nonzero(res["overflow"])[0]
+            raise capi.C2gError(f"query scan(s) {bad[:8].tolist()} proposed more than {D.MAX_CAND} candidate poses (C2G_MAX_CAND): "
+                                "results would differ from the reference")
+        for r in res:
+            n = min(int(r["n_cand"]), D.MAX_CAND)
+            if n and int(r["cand"][:n]["fine_flags"].max()) != 0:
+                raise capi.C2gError("a refinement's pre-selected pair list overflowed the device scratch")
 
     def query_async(self, first_slot: int, B: int, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble):
         capi.check(capi.lib().c2g_query_async(self.h, first_slot, B, C.byref(lb), C.byref(ub)), "c2g_query_async")

@@ -4,6 +4,8 @@ growing DB bookkeeping -> ranged kNN hints -> per-hint cascade scores -> candida
 
 Bar: hint identity/order and squared key distances bit-exact; constellation / pairwise integer scores equal; matched-pair
 sets equal; SE(2) proposals, area_perc and correlation within 1e-5 (north_star)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -193,3 +195,36 @@ def test_incremental_mirror_matches_full_rebuild(built_lib):
     finally:
         a.close()
         b.close()
+
+
+def test_more_candidate_poses_than_the_device_keeps_is_an_error(built_lib):
+    """a place where the vehicle stood still returns dozens of near-identical DB scans per key; the reference keeps every
+    candidate pose, the device keeps C2G_MAX_CAND = 32 and flags the rest.  The flag must not be silent: Engine.query raises."""
+    from contour_context_b200 import capi
+    from contour_context_b200.engine import Engine
+
+    n_dup, n_pts = 44, 60000
+    eng = Engine(scan_capacity=n_dup + 8, max_batch=8, max_points=8 * 65536)
+    try:
+        lb, ub = D.kitti_thres()
+        for i0 in range(0, n_dup, 4):  # the same place (scene 900, visit 0) recorded 44 times, only the sensor noise differs
+            pts, offsets = make_batch([900] * 4, [0] * 4, n_pts, noise_seed=1000 + i0)
+            eng.ingest(pts, offsets, first_slot=i0, int_ids=np.arange(i0, i0 + 4))
+            for j in range(4):
+                eng.db_add_scans(i0 + j, 1, [0.1 * (i0 + j)])
+                eng.db_push_and_balance(i0 + j, 0.1 * (i0 + j))
+        for k in range(12):
+            eng.db_push_and_balance(k, 1000.0 + k)
+        q, qo = make_batch([900], [1], n_pts, noise_seed=5)
+        eng.ingest(q, qo, first_slot=n_dup)
+        res = np.zeros(1, D.QUERY_RESULT_DTYPE)
+        capi.check(capi.lib().c2g_query(eng.h, n_dup, 1, C.byref(lb), C.byref(ub), capi.ptr(res), None, None))
+        if res["n_pose_before"][0] >= D.MAX_CAND and res["overflow"][0]:
+            with pytest.raises(capi.C2gError):
+                eng.query(n_dup, 1, lb, ub)
+        else:  # fewer than 33 duplicates passed the cascade: the cap did not bind, the query must simply succeed
+            assert res["overflow"][0] == 0
+            assert eng.query(n_dup, 1, lb, ub)[0]["n_pose_before"] == res["n_pose_before"][0]
+        assert res["n_pose_before"][0] >= 20, "the duplicates should all be candidate poses"
+    finally:
+        eng.close()
