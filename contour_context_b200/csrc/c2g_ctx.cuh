@@ -6,6 +6,7 @@
 #define C2G_QUERY_STREAMS 8  // sub-batches of one c2g_query_async call that may run concurrently
 #define C2G_WORK_N 8   // knn keys evaluated, knn block boxes tested, gate pre-selection tests, gate terms, refine pre-selection tests,
                        // refine pair terms (pairs x evaluations), refine evaluations, (spare)
+#define C2G_PATCH_RING 64
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
@@ -77,9 +78,17 @@ struct c2g_ctx {
   uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
   int pair_cap;
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk
-  void *h_patch, *d_patch;     // staging of mirror patches (records + block descriptors), pinned host / device
-  size_t patch_cap;
-  cudaEvent_t ev_patch;        // the last patch upload has left h_patch
+  // staging RING of mirror patches (records + block descriptors), pinned host / device: a patch takes the next free stretch, so the
+  // host never waits for the GPU unless the ring wraps onto a patch that is still in flight (the windowed online loop issues ~50
+  // small patches per window while the stream is busy with the next window's ingest)
+  void *h_patch, *d_patch;
+  size_t patch_cap, patch_off;
+  struct {
+    size_t beg, end;
+    cudaEvent_t ev;            // recorded after the kernels that consume the stretch
+    int used;
+  } patch_ring[C2G_PATCH_RING];
+  int patch_head;              // next ring entry to (re)use
   C2gHostDB *hostdb;       // ContourDB::layer_db_ bookkeeping on the host
   int db_dirty;            // device mirror older than the host state
   int db_not_kd;           // some buckets of the mirror are in tree order (fine for the online loop, slow for big batches)

@@ -498,11 +498,17 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
       }
       pair_sync(lev_w);
       C2G_DBG(12);
-      // B3 unions with the runs of the row above that touch [c0 - 1, c0 + len] (8-connectivity): consecutive run ids
-      for (int id = half * 32 + lane; id < n; id += 64) {
+      // B3 unions with the runs of the row above that touch [c0 - 1, c0 + len] (8-connectivity): consecutive run ids.  The runs
+      // are taken in raster-order batches of 64 (two warps) and every batch is flattened before the next one starts: links only go
+      // to smaller ids, i.e. to earlier batches, whose entries then already name their roots - a find is one or two hops instead of
+      // a walk down a chain as long as the component is tall (min-linking without the flatten builds such chains; the unions were
+      // 45-90 kcyc of the ~600 kcyc a scan takes).
+      for (int id0 = 0; id0 < n; id0 += 64) {
+        const int id = id0 + half * 32 + lane;
+        if (id < n) {
         const uint32_t inf = ri[id];
         const int row = inf & 255, c0 = (inf >> 8) & 255, len = (inf >> 16) & 255;
-        if (row == 0) continue;
+        if (row != 0) {
         const int lo = max(c0 - 1, 0), hi = min(c0 + len, ncol - 1);
         const uint32_t *pr = pl + (row - 1) * WPR;
         const uint16_t *wpr = wp + (row - 1) * WPR;
@@ -537,6 +543,11 @@ contour_kernel(const uint32_t *__restrict__ planes_in, const float4 *__restrict_
         }
         if (first >= 0)
           for (int j = 0; j <= extra; ++j) uf_union(rp, (uint32_t) id, (uint32_t) (first + j));
+        }
+        }
+        pair_sync(lev_w);
+        if (id < n) rp[id] = uf_find_ro(rp, (uint32_t) id);  // own entry only; other lanes read either the old parent or the root
+        pair_sync(lev_w);
       }
       pair_sync(lev_w);
       C2G_DBG(13);

@@ -30,6 +30,7 @@
 namespace {
 
 constexpr int QK_WARPS = 8;           // warps per CTA in the kNN kernel
+constexpr int KNN_BOX_CACHE = 256;    // blocks per bucket whose box distance is kept in shared memory between the two passes
 constexpr int SC_WARPS = 4;           // warps per CTA in the score kernel (7.2 KB of scratch per warp)
 constexpr int MAX_POT_PAIRS = 400;    // 4 layers x 10 x 10 neighbour pairs
 constexpr double C2G_PI = 3.14159265358979323846;
@@ -67,6 +68,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
            unsigned long long *__restrict__ work) {
   __shared__ float merge_d[QK_WARPS][64];
   __shared__ int merge_i[QK_WARPS][64], merge_o[QK_WARPS][64];
+  __shared__ float box_cache[QK_WARPS][KNN_BOX_CACHE];  // box distances of a bucket's first blocks: computed once, used by both passes
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * QK_WARPS + (threadIdx.x >> 5);
   const int keys_per_scan = Q.n_q_levels * C2G_MAX_PIV;
@@ -218,12 +220,15 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
       const int beg = bk * T.cap_b, end = beg + T.bucket_cnt[bk];
       if (beg >= end) continue;
       const int b0 = bk * T.blkcap_b, nb = (T.bucket_cnt[bk] + 31) >> 5;
-      n_boxes += 2 * nb;
+      n_boxes += nb + (nb > KNN_BOX_CACHE ? nb - KNN_BOX_CACHE : 0);
       // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
       float best = 3.0e38f;
       int best_j = 0x7FFFFFFF;
+      float *bc = box_cache[threadIdx.x >> 5];
+      __syncwarp();
       for (int j = lane; j < nb; j += 32) {
         const float bdist = box_dist(b0 + j);
+        if (j < KNN_BOX_CACHE) bc[j] = bdist;
         if (bdist < best) {
           best = bdist;
           best_j = j;
@@ -242,7 +247,7 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
       // pass 2: every other block whose box can still hold an admissible key
       for (int j0 = 0; j0 < nb; j0 += 32) {
         const int j = j0 + lane;
-        const float bdist = j < nb ? box_dist(b0 + j) : 3.0e38f;
+        const float bdist = j < nb ? (j < KNN_BOX_CACHE ? bc[j] : box_dist(b0 + j)) : 3.0e38f;  // a lane reads what it wrote itself
         unsigned todo = __ballot_sync(0xFFFFFFFFu, j < nb && j != seed && bdist <= thr);
         while (todo) {
           const int src = __ffs(todo) - 1;
@@ -1506,10 +1511,15 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   }
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long) * C2G_WORK_N));
   C2G_CUDA_TRY(cudaMemset(ctx->d_work, 0, sizeof(unsigned long long) * C2G_WORK_N));
-  ctx->patch_cap = 1 << 20;
+  ctx->patch_cap = 4 << 20;
+  ctx->patch_off = 0;
+  ctx->patch_head = 0;
   C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ctx->patch_cap, cudaHostAllocDefault));
   C2G_CUDA_TRY(cudaMalloc(&ctx->d_patch, ctx->patch_cap));
-  C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_patch, cudaEventDisableTiming));
+  for (int i = 0; i < C2G_PATCH_RING; ++i) {
+    ctx->patch_ring[i].used = 0;
+    C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->patch_ring[i].ev, cudaEventDisableTiming));
+  }
   return 0;
 }
 
@@ -1537,7 +1547,8 @@ void c2g_query_free(c2g_ctx *ctx) {
   }
   if (ctx->h_patch) cudaFreeHost(ctx->h_patch);
   cudaFree(ctx->d_patch);
-  if (ctx->ev_patch) cudaEventDestroy(ctx->ev_patch);
+  for (int i = 0; i < C2G_PATCH_RING; ++i)
+    if (ctx->patch_ring[i].ev) cudaEventDestroy(ctx->patch_ring[i].ev);
 }
 
 extern "C" {
@@ -1636,31 +1647,52 @@ void patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigne
 int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
   if (lp.recs.empty() && lp.blks.empty()) return 0;
   const size_t rb = lp.recs.size() * sizeof(PatchRec), bb = lp.blks.size() * sizeof(PatchBlk), rb_al = (rb + 255) / 256 * 256;
-  if (rb_al + bb > ctx->patch_cap) {
+  const size_t need = (rb_al + bb + 255) / 256 * 256;
+  if (need > ctx->patch_cap) {  // a patch larger than the whole ring: grow it (everything in flight is finished first)
     C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     size_t ncap = ctx->patch_cap;
-    while (ncap < rb_al + bb) ncap *= 2;
+    while (ncap < need) ncap *= 2;
     cudaFreeHost(ctx->h_patch);
     cudaFree(ctx->d_patch);
     ctx->h_patch = ctx->d_patch = nullptr;
     C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ncap, cudaHostAllocDefault));
     C2G_CUDA_TRY(cudaMalloc(&ctx->d_patch, ncap));
     ctx->patch_cap = ncap;
+    ctx->patch_off = 0;
+    for (int i = 0; i < C2G_PATCH_RING; ++i) ctx->patch_ring[i].used = 0;
   }
-  // the device staging buffer is free once the kernels of the previous patch are done: they run on the same stream
-  C2G_CUDA_TRY(cudaEventSynchronize(ctx->ev_patch));
-  memcpy(ctx->h_patch, lp.recs.data(), rb);
-  memcpy((char *) ctx->h_patch + rb_al, lp.blks.data(), bb);
-  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_patch, ctx->h_patch, rb_al + bb, cudaMemcpyHostToDevice, ctx->stream));
-  C2G_CUDA_TRY(cudaEventRecord(ctx->ev_patch, ctx->stream));
+  if (ctx->patch_off + need > ctx->patch_cap) ctx->patch_off = 0;  // wrap
+  const size_t beg = ctx->patch_off, end = beg + need;
+  // the stretch (and the ring entry that will describe it) must not belong to a patch whose kernels have not run yet
+  for (int i = 0; i < C2G_PATCH_RING; ++i) {
+    auto &e = ctx->patch_ring[i];
+    if (e.used && (i == ctx->patch_head || (e.beg < end && beg < e.end))) {
+      C2G_CUDA_TRY(cudaEventSynchronize(e.ev));
+      e.used = 0;
+    }
+  }
+  char *hp = (char *) ctx->h_patch + beg;
+  const char *dp = (const char *) ctx->d_patch + beg;
+  memcpy(hp, lp.recs.data(), rb);
+  memcpy(hp + rb_al, lp.blks.data(), bb);
+  C2G_CUDA_TRY(cudaMemcpyAsync((void *) dp, hp, rb_al + bb, cudaMemcpyHostToDevice, ctx->stream));
   const int stride = C2G_NUM_BUCKETS * t.cap_b, bstride = C2G_NUM_BUCKETS * t.blkcap_b;
   if (!lp.recs.empty())
-    mirror_patch_kernel<<<(unsigned) ((lp.recs.size() + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) ctx->d_patch, (int) lp.recs.size(), t.keys_t,
-                                                                                          stride, t.gidx, t.seq, t.orank);
+    mirror_patch_kernel<<<(unsigned) ((lp.recs.size() + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) dp, (int) lp.recs.size(), t.keys_t, stride,
+                                                                                          t.gidx, t.seq, t.orank);
   if (!lp.blks.empty())
-    mirror_box_kernel<<<(unsigned) ((lp.blks.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>((const PatchBlk *) ((const char *) ctx->d_patch + rb_al),
-                                                                                             (int) lp.blks.size(), t.keys_t, stride, t.box_min, t.box_max, bstride);
+    mirror_box_kernel<<<(unsigned) ((lp.blks.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>((const PatchBlk *) (dp + rb_al), (int) lp.blks.size(), t.keys_t,
+                                                                                             stride, t.box_min, t.box_max, bstride);
   C2G_CUDA_TRY(cudaGetLastError());
+  {
+    auto &e = ctx->patch_ring[ctx->patch_head];
+    e.beg = beg;
+    e.end = end;
+    e.used = 1;
+    C2G_CUDA_TRY(cudaEventRecord(e.ev, ctx->stream));
+    ctx->patch_head = (ctx->patch_head + 1) % C2G_PATCH_RING;
+  }
+  ctx->patch_off = end;
   ctx->launches += 2;
   return 0;
 }
