@@ -75,7 +75,6 @@ struct c2g_ctx {
   cudaStream_t qstream[C2G_QUERY_STREAMS];
   cudaEvent_t ev_qfork, ev_qjoin[C2G_QUERY_STREAMS];
   int *d_survivors, *d_nsurv;  // hint slots that pass the thread-per-hint prefilter, and their count
-  int *d_deferred;             // survivors whose pair lists exceed the small-capacity scoring launch
   uint32_t *d_pair_scratch;    // per (query, pre-selected candidate): ellipse pairs of the GMM-L2 refinement (refine.cu)
   int pair_cap;
   long long n_hint_slots;  // max_batch * n_q_levels * C2G_MAX_PIV * nnk

@@ -139,17 +139,17 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
       r += g[9] * g[9];
       return r;
     };
-    // distance of this lane's key of block [base, end) to the query (nanoflann L2_Adaptor::evalMetric: groups of four, then the
-    // remainder one by one) and its tree-order rank; +big for a lane past the end
-    auto block_dist = [&](int base, int end, float &dist, int &orig) {
+    auto scan_block = [&](int base, int end) {
       const int i = base + lane;
+      const bool in = i < end;
       n_keys_eval += end - base;
-      dist = 3.0e38f;
-      orig = 0x7FFFFFFF;
-      if (i < end) {
+      float dist = 3.0e38f;
+      int orig = 0x7FFFFFFF;
+      if (in) {
         float df[C2G_KEY_DIM];
 #pragma unroll
         for (int d = 0; d < C2G_KEY_DIM; ++d) df[d] = key[d] - T.keys_t[(size_t) d * T.cap + i];
+        // nanoflann L2_Adaptor::evalMetric: groups of four, then the remainder one by one
         // (stopping after the first group when it alone exceeds the bound for the whole block was measured 15 % slower:
         // the kd blocks are not tight enough in those four dimensions for the vote to pass often)
         float r = 0.0f;
@@ -160,10 +160,6 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
         dist = r;
         orig = T.orank[i];
       }
-    };
-    auto merge_block = [&](int base, int end, float dist, int orig) {
-      const int i = base + lane;
-      const bool in = i < end;
       const unsigned cand = __ballot_sync(0xFFFFFFFFu, in && (dist < thr || (dist == thr && orig < thr_o)));
       if (cand == 0u) return;
       // Batch merge of the block's admissible keys into the sorted top-64: every (distance, tree rank) pair is unique, so the
@@ -247,39 +243,19 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
         }
       }
       const int seed = best_j;  // 0x7FFFFFFF when every box distance is NaN (NaN query key): nothing is admitted anyway
-      if (seed < nb && best <= thr) {
-        float d0;
-        int o0;
-        block_dist(beg + seed * 32, min(end, beg + seed * 32 + 32), d0, o0);
-        merge_block(beg + seed * 32, min(end, beg + seed * 32 + 32), d0, o0);
-      }
+      if (seed < nb && best <= thr) scan_block(beg + seed * 32, min(end, beg + seed * 32 + 32));
       // pass 2: every other block whose box can still hold an admissible key
       for (int j0 = 0; j0 < nb; j0 += 32) {
         const int j = j0 + lane;
         const float bdist = j < nb ? (j < KNN_BOX_CACHE ? bc[j] : box_dist(b0 + j)) : 3.0e38f;  // a lane reads what it wrote itself
         unsigned todo = __ballot_sync(0xFFFFFFFFu, j < nb && j != seed && bdist <= thr);
-        // two blocks per step: the 2 x 10 key loads are in flight together (the kernel waits on L2 latency, not bandwidth); the
-        // second block is merged against the bound the first one may have tightened, exactly as if it were scanned afterwards
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
           const float bsrc = __shfl_sync(0xFFFFFFFFu, bdist, src);
           if (!(bsrc <= thr)) continue;  // the bound tightened while earlier blocks of this group were scanned
           const int base = beg + (j0 + src) * 32;
-          int src2 = -1;
-          if (todo) {
-            src2 = __ffs(todo) - 1;
-            todo &= todo - 1;
-          }
-          const float bsrc2 = __shfl_sync(0xFFFFFFFFu, bdist, src2 < 0 ? 0 : src2);
-          const bool two = src2 >= 0 && bsrc2 <= thr;
-          const int base2 = beg + (j0 + (two ? src2 : src)) * 32;
-          float d0, d1 = 3.0e38f;
-          int o0, o1 = 0x7FFFFFFF;
-          block_dist(base, min(end, base + 32), d0, o0);
-          if (two) block_dist(base2, min(end, base2 + 32), d1, o1);
-          merge_block(base, min(end, base + 32), d0, o0);
-          if (two && bsrc2 <= thr) merge_block(base2, min(end, base2 + 32), d1, o1);
+          scan_block(base, min(end, base + 32));
         }
       }
     }
@@ -651,12 +627,7 @@ __device__ __forceinline__ const c2g_view &view_of(const c2g_scan_head *heads, c
   return views[(size_t) slot * C2G_VIEW_CAP + heads[slot].view_off[level] + seq];
 }
 
-// CAP = capacity of the per-thread lists.  Most hints collect a few dozen potential pairs; the worst case is 400 (4 layers x 10 x
-// 10).  The lists live in local memory, so a thread that reserves the worst case drags 4.8 KB through L1/L2 per hint; the kernel
-// therefore runs with CAP = 64 first and hands the few hints that need more to a second launch with the full capacity.  Returns
-// false (record untouched) when the hint needs more than CAP entries.
-template <int CAP>
-__device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *views, int q_slot, const c2g_hint &hint, const QueryParams &Q,
+__device__ void score_hint_serial(const c2g_scan_head *heads, const c2g_view *views, int q_slot, const c2g_hint &hint, const QueryParams &Q,
                                   c2g_pair_score &rec) {
   const int cand = hint.cand_gidx, level = hint.level, cseq = hint.cand_seq, qseq = hint.q_seq;
   const c2g_bci &src = heads[cand].bcis[level][cseq];
@@ -671,9 +642,9 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
       asm volatile("prefetch.global.L1 [%0];" ::"l"(pt + (o < (int) sizeof(c2g_bci) ? o : (int) sizeof(c2g_bci) - 1)));
     }
   }
-  unsigned long long pot[CAP];  // (orie_diff bits << 32) | level << 16 | seq_src << 8 | seq_tgt
-  CPairD c2[CAP + 1];
-  uint8_t drop[CAP + 1];
+  unsigned long long pot[MAX_POT_PAIRS];  // (orie_diff bits << 32) | level << 16 | seq_src << 8 | seq_tgt
+  CPairD c2[MAX_POT_PAIRS + 1];
+  uint8_t drop[MAX_POT_PAIRS + 1];
   {
     int ov1 = 0, ov2 = 0, ov3 = 0;
     for (int i = 0; i < 4; ++i) {
@@ -691,11 +662,11 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
   if (!check_sim(view_of(heads, views, cand, level, cseq), view_of(heads, views, q_slot, level, qseq), Q.sim)) {
     rec.constell[0] = rec.constell[1] = 0;  // cannot happen for prefilter survivors; an anchor failure keeps an all-zero record
     rec.passed = 0;
-    return true;
+    return;
   }
   if (!(rec.constell[0] >= Q.lb.i_ovlp_sum && rec.constell[1] >= Q.lb.i_ovlp_max_one)) {
     rec.passed = -1;
-    return true;
+    return;
   }
   // (2/4) BCI::checkConstellSim (contour_mng.h:309-388): potential pairs, sort by orientation difference, circular window
   int npot = 0;
@@ -711,8 +682,7 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
       for (int i = tgt.seg[p2]; i < tgt.seg[p2 + 1]; i++) {
         const c2g_relpt ti = tgt.nei[i];
         for (int j = j0; j < j1; j++) {
-          if (CAP < MAX_POT_PAIRS && npot >= CAP) return false;  // needs the full-capacity launch
-          if (npot < CAP) {
+          if (npot < MAX_POT_PAIRS) {
             const c2g_relpt sj = src.nei[j];
             const float od = clamp_ang_f(ti.theta - sj.theta);
             pot[npot++] = ((unsigned long long) __float_as_uint(od) << 32) | ((unsigned long long) (uint8_t) sj.level << 16) |
@@ -747,7 +717,7 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
   rec.constell[2] = longest;
   if (longest < Q.lb.i_in_ang_rng) {
     rec.passed = -1;
-    return true;
+    return;
   }
   // (3/4) checkConstellCorrespSim step 1 (contour_mng.h:1135-1152): individual similarity of the window's pairs + the anchor
   int n2 = 0;
@@ -769,7 +739,7 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
   rec.pairwise[1] = 0;
   if (n2 < Q.lb.i_indiv_sim) {
     rec.passed = -2;
-    return true;
+    return;
   }
   // step 2.1: the "shaft" (the last qualifying (i, j) among the first <= 10 pairs wins, see SURVEY.md §8a' #6)
   float ssx = 0.f, ssy = 0.f, stx = 0.f, sty = 0.f;
@@ -816,7 +786,7 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
   rec.pairwise[1] = n2;
   if (n2 < Q.lb.i_orie_sim) {
     rec.passed = -2;
-    return true;
+    return;
   }
   // getTFFromConstell: 2-D Umeyama without scaling, closed form (double), sums in list order
   const double inv_n = 1.0 / (double) n2;
@@ -861,16 +831,13 @@ __device__ bool score_hint_serial(const c2g_scan_head *heads, const c2g_view *vi
     const int bit = (c2[i].level - 1) * 100 + c2[i].seq_src * 10 + c2[i].seq_tgt;
     rec.pair_bits[bit >> 6] |= 1ull << (bit & 63);
   }
-  return true;
 }
 
-// Stage 2 (thread version): one THREAD per surviving hint.  CAP < MAX_POT_PAIRS: hints that need longer lists are appended to
-// `deferred` (count in *n_deferred) for the full-capacity launch, which reads that list instead of `survivors`.
-template <int CAP>
+// Stage 2 (thread version): one THREAD per surviving hint.
 __global__ void __launch_bounds__(128)
 score_thread_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__restrict__ views, int first_slot, QueryParams Q,
                     const c2g_hint *__restrict__ hints, c2g_pair_score *__restrict__ scores, const int *__restrict__ survivors,
-                    const int *__restrict__ n_surv, int *__restrict__ deferred, int *__restrict__ n_deferred) {
+                    const int *__restrict__ n_surv) {
   const int n = *n_surv;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int hid = survivors[i];
@@ -884,10 +851,8 @@ score_thread_kernel(const c2g_scan_head *__restrict__ heads, const c2g_view *__r
     rec.T[0] = rec.T[1] = rec.T[2] = rec.T[3] = 0.0;
     for (int k = 0; k < C2G_PAIR_WORDS; ++k) rec.pair_bits[k] = 0ull;
     rec.pad2_ = 0ull;
-    if (score_hint_serial<CAP>(heads, views, first_slot + h.q_idx, h, Q, rec))
-      scores[hid] = rec;
-    else
-      deferred[atomicAdd(n_deferred, 1)] = hid;
+    score_hint_serial(heads, views, first_slot + h.q_idx, h, Q, rec);
+    scores[hid] = rec;
   }
 }
 
@@ -1516,8 +1481,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_scores, sizeof(c2g_pair_score) * (size_t) ctx->n_hint_slots));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_results, sizeof(c2g_query_result) * (size_t) ctx->max_batch));
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_survivors, sizeof(int) * (size_t) ctx->n_hint_slots));
-  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int) * 2 * C2G_QUERY_STREAMS));  // survivor counts, then deferred counts
-  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_deferred, sizeof(int) * (size_t) ctx->n_hint_slots));
+  C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_nsurv, sizeof(int) * C2G_QUERY_STREAMS));
   for (int i = 0; i < C2G_QUERY_STREAMS; ++i) {
     C2G_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->qstream[i], cudaStreamNonBlocking));
     C2G_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_qjoin[i], cudaEventDisableTiming));
@@ -1565,7 +1529,6 @@ void c2g_query_free(c2g_ctx *ctx) {
   cudaFree(ctx->d_results);
   cudaFree(ctx->d_survivors);
   cudaFree(ctx->d_nsurv);
-  cudaFree(ctx->d_deferred);
   cudaFree(ctx->d_work);
   for (int i = 0; i < C2G_QUERY_STREAMS; ++i) {
     if (ctx->qstream[i]) cudaStreamDestroy(ctx->qstream[i]);
@@ -1820,7 +1783,7 @@ static int launch_query_chain(c2g_ctx *ctx, int first_slot, int B, const QueryPa
   static const int split_env = getenv("C2G_QUERY_SPLIT") ? atoi(getenv("C2G_QUERY_SPLIT")) : 4;
   int n_sub = ctx->prof_on ? 1 : (split_env < 1 ? 1 : (split_env > C2G_QUERY_STREAMS ? C2G_QUERY_STREAMS : split_env));
   if (B < 2 * n_sub) n_sub = 1;
-  C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int) * 2 * C2G_QUERY_STREAMS, ctx->stream));
+  C2G_CUDA_TRY(cudaMemsetAsync(ctx->d_nsurv, 0, sizeof(int) * C2G_QUERY_STREAMS, ctx->stream));
   if (n_sub > 1) C2G_CUDA_TRY(cudaEventRecord(ctx->ev_qfork, ctx->stream));
   const long long per_q = (long long) Q.n_q_levels * C2G_MAX_PIV * Q.nnk;
   for (int sb = 0; sb < n_sub; ++sb) {
@@ -1845,14 +1808,8 @@ static int launch_query_chain(c2g_ctx *ctx, int first_slot, int B, const QueryPa
     if (!warp_variant) {
       const long long want = (n_hints + 127) / 128;
       const long long cap = (long long) ctx->num_sms * 8;
-      int *defer = ctx->d_deferred + hid0, *ndefer = ctx->d_nsurv + C2G_QUERY_STREAMS + sb;
-      score_thread_kernel<64><<<(unsigned) (want < cap ? want : cap), 128, 0, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores,
-                                                                                     surv, nsurv, defer, ndefer);
-      C2G_CUDA_TRY(cudaGetLastError());
-      // the few hints with more than 64 potential pairs: full-capacity lists (the grid strides over the deferred list)
-      score_thread_kernel<MAX_POT_PAIRS><<<ctx->num_sms, 128, 0, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores, defer,
-                                                                        ndefer, nullptr, nullptr);
-      ctx->launches += 1;
+      score_thread_kernel<<<(unsigned) (want < cap ? want : cap), 128, 0, st>>>(ctx->d_heads, ctx->d_views, first_slot, Q, ctx->d_hints, ctx->d_scores, surv,
+                                                                               nsurv);
     } else {
       const long long want = (n_hints + SC_WARPS - 1) / SC_WARPS;
       const long long cap = (long long) ctx->num_sms * 16;
