@@ -58,6 +58,7 @@ def lib():
         L.c2g_online_commit.argtypes = [vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
         L.c2g_online_window.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
         L.c2g_work_counters.argtypes = [vp, ip, vp]
+        L.c2g_online_host_seconds.argtypes = [vp, vp]
         L.c2g_online_runs.restype = ll
         L.c2g_online_runs.argtypes = [vp]
         L.c2g_db_sync.argtypes = [vp]

@@ -588,6 +588,12 @@ int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_h
 
 long long c2g_online_runs(c2g_ctx *ctx) { return ctx ? ctx->online_runs : 0; }
 
+int c2g_online_host_seconds(c2g_ctx *ctx, double *out4) {
+  if (!ctx || !out4) return C2G_ERR_ARG;
+  for (int k = 0; k < 4; ++k) out4[k] = ctx->online_host_s[k];
+  return 0;
+}
+
 int c2g_work_counters(c2g_ctx *ctx, int enable, unsigned long long *out_host) {
   if (!ctx) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);

@@ -6,7 +6,7 @@
 #define C2G_QUERY_STREAMS 8  // sub-batches of one c2g_query_async call that may run concurrently
 #define C2G_WORK_N 8   // knn keys evaluated, knn block boxes tested, gate pre-selection tests, gate terms, refine pre-selection tests,
                        // refine pair terms (pairs x evaluations), refine evaluations, (spare)
-#define C2G_PATCH_RING 64
+#define C2G_PATCH_RING 2048
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
@@ -101,6 +101,7 @@ struct c2g_ctx {
   int n_staged, staged_head;  // FIFO of at most two windows (the next one is ingested while the current one is queried)
   unsigned long long *d_work;  // [C2G_WORK_N] work counters of the query kernels (c2g_work_counters); handed to the kernels only while enabled
   int count_work;
+  double online_host_s[4];    // host seconds spent by c2g_online_commit: LayerDB bookkeeping, kNN launches, mirror patches, chain launches
   long long online_runs;      // kNN launches of the windowed loop so far (= runs of scans that saw identical trees)
   // optional per-kernel timing of the query path (c2g_query_profile): event k is recorded after kernel k - 1
   int prof_on;

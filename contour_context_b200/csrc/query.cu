@@ -20,6 +20,7 @@
 #include "c2g_ctx.cuh"
 #include "layer_db_host.h"
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "stdsort.cuh"
@@ -1511,7 +1512,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
   }
   C2G_CUDA_TRY(cudaMalloc((void **) &ctx->d_work, sizeof(unsigned long long) * C2G_WORK_N));
   C2G_CUDA_TRY(cudaMemset(ctx->d_work, 0, sizeof(unsigned long long) * C2G_WORK_N));
-  ctx->patch_cap = 4 << 20;
+  ctx->patch_cap = 16 << 20;
   ctx->patch_off = 0;
   ctx->patch_head = 0;
   C2G_CUDA_TRY(cudaHostAlloc(&ctx->h_patch, ctx->patch_cap, cudaHostAllocDefault));
@@ -1883,6 +1884,13 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
   build_query_params(ctx, lb, Q);
   int run_begin = 0, n_runs = 0;
   const size_t kstride = (size_t) C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_mark = now();
+  auto lap = [&](int k) {
+    const double t = now();
+    ctx->online_host_s[k] += t - t_mark;
+    t_mark = t;
+  };
   for (int i = 0; i < W; ++i) {
     const unsigned long long v0 = db.tree_version;
     const float *sk = keys_host + (size_t) i * kstride;
@@ -1894,23 +1902,29 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     db.n_scans++;
     c2g_hostdb_push_and_balance(db, seeds_host[i], ts_host[i]);
     if (db.tree_version != v0) {  // scans run_begin..i saw the trees as mirrored now; scan i + 1 sees the new ones
+      lap(0);
       int rc = launch_knn(ctx, first_slot, run_begin, i + 1 - run_begin, Q, ctx->stream);
       if (rc) return rc;
+      lap(1);
       ++n_runs;
       run_begin = i + 1;
       rc = sync_mirror();
       if (rc) return rc;
       build_query_params(ctx, lb, Q);
+      lap(2);
     }
   }
+  lap(0);
   if (run_begin < W) {
     int rc = launch_knn(ctx, first_slot, run_begin, W - run_begin, Q, ctx->stream);
     if (rc) return rc;
     ++n_runs;
   }
   ctx->online_runs += n_runs;
+  lap(1);
   int rc = launch_query_chain(ctx, first_slot, W, Q, 0);
   if (rc) return rc;
+  lap(3);
   if (results_host)
     C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) W, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;

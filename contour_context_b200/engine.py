@@ -154,6 +154,12 @@ class Engine:
         self.check_results(res)
         return res
 
+    def online_host_seconds(self) -> dict:
+        """Host seconds spent so far inside online_commit, by part (measurement aid)."""
+        out = np.zeros(4, np.float64)
+        capi.check(capi.lib().c2g_online_host_seconds(self.h, capi.ptr(out)), "c2g_online_host_seconds")
+        return dict(zip(("layerdb_bookkeeping", "knn_launches", "mirror_patches", "chain_launches"), (float(v) for v in out)))
+
     def online_runs(self) -> int:
         return int(capi.lib().c2g_online_runs(self.h))
 

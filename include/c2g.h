@@ -123,6 +123,9 @@ int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_h
                       const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
                       c2g_query_result *results_host);
 long long c2g_online_runs(c2g_ctx *ctx);
+/* Measurement aid: host seconds c2g_online_commit has spent so far in [0] the LayerDB bookkeeping, [1] kNN launches, [2] mirror
+ * patches, [3] the launches of the rest of the chain. */
+int c2g_online_host_seconds(c2g_ctx *ctx, double *out4);
 /* Upload the host-side tree contents to the device tables if they changed (c2g_query* call it implicitly). */
 int c2g_db_sync(c2g_ctx *ctx);
 /* Introspection for parity tests: bucket boundaries [7], tree sizes [6], buffer sizes [6]; one bucket's tree in order. */
