@@ -105,6 +105,7 @@ int stage_inputs(c2g_ctx *ctx, const float *pts, const long long *offsets_host, 
   const long long total = offsets_host[B] - offsets_host[0];
   if (total < 0) return C2G_ERR_ARG;
   C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_offsets, offsets_host, sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->last_offsets = ctx->d_offsets;
   if (pts_on_device) {
     if (((uintptr_t) pts) & (fpp == 4 ? 15 : 3)) return C2G_ERR_ARG;
     *pts_dev = pts;
@@ -197,12 +198,17 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
   }
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_stage_free[i], cudaEventDisableTiming);
   for (int i = 0; i < C2G_MAX_CHUNK_EVENTS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_patch_up, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     c2g_destroy(ctx);
     return -(int) e;
   }
   ALLOC(ctx->d_offsets, sizeof(long long) * (max_batch + 1));
   ALLOC(ctx->d_int_ids, sizeof(int) * max_batch);
+  for (int i = 0; i < 2; ++i) {
+    ALLOC(ctx->d_offsets2[i], sizeof(long long) * (max_batch + 1));
+    ALLOC(ctx->d_int_ids2[i], sizeof(int) * max_batch);
+  }
   {
     const size_t nwords = (size_t) ctx->P.cfg.n_row * ((ctx->P.cfg.n_col + 31) / 32);
     ALLOC(ctx->d_planes, sizeof(uint32_t) * C2G_NLEV * nwords * max_batch);
@@ -279,6 +285,11 @@ int c2g_destroy(c2g_ctx *ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_offsets);
   cudaFree(ctx->d_int_ids);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->d_offsets2[i]);
+    cudaFree(ctx->d_int_ids2[i]);
+  }
+  if (ctx->ev_patch_up) cudaEventDestroy(ctx->ev_patch_up);
   cudaFree(ctx->d_planes);
   cudaFree(ctx->d_fg);
   cudaFree(ctx->d_hdr);
@@ -351,7 +362,7 @@ int c2g_ingest_bev_only(c2g_ctx *ctx, const float *pts, const long long *offsets
 // Host inputs: the batch is cut into chunks of one wave (num_sms scans); chunk k+1 crosses PCIe on the copy stream while the
 // kernels of chunk k run, and the two staging buffers alternate between calls so that the copy of the NEXT call starts while
 // this call's query kernels are still running.  Device inputs: two launches for the whole batch.
-static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *ids_dev, int fpp) {
+static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int B, int first_slot, const int *int_ids_host, int fpp) {
   if (offsets_host[B] - offsets_host[0] > ctx->max_points) return C2G_ERR_CAPACITY;
   const int cur = ctx->stage_sel;
   ctx->stage_sel ^= 1;
@@ -359,9 +370,18 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
   // offsets relative to the staging buffer
   std::vector<long long> rel((size_t) B + 1);
   for (int i = 0; i <= B; ++i) rel[i] = offsets_host[i] - offsets_host[0];
-  C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_offsets, rel.data(), sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
-  // the copy stream may overwrite this staging buffer only after the kernels that last read it have finished
+  // the copy stream may overwrite this staging buffer (points, offsets, ids) only after the kernels that last read it have
+  // finished.  Everything host->device goes through the copy stream: a small copy issued on the kernel stream would sit in
+  // the copy queue behind whatever that stream still has to run, in front of the next batch's points.
   C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_free[cur], 0));
+  long long *d_off = ctx->d_offsets2[cur];
+  C2G_CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
+  const int *ids_dev = nullptr;
+  if (int_ids_host) {
+    C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids2[cur], int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ids_dev = ctx->d_int_ids2[cur];
+  }
+  ctx->last_offsets = d_off;
   const int CH = ctx->num_sms;
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += CH, ++k) {
@@ -372,7 +392,7 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
     C2G_CUDA_TRY(cudaEventRecord(ev, ctx->copy_stream));
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
     const C2gBevOut bo = bev_out(ctx, b0);
-    int rc = c2g_launch_bev_scatter(stage, ctx->d_offsets + b0, n, ctx->P, bo, 0, fpp == 3, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
+    int rc = c2g_launch_bev_scatter(stage, d_off + b0, n, ctx->P, bo, 0, fpp == 3, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
     if (rc) return rc;
     rc = c2g_launch_contours(bo, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
                              ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
@@ -390,12 +410,12 @@ static int ingest_impl(c2g_ctx *ctx, const float *pts, const long long *offsets_
                        const int *int_ids_host, int fpp) {
   if (!ctx || !pts || !offsets_host || B <= 0 || B > ctx->max_batch || first_slot < 0 || first_slot + B > ctx->scan_cap) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);
+  if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, int_ids_host, fpp);
   const int *ids_dev = nullptr;
   if (int_ids_host) {
     C2G_CUDA_TRY(cudaMemcpyAsync(ctx->d_int_ids, int_ids_host, sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
     ids_dev = ctx->d_int_ids;
   }
-  if (!pts_on_device) return ingest_host_pipelined(ctx, pts, offsets_host, B, first_slot, ids_dev, fpp);
   int rc = bev_only_impl(ctx, pts, offsets_host, B, pts_on_device, fpp);
   if (rc) return rc;
   rc = c2g_launch_contours(bev_out(ctx, 0), B, ctx->P, ids_dev, first_slot, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells, ctx->d_k2_scratch,
@@ -441,7 +461,7 @@ static int rescatter_full(c2g_ctx *ctx, int batch_index) {
   o.fg = ctx->d_fg1;
   o.hdr = ctx->d_hdr1;
   o.tiles = ctx->d_tile1;
-  int rc = c2g_launch_bev_scatter(ctx->last_pts, ctx->d_offsets + batch_index, 1, ctx->P, o, 1, ctx->last_fpp == 3, ctx->d_work_counter_k1, ctx->num_sms,
+  int rc = c2g_launch_bev_scatter(ctx->last_pts, ctx->last_offsets + batch_index, 1, ctx->P, o, 1, ctx->last_fpp == 3, ctx->d_work_counter_k1, ctx->num_sms,
                                   ctx->stream);
   if (rc) return rc;
   ctx->launches += 1;
@@ -454,7 +474,7 @@ int c2g_get_bev(c2g_ctx *ctx, int batch_index, float *bev, float *row_f, float *
   const size_t n = ctx->P.n_cells;
   int rc = rescatter_full(ctx, batch_index);
   if (rc) return rc;
-  rc = c2g_launch_bev_fill(ctx->d_tile1, ctx->last_pts, ctx->d_offsets, batch_index, ctx->last_fpp, ctx->P, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf,
+  rc = c2g_launch_bev_fill(ctx->d_tile1, ctx->last_pts, ctx->last_offsets, batch_index, ctx->last_fpp, ctx->P, ctx->d_bev_h, ctx->d_bev_rf, ctx->d_bev_cf,
                            ctx->stream);
   if (rc) return rc;
   ctx->launches += 1;

@@ -42,8 +42,12 @@ struct c2g_ctx {
   cudaStream_t copy_stream;            // H2D of chunk k+1 overlaps the kernels of chunk k
   cudaEvent_t ev_stage_free[2];        // recorded when the kernels reading a staging buffer are done
   cudaEvent_t ev_chunk[C2G_MAX_CHUNK_EVENTS];
-  long long *d_offsets;
+  long long *d_offsets;                // offsets / internal ids of a batch whose points came by device pointer or c2g_bev_only
   int *d_int_ids;
+  long long *d_offsets2[2];            // the same per staging buffer of the pipelined host ingest (uploaded on the copy stream)
+  int *d_int_ids2[2];
+  const long long *last_offsets;       // offsets of the last batch (c2g_get_bev re-reads them)
+  cudaEvent_t ev_patch_up;             // a window's mirror patches have arrived (copy stream)
   // scatter kernel -> contour kernel hand-off of one batch: bit-planes, foreground cell lists, (occupied, foreground) counts
   uint32_t *d_planes;      // [max_batch][C2G_NLEV][n_row * ceil(n_col / 32)]
   float4 *d_fg;            // [max_batch][n_cells]

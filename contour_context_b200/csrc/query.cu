@@ -1643,14 +1643,12 @@ void patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigne
   t.m_valid[k] = 1;
 }
 
-// uploads one layer's patch and applies it on the context stream (everything asynchronous; the pinned staging buffer is
-// reused only after the previous upload has left it)
-int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
-  if (lp.recs.empty() && lp.blks.empty()) return 0;
-  const size_t rb = lp.recs.size() * sizeof(PatchRec), bb = lp.blks.size() * sizeof(PatchBlk), rb_al = (rb + 255) / 256 * 256;
-  const size_t need = (rb_al + bb + 255) / 256 * 256;
+// The patch staging ring: a pinned host buffer and its device twin, carved into stretches.  A stretch (and the ring entry that
+// describes it) is reused only after the kernels of the patch that last occupied it have run.
+int patch_ring_alloc(c2g_ctx *ctx, size_t need, size_t *beg_out) {
   if (need > ctx->patch_cap) {  // a patch larger than the whole ring: grow it (everything in flight is finished first)
     C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    C2G_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     size_t ncap = ctx->patch_cap;
     while (ncap < need) ncap *= 2;
     cudaFreeHost(ctx->h_patch);
@@ -1664,7 +1662,6 @@ int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
   }
   if (ctx->patch_off + need > ctx->patch_cap) ctx->patch_off = 0;  // wrap
   const size_t beg = ctx->patch_off, end = beg + need;
-  // the stretch (and the ring entry that will describe it) must not belong to a patch whose kernels have not run yet
   for (int i = 0; i < C2G_PATCH_RING; ++i) {
     auto &e = ctx->patch_ring[i];
     if (e.used && (i == ctx->patch_head || (e.beg < end && beg < e.end))) {
@@ -1672,29 +1669,79 @@ int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
       e.used = 0;
     }
   }
+  *beg_out = beg;
+  return 0;
+}
+
+// marks [beg, beg + need) busy until everything enqueued on the context stream so far has run
+int patch_ring_commit(c2g_ctx *ctx, size_t beg, size_t need) {
+  auto &e = ctx->patch_ring[ctx->patch_head];
+  e.beg = beg;
+  e.end = beg + need;
+  e.used = 1;
+  C2G_CUDA_TRY(cudaEventRecord(e.ev, ctx->stream));
+  ctx->patch_head = (ctx->patch_head + 1) % C2G_PATCH_RING;
+  ctx->patch_off = beg + need;
+  return 0;
+}
+
+// the two kernels that apply one layer's uploaded patch (records at dp, blocks at dp + blks_off)
+int launch_patch_kernels(c2g_ctx *ctx, C2gLayerTable &t, const char *dp, int n_recs, size_t blks_off, int n_blks) {
+  const int stride = C2G_NUM_BUCKETS * t.cap_b, bstride = C2G_NUM_BUCKETS * t.blkcap_b;
+  if (n_recs > 0)
+    mirror_patch_kernel<<<(unsigned) ((n_recs + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) dp, n_recs, t.keys_t, stride, t.gidx, t.seq, t.orank);
+  if (n_blks > 0)
+    mirror_box_kernel<<<(unsigned) ((n_blks * 32 + 255) / 256), 256, 0, ctx->stream>>>((const PatchBlk *) (dp + blks_off), n_blks, t.keys_t, stride, t.box_min,
+                                                                                      t.box_max, bstride);
+  C2G_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 2;
+  return 0;
+}
+
+// uploads one layer's patch and applies it on the context stream (everything asynchronous)
+int apply_patch(c2g_ctx *ctx, C2gLayerTable &t, const LayerPatch &lp) {
+  if (lp.recs.empty() && lp.blks.empty()) return 0;
+  const size_t rb = lp.recs.size() * sizeof(PatchRec), bb = lp.blks.size() * sizeof(PatchBlk), rb_al = (rb + 255) / 256 * 256;
+  const size_t need = (rb_al + bb + 255) / 256 * 256;
+  size_t beg = 0;
+  int rc = patch_ring_alloc(ctx, need, &beg);
+  if (rc) return rc;
   char *hp = (char *) ctx->h_patch + beg;
   const char *dp = (const char *) ctx->d_patch + beg;
   memcpy(hp, lp.recs.data(), rb);
   memcpy(hp + rb_al, lp.blks.data(), bb);
   C2G_CUDA_TRY(cudaMemcpyAsync((void *) dp, hp, rb_al + bb, cudaMemcpyHostToDevice, ctx->stream));
-  const int stride = C2G_NUM_BUCKETS * t.cap_b, bstride = C2G_NUM_BUCKETS * t.blkcap_b;
-  if (!lp.recs.empty())
-    mirror_patch_kernel<<<(unsigned) ((lp.recs.size() + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) dp, (int) lp.recs.size(), t.keys_t, stride,
-                                                                                          t.gidx, t.seq, t.orank);
-  if (!lp.blks.empty())
-    mirror_box_kernel<<<(unsigned) ((lp.blks.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>((const PatchBlk *) (dp + rb_al), (int) lp.blks.size(), t.keys_t,
-                                                                                             stride, t.box_min, t.box_max, bstride);
-  C2G_CUDA_TRY(cudaGetLastError());
-  {
-    auto &e = ctx->patch_ring[ctx->patch_head];
-    e.beg = beg;
-    e.end = end;
-    e.used = 1;
-    C2G_CUDA_TRY(cudaEventRecord(e.ev, ctx->stream));
-    ctx->patch_head = (ctx->patch_head + 1) % C2G_PATCH_RING;
+  rc = launch_patch_kernels(ctx, t, dp, (int) lp.recs.size(), rb_al, (int) lp.blks.size());
+  if (rc) return rc;
+  return patch_ring_commit(ctx, beg, need);
+}
+
+// one layer's patch of a window whose upload is deferred: where it sits in the window's staging block
+struct DeferredPatch {
+  int layer, n_recs, n_blks;
+  size_t off, blks_off;  // byte offset of the records in the block; of the blocks relative to the records
+};
+
+// like c2g_db_sync_mode(ctx, 0), but the patches are appended to `block` (host memory) instead of being uploaded
+int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<DeferredPatch> &out) {
+  for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+    const C2gLayerHost &L = ctx->hostdb->layers[ll];
+    C2gLayerTable &t = ctx->layers[ll];
+    LayerPatch lp;
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+      const C2gBucket &bk = L.buckets[k];
+      if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
+      patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp);
+    }
+    for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
+    if (lp.recs.empty() && lp.blks.empty()) continue;
+    const size_t rb = lp.recs.size() * sizeof(PatchRec), bb = lp.blks.size() * sizeof(PatchBlk), rb_al = (rb + 255) / 256 * 256;
+    const size_t need = (rb_al + bb + 255) / 256 * 256, off = block.size();
+    block.resize(off + need);
+    memcpy(block.data() + off, lp.recs.data(), rb);
+    memcpy(block.data() + off + rb_al, lp.blks.data(), bb);
+    out.push_back({ll, (int) lp.recs.size(), (int) lp.blks.size(), off, rb_al});
   }
-  ctx->patch_off = end;
-  ctx->launches += 2;
   return 0;
 }
 
@@ -1880,9 +1927,18 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     int rc = sync_mirror();
     if (rc) return rc;
   }
+  // Pass 1 (host only): the LayerDB bookkeeping of the whole window.  Every change of a tree ends a run of scans that saw
+  // the same trees; the run's kNN parameters are snapshotted and the mirror patch that follows it is appended to one block.
+  struct Run {
+    int q0, n, patch_begin, patch_end;
+    QueryParams Q;
+  };
+  std::vector<Run> runs;
+  std::vector<char> block;
+  std::vector<DeferredPatch> patches;
   QueryParams Q;
   build_query_params(ctx, lb, Q);
-  int run_begin = 0, n_runs = 0;
+  int run_begin = 0;
   const size_t kstride = (size_t) C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_mark = now();
@@ -1903,24 +1959,60 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     c2g_hostdb_push_and_balance(db, seeds_host[i], ts_host[i]);
     if (db.tree_version != v0) {  // scans run_begin..i saw the trees as mirrored now; scan i + 1 sees the new ones
       lap(0);
-      int rc = launch_knn(ctx, first_slot, run_begin, i + 1 - run_begin, Q, ctx->stream);
+      Run r;
+      r.q0 = run_begin;
+      r.n = i + 1 - run_begin;
+      r.Q = Q;
+      r.patch_begin = (int) patches.size();
+      int rc = collect_mirror_patches(ctx, block, patches);
       if (rc) return rc;
-      lap(1);
-      ++n_runs;
+      r.patch_end = (int) patches.size();
+      runs.push_back(r);
       run_begin = i + 1;
-      rc = sync_mirror();
-      if (rc) return rc;
+      ctx->db_dirty = 0;
+      ctx->db_not_kd = 1;
       build_query_params(ctx, lb, Q);
       lap(2);
     }
   }
-  lap(0);
   if (run_begin < W) {
-    int rc = launch_knn(ctx, first_slot, run_begin, W - run_begin, Q, ctx->stream);
-    if (rc) return rc;
-    ++n_runs;
+    Run r;
+    r.q0 = run_begin;
+    r.n = W - run_begin;
+    r.Q = Q;
+    r.patch_begin = r.patch_end = (int) patches.size();
+    runs.push_back(r);
   }
-  ctx->online_runs += n_runs;
+  lap(0);
+  // Pass 2: ONE upload of the window's patches, on the copy stream (all host->device traffic of the online loop is issued on
+  // that stream in the order it is needed, so a small copy never sits in the copy queue in front of the next window's points
+  // waiting for kernels of this window), then per run: kNN against the mirror as it is, then the patch that ends the run.
+  size_t beg = 0;
+  const char *dp = nullptr;
+  if (!block.empty()) {
+    int rc = patch_ring_alloc(ctx, block.size(), &beg);
+    if (rc) return rc;
+    memcpy((char *) ctx->h_patch + beg, block.data(), block.size());
+    dp = (const char *) ctx->d_patch + beg;
+    C2G_CUDA_TRY(cudaMemcpyAsync((void *) dp, (char *) ctx->h_patch + beg, block.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+    C2G_CUDA_TRY(cudaEventRecord(ctx->ev_patch_up, ctx->copy_stream));
+    C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_patch_up, 0));
+  }
+  lap(2);
+  for (const Run &r : runs) {
+    int rc = launch_knn(ctx, first_slot, r.q0, r.n, r.Q, ctx->stream);
+    if (rc) return rc;
+    for (int p = r.patch_begin; p < r.patch_end; ++p) {
+      const DeferredPatch &d = patches[p];
+      rc = launch_patch_kernels(ctx, ctx->layers[d.layer], dp + d.off, d.n_recs, d.blks_off, d.n_blks);
+      if (rc) return rc;
+    }
+  }
+  if (!block.empty()) {
+    int rc = patch_ring_commit(ctx, beg, block.size());
+    if (rc) return rc;
+  }
+  ctx->online_runs += (long long) runs.size();
   lap(1);
   int rc = launch_query_chain(ctx, first_slot, W, Q, 0);
   if (rc) return rc;
