@@ -121,8 +121,28 @@ def refine_problems(n_scenes=60, n_pts=60000, first_scene=900):
             q = c2o.Scan(cfg, 10000 + s0 + k).ingest(np.ascontiguousarray(pts[k]))
             res, _, _ = db.query(q, lb, ub)
             for c in res["cand"][: min(int(res["n_cand"]), dbc.max_fine_opt)]:
-                probs.append((scans[int(c["cand_gidx"])], q, np.array(c["T"]), float(c["corr_fine"]), int(c["fine_iters"])))
+                truth = int(c["cand_gidx"]) % n_scenes == s0 + k  # DB index = visit * n_scenes + scene
+                probs.append((scans[int(c["cand_gidx"])], q, np.array(c["T"]), float(c["corr_fine"]), int(c["fine_iters"]), s0 + k, truth))
     return probs
+
+
+def max_f1_top1(query_ids, corr, truth, n_queries):
+    """Max-F1 of the loop-closure decision 'report the query's best candidate if its correlation >= threshold' over all
+    thresholds (every query here is a revisit, so recall is counted against n_queries; scripts/pr_mpe.py:71-130 logic)."""
+    best = {}
+    for qid, c, t in zip(query_ids, corr, truth):
+        if qid not in best or c > best[qid][0]:
+            best[qid] = (c, t)
+    preds = sorted(best.values(), key=lambda x: -x[0])
+    tp = fp = 0
+    f1 = 0.0
+    for c, t in preds:
+        tp += bool(t)
+        fp += not t
+        prec, rec = tp / (tp + fp), tp / n_queries
+        if prec + rec > 0:
+            f1 = max(f1, 2 * prec * rec / (prec + rec))
+    return f1
 
 
 def refine_study(n_scenes=60, corr_thres=0.65):
@@ -130,7 +150,7 @@ def refine_study(n_scenes=60, corr_thres=0.65):
 
     probs = refine_problems(n_scenes)
     rows = []
-    for a, b, T, corr_fine, iters in probs:
+    for a, b, T, corr_fine, iters, qid, truth in probs:
         p0 = np.array([T[2], T[3], np.arctan2(T[1], T[0])])
         r = c2o.refine_solve(a, b, T)
         fun = lambda p: c2o.refine_eval(a, b, T, p)[0]  # noqa: E731
@@ -141,7 +161,7 @@ def refine_study(n_scenes=60, corr_thres=0.65):
         # ... and the converged optimum as the yardstick
         conv = minimize(fun, p0, jac=jac, method="BFGS", options=dict(maxiter=300, gtol=1e-10))
         norm = r["norm"]
-        rows.append((r["correlation"], -lb10.fun / norm, -bf10.fun / norm, -conv.fun / norm, r["iterations"], r["termination"], abs(corr_fine - r["correlation"])))
+        rows.append((r["correlation"], -lb10.fun / norm, -bf10.fun / norm, -conv.fun / norm, r["iterations"], r["termination"], abs(corr_fine - r["correlation"]), qid, truth))
     R = np.array(rows)
     d_lb, d_bf, d_cv = np.abs(R[:, 0] - R[:, 1]), np.abs(R[:, 0] - R[:, 2]), R[:, 3] - R[:, 0]
 
@@ -157,6 +177,10 @@ def refine_study(n_scenes=60, corr_thres=0.65):
                                     "vs_lbfgsb": int(((R[:, 0] >= corr_thres) != (R[:, 1] >= corr_thres)).sum()),
                                     "vs_bfgs": int(((R[:, 0] >= corr_thres) != (R[:, 2] >= corr_thres)).sum()),
                                     "vs_converged": int(((R[:, 0] >= corr_thres) != (R[:, 3] >= corr_thres)).sum())},
+        "max_f1_top1_per_query": {"queries": int(n_scenes), "restated": max_f1_top1(R[:, 7], R[:, 0], R[:, 8], n_scenes),
+                                  "scipy_lbfgsb_10it": max_f1_top1(R[:, 7], R[:, 1], R[:, 8], n_scenes),
+                                  "scipy_bfgs_10it": max_f1_top1(R[:, 7], R[:, 2], R[:, 8], n_scenes),
+                                  "converged": max_f1_top1(R[:, 7], R[:, 3], R[:, 8], n_scenes)},
         "iterations_hist": {int(k): int(v) for k, v in zip(*np.unique(R[:, 4], return_counts=True))},
         "query_result_equals_standalone_solve_max_abs": float(R[:, 6].max()),
     }
