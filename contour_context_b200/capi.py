@@ -55,6 +55,7 @@ def lib():
         L.c2g_db_push_and_balance.argtypes = [vp, ip, C.c_double]
         L.c2g_db_size.argtypes = [vp]
         L.c2g_online_stage.argtypes = [vp, vp, vp, ip, ip, vp]
+        L.c2g_online_stage_xyz.argtypes = [vp, vp, vp, ip, ip, vp]
         L.c2g_online_commit.argtypes = [vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
         L.c2g_online_window.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble), vp]
         L.c2g_work_counters.argtypes = [vp, ip, vp]

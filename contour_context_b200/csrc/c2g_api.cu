@@ -558,13 +558,13 @@ int c2g_db_add_scans(c2g_ctx *ctx, int first_slot, int n, const double *ts_host)
   return 0;
 }
 
-int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host) {
+static int online_stage_impl(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host, int fpp) {
   if (!ctx || W <= 0 || W > ctx->max_batch) return C2G_ERR_ARG;
   if (ctx->n_staged >= 2) return C2G_ERR_STATE;
   int first_slot = ctx->hostdb->n_scans;
   for (int k = 0; k < ctx->n_staged; ++k) first_slot += ctx->staged[(ctx->staged_head + k) & 1].W;
   if (first_slot + W > ctx->scan_cap) return C2G_ERR_CAPACITY;
-  int rc = c2g_ingest(ctx, pts, offsets_host, W, pts_on_device, first_slot, int_ids_host);
+  int rc = ingest_impl(ctx, pts, offsets_host, W, pts_on_device, first_slot, int_ids_host, fpp);
   if (rc) return rc;
   C2gDeviceGuard guard(ctx->device);
   auto &st = ctx->staged[(ctx->staged_head + ctx->n_staged) & 1];
@@ -578,6 +578,14 @@ int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_ho
   return 0;
 }
 
+int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host) {
+  return online_stage_impl(ctx, pts, offsets_host, W, pts_on_device, int_ids_host, 4);
+}
+
+int c2g_online_stage_xyz(c2g_ctx *ctx, const float *xyz, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host) {
+  return online_stage_impl(ctx, xyz, offsets_host, W, pts_on_device, int_ids_host, 3);
+}
+
 int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
                       c2g_query_result *results_host) {
   if (!ctx || !ts_host || !seeds_host || !lb || !ub) return C2G_ERR_ARG;
@@ -589,7 +597,6 @@ int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host
   if (rc) return rc;
   ctx->staged_head ^= 1;
   ctx->n_staged--;
-  ctx->db_dirty = 1;  // the trees may have changed after the window's last run was launched
   return 0;
 }
 

@@ -120,14 +120,14 @@ class Engine:
         capi.check(capi.lib().c2g_db_push_and_balance(self.h, seed, float(ts)), "c2g_db_push_and_balance")
 
     # ---- windowed online loop (query -> addScan -> pushAndBalance for W consecutive scans) ---------------------------------
-    def online_stage(self, pts, offsets, int_ids=None, on_device: bool = None):
-        """Ingest the next window into slots db_size.. and start reading its keys back (asynchronous)."""
+    def online_stage(self, pts, offsets, int_ids=None, on_device: bool = None, xyz: bool = False):
+        """Ingest the next window into slots db_size.. and start reading its keys back (asynchronous).  xyz: 12 B / point input."""
         offsets = np.ascontiguousarray(offsets, np.int64)
         if on_device is None:
             on_device = bool(getattr(pts, "is_cuda", False))
         ids = None if int_ids is None else np.ascontiguousarray(int_ids, np.int32)
-        capi.check(capi.lib().c2g_online_stage(self.h, capi.ptr(pts), capi.ptr(offsets), len(offsets) - 1, int(on_device),
-                                               capi.ptr(ids)), "c2g_online_stage")
+        fn = capi.lib().c2g_online_stage_xyz if xyz else capi.lib().c2g_online_stage
+        capi.check(fn(self.h, capi.ptr(pts), capi.ptr(offsets), len(offsets) - 1, int(on_device), capi.ptr(ids)), "c2g_online_stage")
 
     def online_commit(self, ts, seeds, lb: D.ScoreEnsemble, ub: D.ScoreEnsemble, results_out):
         """Bookkeeping + queries of the oldest staged window; results_out (numpy QUERY_RESULT_DTYPE array or pinned torch uint8

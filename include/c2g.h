@@ -117,6 +117,8 @@ int c2g_db_size(c2g_ctx *ctx);
  *   c2g_online_window  stage + commit + sync in one call.
  *   c2g_online_runs    kNN launches issued by the windowed loop so far (runs of scans that saw identical trees). */
 int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host);
+/* the same for 12 B / point buffers (x, y, z), as c2g_ingest_xyz */
+int c2g_online_stage_xyz(c2g_ctx *ctx, const float *xyz, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host);
 int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb,
                       const c2g_score_ensemble *ub, c2g_query_result *results_host);
 int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host,

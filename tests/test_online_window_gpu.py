@@ -86,8 +86,10 @@ def test_window_equals_scan_by_scan(built_lib, sequence, seq_result, window):
         eng.close()
 
 
-def test_pipelined_stage_commit(built_lib, sequence, seq_result):
-    """stage(k + 1) before commit(k): the next window's copy + ingest are in flight while window k is queried."""
+@pytest.mark.parametrize("xyz", [False, True])
+def test_pipelined_stage_commit(built_lib, sequence, seq_result, xyz):
+    """stage(k + 1) before commit(k): the next window's copy + ingest are in flight while window k is queried.  xyz: the 12 B /
+    point input variant (c2g_online_stage_xyz)."""
     import torch
     from contour_context_b200.engine import Engine
 
@@ -97,14 +99,15 @@ def test_pipelined_stage_commit(built_lib, sequence, seq_result):
     W = 24
     eng = Engine(scan_capacity=N_DB + 8, max_batch=W, max_points=W * 65536)
     try:
-        host = torch.from_numpy(pts).pin_memory()
+        host = torch.from_numpy(pts).reshape(-1, 4)
+        host = (host[:, :3].contiguous() if xyz else host).pin_memory()
         wins = [(i0, min(W, N_DB - i0)) for i0 in range(0, N_DB, W)]
         outs = [np.zeros(n, D.QUERY_RESULT_DTYPE) for _, n in wins]
 
         def stage(k):
             i0, n = wins[k]
             eng.online_stage(host[offsets[i0]:offsets[i0 + n]], offsets[i0:i0 + n + 1] - offsets[i0], int_ids=np.arange(i0, i0 + n),
-                             on_device=False)
+                             on_device=False, xyz=xyz)
 
         stage(0)
         for k, (i0, n) in enumerate(wins):
