@@ -789,7 +789,7 @@ def run_kitti08(args):
                      "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": f"bev_scatter_kernel + contour_kernel on one {m}-scan window (1.98 MB algorithmic bytes per scan)",
                      "kernel_ms": {"bev_scatter_ms": k1_ms, "ingest_ms": ing_ms}},
-        "sanity": {"scans_with_loop_candidate": n_lc, "of": n, "knn_runs": eng.online_runs(), "windows": len(wins),
+        "sanity": {"scans_with_loop_candidate": n_lc, "of": n, "knn_runs": eng.online_runs(), "knn_launches": eng.online_groups(), "windows": len(wins),
                    "host_seconds_in_commit": eng.online_host_seconds(),
                    "wall_s_device_inputs": wall_dev, "exp_mode": eng.exp_mode()},
     }

@@ -62,6 +62,8 @@ def lib():
         L.c2g_online_host_seconds.argtypes = [vp, vp]
         L.c2g_online_runs.restype = ll
         L.c2g_online_runs.argtypes = [vp]
+        L.c2g_online_groups.restype = ll
+        L.c2g_online_groups.argtypes = [vp]
         L.c2g_db_sync.argtypes = [vp]
         L.c2g_db_layer_state.argtypes = [vp, ip, vp, vp, vp]
         L.c2g_db_bucket_tree.argtypes = [vp, ip, ip, vp, vp, vp]

@@ -154,6 +154,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
     return rc;
   }
   ctx->P.exp_mode = probe_exp_mode();
+  ctx->trace_on = getenv("C2G_TRACE") != nullptr;
   ctx->db = *db_cfg;
   ctx->device = device;
   ctx->scan_cap = scan_capacity;
@@ -269,6 +270,18 @@ int c2g_destroy(c2g_ctx *ctx) {
   if (!ctx) return 0;
   C2gDeviceGuard guard(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->trace_on && ctx->trace_n > 0) {  // developer aid: device and host time of every mark, ms since the first one
+    if (FILE *f = fopen(getenv("C2G_TRACE"), "a")) {
+      fprintf(f, "# context on device %d: %d marks (what, device ms, host ms)\n", ctx->device, ctx->trace_n);
+      for (int i = 0; i < ctx->trace_n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->trace[0].ev, ctx->trace[i].ev);
+        fprintf(f, "%s %.3f %.3f\n", ctx->trace[i].what, ms, (ctx->trace[i].host_s - ctx->trace[0].host_s) * 1e3);
+      }
+      fclose(f);
+    }
+    for (int i = 0; i < ctx->trace_n; ++i) cudaEventDestroy(ctx->trace[i].ev);
+  }
   c2g_query_free(ctx);
   c2g_refine_free(ctx);
   delete ctx->hostdb;
@@ -387,17 +400,21 @@ static int ingest_host_pipelined(c2g_ctx *ctx, const float *pts, const long long
   for (int b0 = 0; b0 < B; b0 += CH, ++k) {
     const int n = (B - b0 < CH) ? (B - b0) : CH;
     const size_t p0 = (size_t) rel[b0], p1 = (size_t) rel[b0 + n];
+    c2g_trace_mark(ctx, "h2d_begin", ctx->copy_stream);
     C2G_CUDA_TRY(cudaMemcpyAsync(stage + fpp * p0, pts + fpp * ((size_t) offsets_host[0] + p0), sizeof(float) * fpp * (p1 - p0), cudaMemcpyHostToDevice, ctx->copy_stream));
+    c2g_trace_mark(ctx, "h2d_end", ctx->copy_stream);
     cudaEvent_t ev = ctx->ev_chunk[k % C2G_MAX_CHUNK_EVENTS];
     C2G_CUDA_TRY(cudaEventRecord(ev, ctx->copy_stream));
     C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
     const C2gBevOut bo = bev_out(ctx, b0);
+    c2g_trace_mark(ctx, "ingest_begin", ctx->stream);
     int rc = c2g_launch_bev_scatter(stage, d_off + b0, n, ctx->P, bo, 0, fpp == 3, ctx->d_work_counter_k1, ctx->num_sms, ctx->stream);
     if (rc) return rc;
     rc = c2g_launch_contours(bo, n, ctx->P, ids_dev ? ids_dev + b0 : nullptr, first_slot + b0, ctx->d_presort, ctx->d_heads, ctx->d_views, ctx->d_ells,
                              ctx->d_k2_scratch, ctx->d_work_counter, ctx->num_sms, ctx->stream, ctx->d_dbg);
     if (rc) return rc;
     ctx->launches += 2;
+    c2g_trace_mark(ctx, "ingest_end", ctx->stream);
   }
   C2G_CUDA_TRY(cudaEventRecord(ctx->ev_stage_free[cur], ctx->stream));
   ctx->last_B = B;
@@ -574,6 +591,7 @@ static int online_stage_impl(c2g_ctx *ctx, const float *pts, const long long *of
   C2G_CUDA_TRY(cudaMemcpy2DAsync(st.h_keys, kbytes, (const char *) (ctx->d_heads + first_slot) + offsetof(c2g_scan_head, keys), sizeof(c2g_scan_head), kbytes,
                                  (size_t) W, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA_TRY(cudaEventRecord(st.ev_keys, ctx->stream));
+  c2g_trace_mark(ctx, "keys_d2h_end", ctx->stream);
   ctx->n_staged++;
   return 0;
 }
@@ -592,7 +610,9 @@ int c2g_online_commit(c2g_ctx *ctx, const double *ts_host, const int *seeds_host
   if (ctx->n_staged <= 0) return C2G_ERR_STATE;
   C2gDeviceGuard guard(ctx->device);
   auto &st = ctx->staged[ctx->staged_head];
+  c2g_trace_mark(ctx, "host:commit_enter", ctx->copy_stream);
   C2G_CUDA_TRY(cudaEventSynchronize(st.ev_keys));  // the only wait of the window: its 1.4 KB of keys per scan
+  c2g_trace_mark(ctx, "host:keys_arrived", ctx->copy_stream);
   int rc = c2g_online_commit_impl(ctx, st.first_slot, st.W, st.h_keys, ts_host, seeds_host, lb, ub, results_host);
   if (rc) return rc;
   ctx->staged_head ^= 1;
@@ -614,6 +634,7 @@ int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_h
 }
 
 long long c2g_online_runs(c2g_ctx *ctx) { return ctx ? ctx->online_runs : 0; }
+long long c2g_online_groups(c2g_ctx *ctx) { return ctx ? ctx->online_groups : 0; }
 
 int c2g_online_host_seconds(c2g_ctx *ctx, double *out4) {
   if (!ctx || !out4) return C2G_ERR_ARG;

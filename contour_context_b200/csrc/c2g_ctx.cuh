@@ -1,6 +1,8 @@
 // c2g_ctx.cuh — the context object behind the opaque c2g_ctx handle of include/c2g.h.
 #pragma once
 #include "c2g_common.cuh"
+#include <time.h>
+#define C2G_TRACE_CAP 4096
 
 #define C2G_MAX_CHUNK_EVENTS 64
 #define C2G_QUERY_STREAMS 8  // sub-batches of one c2g_query_async call that may run concurrently
@@ -9,15 +11,20 @@
 #define C2G_PATCH_RING 2048
 #define C2G_QPROF_N 9  // knn, prefilter, score, replay, corr, output, refine, rank, (spare)
 
+#define C2G_PHYS_BUCKETS (2 * C2G_NUM_BUCKETS)
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
-  // Bucket k owns the fixed region [k * cap_b, (k + 1) * cap_b) of every per-key array and [k * blkcap_b, ..) of the block
-  // arrays, so that a change in one bucket never moves the entries of another.
-  float *keys_t;         // [C2G_KEY_DIM][C2G_NUM_BUCKETS * cap_b] transposed for coalesced scans
+  // Bucket k owns two fixed regions p = 2k, 2k + 1: [p * cap_b, (p + 1) * cap_b) of every per-key array and [p * blkcap_b, ..)
+  // of the block arrays.  phys[k] is the one in use: a change in one bucket never moves the entries of another, appending to
+  // a bucket never disturbs a kNN launch that reads its shorter prefix, and a REWRITE of a bucket (rebalancing move, kd
+  // re-ordering) goes to the bucket's other region, so that launches still reading the previous version are not disturbed
+  // either (the windowed online loop runs the kNN of a whole window after all of the window's patches, c2g_online_commit).
+  float *keys_t;         // [C2G_KEY_DIM][C2G_PHYS_BUCKETS * cap_b] transposed for coalesced scans
   int *gidx;             // IndexOfKey::gidx
   signed char *seq;      // IndexOfKey::seq
   int *orank;            // region base + position in TREE order (tie-break rank; the mirror itself may be kd-ordered)
-  float *box_min, *box_max;  // [C2G_KEY_DIM][C2G_NUM_BUCKETS * blkcap_b]: bounding box of every 32-key block
+  float *box_min, *box_max;  // [C2G_KEY_DIM][C2G_PHYS_BUCKETS * blkcap_b]: bounding box of every 32-key block
   int cap_b, blkcap_b;
+  int phys[C2G_NUM_BUCKETS];
   int bucket_cnt[C2G_NUM_BUCKETS];
   float ranges[C2G_NUM_BUCKETS + 1];
   // what the mirror currently holds per bucket (c2g_db_sync patches the difference to the host trees)
@@ -106,8 +113,29 @@ struct c2g_ctx {
   unsigned long long *d_work;  // [C2G_WORK_N] work counters of the query kernels (c2g_work_counters); handed to the kernels only while enabled
   int count_work;
   double online_host_s[4];    // host seconds spent by c2g_online_commit: LayerDB bookkeeping, kNN launches, mirror patches, chain launches
-  long long online_runs;      // kNN launches of the windowed loop so far (= runs of scans that saw identical trees)
+  long long online_runs;      // runs of scans that saw identical trees in the windowed loop so far
+  long long online_groups;    // kNN launches of the windowed loop so far (a launch serves a group of runs)
   // optional per-kernel timing of the query path (c2g_query_profile): event k is recorded after kernel k - 1
   int prof_on;
   cudaEvent_t prof_ev[C2G_QPROF_N + 1];
+  // developer aid (environment C2G_TRACE=<file>): timed events on both streams of the windowed loop, dumped by c2g_destroy
+  int trace_on, trace_n;
+  struct {
+    const char *what;
+    cudaEvent_t ev;
+    double host_s;
+  } trace[C2G_TRACE_CAP];
 };
+
+// records a timed event on `st` (no-op unless tracing)
+static inline void c2g_trace_mark(c2g_ctx *ctx, const char *what, cudaStream_t st) {
+  if (!ctx->trace_on || ctx->trace_n >= C2G_TRACE_CAP) return;
+  auto &t = ctx->trace[ctx->trace_n];
+  if (cudaEventCreate(&t.ev) != cudaSuccess) return;
+  cudaEventRecord(t.ev, st);
+  t.what = what;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  t.host_s = (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+  ctx->trace_n++;
+}

@@ -42,10 +42,20 @@ struct LayerDev {
   const signed char *seq;
   const int *orank;     // bucket-major TREE order rank (what the entry's position would be without the kd ordering)
   const float *box_min, *box_max;  // [KEY_DIM][blk_cap] bounding boxes of the 32-key blocks
-  int cap, blk_cap;     // row strides of keys_t / box_*: C2G_NUM_BUCKETS * cap_b, C2G_NUM_BUCKETS * blkcap_b
-  int cap_b, blkcap_b;  // keys of bucket k occupy [k * cap_b, k * cap_b + bucket_cnt[k]), in blocks of 32 from k * blkcap_b
+  int cap, blk_cap;     // row strides of keys_t / box_*: C2G_PHYS_BUCKETS * cap_b, C2G_PHYS_BUCKETS * blkcap_b
+  int cap_b, blkcap_b;  // keys of bucket k occupy [p * cap_b, p * cap_b + bucket_cnt[k]), p = phys[k], in blocks of 32 from p * blkcap_b
+  int phys[C2G_NUM_BUCKETS];
   int bucket_cnt[C2G_NUM_BUCKETS];
   float ranges[C2G_NUM_BUCKETS + 1];
+};
+// The part of a LayerDev that changes while a DB grows, per (query scan, layer) of a launch: lets ONE kNN launch serve query
+// scans that must see different states of the trees (windowed online loop; see C2gLayerTable for why the older states are
+// still intact when the launch runs).
+struct KnnVersion {
+  int phys[C2G_NUM_BUCKETS];
+  int bucket_cnt[C2G_NUM_BUCKETS];
+  float ranges[C2G_NUM_BUCKETS + 1];
+  int pad_;
 };
 struct QueryParams {
   LayerDev layer[C2G_NUM_Q_LEVELS_MAX];
@@ -65,8 +75,8 @@ __device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, c
 // across the warp's registers (slot j lives in lane j % 32, register j / 32) and updated by warp-cooperative insertion.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QK_WARPS * 32)
-knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, c2g_hint *__restrict__ hints,
-           unsigned long long *__restrict__ work) {
+knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, const KnnVersion *__restrict__ ver,
+           c2g_hint *__restrict__ hints, unsigned long long *__restrict__ work) {
   __shared__ float merge_d[QK_WARPS][64];
   __shared__ int merge_i[QK_WARPS][64], merge_o[QK_WARPS][64];
   __shared__ float box_cache[QK_WARPS][KNN_BOX_CACHE];  // box distances of a bucket's first blocks: computed once, used by both passes
@@ -103,12 +113,16 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
                           fmaxf((key[1] - b10) * (key[1] - b10), (key[1] - b11) * (key[1] - b11)) +
                           fmaxf((key[2] - b20) * (key[2] - b20), (key[2] - b21) * (key[2] - b21));
     const LayerDev &T = Q.layer[ll];
+    // the state of the trees this query scan sees: the launch parameters, or the scan's own entry of the version table
+    const KnnVersion *V = ver ? ver + ((size_t) (q - q0) * Q.n_q_levels + ll) : nullptr;
     int mid = 0;
-    for (int i = 0; i < C2G_NUM_BUCKETS; ++i)
-      if (T.ranges[i] <= key[0] && T.ranges[i + 1] > key[0]) {
+    for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
+      const float r0 = V ? V->ranges[i] : T.ranges[i], r1 = V ? V->ranges[i + 1] : T.ranges[i + 1];
+      if (r0 <= key[0] && r1 > key[0]) {
         mid = i;
         break;
       }
+    }
     // visited set of layerKNNSearch's else-if chain: {mid, mid-1, .., 0} and {mid+i : i > mid, mid+i < 6}
     unsigned visit = 0;
     for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
@@ -218,9 +232,10 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
     };
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
       if (!((visit >> bk) & 1u)) continue;
-      const int beg = bk * T.cap_b, end = beg + T.bucket_cnt[bk];
+      const int pb = V ? V->phys[bk] : T.phys[bk], cntb = V ? V->bucket_cnt[bk] : T.bucket_cnt[bk];
+      const int beg = pb * T.cap_b, end = beg + cntb;
       if (beg >= end) continue;
-      const int b0 = bk * T.blkcap_b, nb = (T.bucket_cnt[bk] + 31) >> 5;
+      const int b0 = pb * T.blkcap_b, nb = (cntb + 31) >> 5;
       n_boxes += nb + (nb > KNN_BOX_CACHE ? nb - KNN_BOX_CACHE : 0);
       // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
       float best = 3.0e38f;
@@ -1392,9 +1407,10 @@ int build_query_params(c2g_ctx *ctx, const c2g_score_ensemble *lb, QueryParams &
     Q.layer[i].box_max = t.box_max;
     Q.layer[i].cap_b = t.cap_b;
     Q.layer[i].blkcap_b = t.blkcap_b;
-    Q.layer[i].cap = C2G_NUM_BUCKETS * t.cap_b;
-    Q.layer[i].blk_cap = C2G_NUM_BUCKETS * t.blkcap_b;
+    Q.layer[i].cap = C2G_PHYS_BUCKETS * t.cap_b;
+    Q.layer[i].blk_cap = C2G_PHYS_BUCKETS * t.blkcap_b;
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) Q.layer[i].bucket_cnt[k] = t.bucket_cnt[k];
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) Q.layer[i].phys[k] = t.phys[k];
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) Q.layer[i].ranges[k] = t.ranges[k];
   }
   Q.nnk = ctx->db.nnk;
@@ -1494,7 +1510,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     C2gLayerTable &t = ctx->layers[i];
     t.cap_b = ctx->scan_cap * C2G_MAX_PIV;  // any bucket may end up holding every key of the layer
     t.blkcap_b = t.cap_b / 32 + 1;
-    const size_t cap = (size_t) C2G_NUM_BUCKETS * t.cap_b, bcap = (size_t) C2G_NUM_BUCKETS * t.blkcap_b;
+    const size_t cap = (size_t) C2G_PHYS_BUCKETS * t.cap_b, bcap = (size_t) C2G_PHYS_BUCKETS * t.blkcap_b;
     C2G_CUDA_TRY(cudaMalloc((void **) &t.keys_t, sizeof(float) * C2G_KEY_DIM * cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.gidx, sizeof(int) * cap));
     C2G_CUDA_TRY(cudaMalloc((void **) &t.seq, cap));
@@ -1503,6 +1519,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     C2G_CUDA_TRY(cudaMalloc((void **) &t.box_max, sizeof(float) * C2G_KEY_DIM * bcap));
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       t.bucket_cnt[k] = 0;
+      t.phys[k] = 2 * k;
       t.m_n[k] = 0;
       t.m_rv[k] = 0;
       t.m_kd[k] = 0;
@@ -1601,22 +1618,21 @@ struct LayerPatch {
   std::vector<PatchRec> recs;
   std::vector<PatchBlk> blks;
 };
-void patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out) {
-  const int base = k * t.cap_b, bbase = k * t.blkcap_b;
+// what bringing bucket k of the mirror to a tree of n keys (restructure count rv) takes: 0 nothing, 1 an append, 2 a rewrite
+int patch_kind(const C2gLayerTable &t, int k, int n, unsigned rv, bool want_kd) {
   const bool grown_only = t.m_valid[k] && t.m_rv[k] == rv && !t.m_kd[k] && n >= t.m_n[k];
   const bool need_kd = want_kd && n > 32;  // a bucket of one block has nothing to order
-  int from = 0;
-  bool kd = false;
-  if (grown_only && !(need_kd && !t.m_kd[k])) {
-    if (n == t.m_n[k]) {
-      return;  // unchanged
-    }
-    from = t.m_n[k];  // append in tree order
-  } else if (t.m_valid[k] && t.m_rv[k] == rv && n == t.m_n[k] && (t.m_kd[k] || !need_kd)) {
-    return;  // unchanged (kd-ordered mirror of an unchanged tree)
-  } else {
-    kd = need_kd;
-  }
+  if (grown_only && !(need_kd && !t.m_kd[k])) return n == t.m_n[k] ? 0 : 1;
+  if (t.m_valid[k] && t.m_rv[k] == rv && n == t.m_n[k] && (t.m_kd[k] || !need_kd)) return 0;  // kd-ordered mirror of an unchanged tree
+  return 2;
+}
+int patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out) {
+  const int kind = patch_kind(t, k, n, rv, want_kd);
+  if (kind == 0) return 0;
+  if (kind == 2) t.phys[k] ^= 1;  // a rewrite goes to the bucket's other region (launches reading the old one are not disturbed)
+  const int base = t.phys[k] * t.cap_b, bbase = t.phys[k] * t.blkcap_b;
+  const int from = kind == 1 ? t.m_n[k] : 0;  // append in tree order
+  const bool kd = kind == 2 && want_kd && n > 32;
   std::vector<int> order;
   if (kd) kd_order(tree, n, order);
   for (int p = from; p < n; ++p) {
@@ -1641,6 +1657,7 @@ void patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigne
   t.m_rv[k] = rv;
   t.m_kd[k] = kd ? 1 : 0;
   t.m_valid[k] = 1;
+  return kind;
 }
 
 // The patch staging ring: a pinned host buffer and its device twin, carved into stretches.  A stretch (and the ring entry that
@@ -1687,7 +1704,7 @@ int patch_ring_commit(c2g_ctx *ctx, size_t beg, size_t need) {
 
 // the two kernels that apply one layer's uploaded patch (records at dp, blocks at dp + blks_off)
 int launch_patch_kernels(c2g_ctx *ctx, C2gLayerTable &t, const char *dp, int n_recs, size_t blks_off, int n_blks) {
-  const int stride = C2G_NUM_BUCKETS * t.cap_b, bstride = C2G_NUM_BUCKETS * t.blkcap_b;
+  const int stride = C2G_PHYS_BUCKETS * t.cap_b, bstride = C2G_PHYS_BUCKETS * t.blkcap_b;
   if (n_recs > 0)
     mirror_patch_kernel<<<(unsigned) ((n_recs + 255) / 256), 256, 0, ctx->stream>>>((const PatchRec *) dp, n_recs, t.keys_t, stride, t.gidx, t.seq, t.orank);
   if (n_blks > 0)
@@ -1722,8 +1739,19 @@ struct DeferredPatch {
   size_t off, blks_off;  // byte offset of the records in the block; of the blocks relative to the records
 };
 
-// like c2g_db_sync_mode(ctx, 0), but the patches are appended to `block` (host memory) instead of being uploaded
-int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<DeferredPatch> &out) {
+// would bringing the mirror up to date (tree order) rewrite a bucket that `rewritten` already marks?
+bool patches_rewrite_again(c2g_ctx *ctx, const unsigned char (*rewritten)[C2G_NUM_BUCKETS]) {
+  for (int ll = 0; ll < ctx->db.n_q_levels; ++ll)
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+      const C2gBucket &bk = ctx->hostdb->layers[ll].buckets[k];
+      if (rewritten[ll][k] && patch_kind(ctx->layers[ll], k, (int) bk.tree.size(), bk.restructured, false) == 2) return true;
+    }
+  return false;
+}
+
+// like c2g_db_sync_mode(ctx, 0), but the patches are appended to `block` (host memory) instead of being uploaded; buckets that
+// are rewritten (not just appended to) are marked in `rewritten`
+int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<DeferredPatch> &out, unsigned char (*rewritten)[C2G_NUM_BUCKETS]) {
   for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
     const C2gLayerHost &L = ctx->hostdb->layers[ll];
     C2gLayerTable &t = ctx->layers[ll];
@@ -1731,7 +1759,7 @@ int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<D
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       const C2gBucket &bk = L.buckets[k];
       if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
-      patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp);
+      if (patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp) == 2) rewritten[ll][k] = 1;
     }
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
     if (lp.recs.empty() && lp.blks.empty()) continue;
@@ -1809,12 +1837,13 @@ static bool thresholds_ok(const c2g_score_ensemble *lb, const c2g_score_ensemble
          lb->area_perc < ub->area_perc && lb->neg_est_dist < ub->neg_est_dist;
 }
 
-// kNN of queries [q0, q0 + Bs) of the batch against the mirror AS IT IS NOW on `st` (the table sizes and bucket boundaries
-// travel by value in the launch parameters, so a later patch of the mirror does not affect this launch)
-static int launch_knn(c2g_ctx *ctx, int first_slot, int q0, int Bs, const QueryParams &Q, cudaStream_t st) {
+// kNN of queries [q0, q0 + Bs) of the batch on `st`: against the mirror AS IT IS NOW (the table sizes and bucket boundaries
+// travel by value in the launch parameters, so a later patch of the mirror does not affect this launch), or, with `ver`
+// (device, [Bs][n_q_levels]), each query scan against its own recorded state of the trees
+static int launch_knn(c2g_ctx *ctx, int first_slot, int q0, int Bs, const QueryParams &Q, cudaStream_t st, const KnnVersion *ver = nullptr) {
   const int n_keys = Bs * Q.n_q_levels * C2G_MAX_PIV;
   if (n_keys <= 0) return 0;
-  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ctx->d_hints,
+  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ver, ctx->d_hints,
                                                                           ctx->count_work ? ctx->d_work : nullptr);
   C2G_CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
@@ -1927,18 +1956,23 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     int rc = sync_mirror();
     if (rc) return rc;
   }
-  // Pass 1 (host only): the LayerDB bookkeeping of the whole window.  Every change of a tree ends a run of scans that saw
-  // the same trees; the run's kNN parameters are snapshotted and the mirror patch that follows it is appended to one block.
-  struct Run {
+  // Pass 1 (host only): the LayerDB bookkeeping of the whole window.  Every change of a tree ends a run of scans that saw the
+  // same trees; every scan's view of the trees (bucket boundaries, sizes, regions) goes into a version table, and the mirror
+  // patch that follows the run is appended to one block.  Runs are gathered into groups that ONE kNN launch can serve: all
+  // patches of a group are applied before its launch, which is safe as long as no bucket is rewritten twice inside the group
+  // (appends are invisible to scans with a shorter prefix, one rewrite goes to the bucket's other region: C2gLayerTable).
+  struct Group {
     int q0, n, patch_begin, patch_end;
-    QueryParams Q;
   };
-  std::vector<Run> runs;
+  const int nql = ctx->db.n_q_levels;
+  std::vector<Group> groups;
   std::vector<char> block;
   std::vector<DeferredPatch> patches;
+  std::vector<KnnVersion> vers((size_t) W * nql);
+  unsigned char rewritten[C2G_NUM_Q_LEVELS_MAX][C2G_NUM_BUCKETS] = {};
   QueryParams Q;
   build_query_params(ctx, lb, Q);
-  int run_begin = 0;
+  int run_begin = 0, group_begin = 0, group_patch_begin = 0, n_runs = 0;
   const size_t kstride = (size_t) C2G_NLEV * C2G_MAX_PIV * C2G_KEY_DIM;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_mark = now();
@@ -1947,10 +1981,32 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     ctx->online_host_s[k] += t - t_mark;
     t_mark = t;
   };
+  auto close_run = [&](int end) {  // scans run_begin..end-1 see the mirror as the tables describe it now
+    if (end <= run_begin) return;
+    for (int ll = 0; ll < nql; ++ll) {
+      const C2gLayerTable &t = ctx->layers[ll];
+      KnnVersion v;
+      for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
+        v.phys[k] = t.phys[k];
+        v.bucket_cnt[k] = t.bucket_cnt[k];
+      }
+      for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) v.ranges[k] = t.ranges[k];
+      v.pad_ = 0;
+      for (int q = run_begin; q < end; ++q) vers[(size_t) q * nql + ll] = v;
+    }
+    run_begin = end;
+    ++n_runs;
+  };
+  auto close_group = [&](int end) {
+    groups.push_back({group_begin, end - group_begin, group_patch_begin, (int) patches.size()});
+    group_begin = end;
+    group_patch_begin = (int) patches.size();
+    memset(rewritten, 0, sizeof(rewritten));
+  };
   for (int i = 0; i < W; ++i) {
     const unsigned long long v0 = db.tree_version;
     const float *sk = keys_host + (size_t) i * kstride;
-    for (int ll = 0; ll < ctx->db.n_q_levels; ++ll) {
+    for (int ll = 0; ll < nql; ++ll) {
       const int lev = ctx->db.q_levels[ll];
       for (int seq = 0; seq < ctx->P.cfg.piv_firsts; ++seq)
         c2g_hostdb_push(db, ll, sk + ((size_t) lev * C2G_MAX_PIV + seq) * C2G_KEY_DIM, ts_host[i], first_slot + i, seq);
@@ -1959,63 +2015,53 @@ int c2g_online_commit_impl(c2g_ctx *ctx, int first_slot, int W, const float *key
     c2g_hostdb_push_and_balance(db, seeds_host[i], ts_host[i]);
     if (db.tree_version != v0) {  // scans run_begin..i saw the trees as mirrored now; scan i + 1 sees the new ones
       lap(0);
-      Run r;
-      r.q0 = run_begin;
-      r.n = i + 1 - run_begin;
-      r.Q = Q;
-      r.patch_begin = (int) patches.size();
-      int rc = collect_mirror_patches(ctx, block, patches);
+      close_run(i + 1);
+      if (patches_rewrite_again(ctx, rewritten)) close_group(i + 1);
+      int rc = collect_mirror_patches(ctx, block, patches, rewritten);
       if (rc) return rc;
-      r.patch_end = (int) patches.size();
-      runs.push_back(r);
-      run_begin = i + 1;
       ctx->db_dirty = 0;
       ctx->db_not_kd = 1;
-      build_query_params(ctx, lb, Q);
       lap(2);
     }
   }
-  if (run_begin < W) {
-    Run r;
-    r.q0 = run_begin;
-    r.n = W - run_begin;
-    r.Q = Q;
-    r.patch_begin = r.patch_end = (int) patches.size();
-    runs.push_back(r);
-  }
+  close_run(W);
+  close_group(W);
   lap(0);
-  // Pass 2: ONE upload of the window's patches, on the copy stream (all host->device traffic of the online loop is issued on
-  // that stream in the order it is needed, so a small copy never sits in the copy queue in front of the next window's points
-  // waiting for kernels of this window), then per run: kNN against the mirror as it is, then the patch that ends the run.
+  // Pass 2: ONE upload of the window's patches and version table, on the copy stream (all host->device traffic of the online
+  // loop is issued on that stream in the order it is needed, so a small copy never sits in the copy queue in front of the next
+  // window's points waiting for kernels of this window), then per group: its patches, then its kNN launch.
+  const size_t ver_off = (block.size() + 255) / 256 * 256, ver_bytes = vers.size() * sizeof(KnnVersion);
+  block.resize(ver_off + ver_bytes);
+  memcpy(block.data() + ver_off, vers.data(), ver_bytes);
   size_t beg = 0;
-  const char *dp = nullptr;
-  if (!block.empty()) {
-    int rc = patch_ring_alloc(ctx, block.size(), &beg);
-    if (rc) return rc;
-    memcpy((char *) ctx->h_patch + beg, block.data(), block.size());
-    dp = (const char *) ctx->d_patch + beg;
-    C2G_CUDA_TRY(cudaMemcpyAsync((void *) dp, (char *) ctx->h_patch + beg, block.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
-    C2G_CUDA_TRY(cudaEventRecord(ctx->ev_patch_up, ctx->copy_stream));
-    C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_patch_up, 0));
-  }
+  int rc = patch_ring_alloc(ctx, block.size(), &beg);
+  if (rc) return rc;
+  memcpy((char *) ctx->h_patch + beg, block.data(), block.size());
+  const char *dp = (const char *) ctx->d_patch + beg;
+  C2G_CUDA_TRY(cudaMemcpyAsync((void *) dp, (char *) ctx->h_patch + beg, block.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+  C2G_CUDA_TRY(cudaEventRecord(ctx->ev_patch_up, ctx->copy_stream));
+  C2G_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_patch_up, 0));
   lap(2);
-  for (const Run &r : runs) {
-    int rc = launch_knn(ctx, first_slot, r.q0, r.n, r.Q, ctx->stream);
-    if (rc) return rc;
-    for (int p = r.patch_begin; p < r.patch_end; ++p) {
+  c2g_trace_mark(ctx, "knn_runs_begin", ctx->stream);
+  const KnnVersion *d_vers = (const KnnVersion *) (dp + ver_off);
+  for (const Group &g : groups) {
+    for (int p = g.patch_begin; p < g.patch_end; ++p) {
       const DeferredPatch &d = patches[p];
       rc = launch_patch_kernels(ctx, ctx->layers[d.layer], dp + d.off, d.n_recs, d.blks_off, d.n_blks);
       if (rc) return rc;
     }
-  }
-  if (!block.empty()) {
-    int rc = patch_ring_commit(ctx, beg, block.size());
+    rc = launch_knn(ctx, first_slot, g.q0, g.n, Q, ctx->stream, d_vers + (size_t) g.q0 * nql);
     if (rc) return rc;
   }
-  ctx->online_runs += (long long) runs.size();
-  lap(1);
-  int rc = launch_query_chain(ctx, first_slot, W, Q, 0);
+  rc = patch_ring_commit(ctx, beg, block.size());
   if (rc) return rc;
+  ctx->online_runs += n_runs;
+  ctx->online_groups += (long long) groups.size();
+  lap(1);
+  c2g_trace_mark(ctx, "chain_begin", ctx->stream);
+  rc = launch_query_chain(ctx, first_slot, W, Q, 0);
+  if (rc) return rc;
+  c2g_trace_mark(ctx, "chain_end", ctx->stream);
   lap(3);
   if (results_host)
     C2G_CUDA_TRY(cudaMemcpyAsync(results_host, ctx->d_results, sizeof(c2g_query_result) * (size_t) W, cudaMemcpyDeviceToHost, ctx->stream));

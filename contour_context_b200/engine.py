@@ -163,6 +163,9 @@ class Engine:
     def online_runs(self) -> int:
         return int(capi.lib().c2g_online_runs(self.h))
 
+    def online_groups(self) -> int:
+        return int(capi.lib().c2g_online_groups(self.h))
+
     def db_size(self) -> int:
         return int(capi.lib().c2g_db_size(self.h))
 

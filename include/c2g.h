@@ -115,7 +115,8 @@ int c2g_db_size(c2g_ctx *ctx);
  *   c2g_online_commit  oldest staged window: bookkeeping + queries; results_host[W] (pinned memory recommended) is filled
  *                      asynchronously: valid after c2g_sync.
  *   c2g_online_window  stage + commit + sync in one call.
- *   c2g_online_runs    kNN launches issued by the windowed loop so far (runs of scans that saw identical trees). */
+ *   c2g_online_runs    runs of scans that saw identical trees in the windowed loop so far;
+ *   c2g_online_groups  kNN launches it issued (one launch serves a group of runs: every scan carries its own view of the trees). */
 int c2g_online_stage(c2g_ctx *ctx, const float *pts, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host);
 /* the same for 12 B / point buffers (x, y, z), as c2g_ingest_xyz */
 int c2g_online_stage_xyz(c2g_ctx *ctx, const float *xyz, const long long *offsets_host, int W, int pts_on_device, const int *int_ids_host);
@@ -125,6 +126,7 @@ int c2g_online_window(c2g_ctx *ctx, const float *pts, const long long *offsets_h
                       const double *ts_host, const int *seeds_host, const c2g_score_ensemble *lb, const c2g_score_ensemble *ub,
                       c2g_query_result *results_host);
 long long c2g_online_runs(c2g_ctx *ctx);
+long long c2g_online_groups(c2g_ctx *ctx);
 /* Measurement aid: host seconds c2g_online_commit has spent so far in [0] the LayerDB bookkeeping, [1] kNN launches, [2] mirror
  * patches, [3] the launches of the rest of the chain. */
 int c2g_online_host_seconds(c2g_ctx *ctx, double *out4);

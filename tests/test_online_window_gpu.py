@@ -60,14 +60,15 @@ def _same_state(eng, state, trees):
                 assert a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("window", [1, 7, 37, 64])
+@pytest.mark.parametrize("window", [1, 7, 37, 64, 120])
 def test_window_equals_scan_by_scan(built_lib, sequence, seq_result, window):
     from contour_context_b200.engine import Engine
 
     pts, offsets, ts = sequence
     ref, state, trees = seq_result
     lb, ub = D.kitti_thres()
-    eng = Engine(scan_capacity=N_DB + 8, max_batch=64, max_points=64 * 65536)
+    mb = max(64, window)
+    eng = Engine(scan_capacity=N_DB + 8, max_batch=mb, max_points=mb * 65536)
     try:
         got = np.zeros(N_DB, D.QUERY_RESULT_DTYPE)
         for i0 in range(0, N_DB, window):
@@ -80,6 +81,11 @@ def test_window_equals_scan_by_scan(built_lib, sequence, seq_result, window):
         _same_state(eng, state, trees)
         if window >= 37:
             assert eng.online_runs() > N_DB // window + 2, "the windows must have been cut into several kNN runs"
+            n_win = (N_DB + window - 1) // window
+            print(f"window {window}: {eng.online_runs()} runs in {eng.online_groups()} kNN launches over {n_win} windows")
+            assert eng.online_groups() < eng.online_runs(), "one launch must serve several runs"
+        if window == 120:
+            assert eng.online_groups() > 1, "a bucket rewritten twice inside the window must split the launch"
         assert int((ref["n_cand"] > 0).sum()) >= N_DB // 8, "the comparison must cover real loop closures"
         assert int(ref["overflow"].max()) == 0
     finally:
