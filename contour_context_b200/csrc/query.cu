@@ -1852,7 +1852,7 @@ static int launch_knn(c2g_ctx *ctx, int first_slot, int q0, int Bs, const QueryP
 
 // The kernel chain of ContourDB::queryRangedKNN for the B query scans in slots first_slot.. : (kNN ->) prefilter -> score ->
 // proposal replay -> GMM-L2 gate -> output -> refinement -> ranking.  with_knn == 0: the hints are already in ctx->d_hints
-// (the windowed online loop fills them run by run, c2g_online_commit).
+// (the windowed online loop fills them with its own versioned launch, c2g_online_commit).
 // The batch is cut into sub-batches that run the whole chain on their own streams: most kernels of the chain are
 // latency-bound (sequential solver / replay logic) and leave issue slots idle that the kernels of the other sub-batches
 // fill.  C2G_QUERY_SPLIT=1 (or an active c2g_query_profile) keeps everything on the context's stream.

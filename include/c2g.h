@@ -107,8 +107,10 @@ int c2g_db_size(c2g_ctx *ctx);
  *     ContourDB::pushAndBalance(seeds[i], ts[i])   include/cont2/contour_db.h:827-843
  * with results identical to the scan-by-scan calls (query i sees exactly the trees that exist after scans < i were added
  * and balanced): the W scans are ingested in one batch into slots db_size .. db_size + W - 1, the host replays the LayerDB
- * bookkeeping of the window from their keys, the kNN runs once per run of scans that see identical trees (the device mirror is
- * patched between runs, in stream order), and the rest of the query chain runs once for the window.
+ * bookkeeping of the window from their keys and records for every scan the state of the trees it must see (bucket boundaries,
+ * sizes, regions); the device mirror keeps those states readable (appends + a second region per bucket for rewrites), so the
+ * window's patches are applied first and ONE kNN launch serves all its scans; the rest of the query chain runs once for the
+ * window.
  *   c2g_online_stage   ingests the next window (arguments as c2g_ingest) and starts the read-back of its keys; asynchronous.
  *                      At most two windows may be staged: stage window k+1, then commit window k, and the host -> device copy
  *                      of k+1 overlaps the bookkeeping and the query kernels of k.
