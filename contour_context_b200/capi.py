@@ -75,6 +75,7 @@ def lib():
         L.c2g_hostdb_state.argtypes = [vp, ip, vp, vp, vp]
         L.c2g_hostdb_tree.argtypes = [vp, ip, ip, vp, vp, vp]
         L.c2g_debug_clocks.argtypes = [vp, vp]
+        L.c2g_scatter_deferred.argtypes = [vp, vp]
         L.c2g_exp_mode.argtypes = [vp]
         L.c2g_selftest_libm.argtypes = [ip, ip, vp, vp]
         L.c2g_launch_count.restype = ll

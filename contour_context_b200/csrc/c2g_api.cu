@@ -215,7 +215,7 @@ int c2g_create(const c2g_cm_config *cm_cfg, const c2g_db_config *db_cfg, int dev
     ALLOC(ctx->d_planes, sizeof(uint32_t) * C2G_NLEV * nwords * max_batch);
     ALLOC(ctx->d_fg, sizeof(float4) * ncell * max_batch);
     ALLOC(ctx->d_hdr, sizeof(int2) * max_batch);
-    ALLOC(ctx->d_work_counter_k1, sizeof(int));
+    ALLOC(ctx->d_work_counter_k1, sizeof(int) * (4 + (size_t) max_batch));
     ALLOC(ctx->d_tile1, sizeof(c2g_cellkey) * ncell);
     ALLOC(ctx->d_planes1, sizeof(uint32_t) * C2G_NLEV * nwords);
     ALLOC(ctx->d_fg1, sizeof(float4) * ncell);
@@ -781,6 +781,14 @@ int c2g_query_profile(c2g_ctx *ctx, int enable, float *ms_out) {
 }
 
 /* developer aid: per-phase clock64() stamps of CTA 0's first scan in the last contour kernel (64 values) */
+int c2g_scatter_deferred(c2g_ctx *ctx, int *n_out) {
+  if (!ctx || !n_out) return C2G_ERR_ARG;
+  C2gDeviceGuard guard(ctx->device);
+  C2G_CUDA_TRY(cudaMemcpyAsync(n_out, ctx->d_work_counter_k1 + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host) {
   if (!ctx || !out_host) return C2G_ERR_ARG;
   C2gDeviceGuard guard(ctx->device);

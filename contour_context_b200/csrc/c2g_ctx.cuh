@@ -59,7 +59,7 @@ struct c2g_ctx {
   uint32_t *d_planes;      // [max_batch][C2G_NLEV][n_row * ceil(n_col / 32)]
   float4 *d_fg;            // [max_batch][n_cells]
   int2 *d_hdr;             // [max_batch]
-  int *d_work_counter_k1;  // next scan of the running scatter kernel launch
+  int *d_work_counter_k1;  // scatter kernel launch: [0] next scan, [1] next deferred scan, [2] deferred count, [3..] deferred scans
   // one-scan scratch of the dense-image getters (c2g_get_bev / c2g_get_tiles: the full-tile scatter variant run on demand)
   c2g_cellkey *d_tile1;
   uint32_t *d_planes1;

@@ -102,6 +102,12 @@ class Engine:
                                                   capi.ptr(hdr)), "c2g_get_bev_compact")
         return planes, fg[: int(hdr[1])].copy(), int(hdr[0])
 
+    def scatter_deferred(self) -> int:
+        """Scans of the last scatter launch that the fast kernel handed to the general 64-bit kernel."""
+        n = np.zeros(1, np.int32)
+        capi.check(capi.lib().c2g_scatter_deferred(self.h, capi.ptr(n)), "c2g_scatter_deferred")
+        return int(n[0])
+
     def tiles(self, batch_index: int):
         t = np.empty(self.n_cells, np.uint64)
         capi.check(capi.lib().c2g_get_tiles(self.h, batch_index, capi.ptr(t)), "c2g_get_tiles")

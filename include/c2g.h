@@ -182,6 +182,10 @@ int c2g_exp_mode(c2g_ctx *ctx);
 /* Host execution of the libm restatements (tests only). */
 int c2g_selftest_libm(int kind, int n, const void *in, void *out);
 
+/* Introspection for tests: how many scans of the LAST scatter launch (the last chunk of the last c2g_ingest* / c2g_bev_only call) the
+ * fast scatter kernel handed to the general 64-bit kernel (more than 2^17 points, event log or foreground list overflow). */
+int c2g_scatter_deferred(c2g_ctx *ctx, int *n_out);
+
 /* Developer aid: clock64() stamps of the contour kernel's phases (64 values). */
 int c2g_debug_clocks(c2g_ctx *ctx, long long *out_host);
 

@@ -78,6 +78,35 @@ def test_scatter_handoff_planes_and_foreground_list(engine, oracle):
     assert n_fg_total > 2000
 
 
+def test_scatter_fast_path_and_its_deferrals(engine, oracle):
+    """The 32-bit scatter kernel logs (height, cell, index) events and resolves the winners afterwards; scans it cannot take go to
+    the 64-bit kernel: more than 2^17 points (index field), more events than the log holds (heights ascending in file order:
+    every point above the lowest threshold is a record), more foreground cells than the rank table (cluttered test below).
+    Mixed in one batch with ordinary scans; everything must match the oracle, and exactly the two odd scans must be deferred."""
+    base, _ = make_batch([31, 32, 33], [0, 1, 2], 70000)
+    big = np.concatenate([base[:70000], base[70000:140000]])                 # 140 000 points > 2^17
+    rng = np.random.default_rng(11)
+    asc = np.zeros((60000, 4), np.float32)                                   # 900 cells, heights ascending in file order:
+    asc[:, :2] = rng.uniform(10.0, 40.0, (60000, 2))                         # ~every point raises its cell -> ~60 000 events
+    asc[:, 2] = np.linspace(0.0, 6.0, 60000)
+    ties = base[:60000].copy()
+    ties[:, 2] = np.round(ties[:, 2] * 4) / 4                                # exact ties: the first point in file order wins
+    scans = [base[:70000], big, asc, ties, base[70000:140000]]
+    pts = np.ascontiguousarray(np.concatenate(scans))
+    offsets = np.cumsum([0] + [len(s) for s in scans]).astype(np.int64)
+    engine.ingest_bev_only(pts, offsets)
+    assert engine.scatter_deferred() == 2
+    for b, s in enumerate(_oracle_scans(oracle, engine.cm_cfg, pts, offsets)):
+        ob, orf, ocf = s.bev()
+        planes, fg, n_occ = _compact_from_dense(engine.cm_cfg, ob, orf, ocf)
+        gp, gf, gocc = engine.bev_compact(b)
+        assert gocc == n_occ, (b, gocc, n_occ)
+        assert gp.tobytes() == planes.tobytes(), f"scan {b}: bit-planes differ"
+        assert gf.shape == fg.shape and gf.tobytes() == fg.tobytes(), f"scan {b}: foreground list differs"
+    engine.ingest_bev_only(pts[: offsets[1]], offsets[:2])
+    assert engine.scatter_deferred() == 0
+
+
 def test_views_keys_bci(engine, oracle):
     seeds, visits = [10, 10, 11, 12, 13, 13], [0, 1, 0, 0, 2, 3]
     pts, offsets = make_batch(seeds, visits, 120000)
