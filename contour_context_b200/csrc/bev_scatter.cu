@@ -414,13 +414,13 @@ bev_scatter_fast_kernel(const float *__restrict__ pts, const long long *__restri
 #pragma unroll
       for (int u = 0; u < K1_UNROLL; ++u) cur[u] = *(volatile const uint32_t *) (htile + ix[u]);
       uint32_t evm = 0u;  // bit u: point u goes to the log
+      // all atomics are issued before the first return value is looked at (cur[u] becomes the value the atomic found, or
+      // 'nothing to log' for a point that issued none); equal heights go to the atomic too: a tie is an event
 #pragma unroll
-      for (int u = 0; u < K1_UNROLL; ++u) {
-        if (oh[u] != 0u && oh[u] >= cur[u]) {  // equal heights go to the atomic too: a tie is an event
-          const uint32_t old = atomicMax(htile + ix[u], oh[u]);
-          if (oh[u] > thr_o && old <= oh[u]) evm |= 1u << u;
-        }
-      }
+      for (int u = 0; u < K1_UNROLL; ++u) cur[u] = (oh[u] != 0u && oh[u] >= cur[u]) ? atomicMax(htile + ix[u], oh[u]) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int u = 0; u < K1_UNROLL; ++u)
+        if (oh[u] > thr_o && cur[u] <= oh[u]) evm |= 1u << u;
       const int c = __popc(evm);
       if (__any_sync(FULLMASK, c != 0)) {
         int incl = c;

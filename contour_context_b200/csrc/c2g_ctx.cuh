@@ -13,7 +13,7 @@
 
 #define C2G_PHYS_BUCKETS (2 * C2G_NUM_BUCKETS)
 struct C2gLayerTable {   // device mirror of one LayerDB's KD-tree contents (host logic keeps the authoritative copy)
-  // Bucket k owns two fixed regions p = 2k, 2k + 1: [p * cap_b, (p + 1) * cap_b) of every per-key array and [p * blkcap_b, ..)
+  // Bucket k owns two fixed regions p = k, k + C2G_NUM_BUCKETS: [p * cap_b, (p + 1) * cap_b) of every per-key array and [p * blkcap_b, ..)
   // of the block arrays.  phys[k] is the one in use: a change in one bucket never moves the entries of another, appending to
   // a bucket never disturbs a kNN launch that reads its shorter prefix, and a REWRITE of a bucket (rebalancing move, kd
   // re-ordering) goes to the bucket's other region, so that launches still reading the previous version are not disturbed

@@ -1519,7 +1519,7 @@ int c2g_query_alloc(c2g_ctx *ctx) {
     C2G_CUDA_TRY(cudaMalloc((void **) &t.box_max, sizeof(float) * C2G_KEY_DIM * bcap));
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       t.bucket_cnt[k] = 0;
-      t.phys[k] = 2 * k;
+      t.phys[k] = k;
       t.m_n[k] = 0;
       t.m_rv[k] = 0;
       t.m_kd[k] = 0;
@@ -1629,7 +1629,8 @@ int patch_kind(const C2gLayerTable &t, int k, int n, unsigned rv, bool want_kd) 
 int patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out) {
   const int kind = patch_kind(t, k, n, rv, want_kd);
   if (kind == 0) return 0;
-  if (kind == 2) t.phys[k] ^= 1;  // a rewrite goes to the bucket's other region (launches reading the old one are not disturbed)
+  // a rewrite goes to the bucket's other region (launches reading the old one are not disturbed)
+  if (kind == 2) t.phys[k] = (t.phys[k] + C2G_NUM_BUCKETS) % C2G_PHYS_BUCKETS;
   const int base = t.phys[k] * t.cap_b, bbase = t.phys[k] * t.blkcap_b;
   const int from = kind == 1 ? t.m_n[k] : 0;  // append in tree order
   const bool kd = kind == 2 && want_kd && n > 32;
@@ -1642,7 +1643,7 @@ int patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned
     r.gidx = tree[tp].gidx;
     r.seq = tree[tp].seq;
     r.pos = base + p;
-    r.orank = base + tp;
+    r.orank = k * t.cap_b + tp;  // bucket-major tree order, whichever region holds the bucket
     out.recs.push_back(r);
   }
   for (int j = from / 32; j < (n + 31) / 32; ++j) {
