@@ -10,7 +10,7 @@ done
 ncu --set full --clock-control none --import-source on -k regex:"knn_kernel|prefilter_kernel|score_thread_kernel|finish_replay_kernel|finish_corr_kernel|refine_kernel" -s 18 -c 6 -f -o gpurun_out/${P}_query python scripts/quick_query_bench.py 5000 592 > gpurun_out/${P}_query.log 2>&1
 # launch list of the timed steps: this repo's kernels only (the synthetic-scan generator is torch), DB build skipped (5 000 scans in
 # batches: 2 launches each + mirror kernels)
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bev_scatter_kernel|contour_kernel|knn_kernel|prefilter_kernel|score_thread_kernel|finish_|refine_kernel|rank_kernel|mirror_" -c 400 --csv --log-file gpurun_out/${P}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${P}_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bev_scatter|contour_kernel|knn_kernel|prefilter_kernel|score_thread_kernel|finish_|refine_kernel|rank_kernel|mirror_" -c 600 --csv --log-file gpurun_out/${P}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${P}_launches.log 2>&1
 for f in ${P}_bev_scatter_fast_kernel ${P}_contour_kernel ${P}_query; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/${f}_raw.csv 2>/dev/null
   ncu -i gpurun_out/$f.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${f}_src.csv 2>/dev/null
