@@ -1626,11 +1626,13 @@ int patch_kind(const C2gLayerTable &t, int k, int n, unsigned rv, bool want_kd) 
   if (t.m_valid[k] && t.m_rv[k] == rv && n == t.m_n[k] && (t.m_kd[k] || !need_kd)) return 0;  // kd-ordered mirror of an unchanged tree
   return 2;
 }
-int patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out) {
+int patch_bucket(C2gLayerTable &t, int k, const C2gKeyRec *tree, int n, unsigned rv, bool want_kd, LayerPatch &out, bool flip = false) {
   const int kind = patch_kind(t, k, n, rv, want_kd);
   if (kind == 0) return 0;
-  // a rewrite goes to the bucket's other region (launches reading the old one are not disturbed)
-  if (kind == 2) t.phys[k] = (t.phys[k] + C2G_NUM_BUCKETS) % C2G_PHYS_BUCKETS;
+  // flip: a rewrite goes to the bucket's other region, so that a launch enqueued LATER that must still see the old version is not
+  // disturbed (the deferred patches of the windowed online loop); everywhere else patches and launches alternate in stream
+  // order and the rewrite happens in place
+  if (kind == 2 && flip) t.phys[k] = (t.phys[k] + C2G_NUM_BUCKETS) % C2G_PHYS_BUCKETS;
   const int base = t.phys[k] * t.cap_b, bbase = t.phys[k] * t.blkcap_b;
   const int from = kind == 1 ? t.m_n[k] : 0;  // append in tree order
   const bool kd = kind == 2 && want_kd && n > 32;
@@ -1760,7 +1762,7 @@ int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<D
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       const C2gBucket &bk = L.buckets[k];
       if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
-      if (patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp) == 2) rewritten[ll][k] = 1;
+      if (patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp, true) == 2) rewritten[ll][k] = 1;
     }
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
     if (lp.recs.empty() && lp.blks.empty()) continue;
