@@ -74,6 +74,12 @@ __device__ __forceinline__ const c2g_view &view_at(const c2g_scan_head *heads, c
 // kNN: one warp per query key. Lanes stride over the keys of the visited buckets; the running top-k is kept sorted
 // across the warp's registers (slot j lives in lane j % 32, register j / 32) and updated by warp-cooperative insertion.
 // ------------------------------------------------------------------------------------------------------------------
+// MODE 0: every bucket lives in its primary region and all query scans see the mirror as the launch parameters describe it (a
+//         batch against a static DB).  Its bucket addressing is kept in the textual form of rounds 1-2b on purpose: ptxas
+//         schedules the kernel 9 % slower (1.10 -> 1.20 ms per 1 184 queries, identical instruction count) as soon as the bucket
+//         size is held in a local or the region goes through T.phys;
+// MODE 1: same, but buckets may live in their second region; MODE 2: every query scan has its own KnnVersion (online loop).
+template <int MODE>
 __global__ void __launch_bounds__(QK_WARPS * 32)
 knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int B, QueryParams Q, const KnnVersion *__restrict__ ver,
            c2g_hint *__restrict__ hints, unsigned long long *__restrict__ work) {
@@ -114,14 +120,20 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
                           fmaxf((key[2] - b20) * (key[2] - b20), (key[2] - b21) * (key[2] - b21));
     const LayerDev &T = Q.layer[ll];
     // the state of the trees this query scan sees: the launch parameters, or the scan's own entry of the version table
-    const KnnVersion *V = ver ? ver + ((size_t) (q - q0) * Q.n_q_levels + ll) : nullptr;
+    const KnnVersion *V = MODE == 2 ? ver + ((size_t) (q - q0) * Q.n_q_levels + ll) : nullptr;
     int mid = 0;
-    for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
-      const float r0 = V ? V->ranges[i] : T.ranges[i], r1 = V ? V->ranges[i + 1] : T.ranges[i + 1];
-      if (r0 <= key[0] && r1 > key[0]) {
-        mid = i;
-        break;
-      }
+    if (MODE == 2) {
+      for (int i = 0; i < C2G_NUM_BUCKETS; ++i)
+        if (V->ranges[i] <= key[0] && V->ranges[i + 1] > key[0]) {
+          mid = i;
+          break;
+        }
+    } else {
+      for (int i = 0; i < C2G_NUM_BUCKETS; ++i)
+        if (T.ranges[i] <= key[0] && T.ranges[i + 1] > key[0]) {
+          mid = i;
+          break;
+        }
     }
     // visited set of layerKNNSearch's else-if chain: {mid, mid-1, .., 0} and {mid+i : i > mid, mid+i < 6}
     unsigned visit = 0;
@@ -232,10 +244,17 @@ knn_kernel(const c2g_scan_head *__restrict__ heads, int first_slot, int q0, int 
     };
     for (int bk = 0; bk < C2G_NUM_BUCKETS; ++bk) {
       if (!((visit >> bk) & 1u)) continue;
-      const int pb = V ? V->phys[bk] : T.phys[bk], cntb = V ? V->bucket_cnt[bk] : T.bucket_cnt[bk];
-      const int beg = pb * T.cap_b, end = beg + cntb;
-      if (beg >= end) continue;
-      const int b0 = pb * T.blkcap_b, nb = (cntb + 31) >> 5;
+      int beg, end, b0, nb;
+      if (MODE == 0) {
+        beg = bk * T.cap_b, end = beg + T.bucket_cnt[bk];
+        if (beg >= end) continue;
+        b0 = bk * T.blkcap_b, nb = (T.bucket_cnt[bk] + 31) >> 5;
+      } else {
+        const int pb = MODE == 2 ? V->phys[bk] : T.phys[bk], cntb = MODE == 2 ? V->bucket_cnt[bk] : T.bucket_cnt[bk];
+        beg = pb * T.cap_b, end = beg + cntb;
+        if (beg >= end) continue;
+        b0 = pb * T.blkcap_b, nb = (cntb + 31) >> 5;
+      }
       n_boxes += nb + (nb > KNN_BOX_CACHE ? nb - KNN_BOX_CACHE : 0);
       // pass 1: the block nearest to the query seeds the top-k, so that the sweep below starts with a tight bound
       float best = 3.0e38f;
@@ -1846,8 +1865,17 @@ static bool thresholds_ok(const c2g_score_ensemble *lb, const c2g_score_ensemble
 static int launch_knn(c2g_ctx *ctx, int first_slot, int q0, int Bs, const QueryParams &Q, cudaStream_t st, const KnnVersion *ver = nullptr) {
   const int n_keys = Bs * Q.n_q_levels * C2G_MAX_PIV;
   if (n_keys <= 0) return 0;
-  knn_kernel<<<(n_keys + QK_WARPS - 1) / QK_WARPS, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ver, ctx->d_hints,
-                                                                          ctx->count_work ? ctx->d_work : nullptr);
+  const unsigned grid = (unsigned) ((n_keys + QK_WARPS - 1) / QK_WARPS);
+  unsigned long long *work = ctx->count_work ? ctx->d_work : nullptr;
+  bool primary = true;  // every bucket in its primary region (always, unless the windowed online loop rewrote a bucket)
+  for (int ll = 0; ll < Q.n_q_levels; ++ll)
+    for (int k = 0; k < C2G_NUM_BUCKETS; ++k) primary = primary && Q.layer[ll].phys[k] == k;
+  if (ver)
+    knn_kernel<2><<<grid, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ver, ctx->d_hints, work);
+  else if (primary)
+    knn_kernel<0><<<grid, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ver, ctx->d_hints, work);
+  else
+    knn_kernel<1><<<grid, QK_WARPS * 32, 0, st>>>(ctx->d_heads, first_slot, q0, Bs, Q, ver, ctx->d_hints, work);
   C2G_CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
   return 0;
