@@ -722,6 +722,12 @@ int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int
   }
   return 0;
 }
+int c2g_hostdb_indexed(void *h, int ll, int *indexed) {
+  if (!h || !indexed) return C2G_ERR_ARG;
+  const C2gLayerHost &L = ((C2gHostDB *) h)->layers[ll];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) indexed[i] = (int) L.buckets[i].indexed;
+  return 0;
+}
 int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq) {
   if (!h) return C2G_ERR_ARG;
   const std::vector<C2gKeyRec> &t = ((C2gHostDB *) h)->layers[ll].buckets[bucket].tree;

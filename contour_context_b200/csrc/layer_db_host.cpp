@@ -28,6 +28,7 @@ void pop_buffer_max(C2gBucket &b, double curr_ts, double min_elapse, bool &chang
   changed = true;
   for (size_t i = 0; i < gap; ++i) b.tree.push_back(b.buffer[i].key);
   b.buffer.erase(b.buffer.begin(), b.buffer.begin() + (long) gap);
+  b.indexed = b.tree.size();  // rebuildTree()
 }
 
 // Moves `num` keys out of `from` (the larger tree) into `to`. `perm` is the reference's sort permutation of `from`
@@ -148,7 +149,8 @@ void rebuild_layer(C2gLayerHost &L, int idx_t1, double curr_ts, double max_elaps
   }
   move_tail(big, lit, perm, num_to_move, split_val, donor_is_lower);  // `big` is permuted and cut, `lit` only grows
   big.restructured++;
-  changed = true;
+  big.indexed = big.tree.size();  // (the reference's index of the donor is undefined from here until its next pop)
+  changed = true;                 // `lit` keeps its index: the keys it received are searchable after its next pop
   move_buffer(big, lit, split_val, donor_is_lower);
   tr1.end = tr2.beg = split_val;
   L.ranges[idx_t1 + 1] = split_val;
@@ -170,6 +172,7 @@ void c2g_hostdb_init(C2gHostDB &db, int n_layers, double max_elapse, double min_
     C2gLayerHost &L = db.layers[l];
     for (int i = 0; i < C2G_NUM_BUCKETS; ++i) {
       L.buckets[i].tree.clear();
+      L.buckets[i].indexed = 0;
       L.buckets[i].restructured++;
       L.buckets[i].buffer.clear();
       L.buckets[i].beg = L.buckets[i].end = kMaxBucketVal;

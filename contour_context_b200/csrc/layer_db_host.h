@@ -26,6 +26,13 @@ struct C2gBufRec {
 struct C2gBucket {
   float beg, end;
   std::vector<C2gKeyRec> tree;    // data_tree_ + gkidx_tree_
+  // The first `indexed` entries of `tree` are searchable: the reference searches a bucket through a KD index that it rebuilds
+  // only when the bucket pops something from its buffer (TreeBucket::popBufferMax -> rebuildTree, contour_db.h:119-143).  A
+  // bucket that RECEIVES keys in a rebalancing move (they are appended to its tree) without popping anything keeps its old
+  // index: the moved keys are not found until its next pop (and a bucket that never popped has no index at all).  A bucket
+  // that GIVES keys away without popping is left with an index into a permuted, shortened vector - undefined behaviour in
+  // the reference; here all of its remaining keys stay searchable.
+  size_t indexed = 0;
   std::vector<C2gBufRec> buffer;  // buffer_
   // bumped whenever existing tree entries move or disappear; between two bumps the tree only grows at its end, which is
   // what lets the device mirror (query.cu) be patched instead of rebuilt

@@ -1766,7 +1766,7 @@ bool patches_rewrite_again(c2g_ctx *ctx, const unsigned char (*rewritten)[C2G_NU
   for (int ll = 0; ll < ctx->db.n_q_levels; ++ll)
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       const C2gBucket &bk = ctx->hostdb->layers[ll].buckets[k];
-      if (rewritten[ll][k] && patch_kind(ctx->layers[ll], k, (int) bk.tree.size(), bk.restructured, false) == 2) return true;
+      if (rewritten[ll][k] && patch_kind(ctx->layers[ll], k, (int) bk.indexed, bk.restructured, false) == 2) return true;
     }
   return false;
 }
@@ -1781,7 +1781,7 @@ int collect_mirror_patches(c2g_ctx *ctx, std::vector<char> &block, std::vector<D
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       const C2gBucket &bk = L.buckets[k];
       if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
-      if (patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, false, lp, true) == 2) rewritten[ll][k] = 1;
+      if (patch_bucket(t, k, bk.tree.data(), (int) bk.indexed, bk.restructured, false, lp, true) == 2) rewritten[ll][k] = 1;  // the searchable prefix
     }
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
     if (lp.recs.empty() && lp.blks.empty()) continue;
@@ -1810,7 +1810,7 @@ int c2g_db_sync_mode(c2g_ctx *ctx, int want_kd) {
     for (int k = 0; k < C2G_NUM_BUCKETS; ++k) {
       const C2gBucket &bk = L.buckets[k];
       if ((int) bk.tree.size() > t.cap_b) return C2G_ERR_CAPACITY;
-      patch_bucket(t, k, bk.tree.data(), (int) bk.tree.size(), bk.restructured, want_kd != 0, lp);
+      patch_bucket(t, k, bk.tree.data(), (int) bk.indexed, bk.restructured, want_kd != 0, lp);  // the searchable prefix (C2gBucket::indexed)
     }
     for (int k = 0; k <= C2G_NUM_BUCKETS; ++k) t.ranges[k] = L.ranges[k];
     int rc = apply_patch(ctx, t, lp);

@@ -173,6 +173,8 @@ int c2g_hostdb_push_key(void *h, int ll, const float *key, double ts, int gidx, 
 int c2g_hostdb_balance(void *h, int seed, double ts);
 int c2g_hostdb_state(void *h, int ll, float *bucket_ranges, int *tree_sizes, int *buffer_sizes);
 int c2g_hostdb_tree(void *h, int ll, int bucket, float *keys, int *gidx, int *seq);
+/* searchable prefix of every bucket's tree (what the reference's KD index covers: rebuilt only when the bucket pops its buffer) */
+int c2g_hostdb_indexed(void *h, int ll, int *indexed /* [6] */);
 /* per bucket: how often existing tree entries were moved or removed (LayerDB::rebuild's balancing move); while the counter
  * stands still a tree only grows at its END, which is what lets c2g_db_sync patch the device mirror instead of rebuilding it */
 int c2g_hostdb_versions(void *h, int ll, unsigned int *restructured /* [6] */);

@@ -77,6 +77,7 @@ def lib():
         L.c2o_db_add_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.c2o_db_push_and_balance.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.c2o_db_n_scans.argtypes = [C.c_void_p]
+        L.c2o_db_rebalance_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.c2o_db_layer_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.c2o_db_bucket_tree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.c2o_db_query.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(D.ScoreEnsemble), C.POINTER(D.ScoreEnsemble),
@@ -214,6 +215,13 @@ class DB:
 
     def n_scans(self):
         return lib().c2o_db_n_scans(self.h)
+
+    def rebalance_stats(self):
+        """(rebalancing moves so far, buckets a literal reference would have searched through a stale index afterwards, how many of
+        those were the bucket that gave keys away)."""
+        m, s, d = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        lib().c2o_db_rebalance_stats(self.h, C.byref(m), C.byref(s), C.byref(d))
+        return int(m.value), int(s.value), int(d.value)
 
     def layer_state(self, ll: int):
         rng = np.zeros(D.NUM_BUCKETS + 1, np.float32)

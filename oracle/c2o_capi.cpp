@@ -89,6 +89,21 @@ void c2o_db_free(void *db) { delete (ContourDB *) db; }
 void c2o_db_add_scan(void *db, void *scan, double ts) { ((ContourDB *) db)->addScan(*(ScanPtr *) scan, ts); }
 void c2o_db_push_and_balance(void *db, int seed, double ts) { ((ContourDB *) db)->pushAndBalance(seed, ts); }
 int c2o_db_n_scans(void *db) { return (int) ((ContourDB *) db)->all_bevs_.size(); }
+// rebalancing moves so far / buckets a literal reference would have searched through a stale index afterwards (all layers)
+void c2o_db_rebalance_stats(void *db, long long *moves, long long *stale, long long *stale_donor) {
+  *moves = *stale = *stale_donor = 0;
+  for (const LayerDB &L : ((ContourDB *) db)->layer_db_) {
+    *moves += L.n_moves_;
+    *stale += L.n_stale_;
+    *stale_donor += L.n_stale_donor_;
+  }
+}
+
+// searchable prefix of every bucket of layer ll: 0 without an index, else the size the index was built over
+void c2o_db_indexed(void *db, int ll, int32_t *indexed) {
+  const LayerDB &l = ((ContourDB *) db)->layer_db_[ll];
+  for (int i = 0; i < C2G_NUM_BUCKETS; ++i) indexed[i] = l.buckets_[i].has_tree ? (int32_t) l.buckets_[i].indexed_size : 0;
+}
 
 // layer state for mirroring / parity: bucket_ranges[7], tree_sizes[6], buffer_sizes[6]
 void c2o_db_layer_state(void *db, int ll, float *bucket_ranges, int32_t *tree_sizes, int32_t *buffer_sizes) {

@@ -534,6 +534,9 @@ struct LayerDB {
   static const int bucket_chann_ = 0;
   std::vector<TreeBucket> buckets_;
   std::vector<float> bucket_ranges_;
+  // how often the literal reference would have been left with a stale index (see the end of rebuild): rebalancing moves so far,
+  // and buckets whose data a move changed while their own popBufferMax popped nothing
+  long long n_moves_ = 0, n_stale_ = 0, n_stale_donor_ = 0;  // n_stale_donor_: ... of which the bucket that GAVE keys (its tree was permuted and cut)
 
   explicit LayerDB(double max_elapse, double min_elapse) {
     bucket_ranges_.resize(max_num_backets_ + 1);
@@ -774,14 +777,21 @@ inline void LayerDB::rebuild(int idx_t1, double curr_ts) {
   }
   std::sort(tr1.buffer.begin(), tr1.buffer.end(), [](const auto &a, const auto &b) { return a.ts < b.ts; });
   std::sort(tr2.buffer.begin(), tr2.buffer.end(), [](const auto &a, const auto &b) { return a.ts < b.ts; });
-  // NOTE: rebalancing changed data_tree of both buckets; the reference rebuilds the index only inside popBufferMax
-  // (when something is popped). A bucket whose data moved but popped nothing keeps a stale index in the reference
-  // (nanoflann indexes the vector by reference, sizes mismatch) — we rebuild both, which is what a run that does not
-  // crash observes.
+  // NOTE: rebalancing changed data_tree of both buckets; the reference rebuilds the index only inside popBufferMax (when
+  // something is popped).  The RECEIVER's tree only grew at its end: a stale index over its first indexed_size points is
+  // well defined (nanoflann reads the vector through a reference) and is kept - the moved keys become searchable at the
+  // bucket's next pop, exactly as in the reference.  The DONOR's tree was permuted and cut: a stale index addresses points
+  // beyond its end (undefined behaviour in the reference); it is rebuilt here, which is what a run that does not crash
+  // observes (n_stale_donor_ counts how often).
   tr1.popBufferMax(curr_ts);
   tr2.popBufferMax(curr_ts);
-  tr1.rebuildTree();
-  tr2.rebuildTree();
+  n_moves_++;
+  n_stale_ += (tr1.indexed_size != tr1.data_tree.size()) + (tr2.indexed_size != tr2.data_tree.size());
+  TreeBucket &donor = sz1 > sz2 ? tr1 : tr2;
+  if (donor.indexed_size != donor.data_tree.size() || !donor.has_tree) {
+    n_stale_donor_++;
+    donor.rebuildTree();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -186,8 +186,32 @@ def refine_study(n_scenes=60, corr_thres=0.65):
     }
 
 
+def layerdb_study(n_scans=4071, n_pts=120000, ts_step=0.104, visits=4):
+    """How often the deliberate LayerDB deviation can matter: the reference rebuilds a bucket's KD index only when
+    the bucket pops something from its buffer (contour_db.h:119-143); a bucket whose tree a rebalancing move changed
+    (contour_db.cpp:63-317) without popping anything is searched through a stale index until its next pop.  Counts, over the
+    KITTI-08-shaped sequence of bench.py (same trajectory, same timestamps), the rebalancing moves and the buckets left in
+    that state."""
+    cfg, dbc = D.kitti_cm_config(), D.kitti_db_config()
+    db = c2o.DB(dbc)
+    n_scenes = (n_scans + visits - 1) // visits
+    for i0 in range(0, n_scans, 8):
+        m = min(8, n_scans - i0)
+        seeds = [(i0 + k) % n_scenes for k in range(m)]
+        vis = [(i0 + k) // n_scenes for k in range(m)]
+        pts = synth.make_scans(seeds, vis, n_pts, "cpu", i0).numpy()
+        for k in range(m):
+            sc = c2o.Scan(cfg, i0 + k).ingest(np.ascontiguousarray(pts[k]))
+            db.add_scan(sc, ts_step * (i0 + k))
+            db.push_and_balance(i0 + k, ts_step * (i0 + k))
+    moves, stale, donors = db.rebalance_stats()
+    return {"scans": int(n_scans), "ts_step_s": ts_step, "rebalancing_moves": moves, "buckets_left_with_a_stale_index_in_the_reference": stale,
+            "of_which_donor_buckets_undefined_behaviour": donors, "of_which_receiver_buckets_moved_keys_not_yet_searchable": stale - donors}
+
+
 if __name__ == "__main__":
     import json
 
     print(json.dumps({"eig": eig_study()}, indent=1))
     print(json.dumps({"refine": refine_study()}, indent=1))
+    print(json.dumps({"layerdb": layerdb_study()}, indent=1))

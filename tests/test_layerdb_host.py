@@ -21,20 +21,27 @@ def _state_prod(lib, h, ll):
     return rng, ts, bs
 
 
-@pytest.mark.parametrize("mode", ["continuous", "quantised", "bursty"])
+@pytest.mark.parametrize("mode", ["continuous", "quantised", "bursty", "sparse"])
 def test_rebalance_matches_oracle(built_lib, oracle, mode):
-    rng = np.random.default_rng({"continuous": 1, "quantised": 2, "bursty": 3}[mode])
+    rng = np.random.default_rng({"continuous": 1, "quantised": 2, "bursty": 3, "sparse": 4}[mode])
     cfg = D.kitti_db_config()
     odb = oracle.DB(cfg)
     olib = oracle.lib()
     olib.c2o_test_push_key.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int]
     h = built_lib.c2g_hostdb_create(cfg.n_q_levels, cfg.max_elapse, cfg.min_elapse)
     n_scans = 1500
+    lagging = False  # some bucket held keys its index did not cover yet (received in a move, nothing popped since)
+    olib.c2o_db_indexed.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    built_lib.c2g_hostdb_indexed.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     for i in range(n_scans):
         ts = 0.104 * i if mode != "bursty" else 0.104 * i + (30.0 if (i // 200) % 2 else 0.0)
+        if mode == "sparse":
+            ts = 2.0 * i  # scans far apart: buffers drain completely, so a bucket can receive moved keys with nothing to pop
         for ll in range(cfg.n_q_levels):
             for seq in range(6):
                 key = (rng.random(10) * 30 + 1).astype(np.float32)
+                if mode == "sparse":
+                    key[0] = np.float32(1.0 + 0.03 * i + 6.0 * rng.random())  # a drifting, narrow band of bucket values
                 if mode == "quantised":
                     key[0] = np.float32(np.round(key[0] / 2.0) * 2.0)  # long strips of equal bucket values
                 if rng.random() < 0.05:
@@ -43,12 +50,18 @@ def test_rebalance_matches_oracle(built_lib, oracle, mode):
                 assert built_lib.c2g_hostdb_push_key(h, ll, _p(key), ts, i, seq) == 0
         odb.push_and_balance(i, ts)
         assert built_lib.c2g_hostdb_balance(h, i, ts) == 0
-        if i % 97 == 0 or i == n_scans - 1:
+        if i % 7 == 0 or i == n_scans - 1 or mode == "sparse":
             for ll in range(cfg.n_q_levels):
                 o_rng, o_ts, o_bs = odb.layer_state(ll)
                 p_rng, p_ts, p_bs = _state_prod(built_lib, h, ll)
                 assert o_rng.tobytes() == p_rng.tobytes(), (mode, i, ll)
                 assert np.array_equal(o_ts, p_ts) and np.array_equal(o_bs, p_bs), (mode, i, ll, o_ts, p_ts)
+                # the searchable prefix (what the reference's KD index covers) of every bucket
+                o_ix, p_ix = np.zeros(6, np.int32), np.zeros(6, np.int32)
+                olib.c2o_db_indexed(odb.h, ll, _p(o_ix))
+                assert built_lib.c2g_hostdb_indexed(h, ll, _p(p_ix)) == 0
+                assert np.array_equal(o_ix, p_ix), (mode, i, ll, o_ix, p_ix)
+                lagging |= bool((p_ix < p_ts).any())
     # final: every tree identical in content and order
     split_seen = False
     for ll in range(cfg.n_q_levels):
@@ -63,6 +76,8 @@ def test_rebalance_matches_oracle(built_lib, oracle, mode):
                 assert built_lib.c2g_hostdb_tree(h, ll, b, _p(pk), _p(pg), _p(ps)) == 0
             assert ok.tobytes() == pk.tobytes() and np.array_equal(og, pg) and np.array_equal(osq, ps), (mode, ll, b)
     assert split_seen, "the test never exercised a bucket split"
+    if mode == "sparse":
+        assert lagging, "no bucket ever held received keys that its index did not cover yet: the case is not exercised"
     built_lib.c2g_hostdb_free(h)
 
 
