@@ -680,7 +680,7 @@ __device__ RfOut rf_minimize(const Prob &P, const double x0[3]) {
   return R;
 }
 
-__global__ void __launch_bounds__(RF_MAX_WARPS * 32, 5)
+__global__ void __launch_bounds__(RF_MAX_WARPS * 32, 6)
 refine_kernel(const c2g_scan_head *__restrict__ heads, const c2g_ell *__restrict__ ells, int first_slot, int q0, int B, int max_fine_opt,
               int exp_mode, uint32_t *__restrict__ pair_scratch, int pair_cap, c2g_query_result *__restrict__ results,
               unsigned long long *__restrict__ work) {
