@@ -84,3 +84,77 @@ def test_knn_matches_reference_nanoflann(oracle):
                     uniq = np.concatenate([[True], np.diff(dist) != 0]) & np.concatenate([np.diff(dist) != 0, [True]])
                     assert np.array_equal(gidx[uniq], ridx[valid][uniq])
         R.ref_knn_free(tree)
+
+
+def test_stale_index_of_a_receiving_bucket_with_the_reference_nanoflann(oracle):
+    """after a rebalancing move a bucket that received keys but popped nothing is searched through its old KD index.
+    With the reference's own nanoflann (oracle/_ref/liboracle_nf.so) that index is a real object built over the old size; the
+    restatement (liboracle.so, exhaustive) searches the first indexed_size points.  Both are driven through a stream in which
+    the case occurs and must return the same neighbours for every query, every scan."""
+    import os
+
+    from contour_context_b200 import ctypes_defs as D
+
+    here = os.path.dirname(os.path.abspath(oracle.__file__))
+    p_nf, p_ex = os.path.join(here, "_ref", "liboracle_nf.so"), os.path.join(here, "liboracle.so")
+    if not os.path.exists(p_nf):
+        pytest.skip("oracle/_ref/liboracle_nf.so not built (reference tree absent and no prebuilt copy)")
+    oracle.build()
+    libs = []
+    for p in (p_ex, p_nf):
+        L = C.CDLL(p)
+        L.c2o_db_create.restype = C.c_void_p
+        L.c2o_db_create.argtypes = [C.POINTER(D.DbConfig)]
+        L.c2o_db_free.argtypes = [C.c_void_p]
+        L.c2o_test_push_key.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_int]
+        L.c2o_db_push_and_balance.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.c2o_db_indexed.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.c2o_db_layer_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.c2o_db_layer_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.c2o_uses_nanoflann.restype = C.c_int
+        libs.append(L)
+    assert libs[0].c2o_uses_nanoflann() == 0 and libs[1].c2o_uses_nanoflann() == 1
+    cfg = D.kitti_db_config()
+    dbs = [L.c2o_db_create(C.byref(cfg)) for L in libs]
+    rng = np.random.default_rng(4)
+    lag_scans = compared = 0
+    k = 50
+    for i in range(700):
+        ts = 2.0 * i
+        for ll in range(cfg.n_q_levels):
+            for seq in range(6):
+                key = (rng.random(10) * 30 + 1).astype(np.float32)
+                key[0] = np.float32(1.0 + 0.03 * i + 6.0 * rng.random())
+                for L, db in zip(libs, dbs):
+                    L.c2o_test_push_key(db, ll, _p(key), ts, i, seq)
+        for L, db in zip(libs, dbs):
+            L.c2o_db_push_and_balance(db, i, ts)
+        lag = False
+        for ll in range(cfg.n_q_levels):
+            ix, rngs, tsz, bsz = np.zeros(6, np.int32), np.zeros(7, np.float32), np.zeros(6, np.int32), np.zeros(6, np.int32)
+            libs[1].c2o_db_indexed(dbs[1], ll, _p(ix))
+            libs[1].c2o_db_layer_state(dbs[1], ll, _p(rngs), _p(tsz), _p(bsz))
+            lag |= bool((ix < tsz).any())
+        if not (lag or i % 50 == 0):
+            continue
+        lag_scans += int(lag)
+        for ll in range(cfg.n_q_levels):
+            for _ in range(6):
+                q = (rng.random(10) * 30 + 1).astype(np.float32)
+                q[0] = np.float32(1.0 + 0.03 * i + 6.0 * rng.random())
+                out = []
+                for L, db in zip(libs, dbs):
+                    g, s, d = np.zeros(k, np.int32), np.zeros(k, np.int32), np.zeros(k, np.float32)
+                    n = L.c2o_db_layer_knn(db, ll, _p(q), k, C.c_float(1.0e6), _p(g), _p(s), _p(d))
+                    out.append((n, g[:n].copy(), s[:n].copy(), d[:n].copy()))
+                assert out[0][0] == out[1][0], (i, ll)
+                assert out[0][3].tobytes() == out[1][3].tobytes(), (i, ll)
+                # equal distances may come back in either order: compare the (dist, gidx, seq) multisets
+                a = sorted(zip(out[0][3].tolist(), out[0][1].tolist(), out[0][2].tolist()))
+                b = sorted(zip(out[1][3].tolist(), out[1][1].tolist(), out[1][2].tolist()))
+                assert a == b, (i, ll)
+                compared += 1
+    for L, db in zip(libs, dbs):
+        L.c2o_db_free(db)
+    assert lag_scans >= 1, "no bucket ever lagged behind its tree: the case is not exercised"
+    assert compared > 100
